@@ -1,0 +1,510 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement ("port") of the pinnrl hot path.
+
+This file restates, with plain torch autograd-of-autograd, what the reference
+computes for the path named by BASELINE.json: network forward, nested
+``autograd.grad`` derivative bookkeeping, the five PDE residuals and the loss
+assembly.  It is the *checker* for the CUDA path and the CPU baseline that
+``bench.py`` times; nothing in the product package may import it.
+
+Parity status: PINNED against the reference itself.  ``tests/golden/make_golden.py``
+(run in the build container, where ``/root/reference`` exists) executes the
+unmodified reference and this port on identical weights and points and asserts
+bit-equality before it writes the fixtures under ``tests/golden/``; the
+``-m "not gpu"`` suite re-checks this port against those committed fixtures.
+The reference's own tests pin no residual/gradient values.
+
+Reference files restated (paths relative to /root/reference):
+  pinnrl/neural_networks/feedforward.py:41-73      -> FeedForwardNetwork
+  pinnrl/neural_networks/resnet.py:45-65,113-142   -> ResNetBlock / ResNet
+  pinnrl/neural_networks/siren.py:28-46,69-90      -> SIRENLayer / SIREN
+  pinnrl/neural_networks/fourier.py:12-16,45,96-124-> FourierFeatures / FourierNetwork
+  pinnrl/neural_networks/__init__.py:69-154        -> PINNModel (wrapper with ``.model``)
+  pinnrl/pdes/pde_base.py:590-794                  -> compute_derivatives
+  pinnrl/pdes/pde_base.py:309-326                  -> apply_loss_fn
+  pinnrl/pdes/pde_base.py:1086-1235                -> base_compute_loss
+  pinnrl/pdes/heat_equation.py:54-110,375-623      -> heat residual / heat_compute_loss
+  pinnrl/pdes/burgers_equation.py:40-75            -> burgers residual
+  pinnrl/pdes/kdv_equation.py:38-92                -> kdv residual
+  pinnrl/pdes/allen_cahn.py:39-111                 -> allen-cahn residual
+  pinnrl/pdes/cahn_hilliard.py:39-160              -> cahn-hilliard residual
+"""
+
+from __future__ import annotations
+
+import math
+from typing import Callable, Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+
+# --------------------------------------------------------------------------
+# Networks.  Module/attribute names are chosen so that ``state_dict()`` keys
+# equal the reference's; construction order of the
+# ``nn.Linear`` modules equals the reference's so a shared seed gives equal
+# weights.
+# --------------------------------------------------------------------------
+
+def _act(name: str) -> nn.Module:
+    table = {"tanh": nn.Tanh, "relu": nn.ReLU, "sigmoid": nn.Sigmoid,
+             "gelu": nn.GELU, "leaky_relu": nn.LeakyReLU}
+    if name not in table:
+        raise ValueError(f"Unsupported activation: {name}")
+    return table[name]()
+
+
+class FeedForwardNetwork(nn.Module):
+    """[Linear, (LayerNorm), act, (Dropout)] x L + Linear  (feedforward.py:41-54)."""
+
+    def __init__(self, input_dim, hidden_dims, output_dim, activation="tanh",
+                 dropout=0.0, layer_norm=False):
+        super().__init__()
+        mods: List[nn.Module] = []
+        prev = input_dim
+        for h in hidden_dims:
+            mods.append(nn.Linear(prev, h))
+            if layer_norm:
+                mods.append(nn.LayerNorm(h))
+            mods.append(_act(activation))
+            if dropout > 0.0:
+                mods.append(nn.Dropout(dropout))
+            prev = h
+        mods.append(nn.Linear(prev, output_dim))
+        self.layers = nn.Sequential(*mods)
+
+    def forward(self, x):
+        return self.layers(x)
+
+
+class ResNetBlock(nn.Module):
+    """act(x + [Linear, LN, act, Drop, Linear, LN, Drop](x))  (resnet.py:45-65)."""
+
+    def __init__(self, dim, hidden, activation="tanh", dropout=0.0, layernorm_cls=nn.LayerNorm):
+        super().__init__()
+        self.activation_fn = _act(activation)
+        self.layers = nn.Sequential(
+            nn.Linear(dim, hidden), layernorm_cls(hidden), self.activation_fn, nn.Dropout(dropout),
+            nn.Linear(hidden, dim), layernorm_cls(dim), nn.Dropout(dropout),
+        )
+
+    def forward(self, x):
+        return self.activation_fn(x + self.layers(x))
+
+
+class PrimitiveLayerNorm(nn.Module):
+    """LayerNorm from primitive ops: same forward as
+    ``nn.LayerNorm`` but with exact higher-order autograd."""
+
+    def __init__(self, dim, eps=1e-5):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+        self.bias = nn.Parameter(torch.zeros(dim))
+        self.eps = eps
+
+    def forward(self, z):
+        c = z - z.mean(dim=-1, keepdim=True)
+        v = (c * c).mean(dim=-1, keepdim=True)
+        return self.weight * c / torch.sqrt(v + self.eps) + self.bias
+
+
+class ResNet(nn.Module):
+    """act(Linear) -> blocks -> Linear  (resnet.py:113-142)."""
+
+    def __init__(self, input_dim, hidden_dim, num_blocks, output_dim, activation="tanh",
+                 dropout=0.0, corrected_layernorm=False):
+        super().__init__()
+        ln = PrimitiveLayerNorm if corrected_layernorm else nn.LayerNorm
+        self.activation_fn = _act(activation)
+        self.input_layer = nn.Linear(input_dim, hidden_dim)
+        self.blocks = nn.ModuleList(
+            [ResNetBlock(hidden_dim, hidden_dim, activation, dropout, ln) for _ in range(num_blocks)])
+        self.output_layer = nn.Linear(hidden_dim, output_dim)
+
+    def forward(self, x):
+        x = self.activation_fn(self.input_layer(x))
+        for b in self.blocks:
+            x = b(x)
+        return self.output_layer(x)
+
+
+class SIRENLayer(nn.Module):
+    """sin(omega_0 * Linear(x)) with U(+-sqrt(6/in)/omega_0) weights (siren.py:28-46)."""
+
+    def __init__(self, fin, fout, omega_0=30.0):
+        super().__init__()
+        self.omega_0 = omega_0
+        self.linear = nn.Linear(fin, fout)
+        with torch.no_grad():
+            bound = math.sqrt(6 / fin) / omega_0
+            self.linear.weight.uniform_(-bound, bound)
+
+    def forward(self, x):
+        return torch.sin(self.omega_0 * self.linear(x))
+
+
+class SIREN(nn.Module):
+    def __init__(self, input_dim, hidden_dims, output_dim, omega_0=30.0):
+        super().__init__()
+        self.omega_0 = omega_0
+        self.layers = nn.ModuleList()
+        prev = input_dim
+        for h in hidden_dims:
+            self.layers.append(SIRENLayer(prev, h, omega_0))
+            prev = h
+        self.layers.append(nn.Linear(prev, output_dim))
+
+    def forward(self, x):
+        for l in self.layers[:-1]:
+            x = l(x)
+        return self.layers[-1](x)
+
+
+class FourierFeatures(nn.Module):
+    """[sin(xB), cos(xB)], B ~ N(0, scale^2) buffer (fourier.py:12-16,45)."""
+
+    def __init__(self, input_dim, mapping_size, scale=10.0):
+        super().__init__()
+        self.register_buffer("B", torch.randn(input_dim, mapping_size) * scale)
+
+    def forward(self, x):
+        p = x @ self.B
+        return torch.cat([torch.sin(p), torch.cos(p)], dim=-1)
+
+
+class FourierNetwork(nn.Module):
+    """Fourier features -> act(Linear) x (L-1) -> Linear (fourier.py:96-124)."""
+
+    def __init__(self, input_dim, hidden_dim, num_layers, output_dim, activation="tanh",
+                 mapping_size=32, scale=10.0):
+        super().__init__()
+        self.activation_fn = _act(activation)
+        self.fourier = FourierFeatures(input_dim, mapping_size, scale)
+        self.layers = nn.ModuleList()
+        prev = 2 * mapping_size
+        for _ in range(num_layers - 1):
+            self.layers.append(nn.Linear(prev, hidden_dim))
+            prev = hidden_dim
+        self.layers.append(nn.Linear(prev, output_dim))
+
+    def forward(self, x):
+        x = self.fourier(x)
+        for l in self.layers[:-1]:
+            x = self.activation_fn(l(x))
+        return self.layers[-1](x)
+
+
+class PINNModel(nn.Module):
+    """Wrapper exposing ``.model`` like the reference factory (__init__.py:69-154)."""
+
+    def __init__(self, architecture, input_dim, hidden_dim, num_layers, output_dim=1,
+                 activation="tanh", omega_0=30.0, mapping_size=32, scale=10.0,
+                 corrected_layernorm=False):
+        super().__init__()
+        self.architecture = architecture
+        if architecture == "fourier":
+            self.model = FourierNetwork(input_dim, hidden_dim, num_layers, output_dim,
+                                        activation, mapping_size, scale)
+        elif architecture == "resnet":
+            self.model = ResNet(input_dim, hidden_dim, num_layers, output_dim, activation,
+                                0.0, corrected_layernorm)
+        elif architecture == "siren":
+            self.model = SIREN(input_dim, [hidden_dim] * num_layers, output_dim, omega_0)
+        elif architecture == "feedforward":
+            self.model = FeedForwardNetwork(input_dim, [hidden_dim] * num_layers, output_dim,
+                                            activation, 0.0, False)
+        else:
+            raise ValueError(f"architecture {architecture!r} is outside the hot path")
+
+    def forward(self, x):
+        return self.model(x)
+
+
+# --------------------------------------------------------------------------
+# Derivative bookkeeping (pde_base.py:590-794), including the quirk that each
+# *listed* spatial order costs exactly one more autograd.grad starting from u
+#  and that multi-dim code differentiates w.r.t. a fresh slice of x
+# (the result is None -> zeros).
+# --------------------------------------------------------------------------
+
+def _grad(y, x):
+    g = torch.autograd.grad(y, x, grad_outputs=torch.ones_like(y), create_graph=True,
+                            allow_unused=True, retain_graph=True)[0]
+    return torch.zeros_like(y) if g is None else g
+
+
+def compute_derivatives(model, x, t, spatial: Sequence[int], temporal: Sequence[int],
+                        dimension: int = 1) -> Dict[str, torch.Tensor]:
+    x = x.detach().requires_grad_(True)
+    t = t.detach().requires_grad_(True)
+    u = model(torch.cat([x, t], dim=1))
+    out: Dict[str, torch.Tensor] = {}
+    prev = u
+    for i in sorted(temporal):
+        if i == 0:
+            continue
+        prev = _grad(u if i == 1 else prev, t)
+        out["dt" if i == 1 else f"dt{i}"] = prev
+    if spatial:
+        if dimension == 1:
+            prev = u
+            for i in sorted(spatial):
+                if i == 0:
+                    continue
+                prev = _grad(u if i == 1 else prev, x)
+                out["dx" if i == 1 else f"dx{i}"] = prev
+        else:
+            for d in range(dimension):
+                name = f"x{d + 1}"
+                for order in sorted(spatial):
+                    if order == 0:
+                        continue
+                    for i in range(1, order + 1):
+                        prev = _grad(u if i == 1 else prev, x[:, d:d + 1])
+                        out[f"d{name * i}"] = prev
+        if 2 in spatial:
+            if dimension == 1:
+                out["laplacian"] = out["dx2"]
+            else:
+                lap = torch.zeros_like(u)
+                for d in range(dimension):
+                    lap = lap + out[f"d{f'x{d + 1}' * 2}"]
+                out["laplacian"] = lap
+    out["_x"], out["_t"] = x, t
+    return out
+
+
+# --------------------------------------------------------------------------
+# The five residuals.
+# --------------------------------------------------------------------------
+
+def heat_residual(model, x, t, alpha=0.01, dimension=1):
+    d = compute_derivatives(model, x, t, [2], [1], dimension)
+    return d["dt"] - alpha * d["laplacian"]
+
+
+def burgers_residual(model, x, t, nu=0.01, dimension=1):
+    d = compute_derivatives(model, x, t, [1, 2], [1], dimension)
+    u = model(torch.cat([x, t], dim=1))
+    if dimension == 1:
+        conv = u * d["dx"]
+    else:
+        conv = torch.zeros_like(u)
+        for k in range(dimension):
+            conv = conv + u * d[f"dx{k + 1}"]
+    return d["dt"] + conv - nu * d["laplacian"]
+
+
+def kdv_residual(model, x, t, dimension=1):
+    x = x.detach().requires_grad_(True)
+    t = t.detach().requires_grad_(True)
+    d = compute_derivatives(model, x, t, [1, 2, 3], [1], dimension)
+    u = model(torch.cat([x, t], dim=1))
+    if dimension == 1:
+        return d["dt"] + 6 * u * d["dx"] + d["dx3"]
+    r = d["dt"]
+    for k in range(dimension):
+        n = f"x{k + 1}"
+        r = r + 6 * u * d[f"d{n}"] + d[f"d{n * 3}"]
+    return r
+
+
+def _laplacian_inline(f, x, dimension):
+    """Inline autograd chains of allen_cahn.py:61-108 / cahn_hilliard.py:69-109."""
+    if dimension == 1:
+        return _grad(_grad(f, x), x)
+    lap = torch.zeros_like(f)
+    for k in range(dimension):
+        xs = x[:, k:k + 1]                       # fresh slice: f never saw it (F2)
+        g = torch.autograd.grad(f, xs, torch.ones_like(f), create_graph=True, allow_unused=True)[0]
+        if g is not None:
+            g2 = torch.autograd.grad(g, xs, torch.ones_like(g), create_graph=True, allow_unused=True)[0]
+            if g2 is not None:
+                lap = lap + g2
+    return lap
+
+
+def allen_cahn_residual(model, x, t, epsilon=0.1, dimension=1):
+    x = x.requires_grad_(True)
+    t = t.requires_grad_(True)
+    u = model(torch.cat([x, t], dim=1))
+    u_t = _grad(u, t)
+    lap = _laplacian_inline(u, x, dimension)
+    return u_t - epsilon ** 2 * lap - u + u ** 3
+
+
+def cahn_hilliard_residual(model, x, t, epsilon=0.1, dimension=1):
+    x = x.detach().requires_grad_(True)
+    t = t.detach().requires_grad_(True)
+    u = model(torch.cat([x, t], dim=1))
+    u_t = _grad(u, t)
+    lap = _laplacian_inline(u, x, dimension)
+    uc = torch.clamp(u, -10.0, 10.0)
+    mu = -epsilon ** 2 * lap + uc ** 3 - uc
+    return u_t - _laplacian_inline(mu, x, dimension)
+
+
+RESIDUALS: Dict[str, Callable] = {
+    "heat": heat_residual, "burgers": burgers_residual, "kdv": kdv_residual,
+    "allen_cahn": allen_cahn_residual, "cahn_hilliard": cahn_hilliard_residual,
+}
+
+
+# --------------------------------------------------------------------------
+# Loss assembly.
+# --------------------------------------------------------------------------
+
+def apply_loss_fn(err, name="mse", delta=1.0):
+    if name == "mae":
+        return err.abs().mean()
+    if name == "huber":
+        return torch.nn.functional.huber_loss(err, torch.zeros_like(err), reduction="mean", delta=delta)
+    return (err ** 2).mean()
+
+
+def initial_condition_fn(pde: str, ic: Dict, domain, params: Dict, dimension: int = 1) -> Callable:
+    """IC target closures: per-PDE overrides first (heat_equation.py:214-276,
+    burgers_equation.py:131-161, kdv_equation.py:114-141, allen_cahn.py:131-151,
+    cahn_hilliard.py:180-203), then the base table (pde_base.py:518-572).  1-D only."""
+    kind = ic.get("type")
+    if pde == "heat" and ic.get("type", "sine") in ("sine", "sin_exp_decay"):
+        A, k = ic.get("amplitude", 1.0), ic.get("frequency", 2.0)
+        wave = 2 * torch.pi * k / (domain[0][1] - domain[0][0])
+        if ic.get("type", "sine") == "sine":
+            return lambda x, t: A * torch.sin(wave * x)
+        decay = params["alpha"] * wave ** 2
+        return lambda x, t: A * torch.sin(wave * x) * torch.exp(-decay * t)
+    if pde == "burgers":
+        kind = ic.get("type", "sine")
+        if kind == "sine":
+            A, k = ic.get("amplitude", -1.0), ic.get("frequency", 1.0)
+            return lambda x, t: A * torch.sin(k * torch.pi * x)
+        if kind == "tanh":
+            e = ic.get("epsilon", 0.1)
+            return lambda x, t: torch.tanh((x - 0.5) / e)
+        raise ValueError(f"Unsupported initial condition type: {kind}")
+    if pde == "kdv":
+        kind = ic.get("type", "soliton")
+        if kind != "soliton":
+            raise ValueError(f"Unsupported initial condition type: {kind}")
+        c = torch.tensor(ic.get("speed", params.get("speed", 1.0)), dtype=torch.float32)
+        return lambda x, t: 2 * c * (1 / torch.cosh(torch.sqrt(c) * x)) ** 2
+    if pde in ("allen_cahn", "cahn_hilliard"):
+        kind = ic.get("type", "tanh")
+        if kind == "tanh":
+            e = params.get("epsilon", 0.1)
+            return lambda x, t: torch.tanh(x / (2 * e))
+        if kind == "random" and pde == "cahn_hilliard":
+            amp = ic.get("amplitude", 0.1)
+            return lambda x, t: amp * (2 * torch.rand_like(x[:, 0:1]) - 1)
+        raise ValueError(f"Unsupported initial condition type: {kind}")
+    kind = ic.get("type", "sine")
+    if kind in ("sine", "sin_exp_decay"):
+        a, f = ic.get("amplitude", 1.0), ic.get("frequency", 1.0)
+        return lambda x, t: a * torch.sin(f * torch.pi * x[:, 0:1])
+    if kind == "tanh":
+        e = ic.get("epsilon", 0.1)
+        return lambda x, t: torch.tanh(x[:, 0:1] / e)
+    if kind == "gaussian":
+        m, s = ic.get("mean", 0.0), ic.get("std", 0.1)
+        return lambda x, t: torch.exp(-((x[:, 0:1] - m) ** 2) / (2 * s ** 2))
+    if kind == "fixed":
+        v = ic.get("value", 0.0)
+        return lambda x, t: torch.full_like(x[:, 0:1], v)
+    return lambda x, t: torch.zeros_like(x[:, 0:1])
+
+
+def boundary_condition_fns(pde: str, bcs: Dict, ic: Optional[Dict], domain, params: Dict,
+                           exact: Optional[Dict] = None, dimension=1) -> Dict[str, Callable]:
+    """``PDEBase._setup_boundary_conditions`` (pde_base.py:474-486): every configured
+    BC entry, plus the IC closure under the key ``"initial"``."""
+    fns: Dict[str, Callable] = {}
+    for kind, p in (bcs or {}).items():
+        if kind == "initial":
+            fns[kind] = initial_condition_fn(pde, p, domain, params, dimension)
+            continue
+        if (pde == "heat" and kind == "dirichlet" and (exact or {}).get("type") == "sin_exp_decay"):
+            A, k = exact.get("amplitude", 1.0), exact.get("frequency", 2.0)       # heat_equation.py:277-292
+            wave = 2 * torch.pi * k / (domain[0][1] - domain[0][0])
+            decay = params["alpha"] * wave ** 2
+            fns[kind] = (lambda A, wave, decay: lambda x, t: A * torch.sin(wave * x) * torch.exp(-decay * t))(A, wave, decay)
+            continue
+        k = "dirichlet" if kind in ("left", "right") else kind
+        if k in ("dirichlet", "neumann"):
+            v = p.get("value", 0.0)
+            fns[kind] = (lambda v: lambda x, t: torch.full_like(x[:, 0:1], v))(v)
+        elif k == "periodic":
+            fns[kind] = lambda x, t: torch.sin(2 * torch.pi * x[:, 0:1])
+        else:
+            fns[kind] = lambda x, t: torch.zeros_like(x[:, 0:1])
+    if "initial" not in fns and ic is not None:
+        fns["initial"] = initial_condition_fn(pde, ic, domain, params, dimension)
+    return fns
+
+
+def base_compute_loss(model, residual, domain, time_domain, bc_fns: Dict[str, Callable],
+                      weights=(1.0, 10.0, 10.0), loss_fn="mse", delta=1.0):
+    """pde_base.py:1086-1235 for dimension 1 in forward mode."""
+    dev = residual.device
+    res_loss = apply_loss_fn(residual, loss_fn, delta)
+    xb = torch.tensor([domain[0][0], domain[0][1]], dtype=torch.float32, device=dev).reshape(-1, 1)
+    tb = torch.linspace(time_domain[0], time_domain[1], 100, device=dev).reshape(-1, 1)
+    xb = xb.repeat_interleave(len(tb), dim=0)
+    tb = tb.repeat(len(xb) // len(tb), 1)
+    b_loss = torch.tensor(0.0, device=dev)
+    for fn in bc_fns.values():
+        ub = model(torch.cat([xb, tb], dim=1))
+        b_loss = b_loss + apply_loss_fn(ub - fn(xb, tb), loss_fn, delta)
+    xi = torch.linspace(domain[0][0], domain[0][1], 100, device=dev).reshape(-1, 1)
+    ti = torch.zeros_like(xi)
+    ui = model(torch.cat([xi, ti], dim=1))
+    i_loss = apply_loss_fn(ui - bc_fns["initial"](xi, ti), loss_fn, delta)
+    zero = torch.tensor(0.0, device=dev)
+    total = weights[0] * res_loss + weights[1] * b_loss + weights[2] * i_loss
+    return {"residual": res_loss, "boundary": b_loss, "initial": i_loss,
+            "smoothness": zero, "data": zero.clone(), "total": total}
+
+
+def heat_boundary_points(domain, time_domain, num_boundary, device):
+    """Clustered boundary times of heat_equation.py:407-418."""
+    t_max = time_domain[1]
+    t_early = t_max * 0.01
+    n_early = max(num_boundary // 4, 1)
+    n_late = num_boundary - n_early
+    tb = torch.cat([torch.linspace(0, t_early, n_early, device=device),
+                    torch.linspace(t_early, t_max, n_late, device=device)]).reshape(-1, 1)
+    return tb
+
+
+def heat_initial_points(domain, num_initial, device):
+    """Three linspace segments of heat_equation.py:488-503."""
+    x_min, x_max = domain[0]
+    xb = (x_max - x_min) * 0.1
+    return torch.cat([
+        torch.linspace(x_min, x_min + xb, num_initial // 4, device=device),
+        torch.linspace(x_min + xb, x_max - xb, num_initial // 2, device=device),
+        torch.linspace(x_max - xb, x_max, num_initial // 4, device=device)]).reshape(-1, 1)
+
+
+def heat_compute_loss(model, residual, domain, time_domain, ic_fn, num_boundary, num_initial,
+                      weights=(1.0, 10.0, 10.0), loss_fn="mse", delta=1.0):
+    """heat_equation.py:375-623 for dimension 1, forward mode, smoothness weight 0."""
+    dev = residual.device
+    res_loss = apply_loss_fn(residual, loss_fn, delta)
+    tb = heat_boundary_points(domain, time_domain, num_boundary, dev)
+    x_min, x_max = domain[0]
+    pl = torch.cat([torch.full((num_boundary, 1), x_min, device=dev), tb], dim=1).requires_grad_(True)
+    pr = torch.cat([torch.full((num_boundary, 1), x_max, device=dev), tb], dim=1).requires_grad_(True)
+    ul, ur = model(pl), model(pr)
+    dl = torch.autograd.grad(ul, pl, torch.ones_like(ul), create_graph=True)[0][:, 0:1]
+    dr = torch.autograd.grad(ur, pr, torch.ones_like(ur), create_graph=True)[0][:, 0:1]
+    b_loss = torch.tensor(0.0, device=dev)
+    b_loss = b_loss + apply_loss_fn(ul - ur, loss_fn, delta)
+    b_loss = b_loss + apply_loss_fn(dl - dr, loss_fn, delta)
+    xi = heat_initial_points(domain, num_initial, dev)
+    ti = torch.zeros_like(xi)
+    ui = model(torch.cat([xi, ti], dim=1))
+    i_loss = apply_loss_fn(ui - ic_fn(xi, ti), loss_fn, delta)
+    zero = torch.tensor(0.0, device=dev)
+    total = weights[0] * res_loss + weights[1] * b_loss + weights[2] * i_loss
+    return {"residual": res_loss, "boundary": b_loss, "initial": i_loss,
+            "smoothness": zero, "data": zero.clone(), "total": total}
