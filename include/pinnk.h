@@ -1,0 +1,145 @@
+/* pinnk.h -- C ABI of the B200 PINN hot path (libpinnk.so).
+ *
+ * The reference (josegarciav/PINNs-RL-PDE, package `pinnrl`) is pure Python; it has no FFI.
+ * Its boundary for this path is the Python plugin API
+ *     PINNModel.forward(x)                          pinnrl/neural_networks/__init__.py:144-154
+ *     PDEBase.compute_residual(model, x, t)         pinnrl/pdes/pde_base.py:577-588 (+ five overrides)
+ *     PDEBase.compute_loss(model, x, t) -> dict     pinnrl/pdes/pde_base.py:1086-1235,
+ *                                                   pinnrl/pdes/heat_equation.py:375-623
+ *     loss["total"].backward()                      pinnrl/training/trainer.py:689
+ *     RAR / RL residual scoring                     pinnrl/pdes/pde_base.py:895-935,1364-1377
+ * Each entry point below names the reference call it stands in for.  The Python host
+ * (pinns_rl_pde_b200/) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every pointer marked "device" is a CUDA device pointer owned by the caller (torch);
+ *     the library allocates nothing on the device: the caller supplies the workspace
+ *   - all floating-point data is fp32; loss sums are fp64
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream)
+ *   - every function returns 0 on success or a negative PINNK_E_* code and never throws;
+ *     pinnk_last_error() returns a thread-local message for the last failure
+ *   - a plan is immutable; calls using one workspace must be serialised on one stream
+ */
+#ifndef PINNK_H_
+#define PINNK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PINNK_ABI_VERSION 1
+
+#define PINNK_E_INVALID   (-1)   /* bad argument / unsupported program            */
+#define PINNK_E_CUDA      (-2)   /* CUDA runtime error (message has the string)   */
+#define PINNK_E_WORKSPACE (-3)   /* workspace too small                           */
+
+/* network program: what PINNModel.forward does, op by op (neural_networks/{feedforward,resnet,siren,fourier}.py) */
+enum { PINNK_OP_LINEAR = 1, PINNK_OP_ACT = 2, PINNK_OP_LAYERNORM = 3,
+       PINNK_OP_SKIP_SAVE = 4, PINNK_OP_SKIP_ADD = 5, PINNK_OP_SINCOS = 6 };
+enum { PINNK_ACT_TANH = 1, PINNK_ACT_SIN = 2 };
+
+typedef struct {
+  int32_t kind;          /* PINNK_OP_*                                                        */
+  int32_t in_dim;        /* feature width entering the op                                     */
+  int32_t out_dim;       /* feature width leaving it (SINCOS: 2*in_dim)                       */
+  int32_t act;           /* ACT: PINNK_ACT_*                                                  */
+  float   scale;         /* ACT sin: omega_0 (siren.py:46); otherwise 1                       */
+  float   eps;           /* LAYERNORM eps                                                     */
+  int32_t w_index;       /* index into params[]: LINEAR weight [out,in] | LAYERNORM gamma; -1 */
+  int32_t b_index;       /* index into params[]: bias / beta; -1 = none                       */
+  int32_t w_transposed;  /* LINEAR: weight stored [in,out] (Fourier B, fourier.py:45)         */
+  int32_t reserved;
+  int64_t gw_offset;     /* float offset of dL/dW in the flat gradient buffer; -1 = frozen    */
+  int64_t gb_offset;     /* same for bias / beta                                              */
+} PinnkOp;
+
+/* derivative jets carried through the network: column 0 = value, then order[d] normalised
+ * Taylor coefficients along vec[d] (input space: x..., t).  Replaces the nested autograd.grad
+ * chains of pde_base.py:661-732, allen_cahn.py:61-87, cahn_hilliard.py:61-136. */
+typedef struct {
+  int32_t ndirs;             /* 0..5                                     */
+  int32_t order[5];          /* 1..4 each                                */
+  float   vec[5][4];         /* direction in input space, in_dim entries */
+} PinnkJetSpec;
+
+/* per-row error functional e = f(U[row]) [- f(U[row+pair_offset])] [- target[i]] */
+enum { PINNK_PDE_HEAT = 0, PINNK_PDE_BURGERS = 1, PINNK_PDE_KDV = 2, PINNK_PDE_ALLEN_CAHN = 3,
+       PINNK_PDE_CAHN_HILLIARD = 4, PINNK_PDE_UT_ONLY = 5, PINNK_PDE_UT_ALLEN_CAHN_ND = 6,
+       PINNK_PDE_CAHN_HILLIARD_2D = 7, PINNK_PDE_VALUE = 8, PINNK_PDE_DX = 9 };
+enum { PINNK_LOSS_MSE = 0, PINNK_LOSS_MAE = 1, PINNK_LOSS_HUBER = 2 };
+
+typedef struct {
+  int32_t kind;          /* PINNK_PDE_*                                                        */
+  int32_t compat_math;   /* HEAT: 0 = operator as written (u_t - a u_x), 1 = u_t - a u_xx */
+  float   p0;            /* alpha | nu | epsilon                                               */
+  float   p1;
+} PinnkPde;
+
+typedef struct {
+  PinnkPde pde;          /* functional applied to the rows                                     */
+  int32_t component;     /* loss_sums[] slot this segment adds to                              */
+  int32_t loss_kind;     /* PINNK_LOSS_* (pde_base.py:309-326)                                 */
+  float   huber_delta;
+  float   weight;        /* multiplies rho(e): 1/count for a mean                              */
+  int64_t row_start;     /* first row (point index within this call)                           */
+  int64_t row_count;
+  int64_t pair_offset;   /* != 0: e = f(U[row]) - f(U[row+pair_offset]) (periodic match)       */
+  const float* target;   /* device, nullable, [row_count]: subtracted from e                   */
+  float* error_out;      /* device, nullable, [row_count]: receives e (compute_residual)       */
+  const float* error_grad; /* device, nullable, [row_count]: upstream dL/de per row; when set the reverse
+                            pass is seeded with error_grad * de/dU instead of weight * rho'(e)
+                            (autograd through a compute_residual() result, CONTRIBUTING.md:241) */
+} PinnkSegment;
+
+typedef struct pinnk_plan_s* pinnk_plan_t;
+
+/* Build a plan for (network program, jet spec).  `chunk_points` bounds how many points are
+ * in flight at once (the activation stash lives in the workspace and is reused per chunk). */
+int pinnk_plan_create(const PinnkOp* ops, int32_t n_ops, int32_t in_dim, const PinnkJetSpec* jets,
+                      int64_t chunk_points, int32_t device, pinnk_plan_t* out);
+void pinnk_plan_destroy(pinnk_plan_t plan);
+int64_t pinnk_plan_workspace_bytes(pinnk_plan_t plan);   /* bytes the caller must provide */
+int32_t pinnk_plan_ncols(pinnk_plan_t plan);             /* jet columns C                 */
+int64_t pinnk_plan_grad_floats(pinnk_plan_t plan);       /* length of the flat gradient   */
+
+/* PINNModel.forward / jets of the network output.  x: device [n, in_dim-1] (or [n, in_dim]
+ * when t == NULL), t: device [n, 1]; out_jets: device [n, C].  Forward only. */
+int pinnk_jets_forward(pinnk_plan_t plan, const float* const* params, const float* x, const float* t,
+                       int64_t n, float* out_jets, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Vector-Jacobian product of pinnk_jets_forward w.r.t. the parameters: flat_grad += J^T adj_jets.
+ * Stands in for autograd through compute_residual / model(x) when the caller builds its own loss
+ * (CONTRIBUTING.md:241).  Recomputes the forward chunk by chunk; nothing is kept between calls. */
+int pinnk_jets_vjp(pinnk_plan_t plan, const float* const* params, const float* x, const float* t,
+                   int64_t n, const float* adj_jets, float* flat_grad, void* workspace,
+                   int64_t workspace_bytes, void* stream);
+
+/* compute_loss (+ its backward) over one set of rows: for every segment adds
+ * weight * sum_rows rho(e) to loss_sums[component] (device, fp64) and, when flat_grad != NULL,
+ * adds d/dtheta of sum_seg grad_scale[component] * weight * sum rho(e) to flat_grad (device).
+ * grad_scale: host array indexed by component (NULL = all ones).
+ * Stands in for pde.compute_loss(model,x,t) followed by loss.backward()
+ * (trainer.py:578,689; benchmarks/sampling.py:190-203). */
+int pinnk_loss_step(pinnk_plan_t plan, const float* const* params, const float* x, const float* t,
+                    int64_t n, const PinnkSegment* segments, int32_t n_segments,
+                    const float* grad_scale, double* loss_sums, float* flat_grad,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Forward-only residual scoring for the adaptive samplers (pde_base.py:909-921,1364-1377):
+ * abs_residual_out (device, nullable, [n]) receives |r|; stats (device, fp64 [4]) accumulates
+ * sum|r|, sum r^2, max|r|, count. */
+int pinnk_score(pinnk_plan_t plan, const float* const* params, const float* x, const float* t,
+                int64_t n, const PinnkPde* pde, float* abs_residual_out, double* stats,
+                void* workspace, int64_t workspace_bytes, void* stream);
+
+const char* pinnk_last_error(void);
+int32_t pinnk_abi_version(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+int64_t pinnk_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PINNK_H_ */

@@ -1,0 +1,619 @@
+// kernels_ew.cuh -- CUDA-core kernels of the jet pipeline: first/last Linear (K<=4 / N=1),
+// activation jets and their adjoints, LayerNorm jets and their adjoints, the PDE/loss epilogue
+// and the scoring reduction.  Jet tensors are row-major [points, C, width]: the C jet columns
+// of a point are adjacent rows, so a tensor is also the [points*C, width] operand of a GEMM.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "jet_math.cuh"
+
+namespace pinnk {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float load_in(const float* __restrict__ x, const float* __restrict__ t,
+                                         int64_t p, int i, int in_dim) {
+  if (t == nullptr) return x[p * in_dim + i];
+  return (i < in_dim - 1) ? x[p * (in_dim - 1) + i] : t[p];
+}
+
+// ------------------------------------------------------------------ first Linear (K = in_dim <= 4)
+// Z[p,0,:] = W xt_p + b ; Z[p,col0[d],:] = W vec_d ; higher orders 0.     (first nn.Linear of every net)
+__global__ void first_linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t, int64_t n,
+                                        const float* __restrict__ W, const float* __restrict__ b,
+                                        int w_transposed, int out_dim, JetSpec js, float* __restrict__ Z) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * out_dim) return;
+  const int64_t p = idx / out_dim;
+  const int f = (int)(idx - p * out_dim);
+  float w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    w[i] = (i < js.in_dim) ? (w_transposed ? W[i * out_dim + f] : W[f * js.in_dim + i]) : 0.f;
+  float z0 = b ? b[f] : 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i < js.in_dim) z0 = fmaf(w[i], load_in(x, t, p, i, js.in_dim), z0);
+  float* zp = Z + p * js.ncols * out_dim + f;
+  zp[0] = z0;
+  for (int d = 0; d < js.ndirs; ++d) {
+    float z1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) z1 = fmaf(w[i], js.vec[d][i], z1);
+    zp[(int64_t)js.col0[d] * out_dim] = z1;
+    for (int k = 2; k <= js.order[d]; ++k) zp[(int64_t)(js.col0[d] + k - 1) * out_dim] = 0.f;
+  }
+}
+
+// dW[f,i] += sum_p Zb[p,0,f] xt[p,i] + sum_p sum_d Zb[p,col0[d],f] vec_d[i] ;  db[f] += sum_p Zb[p,0,f]
+__global__ void first_linear_bwd_kernel(const float* __restrict__ x, const float* __restrict__ t, int64_t n,
+                                        int out_dim, JetSpec js, const float* __restrict__ Zb,
+                                        float* __restrict__ gW, float* __restrict__ gb) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= out_dim) return;
+  float aw[4] = {0.f, 0.f, 0.f, 0.f};
+  float ab = 0.f;
+  for (int64_t p = blockIdx.y; p < n; p += gridDim.y) {
+    const float* zp = Zb + p * js.ncols * out_dim + f;
+    const float g0 = zp[0];
+    ab += g0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < js.in_dim) aw[i] = fmaf(g0, load_in(x, t, p, i, js.in_dim), aw[i]);
+    for (int d = 0; d < js.ndirs; ++d) {
+      const float g1 = zp[(int64_t)js.col0[d] * out_dim];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) aw[i] = fmaf(g1, js.vec[d][i], aw[i]);
+    }
+  }
+  if (gW) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < js.in_dim) atomicAdd(gW + (int64_t)f * js.in_dim + i, aw[i]);
+  }
+  if (gb) atomicAdd(gb + f, ab);
+}
+
+// ------------------------------------------------------------------ activation jets
+template <int ACT> struct ActTag {};
+
+// Y = act(Z (+ S)).  One thread per (point, feature); directions processed one at a time.
+template <int ACT, int MAXK>
+__global__ void act_fwd_kernel(const float* __restrict__ Z, const float* __restrict__ S, float* __restrict__ Y,
+                               int64_t n, int width, JetSpec js, float omega) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * width) return;
+  const int64_t p = idx / width;
+  const int f = (int)(idx - p * width);
+  const int64_t base = p * js.ncols * width + f;
+  float z[MAXK + 1], y[MAXK + 1], w[MAXK + 1];
+  z[0] = Z[base] + (S ? S[base] : 0.f);
+  if (ACT == 1) {  // tanh
+    y[0] = tanhf(z[0]);
+    w[0] = 1.f - y[0] * y[0];
+  } else {         // sin(omega z): y = sin, w = cos
+    z[0] *= omega;
+    sincosf(z[0], &y[0], &w[0]);
+  }
+  Y[base] = y[0];
+  for (int d = 0; d < js.ndirs; ++d) {
+    const int K = js.order[d];
+    const int64_t b1 = base + (int64_t)js.col0[d] * width;
+#pragma unroll
+    for (int k = 1; k <= MAXK; ++k)
+      if (k <= K) {
+        const int64_t o = b1 + (int64_t)(k - 1) * width;
+        z[k] = Z[o] + (S ? S[o] : 0.f);
+        if (ACT == 2) z[k] *= omega;
+      }
+    if (ACT == 1) tanh_dir_fwd<MAXK, float>(K, z, y, w);
+    else sincos_dir_fwd<MAXK, float>(K, z, y, w);
+#pragma unroll
+    for (int k = 1; k <= MAXK; ++k)
+      if (k <= K) Y[b1 + (int64_t)(k - 1) * width] = y[k];
+  }
+}
+
+// G (in: dL/dY, out: dL/dZ) in place; Z (+S) is the stashed pre-activation.
+template <int ACT, int MAXK>
+__global__ void act_bwd_kernel(const float* __restrict__ Z, const float* __restrict__ S, float* __restrict__ G,
+                               int64_t n, int width, JetSpec js, float omega) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * width) return;
+  const int64_t p = idx / width;
+  const int f = (int)(idx - p * width);
+  const int64_t base = p * js.ncols * width + f;
+  float z[MAXK + 1], y[MAXK + 1], w[MAXK + 1], yb[MAXK + 1], zb[MAXK + 1], wb[MAXK + 1];
+  z[0] = Z[base] + (S ? S[base] : 0.f);
+  if (ACT == 1) {
+    y[0] = tanhf(z[0]);
+    w[0] = 1.f - y[0] * y[0];
+  } else {
+    z[0] *= omega;
+    sincosf(z[0], &y[0], &w[0]);
+  }
+  yb[0] = G[base];
+  float wb0 = 0.f;   // tanh: adjoint of w0 ; sin: adjoint of c0
+  for (int d = 0; d < js.ndirs; ++d) {
+    const int K = js.order[d];
+    const int64_t b1 = base + (int64_t)js.col0[d] * width;
+#pragma unroll
+    for (int k = 1; k <= MAXK; ++k)
+      if (k <= K) {
+        const int64_t o = b1 + (int64_t)(k - 1) * width;
+        z[k] = Z[o] + (S ? S[o] : 0.f);
+        if (ACT == 2) z[k] *= omega;
+        yb[k] = G[o];
+      } else {
+        yb[k] = 0.f;
+      }
+    if (ACT == 1) {
+      tanh_dir_fwd<MAXK, float>(K, z, y, w);
+      tanh_dir_bwd<MAXK, float>(K, z, y, w, yb, zb, wb0);
+    } else {
+#pragma unroll
+      for (int k = 0; k <= MAXK; ++k) wb[k] = 0.f;
+      wb[0] = wb0;
+      sincos_dir_fwd<MAXK, float>(K, z, y, w);
+      sincos_dir_bwd<MAXK, float>(K, z, y, w, yb, wb, zb);
+      wb0 = wb[0];
+    }
+#pragma unroll
+    for (int k = 1; k <= MAXK; ++k)
+      if (k <= K) G[b1 + (int64_t)(k - 1) * width] = (ACT == 2) ? zb[k] * omega : zb[k];
+  }
+  if (ACT == 1) G[base] = tanh_finish_bwd<float>(y[0], w[0], yb[0], wb0);
+  else G[base] = (yb[0] * w[0] - wb0 * y[0]) * omega;
+}
+
+// Fourier features: Y[..., 0:m] = sin(Z), Y[..., m:2m] = cos(Z)   (fourier.py:12-16); no adjoint (B is a buffer).
+template <int MAXK>
+__global__ void sincos_fwd_kernel(const float* __restrict__ Z, float* __restrict__ Y, int64_t n, int m, JetSpec js) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * m) return;
+  const int64_t p = idx / m;
+  const int f = (int)(idx - p * m);
+  const int64_t zb = p * js.ncols * m + f;
+  const int64_t yb = p * js.ncols * 2 * m + f;
+  float z[MAXK + 1], s[MAXK + 1], c[MAXK + 1];
+  z[0] = Z[zb];
+  sincosf(z[0], &s[0], &c[0]);
+  Y[yb] = s[0];
+  Y[yb + m] = c[0];
+  for (int d = 0; d < js.ndirs; ++d) {
+    const int K = js.order[d];
+#pragma unroll
+    for (int k = 1; k <= MAXK; ++k)
+      if (k <= K) z[k] = Z[zb + (int64_t)(js.col0[d] + k - 1) * m];
+    sincos_dir_fwd<MAXK, float>(K, z, s, c);
+#pragma unroll
+    for (int k = 1; k <= MAXK; ++k)
+      if (k <= K) {
+        const int64_t o = yb + (int64_t)(js.col0[d] + k - 1) * 2 * m;
+        Y[o] = s[k];
+        Y[o + m] = c[k];
+      }
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm jets (one warp per point)
+// NPER = ceil(width/32) features per lane.
+template <int MAXK, int NPER>
+__global__ void layernorm_fwd_kernel(const float* __restrict__ Z, float* __restrict__ Y, int64_t n, int width,
+                                     JetSpec js, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (p >= n) return;
+  const float inv_w = 1.f / (float)width;
+  const int64_t base = p * js.ncols * width;
+  float c0[NPER], g[NPER];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NPER; ++i) {
+    const int f = lane + 32 * i;
+    c0[i] = (f < width) ? Z[base + f] : 0.f;
+    g[i] = (f < width) ? gamma[f] : 0.f;
+    sum += c0[i];
+  }
+  const float mean0 = warp_sum(sum) * inv_w;
+  float vs = 0.f;
+#pragma unroll
+  for (int i = 0; i < NPER; ++i) {
+    const int f = lane + 32 * i;
+    c0[i] = (f < width) ? (c0[i] - mean0) : 0.f;
+    vs += c0[i] * c0[i];
+  }
+  float v[MAXK + 1], s[MAXK + 1];
+  v[0] = warp_sum(vs) * inv_w + eps;
+  s[0] = 1.f / sqrtf(v[0]);
+#pragma unroll
+  for (int i = 0; i < NPER; ++i) {
+    const int f = lane + 32 * i;
+    if (f < width) Y[base + f] = g[i] * c0[i] * s[0] + beta[f];
+  }
+  for (int d = 0; d < js.ndirs; ++d) {
+    const int K = js.order[d];
+    const int64_t b1 = base + (int64_t)js.col0[d] * width;
+    float c[MAXK + 1][NPER];
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) c[0][i] = c0[i];
+#pragma unroll
+    for (int k = 1; k <= MAXK; ++k) {
+      if (k <= K) {
+        float sm = 0.f;
+#pragma unroll
+        for (int i = 0; i < NPER; ++i) {
+          const int f = lane + 32 * i;
+          c[k][i] = (f < width) ? Z[b1 + (int64_t)(k - 1) * width + f] : 0.f;
+          sm += c[k][i];
+        }
+        const float mk = warp_sum(sm) * inv_w;
+        float vk = 0.f;
+#pragma unroll
+        for (int i = 0; i < NPER; ++i) {
+          const int f = lane + 32 * i;
+          c[k][i] = (f < width) ? (c[k][i] - mk) : 0.f;
+#pragma unroll
+          for (int j = 0; j <= k; ++j) vk += c[j][i] * c[k - j][i];
+        }
+        v[k] = warp_sum(vk) * inv_w;
+      }
+    }
+    rsqrt_dir_fwd<MAXK, float>(K, v, s);
+#pragma unroll
+    for (int k = 1; k <= MAXK; ++k) {
+      if (k <= K) {
+#pragma unroll
+        for (int i = 0; i < NPER; ++i) {
+          const int f = lane + 32 * i;
+          float a = 0.f;
+#pragma unroll
+          for (int j = 0; j <= k; ++j) a += c[j][i] * s[k - j];
+          if (f < width) Y[b1 + (int64_t)(k - 1) * width + f] = g[i] * a;
+        }
+      }
+    }
+  }
+}
+
+// Reverse of the above.  G_in = dL/dY, G_out = dL/dZ (distinct buffers); dgamma/dbeta accumulated per block.
+template <int MAXK, int NPER>
+__global__ void layernorm_bwd_kernel(const float* __restrict__ Z, const float* __restrict__ Gin,
+                                     float* __restrict__ Gout, int64_t n, int width, JetSpec js,
+                                     const float* __restrict__ gamma, float eps,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  extern __shared__ float red[];   // [2][width]
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const float inv_w = 1.f / (float)width;
+  for (int i = threadIdx.x; i < 2 * width; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float g[NPER], dg[NPER], db[NPER];
+#pragma unroll
+  for (int i = 0; i < NPER; ++i) {
+    const int f = lane + 32 * i;
+    g[i] = (f < width) ? gamma[f] : 0.f;
+    dg[i] = 0.f;
+    db[i] = 0.f;
+  }
+  for (int64_t p = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < n;
+       p += (int64_t)gridDim.x * warps_per_block) {
+    const int64_t base = p * js.ncols * width;
+    // ---- recompute order 0
+    float c0[NPER], yb0[NPER], cb0[NPER];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) {
+      const int f = lane + 32 * i;
+      c0[i] = (f < width) ? Z[base + f] : 0.f;
+      yb0[i] = (f < width) ? Gin[base + f] : 0.f;
+      sum += c0[i];
+    }
+    const float mean0 = warp_sum(sum) * inv_w;
+    float vs = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) {
+      const int f = lane + 32 * i;
+      c0[i] = (f < width) ? (c0[i] - mean0) : 0.f;
+      vs += c0[i] * c0[i];
+    }
+    float v[MAXK + 1], s[MAXK + 1];
+    v[0] = warp_sum(vs) * inv_w + eps;
+    s[0] = 1.f / sqrtf(v[0]);
+    // order-0 direct terms
+    float sb0 = 0.f, vb0 = 0.f;
+    {
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < NPER; ++i) {
+        dg[i] += yb0[i] * c0[i] * s[0];
+        db[i] += yb0[i];
+        cb0[i] = g[i] * yb0[i] * s[0];
+        part += g[i] * yb0[i] * c0[i];
+      }
+      sb0 = warp_sum(part);
+    }
+    for (int d = 0; d < js.ndirs; ++d) {
+      const int K = js.order[d];
+      const int64_t b1 = base + (int64_t)js.col0[d] * width;
+      float c[MAXK + 1][NPER], yb[MAXK + 1][NPER];
+#pragma unroll
+      for (int i = 0; i < NPER; ++i) { c[0][i] = c0[i]; yb[0][i] = 0.f; }   // yb[0] direct term handled above
+#pragma unroll
+      for (int k = 1; k <= MAXK; ++k) {
+        if (k <= K) {
+          float sm = 0.f;
+#pragma unroll
+          for (int i = 0; i < NPER; ++i) {
+            const int f = lane + 32 * i;
+            c[k][i] = (f < width) ? Z[b1 + (int64_t)(k - 1) * width + f] : 0.f;
+            yb[k][i] = (f < width) ? Gin[b1 + (int64_t)(k - 1) * width + f] : 0.f;
+            sm += c[k][i];
+          }
+          const float mk = warp_sum(sm) * inv_w;
+          float vk = 0.f;
+#pragma unroll
+          for (int i = 0; i < NPER; ++i) {
+            const int f = lane + 32 * i;
+            c[k][i] = (f < width) ? (c[k][i] - mk) : 0.f;
+#pragma unroll
+            for (int j = 0; j <= k; ++j) vk += c[j][i] * c[k - j][i];
+          }
+          v[k] = warp_sum(vk) * inv_w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < NPER; ++i) { c[k][i] = 0.f; yb[k][i] = 0.f; }
+          v[k] = 0.f;
+        }
+      }
+      rsqrt_dir_fwd<MAXK, float>(K, v, s);
+      // y_k = gamma * sum_i c_i s_{k-i}:   dgamma, cb (direct), sb
+      float sb[MAXK + 1], cb[MAXK + 1][NPER];
+#pragma unroll
+      for (int m = 0; m <= MAXK; ++m) {
+        float part = 0.f;
+#pragma unroll
+        for (int i = 0; i < NPER; ++i) {
+          float a = 0.f;
+#pragma unroll
+          for (int k = (m > 1 ? m : 1); k <= MAXK; ++k)
+            if (k <= K) {
+              a += yb[k][i] * s[k - m];          // -> cb[m]
+              part += g[i] * yb[k][i] * c[k - m][i];  // -> sb[m]
+            }
+          cb[m][i] = g[i] * a;
+        }
+        sb[m] = warp_sum(part);
+      }
+#pragma unroll
+      for (int k = 1; k <= MAXK; ++k)
+        if (k <= K) {
+#pragma unroll
+          for (int i = 0; i < NPER; ++i) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j <= k; ++j) a += c[j][i] * s[k - j];
+            dg[i] += yb[k][i] * a;
+          }
+        }
+      // s recurrence
+      float vb[MAXK + 1];
+      float sb_in0 = sb[0];
+      rsqrt_dir_bwd<MAXK, float>(K, v, s, sb, vb, vb0);
+      sb0 += sb[0];
+      (void)sb_in0;
+      // v_k = mean_f sum_i c_i c_{k-i}  (k >= 1) -> cb[i] += (2/W) sum_{k>=max(i,1)} vb_k c_{k-i}
+#pragma unroll
+      for (int m = 0; m <= MAXK; ++m) {
+#pragma unroll
+        for (int i = 0; i < NPER; ++i) {
+          float a = 0.f;
+#pragma unroll
+          for (int k = (m > 1 ? m : 1); k <= MAXK; ++k)
+            if (k <= K) a += vb[k] * c[k - m][i];
+          cb[m][i] += 2.f * inv_w * a;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NPER; ++i) cb0[i] += cb[0][i];
+      // z_k = c_k + mean: zb_k = cb_k - mean_f cb_k
+#pragma unroll
+      for (int k = 1; k <= MAXK; ++k)
+        if (k <= K) {
+          float sm = 0.f;
+#pragma unroll
+          for (int i = 0; i < NPER; ++i) sm += cb[k][i];
+          const float mk = warp_sum(sm) * inv_w;
+#pragma unroll
+          for (int i = 0; i < NPER; ++i) {
+            const int f = lane + 32 * i;
+            if (f < width) Gout[b1 + (int64_t)(k - 1) * width + f] = cb[k][i] - mk;
+          }
+        }
+    }
+    // order-0 closure: s0 = v0^-1/2 ; v0 = mean c0^2 + eps ; c0 = z0 - mean
+    vb0 += sb0 * (-0.5f) * s[0] / v[0];
+    float sm = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) {
+      cb0[i] += 2.f * inv_w * vb0 * c0[i];
+      sm += cb0[i];
+    }
+    const float m0 = warp_sum(sm) * inv_w;
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) {
+      const int f = lane + 32 * i;
+      if (f < width) Gout[base + f] = cb0[i] - m0;
+    }
+  }
+  // block-level accumulation of dgamma / dbeta
+#pragma unroll
+  for (int i = 0; i < NPER; ++i) {
+    const int f = lane + 32 * i;
+    if (f < width) {
+      atomicAdd(&red[f], dg[i]);
+      atomicAdd(&red[width + f], db[i]);
+    }
+  }
+  __syncthreads();
+  for (int f = threadIdx.x; f < width; f += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + f, red[f]);
+    if (dbeta) atomicAdd(dbeta + f, red[width + f]);
+  }
+}
+
+// ------------------------------------------------------------------ last Linear (N = 1)
+// U[row] = sum_f W[f] X[row,f] (+ b on the value column).  One warp per row.
+__global__ void last_linear_fwd_kernel(const float* __restrict__ X, int64_t rows, int width, int ncols,
+                                       const float* __restrict__ W, const float* __restrict__ b,
+                                       float* __restrict__ U) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= rows) return;
+  float a = 0.f;
+  for (int f = lane; f < width; f += 32) a = fmaf(W[f], X[row * width + f], a);
+  a = warp_sum(a);
+  if (lane == 0) U[row] = a + ((b && (row % ncols) == 0) ? b[0] : 0.f);
+}
+
+// Xb[row,f] = Ub[row] W[f] ; dW[f] += sum_row Ub[row] X[row,f] ; db += sum_p Ub[p,0]
+__global__ void last_linear_bwd_kernel(const float* __restrict__ X, const float* __restrict__ Ub, int64_t rows,
+                                       int width, int ncols, const float* __restrict__ W,
+                                       float* __restrict__ Xb, float* __restrict__ gW, float* __restrict__ gb) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = f < width;
+  const float wf = active ? W[f] : 0.f;
+  float acc = 0.f, accb = 0.f;
+  for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
+    const float ub = Ub[row];
+    if (active) {
+      acc = fmaf(ub, X[row * width + f], acc);
+      Xb[row * width + f] = ub * wf;
+    }
+    if (f == 0 && (row % ncols) == 0) accb += ub;
+  }
+  if (active && gW) atomicAdd(gW + f, acc);
+  if (f == 0 && gb) atomicAdd(gb, accb);
+}
+
+// db[f] += sum over value-column rows of G[row,f]    (bias gradient of a hidden Linear)
+__global__ void bias_grad_kernel(const float* __restrict__ G, int64_t n, int width, int ncols, float* __restrict__ gb) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= width) return;
+  float acc = 0.f;
+  for (int64_t p = blockIdx.y; p < n; p += gridDim.y) acc += G[p * ncols * width + f];
+  atomicAdd(gb + f, acc);
+}
+
+__global__ void add_inplace_kernel(float* __restrict__ A, const float* __restrict__ B, int64_t count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) A[i] += B[i];
+}
+
+// ------------------------------------------------------------------ PDE / loss epilogue
+struct SegmentDev {
+  PdeDesc pde;
+  int loss_kind;
+  float huber_delta;
+  float weight;        // multiplies rho(e) in the loss sum
+  float grad_weight;   // multiplies rho'(e) in the seed (grad_scale[component] * weight); 0 = no seeds
+  int64_t row_start, row_count, pair_offset;
+  const float* target;
+  float* error_out;
+  const float* error_grad;   // per-row upstream dL/de (overrides rho' * grad_weight)
+  double* loss_slot;
+};
+
+// rows are relative to the chunk: U / Ub hold [chunk_rows, C]; `row_lo`.. is the part of the segment in this chunk.
+__global__ void epilogue_kernel(const float* __restrict__ U, float* __restrict__ Ub, JetSpec js, SegmentDev sg,
+                                int64_t chunk_row0, int64_t lo, int64_t hi) {
+  const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // absolute row of the call
+  double part = 0.0;
+  if (i < hi) {
+    const int64_t r = i - chunk_row0;
+    float u[kMaxCols], du[kMaxCols];
+    for (int c = 0; c < js.ncols; ++c) u[c] = U[r * js.ncols + c];
+    float e = pde_residual<float>(sg.pde, js, u, du);
+    float du2[kMaxCols];
+    if (sg.pair_offset != 0) {
+      const int64_t r2 = r + sg.pair_offset;
+      for (int c = 0; c < js.ncols; ++c) u[c] = U[r2 * js.ncols + c];
+      e -= pde_residual<float>(sg.pde, js, u, du2);
+    }
+    const int64_t k = i - sg.row_start;
+    if (sg.target) e -= sg.target[k];
+    if (sg.error_out) sg.error_out[k] = e;
+    float drho;
+    const float rho = loss_rho<float>(sg.loss_kind, sg.huber_delta, e, &drho);
+    part = (double)rho * (double)sg.weight;
+    if (Ub != nullptr && (sg.grad_weight != 0.f || sg.error_grad != nullptr)) {
+      const float gsc = sg.error_grad ? sg.error_grad[k] : drho * sg.grad_weight;
+      for (int c = 0; c < js.ncols; ++c) Ub[r * js.ncols + c] += gsc * du[c];
+      if (sg.pair_offset != 0) {
+        const int64_t r2 = r + sg.pair_offset;
+        for (int c = 0; c < js.ncols; ++c) Ub[r2 * js.ncols + c] -= gsc * du2[c];
+      }
+    }
+  }
+  part = warp_sum_d(part);
+  __shared__ double sh[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sh[wid] = part;
+  __syncthreads();
+  if (wid == 0) {
+    double v = (lane < (blockDim.x >> 5)) ? sh[lane] : 0.0;
+    v = warp_sum_d(v);
+    if (lane == 0 && sg.loss_slot) atomicAdd(sg.loss_slot, v);
+  }
+}
+
+// |r| and (sum|r|, sum r^2, max|r|, count) for the adaptive samplers
+__global__ void score_kernel(const float* __restrict__ U, JetSpec js, PdeDesc pde, int64_t rows,
+                             float* __restrict__ abs_out, double* __restrict__ stats) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double s1 = 0.0, s2 = 0.0;
+  float mx = 0.f;
+  if (r < rows) {
+    float u[kMaxCols];
+    for (int c = 0; c < js.ncols; ++c) u[c] = U[r * js.ncols + c];
+    const float a = fabsf(pde_residual<float>(pde, js, u, nullptr));
+    if (abs_out) abs_out[r] = a;
+    s1 = a; s2 = (double)a * a; mx = a;
+  }
+  s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  __shared__ double sh1[32], sh2[32];
+  __shared__ float shm[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) { sh1[wid] = s1; sh2[wid] = s2; shm[wid] = mx; }
+  __syncthreads();
+  if (wid == 0) {
+    const int nw = blockDim.x >> 5;
+    s1 = lane < nw ? sh1[lane] : 0.0; s2 = lane < nw ? sh2[lane] : 0.0; mx = lane < nw ? shm[lane] : 0.f;
+    s1 = warp_sum_d(s1); s2 = warp_sum_d(s2);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) {
+      atomicAdd(stats + 0, s1);
+      atomicAdd(stats + 1, s2);
+      // max of non-negative doubles == max of their bit patterns
+      atomicMax(reinterpret_cast<unsigned long long*>(stats + 2), (unsigned long long)__double_as_longlong((double)mx));
+      const int64_t base = (int64_t)blockIdx.x * blockDim.x;
+      const int64_t cnt = (rows - base) < (int64_t)blockDim.x ? (rows - base) : (int64_t)blockDim.x;
+      atomicAdd(stats + 3, (double)cnt);
+    }
+  }
+}
+
+}  // namespace pinnk

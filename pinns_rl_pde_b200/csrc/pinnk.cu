@@ -1,0 +1,569 @@
+// pinnk.cu -- plan, orchestration and the C ABI (include/pinnk.h) of the B200 PINN hot path.
+//
+// One call = the reference's compute_loss(+backward) / compute_residual / scoring over a set of
+// collocation rows (see include/pinnk.h for the reference call each entry point replaces).
+// Rows are processed in chunks of plan->chunk points: forward jets through the network program
+// (stashing pre-activations in the caller's workspace), PDE/loss epilogue, then the hand-written
+// reverse pass that accumulates into the flat gradient buffer.  Nothing survives between chunks
+// except the gradient and the loss sums, so memory is bounded by the chunk size.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <atomic>
+#include <type_traits>
+#include <string>
+#include <vector>
+
+#include "../../include/pinnk.h"
+#include "jet_math.cuh"
+#include "kernels_ew.cuh"
+#include "sgemm.cuh"
+#include "tc_gemm.cuh"
+
+using namespace pinnk;
+
+static thread_local std::string g_err;
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define PK_CHECK_CUDA(expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return fail(PINNK_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+  } while (0)
+
+#define PK_LAUNCH_OK()                                                                       \
+  do {                                                                                       \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                      \
+    cudaError_t _e = cudaGetLastError();                                                     \
+    if (_e != cudaSuccess)                                                                   \
+      return fail(PINNK_E_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e));    \
+  } while (0)
+
+struct OpRt {
+  PinnkOp op;
+  int64_t out_off;     // float offset (per point -> multiplied by chunk) of the op's output jets; -1 = none
+  int in_op;           // index of the op whose output feeds this one (-1 = network input)
+  int skip_src;        // ACT with fused skip: op index whose output is added (-2 = none)
+};
+
+struct pinnk_plan_s {
+  std::vector<OpRt> ops;
+  JetSpec js;
+  int maxk;
+  int64_t chunk;
+  int device;
+  int max_width;
+  int64_t stash_floats_per_point;   // sum of C*width over stashed outputs
+  int64_t grad_floats;
+  int64_t ws_bytes;
+  int sm_count;
+  // workspace layout (float offsets)
+  int64_t off_stash, off_U, off_Ub, off_adj[3];
+};
+
+static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+extern "C" const char* pinnk_last_error(void) { return g_err.c_str(); }
+extern "C" int32_t pinnk_abi_version(void) { return PINNK_ABI_VERSION; }
+extern "C" int64_t pinnk_launch_count(void) { return g_launches.load(); }
+
+extern "C" int pinnk_plan_create(const PinnkOp* ops, int32_t n_ops, int32_t in_dim, const PinnkJetSpec* jets,
+                                 int64_t chunk_points, int32_t device, pinnk_plan_t* out) {
+  if (!ops || !jets || !out || n_ops < 2) return fail(PINNK_E_INVALID, "plan_create: null argument or fewer than 2 ops");
+  if (in_dim < 1 || in_dim > 4) return fail(PINNK_E_INVALID, "plan_create: in_dim must be 1..4");
+  if (jets->ndirs < 0 || jets->ndirs > kMaxDirs) return fail(PINNK_E_INVALID, "plan_create: ndirs must be 0..5");
+  if (chunk_points < 1) return fail(PINNK_E_INVALID, "plan_create: chunk_points must be >= 1");
+  auto* pl = new pinnk_plan_s();
+  pl->device = device;
+  pl->chunk = chunk_points;
+  JetSpec& js = pl->js;
+  memset(&js, 0, sizeof(js));
+  js.ndirs = jets->ndirs;
+  js.in_dim = in_dim;
+  int col = 1, maxk = 0;
+  for (int d = 0; d < jets->ndirs; ++d) {
+    if (jets->order[d] < 1 || jets->order[d] > kMaxOrder) {
+      delete pl;
+      return fail(PINNK_E_INVALID, "plan_create: jet order must be 1..4");
+    }
+    js.order[d] = jets->order[d];
+    js.col0[d] = col;
+    col += jets->order[d];
+    if (jets->order[d] > maxk) maxk = jets->order[d];
+    for (int i = 0; i < 4; ++i) js.vec[d][i] = (i < in_dim) ? jets->vec[d][i] : 0.f;
+  }
+  js.ncols = col;
+  pl->maxk = maxk;
+
+  // validate the program and lay out the stash
+  int cur_width = in_dim, prev = -1, skip_saved = -2, pending_skip = -2;
+  int64_t off = 0, grad_end = 0;
+  int max_width = 1;
+  for (int i = 0; i < n_ops; ++i) {
+    OpRt r;
+    r.op = ops[i];
+    r.out_off = -1;
+    r.in_op = prev;
+    r.skip_src = -2;
+    const PinnkOp& o = ops[i];
+    std::string where = "plan_create: op " + std::to_string(i) + ": ";
+    auto bad = [&](const std::string& m) { delete pl; return fail(PINNK_E_INVALID, where + m); };
+    switch (o.kind) {
+      case PINNK_OP_LINEAR:
+        if (o.in_dim != cur_width) return bad("LINEAR in_dim does not match the incoming width");
+        if (o.w_index < 0) return bad("LINEAR needs a weight");
+        if (i == 0) {
+          if (o.in_dim != in_dim) return bad("first op must consume the network input");
+        } else if (i == n_ops - 1) {
+          if (o.out_dim != 1) return bad("last LINEAR must have out_dim == 1 (PINN output u)");
+          if (o.w_transposed) return bad("transposed weight only supported on the first LINEAR");
+        } else {
+          if (o.w_transposed) return bad("transposed weight only supported on the first LINEAR");
+          if ((o.in_dim % 4) || (o.out_dim % 4)) return bad("hidden LINEAR widths must be multiples of 4");
+        }
+        if (pending_skip != -2) return bad("SKIP_ADD must be followed by ACT");
+        cur_width = o.out_dim;
+        break;
+      case PINNK_OP_ACT:
+        if (o.act != PINNK_ACT_TANH && o.act != PINNK_ACT_SIN) return bad("unsupported activation (tanh | sin)");
+        if (o.in_dim != cur_width || o.out_dim != cur_width) return bad("ACT width mismatch");
+        if (prev < 0) return bad("ACT cannot be the first op");
+        r.skip_src = pending_skip;
+        pending_skip = -2;
+        break;
+      case PINNK_OP_LAYERNORM:
+        if (o.in_dim != cur_width || o.out_dim != cur_width) return bad("LAYERNORM width mismatch");
+        if (o.w_index < 0 || o.b_index < 0) return bad("LAYERNORM needs gamma and beta");
+        if (cur_width > 256) return bad("LAYERNORM width > 256 not supported");
+        if (prev < 0) return bad("LAYERNORM cannot be the first op");
+        if (pending_skip != -2) return bad("SKIP_ADD must be followed by ACT");
+        break;
+      case PINNK_OP_SINCOS:
+        if (o.in_dim != cur_width || o.out_dim != 2 * cur_width) return bad("SINCOS width mismatch");
+        if (prev < 0) return bad("SINCOS cannot be the first op");
+        if (prev != 0 || ops[0].gw_offset >= 0) return bad("SINCOS is only supported right after a frozen first LINEAR (Fourier features)");
+        cur_width = o.out_dim;
+        break;
+      case PINNK_OP_SKIP_SAVE:
+        if (prev < 0) return bad("SKIP_SAVE cannot be the first op");
+        if (skip_saved != -2) return bad("nested skips are not supported");
+        skip_saved = prev;
+        break;
+      case PINNK_OP_SKIP_ADD:
+        if (skip_saved == -2) return bad("SKIP_ADD without SKIP_SAVE");
+        if (pl->ops[skip_saved].op.out_dim != cur_width) return bad("SKIP_ADD width mismatch");
+        pending_skip = skip_saved;
+        skip_saved = -2;
+        break;
+      default:
+        return bad("unknown op kind");
+    }
+    const bool produces = (o.kind == PINNK_OP_LINEAR || o.kind == PINNK_OP_ACT || o.kind == PINNK_OP_LAYERNORM ||
+                           o.kind == PINNK_OP_SINCOS);
+    if (produces) {
+      if (i != n_ops - 1) {
+        r.out_off = off;
+        off += (int64_t)js.ncols * cur_width;
+      }
+      prev = i;
+      if (cur_width > max_width) max_width = cur_width;
+    }
+    if (o.gw_offset >= 0) {
+      const int64_t cnt = (o.kind == PINNK_OP_LINEAR) ? (int64_t)o.in_dim * o.out_dim : o.out_dim;
+      if (o.gw_offset + cnt > grad_end) grad_end = o.gw_offset + cnt;
+    }
+    if (o.gb_offset >= 0 && o.gb_offset + o.out_dim > grad_end) grad_end = o.gb_offset + o.out_dim;
+    pl->ops.push_back(r);
+  }
+  if (ops[n_ops - 1].kind != PINNK_OP_LINEAR || ops[0].kind != PINNK_OP_LINEAR) {
+    delete pl;
+    return fail(PINNK_E_INVALID, "plan_create: program must start and end with LINEAR");
+  }
+  if (pending_skip != -2 || skip_saved != -2) {
+    delete pl;
+    return fail(PINNK_E_INVALID, "plan_create: dangling skip connection");
+  }
+  pl->max_width = max_width;
+  pl->stash_floats_per_point = off;
+  pl->grad_floats = grad_end;
+  // workspace: stash | U | Ub | adj0 | adj1 | adj2   (all sized for one chunk)
+  int64_t o = 0;
+  const int64_t C = js.ncols, n = chunk_points;
+  pl->off_stash = o; o = align_up(o + off * n, 64);
+  pl->off_U = o;     o = align_up(o + C * n, 64);
+  pl->off_Ub = o;    o = align_up(o + C * n, 64);
+  for (int k = 0; k < 3; ++k) { pl->off_adj[k] = o; o = align_up(o + C * n * max_width, 64); }
+  pl->ws_bytes = o * (int64_t)sizeof(float);
+  int smc = 148;
+  cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, device);   // stays 148 when no device is visible
+  cudaGetLastError();
+  pl->sm_count = smc > 0 ? smc : 148;
+  *out = pl;
+  return 0;
+}
+
+extern "C" void pinnk_plan_destroy(pinnk_plan_t plan) { delete plan; }
+extern "C" int64_t pinnk_plan_workspace_bytes(pinnk_plan_t plan) { return plan ? plan->ws_bytes : 0; }
+extern "C" int32_t pinnk_plan_ncols(pinnk_plan_t plan) { return plan ? plan->js.ncols : 0; }
+extern "C" int64_t pinnk_plan_grad_floats(pinnk_plan_t plan) { return plan ? plan->grad_floats : 0; }
+
+// ------------------------------------------------------------------------------------------------
+template <typename F>
+static int dispatch_maxk(int maxk, F&& f) {
+  switch (maxk) {
+    case 0: case 1: return f(std::integral_constant<int, 1>());
+    case 2: return f(std::integral_constant<int, 2>());
+    case 3: return f(std::integral_constant<int, 3>());
+    default: return f(std::integral_constant<int, 4>());
+  }
+}
+
+static inline unsigned blocks_for(int64_t work, int threads) { return (unsigned)((work + threads - 1) / threads); }
+
+struct ChunkCtx {
+  pinnk_plan_t pl;
+  const float* const* params;
+  float* ws;
+  cudaStream_t st;
+  int64_t n;          // points in this chunk
+  const float* x;     // chunk-local input pointers
+  const float* t;
+  float* stash(int op) const { return ws + pl->off_stash + pl->ops[op].out_off * pl->chunk; }
+  float* U() const { return ws + pl->off_U; }
+  float* Ub() const { return ws + pl->off_Ub; }
+  float* adj(int k) const { return ws + pl->off_adj[k]; }
+};
+
+static int gemm_fwd(const ChunkCtx& c, const float* X, const float* W, const float* b, float* Z, int in_dim, int out_dim) {
+  const int64_t M = c.n * c.pl->js.ncols;
+  int rc = tc_linear_fwd(X, W, b, Z, M, in_dim, out_dim, c.pl->js.ncols, c.pl->sm_count, c.st);
+  if (rc == 0) { g_launches.fetch_add(1); return 0; }
+  if (rc != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, "tc_linear_fwd failed");
+  dim3 grid(blocks_for(M, SG_BM), blocks_for(out_dim, SG_BN), 1);
+  sgemm_kernel<true, true, EPI_BIAS_C0><<<grid, SG_THREADS, 0, c.st>>>(X, W, Z, M, out_dim, in_dim, in_dim, in_dim,
+                                                                        out_dim, b, c.pl->js.ncols, in_dim);
+  PK_LAUNCH_OK();
+  return 0;
+}
+
+static int gemm_dgrad(const ChunkCtx& c, const float* Zb, const float* W, float* Xb, int in_dim, int out_dim) {
+  const int64_t M = c.n * c.pl->js.ncols;
+  dim3 grid(blocks_for(M, SG_BM), blocks_for(in_dim, SG_BN), 1);
+  sgemm_kernel<true, false, EPI_STORE><<<grid, SG_THREADS, 0, c.st>>>(Zb, W, Xb, M, in_dim, out_dim, out_dim, in_dim,
+                                                                       in_dim, nullptr, 1, out_dim);
+  PK_LAUNCH_OK();
+  return 0;
+}
+
+static int gemm_wgrad(const ChunkCtx& c, const float* Zb, const float* X, float* gW, float* gb, int in_dim, int out_dim) {
+  const int64_t M = c.n * c.pl->js.ncols;   // contraction length
+  if (gW) {
+    const unsigned tiles = blocks_for(out_dim, SG_BM) * blocks_for(in_dim, SG_BN);
+    int64_t splits = (2 * (int64_t)c.pl->sm_count + tiles - 1) / tiles;
+    int64_t k_chunk = align_up((M + splits - 1) / splits, 64);
+    if (k_chunk < 256) k_chunk = 256;
+    splits = (M + k_chunk - 1) / k_chunk;
+    dim3 grid(blocks_for(out_dim, SG_BM), blocks_for(in_dim, SG_BN), (unsigned)splits);
+    sgemm_kernel<false, false, EPI_ATOMIC><<<grid, SG_THREADS, 0, c.st>>>(Zb, X, gW, out_dim, in_dim, M, out_dim, in_dim,
+                                                                           in_dim, nullptr, 1, k_chunk);
+    PK_LAUNCH_OK();
+  }
+  if (gb) {
+    dim3 grid(blocks_for(out_dim, 128), (unsigned)std::min<int64_t>(c.n, 256));
+    bias_grad_kernel<<<grid, 128, 0, c.st>>>(Zb, c.n, out_dim, c.pl->js.ncols, gb);
+    PK_LAUNCH_OK();
+  }
+  return 0;
+}
+
+template <int MAXK>
+static int ln_fwd(const ChunkCtx& c, const float* Z, float* Y, int width, const float* g, const float* b, float eps) {
+  const int threads = 256;
+  const unsigned blocks = blocks_for(c.n * 32, threads);
+  const int nper = (width + 31) / 32;
+#define LN_F(NP) layernorm_fwd_kernel<MAXK, NP><<<blocks, threads, 0, c.st>>>(Z, Y, c.n, width, c.pl->js, g, b, eps)
+  if (nper <= 1) LN_F(1); else if (nper <= 2) LN_F(2); else if (nper <= 4) LN_F(4); else LN_F(8);
+#undef LN_F
+  PK_LAUNCH_OK();
+  return 0;
+}
+
+template <int MAXK>
+static int ln_bwd(const ChunkCtx& c, const float* Z, const float* Gin, float* Gout, int width, const float* g, float eps,
+                  float* dg, float* db) {
+  const int threads = 128;
+  const int wpb = threads / 32;
+  int64_t blocks = (c.n + wpb - 1) / wpb;
+  const int64_t cap = (int64_t)c.pl->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  const size_t sh = 2 * (size_t)width * sizeof(float);
+  const int nper = (width + 31) / 32;
+#define LN_B(NP) layernorm_bwd_kernel<MAXK, NP><<<(unsigned)blocks, threads, sh, c.st>>>(Z, Gin, Gout, c.n, width, c.pl->js, g, eps, dg, db)
+  if (nper <= 1) LN_B(1); else if (nper <= 2) LN_B(2); else if (nper <= 4) LN_B(4); else LN_B(8);
+#undef LN_B
+  PK_LAUNCH_OK();
+  return 0;
+}
+
+// forward jets of one chunk; fills the stash and U[n, C]
+template <int MAXK>
+static int forward_chunk(const ChunkCtx& c) {
+  const pinnk_plan_t pl = c.pl;
+  const JetSpec& js = pl->js;
+  const int n_ops = (int)pl->ops.size();
+  const int threads = 256;
+  for (int i = 0; i < n_ops; ++i) {
+    const OpRt& r = pl->ops[i];
+    const PinnkOp& o = r.op;
+    const float* in = (r.in_op >= 0) ? c.stash(r.in_op) : nullptr;
+    switch (o.kind) {
+      case PINNK_OP_LINEAR: {
+        const float* W = c.params[o.w_index];
+        const float* b = (o.b_index >= 0) ? c.params[o.b_index] : nullptr;
+        if (i == 0) {
+          first_linear_fwd_kernel<<<blocks_for(c.n * o.out_dim, threads), threads, 0, c.st>>>(
+              c.x, c.t, c.n, W, b, o.w_transposed, o.out_dim, js, c.stash(i));
+          PK_LAUNCH_OK();
+        } else if (i == n_ops - 1) {
+          const int64_t rows = c.n * js.ncols;
+          last_linear_fwd_kernel<<<blocks_for(rows * 32, threads), threads, 0, c.st>>>(in, rows, o.in_dim, js.ncols, W, b, c.U());
+          PK_LAUNCH_OK();
+        } else {
+          int rc = gemm_fwd(c, in, W, b, c.stash(i), o.in_dim, o.out_dim);
+          if (rc) return rc;
+        }
+        break;
+      }
+      case PINNK_OP_ACT: {
+        const float* S = (r.skip_src >= 0) ? c.stash(r.skip_src) : nullptr;
+        const unsigned blocks = blocks_for(c.n * o.in_dim, threads);
+        if (o.act == PINNK_ACT_TANH)
+          act_fwd_kernel<1, MAXK><<<blocks, threads, 0, c.st>>>(in, S, c.stash(i), c.n, o.in_dim, js, 1.f);
+        else
+          act_fwd_kernel<2, MAXK><<<blocks, threads, 0, c.st>>>(in, S, c.stash(i), c.n, o.in_dim, js, o.scale);
+        PK_LAUNCH_OK();
+        break;
+      }
+      case PINNK_OP_LAYERNORM: {
+        int rc = ln_fwd<MAXK>(c, in, c.stash(i), o.in_dim, c.params[o.w_index], c.params[o.b_index], o.eps);
+        if (rc) return rc;
+        break;
+      }
+      case PINNK_OP_SINCOS:
+        sincos_fwd_kernel<MAXK><<<blocks_for(c.n * o.in_dim, threads), threads, 0, c.st>>>(in, c.stash(i), c.n, o.in_dim, js);
+        PK_LAUNCH_OK();
+        break;
+      default: break;   // skip markers
+    }
+  }
+  return 0;
+}
+
+// reverse pass of one chunk: Ub[n, C] -> flat_grad (accumulated)
+template <int MAXK>
+static int backward_chunk(const ChunkCtx& c, float* flat_grad) {
+  const pinnk_plan_t pl = c.pl;
+  const JetSpec& js = pl->js;
+  const int n_ops = (int)pl->ops.size();
+  const int threads = 256;
+  int cur = 0;            // adjoint buffer holding dL/d(output of the op being processed)
+  int held = -1;          // buffer holding the skip-branch adjoint
+  auto other = [&](int a, int b) { for (int k = 0; k < 3; ++k) if (k != a && k != b) return k; return -1; };
+  auto G = [&](int64_t off) -> float* { return off >= 0 ? flat_grad + off : nullptr; };
+  // earliest op that still needs an input adjoint: stop propagating below the last trainable op
+  int first_trainable = n_ops;
+  for (int i = 0; i < n_ops; ++i)
+    if (pl->ops[i].op.gw_offset >= 0 || pl->ops[i].op.gb_offset >= 0) { first_trainable = i; break; }
+  for (int i = n_ops - 1; i >= first_trainable; --i) {
+    const OpRt& r = pl->ops[i];
+    const PinnkOp& o = r.op;
+    const float* in = (r.in_op >= 0) ? c.stash(r.in_op) : nullptr;
+    switch (o.kind) {
+      case PINNK_OP_LINEAR: {
+        const float* W = c.params[o.w_index];
+        if (i == n_ops - 1) {
+          const int64_t rows = c.n * js.ncols;
+          dim3 grid(blocks_for(o.in_dim, 128), (unsigned)std::min<int64_t>(rows, 4 * (int64_t)pl->sm_count));
+          last_linear_bwd_kernel<<<grid, 128, 0, c.st>>>(in, c.Ub(), rows, o.in_dim, js.ncols, W, c.adj(cur),
+                                                         G(o.gw_offset), G(o.gb_offset));
+          PK_LAUNCH_OK();
+        } else if (i == 0) {
+          dim3 grid(blocks_for(o.out_dim, 128), (unsigned)std::min<int64_t>(c.n, 2 * (int64_t)pl->sm_count));
+          first_linear_bwd_kernel<<<grid, 128, 0, c.st>>>(c.x, c.t, c.n, o.out_dim, js, c.adj(cur), G(o.gw_offset), G(o.gb_offset));
+          PK_LAUNCH_OK();
+        } else {
+          int rc = gemm_wgrad(c, c.adj(cur), in, G(o.gw_offset), G(o.gb_offset), o.in_dim, o.out_dim);
+          if (rc) return rc;
+          if (i > first_trainable) {
+            const int nxt = other(cur, held);
+            rc = gemm_dgrad(c, c.adj(cur), W, c.adj(nxt), o.in_dim, o.out_dim);
+            if (rc) return rc;
+            cur = nxt;
+          }
+        }
+        break;
+      }
+      case PINNK_OP_ACT: {
+        const float* S = (r.skip_src >= 0) ? c.stash(r.skip_src) : nullptr;
+        const unsigned blocks = blocks_for(c.n * o.in_dim, threads);
+        if (o.act == PINNK_ACT_TANH)
+          act_bwd_kernel<1, MAXK><<<blocks, threads, 0, c.st>>>(in, S, c.adj(cur), c.n, o.in_dim, js, 1.f);
+        else
+          act_bwd_kernel<2, MAXK><<<blocks, threads, 0, c.st>>>(in, S, c.adj(cur), c.n, o.in_dim, js, o.scale);
+        PK_LAUNCH_OK();
+        if (r.skip_src >= 0) {
+          // dL/dz feeds both the LayerNorm branch and the skip: keep this buffer, continue in a copy
+          const int nxt = other(cur, -1);
+          PK_CHECK_CUDA(cudaMemcpyAsync(c.adj(nxt), c.adj(cur), sizeof(float) * c.n * js.ncols * o.in_dim,
+                                        cudaMemcpyDeviceToDevice, c.st));
+          held = cur;
+          cur = nxt;
+        }
+        break;
+      }
+      case PINNK_OP_LAYERNORM: {
+        const int nxt = other(cur, held);
+        int rc = ln_bwd<MAXK>(c, in, c.adj(cur), c.adj(nxt), o.in_dim, c.params[o.w_index], o.eps, G(o.gw_offset), G(o.gb_offset));
+        if (rc) return rc;
+        cur = nxt;
+        break;
+      }
+      case PINNK_OP_SKIP_SAVE: {
+        if (held < 0) return fail(PINNK_E_INVALID, "backward: SKIP_SAVE without a held adjoint");
+        const int64_t cnt = c.n * js.ncols * pl->ops[r.in_op].op.out_dim;
+        add_inplace_kernel<<<blocks_for(cnt, threads), threads, 0, c.st>>>(c.adj(cur), c.adj(held), cnt);
+        PK_LAUNCH_OK();
+        held = -1;
+        break;
+      }
+      default: break;   // SKIP_ADD marker, SINCOS (never reached: frozen)
+    }
+  }
+  return 0;
+}
+
+static int check_common(pinnk_plan_t plan, const float* const* params, const float* x, int64_t n, void* ws, int64_t ws_bytes) {
+  if (!plan) return fail(PINNK_E_INVALID, "null plan");
+  if (!params || !x) return fail(PINNK_E_INVALID, "null params / x");
+  if (n < 0) return fail(PINNK_E_INVALID, "negative row count");
+  if (!ws || ws_bytes < plan->ws_bytes) return fail(PINNK_E_WORKSPACE, "workspace smaller than pinnk_plan_workspace_bytes()");
+  return 0;
+}
+
+static ChunkCtx make_ctx(pinnk_plan_t plan, const float* const* params, const float* x, const float* t, int64_t p0,
+                         int64_t cn, void* ws, void* stream) {
+  ChunkCtx c;
+  c.pl = plan; c.params = params; c.ws = (float*)ws; c.st = (cudaStream_t)stream; c.n = cn;
+  const int d = plan->js.in_dim;
+  c.x = t ? x + p0 * (d - 1) : x + p0 * d;
+  c.t = t ? t + p0 : nullptr;
+  return c;
+}
+
+extern "C" int pinnk_jets_forward(pinnk_plan_t plan, const float* const* params, const float* x, const float* t,
+                                  int64_t n, float* out_jets, void* ws, int64_t ws_bytes, void* stream) {
+  int rc = check_common(plan, params, x, n, ws, ws_bytes);
+  if (rc) return rc;
+  if (!out_jets) return fail(PINNK_E_INVALID, "null out_jets");
+  const int C = plan->js.ncols;
+  for (int64_t p0 = 0; p0 < n; p0 += plan->chunk) {
+    const int64_t cn = std::min(plan->chunk, n - p0);
+    ChunkCtx c = make_ctx(plan, params, x, t, p0, cn, ws, stream);
+    rc = dispatch_maxk(plan->maxk, [&](auto mk) { return forward_chunk<decltype(mk)::value>(c); });
+    if (rc) return rc;
+    PK_CHECK_CUDA(cudaMemcpyAsync(out_jets + p0 * C, c.U(), sizeof(float) * cn * C, cudaMemcpyDeviceToDevice, c.st));
+  }
+  return 0;
+}
+
+extern "C" int pinnk_jets_vjp(pinnk_plan_t plan, const float* const* params, const float* x, const float* t,
+                              int64_t n, const float* adj_jets, float* flat_grad, void* ws, int64_t ws_bytes,
+                              void* stream) {
+  int rc = check_common(plan, params, x, n, ws, ws_bytes);
+  if (rc) return rc;
+  if (!adj_jets || !flat_grad) return fail(PINNK_E_INVALID, "null adj_jets / flat_grad");
+  const int C = plan->js.ncols;
+  for (int64_t p0 = 0; p0 < n; p0 += plan->chunk) {
+    const int64_t cn = std::min(plan->chunk, n - p0);
+    ChunkCtx c = make_ctx(plan, params, x, t, p0, cn, ws, stream);
+    rc = dispatch_maxk(plan->maxk, [&](auto mk) { return forward_chunk<decltype(mk)::value>(c); });
+    if (rc) return rc;
+    PK_CHECK_CUDA(cudaMemcpyAsync(c.Ub(), adj_jets + p0 * C, sizeof(float) * cn * C, cudaMemcpyDeviceToDevice, c.st));
+    rc = dispatch_maxk(plan->maxk, [&](auto mk) { return backward_chunk<decltype(mk)::value>(c, flat_grad); });
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" int pinnk_loss_step(pinnk_plan_t plan, const float* const* params, const float* x, const float* t,
+                               int64_t n, const PinnkSegment* segs, int32_t n_segs, const float* grad_scale,
+                               double* loss_sums, float* flat_grad, void* ws, int64_t ws_bytes, void* stream) {
+  int rc = check_common(plan, params, x, n, ws, ws_bytes);
+  if (rc) return rc;
+  if (!segs || n_segs < 1) return fail(PINNK_E_INVALID, "loss_step: no segments");
+  const int C = plan->js.ncols;
+  for (int s = 0; s < n_segs; ++s) {
+    const PinnkSegment& g = segs[s];
+    if (g.row_start < 0 || g.row_count < 0 || g.row_start + g.row_count > n)
+      return fail(PINNK_E_INVALID, "loss_step: segment rows out of range");
+    if (g.pair_offset != 0) {
+      if (n > plan->chunk) return fail(PINNK_E_INVALID, "loss_step: paired segments need n <= chunk_points");
+      if (g.pair_offset < g.row_count || g.row_start + g.pair_offset + g.row_count > n)
+        return fail(PINNK_E_INVALID, "loss_step: pair_offset must address a disjoint row range inside the call");
+    }
+  }
+  const int threads = 256;
+  for (int64_t p0 = 0; p0 < n; p0 += plan->chunk) {
+    const int64_t cn = std::min(plan->chunk, n - p0);
+    ChunkCtx c = make_ctx(plan, params, x, t, p0, cn, ws, stream);
+    rc = dispatch_maxk(plan->maxk, [&](auto mk) { return forward_chunk<decltype(mk)::value>(c); });
+    if (rc) return rc;
+    if (flat_grad) PK_CHECK_CUDA(cudaMemsetAsync(c.Ub(), 0, sizeof(float) * cn * C, c.st));
+    for (int s = 0; s < n_segs; ++s) {
+      const PinnkSegment& g = segs[s];
+      const int64_t lo = std::max(g.row_start, p0), hi = std::min(g.row_start + g.row_count, p0 + cn);
+      if (lo >= hi) continue;
+      SegmentDev sd;
+      sd.pde.kind = g.pde.kind; sd.pde.compat_math = g.pde.compat_math; sd.pde.p0 = g.pde.p0; sd.pde.p1 = g.pde.p1;
+      sd.loss_kind = g.loss_kind; sd.huber_delta = g.huber_delta; sd.weight = g.weight;
+      sd.grad_weight = flat_grad ? g.weight * (grad_scale ? grad_scale[g.component] : 1.f) : 0.f;
+      sd.row_start = g.row_start; sd.row_count = g.row_count; sd.pair_offset = g.pair_offset;
+      sd.target = g.target; sd.error_out = g.error_out; sd.error_grad = flat_grad ? g.error_grad : nullptr;
+      sd.loss_slot = loss_sums ? loss_sums + g.component : nullptr;
+      epilogue_kernel<<<blocks_for(hi - lo, threads), threads, 0, c.st>>>(c.U(), flat_grad ? c.Ub() : nullptr, plan->js, sd, p0, lo, hi);
+      PK_LAUNCH_OK();
+    }
+    if (flat_grad) {
+      rc = dispatch_maxk(plan->maxk, [&](auto mk) { return backward_chunk<decltype(mk)::value>(c, flat_grad); });
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
+extern "C" int pinnk_score(pinnk_plan_t plan, const float* const* params, const float* x, const float* t, int64_t n,
+                           const PinnkPde* pde, float* abs_out, double* stats, void* ws, int64_t ws_bytes, void* stream) {
+  int rc = check_common(plan, params, x, n, ws, ws_bytes);
+  if (rc) return rc;
+  if (!pde || !stats) return fail(PINNK_E_INVALID, "score: null pde / stats");
+  PdeDesc pd;
+  pd.kind = pde->kind; pd.compat_math = pde->compat_math; pd.p0 = pde->p0; pd.p1 = pde->p1;
+  const int threads = 256;
+  for (int64_t p0 = 0; p0 < n; p0 += plan->chunk) {
+    const int64_t cn = std::min(plan->chunk, n - p0);
+    ChunkCtx c = make_ctx(plan, params, x, t, p0, cn, ws, stream);
+    rc = dispatch_maxk(plan->maxk, [&](auto mk) { return forward_chunk<decltype(mk)::value>(c); });
+    if (rc) return rc;
+    score_kernel<<<blocks_for(cn, threads), threads, 0, c.st>>>(c.U(), plan->js, pd, cn, abs_out ? abs_out + p0 : nullptr, stats);
+    PK_LAUNCH_OK();
+  }
+  return 0;
+}
