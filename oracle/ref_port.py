@@ -450,11 +450,14 @@ def base_compute_loss(model, residual, domain, time_domain, bc_fns: Dict[str, Ca
     tb = torch.linspace(time_domain[0], time_domain[1], 100, device=dev).reshape(-1, 1)
     xb = xb.repeat_interleave(len(tb), dim=0)
     tb = tb.repeat(len(xb) // len(tb), 1)
+    # points are generated in float32 like the reference; the cast is a no-op there and lets the
+    # same points drive an fp64 evaluation of the oracle
+    xb, tb = xb.to(residual.dtype), tb.to(residual.dtype)
     b_loss = torch.tensor(0.0, device=dev)
     for fn in bc_fns.values():
         ub = model(torch.cat([xb, tb], dim=1))
         b_loss = b_loss + apply_loss_fn(ub - fn(xb, tb), loss_fn, delta)
-    xi = torch.linspace(domain[0][0], domain[0][1], 100, device=dev).reshape(-1, 1)
+    xi = torch.linspace(domain[0][0], domain[0][1], 100, device=dev).reshape(-1, 1).to(residual.dtype)
     ti = torch.zeros_like(xi)
     ui = model(torch.cat([xi, ti], dim=1))
     i_loss = apply_loss_fn(ui - bc_fns["initial"](xi, ti), loss_fn, delta)
@@ -492,15 +495,15 @@ def heat_compute_loss(model, residual, domain, time_domain, ic_fn, num_boundary,
     res_loss = apply_loss_fn(residual, loss_fn, delta)
     tb = heat_boundary_points(domain, time_domain, num_boundary, dev)
     x_min, x_max = domain[0]
-    pl = torch.cat([torch.full((num_boundary, 1), x_min, device=dev), tb], dim=1).requires_grad_(True)
-    pr = torch.cat([torch.full((num_boundary, 1), x_max, device=dev), tb], dim=1).requires_grad_(True)
+    pl = torch.cat([torch.full((num_boundary, 1), x_min, device=dev), tb], dim=1).to(residual.dtype).requires_grad_(True)
+    pr = torch.cat([torch.full((num_boundary, 1), x_max, device=dev), tb], dim=1).to(residual.dtype).requires_grad_(True)
     ul, ur = model(pl), model(pr)
     dl = torch.autograd.grad(ul, pl, torch.ones_like(ul), create_graph=True)[0][:, 0:1]
     dr = torch.autograd.grad(ur, pr, torch.ones_like(ur), create_graph=True)[0][:, 0:1]
     b_loss = torch.tensor(0.0, device=dev)
     b_loss = b_loss + apply_loss_fn(ul - ur, loss_fn, delta)
     b_loss = b_loss + apply_loss_fn(dl - dr, loss_fn, delta)
-    xi = heat_initial_points(domain, num_initial, dev)
+    xi = heat_initial_points(domain, num_initial, dev).to(residual.dtype)
     ti = torch.zeros_like(xi)
     ui = model(torch.cat([xi, ti], dim=1))
     i_loss = apply_loss_fn(ui - ic_fn(xi, ti), loss_fn, delta)

@@ -1,0 +1,21 @@
+"""pinns_rl_pde_b200 -- B200-native hot path of pinnrl (PINNs + RL adaptive sampling for PDEs).
+
+MLP forward with forward-mode derivative jets, PDE residual, fused loss and the hand-written
+reverse pass, behind the reference's PINNModel / PDE / PDETrainer API.  All arithmetic runs in
+libpinnk.so (CUDA, sm_100a); there is no CPU or PyTorch fallback.
+"""
+from . import _lib
+from .functional import (compute_loss, compute_residual, jets, loss_and_flat_grad, model_forward,
+                         score_residual)
+from .neural_networks import (Config, FeedForwardNetwork, FourierNetwork, ModelConfig, PINNModel, ResNet,
+                              SIREN, make_model)
+from .pdes import (AllenCahnEquation, BurgersEquation, CahnHilliardEquation, HeatEquation, KdVEquation,
+                   PDEBase, PDEConfig, create_pde)
+from .training import PDETrainer, TrainingConfig
+from .dropin import patch_reference
+
+__all__ = ["compute_loss", "compute_residual", "jets", "loss_and_flat_grad", "model_forward", "score_residual",
+           "Config", "ModelConfig", "PINNModel", "FeedForwardNetwork", "ResNet", "SIREN", "FourierNetwork",
+           "make_model", "PDEConfig", "PDEBase", "HeatEquation", "BurgersEquation", "KdVEquation",
+           "AllenCahnEquation", "CahnHilliardEquation", "create_pde", "PDETrainer", "TrainingConfig",
+           "patch_reference"]

@@ -1,0 +1,99 @@
+"""ctypes binding of libpinnk.so (include/pinnk.h).  There is no fallback: if the CUDA library
+is missing or a call fails, the caller gets an exception."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpinnk.so")
+
+OP_LINEAR, OP_ACT, OP_LAYERNORM, OP_SKIP_SAVE, OP_SKIP_ADD, OP_SINCOS = 1, 2, 3, 4, 5, 6
+ACT_TANH, ACT_SIN = 1, 2
+(PDE_HEAT, PDE_BURGERS, PDE_KDV, PDE_ALLEN_CAHN, PDE_CAHN_HILLIARD, PDE_UT_ONLY, PDE_UT_ALLEN_CAHN_ND,
+ PDE_CAHN_HILLIARD_2D, PDE_VALUE, PDE_DX) = range(10)
+LOSS_MSE, LOSS_MAE, LOSS_HUBER = 0, 1, 2
+ABI_VERSION = 1
+
+
+class PinnkOp(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("in_dim", C.c_int32), ("out_dim", C.c_int32), ("act", C.c_int32),
+                ("scale", C.c_float), ("eps", C.c_float), ("w_index", C.c_int32), ("b_index", C.c_int32),
+                ("w_transposed", C.c_int32), ("reserved", C.c_int32), ("gw_offset", C.c_int64),
+                ("gb_offset", C.c_int64)]
+
+
+class PinnkJetSpec(C.Structure):
+    _fields_ = [("ndirs", C.c_int32), ("order", C.c_int32 * 5), ("vec", (C.c_float * 4) * 5)]
+
+
+class PinnkPde(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("compat_math", C.c_int32), ("p0", C.c_float), ("p1", C.c_float)]
+
+
+class PinnkSegment(C.Structure):
+    _fields_ = [("pde", PinnkPde), ("component", C.c_int32), ("loss_kind", C.c_int32),
+                ("huber_delta", C.c_float), ("weight", C.c_float), ("row_start", C.c_int64),
+                ("row_count", C.c_int64), ("pair_offset", C.c_int64), ("target", C.c_void_p),
+                ("error_out", C.c_void_p), ("error_grad", C.c_void_p)]
+
+
+EXPORTS = ["pinnk_plan_create", "pinnk_plan_destroy", "pinnk_plan_workspace_bytes", "pinnk_plan_ncols",
+           "pinnk_plan_grad_floats", "pinnk_jets_forward", "pinnk_jets_vjp", "pinnk_loss_step", "pinnk_score",
+           "pinnk_last_error", "pinnk_abi_version", "pinnk_launch_count"]
+
+_lib = None
+
+
+class PinnkError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libpinnk.so or raise.  Never substitutes another implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PinnkError(f"{LIB_PATH} not found: build it with `python -m pinns_rl_pde_b200.build` "
+                         "(there is no CPU or PyTorch fallback for this path)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int32
+    lib.pinnk_plan_create.argtypes = [C.POINTER(PinnkOp), i32, i32, C.POINTER(PinnkJetSpec), i64, i32, C.POINTER(vp)]
+    lib.pinnk_plan_create.restype = C.c_int
+    lib.pinnk_plan_destroy.argtypes = [vp]
+    lib.pinnk_plan_destroy.restype = None
+    lib.pinnk_plan_workspace_bytes.argtypes = [vp]
+    lib.pinnk_plan_workspace_bytes.restype = i64
+    lib.pinnk_plan_ncols.argtypes = [vp]
+    lib.pinnk_plan_ncols.restype = i32
+    lib.pinnk_plan_grad_floats.argtypes = [vp]
+    lib.pinnk_plan_grad_floats.restype = i64
+    lib.pinnk_jets_forward.argtypes = [vp, vp, vp, vp, i64, vp, vp, i64, vp]
+    lib.pinnk_jets_forward.restype = C.c_int
+    lib.pinnk_jets_vjp.argtypes = [vp, vp, vp, vp, i64, vp, vp, vp, i64, vp]
+    lib.pinnk_jets_vjp.restype = C.c_int
+    lib.pinnk_loss_step.argtypes = [vp, vp, vp, vp, i64, C.POINTER(PinnkSegment), i32, vp, vp, vp, vp, i64, vp]
+    lib.pinnk_loss_step.restype = C.c_int
+    lib.pinnk_score.argtypes = [vp, vp, vp, vp, i64, C.POINTER(PinnkPde), vp, vp, vp, i64, vp]
+    lib.pinnk_score.restype = C.c_int
+    lib.pinnk_last_error.argtypes = []
+    lib.pinnk_last_error.restype = C.c_char_p
+    lib.pinnk_abi_version.argtypes = []
+    lib.pinnk_abi_version.restype = i32
+    lib.pinnk_launch_count.argtypes = []
+    lib.pinnk_launch_count.restype = i64
+    if lib.pinnk_abi_version() != ABI_VERSION:
+        raise PinnkError(f"libpinnk.so ABI {lib.pinnk_abi_version()} != binding {ABI_VERSION}: rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().pinnk_last_error()
+        raise PinnkError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+def launch_count() -> int:
+    return int(load().pinnk_launch_count())

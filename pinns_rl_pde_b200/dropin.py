@@ -1,0 +1,48 @@
+"""Swap the B200 hot path into an installed ``pinnrl`` (the reference) in place.
+
+    import pinns_rl_pde_b200 as pk
+    pk.patch_reference()          # pinnrl's PDE classes now evaluate residual / loss on libpinnk
+
+After patching, the reference's own ``PDETrainer``, RAR sampler and live snapshot run unchanged on
+top of the CUDA path (they only call ``compute_residual`` / ``compute_loss``).
+Models must be one of the four hot-path architectures and live on a CUDA device.
+"""
+from __future__ import annotations
+
+import importlib
+
+from . import functional as F
+
+_PATCHED = {}
+
+
+def patch_reference(compat: str = "reference"):
+    mods = {"heat_equation": "HeatEquation", "burgers_equation": "BurgersEquation", "kdv_equation": "KdVEquation",
+            "allen_cahn": "AllenCahnEquation", "cahn_hilliard": "CahnHilliardEquation"}
+    try:
+        base = importlib.import_module("pinnrl.pdes.pde_base")
+    except ImportError as e:   # pragma: no cover - pinnrl is not installed on the GPU box
+        raise ImportError("patch_reference() needs the reference package `pinnrl` importable") from e
+    for mod, cls_name in mods.items():
+        cls = getattr(importlib.import_module(f"pinnrl.pdes.{mod}"), cls_name)
+        if cls in _PATCHED:
+            continue
+        _PATCHED[cls] = (cls.__dict__.get("compute_residual"), cls.__dict__.get("compute_loss"))
+        cls.compat = compat
+        cls.compute_residual = lambda self, model, x, t: F.compute_residual(self, model, x, t)
+        cls.compute_loss = lambda self, model, x, t: F.compute_loss(self, model, x, t)
+    return sorted(c.__name__ for c in _PATCHED)
+
+
+def unpatch_reference():
+    for cls, (res, loss) in list(_PATCHED.items()):
+        if res is not None:
+            cls.compute_residual = res
+        if loss is not None:
+            cls.compute_loss = loss
+        else:
+            try:
+                del cls.compute_loss
+            except AttributeError:
+                pass
+        _PATCHED.pop(cls)

@@ -1,0 +1,406 @@
+"""Drop-in implementations of the reference's hot-path calls on top of libpinnk.
+
+    compute_residual(pde, model, x, t)   ->  PDEBase.compute_residual      (pde_base.py:577-588 + overrides)
+    compute_loss(pde, model, x, t)       ->  PDEBase.compute_loss          (pde_base.py:1086-1235)
+                                             HeatEquation.compute_loss     (heat_equation.py:375-623)
+    model_forward(model, xt)             ->  PINNModel.forward             (neural_networks/__init__.py:144-154)
+    score_residual(pde, model, x, t)     ->  |compute_residual| for RAR / RL sampling (pde_base.py:909-921,1364-1377)
+
+``pde`` is duck-typed: the reference's own PDE objects and this package's mirrors both work
+(class name, ``dimension``, ``domain``, ``time_domain``, ``config``, ``boundary_conditions``).
+Every returned tensor carries an autograd graph to the model parameters whose backward is the
+hand-written reverse pass; torch autograd never differentiates through the network itself.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .engine import Segment, get_engine, get_program
+
+_PDE_NAMES = {
+    "HeatEquation": "heat", "BurgersEquation": "burgers", "KdVEquation": "kdv",
+    "AllenCahnEquation": "allen_cahn", "CahnHilliardEquation": "cahn_hilliard",
+}
+_ORDER_1D = {"burgers": 2, "kdv": 3, "allen_cahn": 2, "cahn_hilliard": 4}
+_KIND_1D = {"heat": L.PDE_HEAT, "burgers": L.PDE_BURGERS, "kdv": L.PDE_KDV,
+            "allen_cahn": L.PDE_ALLEN_CAHN, "cahn_hilliard": L.PDE_CAHN_HILLIARD}
+
+
+class UnsupportedPDE(NotImplementedError):
+    pass
+
+
+def pde_name(pde) -> str:
+    for klass in type(pde).__mro__:
+        if klass.__name__ in _PDE_NAMES:
+            return _PDE_NAMES[klass.__name__]
+    raise UnsupportedPDE(f"{type(pde).__name__} is not on the B200 hot path "
+                         f"(supported: {sorted(_PDE_NAMES)})")
+
+
+def _float_param(pde, name: str, default=None) -> float:
+    if hasattr(pde, "get_parameter"):
+        v = pde.get_parameter(name, default=default)
+    else:
+        v = getattr(pde, name, default)
+    if isinstance(v, torch.Tensor):
+        if v.requires_grad:
+            raise UnsupportedPDE("trainable PDE parameters (inverse mode) are not supported by the fused path")
+        v = float(v.detach().cpu())
+    if v is None:
+        raise ValueError(f"Required parameter '{name}' not found in config")
+    return float(v)
+
+
+def residual_spec(pde) -> Tuple[List, int, float, int]:
+    """(directions, PINNK_PDE kind, p0, compat_math) for ``pde`` -- the jets its residual needs."""
+    name = pde_name(pde)
+    d = int(pde.dimension)
+    compat = getattr(pde, "compat", "reference")
+    if compat not in ("reference", "math"):
+        raise ValueError("pde.compat must be 'reference' or 'math'")
+    p0 = {"heat": lambda: _float_param(pde, "alpha"), "burgers": lambda: _float_param(pde, "nu", 0.01),
+          "kdv": lambda: 0.0, "allen_cahn": lambda: _float_param(pde, "epsilon", 0.1),
+          "cahn_hilliard": lambda: _float_param(pde, "epsilon", 0.1)}[name]()
+    unit = lambda i: tuple(1.0 if k == i else 0.0 for k in range(d + 1))
+    t_dir = (unit(d), 1)
+    if d == 1:
+        if name == "heat":
+            math = compat == "math"
+            return [(unit(0), 2 if math else 1), t_dir], L.PDE_HEAT, p0, int(math)
+        return [(unit(0), _ORDER_1D[name]), t_dir], _KIND_1D[name], p0, 0
+    if compat == "reference":
+        # as written, every spatial derivative of a multi-dim residual is identically zero
+        kind = L.PDE_UT_ALLEN_CAHN_ND if name == "allen_cahn" else L.PDE_UT_ONLY
+        return [t_dir], kind, p0, 0
+    if name == "cahn_hilliard" and d == 2:
+        dirs = [((1.0, 0.0, 0.0), 4), ((0.0, 1.0, 0.0), 4), ((1.0, 1.0, 0.0), 4), ((1.0, -1.0, 0.0), 4), t_dir]
+        return dirs, L.PDE_CAHN_HILLIARD_2D, p0, 0
+    raise UnsupportedPDE(f"compat='math' is not implemented for {name} in {d} dimensions")
+
+
+def _loss_kind(pde) -> Tuple[int, float]:
+    name = pde._loss_function_name() if hasattr(pde, "_loss_function_name") else "mse"
+    delta = pde._huber_delta() if hasattr(pde, "_huber_delta") else 1.0
+    return {"mae": L.LOSS_MAE, "huber": L.LOSS_HUBER}.get(name, L.LOSS_MSE), float(delta)
+
+
+def _trainable(model: nn.Module) -> List[nn.Parameter]:
+    return get_program(model).grad_params
+
+
+def _prep(model: nn.Module, x: torch.Tensor, t: Optional[torch.Tensor]):
+    dev = next(model.parameters()).device
+    x = x.detach().to(device=dev, dtype=torch.float32)
+    if t is not None:
+        t = t.detach().to(device=dev, dtype=torch.float32)
+    return x, t
+
+
+# ------------------------------------------------------------------ autograd bridges
+class _ErrorFn(torch.autograd.Function):
+    """e[rows] of one segment prototype; backward = reverse pass seeded with dL/de."""
+
+    @staticmethod
+    def forward(ctx, engine, proto: Segment, x, t, *params):
+        e = torch.empty(proto.row_count, dtype=torch.float32, device=x.device)
+        seg = Segment(**{**proto.__dict__, "error_out": e})
+        engine.loss_step(x, t, [seg], 1, want_grad=False)
+        ctx.engine, ctx.proto, ctx.x, ctx.t = engine, proto, x, t
+        return e.view(-1, 1)
+
+    @staticmethod
+    def backward(ctx, ge):
+        ge = ge.reshape(-1).to(torch.float32).contiguous()
+        seg = Segment(**{**ctx.proto.__dict__, "error_grad": ge})
+        _, flat = ctx.engine.loss_step(ctx.x, ctx.t, [seg], 1, want_grad=True)
+        grads = ctx.engine.program.split_flat(flat)
+        return (None, None, None, None, *grads)
+
+
+class _JetsFn(torch.autograd.Function):
+    """Output jets U[n, C]; backward = reverse pass seeded with dL/dU."""
+
+    @staticmethod
+    def forward(ctx, engine, x, t, *params):
+        ctx.engine, ctx.x, ctx.t = engine, x, t
+        return engine.jets_forward(x, t)
+
+    @staticmethod
+    def backward(ctx, gU):
+        flat = ctx.engine.jets_vjp(ctx.x, ctx.t, gU.to(torch.float32).contiguous())
+        return (None, None, None, *ctx.engine.program.split_flat(flat))
+
+
+class _LossFn(torch.autograd.Function):
+    """Component losses [n_components] with the per-component gradients computed eagerly."""
+
+    @staticmethod
+    def forward(ctx, calls, n_components, program, *params):
+        dev = calls[0][1].device
+        want_grad = any(ctx.needs_input_grad[3:])
+        sums = torch.zeros(n_components, dtype=torch.float64, device=dev)
+        G = torch.zeros(n_components, program.grad_floats, dtype=torch.float32, device=dev) if want_grad else None
+        for engine, x, t, segments in calls:
+            comp = segments[0].component
+            assert all(s.component == comp for s in segments)
+            engine.loss_step(x, t, segments, n_components, want_grad, None,
+                             G[comp] if want_grad else None, sums)
+        ctx.G, ctx.program = G, program
+        return sums.to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        flat = (g.to(torch.float32).unsqueeze(0) @ ctx.G).squeeze(0)
+        return (None, None, None, *ctx.program.split_flat(flat))
+
+
+# ------------------------------------------------------------------ public functions
+def jets(model: nn.Module, xt: torch.Tensor, directions: Sequence) -> torch.Tensor:
+    """Differentiable (w.r.t. parameters) output jets of the network: column 0 = u, then the
+    normalised Taylor coefficients along each direction."""
+    xt, _ = _prep(model, xt, None)
+    eng = get_engine(model, directions, xt.shape[0])
+    return _JetsFn.apply(eng, xt, None, *_trainable(model))
+
+
+def model_forward(model: nn.Module, xt: torch.Tensor) -> torch.Tensor:
+    """``model(xt)`` -> [n, 1] through the CUDA path (value column only)."""
+    return jets(model, xt, [])
+
+
+def compute_residual(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
+    dirs, kind, p0, cm = residual_spec(pde)
+    x, t = _prep(model, x, t)
+    n = x.shape[0]
+    eng = get_engine(model, dirs, n)
+    proto = Segment(kind=kind, row_start=0, row_count=n, p0=p0, compat_math=cm)
+    model.train()   # pde_base.py:638 -- the reference flips the model into training mode here
+    return _ErrorFn.apply(eng, proto, x, t, *_trainable(model))
+
+
+def score_residual(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, want_abs: bool = True,
+                   stats: Optional[torch.Tensor] = None):
+    """Forward-only |r| [n] and stats [sum|r|, sum r^2, max|r|, count] (fp64 on device)."""
+    dirs, kind, p0, cm = residual_spec(pde)
+    x, t = _prep(model, x, t)
+    eng = get_engine(model, dirs, x.shape[0])
+    return eng.score(x, t, kind, p0, cm, want_abs, stats)
+
+
+def _weights(pde, heat: bool) -> Tuple[float, float, float, float, bool]:
+    """(w_res, w_bc, w_ic, w_smooth, adaptive) exactly as the reference resolves them."""
+    training = getattr(pde.config, "training", None)
+    if heat:
+        if training is None:
+            return 1.0, 10.0, 10.0, 0.0, False
+        if isinstance(training, dict):
+            lw = training.get("loss_weights", {})
+            aw = training.get("adaptive_weights", {})
+            adaptive = aw.get("enabled", False) if isinstance(aw, dict) else False
+        else:
+            lw = getattr(training, "loss_weights", {}) or {}
+            aw = getattr(training, "adaptive_weights", None)
+            adaptive = bool(getattr(aw, "enabled", False)) if aw is not None else False
+        if isinstance(lw, dict):
+            return (lw.get("pde", lw.get("residual", 1.0)), lw.get("boundary", 10.0), lw.get("initial", 10.0),
+                    lw.get("smoothness", 0.0), adaptive)
+        return (getattr(lw, "pde", getattr(lw, "residual", 1.0)), getattr(lw, "boundary", 10.0),
+                getattr(lw, "initial", 10.0), getattr(lw, "smoothness", 0.0), adaptive)
+    # base class (pde_base.py:1171-1224): hasattr probes fail on plain dicts
+    smooth = 0.0
+    if hasattr(training, "loss_weights") and training.loss_weights:
+        smooth = training.loss_weights.get("smoothness", 0.0)
+    adaptive = (training is not None and hasattr(training, "adaptive_weights")
+                and training.adaptive_weights.enabled)
+    if training is not None and hasattr(training, "loss_weights") and training.loss_weights:
+        lw = training.loss_weights
+        return lw.get("pde", lw.get("residual", 1.0)), lw.get("boundary", 10.0), lw.get("initial", 10.0), smooth, adaptive
+    return 1.0, 10.0, 10.0, smooth, adaptive
+
+
+def _data_loss(pde, model) -> torch.Tensor:
+    obs = getattr(pde, "observation_data", None)
+    dev = next(model.parameters()).device
+    if not obs:
+        return torch.tensor(0.0, device=dev)
+    u = model_forward(model, torch.cat([obs["x"], obs["t"]], dim=1))
+    return pde._apply_loss_fn(u - obs["u"].to(dev))
+
+
+def loss_components(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_global: Optional[int] = None):
+    """The three physics components [residual, boundary, initial] as one differentiable tensor, plus the
+    weights the reference would combine them with.  ``n_global``: number of collocation rows of the whole
+    (possibly sharded) batch -- the reference derives default BC/IC point counts from it."""
+    name = pde_name(pde)
+    heat = name == "heat"
+    dim = int(pde.dimension)
+    if not heat and dim != 1:
+        # the reference builds 2-column boundary points for a (dim+1)-input model and dies in mm
+        raise RuntimeError(f"compute_loss: boundary points have 2 columns but the model takes {dim + 1} "
+                           "(the reference's PDEBase.compute_loss fails the same way for dimension >= 2)")
+    dirs, kind, p0, cm = residual_spec(pde)
+    x, t = _prep(model, x, t)
+    dev = x.device
+    n = x.shape[0]
+    ng = n if n_global is None else int(n_global)
+    lk, delta = _loss_kind(pde)
+    mk = dict(loss_kind=lk, huber_delta=delta)
+    model.train()
+    calls = []
+    eng_r = get_engine(model, dirs, n)
+    calls.append((eng_r, x, t, [Segment(kind=kind, row_start=0, row_count=n, component=0, weight=1.0 / max(n, 1),
+                                        p0=p0, compat_math=cm, **mk)]))
+    dom, td = pde.domain, pde.time_domain
+    if heat:
+        training = getattr(pde.config, "training", None)
+        if training is not None:
+            if isinstance(training, dict):
+                nb = training.get("num_boundary_points", training.get("num_collocation_points", ng) // 10)
+                ni = training.get("num_initial_points", training.get("num_collocation_points", ng) // 5)
+            else:
+                nb = getattr(training, "num_boundary_points", training.num_collocation_points // 10)
+                ni = getattr(training, "num_initial_points", training.num_collocation_points // 5)
+        else:
+            nb, ni = max(ng // 10, 10), max(ng // 5, 10)
+        t_max = pde.config.time_domain[1]
+        t_early = t_max * 0.01
+        n_early = max(nb // 4, 1)
+        tb = torch.cat([torch.linspace(0, t_early, n_early, device=dev),
+                        torch.linspace(t_early, t_max, nb - n_early, device=dev)]).reshape(-1, 1)
+        if dim == 1:
+            x_min, x_max = pde.config.domain[0]
+            pts = torch.cat([torch.cat([torch.full((nb, 1), x_min, device=dev), tb], dim=1),
+                             torch.cat([torch.full((nb, 1), x_max, device=dev), tb], dim=1)], dim=0)
+            eng_b = get_engine(model, [((1.0, 0.0), 1)], 2 * nb)
+            calls.append((eng_b, pts, None, [
+                Segment(kind=L.PDE_VALUE, row_start=0, row_count=nb, component=1, weight=1.0 / nb, pair_offset=nb, **mk),
+                Segment(kind=L.PDE_DX, row_start=0, row_count=nb, component=1, weight=1.0 / nb, pair_offset=nb, **mk)]))
+            xb10 = (x_max - x_min) * 0.1
+            xi = torch.cat([torch.linspace(x_min, x_min + xb10, ni // 4, device=dev),
+                            torch.linspace(x_min + xb10, x_max - xb10, ni // 2, device=dev),
+                            torch.linspace(x_max - xb10, x_max, ni // 4, device=dev)]).reshape(-1, 1)
+            ti = torch.zeros_like(xi)
+            if "initial" in pde.boundary_conditions:
+                target = pde.boundary_conditions["initial"](xi, ti)
+            else:
+                target = torch.sin(pde.config.initial_condition.get("frequency", 2.0) * torch.pi * xi)
+        else:
+            per_axis = max(nb // (2 * dim), 1)
+            lo_pts, hi_pts = [], []
+            for axis in range(dim):
+                free = torch.empty(per_axis, dim, device=dev)
+                for d in range(dim):
+                    lo, hi = pde.config.domain[d]
+                    free[:, d] = torch.rand(per_axis, device=dev) * (hi - lo) + lo
+                t_axis = torch.rand(per_axis, 1, device=dev) * (td[1] - td[0]) + td[0]
+                cmin, cmax = free.clone(), free.clone()
+                cmin[:, axis], cmax[:, axis] = pde.config.domain[axis]
+                lo_pts.append(torch.cat([cmin, t_axis], dim=1))
+                hi_pts.append(torch.cat([cmax, t_axis], dim=1))
+            pts = torch.cat(lo_pts + hi_pts, dim=0)
+            eng_b = get_engine(model, [], pts.shape[0])
+            calls.append((eng_b, pts, None, [
+                Segment(kind=L.PDE_VALUE, row_start=a * per_axis, row_count=per_axis, component=1,
+                        weight=1.0 / per_axis, pair_offset=dim * per_axis, **mk) for a in range(dim)]))
+            xi = torch.empty(ni, dim, device=dev)
+            for d in range(dim):
+                lo, hi = pde.config.domain[d]
+                xi[:, d] = torch.rand(ni, device=dev) * (hi - lo) + lo
+            ti = torch.zeros(ni, 1, device=dev)
+            if "initial" in pde.boundary_conditions:
+                target = pde.boundary_conditions["initial"](xi, ti)
+            else:
+                k = pde.config.initial_condition.get("frequency", 2.0)
+                target = torch.ones(ni, 1, device=dev)
+                for d in range(dim):
+                    target = target * torch.sin(k * torch.pi * xi[:, d:d + 1])
+        n_i = xi.shape[0]
+        eng_i = get_engine(model, [], n_i)
+        calls.append((eng_i, torch.cat([xi, ti], dim=1), None, [
+            Segment(kind=L.PDE_VALUE, row_start=0, row_count=n_i, component=2, weight=1.0 / max(n_i, 1),
+                    target=target.detach().to(torch.float32).reshape(-1).contiguous(), **mk)]))
+    else:
+        xb = torch.tensor([dom[0][0], dom[0][1]], dtype=torch.float32, device=dev).reshape(-1, 1)
+        tb = torch.linspace(td[0], td[1], 100, device=dev).reshape(-1, 1)
+        xb = xb.repeat_interleave(len(tb), dim=0)
+        tb = tb.repeat(len(xb) // len(tb), 1)
+        nbp = xb.shape[0]
+        segs = []
+        for fn in pde.boundary_conditions.values():
+            tgt = fn(xb, tb).detach().to(torch.float32).reshape(-1).contiguous()
+            segs.append(Segment(kind=L.PDE_VALUE, row_start=0, row_count=nbp, component=1, weight=1.0 / nbp,
+                                target=tgt, **mk))
+        if segs:
+            calls.append((get_engine(model, [], nbp), xb, tb, segs))
+        xi = torch.linspace(dom[0][0], dom[0][1], 100, device=dev).reshape(-1, 1)
+        ti = torch.zeros_like(xi)
+        if "initial" in pde.boundary_conditions:
+            target = pde.boundary_conditions["initial"](xi, ti)
+        else:
+            ic = pde.config.initial_condition
+            if ic.get("type", "sine") == "sine" and "amplitude" in ic and "frequency" in ic:
+                target = ic["amplitude"] * torch.sin(ic["frequency"] * torch.pi * xi)
+            else:
+                target = pde._create_boundary_condition("initial", ic)(xi, ti)
+        calls.append((get_engine(model, [], 100), xi, ti, [
+            Segment(kind=L.PDE_VALUE, row_start=0, row_count=100, component=2, weight=0.01,
+                    target=target.detach().to(torch.float32).reshape(-1).contiguous(), **mk)]))
+
+    program = get_program(model)
+    comp = _LossFn.apply(calls, 3, program, *program.grad_params)
+    return comp, _weights(pde, heat)
+
+
+def compute_loss(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor) -> Dict[str, torch.Tensor]:
+    comp, (w_res, w_bc, w_ic, w_smooth, adaptive) = loss_components(pde, model, x, t)
+    dev = comp.device
+    smooth = torch.tensor(0.0, device=dev)
+    if pde_name(pde) == "heat" and w_smooth > 0:
+        xs, ts = _prep(model, x, t)
+        smooth = _heat_smoothness(pde, model, xs, ts)
+    data = _data_loss(pde, model)
+    data_w = pde._data_loss_weight(1.0) if hasattr(pde, "_data_loss_weight") else 1.0
+    mode = pde._training_mode() if hasattr(pde, "_training_mode") else "forward"
+    active = 0.0 if mode == "data_only" else 1.0
+    if mode in ("inverse", "data_only", "data_augmented") and data_w <= 0.0:
+        data_w = 1.0
+    losses = {"residual": comp[0], "boundary": comp[1], "initial": comp[2], "smoothness": smooth, "data": data}
+    if adaptive:
+        losses["total"] = active * comp[0] + active * comp[1] + active * comp[2] + w_smooth * smooth + data_w * data
+    else:
+        losses["total"] = (active * w_res * comp[0] + active * w_bc * comp[1] + active * w_ic * comp[2]
+                           + w_smooth * smooth + data_w * data)
+    return losses
+
+
+def _heat_smoothness(pde, model, x, t):
+    """heat_equation.py:625-650: finite-difference smoothness regulariser on model values."""
+    eps = 1e-4
+    u_c = model_forward(model, torch.cat([x, t], dim=1))
+    out = torch.tensor(0.0, device=x.device)
+    for d in range(int(pde.dimension)):
+        xp, xm = x.clone(), x.clone()
+        xp[:, d:d + 1] = torch.clamp(x[:, d:d + 1] + eps, pde.domain[d][0], pde.domain[d][1])
+        xm[:, d:d + 1] = torch.clamp(x[:, d:d + 1] - eps, pde.domain[d][0], pde.domain[d][1])
+        u_p = model_forward(model, torch.cat([xp, t], dim=1))
+        u_m = model_forward(model, torch.cat([xm, t], dim=1))
+        out = out + torch.mean(torch.abs((u_p - u_c) / eps)) + torch.mean(torch.abs((u_c - u_m) / eps))
+    return out
+
+
+def loss_and_flat_grad(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor):
+    """compute_loss followed by the gradient of losses['total'] as ONE flat buffer in
+    ``model.parameters()`` order -- the unit that data-parallel ranks all-reduce
+    (trainer.py:578,689 collapsed into one call)."""
+    program = get_program(model)
+    with torch.enable_grad():
+        losses = compute_loss(pde, model, x, t)
+        grads = torch.autograd.grad(losses["total"], program.grad_params, allow_unused=True)
+    flat = torch.cat([(torch.zeros_like(p) if g is None else g).reshape(-1)
+                      for p, g in zip(program.grad_params, grads)])
+    return {k: v.detach() for k, v in losses.items()}, flat

@@ -1,0 +1,78 @@
+"""Data parallelism over collocation rows: one process per GPU, rows sharded by
+rank, weights replicated, ONE all-reduce per step of the flat buffer [grad || loss sums].
+
+The collective is torch.distributed (NCCL over NVLink on the B200 box, gloo in the CPU tests); the
+payload is 0.17-3.2 MB so the step is latency-bound and a single fused buffer is the right shape.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+
+def world_size() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank() -> int:
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def shard_bounds(n: int, r: Optional[int] = None, w: Optional[int] = None) -> Tuple[int, int]:
+    """Rows [lo, hi) of an n-row set owned by rank r of w: contiguous, sizes differ by at most one."""
+    r = rank() if r is None else r
+    w = world_size() if w is None else w
+    base, rem = divmod(n, w)
+    lo = r * base + min(r, rem)
+    return lo, lo + base + (1 if r < rem else 0)
+
+
+def reduce_flat(local_flat: torch.Tensor, local_sums: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """All-reduce(sum) of [flat_grad || loss sums] in one call; returns the two views."""
+    if world_size() == 1:
+        return local_flat, local_sums
+    buf = torch.cat([local_flat.reshape(-1), local_sums.reshape(-1).to(local_flat.dtype)])
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    n = local_flat.numel()
+    return buf[:n].view_as(local_flat), buf[n:].view_as(local_sums)
+
+
+def sharded_loss_backward(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor,
+                          components: Optional[Callable] = None, group=None) -> Dict[str, torch.Tensor]:
+    """Data-parallel compute_loss + backward (trainer.py:578,689 on N GPUs).
+
+    ``x, t`` are the GLOBAL collocation rows (identical on every rank, e.g. drawn from a shared seed).
+    Rank r evaluates residual rows [lo_r, hi_r); the few hundred boundary/initial rows are evaluated on
+    every rank (replicated work, no exchange).  With frac_r = n_r / N the global objective is
+        total = sum_r [ frac_r * w_res * res_r + (w_bc * bc + w_ic * ic) / W ]
+    so each rank differentiates its bracket locally and ONE all-reduce(sum) of
+    [flat_grad || frac_r*res_r || bc/W || ic/W] yields the global gradient and the global components.
+    ``param.grad`` is set to views of the reduced buffer.  ``components`` (tests only) replaces
+    functional.loss_components."""
+    from . import functional as F
+    comp_fn = components or F.loss_components
+    w, r = world_size(), rank()
+    n = x.shape[0]
+    lo, hi = shard_bounds(n, r, w)
+    comp, (w_res, w_bc, w_ic, w_smooth, adaptive) = comp_fn(pde, model, x[lo:hi], t[lo:hi], n_global=n)
+    if w_smooth:
+        raise NotImplementedError("smoothness regulariser is not supported with data parallelism")
+    if adaptive:
+        w_res = w_bc = w_ic = 1.0
+    frac = (hi - lo) / max(n, 1)
+    local = frac * w_res * comp[0] + (w_bc * comp[1] + w_ic * comp[2]) / w
+    params = [p for p in model.parameters() if p.requires_grad]
+    grads = torch.autograd.grad(local, params, allow_unused=True)
+    flat = torch.cat([(torch.zeros_like(p) if g is None else g).reshape(-1) for p, g in zip(params, grads)])
+    sums = torch.stack([frac * comp[0].detach(), comp[1].detach() / w, comp[2].detach() / w]).to(flat.dtype)
+    flat, sums = reduce_flat(flat, sums, group)
+    off = 0
+    for p in params:
+        p.grad = flat[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    zero = torch.zeros((), device=flat.device)
+    return {"residual": sums[0], "boundary": sums[1], "initial": sums[2], "smoothness": zero, "data": zero.clone(),
+            "total": w_res * sums[0] + w_bc * sums[1] + w_ic * sums[2]}

@@ -1,0 +1,75 @@
+"""Shared helpers for the parity tests: load golden fixtures, rebuild models / PDEs from them."""
+import json
+import math
+import os
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
+
+PDES = {
+    "heat": dict(domain=[[0.0, 1.0]], time=[0.0, 1.0], params={"alpha": 0.01},
+                 bcs={"dirichlet": {"type": "dirichlet"}}, ic={"type": "sine", "amplitude": 1.0, "frequency": 2.0},
+                 exact={"type": "sin_exp_decay", "amplitude": 1.0, "frequency": 2.0}),
+    "burgers": dict(domain=[[-1.0, 1.0]], time=[0.0, 1.0], params={"nu": 0.01 / math.pi},
+                    bcs={"dirichlet": {"value": 0.0}}, ic={"type": "sine", "amplitude": -1.0, "frequency": 1.0}, exact={}),
+    "kdv": dict(domain=[[-15.0, 15.0]], time=[0.0, 5.0], params={"speed": 1.0},
+                bcs={"dirichlet": {"value": 0.0}}, ic={"type": "soliton", "speed": 1.0}, exact={}),
+    "cahn_hilliard": dict(domain=[[0.0, 1.0]], time=[0.0, 1.0], params={"epsilon": 0.1},
+                          bcs={"dirichlet": {"value": 0.0}}, ic={"type": "tanh", "epsilon": 0.1}, exact={}),
+    "allen_cahn": dict(domain=[[-1.0, 1.0]], time=[0.0, 1.0], params={"epsilon": 0.1},
+                       bcs={"dirichlet": {"value": 0.0}}, ic={"type": "tanh", "epsilon": 0.1}, exact={}),
+}
+
+
+def fixtures():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+
+
+def load_fixture(tag):
+    z = np.load(os.path.join(GOLDEN, tag + ".npz"))
+    meta = json.loads(str(z["meta"]))
+    state = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w::")}
+    return z, meta, state
+
+
+def rel(a, b):
+    a = torch.as_tensor(np.asarray(a)).double().reshape(-1)
+    b = torch.as_tensor(np.asarray(b)).double().reshape(-1)
+    return float((a - b).norm() / max(float(b.norm()), 1e-300))
+
+
+def port_model(meta, state, dtype=torch.float32, corrected=False):
+    from oracle import ref_port
+    ex = meta["extra"]
+    m = ref_port.PINNModel(meta["arch"], meta["dimension"] + 1, meta["hidden"], meta["layers"], 1, "tanh",
+                           omega_0=ex.get("omega_0", 30.0), mapping_size=ex.get("mapping_size", 32),
+                           scale=ex.get("scale", 10.0), corrected_layernorm=corrected)
+    m.load_state_dict(state)
+    return m.to(dtype)
+
+
+def product_model(meta, state, device):
+    import pinns_rl_pde_b200 as pk
+    ex = dict(meta["extra"])
+    m = pk.make_model(meta["arch"], meta["dimension"] + 1, meta["hidden"], meta["layers"], device, **ex)
+    m.load_state_dict(state)
+    return m
+
+
+def product_pde(name, device, dimension=1, training=None, compat="reference"):
+    import pinns_rl_pde_b200 as pk
+    s = PDES[name]
+    cfg = pk.PDEConfig(name=name, domain=[list(d) for d in s["domain"] * dimension], time_domain=list(s["time"]),
+                       parameters=dict(s["params"]), boundary_conditions={k: dict(v) for k, v in s["bcs"].items()},
+                       initial_condition=dict(s["ic"]), exact_solution=dict(s["exact"]), dimension=dimension,
+                       device=device, training=training)
+    pde = pk.create_pde(name, cfg)
+    pde.compat = compat
+    return pde
+
+
+def flat_grad(model):
+    return torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in model.parameters()])

@@ -1,0 +1,286 @@
+"""GPU parity: the CUDA path (through the C ABI) against
+  (1) the committed golden fixtures generated from the UNMODIFIED reference, and
+  (2) the oracle run on the same seeded inputs at sizes it finishes in seconds.
+
+Tolerance (north_star: 1e-5 relative in fp32): errors are norm-wise and judged against the
+reference evaluated in fp64:  err(cuda, ref64) <= max(1e-5, 2 * err(ref32, ref64)).
+For LayerNorm nets the fp64 target is the corrected oracle.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import PDES, fixtures, flat_grad, load_fixture, port_model, product_model, product_pde, rel
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from pinns_rl_pde_b200 import build
+    build.build()
+    return torch.device("cuda:0")
+
+
+def _tol(z, what):
+    floor = {"residual": rel(z["residual32"], z["residual64"]), "grad": rel(z["grad32"], z["grad64"])}[what]
+    return max(TOL, 2 * floor)
+
+
+@pytest.mark.parametrize("tag", fixtures())
+def test_residual_and_gradient_vs_golden(dev, tag):
+    z, meta, state = load_fixture(tag)
+    model = product_model(meta, state, dev)
+    pde = product_pde(meta["pde"], dev, meta["dimension"])
+    x, t = torch.from_numpy(z["x"]).to(dev), torch.from_numpy(z["t"]).to(dev)
+    r = pde.compute_residual(model, x, t)
+    assert r.shape == (meta["n"], 1) and r.requires_grad
+    has_ln = meta["arch"] == "resnet"
+    want_r = z["residual64_corrected"] if has_ln else z["residual64"]
+    assert rel(r.detach().cpu(), want_r) <= _tol(z, "residual")
+    (r ** 2).mean().backward()
+    want_g = z["grad64_mse_corrected"] if has_ln else z["grad64_mse"]
+    assert rel(flat_grad(model).cpu(), want_g) <= _tol(z, "grad")
+
+
+@pytest.mark.parametrize("tag", [f for f in fixtures() if f.startswith(("c1_", "c2_", "x_"))])
+def test_compute_loss_vs_golden(dev, tag):
+    z, meta, state = load_fixture(tag)
+    if meta["mode"] != "loss":
+        pytest.skip("fixture stores residual only")
+    model = product_model(meta, state, dev)
+    pde = product_pde(meta["pde"], dev)
+    x, t = torch.from_numpy(z["x"]).to(dev), torch.from_numpy(z["t"]).to(dev)
+    losses = pde.compute_loss(model, x, t)
+    assert set(losses) == {"residual", "boundary", "initial", "smoothness", "data", "total"}
+    for k in ("residual", "boundary", "initial", "total"):
+        want = float(z[f"loss64_{k}"])
+        assert abs(losses[k].item() - want) <= max(TOL, 2 * abs(float(z[f"loss32_{k}"]) - want) / abs(want)) * abs(want), k
+    losses["total"].backward()
+    assert rel(flat_grad(model).cpu(), z["grad64"]) <= _tol(z, "grad")
+
+
+def test_2d_cahn_hilliard_math_operator(dev):
+    """compat='math': the intended 2-D operator (18 jet columns) vs the corrected multi-dim autograd oracle."""
+    z, meta, state = load_fixture("c4_ch2d_siren_small")
+    model = product_model(meta, state, dev)
+    pde = product_pde("cahn_hilliard", dev, 2, compat="math")
+    x, t = torch.from_numpy(z["x"]).to(dev), torch.from_numpy(z["t"]).to(dev)
+    r = pde.compute_residual(model, x, t)
+    # omega_0 = 30 amplifies each derivative order; 4th-order jets in fp32 carry more rounding noise
+    assert rel(r.detach().cpu(), z["residual64_math"]) <= 5e-5
+    (r ** 2).mean().backward()
+    assert rel(flat_grad(model).cpu(), z["grad64_mse_math"]) <= 5e-5
+
+
+def test_heat_math_operator(dev):
+    from oracle import jets_oracle
+    z, meta, state = load_fixture("c1_heat_fourier")
+    model = product_model(meta, state, dev)
+    pde = product_pde("heat", dev, compat="math")
+    x, t = torch.from_numpy(z["x"]).to(dev), torch.from_numpy(z["t"]).to(dev)
+    r = pde.compute_residual(model, x, t)
+    m64 = port_model(meta, state, torch.float64)
+    want = jets_oracle.residual(m64, "heat", torch.from_numpy(z["x"]).double(), torch.from_numpy(z["t"]).double(),
+                                meta["params"], 1, "math")
+    assert rel(r.detach().cpu(), want.detach()) <= 2e-5
+
+
+FULL = [  # (pde, arch, hidden, layers, dimension, n, extra)  -- BASELINE configs at full network size
+    ("heat", "fourier", 128, 4, 1, 1500, {"mapping_size": 32, "scale": 10.0}),
+    ("burgers", "feedforward", 128, 8, 1, 3000, {}),
+    ("kdv", "resnet", 256, 6, 1, 700, {"num_blocks": 6}),
+    ("cahn_hilliard", "siren", 256, 5, 2, 1500, {"omega_0": 30.0}),
+    ("cahn_hilliard", "siren", 256, 5, 1, 700, {"omega_0": 30.0}),
+    ("allen_cahn", "feedforward", 128, 8, 1, 3000, {}),
+]
+
+
+@pytest.mark.parametrize("pde_name,arch,hidden,layers,dim,n,extra", FULL)
+def test_full_size_configs_vs_oracle(dev, pde_name, arch, hidden, layers, dim, n, extra):
+    """Seeded weights/points; oracle = the reference's autograd algorithm (ref_port) in fp64 on the CPU
+    (with the primitive LayerNorm where the reference's nn.LayerNorm is inexact)."""
+    import pinns_rl_pde_b200 as pk
+    from oracle import ref_port
+    torch.manual_seed(3)
+    model = pk.make_model(arch, dim + 1, hidden, layers, dev, **extra)
+    state = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    meta = dict(arch=arch, hidden=hidden, layers=layers, dimension=dim, extra=extra)
+    m64 = port_model(meta, state, torch.float64, corrected=(arch == "resnet"))
+    s = PDES[pde_name]
+    g = torch.Generator().manual_seed(4)
+    lo, hi = s["domain"][0]
+    x = torch.rand(n, dim, generator=g) * (hi - lo) + lo
+    t = torch.rand(n, 1, generator=g) * (s["time"][1] - s["time"][0]) + s["time"][0]
+    pde = product_pde(pde_name, dev, dim)
+    r = pde.compute_residual(model, x.to(dev), t.to(dev))
+    kw = {k: v for k, v in s["params"].items() if k != "speed"}
+    want = ref_port.RESIDUALS[pde_name](m64, x.double(), t.double(), dimension=dim, **kw)
+    tol = 3e-5 if (arch, pde_name, dim) in (("siren", "cahn_hilliard", 1), ("resnet", "kdv", 1)) else TOL
+    assert rel(r.detach().cpu(), want.detach()) <= tol
+    (r ** 2).mean().backward()
+    (want ** 2).mean().backward()
+    og = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in m64.parameters()])
+    assert rel(flat_grad(model).cpu(), og) <= tol
+
+
+def test_chunking_is_invisible(dev):
+    """Rows beyond the plan's chunk are processed in several passes with identical results."""
+    import pinns_rl_pde_b200 as pk
+    from pinns_rl_pde_b200 import engine
+    torch.manual_seed(0)
+    model = pk.make_model("feedforward", 2, 64, 3, dev)
+    pde = product_pde("burgers", dev)
+    g = torch.Generator().manual_seed(1)
+    x, t = (torch.rand(5000, 1, generator=g) * 2 - 1).to(dev), torch.rand(5000, 1, generator=g).to(dev)
+    l1 = pde.compute_loss(model, x, t)
+    l1["total"].backward()
+    g1 = flat_grad(model).clone()
+    model.zero_grad()
+    old = engine.MAX_CHUNK_POINTS
+    engine.MAX_CHUNK_POINTS = 1024
+    engine._CACHE.clear()
+    try:
+        l2 = pde.compute_loss(model, x, t)
+        l2["total"].backward()
+    finally:
+        engine.MAX_CHUNK_POINTS = old
+        engine._CACHE.clear()
+    assert abs(l1["total"].item() - l2["total"].item()) <= 1e-6 * abs(l1["total"].item())
+    assert rel(flat_grad(model), g1) <= 2e-6
+
+
+def test_model_forward_and_custom_loss_autograd(dev):
+    """model(x) and jets() are differentiable w.r.t. parameters for callers that write their own loss."""
+    import pinns_rl_pde_b200 as pk
+    torch.manual_seed(0)
+    model = pk.make_model("siren", 2, 64, 3, dev, omega_0=30.0)
+    state = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    m64 = port_model(dict(arch="siren", hidden=64, layers=3, dimension=1, extra={"omega_0": 30.0}), state, torch.float64)
+    xt = torch.rand(333, 2, generator=torch.Generator().manual_seed(2))
+    u = model(xt.to(dev))
+    want = m64(xt.double())
+    assert u.shape == (333, 1) and rel(u.detach().cpu(), want.detach()) <= TOL
+    (u.sin().sum()).backward()
+    want.sin().sum().backward()
+    og = torch.cat([p.grad.reshape(-1) for p in m64.parameters()])
+    assert rel(flat_grad(model).cpu(), og) <= TOL
+    U = pk.jets(model, xt.to(dev), [((1.0, 0.0), 2), ((0.0, 1.0), 1)])
+    X = xt.double().requires_grad_(True)
+    uu = m64(X)
+    du = torch.autograd.grad(uu.sum(), X, create_graph=True)[0]
+    uxx = torch.autograd.grad(du[:, 0].sum(), X)[0][:, 0]
+    assert rel(U[:, 1].cpu(), du[:, 0].detach()) <= TOL and rel(2 * U[:, 2].cpu(), uxx) <= TOL
+    assert rel(U[:, 3].cpu(), du[:, 1].detach()) <= TOL
+
+
+def test_scoring_matches_residual(dev):
+    import pinns_rl_pde_b200 as pk
+    torch.manual_seed(0)
+    model = pk.make_model("feedforward", 2, 64, 4, dev)
+    pde = product_pde("allen_cahn", dev)
+    g = torch.Generator().manual_seed(5)
+    x, t = (torch.rand(4097, 1, generator=g) * 2 - 1).to(dev), torch.rand(4097, 1, generator=g).to(dev)
+    r = pde.compute_residual(model, x, t).detach().abs().reshape(-1)
+    mag, stats = pde.score_residual(model, x, t)
+    assert torch.equal(mag, r)
+    s = stats.cpu()
+    assert abs(s[0].item() - r.double().sum().item()) <= 1e-9 * r.double().sum().item() + 1e-12
+    assert abs(s[1].item() - (r.double() ** 2).sum().item()) <= 1e-9 * (r.double() ** 2).sum().item() + 1e-12
+    assert s[2].item() == float(r.max().item()) and s[3].item() == 4097
+    xs, ts = pde.generate_collocation_points(1000, strategy="residual_based", model=model)
+    assert xs.shape == (1000, 1) and ts.shape == (1000, 1)
+
+
+def test_edge_cases(dev):
+    import pinns_rl_pde_b200 as pk
+    from pinns_rl_pde_b200 import _lib
+    torch.manual_seed(0)
+    model = pk.make_model("feedforward", 2, 32, 2, dev)
+    pde = product_pde("burgers", dev)
+    # empty batch
+    r = pde.compute_residual(model, torch.zeros(0, 1, device=dev), torch.zeros(0, 1, device=dev))
+    assert r.shape == (0, 1)
+    # single point, ragged size
+    for n in (1, 7, 257):
+        r = pde.compute_residual(model, torch.rand(n, 1, device=dev), torch.rand(n, 1, device=dev))
+        assert r.shape == (n, 1) and torch.isfinite(r).all()
+    # wrong dtype / shape fail loudly
+    with pytest.raises(_lib.PinnkError):
+        model(torch.zeros(4, 3, device=dev))
+    # compute_loss in 2-D fails like the reference does
+    m3 = pk.make_model("feedforward", 3, 32, 2, dev)
+    with pytest.raises(RuntimeError):
+        product_pde("burgers", dev, 2).compute_loss(m3, torch.rand(8, 2, device=dev), torch.rand(8, 1, device=dev))
+    # frozen parameters receive no gradient and do not break the reverse pass
+    for p in list(model.parameters())[:2]:
+        p.requires_grad_(False)
+    pde.compute_loss(model, torch.rand(64, 1, device=dev), torch.rand(64, 1, device=dev))["total"].backward()
+    assert all((p.grad is None) == (not p.requires_grad) for p in model.parameters())
+
+
+def test_loss_functions_and_training_configs(dev):
+    """mae / huber reductions and the three shapes config.training can take (dataclass, dict, None)."""
+    import pinns_rl_pde_b200 as pk
+    from oracle import ref_port
+    torch.manual_seed(0)
+    model = pk.make_model("feedforward", 2, 32, 3, dev)
+    state = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    m64 = port_model(dict(arch="feedforward", hidden=32, layers=3, dimension=1, extra={}), state, torch.float64)
+    g = torch.Generator().manual_seed(6)
+    x, t = torch.rand(500, 1, generator=g) * 2 - 1, torch.rand(500, 1, generator=g)
+    s = PDES["burgers"]
+    fns = ref_port.boundary_condition_fns("burgers", s["bcs"], s["ic"], s["domain"], s["params"])
+    for fn_name, training, weights in [("mae", {"loss_function": "mae"}, (1.0, 10.0, 10.0)),
+                                       ("huber", {"loss_function": "huber", "huber_delta": 0.05}, (1.0, 10.0, 10.0)),
+                                       ("mse", pk.TrainingConfig(loss_weights={"residual": 15.0, "boundary": 20.0, "initial": 10.0}),
+                                        (15.0, 20.0, 10.0))]:
+        pde = product_pde("burgers", dev, training=training)
+        model.zero_grad()
+        L = pde.compute_loss(model, x.to(dev), t.to(dev))
+        L["total"].backward()
+        r = ref_port.burgers_residual(m64, x.double(), t.double(), nu=s["params"]["nu"])
+        delta = 0.05 if fn_name == "huber" else 1.0
+        want = ref_port.base_compute_loss(m64, r, s["domain"], s["time"], fns, weights, fn_name, delta)
+        for p in m64.parameters():
+            p.grad = None
+        want["total"].backward()
+        og = torch.cat([p.grad.reshape(-1) for p in m64.parameters()])
+        assert abs(L["total"].item() - want["total"].item()) <= 2e-5 * abs(want["total"].item()), fn_name
+        assert rel(flat_grad(model).cpu(), og) <= 5e-5, fn_name
+
+
+def test_loss_trajectory_500_epochs(dev):
+    """north_star: loss trajectories over 500 epochs within 1e-4 relative of the reference algorithm.
+    Same seeded points every epoch, Adam with identical hyper-parameters; the oracle runs in fp64 on the CPU."""
+    import pinns_rl_pde_b200 as pk
+    from oracle import ref_port
+    torch.manual_seed(0)
+    model = pk.make_model("feedforward", 2, 32, 3, dev)
+    state = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    m64 = port_model(dict(arch="feedforward", hidden=32, layers=3, dimension=1, extra={}), state, torch.float64)
+    pde = product_pde("burgers", dev)
+    s = PDES["burgers"]
+    fns = ref_port.boundary_condition_fns("burgers", s["bcs"], s["ic"], s["domain"], s["params"])
+    g = torch.Generator().manual_seed(7)
+    x, t = torch.rand(256, 1, generator=g) * 2 - 1, torch.rand(256, 1, generator=g)
+    xd, td = x.to(dev), t.to(dev)
+    opt_a = torch.optim.Adam(model.parameters(), lr=1e-3)
+    opt_b = torch.optim.Adam(m64.parameters(), lr=1e-3)
+    worst = 0.0
+    for epoch in range(500):
+        opt_a.zero_grad()
+        la = pde.compute_loss(model, xd, td)["total"]
+        la.backward()
+        opt_a.step()
+        opt_b.zero_grad()
+        r = ref_port.burgers_residual(m64, x.double(), t.double(), nu=s["params"]["nu"])
+        lb = ref_port.base_compute_loss(m64, r, s["domain"], s["time"], fns)["total"]
+        lb.backward()
+        opt_b.step()
+        worst = max(worst, abs(la.item() - lb.item()) / abs(lb.item()))
+    assert worst <= 1e-4, worst
