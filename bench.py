@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- headline metric of BASELINE.json: collocation points/s for one residual+grad step.
+
+Workload (configs[1], the configuration the metric is quoted on): Burgers nu=0.01/pi, feedforward tanh
+8x128, 1M collocation points per B200 (weak scaling: every rank owns 1M rows).  One step =
+PDETrainer's inner step (trainer.py:577-578,689-694): zero_grad -> compute_loss (residual + 200
+boundary + 100 initial rows) -> backward -> [all-reduce of the flat gradient when N>1] -> clip -> Adam.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--points P]
+
+`value`   device-timed steps with the collocation rows resident in HBM;
+`e2e`     the same step through the public API from pinned HOST buffers (H2D of the rows and D2H of the
+          loss inside the timed region);
+`roofline`     dominant kernel class timed with CUDA event pairs inside libpinnk (profiling pass);
+`cpu_baseline` the oracle port of the reference's autograd-of-autograd path on the host cores.
+`--impl reference` times that CPU path alone, on a bounded sample of the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "collocation points/sec (residual+grad step)"
+HIDDEN, LAYERS, NU = 128, 8, 0.01 / math.pi
+W_ELEMS = 2 * 128 + 7 * 128 * 128 + 128          # Linear weight elements (115 072)
+JET_COLS = 4                                      # u, u_x, u_xx, u_t
+FLOPS_PER_POINT_STEP = 6 * JET_COLS * W_ELEMS     # fwd 2CW + dgrad 2CW + wgrad 2CW = 2.76 MFLOP
+CPU_SAMPLE_POINTS = 32768
+
+
+def burgers_cfg(pk, dev):
+    return pk.PDEConfig(name="burgers", domain=[[-1.0, 1.0]], time_domain=[0.0, 1.0], parameters={"nu": NU},
+                        boundary_conditions={"dirichlet": {"value": 0.0}},
+                        initial_condition={"type": "sine", "amplitude": -1.0, "frequency": 1.0},
+                        exact_solution={}, dimension=1, device=dev)
+
+
+def synth_points(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(n, 1, generator=g) * 2 - 1, torch.rand(n, 1, generator=g)
+
+
+# --------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_step_fn(n_points):
+    """The reference algorithm (oracle/ref_port.py: nn.Linear/Tanh + nested autograd.grad + loss assembly,
+    bit-identical to pinnrl on the same inputs) on the host cores, fp32."""
+    from oracle import ref_port
+    torch.manual_seed(0)
+    model = ref_port.PINNModel("feedforward", 2, HIDDEN, LAYERS)
+    x, t = synth_points(n_points, 1)
+    fns = ref_port.boundary_condition_fns("burgers", {"dirichlet": {"value": 0.0}},
+                                          {"type": "sine", "amplitude": -1.0, "frequency": 1.0}, [(-1.0, 1.0)], {"nu": NU})
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+
+    def step():
+        opt.zero_grad()
+        r = ref_port.burgers_residual(model, x, t, nu=NU)
+        losses = ref_port.base_compute_loss(model, r, [(-1.0, 1.0)], (0.0, 1.0), fns)
+        losses["total"].backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        return float(losses["total"].detach())
+    return step
+
+
+def time_cpu(n_points, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_reference_step_fn(n_points)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return n_points / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pps, dt = time_cpu(CPU_SAMPLE_POINTS, args.steps, args.warmup)
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": pps, "unit": "points/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": pps, "unit": "points/s", "cores": cores, "kind": "port",
+                             "sample": f"{CPU_SAMPLE_POINTS} of the workload's collocation rows per step "
+                                       f"(+200 boundary +100 initial rows), torch {torch.__version__} CPU fp32"},
+            "e2e": {"value": pps, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    return {"workload": "Burgers nu=0.01/pi, feedforward tanh 8x128, 1M collocation pts per B200 (BASELINE configs[1])",
+            "points_per_gpu": args.points, "global_points": args.points * world, "jet_columns": JET_COLS,
+            "boundary_rows": 200, "initial_rows": 100, "optimizer": "Adam lr=1e-3, clip 1.0",
+            "parallelism": f"dp{world} (rows sharded, one all-reduce of the flat gradient)",
+            "l2": "flushed between timed steps (256 MiB write); per-step CUDA events summed"}
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            self.path = tempfile.mktemp(suffix=".csv")
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in open(self.path):
+            f = [c.strip() for c in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch.distributed as dist
+    import pinns_rl_pde_b200 as pk
+    from pinns_rl_pde_b200 import _lib, parallel
+    import __graft_entry__ as ge
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+
+    torch.manual_seed(0)
+    model = pk.make_model("feedforward", 2, HIDDEN, LAYERS, dev)
+    pde = pk.BurgersEquation(burgers_cfg(pk, dev))
+    n_local, n_global = args.points, args.points * world
+    xh, th = synth_points(n_local, 1 + rank)
+    xh, th = xh.pin_memory(), th.pin_memory()
+    x, t = xh.to(dev), th.to(dev)
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(xd, td):
+        opt.zero_grad(set_to_none=True)
+        if world > 1:
+            losses = parallel.sharded_loss_backward(pde, model, xd, td, n_global=n_global)
+        else:
+            losses = pde.compute_loss(model, xd, td)
+            losses["total"].backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        return losses["total"]
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        evs = []
+        sync()
+        for _ in range(steps):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            evs.append((a, b))
+        sync()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    for _ in range(args.warmup):
+        step(x, t)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms_total = timed(lambda: step(x, t), args.steps)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+
+    if args.lite:
+        if rank == 0:
+            print(json.dumps({"lite": True, "ms_per_step": ms_total / args.steps, "gpu_launches": int(launches),
+                              "value": n_global * args.steps / (ms_total * 1e-3)}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # end to end: pinned host rows -> device -> step -> loss back on the host, every step
+    xd, td = torch.empty_like(x), torch.empty_like(t)
+
+    def e2e_step():
+        xd.copy_(xh, non_blocking=True)
+        td.copy_(th, non_blocking=True)
+        return float(step(xd, td).item())
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+
+    # roofline: profiling pass (event pairs around every libpinnk kernel class)
+    roof = None
+    if rank == 0:
+        _lib.prof_enable(True)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(2):
+            step(x, t)
+        b.record()
+        torch.cuda.synchronize()
+        prof = _lib.prof_collect()
+        _lib.prof_enable(False)
+        step_ms = a.elapsed_time(b) / 2
+        gemm = {k: prof[k] for k in ("gemm_fwd", "gemm_dgrad", "gemm_wgrad")}
+        dom = max(gemm, key=lambda k: gemm[k][0])
+        ms_dom, n_dom = gemm[dom]
+        chunks = max(1, n_dom // (2 * (LAYERS - 1)))                   # launches per step / hidden GEMM layers
+        rows_per_launch = n_local / max(1, -(-n_local // 131072))
+        flops_per_launch = 2 * JET_COLS * rows_per_launch * HIDDEN * HIDDEN
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        bf16 = peaks.get("bf16_tflops_sustained")
+        which = "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (tf32) / 3 (3xTF32 split)"
+        if bf16 is None:
+            bf16, which = 1400.0, "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md) / 2 / 3"
+        peak = bf16 / 6.0
+        achieved = flops_per_launch / (ms_dom / n_dom * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": which,
+                "launch_ms": ms_dom / n_dom, "launches_per_step": n_dom // 2,
+                "share_of_step": {k: v[0] / 2 / step_ms for k, v in prof.items() if v[1]},
+                "step_flops_frac_of_peak": (FLOPS_PER_POINT_STEP * n_local / (ms_total / args.steps * 1e-3) / 1e12) / peak}
+
+    if rank == 0:
+        cpu_pps, cpu_dt = time_cpu(CPU_SAMPLE_POINTS, 3, 1) if world == 1 else (None, None)
+        value = n_global * args.steps / (ms_total * 1e-3)
+        line = {"metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": workload_config(args, world), "clocks": clocks,
+                "e2e": {"value": n_global * args.steps / (ms_e2e * 1e-3), "unit": "points/s",
+                        "h2d_bytes_per_step": int(xh.numel() * 4 + th.numel() * 4), "d2h_bytes_per_step": 4},
+                "gpu_launches": int(launches), "roofline": roof}
+        if cpu_pps is not None:
+            line["cpu_baseline"] = {"value": cpu_pps, "unit": "points/s", "cores": torch.get_num_threads(), "kind": "port",
+                                    "sample": f"{CPU_SAMPLE_POINTS} collocation rows per step (+300 BC/IC rows), "
+                                              f"1 warm-up + 3 steps, oracle port of the reference autograd path, fp32"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--points", type=int, default=1 << 20, help="collocation rows per GPU")
+    ap.add_argument("--lite", action="store_true", help="timed steps only (for runs under ncu): no e2e / roofline / cpu passes")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -139,6 +139,14 @@ int32_t pinnk_abi_version(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 int64_t pinnk_launch_count(void);
 
+
+/* Optional per-kernel-class device timing (CUDA event pairs on the launching stream), used by bench.py
+ * for the roofline line.  Off by default; enabling it adds two event records per launch. */
+void pinnk_prof_enable(int32_t on);
+int32_t pinnk_prof_classes(void);
+const char* pinnk_prof_class_name(int32_t cls);
+int pinnk_prof_collect(double* ms_per_class, int64_t* launches_per_class, int32_t n_classes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,7 +40,8 @@ class PinnkSegment(C.Structure):
 
 EXPORTS = ["pinnk_plan_create", "pinnk_plan_destroy", "pinnk_plan_workspace_bytes", "pinnk_plan_ncols",
            "pinnk_plan_grad_floats", "pinnk_jets_forward", "pinnk_jets_vjp", "pinnk_loss_step", "pinnk_score",
-           "pinnk_last_error", "pinnk_abi_version", "pinnk_launch_count"]
+           "pinnk_last_error", "pinnk_abi_version", "pinnk_launch_count", "pinnk_prof_enable", "pinnk_prof_classes",
+           "pinnk_prof_class_name", "pinnk_prof_collect"]
 
 _lib = None
 
@@ -83,6 +84,14 @@ def load():
     lib.pinnk_abi_version.restype = i32
     lib.pinnk_launch_count.argtypes = []
     lib.pinnk_launch_count.restype = i64
+    lib.pinnk_prof_enable.argtypes = [i32]
+    lib.pinnk_prof_enable.restype = None
+    lib.pinnk_prof_classes.argtypes = []
+    lib.pinnk_prof_classes.restype = i32
+    lib.pinnk_prof_class_name.argtypes = [i32]
+    lib.pinnk_prof_class_name.restype = C.c_char_p
+    lib.pinnk_prof_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(i64), i32]
+    lib.pinnk_prof_collect.restype = C.c_int
     if lib.pinnk_abi_version() != ABI_VERSION:
         raise PinnkError(f"libpinnk.so ABI {lib.pinnk_abi_version()} != binding {ABI_VERSION}: rebuild")
     _lib = lib
@@ -97,3 +106,17 @@ def check(rc: int, what: str):
 
 def launch_count() -> int:
     return int(load().pinnk_launch_count())
+
+
+def prof_enable(on: bool):
+    load().pinnk_prof_enable(1 if on else 0)
+
+
+def prof_collect():
+    """{class name: (total ms, launches)} since the last collect (synchronises the recorded events)."""
+    lib = load()
+    n = lib.pinnk_prof_classes()
+    ms = (C.c_double * n)()
+    cnt = (C.c_int64 * n)()
+    lib.pinnk_prof_collect(ms, cnt, n)
+    return {lib.pinnk_prof_class_name(i).decode(): (ms[i], int(cnt[i])) for i in range(n)}

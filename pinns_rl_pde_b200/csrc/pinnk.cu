@@ -27,6 +27,23 @@ using namespace pinnk;
 static thread_local std::string g_err;
 static std::atomic<int64_t> g_launches{0};
 
+// ---- optional per-kernel-class timing (bench.py roofline): CUDA event pairs on the launching stream
+enum ProfClass { PC_FIRST_FWD = 0, PC_GEMM_FWD, PC_ACT_FWD, PC_LN_FWD, PC_LAST_FWD, PC_EPILOGUE, PC_LAST_BWD,
+                 PC_ACT_BWD, PC_LN_BWD, PC_GEMM_DGRAD, PC_GEMM_WGRAD, PC_FIRST_BWD, PC_MISC, PC_COUNT };
+static const char* kProfNames[PC_COUNT] = {"first_linear_fwd", "gemm_fwd", "act_fwd", "layernorm_fwd", "last_linear_fwd",
+                                           "epilogue", "last_linear_bwd", "act_bwd", "layernorm_bwd", "gemm_dgrad",
+                                           "gemm_wgrad", "first_linear_bwd", "misc"};
+struct ProfRec { int cls; cudaEvent_t a, b; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+struct ProfScope {
+  bool on; ProfRec r; cudaStream_t st;
+  ProfScope(int cls, cudaStream_t s) : on(g_prof_on), st(s) {
+    if (on) { r.cls = cls; cudaEventCreate(&r.a); cudaEventCreate(&r.b); cudaEventRecord(r.a, st); }
+  }
+  ~ProfScope() { if (on) { cudaEventRecord(r.b, st); g_prof.push_back(r); } }
+};
+
 static int fail(int code, const std::string& msg) {
   g_err = msg;
   return code;
@@ -74,6 +91,21 @@ static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 extern "C" const char* pinnk_last_error(void) { return g_err.c_str(); }
 extern "C" int32_t pinnk_abi_version(void) { return PINNK_ABI_VERSION; }
 extern "C" int64_t pinnk_launch_count(void) { return g_launches.load(); }
+extern "C" void pinnk_prof_enable(int32_t on) { g_prof_on = on != 0; }
+extern "C" int32_t pinnk_prof_classes(void) { return PC_COUNT; }
+extern "C" const char* pinnk_prof_class_name(int32_t c) { return (c >= 0 && c < PC_COUNT) ? kProfNames[c] : ""; }
+extern "C" int pinnk_prof_collect(double* ms, int64_t* launches, int32_t n) {
+  for (int i = 0; i < n; ++i) { ms[i] = 0.0; launches[i] = 0; }
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    cudaEventSynchronize(r.b);
+    cudaEventElapsedTime(&t, r.a, r.b);
+    if (r.cls < n) { ms[r.cls] += t; launches[r.cls] += 1; }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  return 0;
+}
 
 extern "C" int pinnk_plan_create(const PinnkOp* ops, int32_t n_ops, int32_t in_dim, const PinnkJetSpec* jets,
                                  int64_t chunk_points, int32_t device, pinnk_plan_t* out) {
@@ -243,6 +275,7 @@ struct ChunkCtx {
 };
 
 static int gemm_fwd(const ChunkCtx& c, const float* X, const float* W, const float* b, float* Z, int in_dim, int out_dim) {
+  ProfScope ps(PC_GEMM_FWD, c.st);
   const int64_t M = c.n * c.pl->js.ncols;
   int rc = tc_linear_fwd(X, W, b, Z, M, in_dim, out_dim, c.pl->js.ncols, c.pl->sm_count, c.st);
   if (rc == 0) { g_launches.fetch_add(1); return 0; }
@@ -255,6 +288,7 @@ static int gemm_fwd(const ChunkCtx& c, const float* X, const float* W, const flo
 }
 
 static int gemm_dgrad(const ChunkCtx& c, const float* Zb, const float* W, float* Xb, int in_dim, int out_dim) {
+  ProfScope ps(PC_GEMM_DGRAD, c.st);
   const int64_t M = c.n * c.pl->js.ncols;
   dim3 grid(blocks_for(M, SG_BM), blocks_for(in_dim, SG_BN), 1);
   sgemm_kernel<true, false, EPI_STORE><<<grid, SG_THREADS, 0, c.st>>>(Zb, W, Xb, M, in_dim, out_dim, out_dim, in_dim,
@@ -264,6 +298,7 @@ static int gemm_dgrad(const ChunkCtx& c, const float* Zb, const float* W, float*
 }
 
 static int gemm_wgrad(const ChunkCtx& c, const float* Zb, const float* X, float* gW, float* gb, int in_dim, int out_dim) {
+  ProfScope ps(PC_GEMM_WGRAD, c.st);
   const int64_t M = c.n * c.pl->js.ncols;   // contraction length
   if (gW) {
     const unsigned tiles = blocks_for(out_dim, SG_BM) * blocks_for(in_dim, SG_BN);
@@ -286,6 +321,7 @@ static int gemm_wgrad(const ChunkCtx& c, const float* Zb, const float* X, float*
 
 template <int MAXK>
 static int ln_fwd(const ChunkCtx& c, const float* Z, float* Y, int width, const float* g, const float* b, float eps) {
+  ProfScope ps(PC_LN_FWD, c.st);
   const int threads = 256;
   const unsigned blocks = blocks_for(c.n * 32, threads);
   const int nper = (width + 31) / 32;
@@ -299,6 +335,7 @@ static int ln_fwd(const ChunkCtx& c, const float* Z, float* Y, int width, const 
 template <int MAXK>
 static int ln_bwd(const ChunkCtx& c, const float* Z, const float* Gin, float* Gout, int width, const float* g, float eps,
                   float* dg, float* db) {
+  ProfScope ps(PC_LN_BWD, c.st);
   const int threads = 128;
   const int wpb = threads / 32;
   int64_t blocks = (c.n + wpb - 1) / wpb;
@@ -329,10 +366,12 @@ static int forward_chunk(const ChunkCtx& c) {
         const float* W = c.params[o.w_index];
         const float* b = (o.b_index >= 0) ? c.params[o.b_index] : nullptr;
         if (i == 0) {
+          ProfScope ps(PC_FIRST_FWD, c.st);
           first_linear_fwd_kernel<<<blocks_for(c.n * o.out_dim, threads), threads, 0, c.st>>>(
               c.x, c.t, c.n, W, b, o.w_transposed, o.out_dim, js, c.stash(i));
           PK_LAUNCH_OK();
         } else if (i == n_ops - 1) {
+          ProfScope ps(PC_LAST_FWD, c.st);
           const int64_t rows = c.n * js.ncols;
           last_linear_fwd_kernel<<<blocks_for(rows * 32, threads), threads, 0, c.st>>>(in, rows, o.in_dim, js.ncols, W, b, c.U());
           PK_LAUNCH_OK();
@@ -343,6 +382,7 @@ static int forward_chunk(const ChunkCtx& c) {
         break;
       }
       case PINNK_OP_ACT: {
+        ProfScope ps(PC_ACT_FWD, c.st);
         const float* S = (r.skip_src >= 0) ? c.stash(r.skip_src) : nullptr;
         const unsigned blocks = blocks_for(c.n * o.in_dim, threads);
         if (o.act == PINNK_ACT_TANH)
@@ -357,10 +397,12 @@ static int forward_chunk(const ChunkCtx& c) {
         if (rc) return rc;
         break;
       }
-      case PINNK_OP_SINCOS:
+      case PINNK_OP_SINCOS: {
+        ProfScope ps(PC_MISC, c.st);
         sincos_fwd_kernel<MAXK><<<blocks_for(c.n * o.in_dim, threads), threads, 0, c.st>>>(in, c.stash(i), c.n, o.in_dim, js);
         PK_LAUNCH_OK();
         break;
+      }
       default: break;   // skip markers
     }
   }
@@ -390,12 +432,14 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad) {
       case PINNK_OP_LINEAR: {
         const float* W = c.params[o.w_index];
         if (i == n_ops - 1) {
+          ProfScope ps(PC_LAST_BWD, c.st);
           const int64_t rows = c.n * js.ncols;
           dim3 grid(blocks_for(o.in_dim, 128), (unsigned)std::min<int64_t>(rows, 4 * (int64_t)pl->sm_count));
           last_linear_bwd_kernel<<<grid, 128, 0, c.st>>>(in, c.Ub(), rows, o.in_dim, js.ncols, W, c.adj(cur),
                                                          G(o.gw_offset), G(o.gb_offset));
           PK_LAUNCH_OK();
         } else if (i == 0) {
+          ProfScope ps(PC_FIRST_BWD, c.st);
           dim3 grid(blocks_for(o.out_dim, 128), (unsigned)std::min<int64_t>(c.n, 2 * (int64_t)pl->sm_count));
           first_linear_bwd_kernel<<<grid, 128, 0, c.st>>>(c.x, c.t, c.n, o.out_dim, js, c.adj(cur), G(o.gw_offset), G(o.gb_offset));
           PK_LAUNCH_OK();
@@ -414,6 +458,7 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad) {
       case PINNK_OP_ACT: {
         const float* S = (r.skip_src >= 0) ? c.stash(r.skip_src) : nullptr;
         const unsigned blocks = blocks_for(c.n * o.in_dim, threads);
+        ProfScope ps(PC_ACT_BWD, c.st);
         if (o.act == PINNK_ACT_TANH)
           act_bwd_kernel<1, MAXK><<<blocks, threads, 0, c.st>>>(in, S, c.adj(cur), c.n, o.in_dim, js, 1.f);
         else
@@ -538,6 +583,7 @@ extern "C" int pinnk_loss_step(pinnk_plan_t plan, const float* const* params, co
       sd.row_start = g.row_start; sd.row_count = g.row_count; sd.pair_offset = g.pair_offset;
       sd.target = g.target; sd.error_out = g.error_out; sd.error_grad = flat_grad ? g.error_grad : nullptr;
       sd.loss_slot = loss_sums ? loss_sums + g.component : nullptr;
+      ProfScope ps(PC_EPILOGUE, c.st);
       epilogue_kernel<<<blocks_for(hi - lo, threads), threads, 0, c.st>>>(c.U(), flat_grad ? c.Ub() : nullptr, plan->js, sd, p0, lo, hi);
       PK_LAUNCH_OK();
     }

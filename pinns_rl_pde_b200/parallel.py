@@ -41,12 +41,14 @@ def reduce_flat(local_flat: torch.Tensor, local_sums: torch.Tensor, group=None) 
 
 
 def sharded_loss_backward(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor,
-                          components: Optional[Callable] = None, group=None) -> Dict[str, torch.Tensor]:
+                          components: Optional[Callable] = None, group=None,
+                          n_global: Optional[int] = None) -> Dict[str, torch.Tensor]:
     """Data-parallel compute_loss + backward (trainer.py:578,689 on N GPUs).
 
-    ``x, t`` are the GLOBAL collocation rows (identical on every rank, e.g. drawn from a shared seed).
-    Rank r evaluates residual rows [lo_r, hi_r); the few hundred boundary/initial rows are evaluated on
-    every rank (replicated work, no exchange).  With frac_r = n_r / N the global objective is
+    With ``n_global=None``, ``x, t`` are the GLOBAL collocation rows (identical on every rank, e.g. drawn
+    from a shared seed) and rank r takes rows [lo_r, hi_r); with ``n_global`` given, ``x, t`` already are
+    this rank's shard.  The few hundred boundary/initial rows are evaluated on every rank (replicated
+    work, no exchange).  With frac_r = n_r / N the global objective is
         total = sum_r [ frac_r * w_res * res_r + (w_bc * bc + w_ic * ic) / W ]
     so each rank differentiates its bracket locally and ONE all-reduce(sum) of
     [flat_grad || frac_r*res_r || bc/W || ic/W] yields the global gradient and the global components.
@@ -55,9 +57,14 @@ def sharded_loss_backward(pde, model: nn.Module, x: torch.Tensor, t: torch.Tenso
     from . import functional as F
     comp_fn = components or F.loss_components
     w, r = world_size(), rank()
-    n = x.shape[0]
-    lo, hi = shard_bounds(n, r, w)
-    comp, (w_res, w_bc, w_ic, w_smooth, adaptive) = comp_fn(pde, model, x[lo:hi], t[lo:hi], n_global=n)
+    if n_global is None:
+        n = x.shape[0]
+        lo, hi = shard_bounds(n, r, w)
+        x, t = x[lo:hi], t[lo:hi]
+    else:
+        n = int(n_global)
+        lo, hi = 0, x.shape[0]
+    comp, (w_res, w_bc, w_ic, w_smooth, adaptive) = comp_fn(pde, model, x, t, n_global=n)
     if w_smooth:
         raise NotImplementedError("smoothness regulariser is not supported with data parallelism")
     if adaptive:

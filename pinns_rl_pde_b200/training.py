@@ -16,7 +16,6 @@ import torch.nn as nn
 
 from . import functional as F
 from . import parallel
-from .engine import get_program
 
 
 @dataclass

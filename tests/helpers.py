@@ -35,9 +35,14 @@ def load_fixture(tag):
     return z, meta, state
 
 
+def _t64(a):
+    if isinstance(a, torch.Tensor):
+        return a.detach().cpu().double().reshape(-1)
+    return torch.as_tensor(np.asarray(a)).double().reshape(-1)
+
+
 def rel(a, b):
-    a = torch.as_tensor(np.asarray(a)).double().reshape(-1)
-    b = torch.as_tensor(np.asarray(b)).double().reshape(-1)
+    a, b = _t64(a), _t64(b)
     return float((a - b).norm() / max(float(b.norm()), 1e-300))
 
 
