@@ -147,6 +147,20 @@ int32_t pinnk_prof_classes(void);
 const char* pinnk_prof_class_name(int32_t cls);
 int pinnk_prof_collect(double* ms_per_class, int64_t* launches_per_class, int32_t n_classes);
 
+/* Debug / micro-benchmark: one hidden nn.Linear forward over stacked jet rows,
+ * Z[M,N] = X[M,K] W[N,K]^T (+ bias on rows with row % jet_cols == 0).
+ * mode 0 = exact-fp32 CUDA-core GEMM, 1 = tcgen05 3xTF32 GEMM (error if the shape is not covered). */
+int pinnk_debug_linear_fwd(const float* X, const float* W, const float* bias, float* Z, int64_t M, int32_t K,
+                           int32_t N, int32_t jet_cols, int32_t mode, void* stream);
+/* dX[M,K] = dZ[M,N] W[N,K] and dW[N,K] += dZ[M,N]^T X[M,K], db[N] += value-column rows of dZ: the two reverse GEMMs. */
+/* Debug: device buffer [grid][8] of int64 cycle counters filled by the tcgen05 row kernels (NULL = off):
+ * loader {wait-empty, work}, epilogue {wait-full, work}, MMA {wait-tmem, wait-smem, issue}. */
+void pinnk_debug_set_clock_buffer(long long* dev_buf);
+int pinnk_debug_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t M, int32_t K, int32_t N,
+                             int32_t mode, void* stream);
+int pinnk_debug_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int32_t K, int32_t N,
+                             int32_t jet_cols, int32_t mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,7 +41,8 @@ class PinnkSegment(C.Structure):
 EXPORTS = ["pinnk_plan_create", "pinnk_plan_destroy", "pinnk_plan_workspace_bytes", "pinnk_plan_ncols",
            "pinnk_plan_grad_floats", "pinnk_jets_forward", "pinnk_jets_vjp", "pinnk_loss_step", "pinnk_score",
            "pinnk_last_error", "pinnk_abi_version", "pinnk_launch_count", "pinnk_prof_enable", "pinnk_prof_classes",
-           "pinnk_prof_class_name", "pinnk_prof_collect"]
+           "pinnk_prof_class_name", "pinnk_prof_collect", "pinnk_debug_linear_fwd",
+           "pinnk_debug_linear_dgrad", "pinnk_debug_linear_wgrad", "pinnk_debug_set_clock_buffer"]
 
 _lib = None
 
@@ -92,6 +93,14 @@ def load():
     lib.pinnk_prof_class_name.restype = C.c_char_p
     lib.pinnk_prof_collect.argtypes = [C.POINTER(C.c_double), C.POINTER(i64), i32]
     lib.pinnk_prof_collect.restype = C.c_int
+    lib.pinnk_debug_linear_fwd.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]
+    lib.pinnk_debug_linear_fwd.restype = C.c_int
+    lib.pinnk_debug_set_clock_buffer.argtypes = [vp]
+    lib.pinnk_debug_set_clock_buffer.restype = None
+    lib.pinnk_debug_linear_dgrad.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp]
+    lib.pinnk_debug_linear_dgrad.restype = C.c_int
+    lib.pinnk_debug_linear_wgrad.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]
+    lib.pinnk_debug_linear_wgrad.restype = C.c_int
     if lib.pinnk_abi_version() != ABI_VERSION:
         raise PinnkError(f"libpinnk.so ABI {lib.pinnk_abi_version()} != binding {ABI_VERSION}: rebuild")
     _lib = lib
@@ -120,3 +129,39 @@ def prof_collect():
     cnt = (C.c_int64 * n)()
     lib.pinnk_prof_collect(ms, cnt, n)
     return {lib.pinnk_prof_class_name(i).decode(): (ms[i], int(cnt[i])) for i in range(n)}
+
+
+def debug_linear_fwd(X, W, bias, jet_cols: int, mode: int):
+    """Z = X W^T (+bias on value rows) through one GEMM kernel of the library (tests / micro-benchmarks)."""
+    import torch
+    lib = load()
+    M, K = X.shape
+    N = W.shape[0]
+    Z = torch.empty(M, N, dtype=torch.float32, device=X.device)
+    check(lib.pinnk_debug_linear_fwd(X.data_ptr(), W.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                     Z.data_ptr(), M, K, N, jet_cols, mode,
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pinnk_debug_linear_fwd")
+    return Z
+
+
+def debug_linear_dgrad(dZ, W, mode: int):
+    import torch
+    lib = load()
+    M, N = dZ.shape
+    K = W.shape[1]
+    dX = torch.empty(M, K, dtype=torch.float32, device=dZ.device)
+    check(lib.pinnk_debug_linear_dgrad(dZ.data_ptr(), W.data_ptr(), dX.data_ptr(), M, K, N, mode,
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pinnk_debug_linear_dgrad")
+    return dX
+
+
+def debug_linear_wgrad(dZ, X, jet_cols: int, mode: int):
+    import torch
+    lib = load()
+    M, N = dZ.shape
+    K = X.shape[1]
+    dW = torch.zeros(N, K, dtype=torch.float32, device=dZ.device)
+    db = torch.zeros(N, dtype=torch.float32, device=dZ.device)
+    check(lib.pinnk_debug_linear_wgrad(dZ.data_ptr(), X.data_ptr(), dW.data_ptr(), db.data_ptr(), M, K, N, jet_cols, mode,
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pinnk_debug_linear_wgrad")
+    return dW, db

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include <atomic>
@@ -63,6 +64,8 @@ static int fail(int code, const std::string& msg) {
     if (_e != cudaSuccess)                                                                   \
       return fail(PINNK_E_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e));    \
   } while (0)
+
+static inline unsigned blocks_for(int64_t work, int threads) { return (unsigned)((work + threads - 1) / threads); }
 
 struct OpRt {
   PinnkOp op;
@@ -258,7 +261,6 @@ static int dispatch_maxk(int maxk, F&& f) {
   }
 }
 
-static inline unsigned blocks_for(int64_t work, int threads) { return (unsigned)((work + threads - 1) / threads); }
 
 struct ChunkCtx {
   pinnk_plan_t pl;
@@ -274,22 +276,40 @@ struct ChunkCtx {
   float* adj(int k) const { return ws + pl->off_adj[k]; }
 };
 
-static int gemm_fwd(const ChunkCtx& c, const float* X, const float* W, const float* b, float* Z, int in_dim, int out_dim) {
-  ProfScope ps(PC_GEMM_FWD, c.st);
-  const int64_t M = c.n * c.pl->js.ncols;
-  int rc = tc_linear_fwd(X, W, b, Z, M, in_dim, out_dim, c.pl->js.ncols, c.pl->sm_count, c.st);
-  if (rc == 0) { g_launches.fetch_add(1); return 0; }
-  if (rc != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, "tc_linear_fwd failed");
+// PINNK_DISABLE_TC=1 routes every GEMM to the exact-fp32 CUDA-core kernel (A/B checks of the tensor-core path)
+static bool tc_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PINNK_DISABLE_TC"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
+static int linear_fwd_any(const float* X, const float* W, const float* b, float* Z, int64_t M, int in_dim, int out_dim,
+                          int ncols, int sm_count, cudaStream_t st, bool allow_tc) {
+  if (allow_tc) {
+    int rc = tc_linear_fwd(X, W, b, Z, M, in_dim, out_dim, ncols, sm_count, st);
+    if (rc == 0) { g_launches.fetch_add(1); return 0; }
+    if (rc != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, std::string("tc_linear_fwd launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+  }
   dim3 grid(blocks_for(M, SG_BM), blocks_for(out_dim, SG_BN), 1);
-  sgemm_kernel<true, true, EPI_BIAS_C0><<<grid, SG_THREADS, 0, c.st>>>(X, W, Z, M, out_dim, in_dim, in_dim, in_dim,
-                                                                        out_dim, b, c.pl->js.ncols, in_dim);
+  sgemm_kernel<true, true, EPI_BIAS_C0><<<grid, SG_THREADS, 0, st>>>(X, W, Z, M, out_dim, in_dim, in_dim, in_dim,
+                                                                      out_dim, b, ncols, in_dim);
   PK_LAUNCH_OK();
   return 0;
+}
+
+static int gemm_fwd(const ChunkCtx& c, const float* X, const float* W, const float* b, float* Z, int in_dim, int out_dim) {
+  ProfScope ps(PC_GEMM_FWD, c.st);
+  return linear_fwd_any(X, W, b, Z, c.n * c.pl->js.ncols, in_dim, out_dim, c.pl->js.ncols, c.pl->sm_count, c.st, tc_enabled());
 }
 
 static int gemm_dgrad(const ChunkCtx& c, const float* Zb, const float* W, float* Xb, int in_dim, int out_dim) {
   ProfScope ps(PC_GEMM_DGRAD, c.st);
   const int64_t M = c.n * c.pl->js.ncols;
+  if (tc_enabled()) {
+    int rc = tc_linear_dgrad(Zb, W, Xb, M, in_dim, out_dim, c.pl->sm_count, c.st);
+    if (rc == 0) { g_launches.fetch_add(1); return 0; }
+    if (rc != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, std::string("tc_linear_dgrad launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+  }
   dim3 grid(blocks_for(M, SG_BM), blocks_for(in_dim, SG_BN), 1);
   sgemm_kernel<true, false, EPI_STORE><<<grid, SG_THREADS, 0, c.st>>>(Zb, W, Xb, M, in_dim, out_dim, out_dim, in_dim,
                                                                        in_dim, nullptr, 1, out_dim);
@@ -300,6 +320,11 @@ static int gemm_dgrad(const ChunkCtx& c, const float* Zb, const float* W, float*
 static int gemm_wgrad(const ChunkCtx& c, const float* Zb, const float* X, float* gW, float* gb, int in_dim, int out_dim) {
   ProfScope ps(PC_GEMM_WGRAD, c.st);
   const int64_t M = c.n * c.pl->js.ncols;   // contraction length
+  if (tc_enabled() && gW) {
+    int rc = tc_linear_wgrad(Zb, X, gW, gb, M, in_dim, out_dim, c.pl->js.ncols, c.pl->sm_count, c.st);
+    if (rc == 0) { g_launches.fetch_add(1); return 0; }
+    if (rc != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, std::string("tc_linear_wgrad launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+  }
   if (gW) {
     const unsigned tiles = blocks_for(out_dim, SG_BM) * blocks_for(in_dim, SG_BN);
     int64_t splits = (2 * (int64_t)c.pl->sm_count + tiles - 1) / tiles;
@@ -350,6 +375,14 @@ static int ln_bwd(const ChunkCtx& c, const float* Z, const float* Gin, float* Go
   return 0;
 }
 
+// (K0, K1) of the fused tcgen05 epilogues, or false when the jet spec has more than two directions
+static bool jet_orders(const JetSpec& js, int& k0, int& k1) {
+  if (js.ndirs > 2) return false;
+  k0 = js.ndirs > 0 ? js.order[0] : 0;
+  k1 = js.ndirs > 1 ? js.order[1] : 0;
+  return true;
+}
+
 // forward jets of one chunk; fills the stash and U[n, C]
 template <int MAXK>
 static int forward_chunk(const ChunkCtx& c) {
@@ -376,6 +409,17 @@ static int forward_chunk(const ChunkCtx& c) {
           last_linear_fwd_kernel<<<blocks_for(rows * 32, threads), threads, 0, c.st>>>(in, rows, o.in_dim, js.ncols, W, b, c.U());
           PK_LAUNCH_OK();
         } else {
+          // Linear + activation in one tcgen05 kernel when the next op is a plain activation
+          int k0 = 0, k1 = 0;
+          if (tc_enabled() && i + 1 < n_ops - 1 && pl->ops[i + 1].op.kind == PINNK_OP_ACT && pl->ops[i + 1].skip_src < 0 &&
+              jet_orders(js, k0, k1)) {
+            const PinnkOp& a = pl->ops[i + 1].op;
+            ProfScope ps(PC_GEMM_FWD, c.st);
+            int rc = tc_linear_act_fwd(in, W, b, c.stash(i), c.stash(i + 1), c.n * js.ncols, o.in_dim, o.out_dim, k0, k1,
+                                       a.act == PINNK_ACT_TANH ? 1 : 2, a.scale, pl->sm_count, c.st);
+            if (rc == 0) { g_launches.fetch_add(1); ++i; break; }
+            if (rc != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, std::string("tc_linear_act_fwd launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+          }
           int rc = gemm_fwd(c, in, W, b, c.stash(i), o.in_dim, o.out_dim);
           if (rc) return rc;
         }
@@ -434,13 +478,13 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad) {
         if (i == n_ops - 1) {
           ProfScope ps(PC_LAST_BWD, c.st);
           const int64_t rows = c.n * js.ncols;
-          dim3 grid(blocks_for(o.in_dim, 128), (unsigned)std::min<int64_t>(rows, 4 * (int64_t)pl->sm_count));
+          dim3 grid(blocks_for(o.in_dim, 128), (unsigned)std::min<int64_t>(rows, 32 * (int64_t)pl->sm_count));
           last_linear_bwd_kernel<<<grid, 128, 0, c.st>>>(in, c.Ub(), rows, o.in_dim, js.ncols, W, c.adj(cur),
                                                          G(o.gw_offset), G(o.gb_offset));
           PK_LAUNCH_OK();
         } else if (i == 0) {
           ProfScope ps(PC_FIRST_BWD, c.st);
-          dim3 grid(blocks_for(o.out_dim, 128), (unsigned)std::min<int64_t>(c.n, 2 * (int64_t)pl->sm_count));
+          dim3 grid(blocks_for(o.out_dim, 128), (unsigned)std::min<int64_t>(c.n, 32 * (int64_t)pl->sm_count));
           first_linear_bwd_kernel<<<grid, 128, 0, c.st>>>(c.x, c.t, c.n, o.out_dim, js, c.adj(cur), G(o.gw_offset), G(o.gb_offset));
           PK_LAUNCH_OK();
         } else {
@@ -448,6 +492,17 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad) {
           if (rc) return rc;
           if (i > first_trainable) {
             const int nxt = other(cur, held);
+            // dgrad + adjoint of the activation feeding this Linear in one tcgen05 kernel
+            int k0 = 0, k1 = 0;
+            const OpRt& pa = pl->ops[i - 1];
+            if (tc_enabled() && r.in_op == i - 1 && pa.op.kind == PINNK_OP_ACT && pa.skip_src < 0 && pa.in_op >= 0 &&
+                jet_orders(js, k0, k1)) {
+              ProfScope ps(PC_GEMM_DGRAD, c.st);
+              rc = tc_linear_dgrad_actbwd(c.adj(cur), W, c.stash(pa.in_op), c.adj(nxt), c.n * js.ncols, o.in_dim, o.out_dim,
+                                          k0, k1, pa.op.act == PINNK_ACT_TANH ? 1 : 2, pa.op.scale, pl->sm_count, c.st);
+              if (rc == 0) { g_launches.fetch_add(1); cur = nxt; --i; break; }
+              if (rc != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, std::string("tc_linear_dgrad_actbwd launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+            }
             rc = gemm_dgrad(c, c.adj(cur), W, c.adj(nxt), o.in_dim, o.out_dim);
             if (rc) return rc;
             cur = nxt;
@@ -613,3 +668,76 @@ extern "C" int pinnk_score(pinnk_plan_t plan, const float* const* params, const 
   }
   return 0;
 }
+
+// ---- debug / micro-benchmark entry: one hidden Linear forward, Z[M,N] = X[M,K] W[N,K]^T (+bias on value rows).
+// mode 0 = exact-fp32 CUDA-core GEMM, 1 = tcgen05 3xTF32 (fails if the shape is unsupported).
+extern "C" int pinnk_debug_linear_fwd(const float* X, const float* W, const float* bias, float* Z, int64_t M, int32_t K,
+                                      int32_t N, int32_t jet_cols, int32_t mode, void* stream) {
+  if (!X || !W || !Z || M < 1 || (K % 4) || (N % 4) || jet_cols < 1) return fail(PINNK_E_INVALID, "debug_linear_fwd: bad argument");
+  int smc = 148;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, dev);
+  if (mode == 1) {
+    int rc = tc_linear_fwd(X, W, bias, Z, M, K, N, jet_cols, smc, (cudaStream_t)stream);
+    if (rc == TC_UNSUPPORTED) return fail(PINNK_E_INVALID, "debug_linear_fwd: shape not covered by the tcgen05 path");
+    if (rc != 0) return fail(PINNK_E_CUDA, std::string("tc_linear_fwd: ") + cudaGetErrorString(cudaGetLastError()));
+    g_launches.fetch_add(1);
+    return 0;
+  }
+  return linear_fwd_any(X, W, bias, Z, M, K, N, jet_cols, smc, (cudaStream_t)stream, false);
+}
+
+// dX[M,K_in] = dZ[M,N] W[N,K_in]  (mode as above)
+extern "C" int pinnk_debug_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t M, int32_t K, int32_t N,
+                                        int32_t mode, void* stream) {
+  if (!dZ || !W || !dX || M < 1 || (K % 4) || (N % 4)) return fail(PINNK_E_INVALID, "debug_linear_dgrad: bad argument");
+  int smc = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 1) {
+    int rc = tc_linear_dgrad(dZ, W, dX, M, K, N, smc, st);
+    if (rc == TC_UNSUPPORTED) return fail(PINNK_E_INVALID, "debug_linear_dgrad: shape not covered by the tcgen05 path");
+    if (rc != 0) return fail(PINNK_E_CUDA, std::string("tc_linear_dgrad: ") + cudaGetErrorString(cudaGetLastError()));
+    g_launches.fetch_add(1);
+    return 0;
+  }
+  dim3 grid(blocks_for(M, SG_BM), blocks_for(K, SG_BN), 1);
+  sgemm_kernel<true, false, EPI_STORE><<<grid, SG_THREADS, 0, st>>>(dZ, W, dX, M, K, N, N, K, K, nullptr, 1, N);
+  PK_LAUNCH_OK();
+  return 0;
+}
+
+// dW[N,K_in] += dZ[M,N]^T X[M,K_in] ; db[N] += sum of value-column rows of dZ  (mode as above)
+extern "C" int pinnk_debug_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int32_t K,
+                                        int32_t N, int32_t jet_cols, int32_t mode, void* stream) {
+  if (!dZ || !X || !dW || M < 1 || (K % 4) || (N % 4) || jet_cols < 1 || (M % jet_cols)) return fail(PINNK_E_INVALID, "debug_linear_wgrad: bad argument");
+  int smc = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (mode == 1) {
+    int rc = tc_linear_wgrad(dZ, X, dW, db, M, K, N, jet_cols, smc, st);
+    if (rc == TC_UNSUPPORTED) return fail(PINNK_E_INVALID, "debug_linear_wgrad: shape not covered by the tcgen05 path");
+    if (rc != 0) return fail(PINNK_E_CUDA, std::string("tc_linear_wgrad: ") + cudaGetErrorString(cudaGetLastError()));
+    g_launches.fetch_add(1);
+    return 0;
+  }
+  const unsigned tiles = blocks_for(N, SG_BM) * blocks_for(K, SG_BN);
+  int64_t splits = (2 * (int64_t)smc + tiles - 1) / tiles;
+  int64_t k_chunk = align_up((M + splits - 1) / splits, 64);
+  if (k_chunk < 256) k_chunk = 256;
+  splits = (M + k_chunk - 1) / k_chunk;
+  dim3 grid(blocks_for(N, SG_BM), blocks_for(K, SG_BN), (unsigned)splits);
+  sgemm_kernel<false, false, EPI_ATOMIC><<<grid, SG_THREADS, 0, st>>>(dZ, X, dW, N, K, M, N, K, K, nullptr, 1, k_chunk);
+  PK_LAUNCH_OK();
+  if (db) {
+    dim3 g2(blocks_for(N, 128), (unsigned)std::min<int64_t>(M / jet_cols, 256));
+    bias_grad_kernel<<<g2, 128, 0, st>>>(dZ, M / jet_cols, N, jet_cols, db);
+    PK_LAUNCH_OK();
+  }
+  return 0;
+}
+
+extern "C" void pinnk_debug_set_clock_buffer(long long* dev_buf) { tc::g_tc_clk = dev_buf; }

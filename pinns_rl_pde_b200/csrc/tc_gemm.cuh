@@ -1,14 +1,1054 @@
-// tc_gemm.cuh -- tcgen05 (5th-gen tensor core) 3xTF32 GEMM path for the hidden Linear layers.
+// tc_gemm.cuh -- tcgen05 (5th-gen tensor core) 3xTF32 GEMMs for the hidden Linear layers (sm_100a).
+//
+// fp32 accuracy on the TF32 tensor pipe: every fp32 operand x is split once into
+//     x_hi = tf32(x)            (cvt.rna, low 13 mantissa bits zero)
+//     x_lo = tf32(x - x_hi)     (exact difference, then rounded)
+// and  A*B ~= A_lo*B_hi + A_hi*B_lo + A_hi*B_hi  is accumulated in fp32 in tensor memory (TMEM)
+// by three tcgen05.mma.kind::tf32 per K-step (the dropped lo*lo term is ~2^-22 relative).
+//
+// Orientation ("features on lanes"): D[feature, row] = W[feature, :] . X[row, :]
+//     A operand = W   [128 out-features x K]   K-major, resident in shared memory for the whole kernel
+//     B operand = X   [TN rows          x K]   K-major, streamed tile by tile (rows = point*jet columns)
+//     D         in TMEM: lane = out-feature, column = row of the tile
+// so an epilogue thread owns one feature and sees all jet columns of a point in consecutive TMEM
+// columns, and a warp's global/shared accesses for one row are 128 contiguous bytes.
+//
+// Shared-memory operand layout = the canonical UMMA K-major SWIZZLE_128B layout: the K axis is cut into
+// 32-element (128 B) blocks; inside a block rows are 128 B apart, 8-row groups 1024 B apart, and the
+// 16-byte chunk index of a row is XORed with (row % 8).
+//
+// Warp roles (1 CTA per SM, persistent over row tiles):
+//     NLW warps  loaders : global fp32 -> hi/lo split in registers -> swizzled smem stage (register prefetch ring)
+//     4 warps    epilogue: TMEM -> registers (tcgen05.ld) -> (+bias) -> global
+//     1 warp     MMA     : one elected thread issues tcgen05.mma / tcgen05.commit; owns TMEM alloc
+// Pipelines: smem full/empty mbarriers (loaders <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
+#include "jet_math.cuh"
 
 namespace pinnk {
 constexpr int TC_UNSUPPORTED = 1;
 
+namespace tc {
+
+static long long* g_tc_clk = nullptr;   // optional device buffer [grid][8] of per-role cycle counters (debug)
+constexpr int kEpiThreads = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug must trap (error returned to the host), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {   // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {     // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {                        // one thread
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, issued by one thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 consecutive TMEM columns of this thread's lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 16 consecutive TMEM columns of this thread's lane, no wait (caller issues tmem_wait_ld once for a batch of loads)
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor, K-major, SWIZZLE_128B: SBO = 1024 B (one 8-row group), LBO unused (1)
+__device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);     // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                          // leading byte offset (ignored for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset, bits [32,46)
+  d |= (uint64_t)1 << 46;                          // descriptor version 1 (Blackwell)
+  d |= (uint64_t)2 << 61;                          // layout type: SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=tf32, both K-major, M x N
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ void split4(const float4& v, float4& hi, float4& lo) {
+  hi.x = to_tf32(v.x); hi.y = to_tf32(v.y); hi.z = to_tf32(v.z); hi.w = to_tf32(v.w);
+  lo.x = to_tf32(v.x - hi.x); lo.y = to_tf32(v.y - hi.y); lo.z = to_tf32(v.z - hi.z); lo.w = to_tf32(v.w - hi.w);
+}
+// byte offset of 16-byte chunk `chunk` (along K) of row `row` inside a K-major SW128 operand with `rows` rows
+__device__ __forceinline__ uint32_t sw128_offset(int rows, int row, int chunk) {
+  const int kb = chunk >> 3, cj = chunk & 7;
+  return (uint32_t)(kb * rows * 128 + (row >> 3) * 1024 + (row & 7) * 128 + ((cj ^ (row & 7)) << 4));
+}
+
+// UMMA shared-memory matrix descriptor, MN-major tf32.  32-bit MN-major operands must use the SWIZZLE_128B_BASE32B
+// layout (type 1): an atom is 4 K-rows x 128 B (32 floats along M/N), rows 128 B apart, the 32-byte chunk index of
+// a row XORed with (row % 4).  Further 32-float groups along M/N are LBO bytes apart, further 4-row groups along K are
+// SBO bytes apart; one kind::tf32 MMA (K = 8) consumes two 4-row groups.
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                          // layout type: SWIZZLE_128B_BASE32B
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int M, int N) {   // both operands MN-major
+  return make_idesc_tf32(M, N) | (1u << 15) | (1u << 16);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// "features on lanes" GEMM over row tiles (forward and dgrad share it):
+//   TRANS_W = false:  Y[M, ldy] (cols n0..n0+127) = X[M, K] * W[n0.., 0..K)^T  (+ bias on rows with row % jet_cols == 0)
+//                     W is [n_out, K] row-major (ldw = K)                      -- nn.Linear forward
+//   TRANS_W = true :  Y[M, ldy] (cols n0..n0+127) = X[M, K] * W[0..K, n0..)    -- dgrad: X = dL/dZ [M, out=K], W is
+//                     [out=K, in] row-major (ldw = in), Y = dL/dX [M, in]
+// NLW loader warps (global fp32 -> hi/lo -> swizzled smem, PF tiles of register prefetch), 4 epilogue warps, 1 MMA warp.
+template <int K, int TN, int STAGES, int ACC, int NLW, int PF, bool TRANS_W>
+__global__ void __launch_bounds__((NLW + 4 * (TN / 16) + 1) * 32, 1)
+linear_rows_kernel(const float* __restrict__ X, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
+                   float* __restrict__ Y, int64_t M, int ldy, int jet_cols, int dbg, long long* __restrict__ clk) {
+  static_assert(K % 32 == 0 && TN % 16 == 0 && TN <= 256 && (TN % NLW) == 0, "tile shape");
+  long long c_wait0 = 0, c_wait1 = 0, c_work = 0, c_t = 0;
+#define CLK_MARK(acc) do { if (clk) { long long _n = clock64(); acc += _n - c_t; c_t = _n; } } while (0)
+  if (clk) c_t = clock64();
+  constexpr int KB = K / 32;                      // 128-byte K blocks
+  constexpr int CHUNKS = K / 4;                   // 16-byte chunks per row
+  constexpr uint32_t W_BYTES = 128 * K * 4;       // one of W_hi / W_lo
+  constexpr uint32_t X_BYTES = TN * K * 4;        // one of X_hi / X_lo per stage
+  constexpr int EH = TN / 16;                     // epilogue warps per TMEM lane quarter: 16 tile rows each
+  constexpr int NEW = 4 * EH;
+  constexpr int NTHREADS = (NLW + NEW + 1) * 32;
+  constexpr int EPI0 = NLW, MMAW = NLW + NEW;
+  static_assert(EPI0 % 4 == 0, "epilogue warps must start at a multiple of 4 (TMEM lane quarters)");
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_hi = smem;
+  uint8_t* w_lo = smem + W_BYTES;
+  uint8_t* x_st = smem + 2 * W_BYTES;             // [STAGES][hi|lo][X_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(x_st + (size_t)STAGES * 2 * X_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * 128;
+  const int64_t ntiles = (M + TN - 1) / TN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], NLW); mbar_init(&empty[s], 1); }     // one arrive per warp
+    for (int b = 0; b < ACC; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], NEW); }
+    fence_mbar_init();
+  }
+  // TMEM: per accumulator buffer KB "main" partials (one per 32-wide K block, 4 accumulate steps each) plus one
+  // "correction" partial (the lo*hi + hi*lo terms).  The tensor core rounds every accumulate step toward zero, so
+  // short accumulation chains summed afterwards in registers (round-to-nearest) keep the result at fp32 quality.
+  constexpr int BUF_COLS = TN * (KB + 1);
+  constexpr uint32_t TMEM_COLS = (ACC * BUF_COLS <= 32) ? 32 : (ACC * BUF_COLS <= 64) ? 64 : (ACC * BUF_COLS <= 128) ? 128
+                               : (ACC * BUF_COLS <= 256) ? 256 : 512;
+  static_assert(ACC * BUF_COLS <= 512, "TMEM budget");
+  if (warp == MMAW) tmem_alloc(tmem_slot, TMEM_COLS);
+  // resident weights: split to hi/lo and store in the swizzled A-operand layout (row = output feature of this kernel)
+  if (!TRANS_W) {
+    for (int idx = threadIdx.x; idx < 128 * CHUNKS; idx += NTHREADS) {
+      const int row = idx / CHUNKS, chunk = idx - row * CHUNKS;
+      const float4 v = *reinterpret_cast<const float4*>(W + (int64_t)(n0 + row) * ldw + chunk * 4);
+      float4 hi, lo;
+      split4(v, hi, lo);
+      const uint32_t off = sw128_offset(128, row, chunk);
+      *reinterpret_cast<float4*>(w_hi + off) = hi;
+      *reinterpret_cast<float4*>(w_lo + off) = lo;
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < K * 32; idx += NTHREADS) {        // 32 float4 per W row segment [k, n0..n0+127]
+      const int k = idx >> 5, c4 = idx & 31;
+      const float4 v = *reinterpret_cast<const float4*>(W + (int64_t)k * ldw + n0 + c4 * 4);
+      float4 hi, lo;
+      split4(v, hi, lo);
+      const float h[4] = {hi.x, hi.y, hi.z, hi.w}, l[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const uint32_t off = sw128_offset(128, c4 * 4 + e, k >> 2) + (uint32_t)(k & 3) * 4;
+        *reinterpret_cast<float*>(w_hi + off) = h[e];
+        *reinterpret_cast<float*>(w_lo + off) = l[e];
+      }
+    }
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < NLW) {
+    // ===================== loaders =====================
+    constexpr int PER_ROW = (CHUNKS + 31) / 32;          // chunks per lane per row
+    constexpr int RPW = TN / NLW;                        // rows per warp per tile
+    float4 v[PF][RPW][PER_ROW];
+    auto issue = [&](int64_t tile, float4 (&dst)[RPW][PER_ROW]) {
+      const int64_t r0 = tile * TN;
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) {
+        const int64_t row = r0 + warp + NLW * i;
+#pragma unroll
+        for (int c = 0; c < PER_ROW; ++c) {
+          const int chunk = lane + 32 * c;
+          dst[i][c] = (tile < ntiles && row < M && chunk < CHUNKS && !(dbg & 1))
+                          ? __ldg(reinterpret_cast<const float4*>(X + row * K + chunk * 4))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    };
+    const int64_t stride = gridDim.x;
+    int64_t tile = blockIdx.x;
+#pragma unroll
+    for (int d = 0; d < PF; ++d) issue(tile + d * stride, v[d]);
+    int it = 0;
+    while (tile < ntiles) {
+#pragma unroll
+      for (int d = 0; d < PF; ++d) {
+        if (tile < ntiles) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          CLK_MARK(c_work);
+          mbar_wait(&empty[s], ph ^ 1u);
+          CLK_MARK(c_wait0);
+          uint8_t* xh = x_st + (size_t)s * 2 * X_BYTES;
+          uint8_t* xl = xh + X_BYTES;
+#pragma unroll
+          for (int i = 0; i < RPW; ++i) {
+            const int r = warp + NLW * i;
+#pragma unroll
+            for (int c = 0; c < PER_ROW; ++c) {
+              const int chunk = lane + 32 * c;
+              if (chunk < CHUNKS) {
+                float4 hi, lo;
+                split4(v[d][i][c], hi, lo);
+                const uint32_t off = sw128_offset(TN, r, chunk);
+                *reinterpret_cast<float4*>(xh + off) = hi;
+                *reinterpret_cast<float4*>(xl + off) = lo;
+              }
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[s]);
+          issue(tile + PF * stride, v[d]);
+          tile += stride;
+          ++it;
+        }
+      }
+    }
+    if (clk && threadIdx.x == 0) { CLK_MARK(c_work); clk[blockIdx.x * 8 + 0] = c_wait0; clk[blockIdx.x * 8 + 1] = c_work; }
+  } else if (warp < MMAW) {
+    // ===================== epilogue: warp (q, h) owns lanes 32q.. and tile rows 16h..16h+15 =====================
+    const int e = warp - EPI0;
+    const int q = e & 3, h = e >> 2;
+    const int f = q * 32 + lane;
+    const float bf = (!TRANS_W && bias) ? bias[n0 + f] : 0.f;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int b = it % ACC;
+      const uint32_t ph = (uint32_t)(it / ACC) & 1u;
+      const int64_t r0 = tile * TN + h * 16;
+      // which of my 16 rows are value-column rows (bias applies): bit j set <=> (r0 + j) % jet_cols == 0
+      uint32_t vmask = 0;
+      if (!TRANS_W && bias) {
+        int cj = (int)((uint32_t)r0 % (uint32_t)jet_cols);     // row counts of a chunk fit 32 bits
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { vmask |= (cj == 0 ? 1u : 0u) << j; cj = (cj + 1 == jet_cols) ? 0 : cj + 1; }
+      }
+      float* yp = Y + r0 * ldy + n0 + f;
+      CLK_MARK(c_work);
+      mbar_wait(&tfull[b], ph);
+      CLK_MARK(c_wait0);
+      tc_fence_after();
+      const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BUF_COLS + h * 16);
+      uint32_t part[KB + 1][16];
+#pragma unroll
+      for (int kb = 0; kb <= KB; ++kb) tmem_ld16_nowait(tb + kb * TN, part[kb]);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[b]);
+      const int nrows = (M - r0 >= 16) ? 16 : (int)(M - r0 > 0 ? M - r0 : 0);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float v = __uint_as_float(part[KB][j]);               // correction partial first (smallest magnitude)
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) v += __uint_as_float(part[kb][j]);
+        if ((vmask >> j) & 1u) v += bf;
+        if (j < nrows && !(dbg & 4)) yp[(int64_t)j * ldy] = v;
+      }
+    }
+    if (clk && threadIdx.x == EPI0 * 32) { CLK_MARK(c_work); clk[blockIdx.x * 8 + 2] = c_wait0; clk[blockIdx.x * 8 + 3] = c_work; }
+  } else {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(128, TN);
+      // descriptors differ only in the 14-bit start-address field (16-byte units): build the constant part once
+      const uint64_t dconst = make_desc_k_sw128(0);
+      const uint32_t wh = smem_u32(w_hi) >> 4, wl = smem_u32(w_lo) >> 4;
+      int it = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it % STAGES, b = it % ACC;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u, bph = (uint32_t)(it / ACC) & 1u;
+        CLK_MARK(c_work);
+        mbar_wait(&tempty[b], bph ^ 1u);
+        CLK_MARK(c_wait0);
+        mbar_wait(&full[s], ph);
+        CLK_MARK(c_wait1);
+        tc_fence_after();
+        const uint32_t xh = smem_u32(x_st + (size_t)s * 2 * X_BYTES) >> 4, xl = xh + (X_BYTES >> 4);
+        const uint32_t d = tmem_base + (uint32_t)(b * BUF_COLS);
+        const uint32_t d_corr = d + (uint32_t)(KB * TN);
+        if (!(dbg & 2))
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            constexpr uint32_t dummy = 0; (void)dummy;
+            const uint32_t ao = (uint32_t)((kb * 128 * 128 + ks * 32) >> 4), bo = (uint32_t)((kb * TN * 128 + ks * 32) >> 4);
+            const uint64_t a_hi = dconst | (uint64_t)(wh + ao), a_lo = dconst | (uint64_t)(wl + ao);
+            const uint64_t b_hi = dconst | (uint64_t)(xh + bo), b_lo = dconst | (uint64_t)(xl + bo);
+            umma_tf32(d_corr, a_lo, b_hi, idesc, (kb | ks) ? 1u : 0u);
+            umma_tf32(d_corr, a_hi, b_lo, idesc, 1);
+            umma_tf32(d + (uint32_t)(kb * TN), a_hi, b_hi, idesc, ks ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[s]);     // smem stage may be refilled once these MMAs have read it
+        umma_commit(&tfull[b]);     // accumulator complete
+      }
+      if (clk) { CLK_MARK(c_work); clk[blockIdx.x * 8 + 4] = c_wait0; clk[blockIdx.x * 8 + 5] = c_wait1; clk[blockIdx.x * 8 + 6] = c_work; }
+    }
+    __syncwarp();
+  }
+#undef CLK_MARK
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMAW) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+template <int K, int TN, int STAGES, int ACC, int NLW, int PF, bool TRANS_W>
+static int launch_linear_rows(const float* X, const float* W, int ldw, const float* bias, float* Y, int64_t M, int n_cols,
+                              int jet_cols, int sm_count, cudaStream_t st) {
+  constexpr size_t smem = 1024 + 2 * (size_t)128 * K * 4 + (size_t)STAGES * 2 * TN * K * 4 + (2 * STAGES + 2 * ACC) * 8 + 16;
+  static_assert(smem <= 232448, "shared memory budget (227 KB per CTA)");
+  auto kern = linear_rows_kernel<K, TN, STAGES, ACC, NLW, PF, TRANS_W>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    configured = true;
+  }
+  const int64_t ntiles = (M + TN - 1) / TN;
+  const int per_y = n_cols / 128;
+  int gx = sm_count / per_y;
+  if (gx < 1) gx = 1;
+  if ((int64_t)gx > ntiles) gx = (int)ntiles;
+  dim3 grid((unsigned)gx, (unsigned)per_y, 1);
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("PINNK_TC_DBG"); dbg = e ? atoi(e) : 0; }
+  kern<<<grid, (NLW + 4 * (TN / 16) + 1) * 32, smem, st>>>(X, W, ldw, bias, Y, M, n_cols, jet_cols, dbg, g_tc_clk);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TS variant of the rows kernel for K = 128: the resident weight operand lives in TENSOR MEMORY (A-from-TMEM,
+// tcgen05.mma [d], [a], bdesc), which (1) removes the 4 KB shared-memory read of A that every SS-mode MMA pays and
+// (2) frees 128 KB of shared memory, so row tiles are 64 wide (half the MMA instructions per row) and 3 deep.
+//   TMEM columns: [0,128) W_hi | [128,256) W_lo | 2 accumulator buffers x {main 64, correction 64}
+// fp32 -> tf32 hi/lo splitting uses integer round-to-nearest (2 ALU ops per conversion).
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// round-to-nearest (ties away) fp32 -> tf32 on the bit pattern: what cvt.rna.tf32.f32 computes for finite inputs
+__device__ __forceinline__ uint32_t rn_tf32_bits(uint32_t b) { return (b + 0x1000u) & 0xFFFFE000u; }
+__device__ __forceinline__ void split_bits(float v, uint32_t& hi, uint32_t& lo) {
+  hi = rn_tf32_bits(__float_as_uint(v));
+  lo = rn_tf32_bits(__float_as_uint(v - __uint_as_float(hi)));
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// EPI selects the epilogue:
+//   EPI_PLAIN   Y = acc (+ bias on value rows)
+//   EPI_ACT     forward Linear + activation jets: Y = Z = acc + bias (the stash the reverse pass needs) and
+//               Yact = act(Z) jets (the next layer's operand)              -- replaces gemm + act_fwd_kernel
+//   EPI_ACTBWD  dgrad + activation adjoint: acc = dL/d(act output); Zs = stashed pre-activation jets of that activation;
+//               Y = dL/d(pre-activation)                                   -- replaces gemm + act_bwd_kernel
+// For the fused epilogues the jet layout is a compile-time (K0, K1): value column, K0 columns of direction 0, K1 of
+// direction 1, with C = 1 + K0 + K1 dividing 32 so that every epilogue warp owns whole points.
+enum { EPI_PLAIN = 0, EPI_ACT = 1, EPI_ACTBWD = 2 };
+
+template <bool TRANS_W, int EPI, int ACT, int K0, int K1, int NLW, int ECOLS>
+__global__ void __launch_bounds__((NLW + 4 * (64 / ECOLS) + 1) * 32, 1)
+linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
+                      float* __restrict__ Y, int64_t M, int ldy, int jet_cols, const float* __restrict__ Zs,
+                      float* __restrict__ Yact, float omega) {
+  constexpr int K = 128, TN = 64, STAGES = 3, ACC = 2, NEW = 4 * (TN / ECOLS);
+  static_assert(ECOLS == 16 || ECOLS == 32, "epilogue warps own 16 or 32 tile rows");
+  constexpr int JC = 1 + K0 + K1;                       // jet columns of the fused epilogues
+  constexpr int MAXK = (K0 > K1 ? K0 : K1) > 0 ? (K0 > K1 ? K0 : K1) : 1;
+  static_assert(EPI == EPI_PLAIN || (ECOLS % JC) == 0, "fused epilogues need the jet column count to divide the rows per epilogue warp");
+  constexpr int CHUNKS = K / 4;
+  constexpr uint32_t X_BYTES = TN * K * 4;        // one of X_hi / X_lo per stage (32 KB)
+  constexpr int EPI0 = NLW, MMAW = NLW + NEW;
+  constexpr uint32_t COL_WHI = 0, COL_WLO = 128, COL_ACC = 256;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* x_st = smem;                           // [STAGES][hi|lo][X_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(x_st + (size_t)STAGES * 2 * X_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * 128;
+  const int64_t ntiles = (M + TN - 1) / TN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], NLW); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < ACC; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], NEW); }
+    fence_mbar_init();
+  }
+  if (warp == MMAW) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // resident weights -> TMEM: thread f of the first four epilogue warps owns row f of the A operand (lane f)
+  if (warp >= EPI0 && warp < EPI0 + 4) {
+    const int q = warp - EPI0, f = q * 32 + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+    for (int c0 = 0; c0 < K; c0 += 32) {
+      uint32_t hi[32], lo[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float v = TRANS_W ? W[(int64_t)(c0 + j) * ldw + n0 + f] : W[(int64_t)(n0 + f) * ldw + c0 + j];
+        split_bits(v, hi[j], lo[j]);
+      }
+      tmem_st32(lane_base + COL_WHI + c0, hi);
+      tmem_st32(lane_base + COL_WLO + c0, lo);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp < NLW) {
+    // ===================== loaders: 64 rows x 32 chunks per tile, 8 chunks per thread =====================
+    constexpr int RPW = TN / NLW;                        // 8 rows per warp per tile, lane = chunk
+    float4 v[RPW];
+    auto issue = [&](int64_t tile) {
+      const int64_t r0 = tile * TN;
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) {
+        const int64_t row = r0 + warp + NLW * i;
+        v[i] = (tile < ntiles && row < M) ? __ldg(reinterpret_cast<const float4*>(X + row * K + lane * 4))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    issue(blockIdx.x);
+    const uint32_t x_base = smem_u32(x_st);
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(&empty[s], ph ^ 1u);
+      const uint32_t xh = x_base + (uint32_t)s * 2 * X_BYTES, xl = xh + X_BYTES;
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) {
+        const int r = warp + NLW * i;
+        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+        split_bits(v[i].x, h0, l0); split_bits(v[i].y, h1, l1); split_bits(v[i].z, h2, l2); split_bits(v[i].w, h3, l3);
+        const uint32_t off = sw128_offset(TN, r, lane);
+        sts128(xh + off, h0, h1, h2, h3);
+        sts128(xl + off, l0, l1, l2, l3);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+      issue(tile + gridDim.x);
+    }
+  } else if (warp < MMAW) {
+    // ===================== epilogue: warp (q, h) owns lanes 32q.. and tile rows ECOLS*h .. ECOLS*h + ECOLS-1 ==========
+    const int e = warp - EPI0;
+    const int q = e & 3, h = e >> 2;
+    const int f = q * 32 + lane;
+    const float bf = (!TRANS_W && bias) ? bias[n0 + f] : 0.f;
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int b = it % ACC;
+      const uint32_t ph = (uint32_t)(it / ACC) & 1u;
+      const int64_t r0 = tile * TN + h * ECOLS;
+      uint32_t vmask = 0;
+      if (!TRANS_W && bias) {
+        int cj = (int)((uint32_t)r0 % (uint32_t)jet_cols);
+#pragma unroll
+        for (int j = 0; j < ECOLS; ++j) { vmask |= (cj == 0 ? 1u : 0u) << j; cj = (cj + 1 == jet_cols) ? 0 : cj + 1; }
+      }
+      float* yp = Y + r0 * ldy + n0 + f;
+      const int nrows = (M - r0 >= ECOLS) ? ECOLS : (int)(M - r0 > 0 ? M - r0 : 0);
+      // the stashed pre-activations do not depend on the MMA: fetch them while the accumulator is still being produced
+      float zsr[(EPI == EPI_ACTBWD) ? ECOLS : 1];
+      if constexpr (EPI == EPI_ACTBWD) {
+        const float* zs0 = Zs + r0 * ldy + n0 + f;
+#pragma unroll
+        for (int j = 0; j < ECOLS; ++j) zsr[j] = (j < nrows) ? __ldg(zs0 + (int64_t)j * ldy) : 0.f;
+      }
+      mbar_wait(&tfull[b], ph);
+      tc_fence_after();
+      const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + COL_ACC + (uint32_t)(b * 2 * TN + h * ECOLS);
+      uint32_t pm[ECOLS], pc[ECOLS];
+      if constexpr (ECOLS == 32) { tmem_ld32_nowait(tb, pm); tmem_ld32_nowait(tb + TN, pc); }
+      else { tmem_ld16_nowait(tb, pm); tmem_ld16_nowait(tb + TN, pc); }
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[b]);
+      if constexpr (EPI == EPI_PLAIN) {
+        if (nrows == ECOLS) {
+#pragma unroll
+          for (int j = 0; j < ECOLS; ++j) {
+            float val = __uint_as_float(pc[j]) + __uint_as_float(pm[j]);
+            if ((vmask >> j) & 1u) val += bf;
+            yp[(int64_t)j * ldy] = val;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < ECOLS; ++j) {
+            float val = __uint_as_float(pc[j]) + __uint_as_float(pm[j]);
+            if ((vmask >> j) & 1u) val += bf;
+            if (j < nrows) yp[(int64_t)j * ldy] = val;
+          }
+        }
+      } else {
+        // whole points: columns [pp*JC, pp*JC + JC) of this warp's 32 are the jet of point pp at feature f
+        float* ya = (EPI == EPI_ACT) ? Yact + r0 * ldy + n0 + f : nullptr;
+#pragma unroll
+        for (int pp = 0; pp < ECOLS / JC; ++pp) {
+          const int jb = pp * JC;
+          if (jb < nrows) {
+            float z[MAXK + 1], y[MAXK + 1], w[MAXK + 1];
+            if constexpr (EPI == EPI_ACT) {
+              z[0] = __uint_as_float(pc[jb]) + __uint_as_float(pm[jb]) + bf;
+              yp[(int64_t)jb * ldy] = z[0];
+              if (ACT == 1) { y[0] = tanhf(z[0]); w[0] = 1.f - y[0] * y[0]; }
+              else { z[0] *= omega; sincosf(z[0], &y[0], &w[0]); }
+              ya[(int64_t)jb * ldy] = y[0];
+#pragma unroll
+              for (int d = 0; d < 2; ++d) {
+                const int KD = d ? K1 : K0, cb = jb + (d ? K0 : 0);
+                if (KD > 0) {
+#pragma unroll
+                  for (int k = 1; k <= MAXK; ++k)
+                    if (k <= KD) {
+                      z[k] = __uint_as_float(pc[cb + k]) + __uint_as_float(pm[cb + k]);
+                      yp[(int64_t)(cb + k) * ldy] = z[k];
+                      if (ACT == 2) z[k] *= omega;
+                    }
+                  if (ACT == 1) tanh_dir_fwd<MAXK, float>(KD, z, y, w);
+                  else sincos_dir_fwd<MAXK, float>(KD, z, y, w);
+#pragma unroll
+                  for (int k = 1; k <= MAXK; ++k)
+                    if (k <= KD) ya[(int64_t)(cb + k) * ldy] = y[k];
+                }
+              }
+            } else {   // EPI_ACTBWD
+              float yb[MAXK + 1], zb[MAXK + 1], wb[MAXK + 1];
+              z[0] = zsr[jb];
+              if (ACT == 1) { y[0] = tanhf(z[0]); w[0] = 1.f - y[0] * y[0]; }
+              else { z[0] *= omega; sincosf(z[0], &y[0], &w[0]); }
+              yb[0] = __uint_as_float(pc[jb]) + __uint_as_float(pm[jb]);
+              float wb0 = 0.f;
+#pragma unroll
+              for (int d = 0; d < 2; ++d) {
+                const int KD = d ? K1 : K0, cb = jb + (d ? K0 : 0);
+                if (KD > 0) {
+#pragma unroll
+                  for (int k = 1; k <= MAXK; ++k) {
+                    if (k <= KD) {
+                      z[k] = zsr[cb + k];
+                      if (ACT == 2) z[k] *= omega;
+                      yb[k] = __uint_as_float(pc[cb + k]) + __uint_as_float(pm[cb + k]);
+                    } else {
+                      yb[k] = 0.f;
+                    }
+                  }
+                  if (ACT == 1) {
+                    tanh_dir_fwd<MAXK, float>(KD, z, y, w);
+                    tanh_dir_bwd<MAXK, float>(KD, z, y, w, yb, zb, wb0);
+                  } else {
+#pragma unroll
+                    for (int k = 0; k <= MAXK; ++k) wb[k] = 0.f;
+                    wb[0] = wb0;
+                    sincos_dir_fwd<MAXK, float>(KD, z, y, w);
+                    sincos_dir_bwd<MAXK, float>(KD, z, y, w, yb, wb, zb);
+                    wb0 = wb[0];
+                  }
+#pragma unroll
+                  for (int k = 1; k <= MAXK; ++k)
+                    if (k <= KD) yp[(int64_t)(cb + k) * ldy] = (ACT == 2) ? zb[k] * omega : zb[k];
+                }
+              }
+              yp[(int64_t)jb * ldy] = (ACT == 1) ? tanh_finish_bwd<float>(y[0], w[0], yb[0], wb0)
+                                                 : (yb[0] * w[0] - wb0 * y[0]) * omega;
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(128, TN);
+      const uint64_t dconst = make_desc_k_sw128(0);
+      const uint32_t x_base = smem_u32(x_st) >> 4;
+      int it = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it % STAGES, b = it % ACC;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u, bph = (uint32_t)(it / ACC) & 1u;
+        mbar_wait(&tempty[b], bph ^ 1u);
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t xh = x_base + (uint32_t)s * (2 * X_BYTES >> 4), xl = xh + (X_BYTES >> 4);
+        const uint32_t d_main = tmem_base + COL_ACC + (uint32_t)(b * 2 * TN), d_corr = d_main + TN;
+#pragma unroll
+        for (int k8 = 0; k8 < K / 8; ++k8) {
+          const uint32_t bo = (uint32_t)(((k8 >> 2) * TN * 128 + (k8 & 3) * 32) >> 4);
+          const uint64_t b_hi = dconst | (uint64_t)(xh + bo), b_lo = dconst | (uint64_t)(xl + bo);
+          const uint32_t a_hi = tmem_base + COL_WHI + (uint32_t)(k8 * 8), a_lo = tmem_base + COL_WLO + (uint32_t)(k8 * 8);
+          umma_tf32_ts(d_corr, a_lo, b_hi, idesc, k8 ? 1u : 0u);
+          umma_tf32_ts(d_corr, a_hi, b_lo, idesc, 1u);
+          umma_tf32_ts(d_main, a_hi, b_hi, idesc, k8 ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+        umma_commit(&tfull[b]);
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMAW) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <bool TRANS_W, int EPI, int ACT, int K0, int K1>
+static int launch_linear_rows_ts(const float* X, const float* W, int ldw, const float* bias, float* Y, int64_t M, int n_cols,
+                                 int jet_cols, const float* Zs, float* Yact, float omega, int sm_count, cudaStream_t st) {
+  constexpr size_t smem = 1024 + (size_t)3 * 2 * 64 * 128 * 4 + (2 * 3 + 2 * 2) * 8 + 16;
+  static_assert(smem <= 232448, "shared memory budget (227 KB per CTA)");
+  constexpr int NLW = (EPI == EPI_ACTBWD) ? 4 : 8, ECOLS = (EPI == EPI_ACTBWD) ? 16 : 32;
+  auto kern = linear_rows_ts_kernel<TRANS_W, EPI, ACT, K0, K1, NLW, ECOLS>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    configured = true;
+  }
+  const int64_t ntiles = (M + 63) / 64;
+  const int per_y = n_cols / 128;
+  int gx = sm_count / per_y;
+  if (gx < 1) gx = 1;
+  if ((int64_t)gx > ntiles) gx = (int)ntiles;
+  dim3 grid((unsigned)gx, (unsigned)per_y, 1);
+  kern<<<grid, (NLW + 4 * (64 / ECOLS) + 1) * 32, smem, st>>>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient: dW[o0.., i0..] (128 x 128 block) += sum_rows G[row, o0..]^T X[row, i0..]   (+ db[o] += G rows with
+// row % jet_cols == 0).  The contraction runs over the rows, so both operands are MN-major (see make_desc_mn_sw128).
+//
+// Accuracy: the tensor core rounds every accumulate step toward zero, which over the thousands of K-steps of a
+// 1M-point batch would shrink the gradient by ~1e-4.  So each CTA accumulates SEG row tiles at a time in one of two
+// "main" TMEM accumulators (hi*hi products), while four flush warps fold the finished segment into a running fp32 sum
+// (kept in TMEM, added in registers with round-to-nearest).  The tiny lo*hi + hi*lo corrections accumulate in their own
+// TMEM region for the whole kernel.   TMEM: [0,128) main0 | [128,256) main1 | [256,384) corr | [384,512) sum
+template <int TK, int STAGES, int NLW, int SEG>
+__global__ void __launch_bounds__((NLW + 5) * 32, 1)
+wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, int ldx, float* __restrict__ dW, int lddw,
+             float* __restrict__ db, int64_t M, int jet_cols, int in_blocks) {
+  static_assert(TK % 8 == 0 && (TK % NLW) == 0 || (NLW % TK) == 0, "tile shape");
+  constexpr uint32_t OP_BYTES = TK * 512;          // one of G_hi / G_lo / X_hi / X_lo per stage (TK rows x 128 floats)
+  constexpr int EPI0 = NLW, MMAW = NLW + 4;
+  static_assert(EPI0 % 4 == 0, "flush warps must start at a multiple of 4 (TMEM lane quarters)");
+  constexpr uint32_t COL_MAIN = 0, COL_CORR = 256, COL_SUM = 384;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* st_base = smem;                          // [STAGES][G_hi|G_lo|X_hi|X_lo][OP_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(st_base + (size_t)STAGES * 4 * OP_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;              // [2] segment accumulated
+  uint64_t* tempty = bars + 2 * STAGES + 2;         // [2] segment flushed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o0 = (blockIdx.y / in_blocks) * 128, i0 = (blockIdx.y % in_blocks) * 128;
+  const int64_t ntiles = (M + TK - 1) / TK;
+  // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+  const int64_t my_tiles = (ntiles > (int64_t)blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t my_segs = (my_tiles + SEG - 1) / SEG;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], NLW); mbar_init(&empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+    fence_mbar_init();
+  }
+  if (warp == MMAW) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < NLW) {
+    // ===================== loaders: lane = 16-byte chunk (4 features) of G and of X, RPW rows per warp per tile =====
+    constexpr int RPW = (TK >= NLW) ? TK / NLW : 1;
+    const bool active = (TK >= NLW) || (warp < TK);
+    constexpr int PF = 2;                                   // tiles of register prefetch (bytes in flight per SM)
+    float4 vg[PF][RPW], vx[PF][RPW];
+    auto issue = [&](int64_t tile, float4 (&dg)[RPW], float4 (&dx)[RPW]) {
+      const int64_t r0 = tile * TK;
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) {
+        const int64_t row = r0 + warp + NLW * i;
+        const bool ok = active && tile < ntiles && row < M;
+        dg[i] = ok ? __ldg(reinterpret_cast<const float4*>(G + row * ldg + o0 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        dx[i] = ok ? __ldg(reinterpret_cast<const float4*>(X + row * ldx + i0 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool want_b = (db != nullptr) && (i0 == 0);
+    const int64_t stride = gridDim.x;
+#pragma unroll
+    for (int d = 0; d < PF; ++d) issue((int64_t)blockIdx.x + d * stride, vg[d], vx[d]);
+    const uint32_t sbase = smem_u32(st_base);
+    int it = 0;
+    int64_t tile = blockIdx.x;
+    while (tile < ntiles) {
+#pragma unroll
+      for (int d = 0; d < PF; ++d) {
+        if (tile < ntiles) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(&empty[s], ph ^ 1u);
+          const uint32_t gh = sbase + (uint32_t)s * 4 * OP_BYTES, gl = gh + OP_BYTES, xh = gl + OP_BYTES, xl = xh + OP_BYTES;
+          uint32_t cj = want_b ? (uint32_t)((uint32_t)(tile * TK + warp) % (uint32_t)jet_cols) : 1u;
+#pragma unroll
+          for (int i = 0; i < RPW; ++i) {
+            if (active) {
+              const int r = warp + NLW * i;                       // row inside the tile == K index
+              // MN-major SW128/32B: [4-row K group: 2048 B][32-float M/N group: 512 B][row % 4: 128 B][32B chunk ^ (row % 4)][16 B half]
+              const uint32_t off = (uint32_t)((r >> 2) * 2048 + (lane >> 3) * 512 + (r & 3) * 128 +
+                                              (((((lane & 7) >> 1) ^ (r & 3)) << 5)) + ((lane & 1) << 4));
+              uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+              const float4 g4 = vg[d][i], x4 = vx[d][i];
+              split_bits(g4.x, h0, l0); split_bits(g4.y, h1, l1); split_bits(g4.z, h2, l2); split_bits(g4.w, h3, l3);
+              sts128(gh + off, h0, h1, h2, h3);
+              sts128(gl + off, l0, l1, l2, l3);
+              if (want_b) {
+                if (cj == 0) { bsum.x += g4.x; bsum.y += g4.y; bsum.z += g4.z; bsum.w += g4.w; }
+                cj = (cj + NLW) % (uint32_t)jet_cols;
+              }
+              split_bits(x4.x, h0, l0); split_bits(x4.y, h1, l1); split_bits(x4.z, h2, l2); split_bits(x4.w, h3, l3);
+              sts128(xh + off, h0, h1, h2, h3);
+              sts128(xl + off, l0, l1, l2, l3);
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[s]);
+          issue(tile + PF * stride, vg[d], vx[d]);
+          tile += stride;
+          ++it;
+        }
+      }
+    }
+    if (want_b) {
+      atomicAdd(db + o0 + lane * 4 + 0, bsum.x); atomicAdd(db + o0 + lane * 4 + 1, bsum.y);
+      atomicAdd(db + o0 + lane * 4 + 2, bsum.z); atomicAdd(db + o0 + lane * 4 + 3, bsum.w);
+    }
+  } else if (warp < MMAW) {
+    // ===================== flush warps: fold finished segments into the fp32 running sum, write out at the end ======
+    if (my_segs > 0) {
+      const int q = warp - EPI0;
+      const int f = q * 32 + lane;                               // out-feature (TMEM lane)
+      const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+      for (int64_t seg = 0; seg < my_segs; ++seg) {
+        const int b = (int)(seg & 1);
+        mbar_wait(&tfull[b], (uint32_t)(seg >> 1) & 1u);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t p[32], a[32];
+          tmem_ld32_nowait(lane_base + COL_MAIN + b * 128 + c0, p);
+          if (seg > 0) tmem_ld32_nowait(lane_base + COL_SUM + c0, a);
+          tmem_wait_ld();
+          if (seg > 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) p[j] = __float_as_uint(__uint_as_float(p[j]) + __uint_as_float(a[j]));
+          }
+          tmem_st32(lane_base + COL_SUM + c0, p);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[b]);
+      }
+      // all MMAs (including the corrections) are complete: the last tfull commit covered them
+      float* tr = reinterpret_cast<float*>(st_base);             // stages are idle now: [128][129] transpose buffer
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t p[32], a[32];
+        tmem_ld32_nowait(lane_base + COL_SUM + c0, p);
+        tmem_ld32_nowait(lane_base + COL_CORR + c0, a);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) tr[f * 129 + c0 + j] = __uint_as_float(p[j]) + __uint_as_float(a[j]);
+      }
+      named_bar_sync(1, kEpiThreads);
+      const int t = threadIdx.x - EPI0 * 32;
+      for (int idx = t; idx < 128 * 128; idx += kEpiThreads) {
+        const int row = idx >> 7, col = idx & 127;
+        atomicAdd(dW + (int64_t)(o0 + row) * lddw + i0 + col, tr[row * 129 + col]);
+      }
+    }
+  } else {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && my_segs > 0) {
+      constexpr uint32_t idesc = make_idesc_tf32_mn(128, 128);
+      const uint64_t dconst = make_desc_mn_sw128(0, 512, 2048);
+      const uint32_t sbase = smem_u32(st_base) >> 4;
+      int it = 0;
+      int64_t seg = 0;
+      int in_seg = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        const int b = (int)(seg & 1);
+        if (in_seg == 0) mbar_wait(&tempty[b], ((uint32_t)(seg >> 1) & 1u) ^ 1u);    // previous use of this buffer flushed
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t gh = sbase + (uint32_t)s * (4 * OP_BYTES >> 4), gl = gh + (OP_BYTES >> 4), xh = gl + (OP_BYTES >> 4),
+                       xl = xh + (OP_BYTES >> 4);
+        const uint32_t d_main = tmem_base + COL_MAIN + (uint32_t)b * 128, d_corr = tmem_base + COL_CORR;
+#pragma unroll
+        for (int ks = 0; ks < TK / 8; ++ks) {
+          const uint32_t o = (uint32_t)ks * (4096 >> 4);
+          const uint64_t a_hi = dconst | (uint64_t)(gh + o), a_lo = dconst | (uint64_t)(gl + o);
+          const uint64_t b_hi = dconst | (uint64_t)(xh + o), b_lo = dconst | (uint64_t)(xl + o);
+          umma_tf32(d_corr, a_lo, b_hi, idesc, (it | ks) ? 1u : 0u);
+          umma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
+          umma_tf32(d_main, a_hi, b_hi, idesc, (in_seg | ks) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+        if (++in_seg == SEG || tile + gridDim.x >= ntiles) {
+          umma_commit(&tfull[b]);
+          in_seg = 0;
+          ++seg;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == MMAW) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int TK, int STAGES, int NLW, int SEG>
+static int launch_wgrad(const float* G, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
+                        int jet_cols, int sm_count, cudaStream_t st) {
+  constexpr size_t smem = 1024 + (size_t)STAGES * 4 * TK * 512 + (2 * STAGES + 4) * 8 + 16;
+  static_assert(smem <= 232448 && (size_t)STAGES * 4 * TK * 512 >= 128 * 129 * 4, "shared memory budget / transpose buffer");
+  auto kern = wgrad_kernel<TK, STAGES, NLW, SEG>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    configured = true;
+  }
+  const int64_t ntiles = (M + TK - 1) / TK;
+  const int in_blocks = in_dim / 128, blocks = in_blocks * (out_dim / 128);
+  int gx = sm_count / blocks;
+  if (gx < 1) gx = 1;
+  if ((int64_t)gx > ntiles) gx = (int)ntiles;
+  dim3 grid((unsigned)gx, (unsigned)blocks, 1);
+  kern<<<grid, (NLW + 5) * 32, smem, st>>>(G, out_dim, X, in_dim, dW, in_dim, db, M, jet_cols, in_blocks);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+}  // namespace tc
+
 // Z[M,N] = X[M,K] W[N,K]^T (+ bias on value-column rows).  Returns 0 when launched,
-// TC_UNSUPPORTED when the shape is not covered (caller uses the exact-fp32 CUDA-core GEMM).
-static inline int tc_linear_fwd(const float*, const float*, const float*, float*, int64_t, int, int, int, int, cudaStream_t) {
+// TC_UNSUPPORTED when the shape is not covered (caller uses the exact-fp32 CUDA-core GEMM), <0 on error.
+static inline int tc_linear_fwd(const float* X, const float* W, const float* bias, float* Z, int64_t M, int K, int N,
+                                int jet_cols, int sm_count, cudaStream_t st) {
+  if (M < 1 || (N % 128) != 0) return TC_UNSUPPORTED;
+  static int use_ss = -1;
+  if (use_ss < 0) { const char* e = getenv("PINNK_TC_SS"); use_ss = (e && e[0] == '1') ? 1 : 0; }
+  if (K == 128 && !use_ss) return tc::launch_linear_rows_ts<false, tc::EPI_PLAIN, 1, 0, 0>(X, W, K, bias, Z, M, N, jet_cols, nullptr, nullptr, 1.f, sm_count, st);
+  if (K == 128) return tc::launch_linear_rows<128, 32, 3, 3, 8, 3, false>(X, W, K, bias, Z, M, N, jet_cols, sm_count, st);
+  if (K == 64) return tc::launch_linear_rows<64, 64, 4, 2, 8, 2, false>(X, W, K, bias, Z, M, N, jet_cols, sm_count, st);
   return TC_UNSUPPORTED;
+}
+// dX[M,in] = dZ[M,out] W[out,in]   (W row-major [out,in])
+static inline int tc_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t M, int in_dim, int out_dim,
+                                  int sm_count, cudaStream_t st) {
+  if (M < 1 || (in_dim % 128) != 0) return TC_UNSUPPORTED;
+  static int use_ss = -1;
+  if (use_ss < 0) { const char* e = getenv("PINNK_TC_SS"); use_ss = (e && e[0] == '1') ? 1 : 0; }
+  if (out_dim == 128 && !use_ss) return tc::launch_linear_rows_ts<true, tc::EPI_PLAIN, 1, 0, 0>(dZ, W, in_dim, nullptr, dX, M, in_dim, 1, nullptr, nullptr, 1.f, sm_count, st);
+  if (out_dim == 128) return tc::launch_linear_rows<128, 32, 3, 3, 8, 3, true>(dZ, W, in_dim, nullptr, dX, M, in_dim, 1, sm_count, st);
+  return TC_UNSUPPORTED;
+}
+// jet layouts the fused epilogues are instantiated for: (K0, K1) = orders of the (at most two) directions
+template <bool TRANS_W, int EPI, int ACT>
+static inline int tc_dispatch_jets(int k0, int k1, const float* X, const float* W, int ldw, const float* bias, float* Y,
+                                   int64_t M, int n_cols, const float* Zs, float* Yact, float omega, int sm_count,
+                                   cudaStream_t st) {
+#define PK_TC_CASE(A, B)                                                                                         \
+  if (k0 == A && k1 == B)                                                                                        \
+    return tc::launch_linear_rows_ts<TRANS_W, EPI, ACT, A, B>(X, W, ldw, bias, Y, M, n_cols, 1 + A + B, Zs, Yact, omega, \
+                                                              sm_count, st);
+  PK_TC_CASE(0, 0) PK_TC_CASE(1, 0) PK_TC_CASE(2, 1) PK_TC_CASE(3, 0)
+#undef PK_TC_CASE
+  return TC_UNSUPPORTED;
+}
+// Forward Linear + activation jets in one kernel: Z = X W^T + b (stash), Yact = act(Z).  act: 1 tanh, 2 sin(omega z).
+static inline int tc_linear_act_fwd(const float* X, const float* W, const float* bias, float* Z, float* Yact, int64_t M, int K,
+                                    int N, int k0, int k1, int act, float omega, int sm_count, cudaStream_t st) {
+  if (M < 1 || K != 128 || (N % 128) != 0) return TC_UNSUPPORTED;
+  if (act == 1) return tc_dispatch_jets<false, tc::EPI_ACT, 1>(k0, k1, X, W, K, bias, Z, M, N, nullptr, Yact, 1.f, sm_count, st);
+  if (act == 2) return tc_dispatch_jets<false, tc::EPI_ACT, 2>(k0, k1, X, W, K, bias, Z, M, N, nullptr, Yact, omega, sm_count, st);
+  return TC_UNSUPPORTED;
+}
+// dgrad + activation adjoint in one kernel: dZprev = act'(Zprev)^T (dZ W)
+static inline int tc_linear_dgrad_actbwd(const float* dZ, const float* W, const float* Zprev, float* dZprev, int64_t M,
+                                         int in_dim, int out_dim, int k0, int k1, int act, float omega, int sm_count,
+                                         cudaStream_t st) {
+  if (M < 1 || out_dim != 128 || (in_dim % 128) != 0) return TC_UNSUPPORTED;
+  if (act == 1) return tc_dispatch_jets<true, tc::EPI_ACTBWD, 1>(k0, k1, dZ, W, in_dim, nullptr, dZprev, M, in_dim, Zprev, nullptr, 1.f, sm_count, st);
+  if (act == 2) return tc_dispatch_jets<true, tc::EPI_ACTBWD, 2>(k0, k1, dZ, W, in_dim, nullptr, dZprev, M, in_dim, Zprev, nullptr, omega, sm_count, st);
+  return TC_UNSUPPORTED;
+}
+// dW[out,in] += dZ[M,out]^T X[M,in] ;  db[out] += sum over value-column rows of dZ
+static inline int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
+                                  int jet_cols, int sm_count, cudaStream_t st) {
+  if (M < 1 || (in_dim % 128) != 0 || (out_dim % 128) != 0 || dW == nullptr) return TC_UNSUPPORTED;
+  return tc::launch_wgrad<32, 3, 16, 4>(dZ, X, dW, db, M, in_dim, out_dim, jet_cols, sm_count, st);
 }
 }  // namespace pinnk
