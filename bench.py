@@ -252,15 +252,17 @@ def run_ours(args):
 
     # roofline: profiling pass (event pairs around every libpinnk kernel class)
     roof = None
+    # every rank runs the two profiling steps (they contain the all-reduce); only rank 0 records events
     if rank == 0:
         _lib.prof_enable(True)
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(2):
-            step(x, t)
-        b.record()
-        torch.cuda.synchronize()
+    sync()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(2):
+        step(x, t)
+    b.record()
+    sync()
+    if rank == 0:
         prof = _lib.prof_collect()
         _lib.prof_enable(False)
         step_ms = a.elapsed_time(b) / 2
