@@ -205,6 +205,180 @@ __global__ void sincos_fwd_kernel(const float* __restrict__ Z, float* __restrict
   }
 }
 
+// ------------------------------------------------------------------ fused first / last layer kernels
+// First Linear (K = in_dim <= 4) + activation in one pass: Y = act(W xt + b) jets; the pre-activation is cheap to
+// recompute from (x, t), so it is only written when a caller still wants the stash (Zout != nullptr).
+template <int ACT, int MAXK>
+__global__ void first_act_fwd_kernel(const float* __restrict__ x, const float* __restrict__ t, int64_t n,
+                                     const float* __restrict__ W, const float* __restrict__ b, int out_dim, JetSpec js,
+                                     float* __restrict__ Zout, float* __restrict__ Y, float omega) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * out_dim) return;
+  const int64_t p = idx / out_dim;
+  const int f = (int)(idx - p * out_dim);
+  float wr[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) wr[i] = (i < js.in_dim) ? W[f * js.in_dim + i] : 0.f;
+  float z[MAXK + 1], y[MAXK + 1], w[MAXK + 1];
+  z[0] = b ? b[f] : 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i < js.in_dim) z[0] = fmaf(wr[i], load_in(x, t, p, i, js.in_dim), z[0]);
+  const int64_t base = p * js.ncols * out_dim + f;
+  if (Zout) Zout[base] = z[0];
+  if (ACT == 1) { y[0] = tanhf(z[0]); w[0] = 1.f - y[0] * y[0]; }
+  else { z[0] *= omega; sincosf(z[0], &y[0], &w[0]); }
+  Y[base] = y[0];
+  for (int d = 0; d < js.ndirs; ++d) {
+    const int K = js.order[d];
+    float z1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) z1 = fmaf(wr[i], js.vec[d][i], z1);
+    const int64_t b1 = base + (int64_t)js.col0[d] * out_dim;
+#pragma unroll
+    for (int k = 1; k <= MAXK; ++k) {
+      z[k] = (k == 1) ? z1 : 0.f;
+      if (Zout && k <= K) Zout[b1 + (int64_t)(k - 1) * out_dim] = z[k];
+      if (ACT == 2) z[k] *= omega;
+    }
+    if (ACT == 1) tanh_dir_fwd<MAXK, float>(K, z, y, w);
+    else sincos_dir_fwd<MAXK, float>(K, z, y, w);
+#pragma unroll
+    for (int k = 1; k <= MAXK; ++k)
+      if (k <= K) Y[b1 + (int64_t)(k - 1) * out_dim] = y[k];
+  }
+}
+
+// Reverse of the above in one pass: G = dL/dY jets -> dW[f,i], db[f] of the first Linear (nothing is written back).
+template <int ACT, int MAXK>
+__global__ void first_act_bwd_kernel(const float* __restrict__ x, const float* __restrict__ t, int64_t n,
+                                     const float* __restrict__ W, const float* __restrict__ b, int out_dim, JetSpec js,
+                                     const float* __restrict__ G, float* __restrict__ gW, float* __restrict__ gb, float omega) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= out_dim) return;
+  float wr[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) wr[i] = (i < js.in_dim) ? W[f * js.in_dim + i] : 0.f;
+  const float bf = b ? b[f] : 0.f;
+  float z1d[kMaxDirs];
+  for (int d = 0; d < js.ndirs; ++d) {
+    float a = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a = fmaf(wr[i], js.vec[d][i], a);
+    z1d[d] = a;
+  }
+  float aw[4] = {0.f, 0.f, 0.f, 0.f};
+  float ab = 0.f;
+  for (int64_t p = blockIdx.y; p < n; p += gridDim.y) {
+    float xin[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) xin[i] = (i < js.in_dim) ? load_in(x, t, p, i, js.in_dim) : 0.f;
+    float z[MAXK + 1], y[MAXK + 1], w[MAXK + 1], yb[MAXK + 1], zb[MAXK + 1], wb[MAXK + 1];
+    z[0] = bf;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) z[0] = fmaf(wr[i], xin[i], z[0]);
+    if (ACT == 1) { y[0] = tanhf(z[0]); w[0] = 1.f - y[0] * y[0]; }
+    else { z[0] *= omega; sincosf(z[0], &y[0], &w[0]); }
+    const int64_t base = p * js.ncols * out_dim + f;
+    yb[0] = G[base];
+    float wb0 = 0.f;
+    for (int d = 0; d < js.ndirs; ++d) {
+      const int K = js.order[d];
+      const int64_t b1 = base + (int64_t)js.col0[d] * out_dim;
+#pragma unroll
+      for (int k = 1; k <= MAXK; ++k) {
+        z[k] = (k == 1) ? z1d[d] : 0.f;
+        if (ACT == 2) z[k] *= omega;
+        yb[k] = (k <= K) ? G[b1 + (int64_t)(k - 1) * out_dim] : 0.f;
+      }
+      if (ACT == 1) {
+        tanh_dir_fwd<MAXK, float>(K, z, y, w);
+        tanh_dir_bwd<MAXK, float>(K, z, y, w, yb, zb, wb0);
+      } else {
+#pragma unroll
+        for (int k = 0; k <= MAXK; ++k) wb[k] = 0.f;
+        wb[0] = wb0;
+        sincos_dir_fwd<MAXK, float>(K, z, y, w);
+        sincos_dir_bwd<MAXK, float>(K, z, y, w, yb, wb, zb);
+        wb0 = wb[0];
+      }
+      const float g1 = (ACT == 2) ? zb[1] * omega : zb[1];       // only the first-order pre-activation depends on W
+#pragma unroll
+      for (int i = 0; i < 4; ++i) aw[i] = fmaf(g1, js.vec[d][i], aw[i]);
+    }
+    const float g0 = (ACT == 1) ? tanh_finish_bwd<float>(y[0], w[0], yb[0], wb0) : (yb[0] * w[0] - wb0 * y[0]) * omega;
+    ab += g0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) aw[i] = fmaf(g0, xin[i], aw[i]);
+  }
+  if (gW) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i < js.in_dim) atomicAdd(gW + (int64_t)f * js.in_dim + i, aw[i]);
+  }
+  if (gb) atomicAdd(gb + f, ab);
+}
+
+// Last Linear (N = 1) reverse + adjoint of the activation feeding it, in one pass:
+//   dL/dY[p,c,f] = Ub[p,c] W[f];  dW[f] += sum Ub[p,c] Y[p,c,f] (Y recomputed from the stashed Z);  db += sum_p Ub[p,0]
+//   Gout = dL/dZ jets.
+template <int ACT, int MAXK>
+__global__ void last_act_bwd_kernel(const float* __restrict__ Z, const float* __restrict__ Ub, int64_t n, int width,
+                                    JetSpec js, const float* __restrict__ W, float* __restrict__ Gout,
+                                    float* __restrict__ gW, float* __restrict__ gb, float omega) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = f < width;
+  const float wf = active ? W[f] : 0.f;
+  float acc = 0.f, accb = 0.f;
+  for (int64_t p = blockIdx.y; p < n; p += gridDim.y) {
+    const float* ub = Ub + p * js.ncols;
+    if (f == 0) accb += ub[0];
+    if (!active) continue;
+    const int64_t base = p * js.ncols * width + f;
+    float z[MAXK + 1], y[MAXK + 1], w[MAXK + 1], yb[MAXK + 1], zb[MAXK + 1], wb[MAXK + 1];
+    z[0] = Z[base];
+    if (ACT == 1) { y[0] = tanhf(z[0]); w[0] = 1.f - y[0] * y[0]; }
+    else { z[0] *= omega; sincosf(z[0], &y[0], &w[0]); }
+    yb[0] = ub[0] * wf;
+    acc = fmaf(ub[0], y[0], acc);
+    float wb0 = 0.f;
+    for (int d = 0; d < js.ndirs; ++d) {
+      const int K = js.order[d];
+      const int64_t b1 = base + (int64_t)js.col0[d] * width;
+#pragma unroll
+      for (int k = 1; k <= MAXK; ++k) {
+        if (k <= K) {
+          z[k] = Z[b1 + (int64_t)(k - 1) * width];
+          if (ACT == 2) z[k] *= omega;
+          yb[k] = ub[js.col0[d] + k - 1] * wf;
+        } else {
+          yb[k] = 0.f;
+        }
+      }
+      if (ACT == 1) tanh_dir_fwd<MAXK, float>(K, z, y, w);
+      else sincos_dir_fwd<MAXK, float>(K, z, y, w);
+#pragma unroll
+      for (int k = 1; k <= MAXK; ++k)
+        if (k <= K) acc = fmaf(ub[js.col0[d] + k - 1], y[k], acc);
+      if (ACT == 1) {
+        tanh_dir_bwd<MAXK, float>(K, z, y, w, yb, zb, wb0);
+      } else {
+#pragma unroll
+        for (int k = 0; k <= MAXK; ++k) wb[k] = 0.f;
+        wb[0] = wb0;
+        sincos_dir_bwd<MAXK, float>(K, z, y, w, yb, wb, zb);
+        wb0 = wb[0];
+      }
+#pragma unroll
+      for (int k = 1; k <= MAXK; ++k)
+        if (k <= K) Gout[b1 + (int64_t)(k - 1) * width] = (ACT == 2) ? zb[k] * omega : zb[k];
+    }
+    Gout[base] = (ACT == 1) ? tanh_finish_bwd<float>(y[0], w[0], yb[0], wb0) : (yb[0] * w[0] - wb0 * y[0]) * omega;
+  }
+  if (active && gW) atomicAdd(gW + f, acc);
+  if (f == 0 && gb) atomicAdd(gb, accb);
+}
+
 // ------------------------------------------------------------------ LayerNorm jets (one warp per point)
 // NPER = ceil(width/32) features per lane.
 template <int MAXK, int NPER>

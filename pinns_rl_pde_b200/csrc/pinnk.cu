@@ -85,6 +85,8 @@ struct pinnk_plan_s {
   int64_t grad_floats;
   int64_t ws_bytes;
   int sm_count;
+  bool fuse_first;   // ops[0] LINEAR (trainable, not transposed) + ops[1] plain ACT: one kernel each way, no Z stash
+  bool fuse_last;    // last LINEAR preceded by a plain ACT: reverse of both in one kernel
   // workspace layout (float offsets)
   int64_t off_stash, off_U, off_Ub, off_adj[3];
 };
@@ -226,6 +228,10 @@ extern "C" int pinnk_plan_create(const PinnkOp* ops, int32_t n_ops, int32_t in_d
     delete pl;
     return fail(PINNK_E_INVALID, "plan_create: dangling skip connection");
   }
+  pl->fuse_first = n_ops >= 3 && ops[1].kind == PINNK_OP_ACT && pl->ops[1].skip_src < 0 && !ops[0].w_transposed &&
+                   (ops[0].gw_offset >= 0 || ops[0].gb_offset >= 0);
+  pl->fuse_last = n_ops >= 3 && ops[n_ops - 2].kind == PINNK_OP_ACT && pl->ops[n_ops - 2].skip_src < 0 &&
+                  pl->ops[n_ops - 2].in_op >= 1;
   pl->max_width = max_width;
   pl->stash_floats_per_point = off;
   pl->grad_floats = grad_end;
@@ -384,8 +390,10 @@ static bool jet_orders(const JetSpec& js, int& k0, int& k1) {
 }
 
 // forward jets of one chunk; fills the stash and U[n, C]
+// keep_stash = false (forward-only callers: jets_forward, scoring): fused Linear+activation kernels skip the
+// pre-activation store, which nothing reads without a reverse pass
 template <int MAXK>
-static int forward_chunk(const ChunkCtx& c) {
+static int forward_chunk(const ChunkCtx& c, bool keep_stash = true) {
   const pinnk_plan_t pl = c.pl;
   const JetSpec& js = pl->js;
   const int n_ops = (int)pl->ops.size();
@@ -398,7 +406,17 @@ static int forward_chunk(const ChunkCtx& c) {
       case PINNK_OP_LINEAR: {
         const float* W = c.params[o.w_index];
         const float* b = (o.b_index >= 0) ? c.params[o.b_index] : nullptr;
-        if (i == 0) {
+        if (i == 0 && pl->fuse_first && tc_enabled()) {
+          ProfScope ps(PC_FIRST_FWD, c.st);
+          const PinnkOp& a = pl->ops[1].op;
+          const unsigned blocks = blocks_for(c.n * o.out_dim, threads);
+          if (a.act == PINNK_ACT_TANH)
+            first_act_fwd_kernel<1, MAXK><<<blocks, threads, 0, c.st>>>(c.x, c.t, c.n, W, b, o.out_dim, js, nullptr, c.stash(1), 1.f);
+          else
+            first_act_fwd_kernel<2, MAXK><<<blocks, threads, 0, c.st>>>(c.x, c.t, c.n, W, b, o.out_dim, js, nullptr, c.stash(1), a.scale);
+          PK_LAUNCH_OK();
+          ++i;
+        } else if (i == 0) {
           ProfScope ps(PC_FIRST_FWD, c.st);
           first_linear_fwd_kernel<<<blocks_for(c.n * o.out_dim, threads), threads, 0, c.st>>>(
               c.x, c.t, c.n, W, b, o.w_transposed, o.out_dim, js, c.stash(i));
@@ -415,7 +433,7 @@ static int forward_chunk(const ChunkCtx& c) {
               jet_orders(js, k0, k1)) {
             const PinnkOp& a = pl->ops[i + 1].op;
             ProfScope ps(PC_GEMM_FWD, c.st);
-            int rc = tc_linear_act_fwd(in, W, b, c.stash(i), c.stash(i + 1), c.n * js.ncols, o.in_dim, o.out_dim, k0, k1,
+            int rc = tc_linear_act_fwd(in, W, b, keep_stash ? c.stash(i) : nullptr, c.stash(i + 1), c.n * js.ncols, o.in_dim, o.out_dim, k0, k1,
                                        a.act == PINNK_ACT_TANH ? 1 : 2, a.scale, pl->sm_count, c.st);
             if (rc == 0) { g_launches.fetch_add(1); ++i; break; }
             if (rc != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, std::string("tc_linear_act_fwd launch failed: ") + cudaGetErrorString(cudaGetLastError()));
@@ -475,7 +493,19 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad) {
     switch (o.kind) {
       case PINNK_OP_LINEAR: {
         const float* W = c.params[o.w_index];
-        if (i == n_ops - 1) {
+        if (i == n_ops - 1 && pl->fuse_last && tc_enabled() && first_trainable <= n_ops - 2) {
+          ProfScope ps(PC_LAST_BWD, c.st);
+          const OpRt& pa = pl->ops[n_ops - 2];
+          dim3 grid(blocks_for(o.in_dim, 128), (unsigned)std::min<int64_t>(c.n, 32 * (int64_t)pl->sm_count));
+          if (pa.op.act == PINNK_ACT_TANH)
+            last_act_bwd_kernel<1, MAXK><<<grid, 128, 0, c.st>>>(c.stash(pa.in_op), c.Ub(), c.n, o.in_dim, js, W, c.adj(cur),
+                                                                  G(o.gw_offset), G(o.gb_offset), 1.f);
+          else
+            last_act_bwd_kernel<2, MAXK><<<grid, 128, 0, c.st>>>(c.stash(pa.in_op), c.Ub(), c.n, o.in_dim, js, W, c.adj(cur),
+                                                                  G(o.gw_offset), G(o.gb_offset), pa.op.scale);
+          PK_LAUNCH_OK();
+          --i;     // the activation's adjoint is done
+        } else if (i == n_ops - 1) {
           ProfScope ps(PC_LAST_BWD, c.st);
           const int64_t rows = c.n * js.ncols;
           dim3 grid(blocks_for(o.in_dim, 128), (unsigned)std::min<int64_t>(rows, 32 * (int64_t)pl->sm_count));
@@ -495,8 +525,10 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad) {
             // dgrad + adjoint of the activation feeding this Linear in one tcgen05 kernel
             int k0 = 0, k1 = 0;
             const OpRt& pa = pl->ops[i - 1];
+            // (the first activation's adjoint is fused with the first Linear instead, and has no stash to read)
+            const bool first_pair = pl->fuse_first && i - 1 == 1 && first_trainable == 0;
             if (tc_enabled() && r.in_op == i - 1 && pa.op.kind == PINNK_OP_ACT && pa.skip_src < 0 && pa.in_op >= 0 &&
-                jet_orders(js, k0, k1)) {
+                !first_pair && jet_orders(js, k0, k1)) {
               ProfScope ps(PC_GEMM_DGRAD, c.st);
               rc = tc_linear_dgrad_actbwd(c.adj(cur), W, c.stash(pa.in_op), c.adj(nxt), c.n * js.ncols, o.in_dim, o.out_dim,
                                           k0, k1, pa.op.act == PINNK_ACT_TANH ? 1 : 2, pa.op.scale, pl->sm_count, c.st);
@@ -511,6 +543,23 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad) {
         break;
       }
       case PINNK_OP_ACT: {
+        if (i == 1 && pl->fuse_first && tc_enabled() && first_trainable == 0) {
+          // adjoint of the first activation + weight gradient of the first Linear, pre-activation recomputed from (x, t)
+          ProfScope ps(PC_FIRST_BWD, c.st);
+          const PinnkOp& l0 = pl->ops[0].op;
+          const float* W0 = c.params[l0.w_index];
+          const float* b0 = (l0.b_index >= 0) ? c.params[l0.b_index] : nullptr;
+          dim3 grid(blocks_for(l0.out_dim, 128), (unsigned)std::min<int64_t>(c.n, 32 * (int64_t)pl->sm_count));
+          if (o.act == PINNK_ACT_TANH)
+            first_act_bwd_kernel<1, MAXK><<<grid, 128, 0, c.st>>>(c.x, c.t, c.n, W0, b0, l0.out_dim, js, c.adj(cur),
+                                                                   G(l0.gw_offset), G(l0.gb_offset), 1.f);
+          else
+            first_act_bwd_kernel<2, MAXK><<<grid, 128, 0, c.st>>>(c.x, c.t, c.n, W0, b0, l0.out_dim, js, c.adj(cur),
+                                                                   G(l0.gw_offset), G(l0.gb_offset), o.scale);
+          PK_LAUNCH_OK();
+          --i;     // the first Linear is done
+          break;
+        }
         const float* S = (r.skip_src >= 0) ? c.stash(r.skip_src) : nullptr;
         const unsigned blocks = blocks_for(c.n * o.in_dim, threads);
         ProfScope ps(PC_ACT_BWD, c.st);
@@ -577,7 +626,7 @@ extern "C" int pinnk_jets_forward(pinnk_plan_t plan, const float* const* params,
   for (int64_t p0 = 0; p0 < n; p0 += plan->chunk) {
     const int64_t cn = std::min(plan->chunk, n - p0);
     ChunkCtx c = make_ctx(plan, params, x, t, p0, cn, ws, stream);
-    rc = dispatch_maxk(plan->maxk, [&](auto mk) { return forward_chunk<decltype(mk)::value>(c); });
+    rc = dispatch_maxk(plan->maxk, [&](auto mk) { return forward_chunk<decltype(mk)::value>(c, false); });
     if (rc) return rc;
     PK_CHECK_CUDA(cudaMemcpyAsync(out_jets + p0 * C, c.U(), sizeof(float) * cn * C, cudaMemcpyDeviceToDevice, c.st));
   }
@@ -624,7 +673,8 @@ extern "C" int pinnk_loss_step(pinnk_plan_t plan, const float* const* params, co
   for (int64_t p0 = 0; p0 < n; p0 += plan->chunk) {
     const int64_t cn = std::min(plan->chunk, n - p0);
     ChunkCtx c = make_ctx(plan, params, x, t, p0, cn, ws, stream);
-    rc = dispatch_maxk(plan->maxk, [&](auto mk) { return forward_chunk<decltype(mk)::value>(c); });
+    const bool keep = flat_grad != nullptr;
+    rc = dispatch_maxk(plan->maxk, [&](auto mk) { return forward_chunk<decltype(mk)::value>(c, keep); });
     if (rc) return rc;
     if (flat_grad) PK_CHECK_CUDA(cudaMemsetAsync(c.Ub(), 0, sizeof(float) * cn * C, c.st));
     for (int s = 0; s < n_segs; ++s) {
@@ -661,7 +711,7 @@ extern "C" int pinnk_score(pinnk_plan_t plan, const float* const* params, const 
   for (int64_t p0 = 0; p0 < n; p0 += plan->chunk) {
     const int64_t cn = std::min(plan->chunk, n - p0);
     ChunkCtx c = make_ctx(plan, params, x, t, p0, cn, ws, stream);
-    rc = dispatch_maxk(plan->maxk, [&](auto mk) { return forward_chunk<decltype(mk)::value>(c); });
+    rc = dispatch_maxk(plan->maxk, [&](auto mk) { return forward_chunk<decltype(mk)::value>(c, false); });
     if (rc) return rc;
     score_kernel<<<blocks_for(cn, threads), threads, 0, c.st>>>(c.U(), plan->js, pd, cn, abs_out ? abs_out + p0 : nullptr, stats);
     PK_LAUNCH_OK();

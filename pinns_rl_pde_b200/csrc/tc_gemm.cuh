@@ -473,6 +473,22 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// TMA bulk copy (cp.async.bulk, SASS UBLKCP): contiguous global bytes -> shared memory, completion signalled on an
+// mbarrier by transaction bytes.  Issued by one thread; no register staging, no generic-proxy fence on the load side.
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 // EPI selects the epilogue:
 //   EPI_PLAIN   Y = acc (+ bias on value rows)
 //   EPI_ACT     forward Linear + activation jets: Y = Z = acc + bias (the stash the reverse pass needs) and
@@ -484,28 +500,32 @@ __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, ui
 enum { EPI_PLAIN = 0, EPI_ACT = 1, EPI_ACTBWD = 2 };
 
 template <bool TRANS_W, int EPI, int ACT, int K0, int K1, int NLW, int ECOLS>
-__global__ void __launch_bounds__((NLW + 4 * (64 / ECOLS) + 1) * 32, 1)
+__global__ void __launch_bounds__((NLW + 4 * (64 / ECOLS) + 2) * 32, 1)
 linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
                       float* __restrict__ Y, int64_t M, int ldy, int jet_cols, const float* __restrict__ Zs,
                       float* __restrict__ Yact, float omega) {
-  constexpr int K = 128, TN = 64, STAGES = 3, ACC = 2, NEW = 4 * (TN / ECOLS);
+  constexpr int K = 128, TN = 64, STAGES = 2, RS = 3, ACC = 2, NEW = 4 * (TN / ECOLS);
   static_assert(ECOLS == 16 || ECOLS == 32, "epilogue warps own 16 or 32 tile rows");
   constexpr int JC = 1 + K0 + K1;                       // jet columns of the fused epilogues
   constexpr int MAXK = (K0 > K1 ? K0 : K1) > 0 ? (K0 > K1 ? K0 : K1) : 1;
   static_assert(EPI == EPI_PLAIN || (ECOLS % JC) == 0, "fused epilogues need the jet column count to divide the rows per epilogue warp");
   constexpr int CHUNKS = K / 4;
   constexpr uint32_t X_BYTES = TN * K * 4;        // one of X_hi / X_lo per stage (32 KB)
-  constexpr int EPI0 = NLW, MMAW = NLW + NEW;
+  constexpr uint32_t RAW_BYTES = TN * K * 4;      // raw fp32 row tile (32 KB)
+  constexpr int EPI0 = NLW, MMAW = NLW + NEW, TMAW = NLW + NEW + 1;   // NLW convert warps | NEW epilogue | MMA | TMA
   constexpr uint32_t COL_WHI = 0, COL_WLO = 128, COL_ACC = 256;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* x_st = smem;                           // [STAGES][hi|lo][X_BYTES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(x_st + (size_t)STAGES * 2 * X_BYTES);
+  uint8_t* x_st = smem;                           // [STAGES][hi|lo][X_BYTES]  UMMA operand tiles
+  uint8_t* raw_st = x_st + (size_t)STAGES * 2 * X_BYTES;     // [RS][RAW_BYTES]   raw tiles landed by TMA
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw_st + (size_t)RS * RAW_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + ACC;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * ACC);
+  uint64_t* raw_full = bars + 2 * STAGES + 2 * ACC;
+  uint64_t* raw_empty = raw_full + RS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + RS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * 128;
@@ -514,6 +534,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], NLW); mbar_init(&empty[s], 1); }
     for (int b = 0; b < ACC; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], NEW); }
+    for (int s = 0; s < RS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], NLW); }
     fence_mbar_init();
   }
   if (warp == MMAW) tmem_alloc(tmem_slot, 512);
@@ -543,25 +564,42 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
   __syncthreads();
   tc_fence_after();
 
-  if (warp < NLW) {
-    // ===================== loaders: 64 rows x 32 chunks per tile, 8 chunks per thread =====================
-    constexpr int RPW = TN / NLW;                        // 8 rows per warp per tile, lane = chunk
-    float4 v[RPW];
-    auto issue = [&](int64_t tile) {
-      const int64_t r0 = tile * TN;
-#pragma unroll
-      for (int i = 0; i < RPW; ++i) {
-        const int64_t row = r0 + warp + NLW * i;
-        v[i] = (tile < ntiles && row < M) ? __ldg(reinterpret_cast<const float4*>(X + row * K + lane * 4))
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (warp == TMAW) {
+    // ===================== TMA producer: raw 64-row tiles (contiguous 32 KB), one elected thread =====================
+    if (lane == 0) {
+      const uint32_t rb = smem_u32(raw_st);
+      int it = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it % RS;
+        const uint32_t ph = (uint32_t)(it / RS) & 1u;
+        mbar_wait(&raw_empty[s], ph ^ 1u);
+        const int64_t r0 = tile * TN;
+        const uint32_t nrows = (M - r0 >= TN) ? TN : (uint32_t)(M - r0);
+        mbar_arrive_expect_tx(&raw_full[s], nrows * (uint32_t)(K * 4));
+        tma_bulk_g2s(rb + (uint32_t)s * RAW_BYTES, X + r0 * K, nrows * (uint32_t)(K * 4), &raw_full[s]);
       }
-    };
-    issue(blockIdx.x);
-    const uint32_t x_base = smem_u32(x_st);
+    }
+    __syncwarp();
+  } else if (warp < NLW) {
+    // ===================== convert warps: raw tile -> hi/lo operand tile (lane = 16-byte chunk of a row) ==============
+    constexpr int RPW = TN / NLW;
+    const uint32_t x_base = smem_u32(x_st), rb = smem_u32(raw_st);
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      const int rs = it % RS, s = it % STAGES;
+      const uint32_t rph = (uint32_t)(it / RS) & 1u, ph = (uint32_t)(it / STAGES) & 1u;
+      const int64_t r0 = tile * TN;
+      const int nrows = (M - r0 >= TN) ? TN : (int)(M - r0);
+      mbar_wait(&raw_full[rs], rph);
+      const uint32_t raw = rb + (uint32_t)rs * RAW_BYTES;
+      float4 v[RPW];
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) {
+        const int r = warp + NLW * i;
+        v[i] = (r < nrows) ? lds128(raw + r * (K * 4) + lane * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&raw_empty[rs]);                 // raw data is in registers: slot may be refilled
       mbar_wait(&empty[s], ph ^ 1u);
       const uint32_t xh = x_base + (uint32_t)s * 2 * X_BYTES, xl = xh + X_BYTES;
 #pragma unroll
@@ -576,7 +614,6 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
-      issue(tile + gridDim.x);
     }
   } else if (warp < MMAW) {
     // ===================== epilogue: warp (q, h) owns lanes 32q.. and tile rows ECOLS*h .. ECOLS*h + ECOLS-1 ==========
@@ -596,6 +633,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
         for (int j = 0; j < ECOLS; ++j) { vmask |= (cj == 0 ? 1u : 0u) << j; cj = (cj + 1 == jet_cols) ? 0 : cj + 1; }
       }
       float* yp = Y + r0 * ldy + n0 + f;
+      const bool store_z = (EPI != EPI_ACT) || (Y != nullptr);     // forward-only callers (scoring) pass no stash buffer
       const int nrows = (M - r0 >= ECOLS) ? ECOLS : (int)(M - r0 > 0 ? M - r0 : 0);
       // the stashed pre-activations do not depend on the MMA: fetch them while the accumulator is still being produced
       float zsr[(EPI == EPI_ACTBWD) ? ECOLS : 1];
@@ -640,7 +678,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
             float z[MAXK + 1], y[MAXK + 1], w[MAXK + 1];
             if constexpr (EPI == EPI_ACT) {
               z[0] = __uint_as_float(pc[jb]) + __uint_as_float(pm[jb]) + bf;
-              yp[(int64_t)jb * ldy] = z[0];
+              if (store_z) yp[(int64_t)jb * ldy] = z[0];
               if (ACT == 1) { y[0] = tanhf(z[0]); w[0] = 1.f - y[0] * y[0]; }
               else { z[0] *= omega; sincosf(z[0], &y[0], &w[0]); }
               ya[(int64_t)jb * ldy] = y[0];
@@ -652,7 +690,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
                   for (int k = 1; k <= MAXK; ++k)
                     if (k <= KD) {
                       z[k] = __uint_as_float(pc[cb + k]) + __uint_as_float(pm[cb + k]);
-                      yp[(int64_t)(cb + k) * ldy] = z[k];
+                      if (store_z) yp[(int64_t)(cb + k) * ldy] = z[k];
                       if (ACT == 2) z[k] *= omega;
                     }
                   if (ACT == 1) tanh_dir_fwd<MAXK, float>(KD, z, y, w);
@@ -706,7 +744,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
         }
       }
     }
-  } else {
+  } else if (warp == MMAW) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_tf32(128, TN);
@@ -747,7 +785,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
 template <bool TRANS_W, int EPI, int ACT, int K0, int K1>
 static int launch_linear_rows_ts(const float* X, const float* W, int ldw, const float* bias, float* Y, int64_t M, int n_cols,
                                  int jet_cols, const float* Zs, float* Yact, float omega, int sm_count, cudaStream_t st) {
-  constexpr size_t smem = 1024 + (size_t)3 * 2 * 64 * 128 * 4 + (2 * 3 + 2 * 2) * 8 + 16;
+  constexpr size_t smem = 1024 + (size_t)2 * 2 * 64 * 128 * 4 + (size_t)3 * 64 * 128 * 4 + (2 * 2 + 2 * 2 + 2 * 3) * 8 + 16;
   static_assert(smem <= 232448, "shared memory budget (227 KB per CTA)");
   constexpr int NLW = (EPI == EPI_ACTBWD) ? 4 : 8, ECOLS = (EPI == EPI_ACTBWD) ? 16 : 32;
   auto kern = linear_rows_ts_kernel<TRANS_W, EPI, ACT, K0, K1, NLW, ECOLS>;
@@ -762,47 +800,57 @@ static int launch_linear_rows_ts(const float* X, const float* W, int ldw, const 
   if (gx < 1) gx = 1;
   if ((int64_t)gx > ntiles) gx = (int)ntiles;
   dim3 grid((unsigned)gx, (unsigned)per_y, 1);
-  kern<<<grid, (NLW + 4 * (64 / ECOLS) + 1) * 32, smem, st>>>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega);
+  kern<<<grid, (NLW + 4 * (64 / ECOLS) + 2) * 32, smem, st>>>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
 // Weight gradient: dW[o0.., i0..] (128 x 128 block) += sum_rows G[row, o0..]^T X[row, i0..]   (+ db[o] += G rows with
 // row % jet_cols == 0).  The contraction runs over the rows, so both operands are MN-major (see make_desc_mn_sw128).
+//
+// Data path: one TMA thread bulk-copies raw fp32 row tiles (global -> smem ring, mbarrier transaction bytes), NCW convert
+// warps turn a raw tile into the hi/lo UMMA operand tile (smem -> registers -> swizzled smem), one thread issues the
+// MMAs.  No warp that executes the generic->async proxy fence has global loads in flight (the fence is a full memory
+// barrier for the executing thread and would otherwise expose the HBM latency every tile).
 //
 // Accuracy: the tensor core rounds every accumulate step toward zero, which over the thousands of K-steps of a
 // 1M-point batch would shrink the gradient by ~1e-4.  So each CTA accumulates SEG row tiles at a time in one of two
 // "main" TMEM accumulators (hi*hi products), while four flush warps fold the finished segment into a running fp32 sum
 // (kept in TMEM, added in registers with round-to-nearest).  The tiny lo*hi + hi*lo corrections accumulate in their own
 // TMEM region for the whole kernel.   TMEM: [0,128) main0 | [128,256) main1 | [256,384) corr | [384,512) sum
-template <int TK, int STAGES, int NLW, int SEG>
-__global__ void __launch_bounds__((NLW + 5) * 32, 1)
+template <int TK, int RS, int OS, int NCW, int SEG>
+__global__ void __launch_bounds__((NCW + 8) * 32, 1)
 wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, int ldx, float* __restrict__ dW, int lddw,
              float* __restrict__ db, int64_t M, int jet_cols, int in_blocks) {
-  static_assert(TK % 8 == 0 && (TK % NLW) == 0 || (NLW % TK) == 0, "tile shape");
-  constexpr uint32_t OP_BYTES = TK * 512;          // one of G_hi / G_lo / X_hi / X_lo per stage (TK rows x 128 floats)
-  constexpr int EPI0 = NLW, MMAW = NLW + 4;
-  static_assert(EPI0 % 4 == 0, "flush warps must start at a multiple of 4 (TMEM lane quarters)");
+  static_assert(TK == 32 && (NCW == 8 || NCW == 16), "tile shape");
+  constexpr uint32_t OP_BYTES = TK * 512;          // one of G_hi / G_lo / X_hi / X_lo per operand stage (TK rows x 128 floats)
+  constexpr uint32_t RAW_BYTES = TK * 512;         // raw G (or X) tile
+  // warp roles: [0, NCW) convert | NCW..NCW+3 flush (TMEM lane quarters; NCW % 4 == 0) | NCW+4 MMA | NCW+5 TMA | 2 idle
+  constexpr int EPI0 = NCW, MMAW = NCW + 4, TMAW = NCW + 5;
   constexpr uint32_t COL_MAIN = 0, COL_CORR = 256, COL_SUM = 384;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* st_base = smem;                          // [STAGES][G_hi|G_lo|X_hi|X_lo][OP_BYTES]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(st_base + (size_t)STAGES * 4 * OP_BYTES);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + STAGES;
-  uint64_t* tfull = bars + 2 * STAGES;              // [2] segment accumulated
-  uint64_t* tempty = bars + 2 * STAGES + 2;         // [2] segment flushed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint8_t* op_base = smem;                                  // [OS][G_hi|G_lo|X_hi|X_lo][OP_BYTES]
+  uint8_t* raw_base = smem + (size_t)OS * 4 * OP_BYTES;     // [RS][G|X][RAW_BYTES]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(raw_base + (size_t)RS * 2 * RAW_BYTES);
+  uint64_t* raw_full = bars;
+  uint64_t* raw_empty = bars + RS;
+  uint64_t* full = bars + 2 * RS;
+  uint64_t* empty = bars + 2 * RS + OS;
+  uint64_t* tfull = bars + 2 * RS + 2 * OS;          // [2] segment accumulated
+  uint64_t* tempty = tfull + 2;                      // [2] segment flushed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o0 = (blockIdx.y / in_blocks) * 128, i0 = (blockIdx.y % in_blocks) * 128;
   const int64_t ntiles = (M + TK - 1) / TK;
-  // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
   const int64_t my_tiles = (ntiles > (int64_t)blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const int64_t my_segs = (my_tiles + SEG - 1) / SEG;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], NLW); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < RS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], NCW); }
+    for (int s = 0; s < OS; ++s) { mbar_init(&full[s], NCW); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
     fence_mbar_init();
   }
@@ -812,68 +860,73 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < NLW) {
-    // ===================== loaders: lane = 16-byte chunk (4 features) of G and of X, RPW rows per warp per tile =====
-    constexpr int RPW = (TK >= NLW) ? TK / NLW : 1;
-    const bool active = (TK >= NLW) || (warp < TK);
-    constexpr int PF = 2;                                   // tiles of register prefetch (bytes in flight per SM)
-    float4 vg[PF][RPW], vx[PF][RPW];
-    auto issue = [&](int64_t tile, float4 (&dg)[RPW], float4 (&dx)[RPW]) {
-      const int64_t r0 = tile * TK;
-#pragma unroll
-      for (int i = 0; i < RPW; ++i) {
-        const int64_t row = r0 + warp + NLW * i;
-        const bool ok = active && tile < ntiles && row < M;
-        dg[i] = ok ? __ldg(reinterpret_cast<const float4*>(G + row * ldg + o0 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        dx[i] = ok ? __ldg(reinterpret_cast<const float4*>(X + row * ldx + i0 + lane * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (warp == TMAW) {
+    // ===================== TMA producer: raw row tiles, one elected thread =====================
+    if (lane == 0) {
+      const uint32_t rb = smem_u32(raw_base);
+      int it = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int s = it % RS;
+        const uint32_t ph = (uint32_t)(it / RS) & 1u;
+        mbar_wait(&raw_empty[s], ph ^ 1u);
+        const int64_t r0 = tile * TK;
+        const int nrows = (M - r0 >= TK) ? TK : (int)(M - r0);
+        const uint32_t dg = rb + (uint32_t)s * 2 * RAW_BYTES, dx = dg + RAW_BYTES;
+        mbar_arrive_expect_tx(&raw_full[s], (uint32_t)nrows * 1024u);
+        if (ldg == 128) tma_bulk_g2s(dg, G + r0 * 128, (uint32_t)nrows * 512u, &raw_full[s]);
+        else for (int r = 0; r < nrows; ++r) tma_bulk_g2s(dg + r * 512, G + (r0 + r) * ldg + o0, 512u, &raw_full[s]);
+        if (ldx == 128) tma_bulk_g2s(dx, X + r0 * 128, (uint32_t)nrows * 512u, &raw_full[s]);
+        else for (int r = 0; r < nrows; ++r) tma_bulk_g2s(dx + r * 512, X + (r0 + r) * ldx + i0, 512u, &raw_full[s]);
       }
-    };
+    }
+    __syncwarp();
+  } else if (warp < NCW) {
+    // ===================== convert warps: raw tile -> hi/lo operand tile; lane = 16-byte chunk (4 features) ==========
+    constexpr int RPW = TK / NCW;
     float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
     const bool want_b = (db != nullptr) && (i0 == 0);
-    const int64_t stride = gridDim.x;
-#pragma unroll
-    for (int d = 0; d < PF; ++d) issue((int64_t)blockIdx.x + d * stride, vg[d], vx[d]);
-    const uint32_t sbase = smem_u32(st_base);
+    const uint32_t ob = smem_u32(op_base), rb = smem_u32(raw_base);
     int it = 0;
-    int64_t tile = blockIdx.x;
-    while (tile < ntiles) {
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int rs = it % RS, os = it % OS;
+      const uint32_t rph = (uint32_t)(it / RS) & 1u, oph = (uint32_t)(it / OS) & 1u;
+      const int64_t r0 = tile * TK;
+      const int nrows = (M - r0 >= TK) ? TK : (int)(M - r0);
+      mbar_wait(&raw_full[rs], rph);
+      const uint32_t rg = rb + (uint32_t)rs * 2 * RAW_BYTES, rx = rg + RAW_BYTES;
+      float4 g4[RPW], x4[RPW];
 #pragma unroll
-      for (int d = 0; d < PF; ++d) {
-        if (tile < ntiles) {
-          const int s = it % STAGES;
-          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-          mbar_wait(&empty[s], ph ^ 1u);
-          const uint32_t gh = sbase + (uint32_t)s * 4 * OP_BYTES, gl = gh + OP_BYTES, xh = gl + OP_BYTES, xl = xh + OP_BYTES;
-          uint32_t cj = want_b ? (uint32_t)((uint32_t)(tile * TK + warp) % (uint32_t)jet_cols) : 1u;
-#pragma unroll
-          for (int i = 0; i < RPW; ++i) {
-            if (active) {
-              const int r = warp + NLW * i;                       // row inside the tile == K index
-              // MN-major SW128/32B: [4-row K group: 2048 B][32-float M/N group: 512 B][row % 4: 128 B][32B chunk ^ (row % 4)][16 B half]
-              const uint32_t off = (uint32_t)((r >> 2) * 2048 + (lane >> 3) * 512 + (r & 3) * 128 +
-                                              (((((lane & 7) >> 1) ^ (r & 3)) << 5)) + ((lane & 1) << 4));
-              uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-              const float4 g4 = vg[d][i], x4 = vx[d][i];
-              split_bits(g4.x, h0, l0); split_bits(g4.y, h1, l1); split_bits(g4.z, h2, l2); split_bits(g4.w, h3, l3);
-              sts128(gh + off, h0, h1, h2, h3);
-              sts128(gl + off, l0, l1, l2, l3);
-              if (want_b) {
-                if (cj == 0) { bsum.x += g4.x; bsum.y += g4.y; bsum.z += g4.z; bsum.w += g4.w; }
-                cj = (cj + NLW) % (uint32_t)jet_cols;
-              }
-              split_bits(x4.x, h0, l0); split_bits(x4.y, h1, l1); split_bits(x4.z, h2, l2); split_bits(x4.w, h3, l3);
-              sts128(xh + off, h0, h1, h2, h3);
-              sts128(xl + off, l0, l1, l2, l3);
-            }
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&full[s]);
-          issue(tile + PF * stride, vg[d], vx[d]);
-          tile += stride;
-          ++it;
-        }
+      for (int i = 0; i < RPW; ++i) {
+        const int r = warp + NCW * i;
+        if (r < nrows) { g4[i] = lds128(rg + r * 512 + lane * 16); x4[i] = lds128(rx + r * 512 + lane * 16); }
+        else { g4[i] = make_float4(0.f, 0.f, 0.f, 0.f); x4[i] = g4[i]; }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&raw_empty[rs]);                 // raw data is in registers: slot may be refilled
+      mbar_wait(&empty[os], oph ^ 1u);
+      const uint32_t gh = ob + (uint32_t)os * 4 * OP_BYTES, gl = gh + OP_BYTES, xh = gl + OP_BYTES, xl = xh + OP_BYTES;
+      uint32_t cj = want_b ? (uint32_t)((uint32_t)(r0 + warp) % (uint32_t)jet_cols) : 1u;
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) {
+        const int r = warp + NCW * i;                       // row inside the tile == K index
+        // MN-major SW128/32B: [4-row K group: 2048 B][32-float M/N group: 512 B][row % 4: 128 B][32B chunk ^ (row % 4)][16 B half]
+        const uint32_t off = (uint32_t)((r >> 2) * 2048 + (lane >> 3) * 512 + (r & 3) * 128 +
+                                        (((((lane & 7) >> 1) ^ (r & 3)) << 5)) + ((lane & 1) << 4));
+        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+        split_bits(g4[i].x, h0, l0); split_bits(g4[i].y, h1, l1); split_bits(g4[i].z, h2, l2); split_bits(g4[i].w, h3, l3);
+        sts128(gh + off, h0, h1, h2, h3);
+        sts128(gl + off, l0, l1, l2, l3);
+        if (want_b) {
+          if (cj == 0) { bsum.x += g4[i].x; bsum.y += g4[i].y; bsum.z += g4[i].z; bsum.w += g4[i].w; }
+          cj = (cj + NCW) % (uint32_t)jet_cols;
+        }
+        split_bits(x4[i].x, h0, l0); split_bits(x4[i].y, h1, l1); split_bits(x4[i].z, h2, l2); split_bits(x4[i].w, h3, l3);
+        sts128(xh + off, h0, h1, h2, h3);
+        sts128(xl + off, l0, l1, l2, l3);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[os]);
     }
     if (want_b) {
       atomicAdd(db + o0 + lane * 4 + 0, bsum.x); atomicAdd(db + o0 + lane * 4 + 1, bsum.y);
@@ -907,7 +960,7 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
         if (lane == 0) mbar_arrive(&tempty[b]);
       }
       // all MMAs (including the corrections) are complete: the last tfull commit covered them
-      float* tr = reinterpret_cast<float*>(st_base);             // stages are idle now: [128][129] transpose buffer
+      float* tr = reinterpret_cast<float*>(op_base);             // operand stages are idle now: [128][129] transpose buffer
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32) {
         uint32_t p[32], a[32];
@@ -924,18 +977,18 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
         atomicAdd(dW + (int64_t)(o0 + row) * lddw + i0 + col, tr[row * 129 + col]);
       }
     }
-  } else {
+  } else if (warp == MMAW) {
     // ===================== MMA issuer =====================
     if (lane == 0 && my_segs > 0) {
       constexpr uint32_t idesc = make_idesc_tf32_mn(128, 128);
       const uint64_t dconst = make_desc_mn_sw128(0, 512, 2048);
-      const uint32_t sbase = smem_u32(st_base) >> 4;
+      const uint32_t sbase = smem_u32(op_base) >> 4;
       int it = 0;
       int64_t seg = 0;
       int in_seg = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        const int s = it % OS;
+        const uint32_t ph = (uint32_t)(it / OS) & 1u;
         const int b = (int)(seg & 1);
         if (in_seg == 0) mbar_wait(&tempty[b], ((uint32_t)(seg >> 1) & 1u) ^ 1u);    // previous use of this buffer flushed
         mbar_wait(&full[s], ph);
@@ -970,12 +1023,12 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
   }
 }
 
-template <int TK, int STAGES, int NLW, int SEG>
+template <int TK, int RS, int OS, int NCW, int SEG>
 static int launch_wgrad(const float* G, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
                         int jet_cols, int sm_count, cudaStream_t st) {
-  constexpr size_t smem = 1024 + (size_t)STAGES * 4 * TK * 512 + (2 * STAGES + 4) * 8 + 16;
-  static_assert(smem <= 232448 && (size_t)STAGES * 4 * TK * 512 >= 128 * 129 * 4, "shared memory budget / transpose buffer");
-  auto kern = wgrad_kernel<TK, STAGES, NLW, SEG>;
+  constexpr size_t smem = 1024 + (size_t)OS * 4 * TK * 512 + (size_t)RS * 2 * TK * 512 + (2 * RS + 2 * OS + 4) * 8 + 16;
+  static_assert(smem <= 232448 && (size_t)OS * 4 * TK * 512 >= 128 * 129 * 4, "shared memory budget / transpose buffer");
+  auto kern = wgrad_kernel<TK, RS, OS, NCW, SEG>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
@@ -987,7 +1040,7 @@ static int launch_wgrad(const float* G, const float* X, float* dW, float* db, in
   if (gx < 1) gx = 1;
   if ((int64_t)gx > ntiles) gx = (int)ntiles;
   dim3 grid((unsigned)gx, (unsigned)blocks, 1);
-  kern<<<grid, (NLW + 5) * 32, smem, st>>>(G, out_dim, X, in_dim, dW, in_dim, db, M, jet_cols, in_blocks);
+  kern<<<grid, (NCW + 8) * 32, smem, st>>>(G, out_dim, X, in_dim, dW, in_dim, db, M, jet_cols, in_blocks);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -1049,6 +1102,6 @@ static inline int tc_linear_dgrad_actbwd(const float* dZ, const float* W, const 
 static inline int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
                                   int jet_cols, int sm_count, cudaStream_t st) {
   if (M < 1 || (in_dim % 128) != 0 || (out_dim % 128) != 0 || dW == nullptr) return TC_UNSUPPORTED;
-  return tc::launch_wgrad<32, 3, 16, 4>(dZ, X, dW, db, M, in_dim, out_dim, jet_cols, sm_count, st);
+  return tc::launch_wgrad<32, 3, 2, 16, 4>(dZ, X, dW, db, M, in_dim, out_dim, jet_cols, sm_count, st);
 }
 }  // namespace pinnk
