@@ -153,9 +153,6 @@ int pinnk_prof_collect(double* ms_per_class, int64_t* launches_per_class, int32_
 int pinnk_debug_linear_fwd(const float* X, const float* W, const float* bias, float* Z, int64_t M, int32_t K,
                            int32_t N, int32_t jet_cols, int32_t mode, void* stream);
 /* dX[M,K] = dZ[M,N] W[N,K] and dW[N,K] += dZ[M,N]^T X[M,K], db[N] += value-column rows of dZ: the two reverse GEMMs. */
-/* Debug: device buffer [grid][8] of int64 cycle counters filled by the tcgen05 row kernels (NULL = off):
- * loader {wait-empty, work}, epilogue {wait-full, work}, MMA {wait-tmem, wait-smem, issue}. */
-void pinnk_debug_set_clock_buffer(long long* dev_buf);
 int pinnk_debug_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t M, int32_t K, int32_t N,
                              int32_t mode, void* stream);
 int pinnk_debug_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int32_t K, int32_t N,

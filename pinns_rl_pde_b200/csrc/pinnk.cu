@@ -433,7 +433,7 @@ static int forward_chunk(const ChunkCtx& c, bool keep_stash = true) {
               jet_orders(js, k0, k1)) {
             const PinnkOp& a = pl->ops[i + 1].op;
             ProfScope ps(PC_GEMM_FWD, c.st);
-            int rc = tc_linear_act_fwd(in, W, b, keep_stash ? c.stash(i) : nullptr, c.stash(i + 1), c.n * js.ncols, o.in_dim, o.out_dim, k0, k1,
+            int rc = tc_linear_act_fwd(in, W, b, (keep_stash || o.in_dim != 128) ? c.stash(i) : nullptr, c.stash(i + 1), c.n * js.ncols, o.in_dim, o.out_dim, k0, k1,
                                        a.act == PINNK_ACT_TANH ? 1 : 2, a.scale, pl->sm_count, c.st);
             if (rc == 0) { g_launches.fetch_add(1); ++i; break; }
             if (rc != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, std::string("tc_linear_act_fwd launch failed: ") + cudaGetErrorString(cudaGetLastError()));
@@ -789,5 +789,3 @@ extern "C" int pinnk_debug_linear_wgrad(const float* dZ, const float* X, float* 
   }
   return 0;
 }
-
-extern "C" void pinnk_debug_set_clock_buffer(long long* dev_buf) { tc::g_tc_clk = dev_buf; }

@@ -33,7 +33,6 @@ constexpr int TC_UNSUPPORTED = 1;
 
 namespace tc {
 
-static long long* g_tc_clk = nullptr;   // optional device buffer [grid][8] of per-role cycle counters (debug)
 constexpr int kEpiThreads = 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -176,11 +175,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 template <int K, int TN, int STAGES, int ACC, int NLW, int PF, bool TRANS_W>
 __global__ void __launch_bounds__((NLW + 4 * (TN / 16) + 1) * 32, 1)
 linear_rows_kernel(const float* __restrict__ X, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
-                   float* __restrict__ Y, int64_t M, int ldy, int jet_cols, int dbg, long long* __restrict__ clk) {
+                   float* __restrict__ Y, int64_t M, int ldy, int jet_cols) {
   static_assert(K % 32 == 0 && TN % 16 == 0 && TN <= 256 && (TN % NLW) == 0, "tile shape");
-  long long c_wait0 = 0, c_wait1 = 0, c_work = 0, c_t = 0;
-#define CLK_MARK(acc) do { if (clk) { long long _n = clock64(); acc += _n - c_t; c_t = _n; } } while (0)
-  if (clk) c_t = clock64();
   constexpr int KB = K / 32;                      // 128-byte K blocks
   constexpr int CHUNKS = K / 4;                   // 16-byte chunks per row
   constexpr uint32_t W_BYTES = 128 * K * 4;       // one of W_hi / W_lo
@@ -264,7 +260,7 @@ linear_rows_kernel(const float* __restrict__ X, const float* __restrict__ W, int
 #pragma unroll
         for (int c = 0; c < PER_ROW; ++c) {
           const int chunk = lane + 32 * c;
-          dst[i][c] = (tile < ntiles && row < M && chunk < CHUNKS && !(dbg & 1))
+          dst[i][c] = (tile < ntiles && row < M && chunk < CHUNKS )
                           ? __ldg(reinterpret_cast<const float4*>(X + row * K + chunk * 4))
                           : make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -281,9 +277,7 @@ linear_rows_kernel(const float* __restrict__ X, const float* __restrict__ W, int
         if (tile < ntiles) {
           const int s = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-          CLK_MARK(c_work);
           mbar_wait(&empty[s], ph ^ 1u);
-          CLK_MARK(c_wait0);
           uint8_t* xh = x_st + (size_t)s * 2 * X_BYTES;
           uint8_t* xl = xh + X_BYTES;
 #pragma unroll
@@ -310,7 +304,6 @@ linear_rows_kernel(const float* __restrict__ X, const float* __restrict__ W, int
         }
       }
     }
-    if (clk && threadIdx.x == 0) { CLK_MARK(c_work); clk[blockIdx.x * 8 + 0] = c_wait0; clk[blockIdx.x * 8 + 1] = c_work; }
   } else if (warp < MMAW) {
     // ===================== epilogue: warp (q, h) owns lanes 32q.. and tile rows 16h..16h+15 =====================
     const int e = warp - EPI0;
@@ -330,9 +323,7 @@ linear_rows_kernel(const float* __restrict__ X, const float* __restrict__ W, int
         for (int j = 0; j < 16; ++j) { vmask |= (cj == 0 ? 1u : 0u) << j; cj = (cj + 1 == jet_cols) ? 0 : cj + 1; }
       }
       float* yp = Y + r0 * ldy + n0 + f;
-      CLK_MARK(c_work);
       mbar_wait(&tfull[b], ph);
-      CLK_MARK(c_wait0);
       tc_fence_after();
       const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * BUF_COLS + h * 16);
       uint32_t part[KB + 1][16];
@@ -349,10 +340,9 @@ linear_rows_kernel(const float* __restrict__ X, const float* __restrict__ W, int
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) v += __uint_as_float(part[kb][j]);
         if ((vmask >> j) & 1u) v += bf;
-        if (j < nrows && !(dbg & 4)) yp[(int64_t)j * ldy] = v;
+        if (j < nrows) yp[(int64_t)j * ldy] = v;
       }
     }
-    if (clk && threadIdx.x == EPI0 * 32) { CLK_MARK(c_work); clk[blockIdx.x * 8 + 2] = c_wait0; clk[blockIdx.x * 8 + 3] = c_work; }
   } else {
     // ===================== MMA issuer =====================
     if (lane == 0) {
@@ -364,21 +354,16 @@ linear_rows_kernel(const float* __restrict__ X, const float* __restrict__ W, int
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int s = it % STAGES, b = it % ACC;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u, bph = (uint32_t)(it / ACC) & 1u;
-        CLK_MARK(c_work);
         mbar_wait(&tempty[b], bph ^ 1u);
-        CLK_MARK(c_wait0);
         mbar_wait(&full[s], ph);
-        CLK_MARK(c_wait1);
         tc_fence_after();
         const uint32_t xh = smem_u32(x_st + (size_t)s * 2 * X_BYTES) >> 4, xl = xh + (X_BYTES >> 4);
         const uint32_t d = tmem_base + (uint32_t)(b * BUF_COLS);
         const uint32_t d_corr = d + (uint32_t)(KB * TN);
-        if (!(dbg & 2))
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
-            constexpr uint32_t dummy = 0; (void)dummy;
             const uint32_t ao = (uint32_t)((kb * 128 * 128 + ks * 32) >> 4), bo = (uint32_t)((kb * TN * 128 + ks * 32) >> 4);
             const uint64_t a_hi = dconst | (uint64_t)(wh + ao), a_lo = dconst | (uint64_t)(wl + ao);
             const uint64_t b_hi = dconst | (uint64_t)(xh + bo), b_lo = dconst | (uint64_t)(xl + bo);
@@ -390,11 +375,9 @@ linear_rows_kernel(const float* __restrict__ X, const float* __restrict__ W, int
         umma_commit(&empty[s]);     // smem stage may be refilled once these MMAs have read it
         umma_commit(&tfull[b]);     // accumulator complete
       }
-      if (clk) { CLK_MARK(c_work); clk[blockIdx.x * 8 + 4] = c_wait0; clk[blockIdx.x * 8 + 5] = c_wait1; clk[blockIdx.x * 8 + 6] = c_work; }
     }
     __syncwarp();
   }
-#undef CLK_MARK
   tc_fence_before();
   __syncthreads();
   if (warp == MMAW) {
@@ -420,9 +403,7 @@ static int launch_linear_rows(const float* X, const float* W, int ldw, const flo
   if (gx < 1) gx = 1;
   if ((int64_t)gx > ntiles) gx = (int)ntiles;
   dim3 grid((unsigned)gx, (unsigned)per_y, 1);
-  static int dbg = -1;
-  if (dbg < 0) { const char* e = getenv("PINNK_TC_DBG"); dbg = e ? atoi(e) : 0; }
-  kern<<<grid, (NLW + 4 * (TN / 16) + 1) * 32, smem, st>>>(X, W, ldw, bias, Y, M, n_cols, jet_cols, dbg, g_tc_clk);
+  kern<<<grid, (NLW + 4 * (TN / 16) + 1) * 32, smem, st>>>(X, W, ldw, bias, Y, M, n_cols, jet_cols);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -499,11 +480,13 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 // direction 1, with C = 1 + K0 + K1 dividing 32 so that every epilogue warp owns whole points.
 enum { EPI_PLAIN = 0, EPI_ACT = 1, EPI_ACTBWD = 2 };
 
-template <bool TRANS_W, int EPI, int ACT, int K0, int K1, int NLW, int ECOLS>
+template <bool TRANS_W, int EPI, int ACT, int K0, int K1, int NLW, int ECOLS, bool ACCUM>
 __global__ void __launch_bounds__((NLW + 4 * (64 / ECOLS) + 2) * 32, 1)
 linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
                       float* __restrict__ Y, int64_t M, int ldy, int jet_cols, const float* __restrict__ Zs,
-                      float* __restrict__ Yact, float omega) {
+                      float* __restrict__ Yact, float omega, int ldx) {
+  // ldx: row stride of X in floats (K = 128 columns of it are contracted: one half of a 256-wide layer);
+  // ACCUM: the epilogue adds the partial result already stored in Y (second K half of a 256-wide layer)
   constexpr int K = 128, TN = 64, STAGES = 2, RS = 3, ACC = 2, NEW = 4 * (TN / ECOLS);
   static_assert(ECOLS == 16 || ECOLS == 32, "epilogue warps own 16 or 32 tile rows");
   constexpr int JC = 1 + K0 + K1;                       // jet columns of the fused epilogues
@@ -576,7 +559,9 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
         const int64_t r0 = tile * TN;
         const uint32_t nrows = (M - r0 >= TN) ? TN : (uint32_t)(M - r0);
         mbar_arrive_expect_tx(&raw_full[s], nrows * (uint32_t)(K * 4));
-        tma_bulk_g2s(rb + (uint32_t)s * RAW_BYTES, X + r0 * K, nrows * (uint32_t)(K * 4), &raw_full[s]);
+        const uint32_t dst = rb + (uint32_t)s * RAW_BYTES;
+        if (ldx == K) tma_bulk_g2s(dst, X + r0 * K, nrows * (uint32_t)(K * 4), &raw_full[s]);
+        else for (uint32_t r = 0; r < nrows; ++r) tma_bulk_g2s(dst + r * (K * 4), X + (r0 + r) * ldx, (uint32_t)(K * 4), &raw_full[s]);
       }
     }
     __syncwarp();
@@ -642,6 +627,12 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
 #pragma unroll
         for (int j = 0; j < ECOLS; ++j) zsr[j] = (j < nrows) ? __ldg(zs0 + (int64_t)j * ldy) : 0.f;
       }
+      // second K half of a 256-wide layer: the first half's partial result is in Y
+      float part[ACCUM ? ECOLS : 1];
+      if constexpr (ACCUM) {
+#pragma unroll
+        for (int j = 0; j < ECOLS; ++j) part[j] = (j < nrows) ? yp[(int64_t)j * ldy] : 0.f;
+      }
       mbar_wait(&tfull[b], ph);
       tc_fence_after();
       const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + COL_ACC + (uint32_t)(b * 2 * TN + h * ECOLS);
@@ -652,6 +643,10 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[b]);
+      if constexpr (ACCUM) {
+#pragma unroll
+        for (int j = 0; j < ECOLS; ++j) pm[j] = __float_as_uint(__uint_as_float(pm[j]) + part[j]);
+      }
       if constexpr (EPI == EPI_PLAIN) {
         if (nrows == ECOLS) {
 #pragma unroll
@@ -784,27 +779,38 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
 
 template <bool TRANS_W, int EPI, int ACT, int K0, int K1>
 static int launch_linear_rows_ts(const float* X, const float* W, int ldw, const float* bias, float* Y, int64_t M, int n_cols,
-                                 int jet_cols, const float* Zs, float* Yact, float omega, int sm_count, cudaStream_t st) {
+                                 int jet_cols, const float* Zs, float* Yact, float omega, int sm_count, cudaStream_t st,
+                                 int ldx = 128, int accum = 0) {
   constexpr size_t smem = 1024 + (size_t)2 * 2 * 64 * 128 * 4 + (size_t)3 * 64 * 128 * 4 + (2 * 2 + 2 * 2 + 2 * 3) * 8 + 16;
   static_assert(smem <= 232448, "shared memory budget (227 KB per CTA)");
   constexpr int NLW = (EPI == EPI_ACTBWD) ? 4 : 8, ECOLS = (EPI == EPI_ACTBWD) ? 16 : 32;
-  auto kern = linear_rows_ts_kernel<TRANS_W, EPI, ACT, K0, K1, NLW, ECOLS>;
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    configured = true;
-  }
   const int64_t ntiles = (M + 63) / 64;
   const int per_y = n_cols / 128;
   int gx = sm_count / per_y;
   if (gx < 1) gx = 1;
   if ((int64_t)gx > ntiles) gx = (int)ntiles;
   dim3 grid((unsigned)gx, (unsigned)per_y, 1);
-  kern<<<grid, (NLW + 4 * (64 / ECOLS) + 2) * 32, smem, st>>>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega);
+  constexpr int threads = (NLW + 4 * (64 / ECOLS) + 2) * 32;
+  if (accum) {
+    auto kern = linear_rows_ts_kernel<TRANS_W, EPI, ACT, K0, K1, NLW, ECOLS, true>;
+    static bool configured = false;
+    if (!configured) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+      configured = true;
+    }
+    kern<<<grid, threads, smem, st>>>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, ldx);
+  } else {
+    auto kern = linear_rows_ts_kernel<TRANS_W, EPI, ACT, K0, K1, NLW, ECOLS, false>;
+    static bool configured = false;
+    if (!configured) {
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+      configured = true;
+    }
+    kern<<<grid, threads, smem, st>>>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, ldx);
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
-// ------------------------------------------------------------------------------------------------
 // ------------------------------------------------------------------------------------------------
 // Weight gradient: dW[o0.., i0..] (128 x 128 block) += sum_rows G[row, o0..]^T X[row, i0..]   (+ db[o] += G rows with
 // row % jet_cols == 0).  The contraction runs over the rows, so both operands are MN-major (see make_desc_mn_sw128).
@@ -1054,6 +1060,11 @@ static inline int tc_linear_fwd(const float* X, const float* W, const float* bia
   static int use_ss = -1;
   if (use_ss < 0) { const char* e = getenv("PINNK_TC_SS"); use_ss = (e && e[0] == '1') ? 1 : 0; }
   if (K == 128 && !use_ss) return tc::launch_linear_rows_ts<false, tc::EPI_PLAIN, 1, 0, 0>(X, W, K, bias, Z, M, N, jet_cols, nullptr, nullptr, 1.f, sm_count, st);
+  if (K == 256) {      // two K halves, the second accumulates onto the first and adds the bias
+    int rc = tc::launch_linear_rows_ts<false, tc::EPI_PLAIN, 1, 0, 0>(X, W, K, nullptr, Z, M, N, jet_cols, nullptr, nullptr, 1.f, sm_count, st, K, 0);
+    if (rc) return rc;
+    return tc::launch_linear_rows_ts<false, tc::EPI_PLAIN, 1, 0, 0>(X + 128, W + 128, K, bias, Z, M, N, jet_cols, nullptr, nullptr, 1.f, sm_count, st, K, 1);
+  }
   if (K == 128) return tc::launch_linear_rows<128, 32, 3, 3, 8, 3, false>(X, W, K, bias, Z, M, N, jet_cols, sm_count, st);
   if (K == 64) return tc::launch_linear_rows<64, 64, 4, 2, 8, 2, false>(X, W, K, bias, Z, M, N, jet_cols, sm_count, st);
   return TC_UNSUPPORTED;
@@ -1065,6 +1076,11 @@ static inline int tc_linear_dgrad(const float* dZ, const float* W, float* dX, in
   static int use_ss = -1;
   if (use_ss < 0) { const char* e = getenv("PINNK_TC_SS"); use_ss = (e && e[0] == '1') ? 1 : 0; }
   if (out_dim == 128 && !use_ss) return tc::launch_linear_rows_ts<true, tc::EPI_PLAIN, 1, 0, 0>(dZ, W, in_dim, nullptr, dX, M, in_dim, 1, nullptr, nullptr, 1.f, sm_count, st);
+  if (out_dim == 256) {
+    int rc = tc::launch_linear_rows_ts<true, tc::EPI_PLAIN, 1, 0, 0>(dZ, W, in_dim, nullptr, dX, M, in_dim, 1, nullptr, nullptr, 1.f, sm_count, st, out_dim, 0);
+    if (rc) return rc;
+    return tc::launch_linear_rows_ts<true, tc::EPI_PLAIN, 1, 0, 0>(dZ + 128, W + (int64_t)128 * in_dim, in_dim, nullptr, dX, M, in_dim, 1, nullptr, nullptr, 1.f, sm_count, st, out_dim, 1);
+  }
   if (out_dim == 128) return tc::launch_linear_rows<128, 32, 3, 3, 8, 3, true>(dZ, W, in_dim, nullptr, dX, M, in_dim, 1, sm_count, st);
   return TC_UNSUPPORTED;
 }
@@ -1072,31 +1088,48 @@ static inline int tc_linear_dgrad(const float* dZ, const float* W, float* dX, in
 template <bool TRANS_W, int EPI, int ACT>
 static inline int tc_dispatch_jets(int k0, int k1, const float* X, const float* W, int ldw, const float* bias, float* Y,
                                    int64_t M, int n_cols, const float* Zs, float* Yact, float omega, int sm_count,
-                                   cudaStream_t st) {
+                                   cudaStream_t st, int ldx = 128, int accum = 0) {
 #define PK_TC_CASE(A, B)                                                                                         \
   if (k0 == A && k1 == B)                                                                                        \
     return tc::launch_linear_rows_ts<TRANS_W, EPI, ACT, A, B>(X, W, ldw, bias, Y, M, n_cols, 1 + A + B, Zs, Yact, omega, \
-                                                              sm_count, st);
+                                                              sm_count, st, ldx, accum);
   PK_TC_CASE(0, 0) PK_TC_CASE(1, 0) PK_TC_CASE(2, 1) PK_TC_CASE(3, 0)
 #undef PK_TC_CASE
   return TC_UNSUPPORTED;
 }
+// A 256-wide contraction runs as two K halves of the K = 128 kernel: the first writes the partial result (plain
+// epilogue, no bias), the second adds it in its epilogue (bias, activation ... as requested).
+static inline bool tc_jets_supported(int k0, int k1) {
+  return (k0 == 0 && k1 == 0) || (k0 == 1 && k1 == 0) || (k0 == 2 && k1 == 1) || (k0 == 3 && k1 == 0);
+}
 // Forward Linear + activation jets in one kernel: Z = X W^T + b (stash), Yact = act(Z).  act: 1 tanh, 2 sin(omega z).
 static inline int tc_linear_act_fwd(const float* X, const float* W, const float* bias, float* Z, float* Yact, int64_t M, int K,
                                     int N, int k0, int k1, int act, float omega, int sm_count, cudaStream_t st) {
-  if (M < 1 || K != 128 || (N % 128) != 0) return TC_UNSUPPORTED;
-  if (act == 1) return tc_dispatch_jets<false, tc::EPI_ACT, 1>(k0, k1, X, W, K, bias, Z, M, N, nullptr, Yact, 1.f, sm_count, st);
-  if (act == 2) return tc_dispatch_jets<false, tc::EPI_ACT, 2>(k0, k1, X, W, K, bias, Z, M, N, nullptr, Yact, omega, sm_count, st);
-  return TC_UNSUPPORTED;
+  if (M < 1 || (K != 128 && K != 256) || (N % 128) != 0 || !tc_jets_supported(k0, k1) || (act != 1 && act != 2)) return TC_UNSUPPORTED;
+  int accum = 0;
+  if (K == 256) {
+    if (Z == nullptr) return TC_UNSUPPORTED;       // the partial result needs a buffer
+    int rc = tc::launch_linear_rows_ts<false, tc::EPI_PLAIN, 1, 0, 0>(X, W, K, nullptr, Z, M, N, 1, nullptr, nullptr, 1.f, sm_count, st, K, 0);
+    if (rc) return rc;
+    X += 128; W += 128; accum = 1;
+  }
+  if (act == 1) return tc_dispatch_jets<false, tc::EPI_ACT, 1>(k0, k1, X, W, K, bias, Z, M, N, nullptr, Yact, 1.f, sm_count, st, K, accum);
+  return tc_dispatch_jets<false, tc::EPI_ACT, 2>(k0, k1, X, W, K, bias, Z, M, N, nullptr, Yact, omega, sm_count, st, K, accum);
 }
 // dgrad + activation adjoint in one kernel: dZprev = act'(Zprev)^T (dZ W)
 static inline int tc_linear_dgrad_actbwd(const float* dZ, const float* W, const float* Zprev, float* dZprev, int64_t M,
                                          int in_dim, int out_dim, int k0, int k1, int act, float omega, int sm_count,
                                          cudaStream_t st) {
-  if (M < 1 || out_dim != 128 || (in_dim % 128) != 0) return TC_UNSUPPORTED;
-  if (act == 1) return tc_dispatch_jets<true, tc::EPI_ACTBWD, 1>(k0, k1, dZ, W, in_dim, nullptr, dZprev, M, in_dim, Zprev, nullptr, 1.f, sm_count, st);
-  if (act == 2) return tc_dispatch_jets<true, tc::EPI_ACTBWD, 2>(k0, k1, dZ, W, in_dim, nullptr, dZprev, M, in_dim, Zprev, nullptr, omega, sm_count, st);
-  return TC_UNSUPPORTED;
+  if (M < 1 || (out_dim != 128 && out_dim != 256) || (in_dim % 128) != 0 || !tc_jets_supported(k0, k1) || (act != 1 && act != 2))
+    return TC_UNSUPPORTED;
+  int accum = 0;
+  if (out_dim == 256) {
+    int rc = tc::launch_linear_rows_ts<true, tc::EPI_PLAIN, 1, 0, 0>(dZ, W, in_dim, nullptr, dZprev, M, in_dim, 1, nullptr, nullptr, 1.f, sm_count, st, out_dim, 0);
+    if (rc) return rc;
+    dZ += 128; W += (int64_t)128 * in_dim; accum = 1;
+  }
+  if (act == 1) return tc_dispatch_jets<true, tc::EPI_ACTBWD, 1>(k0, k1, dZ, W, in_dim, nullptr, dZprev, M, in_dim, Zprev, nullptr, 1.f, sm_count, st, out_dim, accum);
+  return tc_dispatch_jets<true, tc::EPI_ACTBWD, 2>(k0, k1, dZ, W, in_dim, nullptr, dZprev, M, in_dim, Zprev, nullptr, omega, sm_count, st, out_dim, accum);
 }
 // dW[out,in] += dZ[M,out]^T X[M,in] ;  db[out] += sum over value-column rows of dZ
 static inline int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,

@@ -210,14 +210,17 @@ def get_program(model: nn.Module) -> NetProgram:
 
 
 def get_engine(model: nn.Module, directions: Sequence[Direction], n_points: int,
-               max_chunk: Optional[int] = None) -> JetEngine:
-    """Engine for (model, jet spec) able to process ``n_points`` rows per call; cached per model."""
+               max_chunk: Optional[int] = None, whole: bool = False) -> JetEngine:
+    """Engine for (model, jet spec) able to process ``n_points`` rows per call; cached per model.
+    ``whole``: the call must fit ONE chunk (paired periodic-BC rows reference each other), so only the
+    workspace budget caps the chunk size."""
     program = get_program(model)
     cache = _CACHE[model]
     dirs = tuple((tuple(float(v) for v in vec), int(order)) for vec, order in directions)
     ncols = 1 + sum(o for _, o in dirs)
-    cap = min(MAX_CHUNK_POINTS if max_chunk is None else max_chunk,
-              max(1024, MAX_WORKSPACE_BYTES // _bytes_per_point(program, ncols)))
+    cap = max(1024, MAX_WORKSPACE_BYTES // _bytes_per_point(program, ncols))
+    if not whole:
+        cap = min(MAX_CHUNK_POINTS if max_chunk is None else max_chunk, cap)
     want = min(cap, max(256, -(-n_points // 256) * 256))
     eng: Optional[JetEngine] = cache.get(dirs)
     if eng is None or eng.chunk < want:

@@ -276,7 +276,7 @@ def loss_components(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_g
             x_min, x_max = pde.config.domain[0]
             pts = torch.cat([torch.cat([torch.full((nb, 1), x_min, device=dev), tb], dim=1),
                              torch.cat([torch.full((nb, 1), x_max, device=dev), tb], dim=1)], dim=0)
-            eng_b = get_engine(model, [((1.0, 0.0), 1)], 2 * nb)
+            eng_b = get_engine(model, [((1.0, 0.0), 1)], 2 * nb, whole=True)
             calls.append((eng_b, pts, None, [
                 Segment(kind=L.PDE_VALUE, row_start=0, row_count=nb, component=1, weight=1.0 / nb, pair_offset=nb, **mk),
                 Segment(kind=L.PDE_DX, row_start=0, row_count=nb, component=1, weight=1.0 / nb, pair_offset=nb, **mk)]))
@@ -303,7 +303,7 @@ def loss_components(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_g
                 lo_pts.append(torch.cat([cmin, t_axis], dim=1))
                 hi_pts.append(torch.cat([cmax, t_axis], dim=1))
             pts = torch.cat(lo_pts + hi_pts, dim=0)
-            eng_b = get_engine(model, [], pts.shape[0])
+            eng_b = get_engine(model, [], pts.shape[0], whole=True)
             calls.append((eng_b, pts, None, [
                 Segment(kind=L.PDE_VALUE, row_start=a * per_axis, row_count=per_axis, component=1,
                         weight=1.0 / per_axis, pair_offset=dim * per_axis, **mk) for a in range(dim)]))

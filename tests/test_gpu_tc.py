@@ -18,7 +18,8 @@ def _err(Z, ref):
 
 
 @pytest.mark.parametrize("M,K,N,C", [(4 * 3001, 128, 128, 4), (5 * 777, 128, 128, 5), (31, 128, 128, 1),
-                                     (3 * 4096, 64, 128, 3), (4 * 2048, 128, 256, 4)])
+                                     (3 * 4096, 64, 128, 3), (4 * 2048, 128, 256, 4), (4 * 1001, 256, 256, 4),
+                                     (5 * 333, 256, 128, 5)])
 def test_tc_linear_fwd_matches_fp64(dev, M, K, N, C):
     from pinns_rl_pde_b200 import _lib
     g = torch.Generator(device="cpu").manual_seed(M + K)
@@ -37,7 +38,8 @@ def test_tc_linear_fwd_matches_fp64(dev, M, K, N, C):
     assert e_tc < 2e-6 and m_tc < 5e-6
 
 
-@pytest.mark.parametrize("M,K,N", [(4 * 3001, 128, 128), (5 * 777, 128, 128), (17, 128, 128), (4 * 1024, 256, 128)])
+@pytest.mark.parametrize("M,K,N", [(4 * 3001, 128, 128), (5 * 777, 128, 128), (17, 128, 128), (4 * 1024, 256, 128),
+                                   (4 * 1001, 256, 256), (6 * 500, 128, 256)])
 def test_tc_linear_dgrad_matches_fp64(dev, M, K, N):
     from pinns_rl_pde_b200 import _lib
     g = torch.Generator(device="cpu").manual_seed(M + K + 1)
