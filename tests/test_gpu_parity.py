@@ -301,3 +301,41 @@ def test_loss_trajectory_500_epochs(dev):
             assert d_cuda <= 1e-4, (epoch, d_cuda)
     print(f"trajectory: worst dev cuda-vs-ref64 {worst_cuda:.3e}, ref32-vs-ref64 {worst_ref32:.3e}")
     assert worst_cuda <= max(1e-4, 2 * worst_ref32), (worst_cuda, worst_ref32)
+
+
+def test_full_size_1m_points_properties(dev):
+    """BASELINE config 2 at its full size (1 M collocation points, 8x128 tanh): size-independent properties.
+      * the residual of a random 2 048-row subsample taken from the 1 M-row call equals the oracle's (fp64, CPU)
+      * shard additivity: loss and gradient of the whole batch = row-weighted sum over two halves (what the
+        data-parallel all-reduce relies on), and the forward-only scoring statistics agree with the residual."""
+    import pinns_rl_pde_b200 as pk
+    from oracle import ref_port
+    from pinns_rl_pde_b200 import functional as F
+    torch.manual_seed(11)
+    model = pk.make_model("feedforward", 2, 128, 8, dev)
+    state = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    m64 = port_model(dict(arch="feedforward", hidden=128, layers=8, dimension=1, extra={}), state, torch.float64)
+    pde = product_pde("burgers", dev)
+    n = 1 << 20
+    g = torch.Generator(device="cuda").manual_seed(12)
+    x = torch.rand(n, 1, generator=g, device=dev) * 2 - 1
+    t = torch.rand(n, 1, generator=g, device=dev)
+    r = pde.compute_residual(model, x, t).detach()
+    idx = torch.randint(0, n, (2048,), generator=g, device=dev)
+    want = ref_port.burgers_residual(m64, x[idx].cpu().double(), t[idx].cpu().double(), nu=PDES["burgers"]["params"]["nu"])
+    assert rel(r[idx], want) <= TOL
+    mag, stats = pde.score_residual(model, x, t)
+    assert torch.equal(mag, r.abs().reshape(-1))
+    assert abs(stats[1].item() - float((r.double() ** 2).sum())) <= 1e-9 * stats[1].item()
+    # whole batch
+    comp, _ = F.loss_components(pde, model, x, t)
+    (gw,) = torch.autograd.grad(comp[0], [p for p in model.parameters()][4:5])          # one 128x128 weight is enough
+    h = n // 2
+    c1, _ = F.loss_components(pde, model, x[:h], t[:h], n_global=n)
+    c2, _ = F.loss_components(pde, model, x[h:], t[h:], n_global=n)
+    (g1,) = torch.autograd.grad(c1[0], [p for p in model.parameters()][4:5])
+    (g2,) = torch.autograd.grad(c2[0], [p for p in model.parameters()][4:5])
+    assert abs(comp[0].item() - 0.5 * (c1[0].item() + c2[0].item())) <= 2e-6 * abs(comp[0].item())
+    assert abs(comp[0].item() - float((r.double() ** 2).mean())) <= 2e-6 * abs(comp[0].item())
+    assert rel(0.5 * (g1 + g2), gw) <= 5e-6
+    assert abs(comp[1].item() - c1[1].item()) <= 1e-7 * abs(comp[1].item()) + 1e-12       # BC/IC terms do not depend on the shard
