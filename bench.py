@@ -108,7 +108,7 @@ def run_reference(args):
 def workload_config(args, world):
     return {"workload": "Burgers nu=0.01/pi, feedforward tanh 8x128, 1M collocation pts per B200 (BASELINE configs[1])",
             "points_per_gpu": args.points, "global_points": args.points * world, "jet_columns": JET_COLS,
-            "boundary_rows": 200, "initial_rows": 100, "optimizer": "Adam lr=1e-3, clip 1.0",
+            "boundary_rows": 200, "initial_rows": 100, "optimizer": "Adam lr=1e-3, clip_grad_norm 1.0 (fused in libpinnk)",
             "parallelism": f"dp{world} (rows sharded, one all-reduce of the flat gradient)",
             "l2": "flushed between timed steps (256 MiB write); per-step CUDA events summed"}
 
@@ -185,19 +185,14 @@ def run_ours(args):
     xh, th = synth_points(n_local, 1 + rank)
     xh, th = xh.pin_memory(), th.pin_memory()
     x, t = xh.to(dev), th.to(dev)
-    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    # the package's public trainer step (mirror of PDETrainer's inner step): loss + weighted gradient in one pass per
+    # row set, [all-reduce], clip_grad_norm_(1.0) + Adam in libpinnk.  --unfused uses compute_loss().backward() + torch Adam.
+    cfg = pk.TrainingConfig(learning_rate=1e-3, weight_decay=0.0, gradient_clipping=1.0, scheduler="none")
+    trainer = pk.PDETrainer(model, pde, config=cfg, device=dev, fused=not args.unfused)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def step(xd, td):
-        opt.zero_grad(set_to_none=True)
-        if world > 1:
-            losses = parallel.sharded_loss_backward(pde, model, xd, td, n_global=n_global)
-        else:
-            losses = pde.compute_loss(model, xd, td)
-            losses["total"].backward()
-        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
-        opt.step()
-        return losses["total"]
+        return trainer.train_step(xd, td, n_global=n_global)["total"]
 
     def sync():
         if world > 1:
@@ -334,6 +329,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--points", type=int, default=1 << 20, help="collocation rows per GPU")
+    ap.add_argument("--unfused", action="store_true", help="autograd route: compute_loss().backward() + torch clip/Adam")
     ap.add_argument("--lite", action="store_true", help="timed steps only (for runs under ncu): no e2e / roofline / cpu passes")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -134,6 +134,13 @@ int pinnk_score(pinnk_plan_t plan, const float* const* params, const float* x, c
                 int64_t n, const PinnkPde* pde, float* abs_residual_out, double* stats,
                 void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Fused optimizer tail of the trainer step (trainer.py:690-694 clip_grad_norm_, :292-297 Adam with L2 weight decay):
+ * params[i] (device, numels[i] floats, written in place) are laid out in flat_grad / exp_avg / exp_avg_sq in order.
+ * max_norm <= 0 disables clipping.  scratch: device, 1 double.  step counts from 1. */
+int pinnk_adam_step(float* const* params, const int64_t* numels, int32_t n_tensors, const float* flat_grad,
+                    float* exp_avg, float* exp_avg_sq, double* scratch, int64_t step, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, float max_norm, void* stream);
+
 const char* pinnk_last_error(void);
 int32_t pinnk_abi_version(void);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */

@@ -42,7 +42,7 @@ EXPORTS = ["pinnk_plan_create", "pinnk_plan_destroy", "pinnk_plan_workspace_byte
            "pinnk_plan_grad_floats", "pinnk_jets_forward", "pinnk_jets_vjp", "pinnk_loss_step", "pinnk_score",
            "pinnk_last_error", "pinnk_abi_version", "pinnk_launch_count", "pinnk_prof_enable", "pinnk_prof_classes",
            "pinnk_prof_class_name", "pinnk_prof_collect", "pinnk_debug_linear_fwd",
-           "pinnk_debug_linear_dgrad", "pinnk_debug_linear_wgrad"]
+           "pinnk_debug_linear_dgrad", "pinnk_debug_linear_wgrad", "pinnk_adam_step"]
 
 _lib = None
 
@@ -95,6 +95,9 @@ def load():
     lib.pinnk_prof_collect.restype = C.c_int
     lib.pinnk_debug_linear_fwd.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]
     lib.pinnk_debug_linear_fwd.restype = C.c_int
+    lib.pinnk_adam_step.argtypes = [vp, vp, i32, vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float,
+                                    C.c_float, C.c_float, vp]
+    lib.pinnk_adam_step.restype = C.c_int
     lib.pinnk_debug_linear_dgrad.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp]
     lib.pinnk_debug_linear_dgrad.restype = C.c_int
     lib.pinnk_debug_linear_wgrad.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]

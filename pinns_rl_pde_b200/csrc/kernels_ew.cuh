@@ -790,4 +790,57 @@ __global__ void score_kernel(const float* __restrict__ U, JetSpec js, PdeDesc pd
   }
 }
 
+// ------------------------------------------------------------------ fused optimizer tail (trainer.py:690-694,292-297)
+// clip_grad_norm_(max_norm) + Adam with L2 weight decay on the flat gradient, writing the parameters in place.
+struct ParamTable {
+  float* ptr[64];
+  int64_t off[65];      // flat offsets, off[n] = total
+  int n;
+};
+
+__global__ void sumsq_kernel(const float* __restrict__ g, int64_t count, double* __restrict__ out) {
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = g[i];
+    acc += v * v;
+  }
+  acc = warp_sum_d(acc);
+  __shared__ double sh[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) sh[wid] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    double v = (lane < (blockDim.x >> 5)) ? sh[lane] : 0.0;
+    v = warp_sum_d(v);
+    if (lane == 0) atomicAdd(out, v);
+  }
+}
+
+__global__ void adam_kernel(ParamTable tab, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            const double* __restrict__ sumsq, float max_norm, float lr, float beta1, float beta2, float eps,
+                            float weight_decay, float bc1, float bc2_sqrt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= tab.off[tab.n]) return;
+  int lo = 0, hi = tab.n - 1;                      // tensor holding flat index i
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tab.off[mid] <= i) lo = mid; else hi = mid - 1;
+  }
+  float* p = tab.ptr[lo] + (i - tab.off[lo]);
+  float clip = 1.f;
+  if (max_norm > 0.f) {                            // torch: clip_coef = max_norm / (total_norm + 1e-6), clamped to 1
+    const float total = (float)sqrt(*sumsq);
+    clip = fminf(max_norm / (total + 1e-6f), 1.f);
+  }
+  float grad = g[i] * clip;
+  const float pv = *p;
+  if (weight_decay != 0.f) grad = fmaf(weight_decay, pv, grad);
+  const float mi = beta1 * m[i] + (1.f - beta1) * grad;        // torch.lerp(m, g, 1 - beta1)
+  const float vi = beta2 * v[i] + (1.f - beta2) * grad * grad;
+  m[i] = mi;
+  v[i] = vi;
+  const float denom = sqrtf(vi) / bc2_sqrt + eps;
+  *p = pv - (lr / bc1) * (mi / denom);
+}
+
 }  // namespace pinnk

@@ -10,6 +10,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <math.h>
 #include <string.h>
 #include <algorithm>
 #include <atomic>
@@ -787,5 +788,30 @@ extern "C" int pinnk_debug_linear_wgrad(const float* dZ, const float* X, float* 
     bias_grad_kernel<<<g2, 128, 0, st>>>(dZ, M / jet_cols, N, jet_cols, db);
     PK_LAUNCH_OK();
   }
+  return 0;
+}
+
+// ---- fused optimizer tail: clip_grad_norm_ + Adam(L2) on the flat gradient (trainer.py:690-694,292-297)
+extern "C" int pinnk_adam_step(float* const* params, const int64_t* numels, int32_t n_tensors, const float* flat_grad,
+                               float* exp_avg, float* exp_avg_sq, double* scratch, int64_t step, float lr, float beta1,
+                               float beta2, float eps, float weight_decay, float max_norm, void* stream) {
+  if (!params || !numels || !flat_grad || !exp_avg || !exp_avg_sq || !scratch || n_tensors < 1 || n_tensors > 64 || step < 1)
+    return fail(PINNK_E_INVALID, "adam_step: bad argument (1..64 tensors, step >= 1)");
+  ParamTable tab;
+  tab.n = n_tensors;
+  int64_t off = 0;
+  for (int i = 0; i < n_tensors; ++i) { tab.ptr[i] = params[i]; tab.off[i] = off; off += numels[i]; }
+  tab.off[n_tensors] = off;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (max_norm > 0.f) {
+    PK_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(double), st));
+    sumsq_kernel<<<(unsigned)std::min<int64_t>((off + 255) / 256, 592), 256, 0, st>>>(flat_grad, off, scratch);
+    PK_LAUNCH_OK();
+  }
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  adam_kernel<<<blocks_for(off, 256), 256, 0, st>>>(tab, flat_grad, exp_avg, exp_avg_sq, scratch, max_norm, lr, beta1, beta2, eps,
+                                                    weight_decay, bc1, bc2_sqrt);
+  PK_LAUNCH_OK();
   return 0;
 }

@@ -232,10 +232,9 @@ def _data_loss(pde, model) -> torch.Tensor:
     return pde._apply_loss_fn(u - obs["u"].to(dev))
 
 
-def loss_components(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_global: Optional[int] = None):
-    """The three physics components [residual, boundary, initial] as one differentiable tensor, plus the
-    weights the reference would combine them with.  ``n_global``: number of collocation rows of the whole
-    (possibly sharded) batch -- the reference derives default BC/IC point counts from it."""
+def _build_calls(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_global: Optional[int] = None):
+    """The libpinnk calls (engine, rows, segments) that make up compute_loss: residual rows (component 0), boundary
+    rows (1), initial rows (2), exactly the point sets and targets the reference builds."""
     name = pde_name(pde)
     heat = name == "heat"
     dim = int(pde.dimension)
@@ -351,9 +350,45 @@ def loss_components(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_g
             Segment(kind=L.PDE_VALUE, row_start=0, row_count=100, component=2, weight=0.01,
                     target=target.detach().to(torch.float32).reshape(-1).contiguous(), **mk)]))
 
+    return calls, _weights(pde, heat)
+
+
+def loss_components(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_global: Optional[int] = None):
+    """The three physics components [residual, boundary, initial] as one differentiable tensor, plus the
+    weights the reference would combine them with.  ``n_global``: number of collocation rows of the whole
+    (possibly sharded) batch -- the reference derives default BC/IC point counts from it."""
+    calls, weights = _build_calls(pde, model, x, t, n_global)
     program = get_program(model)
     comp = _LossFn.apply(calls, 3, program, *program.grad_params)
-    return comp, _weights(pde, heat)
+    return comp, weights
+
+
+def loss_step_flat(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_global: Optional[int] = None,
+                   res_scale: float = 1.0, rest_scale: float = 1.0, flat: Optional[torch.Tensor] = None):
+    """compute_loss and the gradient of its weighted total in ONE pass per row set, with the final weights folded into
+    the seeds of the reverse pass -- the trainer's inner step when the weights are known up front
+    (trainer.py:578,689 with fixed ``loss_weights``).  No per-component gradient buffers, no autograd graph.
+
+    Returns (components fp32 [3] = residual, boundary, initial means; weights; flat gradient of
+    ``res_scale * w_res * residual + rest_scale * (w_bc * boundary + w_ic * initial)`` in ``model.parameters()`` order).
+    ``res_scale`` / ``rest_scale`` are the shard weights of the data-parallel step (parallel.py)."""
+    calls, weights = _build_calls(pde, model, x, t, n_global)
+    w_res, w_bc, w_ic, w_smooth, adaptive = weights
+    if w_smooth:
+        raise NotImplementedError("the fused step does not cover the smoothness regulariser; use compute_loss")
+    if adaptive:
+        w_res = w_bc = w_ic = 1.0
+    program = get_program(model)
+    dev = calls[0][1].device
+    if flat is None:
+        flat = torch.zeros(program.grad_floats, dtype=torch.float32, device=dev)
+    else:
+        flat.zero_()
+    sums = torch.zeros(3, dtype=torch.float64, device=dev)
+    scale = [res_scale * w_res, rest_scale * w_bc, rest_scale * w_ic]
+    for engine, xx, tt, segments in calls:
+        engine.loss_step(xx, tt, segments, 3, True, scale, flat, sums)
+    return sums.to(torch.float32), (w_res, w_bc, w_ic), flat
 
 
 def compute_loss(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor) -> Dict[str, torch.Tensor]:

@@ -339,3 +339,26 @@ def test_full_size_1m_points_properties(dev):
     assert abs(comp[0].item() - float((r.double() ** 2).mean())) <= 2e-6 * abs(comp[0].item())
     assert rel(0.5 * (g1 + g2), gw) <= 5e-6
     assert abs(comp[1].item() - c1[1].item()) <= 1e-7 * abs(comp[1].item()) + 1e-12       # BC/IC terms do not depend on the shard
+
+
+def test_fused_trainer_step_matches_autograd_route(dev):
+    """PDETrainer(fused=True): loss + weighted gradient in one pass and clip + Adam in libpinnk must follow the same
+    trajectory as compute_loss().backward() + torch clip_grad_norm_ + torch.optim.Adam (trainer.py:577-578,689-694)."""
+    import copy
+    import pinns_rl_pde_b200 as pk
+    torch.manual_seed(0)
+    m1 = pk.make_model("feedforward", 2, 128, 3, dev)
+    m2 = copy.deepcopy(m1)
+    pde = product_pde("burgers", dev)
+    cfg = pk.TrainingConfig(learning_rate=2e-3, weight_decay=1e-4, gradient_clipping=0.5, scheduler="none")
+    t1 = pk.PDETrainer(m1, pde, config=cfg, device=dev, fused=True)
+    t2 = pk.PDETrainer(m2, pde, config=cfg, device=dev, fused=False)
+    g = torch.Generator().manual_seed(3)
+    for it in range(20):
+        x, t = (torch.rand(3000, 1, generator=g) * 2 - 1).to(dev), torch.rand(3000, 1, generator=g).to(dev)
+        l1 = t1.train_step(x, t)
+        l2 = t2.train_step(x, t)
+        assert abs(l1["total"].item() - l2["total"].item()) <= 2e-5 * abs(l2["total"].item()), it
+    p1 = torch.cat([p.detach().reshape(-1) for p in m1.parameters()])
+    p2 = torch.cat([p.detach().reshape(-1) for p in m2.parameters()])
+    assert rel(p1, p2) <= 1e-5
