@@ -1,0 +1,50 @@
+"""CPU: patch_reference() swaps the hot path into the reference's own classes (only runs where /root/reference
+exists, i.e. in the build container); with no GPU the patched methods must raise -- never fall back."""
+import os
+import sys
+from unittest.mock import MagicMock
+
+import pytest
+import torch
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pinnrl")), reason="reference not mounted")
+
+
+def test_patch_and_unpatch_reference():
+    sys.path.insert(0, REF)
+    for m in ("matplotlib", "matplotlib.pyplot", "matplotlib.colors", "plotly", "plotly.graph_objects",
+              "plotly.subplots", "plotly.express"):
+        if m not in sys.modules:
+            mm = MagicMock()
+            mm.__path__ = []
+            sys.modules[m] = mm
+    try:
+        import pinnrl.pdes.burgers_equation as be
+        from pinnrl.config import Config, ModelConfig
+        from pinnrl.neural_networks import PINNModel
+        from pinnrl.pdes.pde_base import PDEConfig
+        import pinns_rl_pde_b200 as pk
+        from pinns_rl_pde_b200 import _lib, dropin
+        from pinns_rl_pde_b200.program import compile_network
+        orig = be.BurgersEquation.compute_residual
+        names = pk.patch_reference()
+        assert "BurgersEquation" in names and be.BurgersEquation.compute_residual is not orig
+        c = Config.__new__(Config)
+        c.device = torch.device("cpu")
+        c.model = ModelConfig(2, 32, 1, 3, "tanh", architecture="feedforward")
+        model = PINNModel(config=c, device=torch.device("cpu"))
+        prog = compile_network(model)                      # the reference's own module lowers to the op program
+        assert len(prog.ops) == 7 and prog.grad_floats == sum(p.numel() for p in model.parameters())
+        pde = be.BurgersEquation(config=PDEConfig(name="burgers", domain=[[-1.0, 1.0]], time_domain=[0.0, 1.0],
+                                                  parameters={"nu": 0.01}, boundary_conditions={"dirichlet": {"value": 0.0}},
+                                                  initial_condition={"type": "sine"}, exact_solution={}, dimension=1,
+                                                  device=torch.device("cpu")))
+        with pytest.raises(_lib.PinnkError):               # CPU tensors: loud failure, no fallback
+            pde.compute_residual(model, torch.zeros(4, 1), torch.zeros(4, 1))
+        dropin.unpatch_reference()
+        assert be.BurgersEquation.compute_residual is orig
+        r = pde.compute_residual(model, torch.zeros(4, 1), torch.zeros(4, 1))      # the reference path again
+        assert r.shape == (4, 1)
+    finally:
+        sys.path.remove(REF)
