@@ -887,10 +887,15 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
     }
     __syncwarp();
   } else if (warp < NCW) {
-    // ===================== convert warps: raw tile -> hi/lo operand tile; lane = 16-byte chunk (4 features) ==========
-    constexpr int RPW = TK / NCW;
-    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
-    const bool want_b = (db != nullptr) && (i0 == 0);
+    // ===================== convert warps: raw [rows x 128] tile -> TRANSPOSED hi/lo operand tile [128 features x TK] ====
+    // Both UMMA operands are K-major (K = rows of the tile): feature f owns one 128-byte swizzle row holding its TK = 32
+    // row values.  Warp w converts row quad (w % 8) of tensor (w / 8: 0 = G, 1 = X); lane l owns features l, l+32, l+64,
+    // l+96, so the four values of a feature for the quad are one 16-byte chunk and a quarter-warp's STS.128 hit eight
+    // distinct 16-byte slots (conflict-free), while the raw reads are lane-contiguous LDS.32.
+    static_assert(NCW == 16 && TK == 32, "convert mapping");
+    const int rq = warp & 7, sel = warp >> 3;
+    float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool want_b = (db != nullptr) && (i0 == 0) && sel == 0;
     const uint32_t ob = smem_u32(op_base), rb = smem_u32(raw_base);
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -899,44 +904,46 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
       const int64_t r0 = tile * TK;
       const int nrows = (M - r0 >= TK) ? TK : (int)(M - r0);
       mbar_wait(&raw_full[rs], rph);
-      const uint32_t rg = rb + (uint32_t)rs * 2 * RAW_BYTES, rx = rg + RAW_BYTES;
-      float4 g4[RPW], x4[RPW];
+      const uint32_t raw = rb + (uint32_t)rs * 2 * RAW_BYTES + (uint32_t)sel * RAW_BYTES;
+      float v[4][4];                                       // [row of the quad][feature e]
 #pragma unroll
-      for (int i = 0; i < RPW; ++i) {
-        const int r = warp + NCW * i;
-        if (r < nrows) { g4[i] = lds128(rg + r * 512 + lane * 16); x4[i] = lds128(rx + r * 512 + lane * 16); }
-        else { g4[i] = make_float4(0.f, 0.f, 0.f, 0.f); x4[i] = g4[i]; }
+      for (int r = 0; r < 4; ++r) {
+        const int row = rq * 4 + r;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float x = 0.f;
+          if (row < nrows) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(raw + row * 512 + (lane + 32 * e) * 4));
+          v[r][e] = x;
+        }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&raw_empty[rs]);                 // raw data is in registers: slot may be refilled
       mbar_wait(&empty[os], oph ^ 1u);
-      const uint32_t gh = ob + (uint32_t)os * 4 * OP_BYTES, gl = gh + OP_BYTES, xh = gl + OP_BYTES, xl = xh + OP_BYTES;
-      uint32_t cj = want_b ? (uint32_t)((uint32_t)(r0 + warp) % (uint32_t)jet_cols) : 1u;
+      const uint32_t hi_base = ob + (uint32_t)os * 4 * OP_BYTES + (uint32_t)sel * 2 * OP_BYTES, lo_base = hi_base + OP_BYTES;
+      if (want_b) {
+        uint32_t cj = (uint32_t)((uint32_t)(r0 + rq * 4) % (uint32_t)jet_cols);
 #pragma unroll
-      for (int i = 0; i < RPW; ++i) {
-        const int r = warp + NCW * i;                       // row inside the tile == K index
-        // MN-major SW128/32B: [4-row K group: 2048 B][32-float M/N group: 512 B][row % 4: 128 B][32B chunk ^ (row % 4)][16 B half]
-        const uint32_t off = (uint32_t)((r >> 2) * 2048 + (lane >> 3) * 512 + (r & 3) * 128 +
-                                        (((((lane & 7) >> 1) ^ (r & 3)) << 5)) + ((lane & 1) << 4));
-        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-        split_bits(g4[i].x, h0, l0); split_bits(g4[i].y, h1, l1); split_bits(g4[i].z, h2, l2); split_bits(g4[i].w, h3, l3);
-        sts128(gh + off, h0, h1, h2, h3);
-        sts128(gl + off, l0, l1, l2, l3);
-        if (want_b) {
-          if (cj == 0) { bsum.x += g4[i].x; bsum.y += g4[i].y; bsum.z += g4[i].z; bsum.w += g4[i].w; }
-          cj = (cj + NCW) % (uint32_t)jet_cols;
+        for (int r = 0; r < 4; ++r) {
+          if (cj == 0) { bsum[0] += v[r][0]; bsum[1] += v[r][1]; bsum[2] += v[r][2]; bsum[3] += v[r][3]; }
+          cj = (cj + 1 == (uint32_t)jet_cols) ? 0u : cj + 1;
         }
-        split_bits(x4[i].x, h0, l0); split_bits(x4[i].y, h1, l1); split_bits(x4[i].z, h2, l2); split_bits(x4[i].w, h3, l3);
-        sts128(xh + off, h0, h1, h2, h3);
-        sts128(xl + off, l0, l1, l2, l3);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int f = lane + 32 * e;
+        uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+        split_bits(v[0][e], h0, l0); split_bits(v[1][e], h1, l1); split_bits(v[2][e], h2, l2); split_bits(v[3][e], h3, l3);
+        const uint32_t off = sw128_offset(128, f, rq);            // K-major SW128: row = feature, 16-byte chunk = row quad
+        sts128(hi_base + off, h0, h1, h2, h3);
+        sts128(lo_base + off, l0, l1, l2, l3);
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[os]);
     }
     if (want_b) {
-      atomicAdd(db + o0 + lane * 4 + 0, bsum.x); atomicAdd(db + o0 + lane * 4 + 1, bsum.y);
-      atomicAdd(db + o0 + lane * 4 + 2, bsum.z); atomicAdd(db + o0 + lane * 4 + 3, bsum.w);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) atomicAdd(db + o0 + lane + 32 * e, bsum[e]);
     }
   } else if (warp < MMAW) {
     // ===================== flush warps: fold finished segments into the fp32 running sum, write out at the end ======
@@ -986,8 +993,8 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
   } else if (warp == MMAW) {
     // ===================== MMA issuer =====================
     if (lane == 0 && my_segs > 0) {
-      constexpr uint32_t idesc = make_idesc_tf32_mn(128, 128);
-      const uint64_t dconst = make_desc_mn_sw128(0, 512, 2048);
+      constexpr uint32_t idesc = make_idesc_tf32(128, 128);
+      const uint64_t dconst = make_desc_k_sw128(0);
       const uint32_t sbase = smem_u32(op_base) >> 4;
       int it = 0;
       int64_t seg = 0;
@@ -1004,7 +1011,7 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
         const uint32_t d_main = tmem_base + COL_MAIN + (uint32_t)b * 128, d_corr = tmem_base + COL_CORR;
 #pragma unroll
         for (int ks = 0; ks < TK / 8; ++ks) {
-          const uint32_t o = (uint32_t)ks * (4096 >> 4);
+          const uint32_t o = (uint32_t)ks * (32 >> 4);                 // 8 K values = 32 bytes inside the swizzle row
           const uint64_t a_hi = dconst | (uint64_t)(gh + o), a_lo = dconst | (uint64_t)(gl + o);
           const uint64_t b_hi = dconst | (uint64_t)(xh + o), b_lo = dconst | (uint64_t)(xl + o);
           umma_tf32(d_corr, a_lo, b_hi, idesc, (it | ks) ? 1u : 0u);
