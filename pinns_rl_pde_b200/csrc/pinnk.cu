@@ -22,7 +22,7 @@
 #include "jet_math.cuh"
 #include "kernels_ew.cuh"
 #include "sgemm.cuh"
-#include "tc_gemm.cuh"
+#include "tc_api.h"
 
 using namespace pinnk;
 
@@ -93,6 +93,16 @@ struct pinnk_plan_s {
 };
 
 static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// PINNK_SM_COUNT=n sizes every persistent grid for n SMs (experiments: kernels sharing the GPU on two streams)
+static int sm_count_of(int device) {
+  int smc = 148;
+  cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, device);   // stays 148 when no device is visible
+  cudaGetLastError();
+  if (smc <= 0) smc = 148;
+  if (const char* e = getenv("PINNK_SM_COUNT")) { const int v = atoi(e); if (v > 0 && v < smc) smc = v; }
+  return smc;
+}
 
 extern "C" const char* pinnk_last_error(void) { return g_err.c_str(); }
 extern "C" int32_t pinnk_abi_version(void) { return PINNK_ABI_VERSION; }
@@ -244,10 +254,7 @@ extern "C" int pinnk_plan_create(const PinnkOp* ops, int32_t n_ops, int32_t in_d
   pl->off_Ub = o;    o = align_up(o + C * n, 64);
   for (int k = 0; k < 3; ++k) { pl->off_adj[k] = o; o = align_up(o + C * n * max_width, 64); }
   pl->ws_bytes = o * (int64_t)sizeof(float);
-  int smc = 148;
-  cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, device);   // stays 148 when no device is visible
-  cudaGetLastError();
-  pl->sm_count = smc > 0 ? smc : 148;
+  pl->sm_count = sm_count_of(device);
   *out = pl;
   return 0;
 }
@@ -725,10 +732,9 @@ extern "C" int pinnk_score(pinnk_plan_t plan, const float* const* params, const 
 extern "C" int pinnk_debug_linear_fwd(const float* X, const float* W, const float* bias, float* Z, int64_t M, int32_t K,
                                       int32_t N, int32_t jet_cols, int32_t mode, void* stream) {
   if (!X || !W || !Z || M < 1 || (K % 4) || (N % 4) || jet_cols < 1) return fail(PINNK_E_INVALID, "debug_linear_fwd: bad argument");
-  int smc = 148;
   int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, dev);
+  const int smc = sm_count_of(dev);
   if (mode == 1) {
     int rc = tc_linear_fwd(X, W, bias, Z, M, K, N, jet_cols, smc, (cudaStream_t)stream);
     if (rc == TC_UNSUPPORTED) return fail(PINNK_E_INVALID, "debug_linear_fwd: shape not covered by the tcgen05 path");
@@ -743,9 +749,9 @@ extern "C" int pinnk_debug_linear_fwd(const float* X, const float* W, const floa
 extern "C" int pinnk_debug_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t M, int32_t K, int32_t N,
                                         int32_t mode, void* stream) {
   if (!dZ || !W || !dX || M < 1 || (K % 4) || (N % 4)) return fail(PINNK_E_INVALID, "debug_linear_dgrad: bad argument");
-  int smc = 148, dev = 0;
+  int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, dev);
+  const int smc = sm_count_of(dev);
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == 1) {
     int rc = tc_linear_dgrad(dZ, W, dX, M, K, N, smc, st);
@@ -764,9 +770,9 @@ extern "C" int pinnk_debug_linear_dgrad(const float* dZ, const float* W, float* 
 extern "C" int pinnk_debug_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int32_t K,
                                         int32_t N, int32_t jet_cols, int32_t mode, void* stream) {
   if (!dZ || !X || !dW || M < 1 || (K % 4) || (N % 4) || jet_cols < 1 || (M % jet_cols)) return fail(PINNK_E_INVALID, "debug_linear_wgrad: bad argument");
-  int smc = 148, dev = 0;
+  int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, dev);
+  const int smc = sm_count_of(dev);
   cudaStream_t st = (cudaStream_t)stream;
   if (mode == 1) {
     int rc = tc_linear_wgrad(dZ, X, dW, db, M, K, N, jet_cols, smc, st);

@@ -1,0 +1,28 @@
+// tc_api.h -- entry points of the tcgen05 3xTF32 GEMM kernels (tc_gemm.cuh), one translation unit per kernel family
+// (tc_rows_fwd.cu, tc_rows_bwd.cu, tc_wgrad.cu) so that the library builds in parallel.
+// Every function returns 0 when launched, TC_UNSUPPORTED when the shape is not covered (the caller then uses the
+// exact-fp32 CUDA-core GEMM), < 0 on a launch error.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pinnk {
+constexpr int TC_UNSUPPORTED = 1;
+
+// Z[M,N] = X[M,K] W[N,K]^T (+ bias on value-column rows)
+int tc_linear_fwd(const float* X, const float* W, const float* bias, float* Z, int64_t M, int K, int N, int jet_cols,
+                  int sm_count, cudaStream_t st);
+// Forward Linear + activation jets in one kernel: Z = X W^T + b (stash, may be null for K = 128), Yact = act(Z).
+// act: 1 tanh, 2 sin(omega z); (k0, k1) = jet orders of the (at most two) directions
+int tc_linear_act_fwd(const float* X, const float* W, const float* bias, float* Z, float* Yact, int64_t M, int K, int N,
+                      int k0, int k1, int act, float omega, int sm_count, cudaStream_t st);
+// dX[M,in] = dZ[M,out] W[out,in]   (W row-major [out,in])
+int tc_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t M, int in_dim, int out_dim, int sm_count,
+                    cudaStream_t st);
+// dgrad + activation adjoint in one kernel: dZprev = act'(Zprev)^T (dZ W)
+int tc_linear_dgrad_actbwd(const float* dZ, const float* W, const float* Zprev, float* dZprev, int64_t M, int in_dim,
+                           int out_dim, int k0, int k1, int act, float omega, int sm_count, cudaStream_t st);
+// dW[out,in] += dZ[M,out]^T X[M,in] ;  db[out] += sum over value-column rows of dZ
+int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
+                    int jet_cols, int sm_count, cudaStream_t st);
+}  // namespace pinnk

@@ -26,10 +26,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <type_traits>
 #include "jet_math.cuh"
+#include "tc_api.h"
 
 namespace pinnk {
-constexpr int TC_UNSUPPORTED = 1;
 
 namespace tc {
 
@@ -47,13 +48,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
-  for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+  // the suspend-time hint lets the hardware park the warp until the phase completes instead of re-polling every few
+  // hundred cycles (polling warps took ~25 % of the issue slots of the rows kernels)
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(100000u)
         : "memory");
     if (done) return;
   }
@@ -480,11 +483,14 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 // direction 1, with C = 1 + K0 + K1 dividing 32 so that every epilogue warp owns whole points.
 enum { EPI_PLAIN = 0, EPI_ACT = 1, EPI_ACTBWD = 2 };
 
-template <bool TRANS_W, int EPI, int ACT, int K0, int K1, int NLW, int ECOLS, bool ACCUM>
+template <bool TRANS_W, int EPI, int ACT, int K0, int K1, int NLW, int ECOLS, bool ACCUM, int LDYC>
 __global__ void __launch_bounds__((NLW + 4 * (64 / ECOLS) + 2) * 32, 1)
 linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
-                      float* __restrict__ Y, int64_t M, int ldy, int jet_cols, const float* __restrict__ Zs,
+                      float* __restrict__ Y, int64_t M, int ldy_rt, int jet_cols, const float* __restrict__ Zs,
                       float* __restrict__ Yact, float omega, int ldx) {
+  // LDYC: compile-time row stride of Y / Zs / Yact (0 = use the runtime value): with it every row address of the
+  // epilogue is base + immediate instead of a 64-bit multiply-add per access
+  const int ldy = LDYC ? LDYC : ldy_rt;
   // ldx: row stride of X in floats (K = 128 columns of it are contracted: one half of a 256-wide layer);
   // ACCUM: the epilogue adds the partial result already stored in Y (second K half of a 256-wide layer)
   constexpr int K = 128, TN = 64, STAGES = 2, RS = 3, ACC = 2, NEW = 4 * (TN / ECOLS);
@@ -533,10 +539,18 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
 #pragma unroll 1
     for (int c0 = 0; c0 < K; c0 += 32) {
       uint32_t hi[32], lo[32];
+      if constexpr (TRANS_W) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float v = TRANS_W ? W[(int64_t)(c0 + j) * ldw + n0 + f] : W[(int64_t)(n0 + f) * ldw + c0 + j];
-        split_bits(v, hi[j], lo[j]);
+        for (int j = 0; j < 32; ++j) split_bits(W[(int64_t)(c0 + j) * ldw + n0 + f], hi[j], lo[j]);   // lanes contiguous
+      } else {
+        // a thread's 32 values are one 128-byte line of its weight row: 8 x LDG.128 (ldw % 4 == 0)
+        const float4* wr = reinterpret_cast<const float4*>(W + (int64_t)(n0 + f) * ldw + c0);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const float4 v = __ldg(wr + j4);
+          split_bits(v.x, hi[4 * j4], lo[4 * j4]); split_bits(v.y, hi[4 * j4 + 1], lo[4 * j4 + 1]);
+          split_bits(v.z, hi[4 * j4 + 2], lo[4 * j4 + 2]); split_bits(v.w, hi[4 * j4 + 3], lo[4 * j4 + 3]);
+        }
       }
       tmem_st32(lane_base + COL_WHI + c0, hi);
       tmem_st32(lane_base + COL_WLO + c0, lo);
@@ -606,36 +620,37 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
     const int q = e & 3, h = e >> 2;
     const int f = q * 32 + lane;
     const float bf = (!TRANS_W && bias) ? bias[n0 + f] : 0.f;
-    int it = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const int b = it % ACC;
-      const uint32_t ph = (uint32_t)(it / ACC) & 1u;
-      const int64_t r0 = tile * TN + h * ECOLS;
+    const bool store_z = (EPI != EPI_ACT) || (Y != nullptr);     // forward-only callers (scoring) pass no stash buffer
+    const uint32_t lane_acc = tmem_base + ((uint32_t)(q * 32) << 16) + COL_ACC + (uint32_t)(h * ECOLS);
+    // One tile of this warp.  FULL: all ECOLS rows exist, so no access is predicated and (with LDYC) every row address
+    // is the tile base plus an immediate.
+    auto run_tile = [&](auto full_tag, const int b, const uint32_t ph, const int64_t r0, const int nrows) {
+      constexpr bool FULL = decltype(full_tag)::value;
       uint32_t vmask = 0;
-      if (!TRANS_W && bias) {
-        int cj = (int)((uint32_t)r0 % (uint32_t)jet_cols);
+      if constexpr (EPI == EPI_PLAIN) {
+        if (!TRANS_W && bias) {
+          int cj = (int)((uint32_t)r0 % (uint32_t)jet_cols);
 #pragma unroll
-        for (int j = 0; j < ECOLS; ++j) { vmask |= (cj == 0 ? 1u : 0u) << j; cj = (cj + 1 == jet_cols) ? 0 : cj + 1; }
+          for (int j = 0; j < ECOLS; ++j) { vmask |= (cj == 0 ? 1u : 0u) << j; cj = (cj + 1 == jet_cols) ? 0 : cj + 1; }
+        }
       }
-      float* yp = Y + r0 * ldy + n0 + f;
-      const bool store_z = (EPI != EPI_ACT) || (Y != nullptr);     // forward-only callers (scoring) pass no stash buffer
-      const int nrows = (M - r0 >= ECOLS) ? ECOLS : (int)(M - r0 > 0 ? M - r0 : 0);
+      float* const yp = Y + r0 * ldy + n0 + f;
       // the stashed pre-activations do not depend on the MMA: fetch them while the accumulator is still being produced
       float zsr[(EPI == EPI_ACTBWD) ? ECOLS : 1];
       if constexpr (EPI == EPI_ACTBWD) {
-        const float* zs0 = Zs + r0 * ldy + n0 + f;
+        const float* const zs0 = Zs + r0 * ldy + n0 + f;
 #pragma unroll
-        for (int j = 0; j < ECOLS; ++j) zsr[j] = (j < nrows) ? __ldg(zs0 + (int64_t)j * ldy) : 0.f;
+        for (int j = 0; j < ECOLS; ++j) zsr[j] = (FULL || j < nrows) ? __ldg(zs0 + j * ldy) : 0.f;
       }
       // second K half of a 256-wide layer: the first half's partial result is in Y
       float part[ACCUM ? ECOLS : 1];
       if constexpr (ACCUM) {
 #pragma unroll
-        for (int j = 0; j < ECOLS; ++j) part[j] = (j < nrows) ? yp[(int64_t)j * ldy] : 0.f;
+        for (int j = 0; j < ECOLS; ++j) part[j] = (FULL || j < nrows) ? yp[j * ldy] : 0.f;
       }
       mbar_wait(&tfull[b], ph);
       tc_fence_after();
-      const uint32_t tb = tmem_base + ((uint32_t)(q * 32) << 16) + COL_ACC + (uint32_t)(b * 2 * TN + h * ECOLS);
+      const uint32_t tb = lane_acc + (uint32_t)(b * 2 * TN);
       uint32_t pm[ECOLS], pc[ECOLS];
       if constexpr (ECOLS == 32) { tmem_ld32_nowait(tb, pm); tmem_ld32_nowait(tb + TN, pc); }
       else { tmem_ld16_nowait(tb, pm); tmem_ld16_nowait(tb + TN, pc); }
@@ -643,40 +658,33 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[b]);
-      if constexpr (ACCUM) {
+      float acc[ECOLS];                                            // main + correction (+ first K half)
 #pragma unroll
-        for (int j = 0; j < ECOLS; ++j) pm[j] = __float_as_uint(__uint_as_float(pm[j]) + part[j]);
+      for (int j = 0; j < ECOLS; ++j) {
+        acc[j] = __uint_as_float(pc[j]) + __uint_as_float(pm[j]);
+        if constexpr (ACCUM) acc[j] += part[j];
       }
       if constexpr (EPI == EPI_PLAIN) {
-        if (nrows == ECOLS) {
 #pragma unroll
-          for (int j = 0; j < ECOLS; ++j) {
-            float val = __uint_as_float(pc[j]) + __uint_as_float(pm[j]);
-            if ((vmask >> j) & 1u) val += bf;
-            yp[(int64_t)j * ldy] = val;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < ECOLS; ++j) {
-            float val = __uint_as_float(pc[j]) + __uint_as_float(pm[j]);
-            if ((vmask >> j) & 1u) val += bf;
-            if (j < nrows) yp[(int64_t)j * ldy] = val;
-          }
+        for (int j = 0; j < ECOLS; ++j) {
+          float val = acc[j];
+          if ((vmask >> j) & 1u) val += bf;
+          if (FULL || j < nrows) yp[j * ldy] = val;
         }
       } else {
-        // whole points: columns [pp*JC, pp*JC + JC) of this warp's 32 are the jet of point pp at feature f
-        float* ya = (EPI == EPI_ACT) ? Yact + r0 * ldy + n0 + f : nullptr;
+        // whole points: columns [pp*JC, pp*JC + JC) of this warp's ECOLS are the jet of point pp at feature f
+        float* const ya = (EPI == EPI_ACT) ? Yact + r0 * ldy + n0 + f : nullptr;
 #pragma unroll
         for (int pp = 0; pp < ECOLS / JC; ++pp) {
           const int jb = pp * JC;
-          if (jb < nrows) {
+          if (FULL || jb < nrows) {
             float z[MAXK + 1], y[MAXK + 1], w[MAXK + 1];
             if constexpr (EPI == EPI_ACT) {
-              z[0] = __uint_as_float(pc[jb]) + __uint_as_float(pm[jb]) + bf;
-              if (store_z) yp[(int64_t)jb * ldy] = z[0];
+              z[0] = acc[jb] + bf;
+              if (store_z) yp[jb * ldy] = z[0];
               if (ACT == 1) { y[0] = tanhf(z[0]); w[0] = 1.f - y[0] * y[0]; }
               else { z[0] *= omega; sincosf(z[0], &y[0], &w[0]); }
-              ya[(int64_t)jb * ldy] = y[0];
+              ya[jb * ldy] = y[0];
 #pragma unroll
               for (int d = 0; d < 2; ++d) {
                 const int KD = d ? K1 : K0, cb = jb + (d ? K0 : 0);
@@ -684,15 +692,15 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
 #pragma unroll
                   for (int k = 1; k <= MAXK; ++k)
                     if (k <= KD) {
-                      z[k] = __uint_as_float(pc[cb + k]) + __uint_as_float(pm[cb + k]);
-                      if (store_z) yp[(int64_t)(cb + k) * ldy] = z[k];
+                      z[k] = acc[cb + k];
+                      if (store_z) yp[(cb + k) * ldy] = z[k];
                       if (ACT == 2) z[k] *= omega;
                     }
                   if (ACT == 1) tanh_dir_fwd<MAXK, float>(KD, z, y, w);
                   else sincos_dir_fwd<MAXK, float>(KD, z, y, w);
 #pragma unroll
                   for (int k = 1; k <= MAXK; ++k)
-                    if (k <= KD) ya[(int64_t)(cb + k) * ldy] = y[k];
+                    if (k <= KD) ya[(cb + k) * ldy] = y[k];
                 }
               }
             } else {   // EPI_ACTBWD
@@ -700,7 +708,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
               z[0] = zsr[jb];
               if (ACT == 1) { y[0] = tanhf(z[0]); w[0] = 1.f - y[0] * y[0]; }
               else { z[0] *= omega; sincosf(z[0], &y[0], &w[0]); }
-              yb[0] = __uint_as_float(pc[jb]) + __uint_as_float(pm[jb]);
+              yb[0] = acc[jb];
               float wb0 = 0.f;
 #pragma unroll
               for (int d = 0; d < 2; ++d) {
@@ -711,7 +719,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
                     if (k <= KD) {
                       z[k] = zsr[cb + k];
                       if (ACT == 2) z[k] *= omega;
-                      yb[k] = __uint_as_float(pc[cb + k]) + __uint_as_float(pm[cb + k]);
+                      yb[k] = acc[cb + k];
                     } else {
                       yb[k] = 0.f;
                     }
@@ -729,15 +737,23 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
                   }
 #pragma unroll
                   for (int k = 1; k <= MAXK; ++k)
-                    if (k <= KD) yp[(int64_t)(cb + k) * ldy] = (ACT == 2) ? zb[k] * omega : zb[k];
+                    if (k <= KD) yp[(cb + k) * ldy] = (ACT == 2) ? zb[k] * omega : zb[k];
                 }
               }
-              yp[(int64_t)jb * ldy] = (ACT == 1) ? tanh_finish_bwd<float>(y[0], w[0], yb[0], wb0)
-                                                 : (yb[0] * w[0] - wb0 * y[0]) * omega;
+              yp[jb * ldy] = (ACT == 1) ? tanh_finish_bwd<float>(y[0], w[0], yb[0], wb0)
+                                        : (yb[0] * w[0] - wb0 * y[0]) * omega;
             }
           }
         }
       }
+    };
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int b = it % ACC;
+      const uint32_t ph = (uint32_t)(it / ACC) & 1u;
+      const int64_t r0 = tile * TN + h * ECOLS;
+      if (M - r0 >= ECOLS) run_tile(std::true_type(), b, ph, r0, ECOLS);
+      else run_tile(std::false_type(), b, ph, r0, (int)(M - r0 > 0 ? M - r0 : 0));
     }
   } else if (warp == MMAW) {
     // ===================== MMA issuer =====================
@@ -777,10 +793,10 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
   }
 }
 
-template <bool TRANS_W, int EPI, int ACT, int K0, int K1>
-static int launch_linear_rows_ts(const float* X, const float* W, int ldw, const float* bias, float* Y, int64_t M, int n_cols,
-                                 int jet_cols, const float* Zs, float* Yact, float omega, int sm_count, cudaStream_t st,
-                                 int ldx = 128, int accum = 0) {
+template <bool TRANS_W, int EPI, int ACT, int K0, int K1, bool ACCUM, int LDYC>
+static int launch_linear_rows_ts_inst(const float* X, const float* W, int ldw, const float* bias, float* Y, int64_t M, int n_cols,
+                                      int jet_cols, const float* Zs, float* Yact, float omega, int sm_count, cudaStream_t st,
+                                      int ldx) {
   constexpr size_t smem = 1024 + (size_t)2 * 2 * 64 * 128 * 4 + (size_t)3 * 64 * 128 * 4 + (2 * 2 + 2 * 2 + 2 * 3) * 8 + 16;
   static_assert(smem <= 232448, "shared memory budget (227 KB per CTA)");
   constexpr int NLW = (EPI == EPI_ACTBWD) ? 4 : 8, ECOLS = (EPI == EPI_ACTBWD) ? 16 : 32;
@@ -791,24 +807,27 @@ static int launch_linear_rows_ts(const float* X, const float* W, int ldw, const 
   if ((int64_t)gx > ntiles) gx = (int)ntiles;
   dim3 grid((unsigned)gx, (unsigned)per_y, 1);
   constexpr int threads = (NLW + 4 * (64 / ECOLS) + 2) * 32;
-  if (accum) {
-    auto kern = linear_rows_ts_kernel<TRANS_W, EPI, ACT, K0, K1, NLW, ECOLS, true>;
-    static bool configured = false;
-    if (!configured) {
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-      configured = true;
-    }
-    kern<<<grid, threads, smem, st>>>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, ldx);
-  } else {
-    auto kern = linear_rows_ts_kernel<TRANS_W, EPI, ACT, K0, K1, NLW, ECOLS, false>;
-    static bool configured = false;
-    if (!configured) {
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-      configured = true;
-    }
-    kern<<<grid, threads, smem, st>>>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, ldx);
+  auto kern = linear_rows_ts_kernel<TRANS_W, EPI, ACT, K0, K1, NLW, ECOLS, ACCUM, LDYC>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    configured = true;
   }
+  kern<<<grid, threads, smem, st>>>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, ldx);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// 128-wide outputs (every BASELINE feed-forward / Fourier layer) get the compile-time row stride; 256-wide layers run as
+// two K halves (ACCUM) with the runtime stride
+template <bool TRANS_W, int EPI, int ACT, int K0, int K1>
+static int launch_linear_rows_ts(const float* X, const float* W, int ldw, const float* bias, float* Y, int64_t M, int n_cols,
+                                 int jet_cols, const float* Zs, float* Yact, float omega, int sm_count, cudaStream_t st,
+                                 int ldx = 128, int accum = 0) {
+  if (accum)
+    return launch_linear_rows_ts_inst<TRANS_W, EPI, ACT, K0, K1, true, 0>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, sm_count, st, ldx);
+  if (n_cols == 128)
+    return launch_linear_rows_ts_inst<TRANS_W, EPI, ACT, K0, K1, false, 128>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, sm_count, st, ldx);
+  return launch_linear_rows_ts_inst<TRANS_W, EPI, ACT, K0, K1, false, 0>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, sm_count, st, ldx);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1059,38 +1078,7 @@ static int launch_wgrad(const float* G, const float* X, float* dW, float* db, in
 
 }  // namespace tc
 
-// Z[M,N] = X[M,K] W[N,K]^T (+ bias on value-column rows).  Returns 0 when launched,
-// TC_UNSUPPORTED when the shape is not covered (caller uses the exact-fp32 CUDA-core GEMM), <0 on error.
-static inline int tc_linear_fwd(const float* X, const float* W, const float* bias, float* Z, int64_t M, int K, int N,
-                                int jet_cols, int sm_count, cudaStream_t st) {
-  if (M < 1 || (N % 128) != 0) return TC_UNSUPPORTED;
-  static int use_ss = -1;
-  if (use_ss < 0) { const char* e = getenv("PINNK_TC_SS"); use_ss = (e && e[0] == '1') ? 1 : 0; }
-  if (K == 128 && !use_ss) return tc::launch_linear_rows_ts<false, tc::EPI_PLAIN, 1, 0, 0>(X, W, K, bias, Z, M, N, jet_cols, nullptr, nullptr, 1.f, sm_count, st);
-  if (K == 256) {      // two K halves, the second accumulates onto the first and adds the bias
-    int rc = tc::launch_linear_rows_ts<false, tc::EPI_PLAIN, 1, 0, 0>(X, W, K, nullptr, Z, M, N, jet_cols, nullptr, nullptr, 1.f, sm_count, st, K, 0);
-    if (rc) return rc;
-    return tc::launch_linear_rows_ts<false, tc::EPI_PLAIN, 1, 0, 0>(X + 128, W + 128, K, bias, Z, M, N, jet_cols, nullptr, nullptr, 1.f, sm_count, st, K, 1);
-  }
-  if (K == 128) return tc::launch_linear_rows<128, 32, 3, 3, 8, 3, false>(X, W, K, bias, Z, M, N, jet_cols, sm_count, st);
-  if (K == 64) return tc::launch_linear_rows<64, 64, 4, 2, 8, 2, false>(X, W, K, bias, Z, M, N, jet_cols, sm_count, st);
-  return TC_UNSUPPORTED;
-}
-// dX[M,in] = dZ[M,out] W[out,in]   (W row-major [out,in])
-static inline int tc_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t M, int in_dim, int out_dim,
-                                  int sm_count, cudaStream_t st) {
-  if (M < 1 || (in_dim % 128) != 0) return TC_UNSUPPORTED;
-  static int use_ss = -1;
-  if (use_ss < 0) { const char* e = getenv("PINNK_TC_SS"); use_ss = (e && e[0] == '1') ? 1 : 0; }
-  if (out_dim == 128 && !use_ss) return tc::launch_linear_rows_ts<true, tc::EPI_PLAIN, 1, 0, 0>(dZ, W, in_dim, nullptr, dX, M, in_dim, 1, nullptr, nullptr, 1.f, sm_count, st);
-  if (out_dim == 256) {
-    int rc = tc::launch_linear_rows_ts<true, tc::EPI_PLAIN, 1, 0, 0>(dZ, W, in_dim, nullptr, dX, M, in_dim, 1, nullptr, nullptr, 1.f, sm_count, st, out_dim, 0);
-    if (rc) return rc;
-    return tc::launch_linear_rows_ts<true, tc::EPI_PLAIN, 1, 0, 0>(dZ + 128, W + (int64_t)128 * in_dim, in_dim, nullptr, dX, M, in_dim, 1, nullptr, nullptr, 1.f, sm_count, st, out_dim, 1);
-  }
-  if (out_dim == 128) return tc::launch_linear_rows<128, 32, 3, 3, 8, 3, true>(dZ, W, in_dim, nullptr, dX, M, in_dim, 1, sm_count, st);
-  return TC_UNSUPPORTED;
-}
+#if defined(PINNK_TC_TU_FWD) || defined(PINNK_TC_TU_BWD)
 // jet layouts the fused epilogues are instantiated for: (K0, K1) = orders of the (at most two) directions
 template <bool TRANS_W, int EPI, int ACT>
 static inline int tc_dispatch_jets(int k0, int k1, const float* X, const float* W, int ldw, const float* bias, float* Y,
@@ -1109,8 +1097,28 @@ static inline int tc_dispatch_jets(int k0, int k1, const float* X, const float* 
 static inline bool tc_jets_supported(int k0, int k1) {
   return (k0 == 0 && k1 == 0) || (k0 == 1 && k1 == 0) || (k0 == 2 && k1 == 1) || (k0 == 3 && k1 == 0);
 }
+#endif
+
+#ifdef PINNK_TC_TU_FWD
+// Z[M,N] = X[M,K] W[N,K]^T (+ bias on value-column rows).  Returns 0 when launched,
+// TC_UNSUPPORTED when the shape is not covered (caller uses the exact-fp32 CUDA-core GEMM), <0 on error.
+int tc_linear_fwd(const float* X, const float* W, const float* bias, float* Z, int64_t M, int K, int N,
+                                int jet_cols, int sm_count, cudaStream_t st) {
+  if (M < 1 || (N % 128) != 0) return TC_UNSUPPORTED;
+  static int use_ss = -1;
+  if (use_ss < 0) { const char* e = getenv("PINNK_TC_SS"); use_ss = (e && e[0] == '1') ? 1 : 0; }
+  if (K == 128 && !use_ss) return tc::launch_linear_rows_ts<false, tc::EPI_PLAIN, 1, 0, 0>(X, W, K, bias, Z, M, N, jet_cols, nullptr, nullptr, 1.f, sm_count, st);
+  if (K == 256) {      // two K halves, the second accumulates onto the first and adds the bias
+    int rc = tc::launch_linear_rows_ts<false, tc::EPI_PLAIN, 1, 0, 0>(X, W, K, nullptr, Z, M, N, jet_cols, nullptr, nullptr, 1.f, sm_count, st, K, 0);
+    if (rc) return rc;
+    return tc::launch_linear_rows_ts<false, tc::EPI_PLAIN, 1, 0, 0>(X + 128, W + 128, K, bias, Z, M, N, jet_cols, nullptr, nullptr, 1.f, sm_count, st, K, 1);
+  }
+  if (K == 128) return tc::launch_linear_rows<128, 32, 3, 3, 8, 3, false>(X, W, K, bias, Z, M, N, jet_cols, sm_count, st);
+  if (K == 64) return tc::launch_linear_rows<64, 64, 4, 2, 8, 2, false>(X, W, K, bias, Z, M, N, jet_cols, sm_count, st);
+  return TC_UNSUPPORTED;
+}
 // Forward Linear + activation jets in one kernel: Z = X W^T + b (stash), Yact = act(Z).  act: 1 tanh, 2 sin(omega z).
-static inline int tc_linear_act_fwd(const float* X, const float* W, const float* bias, float* Z, float* Yact, int64_t M, int K,
+int tc_linear_act_fwd(const float* X, const float* W, const float* bias, float* Z, float* Yact, int64_t M, int K,
                                     int N, int k0, int k1, int act, float omega, int sm_count, cudaStream_t st) {
   if (M < 1 || (K != 128 && K != 256) || (N % 128) != 0 || !tc_jets_supported(k0, k1) || (act != 1 && act != 2)) return TC_UNSUPPORTED;
   int accum = 0;
@@ -1123,8 +1131,26 @@ static inline int tc_linear_act_fwd(const float* X, const float* W, const float*
   if (act == 1) return tc_dispatch_jets<false, tc::EPI_ACT, 1>(k0, k1, X, W, K, bias, Z, M, N, nullptr, Yact, 1.f, sm_count, st, K, accum);
   return tc_dispatch_jets<false, tc::EPI_ACT, 2>(k0, k1, X, W, K, bias, Z, M, N, nullptr, Yact, omega, sm_count, st, K, accum);
 }
+#endif
+
+#ifdef PINNK_TC_TU_BWD
+// dX[M,in] = dZ[M,out] W[out,in]   (W row-major [out,in])
+int tc_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t M, int in_dim, int out_dim,
+                                  int sm_count, cudaStream_t st) {
+  if (M < 1 || (in_dim % 128) != 0) return TC_UNSUPPORTED;
+  static int use_ss = -1;
+  if (use_ss < 0) { const char* e = getenv("PINNK_TC_SS"); use_ss = (e && e[0] == '1') ? 1 : 0; }
+  if (out_dim == 128 && !use_ss) return tc::launch_linear_rows_ts<true, tc::EPI_PLAIN, 1, 0, 0>(dZ, W, in_dim, nullptr, dX, M, in_dim, 1, nullptr, nullptr, 1.f, sm_count, st);
+  if (out_dim == 256) {
+    int rc = tc::launch_linear_rows_ts<true, tc::EPI_PLAIN, 1, 0, 0>(dZ, W, in_dim, nullptr, dX, M, in_dim, 1, nullptr, nullptr, 1.f, sm_count, st, out_dim, 0);
+    if (rc) return rc;
+    return tc::launch_linear_rows_ts<true, tc::EPI_PLAIN, 1, 0, 0>(dZ + 128, W + (int64_t)128 * in_dim, in_dim, nullptr, dX, M, in_dim, 1, nullptr, nullptr, 1.f, sm_count, st, out_dim, 1);
+  }
+  if (out_dim == 128) return tc::launch_linear_rows<128, 32, 3, 3, 8, 3, true>(dZ, W, in_dim, nullptr, dX, M, in_dim, 1, sm_count, st);
+  return TC_UNSUPPORTED;
+}
 // dgrad + activation adjoint in one kernel: dZprev = act'(Zprev)^T (dZ W)
-static inline int tc_linear_dgrad_actbwd(const float* dZ, const float* W, const float* Zprev, float* dZprev, int64_t M,
+int tc_linear_dgrad_actbwd(const float* dZ, const float* W, const float* Zprev, float* dZprev, int64_t M,
                                          int in_dim, int out_dim, int k0, int k1, int act, float omega, int sm_count,
                                          cudaStream_t st) {
   if (M < 1 || (out_dim != 128 && out_dim != 256) || (in_dim % 128) != 0 || !tc_jets_supported(k0, k1) || (act != 1 && act != 2))
@@ -1138,10 +1164,14 @@ static inline int tc_linear_dgrad_actbwd(const float* dZ, const float* W, const 
   if (act == 1) return tc_dispatch_jets<true, tc::EPI_ACTBWD, 1>(k0, k1, dZ, W, in_dim, nullptr, dZprev, M, in_dim, Zprev, nullptr, 1.f, sm_count, st, out_dim, accum);
   return tc_dispatch_jets<true, tc::EPI_ACTBWD, 2>(k0, k1, dZ, W, in_dim, nullptr, dZprev, M, in_dim, Zprev, nullptr, omega, sm_count, st, out_dim, accum);
 }
+#endif
+
+#ifdef PINNK_TC_TU_WGRAD
 // dW[out,in] += dZ[M,out]^T X[M,in] ;  db[out] += sum over value-column rows of dZ
-static inline int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
+int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
                                   int jet_cols, int sm_count, cudaStream_t st) {
   if (M < 1 || (in_dim % 128) != 0 || (out_dim % 128) != 0 || dW == nullptr) return TC_UNSUPPORTED;
   return tc::launch_wgrad<32, 3, 2, 16, 4>(dZ, X, dW, db, M, in_dim, out_dim, jet_cols, sm_count, st);
 }
+#endif
 }  // namespace pinnk

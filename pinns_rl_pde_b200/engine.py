@@ -6,6 +6,7 @@ CUDA stream; all arithmetic of the path happens inside libpinnk.so.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -20,7 +21,7 @@ Direction = Tuple[Tuple[float, ...], int]
 
 # upper bound for the per-engine workspace; the chunk size is derived from it
 MAX_WORKSPACE_BYTES = 24 << 30
-MAX_CHUNK_POINTS = 1 << 17
+MAX_CHUNK_POINTS = int(os.environ.get("PINNK_MAX_CHUNK_POINTS", 1 << 17))
 
 
 @dataclass
