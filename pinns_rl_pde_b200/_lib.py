@@ -42,7 +42,7 @@ EXPORTS = ["pinnk_plan_create", "pinnk_plan_destroy", "pinnk_plan_workspace_byte
            "pinnk_plan_grad_floats", "pinnk_jets_forward", "pinnk_jets_vjp", "pinnk_loss_step", "pinnk_score",
            "pinnk_last_error", "pinnk_abi_version", "pinnk_launch_count", "pinnk_prof_enable", "pinnk_prof_classes",
            "pinnk_prof_class_name", "pinnk_prof_collect", "pinnk_debug_linear_fwd",
-           "pinnk_debug_linear_dgrad", "pinnk_debug_linear_wgrad", "pinnk_adam_step"]
+           "pinnk_debug_linear_dgrad", "pinnk_debug_linear_wgrad", "pinnk_adam_step", "pinnk_debug_stage_timers"]
 
 _lib = None
 
@@ -102,6 +102,8 @@ def load():
     lib.pinnk_debug_linear_dgrad.restype = C.c_int
     lib.pinnk_debug_linear_wgrad.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]
     lib.pinnk_debug_linear_wgrad.restype = C.c_int
+    lib.pinnk_debug_stage_timers.argtypes = [i32, C.POINTER(C.c_uint64), i32]
+    lib.pinnk_debug_stage_timers.restype = C.c_int
     if lib.pinnk_abi_version() != ABI_VERSION:
         raise PinnkError(f"libpinnk.so ABI {lib.pinnk_abi_version()} != binding {ABI_VERSION}: rebuild")
     _lib = lib
@@ -166,3 +168,12 @@ def debug_linear_wgrad(dZ, X, jet_cols: int, mode: int):
     check(lib.pinnk_debug_linear_wgrad(dZ.data_ptr(), X.data_ptr(), dW.data_ptr(), db.data_ptr(), M, K, N, jet_cols, mode,
                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pinnk_debug_linear_wgrad")
     return dW, db
+
+
+def stage_timers(which: int, reset: bool = True):
+    """Per-role barrier wait cycles of the rows kernels (zeros unless built with -DPINNK_STAGE_TIMERS)."""
+    out = (C.c_uint64 * 16)()
+    rc = load().pinnk_debug_stage_timers(which, out, 1 if reset else 0)
+    names = ["tma:raw_empty", "cvt:raw_full", "cvt:empty", "cvt:work", "mma:tempty", "mma:full", "mma:issue",
+             "epi:tfull", "epi:work", "tiles", "total"]
+    return rc, {n: int(out[i]) for i, n in enumerate(names)}

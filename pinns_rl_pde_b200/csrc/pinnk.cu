@@ -797,6 +797,13 @@ extern "C" int pinnk_debug_linear_wgrad(const float* dZ, const float* X, float* 
   return 0;
 }
 
+// ---- builder tool: per-role barrier wait cycles of the rows kernels (which = 0 forward TU, 1 backward TU)
+extern "C" int pinnk_debug_stage_timers(int32_t which, uint64_t* out16, int32_t reset) {
+  if (!out16) return fail(PINNK_E_INVALID, "debug_stage_timers: null output");
+  cudaDeviceSynchronize();
+  return which == 0 ? tc_stage_timers_fwd((unsigned long long*)out16, reset) : tc_stage_timers_bwd((unsigned long long*)out16, reset);
+}
+
 // ---- fused optimizer tail: clip_grad_norm_ + Adam(L2) on the flat gradient (trainer.py:690-694,292-297)
 extern "C" int pinnk_adam_step(float* const* params, const int64_t* numels, int32_t n_tensors, const float* flat_grad,
                                float* exp_avg, float* exp_avg_sq, double* scratch, int64_t step, float lr, float beta1,

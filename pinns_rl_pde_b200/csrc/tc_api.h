@@ -25,4 +25,7 @@ int tc_linear_dgrad_actbwd(const float* dZ, const float* W, const float* Zprev, 
 // dW[out,in] += dZ[M,out]^T X[M,in] ;  db[out] += sum over value-column rows of dZ
 int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
                     int jet_cols, int sm_count, cudaStream_t st);
+// stage timers of the rows kernels (zeros unless built with -DPINNK_STAGE_TIMERS); 0 ok, 1 not compiled in
+int tc_stage_timers_fwd(unsigned long long* out16, int reset);
+int tc_stage_timers_bwd(unsigned long long* out16, int reset);
 }  // namespace pinnk

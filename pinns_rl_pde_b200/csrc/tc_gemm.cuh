@@ -56,11 +56,39 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity), "r"(100000u)
+        : "r"(addr), "r"(parity), "r"(20000u)
         : "memory");
     if (done) return;
   }
   __trap();
+}
+// Wait used by the (many) epilogue / flush warps: they have slack (double-buffered accumulators), so after a failed
+// probe they sleep instead of re-polling -- polling warps were stealing ~30 % of the issue slots from the convert warps
+// that share their scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    __nanosleep(64);
+  }
+  __trap();
+}
+// One lane of a converged warp (elect.sync).  The single-thread issuers (tcgen05.mma / commit, TMA) branch on this and
+// not on `lane == 0`: under a lane-id branch the compiler treats the region as divergent and wraps EVERY uniform-datapath
+// instruction (UTCHMMA, UBLKCP ...) in an ELECT / BRA.U.ANY serialisation loop, ~50 cycles per MMA -- the MMA issue, not
+// the tensor pipe, was what bounded the rows kernels (2600 issue cycles per 64-row tile against 1536 of tensor time).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -348,7 +376,7 @@ linear_rows_kernel(const float* __restrict__ X, const float* __restrict__ W, int
     }
   } else {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_tf32(128, TN);
       // descriptors differ only in the 14-bit start-address field (16-byte units): build the constant part once
       const uint64_t dconst = make_desc_k_sw128(0);
@@ -473,6 +501,18 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
+// Optional stage timers (build with -DPINNK_STAGE_TIMERS): block 0 accumulates, per role, the cycles spent waiting on
+// each pipeline barrier; read back with pinnk_debug_stage_timers().  Slots: 0 tma:raw_empty  1 cvt:raw_full  2 cvt:empty
+// 3 cvt:work  4 mma:tempty  5 mma:full  6 mma:issue  7 epi:tfull  8 epi:work  9 tiles  10 total cycles of block 0
+#ifdef PINNK_STAGE_TIMERS
+static __device__ unsigned long long g_stage_timers[16];
+#define PK_T0() const long long _t0 = clock64()
+#define PK_TACC(var) var += clock64() - _t0
+#else
+#define PK_T0()
+#define PK_TACC(var)
+#endif
+
 // EPI selects the epilogue:
 //   EPI_PLAIN   Y = acc (+ bias on value rows)
 //   EPI_ACT     forward Linear + activation jets: Y = Z = acc + bias (the stash the reverse pass needs) and
@@ -563,13 +603,14 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
 
   if (warp == TMAW) {
     // ===================== TMA producer: raw 64-row tiles (contiguous 32 KB), one elected thread =====================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t rb = smem_u32(raw_st);
+      long long t_a = 0; (void)t_a;
       int it = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int s = it % RS;
         const uint32_t ph = (uint32_t)(it / RS) & 1u;
-        mbar_wait(&raw_empty[s], ph ^ 1u);
+        { PK_T0(); mbar_wait(&raw_empty[s], ph ^ 1u); PK_TACC(t_a); }
         const int64_t r0 = tile * TN;
         const uint32_t nrows = (M - r0 >= TN) ? TN : (uint32_t)(M - r0);
         mbar_arrive_expect_tx(&raw_full[s], nrows * (uint32_t)(K * 4));
@@ -577,19 +618,24 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
         if (ldx == K) tma_bulk_g2s(dst, X + r0 * K, nrows * (uint32_t)(K * 4), &raw_full[s]);
         else for (uint32_t r = 0; r < nrows; ++r) tma_bulk_g2s(dst + r * (K * 4), X + (r0 + r) * ldx, (uint32_t)(K * 4), &raw_full[s]);
       }
+#ifdef PINNK_STAGE_TIMERS
+      if (blockIdx.x == 0 && blockIdx.y == 0) atomicAdd(&g_stage_timers[0], (unsigned long long)t_a);
+#endif
     }
     __syncwarp();
   } else if (warp < NLW) {
     // ===================== convert warps: raw tile -> hi/lo operand tile (lane = 16-byte chunk of a row) ==============
     constexpr int RPW = TN / NLW;
     const uint32_t x_base = smem_u32(x_st), rb = smem_u32(raw_st);
+    long long t_a = 0, t_b = 0, t_c = 0; (void)t_a; (void)t_b; (void)t_c;
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int rs = it % RS, s = it % STAGES;
       const uint32_t rph = (uint32_t)(it / RS) & 1u, ph = (uint32_t)(it / STAGES) & 1u;
       const int64_t r0 = tile * TN;
       const int nrows = (M - r0 >= TN) ? TN : (int)(M - r0);
-      mbar_wait(&raw_full[rs], rph);
+      { PK_T0(); mbar_wait(&raw_full[rs], rph); PK_TACC(t_a); }
+      PK_T0();
       const uint32_t raw = rb + (uint32_t)rs * RAW_BYTES;
       float4 v[RPW];
 #pragma unroll
@@ -599,7 +645,9 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&raw_empty[rs]);                 // raw data is in registers: slot may be refilled
-      mbar_wait(&empty[s], ph ^ 1u);
+      PK_TACC(t_c);
+      { PK_T0(); mbar_wait(&empty[s], ph ^ 1u); PK_TACC(t_b); }
+      const long long _t1 = clock64(); (void)_t1;
       const uint32_t xh = x_base + (uint32_t)s * 2 * X_BYTES, xl = xh + X_BYTES;
 #pragma unroll
       for (int i = 0; i < RPW; ++i) {
@@ -613,7 +661,16 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
+#ifdef PINNK_STAGE_TIMERS
+      t_c += clock64() - _t1;
+#endif
     }
+#ifdef PINNK_STAGE_TIMERS
+    if (blockIdx.x == 0 && blockIdx.y == 0 && warp == 0 && lane == 0) {
+      atomicAdd(&g_stage_timers[1], (unsigned long long)t_a); atomicAdd(&g_stage_timers[2], (unsigned long long)t_b);
+      atomicAdd(&g_stage_timers[3], (unsigned long long)t_c);
+    }
+#endif
   } else if (warp < MMAW) {
     // ===================== epilogue: warp (q, h) owns lanes 32q.. and tile rows ECOLS*h .. ECOLS*h + ECOLS-1 ==========
     const int e = warp - EPI0;
@@ -624,6 +681,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
     const uint32_t lane_acc = tmem_base + ((uint32_t)(q * 32) << 16) + COL_ACC + (uint32_t)(h * ECOLS);
     // One tile of this warp.  FULL: all ECOLS rows exist, so no access is predicated and (with LDYC) every row address
     // is the tile base plus an immediate.
+    long long t_ea = 0, t_eb = 0; (void)t_ea; (void)t_eb;
     auto run_tile = [&](auto full_tag, const int b, const uint32_t ph, const int64_t r0, const int nrows) {
       constexpr bool FULL = decltype(full_tag)::value;
       uint32_t vmask = 0;
@@ -648,7 +706,8 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
 #pragma unroll
         for (int j = 0; j < ECOLS; ++j) part[j] = (FULL || j < nrows) ? yp[j * ldy] : 0.f;
       }
-      mbar_wait(&tfull[b], ph);
+      { PK_T0(); mbar_wait_relaxed(&tfull[b], ph); PK_TACC(t_ea); }
+      PK_T0();
       tc_fence_after();
       const uint32_t tb = lane_acc + (uint32_t)(b * 2 * TN);
       uint32_t pm[ECOLS], pc[ECOLS];
@@ -746,6 +805,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
           }
         }
       }
+      PK_TACC(t_eb);
     };
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -755,18 +815,26 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
       if (M - r0 >= ECOLS) run_tile(std::true_type(), b, ph, r0, ECOLS);
       else run_tile(std::false_type(), b, ph, r0, (int)(M - r0 > 0 ? M - r0 : 0));
     }
+#ifdef PINNK_STAGE_TIMERS
+    if (blockIdx.x == 0 && blockIdx.y == 0 && e == 0 && lane == 0) {
+      atomicAdd(&g_stage_timers[7], (unsigned long long)t_ea); atomicAdd(&g_stage_timers[8], (unsigned long long)t_eb);
+    }
+#endif
   } else if (warp == MMAW) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_tf32(128, TN);
       const uint64_t dconst = make_desc_k_sw128(0);
       const uint32_t x_base = smem_u32(x_st) >> 4;
+      long long t_a = 0, t_b = 0, t_c = 0, n_t = 0; const long long t_start = clock64();
+      (void)t_a; (void)t_b; (void)t_c; (void)n_t; (void)t_start;
       int it = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int s = it % STAGES, b = it % ACC;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u, bph = (uint32_t)(it / ACC) & 1u;
-        mbar_wait(&tempty[b], bph ^ 1u);
-        mbar_wait(&full[s], ph);
+        { PK_T0(); mbar_wait(&tempty[b], bph ^ 1u); PK_TACC(t_a); }
+        { PK_T0(); mbar_wait(&full[s], ph); PK_TACC(t_b); }
+        PK_T0();
         tc_fence_after();
         const uint32_t xh = x_base + (uint32_t)s * (2 * X_BYTES >> 4), xl = xh + (X_BYTES >> 4);
         const uint32_t d_main = tmem_base + COL_ACC + (uint32_t)(b * 2 * TN), d_corr = d_main + TN;
@@ -781,7 +849,16 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
         }
         umma_commit(&empty[s]);
         umma_commit(&tfull[b]);
+        PK_TACC(t_c);
+        ++n_t;
       }
+#ifdef PINNK_STAGE_TIMERS
+      if (blockIdx.x == 0 && blockIdx.y == 0) {
+        atomicAdd(&g_stage_timers[4], (unsigned long long)t_a); atomicAdd(&g_stage_timers[5], (unsigned long long)t_b);
+        atomicAdd(&g_stage_timers[6], (unsigned long long)t_c); atomicAdd(&g_stage_timers[9], (unsigned long long)n_t);
+        atomicAdd(&g_stage_timers[10], (unsigned long long)(clock64() - t_start));
+      }
+#endif
     }
     __syncwarp();
   }
@@ -799,7 +876,7 @@ static int launch_linear_rows_ts_inst(const float* X, const float* W, int ldw, c
                                       int ldx) {
   constexpr size_t smem = 1024 + (size_t)2 * 2 * 64 * 128 * 4 + (size_t)3 * 64 * 128 * 4 + (2 * 2 + 2 * 2 + 2 * 3) * 8 + 16;
   static_assert(smem <= 232448, "shared memory budget (227 KB per CTA)");
-  constexpr int NLW = (EPI == EPI_ACTBWD) ? 4 : 8, ECOLS = (EPI == EPI_ACTBWD) ? 16 : 32;
+  constexpr int NLW = 8, ECOLS = (EPI == EPI_PLAIN) ? 32 : 16;
   const int64_t ntiles = (M + 63) / 64;
   const int per_y = n_cols / 128;
   int gx = sm_count / per_y;
@@ -887,7 +964,7 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
 
   if (warp == TMAW) {
     // ===================== TMA producer: raw row tiles, one elected thread =====================
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t rb = smem_u32(raw_base);
       int it = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
@@ -972,7 +1049,7 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
       for (int64_t seg = 0; seg < my_segs; ++seg) {
         const int b = (int)(seg & 1);
-        mbar_wait(&tfull[b], (uint32_t)(seg >> 1) & 1u);
+        mbar_wait_relaxed(&tfull[b], (uint32_t)(seg >> 1) & 1u);
         tc_fence_after();
 #pragma unroll 1
         for (int c0 = 0; c0 < 128; c0 += 32) {
@@ -1011,7 +1088,7 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
     }
   } else if (warp == MMAW) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && my_segs > 0) {
+    if (my_segs > 0 && elect_one()) {
       constexpr uint32_t idesc = make_idesc_tf32(128, 128);
       const uint64_t dconst = make_desc_k_sw128(0);
       const uint32_t sbase = smem_u32(op_base) >> 4;
@@ -1100,6 +1177,17 @@ static inline bool tc_jets_supported(int k0, int k1) {
 #endif
 
 #ifdef PINNK_TC_TU_FWD
+int tc_stage_timers_fwd(unsigned long long* out16, int reset) {
+#ifdef PINNK_STAGE_TIMERS
+  if (cudaMemcpyFromSymbol(out16, tc::g_stage_timers, 16 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(tc::g_stage_timers, z, sizeof(z)); }
+  return 0;
+#else
+  for (int i = 0; i < 16; ++i) out16[i] = 0;
+  (void)reset;
+  return 1;
+#endif
+}
 // Z[M,N] = X[M,K] W[N,K]^T (+ bias on value-column rows).  Returns 0 when launched,
 // TC_UNSUPPORTED when the shape is not covered (caller uses the exact-fp32 CUDA-core GEMM), <0 on error.
 int tc_linear_fwd(const float* X, const float* W, const float* bias, float* Z, int64_t M, int K, int N,
@@ -1134,6 +1222,17 @@ int tc_linear_act_fwd(const float* X, const float* W, const float* bias, float* 
 #endif
 
 #ifdef PINNK_TC_TU_BWD
+int tc_stage_timers_bwd(unsigned long long* out16, int reset) {
+#ifdef PINNK_STAGE_TIMERS
+  if (cudaMemcpyFromSymbol(out16, tc::g_stage_timers, 16 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(tc::g_stage_timers, z, sizeof(z)); }
+  return 0;
+#else
+  for (int i = 0; i < 16; ++i) out16[i] = 0;
+  (void)reset;
+  return 1;
+#endif
+}
 // dX[M,in] = dZ[M,out] W[out,in]   (W row-major [out,in])
 int tc_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t M, int in_dim, int out_dim,
                                   int sm_count, cudaStream_t st) {
