@@ -166,7 +166,7 @@ int pinnk_debug_linear_wgrad(const float* dZ, const float* X, float* dW, float* 
                              int32_t jet_cols, int32_t mode, void* stream);
 
 /* Builder tool: cycles block 0 of the tcgen05 rows kernels spent waiting on each pipeline barrier, accumulated since the
- * last reset (which: 0 = forward kernels, 1 = reverse kernels; out16: 16 counters, see csrc/tc_gemm.cuh).
+ * last reset (which: 0 = forward rows kernels, 1 = reverse rows kernels, 2 = wgrad; out16: 16 counters, see csrc/tc_gemm.cuh).
  * Returns 1 and zeros unless the library was built with -DPINNK_STAGE_TIMERS. */
 int pinnk_debug_stage_timers(int32_t which, uint64_t* out16, int32_t reset);
 

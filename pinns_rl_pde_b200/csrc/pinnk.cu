@@ -21,6 +21,7 @@
 #include "../../include/pinnk.h"
 #include "jet_math.cuh"
 #include "kernels_ew.cuh"
+#include "kernels_edge.cuh"
 #include "sgemm.cuh"
 #include "tc_api.h"
 
@@ -397,6 +398,20 @@ static bool jet_orders(const JetSpec& js, int& k0, int& k1) {
   return true;
 }
 
+// compile-time jet layouts of the specialised edge-layer kernels (kernels_edge.cuh)
+template <typename F>
+static bool dispatch_edge_jets(int k0, int k1, F&& f) {
+#define PK_EDGE_CASE(A, B) if (k0 == A && k1 == B) { f(std::integral_constant<int, A>(), std::integral_constant<int, B>()); return true; }
+  PK_EDGE_CASE(0, 0) PK_EDGE_CASE(1, 0) PK_EDGE_CASE(1, 1) PK_EDGE_CASE(2, 1) PK_EDGE_CASE(3, 1) PK_EDGE_CASE(4, 1)
+#undef PK_EDGE_CASE
+  return false;
+}
+static bool edge_fast_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PINNK_DISABLE_EDGE_FAST"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1;
+}
+
 // forward jets of one chunk; fills the stash and U[n, C]
 // keep_stash = false (forward-only callers: jets_forward, scoring): fused Linear+activation kernels skip the
 // pre-activation store, which nothing reads without a reverse pass
@@ -418,6 +433,18 @@ static int forward_chunk(const ChunkCtx& c, bool keep_stash = true) {
           ProfScope ps(PC_FIRST_FWD, c.st);
           const PinnkOp& a = pl->ops[1].op;
           const unsigned blocks = blocks_for(c.n * o.out_dim, threads);
+          int ek0 = 0, ek1 = 0;
+          if (edge_fast_enabled() && (o.out_dim % 128) == 0 && jet_orders(js, ek0, ek1)) {
+            constexpr int PPT = 2;
+            dim3 grid((unsigned)(o.out_dim / 128), (unsigned)std::min<int64_t>((c.n + PPT - 1) / PPT, 16 * (int64_t)pl->sm_count));
+            const bool tanh_act = a.act == PINNK_ACT_TANH;
+            const bool ok = dispatch_edge_jets(ek0, ek1, [&](auto ka, auto kb) {
+              constexpr int KA = decltype(ka)::value, KB = decltype(kb)::value;
+              if (tanh_act) first_act_fwd_fast_kernel<1, KA, KB, PPT><<<grid, 128, 0, c.st>>>(c.x, c.t, c.n, W, b, o.out_dim, js, c.stash(1), 1.f);
+              else first_act_fwd_fast_kernel<2, KA, KB, PPT><<<grid, 128, 0, c.st>>>(c.x, c.t, c.n, W, b, o.out_dim, js, c.stash(1), a.scale);
+            });
+            if (ok) { PK_LAUNCH_OK(); ++i; break; }
+          }
           if (a.act == PINNK_ACT_TANH)
             first_act_fwd_kernel<1, MAXK><<<blocks, threads, 0, c.st>>>(c.x, c.t, c.n, W, b, o.out_dim, js, nullptr, c.stash(1), 1.f);
           else
@@ -432,6 +459,12 @@ static int forward_chunk(const ChunkCtx& c, bool keep_stash = true) {
         } else if (i == n_ops - 1) {
           ProfScope ps(PC_LAST_FWD, c.st);
           const int64_t rows = c.n * js.ncols;
+          if (edge_fast_enabled() && o.in_dim == 128) {
+            constexpr int RPW = 4;
+            const int64_t warps = (rows + RPW - 1) / RPW;
+            const unsigned blocks = (unsigned)std::min<int64_t>((warps + 7) / 8, 8 * (int64_t)pl->sm_count);
+            last_linear_fwd_w128_kernel<RPW><<<blocks, 256, 0, c.st>>>(in, rows, js.ncols, W, b, c.U());
+          } else
           last_linear_fwd_kernel<<<blocks_for(rows * 32, threads), threads, 0, c.st>>>(in, rows, o.in_dim, js.ncols, W, b, c.U());
           PK_LAUNCH_OK();
         } else {
@@ -505,6 +538,18 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad) {
           ProfScope ps(PC_LAST_BWD, c.st);
           const OpRt& pa = pl->ops[n_ops - 2];
           dim3 grid(blocks_for(o.in_dim, 128), (unsigned)std::min<int64_t>(c.n, 32 * (int64_t)pl->sm_count));
+          int ek0 = 0, ek1 = 0;
+          if (edge_fast_enabled() && (o.in_dim % 128) == 0 && jet_orders(js, ek0, ek1)) {
+            constexpr int PPT = 2;
+            dim3 g2((unsigned)(o.in_dim / 128), (unsigned)std::min<int64_t>((c.n + PPT - 1) / PPT, 16 * (int64_t)pl->sm_count));
+            const bool tanh_act = pa.op.act == PINNK_ACT_TANH;
+            const bool ok = dispatch_edge_jets(ek0, ek1, [&](auto ka, auto kb) {
+              constexpr int KA = decltype(ka)::value, KB = decltype(kb)::value;
+              if (tanh_act) last_act_bwd_fast_kernel<1, KA, KB, PPT><<<g2, 128, 0, c.st>>>(c.stash(pa.in_op), c.Ub(), c.n, o.in_dim, W, c.adj(cur), G(o.gw_offset), G(o.gb_offset), 1.f);
+              else last_act_bwd_fast_kernel<2, KA, KB, PPT><<<g2, 128, 0, c.st>>>(c.stash(pa.in_op), c.Ub(), c.n, o.in_dim, W, c.adj(cur), G(o.gw_offset), G(o.gb_offset), pa.op.scale);
+            });
+            if (ok) { PK_LAUNCH_OK(); --i; break; }
+          }
           if (pa.op.act == PINNK_ACT_TANH)
             last_act_bwd_kernel<1, MAXK><<<grid, 128, 0, c.st>>>(c.stash(pa.in_op), c.Ub(), c.n, o.in_dim, js, W, c.adj(cur),
                                                                   G(o.gw_offset), G(o.gb_offset), 1.f);
@@ -558,6 +603,18 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad) {
           const float* W0 = c.params[l0.w_index];
           const float* b0 = (l0.b_index >= 0) ? c.params[l0.b_index] : nullptr;
           dim3 grid(blocks_for(l0.out_dim, 128), (unsigned)std::min<int64_t>(c.n, 32 * (int64_t)pl->sm_count));
+          int ek0 = 0, ek1 = 0;
+          if (edge_fast_enabled() && (l0.out_dim % 128) == 0 && jet_orders(js, ek0, ek1)) {
+            constexpr int PPT = 2;
+            dim3 g2((unsigned)(l0.out_dim / 128), (unsigned)std::min<int64_t>((c.n + PPT - 1) / PPT, 16 * (int64_t)pl->sm_count));
+            const bool tanh_act = o.act == PINNK_ACT_TANH;
+            const bool ok = dispatch_edge_jets(ek0, ek1, [&](auto ka, auto kb) {
+              constexpr int KA = decltype(ka)::value, KB = decltype(kb)::value;
+              if (tanh_act) first_act_bwd_fast_kernel<1, KA, KB, PPT><<<g2, 128, 0, c.st>>>(c.x, c.t, c.n, W0, b0, l0.out_dim, js, c.adj(cur), G(l0.gw_offset), G(l0.gb_offset), 1.f);
+              else first_act_bwd_fast_kernel<2, KA, KB, PPT><<<g2, 128, 0, c.st>>>(c.x, c.t, c.n, W0, b0, l0.out_dim, js, c.adj(cur), G(l0.gw_offset), G(l0.gb_offset), o.scale);
+            });
+            if (ok) { PK_LAUNCH_OK(); --i; break; }
+          }
           if (o.act == PINNK_ACT_TANH)
             first_act_bwd_kernel<1, MAXK><<<grid, 128, 0, c.st>>>(c.x, c.t, c.n, W0, b0, l0.out_dim, js, c.adj(cur),
                                                                    G(l0.gw_offset), G(l0.gb_offset), 1.f);
@@ -801,7 +858,9 @@ extern "C" int pinnk_debug_linear_wgrad(const float* dZ, const float* X, float* 
 extern "C" int pinnk_debug_stage_timers(int32_t which, uint64_t* out16, int32_t reset) {
   if (!out16) return fail(PINNK_E_INVALID, "debug_stage_timers: null output");
   cudaDeviceSynchronize();
-  return which == 0 ? tc_stage_timers_fwd((unsigned long long*)out16, reset) : tc_stage_timers_bwd((unsigned long long*)out16, reset);
+  if (which == 0) return tc_stage_timers_fwd((unsigned long long*)out16, reset);
+  if (which == 1) return tc_stage_timers_bwd((unsigned long long*)out16, reset);
+  return tc_stage_timers_wgrad((unsigned long long*)out16, reset);
 }
 
 // ---- fused optimizer tail: clip_grad_norm_ + Adam(L2) on the flat gradient (trainer.py:690-694,292-297)

@@ -28,4 +28,5 @@ int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64
 // stage timers of the rows kernels (zeros unless built with -DPINNK_STAGE_TIMERS); 0 ok, 1 not compiled in
 int tc_stage_timers_fwd(unsigned long long* out16, int reset);
 int tc_stage_timers_bwd(unsigned long long* out16, int reset);
+int tc_stage_timers_wgrad(unsigned long long* out16, int reset);
 }  // namespace pinnk

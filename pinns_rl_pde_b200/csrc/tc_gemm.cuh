@@ -828,6 +828,9 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
       const uint32_t x_base = smem_u32(x_st) >> 4;
       long long t_a = 0, t_b = 0, t_c = 0, n_t = 0; const long long t_start = clock64();
       (void)t_a; (void)t_b; (void)t_c; (void)n_t; (void)t_start;
+#ifdef PINNK_STAGE_TIMERS
+      unsigned long long g_start; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_start));
+#endif
       int it = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int s = it % STAGES, b = it % ACC;
@@ -857,6 +860,8 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
         atomicAdd(&g_stage_timers[4], (unsigned long long)t_a); atomicAdd(&g_stage_timers[5], (unsigned long long)t_b);
         atomicAdd(&g_stage_timers[6], (unsigned long long)t_c); atomicAdd(&g_stage_timers[9], (unsigned long long)n_t);
         atomicAdd(&g_stage_timers[10], (unsigned long long)(clock64() - t_start));
+        unsigned long long g_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
+        atomicAdd(&g_stage_timers[11], g_end - g_start);
       }
 #endif
     }
@@ -966,11 +971,12 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
     // ===================== TMA producer: raw row tiles, one elected thread =====================
     if (elect_one()) {
       const uint32_t rb = smem_u32(raw_base);
+      long long t_a = 0; (void)t_a;
       int it = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int s = it % RS;
         const uint32_t ph = (uint32_t)(it / RS) & 1u;
-        mbar_wait(&raw_empty[s], ph ^ 1u);
+        { PK_T0(); mbar_wait(&raw_empty[s], ph ^ 1u); PK_TACC(t_a); }
         const int64_t r0 = tile * TK;
         const int nrows = (M - r0 >= TK) ? TK : (int)(M - r0);
         const uint32_t dg = rb + (uint32_t)s * 2 * RAW_BYTES, dx = dg + RAW_BYTES;
@@ -980,6 +986,9 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
         if (ldx == 128) tma_bulk_g2s(dx, X + r0 * 128, (uint32_t)nrows * 512u, &raw_full[s]);
         else for (int r = 0; r < nrows; ++r) tma_bulk_g2s(dx + r * 512, X + (r0 + r) * ldx + i0, 512u, &raw_full[s]);
       }
+#ifdef PINNK_STAGE_TIMERS
+      if (blockIdx.x == 0 && blockIdx.y == 0) atomicAdd(&g_stage_timers[0], (unsigned long long)t_a);
+#endif
     }
     __syncwarp();
   } else if (warp < NCW) {
@@ -993,13 +1002,15 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
     float bsum[4] = {0.f, 0.f, 0.f, 0.f};
     const bool want_b = (db != nullptr) && (i0 == 0) && sel == 0;
     const uint32_t ob = smem_u32(op_base), rb = smem_u32(raw_base);
+    long long t_a = 0, t_b = 0, t_c = 0; (void)t_a; (void)t_b; (void)t_c;
     int it = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int rs = it % RS, os = it % OS;
       const uint32_t rph = (uint32_t)(it / RS) & 1u, oph = (uint32_t)(it / OS) & 1u;
       const int64_t r0 = tile * TK;
       const int nrows = (M - r0 >= TK) ? TK : (int)(M - r0);
-      mbar_wait(&raw_full[rs], rph);
+      { PK_T0(); mbar_wait(&raw_full[rs], rph); PK_TACC(t_a); }
+      PK_T0();
       const uint32_t raw = rb + (uint32_t)rs * 2 * RAW_BYTES + (uint32_t)sel * RAW_BYTES;
       float v[4][4];                                       // [row of the quad][feature e]
 #pragma unroll
@@ -1014,7 +1025,9 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&raw_empty[rs]);                 // raw data is in registers: slot may be refilled
-      mbar_wait(&empty[os], oph ^ 1u);
+      PK_TACC(t_c);
+      { PK_T0(); mbar_wait(&empty[os], oph ^ 1u); PK_TACC(t_b); }
+      const long long _t1 = clock64(); (void)_t1;
       const uint32_t hi_base = ob + (uint32_t)os * 4 * OP_BYTES + (uint32_t)sel * 2 * OP_BYTES, lo_base = hi_base + OP_BYTES;
       if (want_b) {
         uint32_t cj = (uint32_t)((uint32_t)(r0 + rq * 4) % (uint32_t)jet_cols);
@@ -1036,7 +1049,16 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[os]);
+#ifdef PINNK_STAGE_TIMERS
+      t_c += clock64() - _t1;
+#endif
     }
+#ifdef PINNK_STAGE_TIMERS
+    if (blockIdx.x == 0 && blockIdx.y == 0 && warp == 0 && lane == 0) {
+      atomicAdd(&g_stage_timers[1], (unsigned long long)t_a); atomicAdd(&g_stage_timers[2], (unsigned long long)t_b);
+      atomicAdd(&g_stage_timers[3], (unsigned long long)t_c);
+    }
+#endif
     if (want_b) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) atomicAdd(db + o0 + lane + 32 * e, bsum[e]);
@@ -1069,7 +1091,7 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
         if (lane == 0) mbar_arrive(&tempty[b]);
       }
       // all MMAs (including the corrections) are complete: the last tfull commit covered them
-      float* tr = reinterpret_cast<float*>(op_base);             // operand stages are idle now: [128][129] transpose buffer
+      float* tr = reinterpret_cast<float*>(op_base);             // operand stages are idle now: [128][132] transpose buffer
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32) {
         uint32_t p[32], a[32];
@@ -1077,13 +1099,24 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
         tmem_ld32_nowait(lane_base + COL_CORR + c0, a);
         tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) tr[f * 129 + c0 + j] = __uint_as_float(p[j]) + __uint_as_float(a[j]);
+        for (int j = 0; j < 32; ++j) tr[f * 132 + c0 + j] = __uint_as_float(p[j]) + __uint_as_float(a[j]);
       }
       named_bar_sync(1, kEpiThreads);
       const int t = threadIdx.x - EPI0 * 32;
-      for (int idx = t; idx < 128 * 128; idx += kEpiThreads) {
-        const int row = idx >> 7, col = idx & 127;
-        atomicAdd(dW + (int64_t)(o0 + row) * lddw + i0 + col, tr[row * 129 + col]);
+      float* const dw0 = dW + (int64_t)o0 * lddw + i0;
+      if (((reinterpret_cast<uintptr_t>(dw0) & 15) == 0) && (lddw & 3) == 0) {
+        // 16-byte vector reductions: a quarter of the atomic operations (all CTAs add into the same 128 x 128 block)
+        for (int idx = t; idx < 128 * 32; idx += kEpiThreads) {
+          const int row = idx >> 5, c4 = (idx & 31) * 4;
+          const float4 v = *reinterpret_cast<const float4*>(tr + row * 132 + c4);
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dw0 + (int64_t)row * lddw + c4), "f"(v.x), "f"(v.y),
+                       "f"(v.z), "f"(v.w) : "memory");
+        }
+      } else {
+        for (int idx = t; idx < 128 * 128; idx += kEpiThreads) {
+          const int row = idx >> 7, col = idx & 127;
+          atomicAdd(dw0 + (int64_t)row * lddw + col, tr[row * 132 + col]);
+        }
       }
     }
   } else if (warp == MMAW) {
@@ -1092,6 +1125,11 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
       constexpr uint32_t idesc = make_idesc_tf32(128, 128);
       const uint64_t dconst = make_desc_k_sw128(0);
       const uint32_t sbase = smem_u32(op_base) >> 4;
+      long long t_a = 0, t_b = 0, t_c = 0, n_t = 0; const long long t_start = clock64();
+      (void)t_a; (void)t_b; (void)t_c; (void)n_t; (void)t_start;
+#ifdef PINNK_STAGE_TIMERS
+      unsigned long long g_start; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_start));
+#endif
       int it = 0;
       int64_t seg = 0;
       int in_seg = 0;
@@ -1099,8 +1137,9 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
         const int s = it % OS;
         const uint32_t ph = (uint32_t)(it / OS) & 1u;
         const int b = (int)(seg & 1);
-        if (in_seg == 0) mbar_wait(&tempty[b], ((uint32_t)(seg >> 1) & 1u) ^ 1u);    // previous use of this buffer flushed
-        mbar_wait(&full[s], ph);
+        if (in_seg == 0) { PK_T0(); mbar_wait(&tempty[b], ((uint32_t)(seg >> 1) & 1u) ^ 1u); PK_TACC(t_a); }    // previous use of this buffer flushed
+        { PK_T0(); mbar_wait(&full[s], ph); PK_TACC(t_b); }
+        PK_T0();
         tc_fence_after();
         const uint32_t gh = sbase + (uint32_t)s * (4 * OP_BYTES >> 4), gl = gh + (OP_BYTES >> 4), xh = gl + (OP_BYTES >> 4),
                        xl = xh + (OP_BYTES >> 4);
@@ -1120,7 +1159,18 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
           in_seg = 0;
           ++seg;
         }
+        PK_TACC(t_c);
+        ++n_t;
       }
+#ifdef PINNK_STAGE_TIMERS
+      if (blockIdx.x == 0 && blockIdx.y == 0) {
+        atomicAdd(&g_stage_timers[4], (unsigned long long)t_a); atomicAdd(&g_stage_timers[5], (unsigned long long)t_b);
+        atomicAdd(&g_stage_timers[6], (unsigned long long)t_c); atomicAdd(&g_stage_timers[9], (unsigned long long)n_t);
+        atomicAdd(&g_stage_timers[10], (unsigned long long)(clock64() - t_start));
+        unsigned long long g_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
+        atomicAdd(&g_stage_timers[11], g_end - g_start);
+      }
+#endif
     }
     __syncwarp();
   }
@@ -1136,7 +1186,7 @@ template <int TK, int RS, int OS, int NCW, int SEG>
 static int launch_wgrad(const float* G, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
                         int jet_cols, int sm_count, cudaStream_t st) {
   constexpr size_t smem = 1024 + (size_t)OS * 4 * TK * 512 + (size_t)RS * 2 * TK * 512 + (2 * RS + 2 * OS + 4) * 8 + 16;
-  static_assert(smem <= 232448 && (size_t)OS * 4 * TK * 512 >= 128 * 129 * 4, "shared memory budget / transpose buffer");
+  static_assert(smem <= 232448 && (size_t)OS * 4 * TK * 512 >= 128 * 132 * 4, "shared memory budget / transpose buffer");
   auto kern = wgrad_kernel<TK, RS, OS, NCW, SEG>;
   static bool configured = false;
   if (!configured) {
@@ -1266,6 +1316,17 @@ int tc_linear_dgrad_actbwd(const float* dZ, const float* W, const float* Zprev, 
 #endif
 
 #ifdef PINNK_TC_TU_WGRAD
+int tc_stage_timers_wgrad(unsigned long long* out16, int reset) {
+#ifdef PINNK_STAGE_TIMERS
+  if (cudaMemcpyFromSymbol(out16, tc::g_stage_timers, 16 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(tc::g_stage_timers, z, sizeof(z)); }
+  return 0;
+#else
+  for (int i = 0; i < 16; ++i) out16[i] = 0;
+  (void)reset;
+  return 1;
+#endif
+}
 // dW[out,in] += dZ[M,out]^T X[M,in] ;  db[out] += sum over value-column rows of dZ
 int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
                                   int jet_cols, int sm_count, cudaStream_t st) {

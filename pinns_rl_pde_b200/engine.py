@@ -20,7 +20,7 @@ from .program import NetProgram, compile_network
 Direction = Tuple[Tuple[float, ...], int]
 
 # upper bound for the per-engine workspace; the chunk size is derived from it
-MAX_WORKSPACE_BYTES = 24 << 30
+MAX_WORKSPACE_BYTES = int(os.environ.get("PINNK_MAX_WORKSPACE_GB", 24)) << 30
 MAX_CHUNK_POINTS = int(os.environ.get("PINNK_MAX_CHUNK_POINTS", 1 << 17))
 
 

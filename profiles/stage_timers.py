@@ -16,6 +16,7 @@ def show(tag, which, fn):
     print(tag, "rc", rc, {k: round(v / n) for k, v in t.items() if k != "tiles"}, "tiles", t["tiles"])
 show("fwd plain", 0, lambda: _lib.debug_linear_fwd(X, W, b, C, 1))
 show("dgrad plain", 1, lambda: _lib.debug_linear_dgrad(dZ, W, 1))
+show("wgrad (32-row tiles)", 2, lambda: _lib.debug_linear_wgrad(dZ, X, C, 1))
 
 # the fused kernels inside a real C2 step (Linear+tanh jets forward, dgrad+tanh adjoint)
 sys.path.insert(0, os.path.join(_R, 'tests'))
