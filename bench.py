@@ -264,7 +264,8 @@ def run_ours(args):
         gemm = {k: prof[k] for k in ("gemm_fwd", "gemm_dgrad", "gemm_wgrad")}
         dom = max(gemm, key=lambda k: gemm[k][0])
         ms_dom, n_dom = gemm[dom]
-        n_chunks = max(1, -(-n_local // 131072))
+        from pinns_rl_pde_b200 import engine as _engine
+        n_chunks = max(1, -(-n_local // _engine.MAX_CHUNK_POINTS))
         rows_per_launch = JET_COLS * n_local / n_chunks                      # stacked jet rows one launch processes
         # algorithmic bytes per row of 128 floats: fwd+tanh reads X, writes Z and Y; dgrad+adjoint reads dZ and the
         # stashed Z, writes dZ_prev; wgrad reads dZ and X (DESIGN.md "kernels")

@@ -21,7 +21,7 @@ Direction = Tuple[Tuple[float, ...], int]
 
 # upper bound for the per-engine workspace; the chunk size is derived from it
 MAX_WORKSPACE_BYTES = int(os.environ.get("PINNK_MAX_WORKSPACE_GB", 24)) << 30
-MAX_CHUNK_POINTS = int(os.environ.get("PINNK_MAX_CHUNK_POINTS", 1 << 17))
+MAX_CHUNK_POINTS = int(os.environ.get("PINNK_MAX_CHUNK_POINTS", 1 << 18))
 
 
 @dataclass

@@ -30,10 +30,10 @@ run("C4 ch2d/siren 5x256 math 18 cols (mse)", "cahn_hilliard", "siren", 256, 5, 
 run("C5 allen-cahn/ff 8x128 scoring", "allen_cahn", "feedforward", 128, 8, 1, 1 << 22, "score", {})
 
 from pinns_rl_pde_b200 import _lib
-def prof(name, pde_name, arch, hidden, layers, dim, n, extra):
+def prof(name, pde_name, arch, hidden, layers, dim, n, extra, compat="reference"):
     torch.manual_seed(0)
     model = pk.make_model(arch, dim + 1, hidden, layers, dev, **extra)
-    pde = product_pde(pde_name, dev, dim)
+    pde = product_pde(pde_name, dev, dim, compat=compat)
     x = torch.rand(n, dim, device=dev); t = torch.rand(n, 1, device=dev)
     def step():
         model.zero_grad(set_to_none=True)
@@ -46,3 +46,4 @@ def prof(name, pde_name, arch, hidden, layers, dim, n, extra):
     print(name, {k: (round(v[0], 1), v[1]) for k, v in p.items() if v[1]}, "total ms", round(tot, 1))
 if len(sys.argv) > 1:
     prof("C3 kdv/resnet", "kdv", "resnet", 256, 6, 1, 1 << 18, {"num_blocks": 6})
+    prof("C4 ch2d/siren math", "cahn_hilliard", "siren", 256, 5, 2, 1 << 17, {"omega_0": 30.0}, "math")
