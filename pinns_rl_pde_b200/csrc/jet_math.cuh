@@ -88,6 +88,29 @@ PK_HD void tanh_dir_bwd(int K, const T (&z)[MAXK + 1], const T (&y)[MAXK + 1], c
   wb0 += wb[0];
 }
 
+// Pre-activation jets from the OUTPUT jets (reverse pass without a pre-activation stash): given y[0..K], w[0] = 1 - y0^2
+// and inv_w0 = 1 / w[0] (0 when the unit is saturated to w0 == 0: every coefficient of such a unit is exactly 0),
+// fill z[1..K] and w[1..K].  Inverts y_k = (1/k) sum_j j z_j w_{k-j} for z_k; consistent with the forward pass because
+// the forward computed y_k with the same w_0.
+template <int MAXK, typename T>
+PK_HD void tanh_dir_recover(int K, const T (&y)[MAXK + 1], T (&w)[MAXK + 1], T (&z)[MAXK + 1], T inv_w0) {
+#pragma unroll
+  for (int k = 1; k <= MAXK; ++k) {
+    if (k <= K) {
+      T acc = T(0);
+#pragma unroll
+      for (int j = 1; j < k; ++j) acc += T(j) * z[j] * w[k - j];
+      z[k] = (y[k] - acc * (T(1) / T(k))) * inv_w0;
+      T wk = T(0);
+#pragma unroll
+      for (int i = 0; i <= k; ++i) wk -= y[i] * y[k - i];
+      w[k] = wk;
+    } else {
+      z[k] = T(0);
+    }
+  }
+}
+
 // order-0 closure: yb0 holds the value adjoint plus all direction contributions.
 template <typename T>
 PK_HD T tanh_finish_bwd(T y0, T w0, T yb0, T wb0) {

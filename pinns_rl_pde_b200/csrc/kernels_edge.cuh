@@ -161,7 +161,8 @@ first_act_bwd_fast_kernel(const float* __restrict__ x, const float* __restrict__
 // Last Linear (N = 1) reverse + adjoint of the activation feeding it:
 //   dL/dY[p,c,f] = Ub[p,c] W[f];  dW[f] += sum Ub[p,c] Y[p,c,f] (Y recomputed from the stashed Z);  db += sum_p Ub[p,0];
 //   Gout = dL/dZ jets.
-template <int ACT, int K0, int K1, int PPT>
+// FROMY (tanh only): Z holds the activation OUTPUT jets (no pre-activation stash); z jets via tanh_dir_recover.
+template <int ACT, int K0, int K1, int PPT, bool FROMY>
 __global__ void __launch_bounds__(128)
 last_act_bwd_fast_kernel(const float* __restrict__ Z, const float* __restrict__ Ub, int64_t n, int width,
                          const float* __restrict__ W, float* __restrict__ Gout, float* __restrict__ gW,
@@ -188,8 +189,16 @@ last_act_bwd_fast_kernel(const float* __restrict__ Z, const float* __restrict__ 
       if (p < n) {
         if (f == 0) accb += ub[u][0];
         float z[MAXK + 1], y[MAXK + 1], w[MAXK + 1], yb[MAXK + 1], zb[MAXK + 1], wb[MAXK + 1];
-        z[0] = zr[u][0];
-        act0<ACT>(z[0], omega, y[0], w[0]);
+        float inv_w0 = 0.f;
+        if constexpr (FROMY) {
+          y[0] = zr[u][0];
+          w[0] = 1.f - y[0] * y[0];
+          inv_w0 = (w[0] > 1e-30f) ? __fdividef(1.f, w[0]) : 0.f;
+        } else {
+          z[0] = zr[u][0];
+          act0<ACT>(z[0], omega, y[0], w[0]);
+        }
+        (void)inv_w0;
         yb[0] = ub[u][0] * wf;
         acc = fmaf(ub[u][0], y[0], acc);
         float wb0 = 0.f;
@@ -200,10 +209,12 @@ last_act_bwd_fast_kernel(const float* __restrict__ Z, const float* __restrict__ 
           if (KD > 0) {
 #pragma unroll
             for (int k = 1; k <= MAXK; ++k) {
-              z[k] = (k <= KD) ? ((ACT == 2) ? zr[u][cb + k] * omega : zr[u][cb + k]) : 0.f;
+              if constexpr (FROMY) y[k] = (k <= KD) ? zr[u][cb + k] : 0.f;
+              else z[k] = (k <= KD) ? ((ACT == 2) ? zr[u][cb + k] * omega : zr[u][cb + k]) : 0.f;
               yb[k] = (k <= KD) ? ub[u][cb + k] * wf : 0.f;
             }
-            if (ACT == 1) tanh_dir_fwd<MAXK, float>(KD, z, y, w);
+            if constexpr (FROMY) tanh_dir_recover<MAXK, float>(KD, y, w, z, inv_w0);
+            else if (ACT == 1) tanh_dir_fwd<MAXK, float>(KD, z, y, w);
             else sincos_dir_fwd<MAXK, float>(KD, z, y, w);
 #pragma unroll
             for (int k = 1; k <= MAXK; ++k)

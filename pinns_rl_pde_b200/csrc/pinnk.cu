@@ -402,7 +402,7 @@ static bool jet_orders(const JetSpec& js, int& k0, int& k1) {
 template <typename F>
 static bool dispatch_edge_jets(int k0, int k1, F&& f) {
 #define PK_EDGE_CASE(A, B) if (k0 == A && k1 == B) { f(std::integral_constant<int, A>(), std::integral_constant<int, B>()); return true; }
-  PK_EDGE_CASE(0, 0) PK_EDGE_CASE(1, 0) PK_EDGE_CASE(1, 1) PK_EDGE_CASE(2, 1) PK_EDGE_CASE(3, 1) PK_EDGE_CASE(4, 1)
+  PK_EDGE_CASE(0, 0) PK_EDGE_CASE(1, 0) PK_EDGE_CASE(2, 0) PK_EDGE_CASE(3, 0) PK_EDGE_CASE(4, 0) PK_EDGE_CASE(1, 1) PK_EDGE_CASE(2, 1) PK_EDGE_CASE(3, 1) PK_EDGE_CASE(4, 1)
 #undef PK_EDGE_CASE
   return false;
 }
@@ -410,6 +410,37 @@ static bool edge_fast_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("PINNK_DISABLE_EDGE_FAST"); v = (e && e[0] == '1') ? 0 : 1; }
   return v == 1;
+}
+
+static int first_trainable_op(const pinnk_plan_t pl) {
+  const int n_ops = (int)pl->ops.size();
+  for (int i = 0; i < n_ops; ++i)
+    if (pl->ops[i].op.gw_offset >= 0 || pl->ops[i].op.gb_offset >= 0) return i;
+  return n_ops;
+}
+
+// Is the pre-activation stash of hidden LINEAR op `lin` elided?  True when (a) the forward runs it as the fused
+// Linear + tanh kernel without a partial-sum buffer and (b) the only reader of that stash in the reverse pass -- the
+// adjoint of the tanh -- runs in a kernel that can work from the activation OUTPUT jets instead (EPI_ACTBWD_Y /
+// last_act_bwd_fast_kernel<FROMY>).  Forward and reverse pass both ask this one function, so they cannot disagree.
+// PINNK_KEEP_Z=1 switches the elision off (A/B checks).
+static bool z_elided(const pinnk_plan_t pl, int lin) {
+  static int keep = -1;
+  if (keep < 0) { const char* e = getenv("PINNK_KEEP_Z"); keep = (e && e[0] == '1') ? 1 : 0; }
+  if (keep || !tc_enabled() || !edge_fast_enabled()) return false;
+  const int n_ops = (int)pl->ops.size();
+  if (lin <= 0 || lin + 2 > n_ops - 1) return false;
+  const PinnkOp& L = pl->ops[lin].op;
+  const OpRt& A = pl->ops[lin + 1];
+  const OpRt& N = pl->ops[lin + 2];
+  if (L.kind != PINNK_OP_LINEAR || A.op.kind != PINNK_OP_ACT || A.skip_src >= 0 || A.op.act != PINNK_ACT_TANH) return false;
+  if (A.in_op != lin || N.op.kind != PINNK_OP_LINEAR || N.in_op != lin + 1) return false;
+  int k0 = 0, k1 = 0;
+  if (!jet_orders(pl->js, k0, k1) || !tc_jets_supported(k0, k1)) return false;
+  if (L.in_dim != 128 || (L.out_dim % 128) != 0) return false;                    // producer: tc_linear_act_fwd, K = 128
+  if (lin + 2 == n_ops - 1)                                                         // consumer: last_act_bwd_fast_kernel
+    return pl->fuse_last && (N.op.in_dim % 128) == 0 && first_trainable_op(pl) <= n_ops - 2;
+  return (N.op.out_dim == 128 || N.op.out_dim == 256) && (N.op.in_dim % 128) == 0; // consumer: tc_linear_dgrad_actbwd
 }
 
 // forward jets of one chunk; fills the stash and U[n, C]
@@ -474,7 +505,8 @@ static int forward_chunk(const ChunkCtx& c, bool keep_stash = true) {
               jet_orders(js, k0, k1)) {
             const PinnkOp& a = pl->ops[i + 1].op;
             ProfScope ps(PC_GEMM_FWD, c.st);
-            int rc = tc_linear_act_fwd(in, W, b, (keep_stash || o.in_dim != 128) ? c.stash(i) : nullptr, c.stash(i + 1), c.n * js.ncols, o.in_dim, o.out_dim, k0, k1,
+            const bool want_z = (keep_stash && !z_elided(pl, i)) || o.in_dim != 128;
+            int rc = tc_linear_act_fwd(in, W, b, want_z ? c.stash(i) : nullptr, c.stash(i + 1), c.n * js.ncols, o.in_dim, o.out_dim, k0, k1,
                                        a.act == PINNK_ACT_TANH ? 1 : 2, a.scale, pl->sm_count, c.st);
             if (rc == 0) { g_launches.fetch_add(1); ++i; break; }
             if (rc != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, std::string("tc_linear_act_fwd launch failed: ") + cudaGetErrorString(cudaGetLastError()));
@@ -543,12 +575,15 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad) {
             constexpr int PPT = 2;
             dim3 g2((unsigned)(o.in_dim / 128), (unsigned)std::min<int64_t>((c.n + PPT - 1) / PPT, 16 * (int64_t)pl->sm_count));
             const bool tanh_act = pa.op.act == PINNK_ACT_TANH;
+            const bool from_y = z_elided(pl, pa.in_op);
             const bool ok = dispatch_edge_jets(ek0, ek1, [&](auto ka, auto kb) {
               constexpr int KA = decltype(ka)::value, KB = decltype(kb)::value;
-              if (tanh_act) last_act_bwd_fast_kernel<1, KA, KB, PPT><<<g2, 128, 0, c.st>>>(c.stash(pa.in_op), c.Ub(), c.n, o.in_dim, W, c.adj(cur), G(o.gw_offset), G(o.gb_offset), 1.f);
-              else last_act_bwd_fast_kernel<2, KA, KB, PPT><<<g2, 128, 0, c.st>>>(c.stash(pa.in_op), c.Ub(), c.n, o.in_dim, W, c.adj(cur), G(o.gw_offset), G(o.gb_offset), pa.op.scale);
+              if (from_y) last_act_bwd_fast_kernel<1, KA, KB, PPT, true><<<g2, 128, 0, c.st>>>(c.stash(n_ops - 2), c.Ub(), c.n, o.in_dim, W, c.adj(cur), G(o.gw_offset), G(o.gb_offset), 1.f);
+              else if (tanh_act) last_act_bwd_fast_kernel<1, KA, KB, PPT, false><<<g2, 128, 0, c.st>>>(c.stash(pa.in_op), c.Ub(), c.n, o.in_dim, W, c.adj(cur), G(o.gw_offset), G(o.gb_offset), 1.f);
+              else last_act_bwd_fast_kernel<2, KA, KB, PPT, false><<<g2, 128, 0, c.st>>>(c.stash(pa.in_op), c.Ub(), c.n, o.in_dim, W, c.adj(cur), G(o.gw_offset), G(o.gb_offset), pa.op.scale);
             });
             if (ok) { PK_LAUNCH_OK(); --i; break; }
+            if (from_y) return fail(PINNK_E_INVALID, "backward: pre-activation stash elided but no edge kernel for this jet layout");
           }
           if (pa.op.act == PINNK_ACT_TANH)
             last_act_bwd_kernel<1, MAXK><<<grid, 128, 0, c.st>>>(c.stash(pa.in_op), c.Ub(), c.n, o.in_dim, js, W, c.adj(cur),
@@ -583,10 +618,13 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad) {
             if (tc_enabled() && r.in_op == i - 1 && pa.op.kind == PINNK_OP_ACT && pa.skip_src < 0 && pa.in_op >= 0 &&
                 !first_pair && jet_orders(js, k0, k1)) {
               ProfScope ps(PC_GEMM_DGRAD, c.st);
-              rc = tc_linear_dgrad_actbwd(c.adj(cur), W, c.stash(pa.in_op), c.adj(nxt), c.n * js.ncols, o.in_dim, o.out_dim,
-                                          k0, k1, pa.op.act == PINNK_ACT_TANH ? 1 : 2, pa.op.scale, pl->sm_count, c.st);
+              const bool from_y = z_elided(pl, pa.in_op);      // the forward did not stash this pre-activation
+              rc = tc_linear_dgrad_actbwd(c.adj(cur), W, from_y ? c.stash(i - 1) : c.stash(pa.in_op), c.adj(nxt), c.n * js.ncols,
+                                          o.in_dim, o.out_dim, k0, k1, pa.op.act == PINNK_ACT_TANH ? 1 : 2, pa.op.scale,
+                                          pl->sm_count, c.st, from_y ? 1 : 0);
               if (rc == 0) { g_launches.fetch_add(1); cur = nxt; --i; break; }
               if (rc != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, std::string("tc_linear_dgrad_actbwd launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+              if (from_y) return fail(PINNK_E_INVALID, "backward: pre-activation stash elided but the fused adjoint kernel refused the shape");
             }
             rc = gemm_dgrad(c, c.adj(cur), W, c.adj(nxt), o.in_dim, o.out_dim);
             if (rc) return rc;
@@ -627,6 +665,7 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad) {
         }
         const float* S = (r.skip_src >= 0) ? c.stash(r.skip_src) : nullptr;
         const unsigned blocks = blocks_for(c.n * o.in_dim, threads);
+        if (z_elided(pl, r.in_op)) return fail(PINNK_E_INVALID, "backward: generic activation adjoint reached for an elided pre-activation stash");
         ProfScope ps(PC_ACT_BWD, c.st);
         if (o.act == PINNK_ACT_TANH)
           act_bwd_kernel<1, MAXK><<<blocks, threads, 0, c.st>>>(in, S, c.adj(cur), c.n, o.in_dim, js, 1.f);

@@ -19,9 +19,14 @@ int tc_linear_act_fwd(const float* X, const float* W, const float* bias, float* 
 // dX[M,in] = dZ[M,out] W[out,in]   (W row-major [out,in])
 int tc_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t M, int in_dim, int out_dim, int sm_count,
                     cudaStream_t st);
-// dgrad + activation adjoint in one kernel: dZprev = act'(Zprev)^T (dZ W)
+// dgrad + activation adjoint in one kernel: dZprev = act'(Zprev)^T (dZ W).  from_y = 1 (tanh only): Zprev holds the
+// activation OUTPUT jets instead of the pre-activation jets (the forward pass then does not stash the latter)
 int tc_linear_dgrad_actbwd(const float* dZ, const float* W, const float* Zprev, float* dZprev, int64_t M, int in_dim,
-                           int out_dim, int k0, int k1, int act, float omega, int sm_count, cudaStream_t st);
+                           int out_dim, int k0, int k1, int act, float omega, int sm_count, cudaStream_t st, int from_y);
+// jet layouts (orders of the at most two directions) the fused epilogues are instantiated for
+inline bool tc_jets_supported(int k0, int k1) {
+  return (k0 == 0 && k1 == 0) || (k0 == 1 && k1 == 0) || (k0 == 2 && k1 == 1) || (k0 == 3 && k1 == 0);
+}
 // dW[out,in] += dZ[M,out]^T X[M,in] ;  db[out] += sum over value-column rows of dZ
 int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
                     int jet_cols, int sm_count, cudaStream_t st);

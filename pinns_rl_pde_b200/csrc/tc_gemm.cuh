@@ -521,7 +521,9 @@ static __device__ unsigned long long g_stage_timers[16];
 //               Y = dL/d(pre-activation)                                   -- replaces gemm + act_bwd_kernel
 // For the fused epilogues the jet layout is a compile-time (K0, K1): value column, K0 columns of direction 0, K1 of
 // direction 1, with C = 1 + K0 + K1 dividing 32 so that every epilogue warp owns whole points.
-enum { EPI_PLAIN = 0, EPI_ACT = 1, EPI_ACTBWD = 2 };
+//   EPI_ACTBWD_Y  as EPI_ACTBWD for tanh, but Zs holds the activation OUTPUT jets (the forward pass then never writes the
+//               pre-activations: 512 B per row less traffic); z jets are recovered with tanh_dir_recover
+enum { EPI_PLAIN = 0, EPI_ACT = 1, EPI_ACTBWD = 2, EPI_ACTBWD_Y = 3 };
 
 template <bool TRANS_W, int EPI, int ACT, int K0, int K1, int NLW, int ECOLS, bool ACCUM, int LDYC>
 __global__ void __launch_bounds__((NLW + 4 * (64 / ECOLS) + 2) * 32, 1)
@@ -531,6 +533,8 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
   // LDYC: compile-time row stride of Y / Zs / Yact (0 = use the runtime value): with it every row address of the
   // epilogue is base + immediate instead of a 64-bit multiply-add per access
   const int ldy = LDYC ? LDYC : ldy_rt;
+  constexpr bool IS_BWD = (EPI == EPI_ACTBWD || EPI == EPI_ACTBWD_Y);
+  static_assert(EPI != EPI_ACTBWD_Y || ACT == 1, "the output-jet reverse epilogue exists for tanh only");
   // ldx: row stride of X in floats (K = 128 columns of it are contracted: one half of a 256-wide layer);
   // ACCUM: the epilogue adds the partial result already stored in Y (second K half of a 256-wide layer)
   constexpr int K = 128, TN = 64, STAGES = 2, RS = 3, ACC = 2, NEW = 4 * (TN / ECOLS);
@@ -694,8 +698,8 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
       }
       float* const yp = Y + r0 * ldy + n0 + f;
       // the stashed pre-activations do not depend on the MMA: fetch them while the accumulator is still being produced
-      float zsr[(EPI == EPI_ACTBWD) ? ECOLS : 1];
-      if constexpr (EPI == EPI_ACTBWD) {
+      float zsr[IS_BWD ? ECOLS : 1];
+      if constexpr (IS_BWD) {
         const float* const zs0 = Zs + r0 * ldy + n0 + f;
 #pragma unroll
         for (int j = 0; j < ECOLS; ++j) zsr[j] = (FULL || j < nrows) ? __ldg(zs0 + j * ldy) : 0.f;
@@ -762,6 +766,30 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
                     if (k <= KD) ya[(cb + k) * ldy] = y[k];
                 }
               }
+            } else if constexpr (EPI == EPI_ACTBWD_Y) {   // tanh adjoint from the stashed OUTPUT jets
+              float yb[MAXK + 1], zb[MAXK + 1];
+              y[0] = zsr[jb];
+              w[0] = 1.f - y[0] * y[0];
+              const float inv_w0 = (w[0] > 1e-30f) ? __fdividef(1.f, w[0]) : 0.f;
+              yb[0] = acc[jb];
+              float wb0 = 0.f;
+#pragma unroll
+              for (int d = 0; d < 2; ++d) {
+                const int KD = d ? K1 : K0, cb = jb + (d ? K0 : 0);
+                if (KD > 0) {
+#pragma unroll
+                  for (int k = 1; k <= MAXK; ++k) {
+                    y[k] = (k <= KD) ? zsr[cb + k] : 0.f;
+                    yb[k] = (k <= KD) ? acc[cb + k] : 0.f;
+                  }
+                  tanh_dir_recover<MAXK, float>(KD, y, w, z, inv_w0);
+                  tanh_dir_bwd<MAXK, float>(KD, z, y, w, yb, zb, wb0);
+#pragma unroll
+                  for (int k = 1; k <= MAXK; ++k)
+                    if (k <= KD) yp[(cb + k) * ldy] = zb[k];
+                }
+              }
+              yp[jb * ldy] = tanh_finish_bwd<float>(y[0], w[0], yb[0], wb0);
             } else {   // EPI_ACTBWD
               float yb[MAXK + 1], zb[MAXK + 1], wb[MAXK + 1];
               z[0] = zsr[jb];
@@ -1221,9 +1249,6 @@ static inline int tc_dispatch_jets(int k0, int k1, const float* X, const float* 
 }
 // A 256-wide contraction runs as two K halves of the K = 128 kernel: the first writes the partial result (plain
 // epilogue, no bias), the second adds it in its epilogue (bias, activation ... as requested).
-static inline bool tc_jets_supported(int k0, int k1) {
-  return (k0 == 0 && k1 == 0) || (k0 == 1 && k1 == 0) || (k0 == 2 && k1 == 1) || (k0 == 3 && k1 == 0);
-}
 #endif
 
 #ifdef PINNK_TC_TU_FWD
@@ -1301,7 +1326,8 @@ int tc_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t M, int i
 // dgrad + activation adjoint in one kernel: dZprev = act'(Zprev)^T (dZ W)
 int tc_linear_dgrad_actbwd(const float* dZ, const float* W, const float* Zprev, float* dZprev, int64_t M,
                                          int in_dim, int out_dim, int k0, int k1, int act, float omega, int sm_count,
-                                         cudaStream_t st) {
+                                         cudaStream_t st, int from_y) {
+  if (from_y && act != 1) return TC_UNSUPPORTED;
   if (M < 1 || (out_dim != 128 && out_dim != 256) || (in_dim % 128) != 0 || !tc_jets_supported(k0, k1) || (act != 1 && act != 2))
     return TC_UNSUPPORTED;
   int accum = 0;
@@ -1310,6 +1336,7 @@ int tc_linear_dgrad_actbwd(const float* dZ, const float* W, const float* Zprev, 
     if (rc) return rc;
     dZ += 128; W += (int64_t)128 * in_dim; accum = 1;
   }
+  if (act == 1 && from_y) return tc_dispatch_jets<true, tc::EPI_ACTBWD_Y, 1>(k0, k1, dZ, W, in_dim, nullptr, dZprev, M, in_dim, Zprev, nullptr, 1.f, sm_count, st, out_dim, accum);
   if (act == 1) return tc_dispatch_jets<true, tc::EPI_ACTBWD, 1>(k0, k1, dZ, W, in_dim, nullptr, dZprev, M, in_dim, Zprev, nullptr, 1.f, sm_count, st, out_dim, accum);
   return tc_dispatch_jets<true, tc::EPI_ACTBWD, 2>(k0, k1, dZ, W, in_dim, nullptr, dZprev, M, in_dim, Zprev, nullptr, omega, sm_count, st, out_dim, accum);
 }
