@@ -125,10 +125,16 @@ class ClockSampler:
                  "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
                  "clocks_event_reasons.sw_power_cap")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+
+    def count(self):
+        try:
+            return sum(1 for _ in open(self.path))
+        except Exception:
+            return 0
 
     def stop(self):
         if self.proc is None:
@@ -216,11 +222,18 @@ def run_ours(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
-    for _ in range(args.warmup):
-        step(x, t)
+    # clocks are sampled from the first warm-up step on (same load as the timed steps): nvidia-smi needs a few hundred
+    # milliseconds before its first sample, longer than a short timed region
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step(x, t)
+    if rank == 0:
+        t_wait = time.time()
+        while sampler.count() == 0 and time.time() - t_wait < 3.0:      # keep the GPU loaded until the sampler is live
+            step(x, t)
+            torch.cuda.synchronize()
     l0 = _lib.launch_count()
     ms_total = timed(lambda: step(x, t), args.steps)
     launches = _lib.launch_count() - l0

@@ -175,5 +175,5 @@ def stage_timers(which: int, reset: bool = True):
     out = (C.c_uint64 * 16)()
     rc = load().pinnk_debug_stage_timers(which, out, 1 if reset else 0)
     names = ["tma:raw_empty", "cvt:raw_full", "cvt:empty", "cvt:work", "mma:tempty", "mma:full", "mma:issue",
-             "epi:tfull", "epi:work", "tiles", "total", "total_ns"]
+             "epi:tfull", "epi:work", "tiles", "total", "total_ns", "prologue_ns", "kernel_ns", "launches", "max_loop_ns"]
     return rc, {n: int(out[i]) for i, n in enumerate(names)}

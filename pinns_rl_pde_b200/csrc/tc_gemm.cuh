@@ -560,6 +560,9 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
   uint64_t* raw_empty = raw_full + RS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + RS);
 
+#ifdef PINNK_STAGE_TIMERS
+  unsigned long long g_entry; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_entry));
+#endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * 128;
   const int64_t ntiles = (M + TN - 1) / TN;
@@ -884,12 +887,17 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
         ++n_t;
       }
 #ifdef PINNK_STAGE_TIMERS
+      {   // slowest and fastest CTA of the launch (loop time): static tile assignment vs uneven memory paths
+        unsigned long long g_e2; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_e2));
+        atomicMax(&g_stage_timers[15], g_e2 - g_start);
+      }
       if (blockIdx.x == 0 && blockIdx.y == 0) {
         atomicAdd(&g_stage_timers[4], (unsigned long long)t_a); atomicAdd(&g_stage_timers[5], (unsigned long long)t_b);
         atomicAdd(&g_stage_timers[6], (unsigned long long)t_c); atomicAdd(&g_stage_timers[9], (unsigned long long)n_t);
         atomicAdd(&g_stage_timers[10], (unsigned long long)(clock64() - t_start));
         unsigned long long g_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
         atomicAdd(&g_stage_timers[11], g_end - g_start);
+        atomicAdd(&g_stage_timers[12], g_start - g_entry);     // kernel entry -> first MMA wait (prologue)
       }
 #endif
     }
@@ -900,6 +908,13 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
   if (warp == MMAW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+#ifdef PINNK_STAGE_TIMERS
+    if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) {
+      unsigned long long g_exit; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_exit));
+      atomicAdd(&g_stage_timers[13], g_exit - g_entry);         // whole kernel, block 0
+      atomicAdd(&g_stage_timers[14], 1ull);
+    }
+#endif
   }
 }
 
@@ -977,6 +992,9 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
   uint64_t* tempty = tfull + 2;                      // [2] segment flushed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
+#ifdef PINNK_STAGE_TIMERS
+  unsigned long long g_entry; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_entry));
+#endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int o0 = (blockIdx.y / in_blocks) * 128, i0 = (blockIdx.y % in_blocks) * 128;
   const int64_t ntiles = (M + TK - 1) / TK;
@@ -1191,12 +1209,17 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
         ++n_t;
       }
 #ifdef PINNK_STAGE_TIMERS
+      {   // slowest and fastest CTA of the launch (loop time): static tile assignment vs uneven memory paths
+        unsigned long long g_e2; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_e2));
+        atomicMax(&g_stage_timers[15], g_e2 - g_start);
+      }
       if (blockIdx.x == 0 && blockIdx.y == 0) {
         atomicAdd(&g_stage_timers[4], (unsigned long long)t_a); atomicAdd(&g_stage_timers[5], (unsigned long long)t_b);
         atomicAdd(&g_stage_timers[6], (unsigned long long)t_c); atomicAdd(&g_stage_timers[9], (unsigned long long)n_t);
         atomicAdd(&g_stage_timers[10], (unsigned long long)(clock64() - t_start));
         unsigned long long g_end; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_end));
         atomicAdd(&g_stage_timers[11], g_end - g_start);
+        atomicAdd(&g_stage_timers[12], g_start - g_entry);     // kernel entry -> first MMA wait (prologue)
       }
 #endif
     }
@@ -1207,6 +1230,13 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
   if (warp == MMAW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+#ifdef PINNK_STAGE_TIMERS
+    if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) {
+      unsigned long long g_exit; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_exit));
+      atomicAdd(&g_stage_timers[13], g_exit - g_entry);         // whole kernel, block 0
+      atomicAdd(&g_stage_timers[14], 1ull);
+    }
+#endif
   }
 }
 

@@ -45,6 +45,14 @@ void hm_tanh_k(int maxk, int K, const double* z, const double* yb, double* y, do
   if (maxk == 1) tanh_one<1>(K, z, yb, y, zb); else if (maxk == 2) tanh_one<2>(K, z, yb, y, zb);
   else if (maxk == 3) tanh_one<3>(K, z, yb, y, zb); else tanh_one<4>(K, z, yb, y, zb);
 }
+// z jets recovered from the output jets (reverse pass without a pre-activation stash): y in, z[1..K] and w out
+void hm_tanh_recover(int K, const double* y, double* z, double* w) {
+  double yy[5] = {0, 0, 0, 0, 0}, ww[5] = {0, 0, 0, 0, 0}, zz[5] = {0, 0, 0, 0, 0};
+  for (int k = 0; k <= K; ++k) yy[k] = y[k];
+  ww[0] = 1.0 - yy[0] * yy[0];
+  tanh_dir_recover<4, double>(K, yy, ww, zz, ww[0] > 0 ? 1.0 / ww[0] : 0.0);
+  for (int k = 0; k <= K; ++k) { z[k] = zz[k]; w[k] = ww[k]; }
+}
 void hm_sin(int K, double omega, const double* z, const double* sb, const double* cb, double* s, double* c, double* zb) {
   sin_one<4>(K, omega, z, sb, cb, s, c, zb);
 }

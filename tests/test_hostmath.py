@@ -56,6 +56,28 @@ def test_tanh_jet_and_adjoint(hm, K):
 
 
 @pytest.mark.parametrize("K", [1, 2, 3, 4])
+def test_tanh_preactivation_recovered_from_output_jets(hm, K):
+    """The reverse kernels of fused Linear+tanh layers keep only the OUTPUT jets: tanh_dir_recover must give back the
+    pre-activation coefficients z_1..z_K (and the w series) the forward recurrence consumed."""
+    rng = np.random.default_rng(40 + K)
+    for trial in range(20):
+        z = _rand_jet(rng, K, 0.8 if trial < 15 else 3.0)
+        y, zb = np.zeros(K + 1), np.zeros(K + 1)
+        hm.hm_tanh(K, _p(z), _p(np.zeros(K + 1)), _p(y), _p(zb))
+        zr, w = np.zeros(K + 1), np.zeros(K + 1)
+        hm.hm_tanh_recover(K, _p(y), _p(zr), _p(w))
+        np.testing.assert_allclose(zr[1:], z[1:], rtol=1e-9, atol=1e-11)
+        # w is the Taylor series of 1 - tanh^2
+        wt = [-(sum(y[i] * y[k - i] for i in range(k + 1))) + (1.0 if k == 0 else 0.0) for k in range(K + 1)]
+        np.testing.assert_allclose(w, wt, rtol=1e-12, atol=1e-13)
+    # a saturated unit (w0 == 0): every recovered coefficient is 0, nothing is inf / nan
+    y = np.zeros(K + 1); y[0] = 1.0
+    zr, w = np.ones(K + 1), np.ones(K + 1)
+    hm.hm_tanh_recover(K, _p(y), _p(zr), _p(w))
+    assert np.all(np.isfinite(zr)) and np.all(zr[1:] == 0.0)
+
+
+@pytest.mark.parametrize("K", [1, 2, 3, 4])
 @pytest.mark.parametrize("omega", [1.0, 30.0])
 def test_sincos_jet_and_adjoint(hm, K, omega):
     rng = np.random.default_rng(10 + K)
