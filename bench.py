@@ -229,11 +229,15 @@ def run_ours(args):
         sampler.start()
     for _ in range(args.warmup):
         step(x, t)
-    if rank == 0:
-        t_wait = time.time()
-        while sampler.count() == 0 and time.time() - t_wait < 3.0:      # keep the GPU loaded until the sampler is live
-            step(x, t)
-            torch.cuda.synchronize()
+    t_wait = time.time()
+    while True:                                  # keep every rank loaded until rank 0's sampler is live (collective-safe)
+        more = torch.tensor([1 if (rank == 0 and sampler.count() == 0 and time.time() - t_wait < 3.0) else 0], device=dev)
+        if world > 1:
+            dist.broadcast(more, 0)
+        if int(more.item()) == 0:
+            break
+        step(x, t)
+        torch.cuda.synchronize()
     l0 = _lib.launch_count()
     ms_total = timed(lambda: step(x, t), args.steps)
     launches = _lib.launch_count() - l0
