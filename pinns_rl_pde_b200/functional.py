@@ -232,7 +232,8 @@ def _data_loss(pde, model) -> torch.Tensor:
     return pde._apply_loss_fn(u - obs["u"].to(dev))
 
 
-def _build_calls(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_global: Optional[int] = None):
+def _build_calls(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_global: Optional[int] = None,
+                 merge_value_rows: bool = False):
     """The libpinnk calls (engine, rows, segments) that make up compute_loss: residual rows (component 0), boundary
     rows (1), initial rows (2), exactly the point sets and targets the reference builds."""
     name = pde_name(pde)
@@ -334,8 +335,6 @@ def _build_calls(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_glob
             tgt = fn(xb, tb).detach().to(torch.float32).reshape(-1).contiguous()
             segs.append(Segment(kind=L.PDE_VALUE, row_start=0, row_count=nbp, component=1, weight=1.0 / nbp,
                                 target=tgt, **mk))
-        if segs:
-            calls.append((get_engine(model, [], nbp), xb, tb, segs))
         xi = torch.linspace(dom[0][0], dom[0][1], 100, device=dev).reshape(-1, 1)
         ti = torch.zeros_like(xi)
         if "initial" in pde.boundary_conditions:
@@ -346,9 +345,19 @@ def _build_calls(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_glob
                 target = ic["amplitude"] * torch.sin(ic["frequency"] * torch.pi * xi)
             else:
                 target = pde._create_boundary_condition("initial", ic)(xi, ti)
-        calls.append((get_engine(model, [], 100), xi, ti, [
-            Segment(kind=L.PDE_VALUE, row_start=0, row_count=100, component=2, weight=0.01,
-                    target=target.detach().to(torch.float32).reshape(-1).contiguous(), **mk)]))
+        ic_target = target.detach().to(torch.float32).reshape(-1).contiguous()
+        if merge_value_rows and segs:
+            # boundary and initial rows are both value-only rows (one jet column): ONE pass over [boundary rows; initial
+            # rows] with one segment per error functional instead of two passes of ~30 tiny launches each.  Only valid
+            # when all components accumulate into one gradient buffer (the fused trainer step).
+            segs.append(Segment(kind=L.PDE_VALUE, row_start=nbp, row_count=100, component=2, weight=0.01,
+                                target=ic_target, **mk))
+            calls.append((get_engine(model, [], nbp + 100), torch.cat([xb, xi], dim=0), torch.cat([tb, ti], dim=0), segs))
+        else:
+            if segs:
+                calls.append((get_engine(model, [], nbp), xb, tb, segs))
+            calls.append((get_engine(model, [], 100), xi, ti, [
+                Segment(kind=L.PDE_VALUE, row_start=0, row_count=100, component=2, weight=0.01, target=ic_target, **mk)]))
 
     return calls, _weights(pde, heat)
 
@@ -372,7 +381,7 @@ def loss_step_flat(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_gl
     Returns (components fp32 [3] = residual, boundary, initial means; weights; flat gradient of
     ``res_scale * w_res * residual + rest_scale * (w_bc * boundary + w_ic * initial)`` in ``model.parameters()`` order).
     ``res_scale`` / ``rest_scale`` are the shard weights of the data-parallel step (parallel.py)."""
-    calls, weights = _build_calls(pde, model, x, t, n_global)
+    calls, weights = _build_calls(pde, model, x, t, n_global, merge_value_rows=True)
     w_res, w_bc, w_ic, w_smooth, adaptive = weights
     if w_smooth:
         raise NotImplementedError("the fused step does not cover the smoothness regulariser; use compute_loss")
