@@ -266,4 +266,15 @@ last_linear_fwd_w128_kernel(const float* __restrict__ X, int64_t rows, int ncols
   }
 }
 
+// U[row] = sum_{p < parts} u_part[p][row] (+ b on value rows): the fixed-order sum of the per-warp partial output jets the
+// fused last hidden layer wrote (tc_linear_act_fwd with w_out).  20 B per row.
+__global__ void output_combine_kernel(const float* __restrict__ u_part, int parts, int64_t rows, int ncols,
+                                      const float* __restrict__ b, float* __restrict__ U) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  float a = 0.f;
+  for (int p = 0; p < parts; ++p) a += u_part[(int64_t)p * rows + r];
+  U[r] = a + ((b && (r % ncols) == 0) ? b[0] : 0.f);
+}
+
 }  // namespace pinnk

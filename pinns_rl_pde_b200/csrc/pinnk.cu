@@ -412,6 +412,13 @@ static bool edge_fast_enabled() {
   return v == 1;
 }
 
+// PINNK_DISABLE_OUT_FUSE=1: output layer as its own pass over the last activation (A/B checks)
+static bool out_fuse_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PINNK_DISABLE_OUT_FUSE"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1 && tc_enabled();
+}
+
 static int first_trainable_op(const pinnk_plan_t pl) {
   const int n_ops = (int)pl->ops.size();
   for (int i = 0; i < n_ops; ++i)
@@ -506,8 +513,25 @@ static int forward_chunk(const ChunkCtx& c, bool keep_stash = true) {
             const PinnkOp& a = pl->ops[i + 1].op;
             ProfScope ps(PC_GEMM_FWD, c.st);
             const bool want_z = (keep_stash && !z_elided(pl, i)) || o.in_dim != 128;
-            int rc = tc_linear_act_fwd(in, W, b, want_z ? c.stash(i) : nullptr, c.stash(i + 1), c.n * js.ncols, o.in_dim, o.out_dim, k0, k1,
-                                       a.act == PINNK_ACT_TANH ? 1 : 2, a.scale, pl->sm_count, c.st);
+            // last hidden layer: fold the output layer nn.Linear(width, 1) into the epilogue (partials in adj(0), which
+            // is idle during the forward); forward-only callers then do not store the activation output either
+            const bool fuse_out = out_fuse_enabled() && i + 2 == n_ops - 1 && pl->ops[i + 2].op.kind == PINNK_OP_LINEAR &&
+                                  pl->ops[i + 2].in_op == i + 1 && !pl->ops[i + 2].op.w_transposed;
+            const PinnkOp& lo = pl->ops[n_ops - 1].op;
+            const float* w_out = fuse_out ? c.params[lo.w_index] : nullptr;
+            float* y_out = (fuse_out && !keep_stash) ? nullptr : c.stash(i + 1);
+            int rc = tc_linear_act_fwd(in, W, b, want_z ? c.stash(i) : nullptr, y_out, c.n * js.ncols, o.in_dim, o.out_dim, k0, k1,
+                                       a.act == PINNK_ACT_TANH ? 1 : 2, a.scale, pl->sm_count, c.st, w_out, fuse_out ? c.adj(0) : nullptr);
+            if (rc == 0 && fuse_out) {
+              g_launches.fetch_add(1);
+              ProfScope ps2(PC_LAST_FWD, c.st);
+              const int64_t rows = c.n * js.ncols;
+              output_combine_kernel<<<blocks_for(rows, threads), threads, 0, c.st>>>(
+                  c.adj(0), 4 * (o.out_dim / 128), rows, js.ncols, lo.b_index >= 0 ? c.params[lo.b_index] : nullptr, c.U());
+              PK_LAUNCH_OK();
+              i = n_ops - 1;        // activation and output layer are done
+              break;
+            }
             if (rc == 0) { g_launches.fetch_add(1); ++i; break; }
             if (rc != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, std::string("tc_linear_act_fwd launch failed: ") + cudaGetErrorString(cudaGetLastError()));
           }

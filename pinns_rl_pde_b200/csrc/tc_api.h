@@ -13,9 +13,12 @@ constexpr int TC_UNSUPPORTED = 1;
 int tc_linear_fwd(const float* X, const float* W, const float* bias, float* Z, int64_t M, int K, int N, int jet_cols,
                   int sm_count, cudaStream_t st);
 // Forward Linear + activation jets in one kernel: Z = X W^T + b (stash, may be null for K = 128), Yact = act(Z).
-// act: 1 tanh, 2 sin(omega z); (k0, k1) = jet orders of the (at most two) directions
+// act: 1 tanh, 2 sin(omega z); (k0, k1) = jet orders of the (at most two) directions.
+// w_out != null folds the network's output layer nn.Linear(N, 1) in: u_part[(N/128) * 4][M] receives per-warp partial
+// output jets (sum them in order + bias: output_combine_kernel); Yact may then be null (forward-only callers).
 int tc_linear_act_fwd(const float* X, const float* W, const float* bias, float* Z, float* Yact, int64_t M, int K, int N,
-                      int k0, int k1, int act, float omega, int sm_count, cudaStream_t st);
+                      int k0, int k1, int act, float omega, int sm_count, cudaStream_t st,
+                      const float* w_out = nullptr, float* u_part = nullptr);
 // dX[M,in] = dZ[M,out] W[out,in]   (W row-major [out,in])
 int tc_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t M, int in_dim, int out_dim, int sm_count,
                     cudaStream_t st);

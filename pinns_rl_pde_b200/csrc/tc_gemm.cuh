@@ -525,11 +525,21 @@ static __device__ unsigned long long g_stage_timers[16];
 //               pre-activations: 512 B per row less traffic); z jets are recovered with tanh_dir_recover
 enum { EPI_PLAIN = 0, EPI_ACT = 1, EPI_ACTBWD = 2, EPI_ACTBWD_Y = 3 };
 
+// EPI_ACT only: the network's output layer (nn.Linear(width, 1)) folded into the epilogue of the last hidden layer.
+// Every epilogue warp reduces w_out[f] * y[row, f] over its 32 features (butterfly of 16 shuffles for 16 rows) and writes
+// the partial output jets to u_part[(4 * n_block + lane quarter) * M + row]; a tiny kernel adds the partials in a fixed
+// order (deterministic) and the bias.  The activation output Yact then needs no store at all when nothing else reads it
+// (forward-only scoring): 512 B per row less traffic, and no separate pass over Y for the output layer.
+struct OutFuse {
+  const float* w_out = nullptr;
+  float* u_part = nullptr;
+};
+
 template <bool TRANS_W, int EPI, int ACT, int K0, int K1, int NLW, int ECOLS, bool ACCUM, int LDYC>
 __global__ void __launch_bounds__((NLW + 4 * (64 / ECOLS) + 2) * 32, 1)
 linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
                       float* __restrict__ Y, int64_t M, int ldy_rt, int jet_cols, const float* __restrict__ Zs,
-                      float* __restrict__ Yact, float omega, int ldx) {
+                      float* __restrict__ Yact, float omega, int ldx, OutFuse of) {
   // LDYC: compile-time row stride of Y / Zs / Yact (0 = use the runtime value): with it every row address of the
   // epilogue is base + immediate instead of a 64-bit multiply-add per access
   const int ldy = LDYC ? LDYC : ldy_rt;
@@ -579,12 +589,13 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // resident weights -> TMEM: thread f of the first four epilogue warps owns row f of the A operand (lane f)
-  if (warp >= EPI0 && warp < EPI0 + 4) {
-    const int q = warp - EPI0, f = q * 32 + lane;
+  // resident weights -> TMEM: an epilogue warp (q, h) owns TMEM lanes 32q.. (rows f of the A operand) and stages the
+  // 32-column blocks h, h + NEW/4, ...: all epilogue warps load at once, so the prologue is one round of global latency
+  if (warp >= EPI0 && warp < MMAW) {
+    const int q = (warp - EPI0) & 3, hq = (warp - EPI0) >> 2, f = q * 32 + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < K; c0 += 32) {
+    for (int c0 = 32 * hq; c0 < K; c0 += 32 * (NEW / 4)) {
       uint32_t hi[32], lo[32];
       if constexpr (TRANS_W) {
 #pragma unroll
@@ -739,7 +750,8 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
         }
       } else {
         // whole points: columns [pp*JC, pp*JC + JC) of this warp's ECOLS are the jet of point pp at feature f
-        float* const ya = (EPI == EPI_ACT) ? Yact + r0 * ldy + n0 + f : nullptr;
+        float* const ya = (EPI == EPI_ACT && Yact != nullptr) ? Yact + r0 * ldy + n0 + f : nullptr;
+        const float wo = (EPI == EPI_ACT && of.w_out != nullptr) ? of.w_out[n0 + f] : 0.f;
 #pragma unroll
         for (int pp = 0; pp < ECOLS / JC; ++pp) {
           const int jb = pp * JC;
@@ -750,7 +762,8 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
               if (store_z) yp[jb * ldy] = z[0];
               if (ACT == 1) { y[0] = tanhf(z[0]); w[0] = 1.f - y[0] * y[0]; }
               else { z[0] *= omega; sincosf(z[0], &y[0], &w[0]); }
-              ya[jb * ldy] = y[0];
+              if (ya) ya[jb * ldy] = y[0];
+              acc[jb] = y[0] * wo;                                   // (the accumulator value is consumed: reuse the slot)
 #pragma unroll
               for (int d = 0; d < 2; ++d) {
                 const int KD = d ? K1 : K0, cb = jb + (d ? K0 : 0);
@@ -766,7 +779,10 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
                   else sincos_dir_fwd<MAXK, float>(KD, z, y, w);
 #pragma unroll
                   for (int k = 1; k <= MAXK; ++k)
-                    if (k <= KD) ya[(cb + k) * ldy] = y[k];
+                    if (k <= KD) {
+                      if (ya) ya[(cb + k) * ldy] = y[k];
+                      acc[cb + k] = y[k] * wo;
+                    }
                 }
               }
             } else if constexpr (EPI == EPI_ACTBWD_Y) {   // tanh adjoint from the stashed OUTPUT jets
@@ -833,6 +849,35 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
               yp[jb * ldy] = (ACT == 1) ? tanh_finish_bwd<float>(y[0], w[0], yb[0], wb0)
                                         : (yb[0] * w[0] - wb0 * y[0]) * omega;
             }
+          }
+        }
+        if constexpr (EPI == EPI_ACT) {
+          if (of.w_out != nullptr) {
+            // acc[j] = w_out[f] * y[row j, f]: sum over the 32 features of this warp.  Level with stride S halves the
+            // number of rows a lane carries; after the last level lanes 2r, 2r+1 both hold the sum of row r.
+            if (!FULL) {
+#pragma unroll
+              for (int j = 0; j < ECOLS; ++j) if (j >= nrows) acc[j] = 0.f;
+            }
+            constexpr int NLVL = (ECOLS == 16) ? 4 : 5;
+#pragma unroll
+            for (int lvl = 0; lvl < NLVL; ++lvl) {
+              const int S = 16 >> lvl, n = ECOLS >> lvl;
+              const bool upper = (lane & S) != 0;
+#pragma unroll
+              for (int i = 0; i < ECOLS / 2; ++i) {
+                if (i < n / 2) {
+                  const float a = acc[i], bq = acc[i + n / 2];
+                  const float send = upper ? a : bq, keep = upper ? bq : a;
+                  acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, S);
+                }
+              }
+            }
+#pragma unroll
+            for (int S = 32 / ECOLS / 2; S >= 1; S >>= 1) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], S);
+            const int rj = lane / (32 / ECOLS);
+            if ((lane % (32 / ECOLS)) == 0 && (FULL || rj < nrows))
+              of.u_part[(int64_t)(blockIdx.y * 4 + q) * M + r0 + rj] = acc[0];
           }
         }
       }
@@ -921,7 +966,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
 template <bool TRANS_W, int EPI, int ACT, int K0, int K1, bool ACCUM, int LDYC>
 static int launch_linear_rows_ts_inst(const float* X, const float* W, int ldw, const float* bias, float* Y, int64_t M, int n_cols,
                                       int jet_cols, const float* Zs, float* Yact, float omega, int sm_count, cudaStream_t st,
-                                      int ldx) {
+                                      int ldx, OutFuse of = OutFuse{}) {
   constexpr size_t smem = 1024 + (size_t)2 * 2 * 64 * 128 * 4 + (size_t)3 * 64 * 128 * 4 + (2 * 2 + 2 * 2 + 2 * 3) * 8 + 16;
   static_assert(smem <= 232448, "shared memory budget (227 KB per CTA)");
   constexpr int NLW = 8, ECOLS = (EPI == EPI_PLAIN) ? 32 : 16;
@@ -938,7 +983,7 @@ static int launch_linear_rows_ts_inst(const float* X, const float* W, int ldw, c
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     configured = true;
   }
-  kern<<<grid, threads, smem, st>>>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, ldx);
+  kern<<<grid, threads, smem, st>>>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, ldx, of);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -947,12 +992,12 @@ static int launch_linear_rows_ts_inst(const float* X, const float* W, int ldw, c
 template <bool TRANS_W, int EPI, int ACT, int K0, int K1>
 static int launch_linear_rows_ts(const float* X, const float* W, int ldw, const float* bias, float* Y, int64_t M, int n_cols,
                                  int jet_cols, const float* Zs, float* Yact, float omega, int sm_count, cudaStream_t st,
-                                 int ldx = 128, int accum = 0) {
+                                 int ldx = 128, int accum = 0, OutFuse of = OutFuse{}) {
   if (accum)
-    return launch_linear_rows_ts_inst<TRANS_W, EPI, ACT, K0, K1, true, 0>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, sm_count, st, ldx);
+    return launch_linear_rows_ts_inst<TRANS_W, EPI, ACT, K0, K1, true, 0>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, sm_count, st, ldx, of);
   if (n_cols == 128)
-    return launch_linear_rows_ts_inst<TRANS_W, EPI, ACT, K0, K1, false, 128>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, sm_count, st, ldx);
-  return launch_linear_rows_ts_inst<TRANS_W, EPI, ACT, K0, K1, false, 0>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, sm_count, st, ldx);
+    return launch_linear_rows_ts_inst<TRANS_W, EPI, ACT, K0, K1, false, 128>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, sm_count, st, ldx, of);
+  return launch_linear_rows_ts_inst<TRANS_W, EPI, ACT, K0, K1, false, 0>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, sm_count, st, ldx, of);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1268,11 +1313,11 @@ static int launch_wgrad(const float* G, const float* X, float* dW, float* db, in
 template <bool TRANS_W, int EPI, int ACT>
 static inline int tc_dispatch_jets(int k0, int k1, const float* X, const float* W, int ldw, const float* bias, float* Y,
                                    int64_t M, int n_cols, const float* Zs, float* Yact, float omega, int sm_count,
-                                   cudaStream_t st, int ldx = 128, int accum = 0) {
+                                   cudaStream_t st, int ldx = 128, int accum = 0, tc::OutFuse of = tc::OutFuse{}) {
 #define PK_TC_CASE(A, B)                                                                                         \
   if (k0 == A && k1 == B)                                                                                        \
     return tc::launch_linear_rows_ts<TRANS_W, EPI, ACT, A, B>(X, W, ldw, bias, Y, M, n_cols, 1 + A + B, Zs, Yact, omega, \
-                                                              sm_count, st, ldx, accum);
+                                                              sm_count, st, ldx, accum, of);
   PK_TC_CASE(0, 0) PK_TC_CASE(1, 0) PK_TC_CASE(2, 1) PK_TC_CASE(3, 0)
 #undef PK_TC_CASE
   return TC_UNSUPPORTED;
@@ -1312,8 +1357,13 @@ int tc_linear_fwd(const float* X, const float* W, const float* bias, float* Z, i
 }
 // Forward Linear + activation jets in one kernel: Z = X W^T + b (stash), Yact = act(Z).  act: 1 tanh, 2 sin(omega z).
 int tc_linear_act_fwd(const float* X, const float* W, const float* bias, float* Z, float* Yact, int64_t M, int K,
-                                    int N, int k0, int k1, int act, float omega, int sm_count, cudaStream_t st) {
+                                    int N, int k0, int k1, int act, float omega, int sm_count, cudaStream_t st,
+                                    const float* w_out, float* u_part) {
   if (M < 1 || (K != 128 && K != 256) || (N % 128) != 0 || !tc_jets_supported(k0, k1) || (act != 1 && act != 2)) return TC_UNSUPPORTED;
+  if (Yact == nullptr && w_out == nullptr) return TC_UNSUPPORTED;      // nothing would be produced
+  tc::OutFuse of;
+  of.w_out = w_out;
+  of.u_part = u_part;
   int accum = 0;
   if (K == 256) {
     if (Z == nullptr) return TC_UNSUPPORTED;       // the partial result needs a buffer
@@ -1321,8 +1371,8 @@ int tc_linear_act_fwd(const float* X, const float* W, const float* bias, float* 
     if (rc) return rc;
     X += 128; W += 128; accum = 1;
   }
-  if (act == 1) return tc_dispatch_jets<false, tc::EPI_ACT, 1>(k0, k1, X, W, K, bias, Z, M, N, nullptr, Yact, 1.f, sm_count, st, K, accum);
-  return tc_dispatch_jets<false, tc::EPI_ACT, 2>(k0, k1, X, W, K, bias, Z, M, N, nullptr, Yact, omega, sm_count, st, K, accum);
+  if (act == 1) return tc_dispatch_jets<false, tc::EPI_ACT, 1>(k0, k1, X, W, K, bias, Z, M, N, nullptr, Yact, 1.f, sm_count, st, K, accum, of);
+  return tc_dispatch_jets<false, tc::EPI_ACT, 2>(k0, k1, X, W, K, bias, Z, M, N, nullptr, Yact, omega, sm_count, st, K, accum, of);
 }
 #endif
 

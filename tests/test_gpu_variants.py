@@ -4,9 +4,11 @@
                                specialised first / last layer kernels
   PINNK_KEEP_Z=1               pre-activations stashed, adjoint from the stashed z jets
   PINNK_DISABLE_EDGE_FAST=1    generic (run-time jet layout) first / last layer kernels (also keeps the stash)
+  PINNK_DISABLE_OUT_FUSE=1     output layer nn.Linear(width, 1) as its own pass instead of folded into the last hidden
+                               layer's epilogue
   PINNK_DISABLE_TC=1           every GEMM on the exact-fp32 CUDA-core kernel, unfused activations
 
-All four must give the same residuals, loss components and parameter gradients to fp32 round-off; the model has one
+All five must give the same residuals, loss components and parameter gradients to fp32 round-off; the model has one
 layer scaled into saturation so that units with w0 = 1 - tanh^2 down to exactly 0 are exercised."""
 import os
 import subprocess
@@ -39,7 +41,8 @@ def test_optimised_routes_agree_with_plain_routes(tmp_path):
     build.build()
     base = _run(tmp_path, "default", {})
     exact = _run(tmp_path, "no_tc", {"PINNK_DISABLE_TC": "1"})
-    for tag, env in (("keep_z", {"PINNK_KEEP_Z": "1"}), ("generic_edges", {"PINNK_DISABLE_EDGE_FAST": "1"})):
+    for tag, env in (("keep_z", {"PINNK_KEEP_Z": "1"}), ("generic_edges", {"PINNK_DISABLE_EDGE_FAST": "1"}),
+                     ("separate_output_layer", {"PINNK_DISABLE_OUT_FUSE": "1"})):
         v = _run(tmp_path, tag, env)
         for k in base.files:
             assert np.all(np.isfinite(v[k])) and np.all(np.isfinite(base[k])), (tag, k)
