@@ -419,6 +419,13 @@ static bool out_fuse_enabled() {
   return v == 1 && tc_enabled();
 }
 
+// PINNK_DISABLE_FIRST_FUSE=1: reverse of the input layer as its own kernel after a plain dgrad (A/B checks)
+static bool first_fuse_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PINNK_DISABLE_FIRST_FUSE"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1 && tc_enabled();
+}
+
 static int first_trainable_op(const pinnk_plan_t pl) {
   const int n_ops = (int)pl->ops.size();
   for (int i = 0; i < n_ops; ++i)
@@ -649,6 +656,19 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad) {
               if (rc == 0) { g_launches.fetch_add(1); cur = nxt; --i; break; }
               if (rc != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, std::string("tc_linear_dgrad_actbwd launch failed: ") + cudaGetErrorString(cudaGetLastError()));
               if (from_y) return fail(PINNK_E_INVALID, "backward: pre-activation stash elided but the fused adjoint kernel refused the shape");
+            }
+            if (first_pair && first_fuse_enabled() && jet_orders(js, k0, k1)) {
+              // dgrad of the first hidden layer + the complete reverse of the input layer in one tcgen05 kernel:
+              // dL/dY0 is never written, dW0 / db0 accumulate in the epilogue's registers
+              ProfScope ps(PC_FIRST_BWD, c.st);
+              const PinnkOp& l0 = pl->ops[0].op;
+              rc = tc_linear_dgrad_firstbwd(c.adj(cur), W, c.n * js.ncols, o.in_dim, o.out_dim, k0, k1,
+                                            pa.op.act == PINNK_ACT_TANH ? 1 : 2, pa.op.scale, c.x, c.t, js.in_dim,
+                                            js.ndirs > 0 ? js.vec[0] : nullptr, js.ndirs > 1 ? js.vec[1] : nullptr,
+                                            c.params[l0.w_index], l0.b_index >= 0 ? c.params[l0.b_index] : nullptr,
+                                            G(l0.gw_offset), G(l0.gb_offset), pl->sm_count, c.st);
+              if (rc == 0) { g_launches.fetch_add(1); i = 0; break; }      // ops 1 (activation) and 0 (input layer) are done
+              if (rc != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, std::string("tc_linear_dgrad_firstbwd launch failed: ") + cudaGetErrorString(cudaGetLastError()));
             }
             rc = gemm_dgrad(c, c.adj(cur), W, c.adj(nxt), o.in_dim, o.out_dim);
             if (rc) return rc;

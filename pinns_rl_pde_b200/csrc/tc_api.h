@@ -30,6 +30,13 @@ int tc_linear_dgrad_actbwd(const float* dZ, const float* W, const float* Zprev, 
 inline bool tc_jets_supported(int k0, int k1) {
   return (k0 == 0 && k1 == 0) || (k0 == 1 && k1 == 0) || (k0 == 2 && k1 == 1) || (k0 == 3 && k1 == 0);
 }
+// dgrad of the first hidden layer fused with the complete reverse of the network's input layer
+// (nn.Linear(net_in_dim <= 4, in_dim) + activation): accumulates dW0 / db0, writes nothing else.  vec0 / vec1: direction
+// vectors (4 floats) of the two jet directions.
+int tc_linear_dgrad_firstbwd(const float* dZ, const float* W, int64_t M, int in_dim, int out_dim, int k0, int k1, int act,
+                             float omega, const float* x, const float* t, int net_in_dim, const float* vec0,
+                             const float* vec1, const float* W0, const float* b0, float* gW0, float* gb0, int sm_count,
+                             cudaStream_t st);
 // dW[out,in] += dZ[M,out]^T X[M,in] ;  db[out] += sum over value-column rows of dZ
 int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
                     int jet_cols, int sm_count, cudaStream_t st);

@@ -523,7 +523,27 @@ static __device__ unsigned long long g_stage_timers[16];
 // direction 1, with C = 1 + K0 + K1 dividing 32 so that every epilogue warp owns whole points.
 //   EPI_ACTBWD_Y  as EPI_ACTBWD for tanh, but Zs holds the activation OUTPUT jets (the forward pass then never writes the
 //               pre-activations: 512 B per row less traffic); z jets are recovered with tanh_dir_recover
-enum { EPI_PLAIN = 0, EPI_ACT = 1, EPI_ACTBWD = 2, EPI_ACTBWD_Y = 3 };
+enum { EPI_PLAIN = 0, EPI_ACT = 1, EPI_ACTBWD = 2, EPI_ACTBWD_Y = 3, EPI_FIRSTBWD = 4 };
+
+// EPI_FIRSTBWD: dgrad of the first HIDDEN layer fused with the whole reverse of the network's input layer
+// (nn.Linear(in_dim <= 4, width) + activation): the epilogue holds dL/dY0 jets of feature f, recomputes the input layer's
+// pre-activation jets from (x, t) -- z0 = b0[f] + W0[f,:] . xt, first-order coefficient W0[f,:] . vec_d, higher orders 0 --
+// runs the activation adjoint and accumulates dW0[f,:], db0[f] in registers over all tiles of the CTA (atomics at the end).
+// dL/dY0 is never written and the separate first-layer reverse kernel disappears.
+struct FirstLayer {
+  const float* x = nullptr;     // [n, in_dim - 1] with t given, else [n, in_dim]
+  const float* t = nullptr;     // [n] or null
+  const float* W0 = nullptr;    // [width, in_dim]
+  const float* b0 = nullptr;    // [width] or null
+  float* gW0 = nullptr;         // [width, in_dim] accumulated, or null
+  float* gb0 = nullptr;         // [width] accumulated, or null
+  int in_dim = 0;
+  float vec[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};   // direction vectors of the (at most two) jet directions
+};
+__device__ __forceinline__ float load_xt(const float* __restrict__ x, const float* __restrict__ t, int64_t p, int i, int in_dim) {
+  if (t == nullptr) return __ldg(x + p * in_dim + i);
+  return (i < in_dim - 1) ? __ldg(x + p * (in_dim - 1) + i) : __ldg(t + p);
+}
 
 // EPI_ACT only: the network's output layer (nn.Linear(width, 1)) folded into the epilogue of the last hidden layer.
 // Every epilogue warp reduces w_out[f] * y[row, f] over its 32 features (butterfly of 16 shuffles for 16 rows) and writes
@@ -539,7 +559,7 @@ template <bool TRANS_W, int EPI, int ACT, int K0, int K1, int NLW, int ECOLS, bo
 __global__ void __launch_bounds__((NLW + 4 * (64 / ECOLS) + 2) * 32, 1)
 linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
                       float* __restrict__ Y, int64_t M, int ldy_rt, int jet_cols, const float* __restrict__ Zs,
-                      float* __restrict__ Yact, float omega, int ldx, OutFuse of) {
+                      float* __restrict__ Yact, float omega, int ldx, OutFuse of, FirstLayer fl) {
   // LDYC: compile-time row stride of Y / Zs / Yact (0 = use the runtime value): with it every row address of the
   // epilogue is base + immediate instead of a 64-bit multiply-add per access
   const int ldy = LDYC ? LDYC : ldy_rt;
@@ -697,6 +717,20 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
     const float bf = (!TRANS_W && bias) ? bias[n0 + f] : 0.f;
     const bool store_z = (EPI != EPI_ACT) || (Y != nullptr);     // forward-only callers (scoring) pass no stash buffer
     const uint32_t lane_acc = tmem_base + ((uint32_t)(q * 32) << 16) + COL_ACC + (uint32_t)(h * ECOLS);
+    // EPI_FIRSTBWD: this thread's row of the input layer and its gradient accumulators
+    float w0r[4] = {0.f, 0.f, 0.f, 0.f}, z1d[2] = {0.f, 0.f}, aw0[4] = {0.f, 0.f, 0.f, 0.f}, ab0 = 0.f, b0f = 0.f;
+    if constexpr (EPI == EPI_FIRSTBWD) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w0r[i] = (i < fl.in_dim) ? fl.W0[(n0 + f) * fl.in_dim + i] : 0.f;
+      b0f = fl.b0 ? fl.b0[n0 + f] : 0.f;
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        float a = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a = fmaf(w0r[i], fl.vec[d][i], a);
+        z1d[d] = (ACT == 2) ? a * omega : a;
+      }
+    }
     // One tile of this warp.  FULL: all ECOLS rows exist, so no access is predicated and (with LDYC) every row address
     // is the tile base plus an immediate.
     long long t_ea = 0, t_eb = 0; (void)t_ea; (void)t_eb;
@@ -717,6 +751,15 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
         const float* const zs0 = Zs + r0 * ldy + n0 + f;
 #pragma unroll
         for (int j = 0; j < ECOLS; ++j) zsr[j] = (FULL || j < nrows) ? __ldg(zs0 + j * ldy) : 0.f;
+      }
+      float xin[(EPI == EPI_FIRSTBWD) ? ECOLS / JC : 1][4];
+      if constexpr (EPI == EPI_FIRSTBWD) {
+        const int64_t p0 = r0 / JC;                    // r0 is a multiple of JC (whole points per warp)
+#pragma unroll
+        for (int pp = 0; pp < ECOLS / JC; ++pp)
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            xin[pp][i] = (i < fl.in_dim && (FULL || pp * JC < nrows)) ? load_xt(fl.x, fl.t, p0 + pp, i, fl.in_dim) : 0.f;
       }
       // second K half of a 256-wide layer: the first half's partial result is in Y
       float part[ACCUM ? ECOLS : 1];
@@ -785,6 +828,44 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
                     }
                 }
               }
+            } else if constexpr (EPI == EPI_FIRSTBWD) {   // reverse of the input layer: nothing is written per row
+              float yb[MAXK + 1], zb[MAXK + 1], wb[MAXK + 1];
+              z[0] = b0f;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) z[0] = fmaf(w0r[i], xin[pp][i], z[0]);
+              if (ACT == 1) { y[0] = tanhf(z[0]); w[0] = 1.f - y[0] * y[0]; }
+              else { z[0] *= omega; sincosf(z[0], &y[0], &w[0]); }
+              yb[0] = acc[jb];
+              float wb0 = 0.f;
+#pragma unroll
+              for (int d = 0; d < 2; ++d) {
+                const int KD = d ? K1 : K0, cb = jb + (d ? K0 : 0);
+                if (KD > 0) {
+#pragma unroll
+                  for (int k = 1; k <= MAXK; ++k) {
+                    z[k] = (k == 1) ? z1d[d] : 0.f;
+                    yb[k] = (k <= KD) ? acc[cb + k] : 0.f;
+                  }
+                  if (ACT == 1) {
+                    tanh_dir_fwd<MAXK, float>(KD, z, y, w);
+                    tanh_dir_bwd<MAXK, float>(KD, z, y, w, yb, zb, wb0);
+                  } else {
+#pragma unroll
+                    for (int k = 0; k <= MAXK; ++k) wb[k] = 0.f;
+                    wb[0] = wb0;
+                    sincos_dir_fwd<MAXK, float>(KD, z, y, w);
+                    sincos_dir_bwd<MAXK, float>(KD, z, y, w, yb, wb, zb);
+                    wb0 = wb[0];
+                  }
+                  const float g1 = (ACT == 2) ? zb[1] * omega : zb[1];   // only the first-order pre-activation depends on W0
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) aw0[i] = fmaf(g1, fl.vec[d][i], aw0[i]);
+                }
+              }
+              const float g0 = (ACT == 1) ? tanh_finish_bwd<float>(y[0], w[0], yb[0], wb0) : (yb[0] * w[0] - wb0 * y[0]) * omega;
+              ab0 += g0;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) aw0[i] = fmaf(g0, xin[pp][i], aw0[i]);
             } else if constexpr (EPI == EPI_ACTBWD_Y) {   // tanh adjoint from the stashed OUTPUT jets
               float yb[MAXK + 1], zb[MAXK + 1];
               y[0] = zsr[jb];
@@ -891,6 +972,14 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
       if (M - r0 >= ECOLS) run_tile(std::true_type(), b, ph, r0, ECOLS);
       else run_tile(std::false_type(), b, ph, r0, (int)(M - r0 > 0 ? M - r0 : 0));
     }
+    if constexpr (EPI == EPI_FIRSTBWD) {
+      if (fl.gW0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < fl.in_dim) atomicAdd(fl.gW0 + (int64_t)(n0 + f) * fl.in_dim + i, aw0[i]);
+      }
+      if (fl.gb0) atomicAdd(fl.gb0 + n0 + f, ab0);
+    }
 #ifdef PINNK_STAGE_TIMERS
     if (blockIdx.x == 0 && blockIdx.y == 0 && e == 0 && lane == 0) {
       atomicAdd(&g_stage_timers[7], (unsigned long long)t_ea); atomicAdd(&g_stage_timers[8], (unsigned long long)t_eb);
@@ -966,7 +1055,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
 template <bool TRANS_W, int EPI, int ACT, int K0, int K1, bool ACCUM, int LDYC>
 static int launch_linear_rows_ts_inst(const float* X, const float* W, int ldw, const float* bias, float* Y, int64_t M, int n_cols,
                                       int jet_cols, const float* Zs, float* Yact, float omega, int sm_count, cudaStream_t st,
-                                      int ldx, OutFuse of = OutFuse{}) {
+                                      int ldx, OutFuse of = OutFuse{}, FirstLayer fl = FirstLayer{}) {
   constexpr size_t smem = 1024 + (size_t)2 * 2 * 64 * 128 * 4 + (size_t)3 * 64 * 128 * 4 + (2 * 2 + 2 * 2 + 2 * 3) * 8 + 16;
   static_assert(smem <= 232448, "shared memory budget (227 KB per CTA)");
   constexpr int NLW = 8, ECOLS = (EPI == EPI_PLAIN) ? 32 : 16;
@@ -983,7 +1072,7 @@ static int launch_linear_rows_ts_inst(const float* X, const float* W, int ldw, c
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     configured = true;
   }
-  kern<<<grid, threads, smem, st>>>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, ldx, of);
+  kern<<<grid, threads, smem, st>>>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, ldx, of, fl);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -992,12 +1081,12 @@ static int launch_linear_rows_ts_inst(const float* X, const float* W, int ldw, c
 template <bool TRANS_W, int EPI, int ACT, int K0, int K1>
 static int launch_linear_rows_ts(const float* X, const float* W, int ldw, const float* bias, float* Y, int64_t M, int n_cols,
                                  int jet_cols, const float* Zs, float* Yact, float omega, int sm_count, cudaStream_t st,
-                                 int ldx = 128, int accum = 0, OutFuse of = OutFuse{}) {
+                                 int ldx = 128, int accum = 0, OutFuse of = OutFuse{}, FirstLayer fl = FirstLayer{}) {
   if (accum)
-    return launch_linear_rows_ts_inst<TRANS_W, EPI, ACT, K0, K1, true, 0>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, sm_count, st, ldx, of);
+    return launch_linear_rows_ts_inst<TRANS_W, EPI, ACT, K0, K1, true, 0>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, sm_count, st, ldx, of, fl);
   if (n_cols == 128)
-    return launch_linear_rows_ts_inst<TRANS_W, EPI, ACT, K0, K1, false, 128>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, sm_count, st, ldx, of);
-  return launch_linear_rows_ts_inst<TRANS_W, EPI, ACT, K0, K1, false, 0>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, sm_count, st, ldx, of);
+    return launch_linear_rows_ts_inst<TRANS_W, EPI, ACT, K0, K1, false, 128>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, sm_count, st, ldx, of, fl);
+  return launch_linear_rows_ts_inst<TRANS_W, EPI, ACT, K0, K1, false, 0>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, sm_count, st, ldx, of, fl);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1313,11 +1402,12 @@ static int launch_wgrad(const float* G, const float* X, float* dW, float* db, in
 template <bool TRANS_W, int EPI, int ACT>
 static inline int tc_dispatch_jets(int k0, int k1, const float* X, const float* W, int ldw, const float* bias, float* Y,
                                    int64_t M, int n_cols, const float* Zs, float* Yact, float omega, int sm_count,
-                                   cudaStream_t st, int ldx = 128, int accum = 0, tc::OutFuse of = tc::OutFuse{}) {
+                                   cudaStream_t st, int ldx = 128, int accum = 0, tc::OutFuse of = tc::OutFuse{},
+                                   tc::FirstLayer fl = tc::FirstLayer{}) {
 #define PK_TC_CASE(A, B)                                                                                         \
   if (k0 == A && k1 == B)                                                                                        \
     return tc::launch_linear_rows_ts<TRANS_W, EPI, ACT, A, B>(X, W, ldw, bias, Y, M, n_cols, 1 + A + B, Zs, Yact, omega, \
-                                                              sm_count, st, ldx, accum, of);
+                                                              sm_count, st, ldx, accum, of, fl);
   PK_TC_CASE(0, 0) PK_TC_CASE(1, 0) PK_TC_CASE(2, 1) PK_TC_CASE(3, 0)
 #undef PK_TC_CASE
   return TC_UNSUPPORTED;
@@ -1402,6 +1492,21 @@ int tc_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t M, int i
   }
   if (out_dim == 128) return tc::launch_linear_rows<128, 32, 3, 3, 8, 3, true>(dZ, W, in_dim, nullptr, dX, M, in_dim, 1, sm_count, st);
   return TC_UNSUPPORTED;
+}
+// dgrad of the first hidden layer + the whole reverse of the input layer (EPI_FIRSTBWD)
+int tc_linear_dgrad_firstbwd(const float* dZ, const float* W, int64_t M, int in_dim, int out_dim, int k0, int k1, int act,
+                             float omega, const float* x, const float* t, int net_in_dim, const float* vec0,
+                             const float* vec1, const float* W0, const float* b0, float* gW0, float* gb0, int sm_count,
+                             cudaStream_t st) {
+  if (M < 1 || (out_dim != 128 && out_dim != 256) || (in_dim % 128) != 0 || !tc_jets_supported(k0, k1) || (act != 1 && act != 2) ||
+      net_in_dim < 1 || net_in_dim > 4)
+    return TC_UNSUPPORTED;
+  tc::FirstLayer fl;
+  fl.x = x; fl.t = t; fl.W0 = W0; fl.b0 = b0; fl.gW0 = gW0; fl.gb0 = gb0; fl.in_dim = net_in_dim;
+  for (int i = 0; i < 4; ++i) { fl.vec[0][i] = vec0 ? vec0[i] : 0.f; fl.vec[1][i] = vec1 ? vec1[i] : 0.f; }
+  if (out_dim == 256) return TC_UNSUPPORTED;      // (two K halves would need a partial-sum buffer: not wired up)
+  if (act == 1) return tc_dispatch_jets<true, tc::EPI_FIRSTBWD, 1>(k0, k1, dZ, W, in_dim, nullptr, nullptr, M, in_dim, nullptr, nullptr, 1.f, sm_count, st, out_dim, 0, tc::OutFuse{}, fl);
+  return tc_dispatch_jets<true, tc::EPI_FIRSTBWD, 2>(k0, k1, dZ, W, in_dim, nullptr, nullptr, M, in_dim, nullptr, nullptr, omega, sm_count, st, out_dim, 0, tc::OutFuse{}, fl);
 }
 // dgrad + activation adjoint in one kernel: dZprev = act'(Zprev)^T (dZ W)
 int tc_linear_dgrad_actbwd(const float* dZ, const float* W, const float* Zprev, float* dZprev, int64_t M,
