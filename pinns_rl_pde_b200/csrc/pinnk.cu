@@ -480,7 +480,7 @@ static int forward_chunk(const ChunkCtx& c, bool keep_stash = true) {
           const unsigned blocks = blocks_for(c.n * o.out_dim, threads);
           int ek0 = 0, ek1 = 0;
           if (edge_fast_enabled() && (o.out_dim % 128) == 0 && jet_orders(js, ek0, ek1)) {
-            constexpr int PPT = 2;
+            constexpr int PPT = 4;
             dim3 grid((unsigned)(o.out_dim / 128), (unsigned)std::min<int64_t>((c.n + PPT - 1) / PPT, 16 * (int64_t)pl->sm_count));
             const bool tanh_act = a.act == PINNK_ACT_TANH;
             const bool ok = dispatch_edge_jets(ek0, ek1, [&](auto ka, auto kb) {

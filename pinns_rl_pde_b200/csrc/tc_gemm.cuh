@@ -1181,50 +1181,67 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
     const int rq = warp & 7, sel = warp >> 3;
     float bsum[4] = {0.f, 0.f, 0.f, 0.f};
     const bool want_b = (db != nullptr) && (i0 == 0) && sel == 0;
+    // value rows of this warp's quad: tiles start at multiples of 32 rows, so for jet_cols in {1, 2, 4} the pattern is fixed
+    const bool b_fixed = (jet_cols == 1 || jet_cols == 2 || jet_cols == 4);
+    const uint32_t b_mask = (jet_cols == 1) ? 0xFu : (jet_cols == 2) ? 0x5u : 0x1u;
     const uint32_t ob = smem_u32(op_base), rb = smem_u32(raw_base);
+    // everything that does not depend on the tile is hoisted: raw read offset of this lane, swizzled store offsets
+    const uint32_t lane_raw = (uint32_t)sel * RAW_BYTES + (uint32_t)(rq * 4) * 512u + (uint32_t)lane * 4u;
+    uint32_t off_e[4];                                        // K-major SW128: row = feature, 16-byte chunk = row quad
+#pragma unroll
+    for (int e = 0; e < 4; ++e) off_e[e] = (uint32_t)sel * 2 * OP_BYTES + sw128_offset(128, lane + 32 * e, rq);
     long long t_a = 0, t_b = 0, t_c = 0; (void)t_a; (void)t_b; (void)t_c;
-    int it = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      const int rs = it % RS, os = it % OS;
-      const uint32_t rph = (uint32_t)(it / RS) & 1u, oph = (uint32_t)(it / OS) & 1u;
+    int rs = 0, os = 0;
+    uint32_t rph = 0, oph = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int64_t r0 = tile * TK;
       const int nrows = (M - r0 >= TK) ? TK : (int)(M - r0);
       { PK_T0(); mbar_wait(&raw_full[rs], rph); PK_TACC(t_a); }
       PK_T0();
-      const uint32_t raw = rb + (uint32_t)rs * 2 * RAW_BYTES + (uint32_t)sel * RAW_BYTES;
+      const uint32_t raw = rb + (uint32_t)rs * 2 * RAW_BYTES + lane_raw;
       float v[4][4];                                       // [row of the quad][feature e]
+      if (nrows == TK) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) {
-        const int row = rq * 4 + r;
+        for (int r = 0; r < 4; ++r)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float x = 0.f;
-          if (row < nrows) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(raw + row * 512 + (lane + 32 * e) * 4));
-          v[r][e] = x;
-        }
+          for (int e = 0; e < 4; ++e)
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[r][e]) : "r"(raw + (uint32_t)(r * 512 + e * 128)));
+      } else {
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = 0.f;
+            if (rq * 4 + r < nrows) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(raw + (uint32_t)(r * 512 + e * 128)));
+            v[r][e] = x;
+          }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&raw_empty[rs]);                 // raw data is in registers: slot may be refilled
       PK_TACC(t_c);
       { PK_T0(); mbar_wait(&empty[os], oph ^ 1u); PK_TACC(t_b); }
       const long long _t1 = clock64(); (void)_t1;
-      const uint32_t hi_base = ob + (uint32_t)os * 4 * OP_BYTES + (uint32_t)sel * 2 * OP_BYTES, lo_base = hi_base + OP_BYTES;
+      const uint32_t hi_base = ob + (uint32_t)os * 4 * OP_BYTES, lo_base = hi_base + OP_BYTES;
       if (want_b) {
-        uint32_t cj = (uint32_t)((uint32_t)(r0 + rq * 4) % (uint32_t)jet_cols);
+        if (b_fixed) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          if (cj == 0) { bsum[0] += v[r][0]; bsum[1] += v[r][1]; bsum[2] += v[r][2]; bsum[3] += v[r][3]; }
-          cj = (cj + 1 == (uint32_t)jet_cols) ? 0u : cj + 1;
+          for (int r = 0; r < 4; ++r)
+            if ((b_mask >> r) & 1u) { bsum[0] += v[r][0]; bsum[1] += v[r][1]; bsum[2] += v[r][2]; bsum[3] += v[r][3]; }
+        } else {
+          uint32_t cj = (uint32_t)((uint32_t)(r0 + rq * 4) % (uint32_t)jet_cols);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            if (cj == 0) { bsum[0] += v[r][0]; bsum[1] += v[r][1]; bsum[2] += v[r][2]; bsum[3] += v[r][3]; }
+            cj = (cj + 1 == (uint32_t)jet_cols) ? 0u : cj + 1;
+          }
         }
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int f = lane + 32 * e;
         uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
         split_bits(v[0][e], h0, l0); split_bits(v[1][e], h1, l1); split_bits(v[2][e], h2, l2); split_bits(v[3][e], h3, l3);
-        const uint32_t off = sw128_offset(128, f, rq);            // K-major SW128: row = feature, 16-byte chunk = row quad
-        sts128(hi_base + off, h0, h1, h2, h3);
-        sts128(lo_base + off, l0, l1, l2, l3);
+        sts128(hi_base + off_e[e], h0, h1, h2, h3);
+        sts128(lo_base + off_e[e], l0, l1, l2, l3);
       }
       fence_proxy_async();
       __syncwarp();
@@ -1232,6 +1249,8 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
 #ifdef PINNK_STAGE_TIMERS
       t_c += clock64() - _t1;
 #endif
+      if (++rs == RS) { rs = 0; rph ^= 1u; }
+      if (++os == OS) { os = 0; oph ^= 1u; }
     }
 #ifdef PINNK_STAGE_TIMERS
     if (blockIdx.x == 0 && blockIdx.y == 0 && warp == 0 && lane == 0) {
