@@ -340,6 +340,90 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------- secondary workload: sharded scoring
+def run_score(args):
+    """BASELINE configs[4] (not the headline line; `--workload score`): Allen-Cahn, feed-forward 8x128, forward-only
+    residual scoring of a candidate pool sharded over the ranks (parallel.sharded_score: per-rank |r| and statistics, two
+    tiny collectives for the global statistics).  Weak scaling: --points candidates per GPU (default 8M = 64M / 8)."""
+    import torch.distributed as dist
+    import pinns_rl_pde_b200 as pk
+    from pinns_rl_pde_b200 import _lib, parallel
+    import __graft_entry__ as ge
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    torch.manual_seed(0)
+    model = pk.make_model("feedforward", 2, HIDDEN, LAYERS, dev)
+    cfg = pk.PDEConfig(name="allen_cahn", domain=[[-1.0, 1.0]], time_domain=[0.0, 1.0], parameters={"epsilon": 0.1},
+                       boundary_conditions={"dirichlet": {"value": 0.0}}, initial_condition={"type": "tanh", "epsilon": 0.1},
+                       exact_solution={}, dimension=1, device=dev)
+    pde = pk.create_pde("allen_cahn", cfg)
+    n = args.points if args.points != (1 << 20) else (1 << 23)
+    xh, th = synth_points(n, 1 + rank)
+    xh, th = xh.pin_memory(), th.pin_memory()
+    x, t = xh.to(dev), th.to(dev)
+
+    def step(xd, td):
+        return parallel.sharded_score(pde, model, xd, td, want_abs=True)[1]
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        sync()
+        tt = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    for _ in range(args.warmup):
+        step(x, t)
+    l0 = _lib.launch_count()
+    ms = timed(lambda: step(x, t), args.steps)
+    launches = _lib.launch_count() - l0
+    xd, td = torch.empty_like(x), torch.empty_like(t)
+
+    def e2e_step():
+        xd.copy_(xh, non_blocking=True)
+        td.copy_(th, non_blocking=True)
+        return step(xd, td).cpu()
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "candidate points/sec (forward residual scoring)", "value": n * world * args.steps / (ms * 1e-3),
+            "unit": "points/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "Allen-Cahn eps=0.1, feedforward tanh 8x128, candidate residual scoring sharded over the "
+                                   "GPUs (BASELINE configs[4])", "points_per_gpu": n, "global_points": n * world,
+                       "jet_columns": JET_COLS, "l2": "inputs (64 MB per GPU) and per-layer tensors (2 GB per chunk) exceed the 126 MB L2",
+                       "parallelism": f"dp{world} (candidates sharded; global statistics by two 32-byte all-reduces)"},
+            "e2e": {"value": n * world * args.steps / (ms_e2e * 1e-3), "unit": "points/s",
+                    "h2d_bytes_per_step": int(xh.numel() * 4 + th.numel() * 4), "d2h_bytes_per_step": 32},
+            "gpu_launches": int(launches)}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -349,9 +433,13 @@ def main():
     ap.add_argument("--points", type=int, default=1 << 20, help="collocation rows per GPU")
     ap.add_argument("--unfused", action="store_true", help="autograd route: compute_loss().backward() + torch clip/Adam")
     ap.add_argument("--lite", action="store_true", help="timed steps only (for runs under ncu): no e2e / roofline / cpu passes")
+    ap.add_argument("--workload", default="train", choices=["train", "score"],
+                    help="train = the headline metric (BASELINE configs[1]); score = sharded candidate scoring (configs[4])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "score":
+        run_score(args)
     else:
         run_ours(args)
 

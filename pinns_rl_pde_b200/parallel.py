@@ -83,3 +83,74 @@ def sharded_loss_backward(pde, model: nn.Module, x: torch.Tensor, t: torch.Tenso
     zero = torch.zeros((), device=flat.device)
     return {"residual": sums[0], "boundary": sums[1], "initial": sums[2], "smoothness": zero, "data": zero.clone(),
             "total": w_res * sums[0] + w_bc * sums[1] + w_ic * sums[2]}
+
+
+# ---------------------------------------------------------------------------------- sharded residual scoring
+def sharded_score(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, want_abs: bool = True, group=None,
+                  score_fn: Optional[Callable] = None):
+    """Forward-only residual scoring of a candidate set sharded over the ranks (the callers are
+    pde_base.py:895-935 RAR, :1364-1377 the RL reward, trainer.py:210-262 live snapshots).
+
+    ``x, t`` are THIS rank's candidates.  Returns ``(abs_r_local, stats)``: ``|r|`` of the local candidates (or None)
+    and the GLOBAL statistics ``[sum|r|, sum r^2, max|r|, count]`` (fp64), reduced with two tiny collectives
+    (sum of 3 doubles, max of 1).  The scores themselves never move.  ``score_fn`` (tests only) replaces
+    functional.score_residual."""
+    from . import functional as F
+    fn = score_fn or F.score_residual
+    mag, stats = fn(pde, model, x, t, want_abs)
+    stats = stats.to(torch.float64).clone()
+    if world_size() > 1:
+        sums = torch.stack([stats[0], stats[1], stats[3]])
+        mx = stats[2:3].clone()
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+        stats = torch.stack([sums[0], sums[1], mx[0], sums[2]])
+    return mag, stats
+
+
+def sharded_residual_sample(pde, model: nn.Module, x_pool: torch.Tensor, t_pool: torch.Tensor, num_points: int,
+                            gather: bool = False, generator: Optional[torch.Generator] = None, group=None,
+                            score_fn: Optional[Callable] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Residual-adaptive refinement over a candidate pool sharded over the ranks (pde_base.py:895-935 on N GPUs).
+
+    The reference draws ``num_points`` candidates with probability proportional to ``|r| + 1e-8`` from ONE pool.  Here the
+    draw is two-level and exact in distribution: (1) every rank computes the mass of its shard, the W masses are
+    all-gathered, and the per-rank sample counts are drawn from the multinomial over shard masses -- by rank 0,
+    broadcast, so that all ranks agree; (2) each rank draws its count locally, proportionally to its own scores
+    (``multinomial_large``, no 2^24 limit).  Only W doubles and W integers cross the fabric.
+
+    Returns this rank's selected ``(x, t)`` (the data-parallel trainer consumes per-rank shards directly), or with
+    ``gather=True`` the whole selection on every rank (``num_points`` rows, rank order)."""
+    from .pdes import multinomial_large
+    w, r = world_size(), rank()
+    mag, _ = sharded_score(pde, model, x_pool, t_pool, True, group, score_fn)
+    wts = mag.reshape(-1).to(torch.float32) + 1e-8
+    mass = wts.sum(dtype=torch.float64).reshape(1)
+    if w > 1:
+        masses = [torch.zeros_like(mass) for _ in range(w)]
+        dist.all_gather(masses, mass, group=group)
+        masses = torch.cat(masses)
+        counts = torch.zeros(w, dtype=torch.int64, device=mass.device)
+        if r == 0:
+            p = (masses / masses.sum()).to(torch.float32).cpu()
+            which = torch.multinomial(p, num_points, replacement=True, generator=generator)
+            counts = torch.bincount(which, minlength=w).to(mass.device)
+        dist.broadcast(counts, 0, group=group)
+        k = int(counts[r].item())
+    else:
+        k = int(num_points)
+    if k > 0:
+        sel = multinomial_large(wts, k)
+        xs, ts = x_pool[sel].detach(), t_pool[sel].detach()
+    else:
+        xs, ts = x_pool[:0].detach(), t_pool[:0].detach()
+    if not gather or w == 1:
+        return xs, ts
+    # variable-size all-gather of the (small) selection: pad to the largest count
+    kmax = int(counts.max().item())
+    pad = torch.zeros(kmax, x_pool.shape[1] + 1, dtype=x_pool.dtype, device=x_pool.device)
+    pad[:k, :-1], pad[:k, -1:] = xs, ts
+    bufs = [torch.zeros_like(pad) for _ in range(w)]
+    dist.all_gather(bufs, pad, group=group)
+    allp = torch.cat([b[:int(counts[i].item())] for i, b in enumerate(bufs)], dim=0)
+    return allp[:, :-1].contiguous(), allp[:, -1:].contiguous()

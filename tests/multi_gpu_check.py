@@ -37,6 +37,16 @@ def main():
     dl = abs(losses["total"].item() - ref["total"].item()) / abs(ref["total"].item())
     ok = err < 5e-6 and dl < 5e-6
     print(f"rank {dist.get_rank()}/{dist.get_world_size()}: sharded-vs-single grad rel {err:.2e}, loss rel {dl:.2e} -> {'OK' if ok else 'FAIL'}")
+    # sharded candidate scoring: global statistics equal the single-GPU ones; the two-level RAR draw returns the request
+    ac = product_pde("allen_cahn", dev)
+    lo, hi = parallel.shard_bounds(n)
+    _, st_sh = parallel.sharded_score(ac, model, x[lo:hi], t[lo:hi])
+    _, st_1 = ac.score_residual(model, x, t)
+    ds = float(((st_sh - st_1).abs() / st_1.abs().clamp_min(1e-30)).max())
+    xs, ts = parallel.sharded_residual_sample(ac, model, x[lo:hi], t[lo:hi], 4096, gather=True)
+    ok2 = ds < 1e-6 and xs.shape == (4096, 1) and ts.shape == (4096, 1)
+    print(f"rank {dist.get_rank()}: sharded score stats rel {ds:.2e}, RAR selection {tuple(xs.shape)} -> {'OK' if ok2 else 'FAIL'}")
+    ok = ok and ok2
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

@@ -102,3 +102,71 @@ def test_multinomial_large_matches_distribution():
     counts = torch.stack([(sel2 == h).sum() for h in hot]).double()
     assert counts.sum() == 60000
     assert torch.allclose(counts / 60000, torch.tensor([1 / 6, 2 / 6, 3 / 6], dtype=torch.float64), atol=0.01)
+
+
+# ---------------------------------------------------------------------------------- sharded residual scoring / RAR
+def _stub_score(pde, model, x, t, want_abs=True):
+    """Stand-in for functional.score_residual (same return contract): r = x^3 * (1 + t)."""
+    r = (x.double() ** 3 * (1 + t.double())).reshape(-1)
+    a = r.abs()
+    stats = torch.stack([a.sum(), (r * r).sum(), a.max() if a.numel() else torch.zeros((), dtype=torch.float64),
+                         torch.tensor(float(a.numel()), dtype=torch.float64)])
+    return (a.to(torch.float32) if want_abs else None), stats
+
+
+def _pool(n):
+    g = torch.Generator().manual_seed(5)
+    return torch.rand(n, 1, generator=g) * 2 - 1, torch.rand(n, 1, generator=g)
+
+
+def _score_worker(rank, world, port, n, k, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pinns_rl_pde_b200 import parallel
+        x, t = _pool(n)
+        lo, hi = parallel.shard_bounds(n)
+        mag, stats = parallel.sharded_score(None, None, x[lo:hi], t[lo:hi], score_fn=_stub_score)
+        assert mag.shape[0] == hi - lo
+        torch.manual_seed(100 + rank)
+        xs, ts = parallel.sharded_residual_sample(None, None, x[lo:hi], t[lo:hi], k, gather=True,
+                                                  generator=torch.Generator().manual_seed(9), score_fn=_stub_score)
+        xl, tl = parallel.sharded_residual_sample(None, None, x[lo:hi], t[lo:hi], k, gather=False,
+                                                  generator=torch.Generator().manual_seed(9), score_fn=_stub_score)
+        cnt = torch.tensor([xl.shape[0]])
+        dist.all_reduce(cnt)
+        assert int(cnt) == k                                  # the per-rank draws add up to the request
+        if rank == 0:
+            torch.save({"stats": stats, "xs": xs, "ts": ts}, out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_score_and_two_level_rar_sampling(tmp_path):
+    n, k = 20001, 40000
+    out = str(tmp_path / "score.pt")
+    mp.spawn(_score_worker, args=(2, _free_port(), n, k, out), nprocs=2, join=True)
+    got = torch.load(out)
+    x, t = _pool(n)
+    mag, stats = _stub_score(None, None, x, t)
+    assert torch.allclose(got["stats"], stats, rtol=1e-12)                     # global statistics = single-process ones
+    xs, ts = got["xs"], got["ts"]
+    assert xs.shape == (k, 1) and ts.shape == (k, 1)
+    # every selected point is a pool point, and the selection follows |r| + 1e-8: compare the mass drawn from the
+    # region |x| > 0.8 (which carries most of the |x|^3 weight) with its exact probability
+    pool = {(round(float(a), 6), round(float(b), 6)) for a, b in zip(x[:, 0], t[:, 0])}
+    assert all((round(float(a), 6), round(float(b), 6)) in pool for a, b in zip(xs[:200, 0], ts[:200, 0]))
+    w = mag.double() + 1e-8
+    p_hot = float(w[(x[:, 0].abs() > 0.8)].sum() / w.sum())
+    f_hot = float((xs[:, 0].abs() > 0.8).double().mean())
+    assert abs(f_hot - p_hot) < 0.01, (f_hot, p_hot)
+
+
+def test_sharded_score_single_process_is_plain_score():
+    from pinns_rl_pde_b200 import parallel
+    x, t = _pool(1000)
+    mag, stats = parallel.sharded_score(None, None, x, t, score_fn=_stub_score)
+    m2, s2 = _stub_score(None, None, x, t)
+    assert torch.equal(mag, m2) and torch.equal(stats, s2)
+    xs, ts = parallel.sharded_residual_sample(None, None, x, t, 50, score_fn=_stub_score)
+    assert xs.shape == (50, 1) and ts.shape == (50, 1)
