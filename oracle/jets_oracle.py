@@ -169,8 +169,8 @@ def jet_spec(pde: str, dimension: int = 1, compat: str = "reference"):
     t_dir = (e(d), 1)
     if d == 1:
         order = {"heat": 1 if compat == "reference" else 2, "burgers": 2, "kdv": 3,
-                 "allen_cahn": 2, "cahn_hilliard": 4}[pde]
-        return [(e(0), order), t_dir]
+                 "allen_cahn": 2, "cahn_hilliard": 4, "wave": 2, "convection": 1}[pde]
+        return [(e(0), order), (e(d), 2) if pde == "wave" else t_dir]
     if compat == "reference":
         # every multi-dim residual degenerates; only u and u_t enter.
         return [t_dir]
@@ -200,6 +200,11 @@ def residual_from_jet(pde: str, j: Jet, params: Dict[str, float], dimension: int
             e2 = params.get("epsilon", 0.1) ** 2
             inside = (u.abs() <= 10.0).to(u.dtype)
             return u_t + e2 * D(0, 4) - inside * ((3 * u * u - 1) * D(0, 2) + 6 * u * D(0, 1) ** 2)
+        if pde == "wave":
+            return D(1, 2) - params.get("c", 1.0) ** 2 * D(0, 2)
+        if pde == "convection":
+            v = params.get("velocity", 1.0)
+            return u_t + (v[0] if isinstance(v, (list, tuple)) else v) * D(0, 1)
         raise NotImplementedError(pde)
     if compat == "reference":
         u_t = D(0, 1)

@@ -343,9 +343,37 @@ def cahn_hilliard_residual(model, x, t, epsilon=0.1, dimension=1):
     return u_t - _laplacian_inline(mu, x, dimension)
 
 
+def wave_residual(model, x, t, c=1.0, dimension=1):
+    """wave_equation.py:38-119 (1-D branch): r = u_tt - c^2 u_xx; mutates the caller's x, t (no detach, :50-51)."""
+    if dimension != 1:
+        raise NotImplementedError("wave: 1-D only in the oracle")
+    x = x.requires_grad_(True)
+    t = t.requires_grad_(True)
+    u = model(torch.cat([x, t], dim=1))
+    u_t = _grad(u, t)
+    u_tt = _grad(u_t, t)
+    u_x = _grad(u, x)
+    u_xx = _grad(u_x, x)
+    return u_tt - c ** 2 * u_xx
+
+
+def convection_residual(model, x, t, velocity=1.0, dimension=1):
+    """convection_equation.py:43-78 (1-D branch): r = u_t + v u_x."""
+    if dimension != 1:
+        raise NotImplementedError("convection: 1-D only in the oracle")
+    x = x.detach().requires_grad_(True)
+    t = t.detach().requires_grad_(True)
+    u = model(torch.cat([x, t], dim=1))
+    u_t = torch.autograd.grad(u, t, grad_outputs=torch.ones_like(u), create_graph=True)[0]
+    u_x = torch.autograd.grad(u, x, grad_outputs=torch.ones_like(u), create_graph=True)[0]
+    v = velocity[0] if isinstance(velocity, (list, tuple)) else velocity
+    return u_t + v * u_x
+
+
 RESIDUALS: Dict[str, Callable] = {
     "heat": heat_residual, "burgers": burgers_residual, "kdv": kdv_residual,
     "allen_cahn": allen_cahn_residual, "cahn_hilliard": cahn_hilliard_residual,
+    "wave": wave_residual, "convection": convection_residual,
 }
 
 
@@ -388,6 +416,13 @@ def initial_condition_fn(pde: str, ic: Dict, domain, params: Dict, dimension: in
             raise ValueError(f"Unsupported initial condition type: {kind}")
         c = torch.tensor(ic.get("speed", params.get("speed", 1.0)), dtype=torch.float32)
         return lambda x, t: 2 * c * (1 / torch.cosh(torch.sqrt(c) * x)) ** 2
+    if pde in ("wave", "convection"):
+        # wave_equation.py:138-169, convection_equation.py:97-119
+        kind = ic.get("type", "sine")
+        if kind == "sine" or (pde == "convection" and kind == "sin"):
+            A, k = ic.get("amplitude", 1.0), ic.get("frequency", 2.0)
+            return lambda x, t: A * torch.sin(k * torch.pi * x)
+        raise ValueError(f"Unsupported initial condition type: {kind}")
     if pde in ("allen_cahn", "cahn_hilliard"):
         kind = ic.get("type", "tanh")
         if kind == "tanh":

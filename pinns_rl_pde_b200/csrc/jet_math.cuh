@@ -207,6 +207,8 @@ enum PdeKind : int {
   PDE_CAHN_HILLIARD_2D = 7,// intended 2-D operator from x, y, x+y, x-y order-4 jets (+t)
   PDE_VALUE = 8,           // r = u              (BC/IC rows: error is u - target)
   PDE_DX = 9,              // r = u_x            (Heat periodic BC derivative match)
+  PDE_WAVE = 10,           // r = u_tt - c^2 u_xx          (1-D; spec [x order 2, t order 2])   wave_equation.py:38-119
+  PDE_CONVECTION = 11,     // r = u_t + v u_x              (1-D; spec [x order 1, t order 1])   convection_equation.py:43-78
 };
 
 struct PdeDesc {
@@ -266,6 +268,15 @@ PK_HD T pde_residual(const PdeDesc& pd, const JetSpec& js, const T* U, T* dU) {
       if (pd.compat_math) { if (dU) { dU[ct] = T(1); dU[cx + 1] = -T(2) * p0; } return u_t - p0 * T(2) * U[cx + 1]; }
       if (dU) { dU[ct] = T(1); dU[cx] = -p0; }
       return u_t - p0 * U[cx];
+    }
+    case PDE_WAVE: {       // spec [x order 2, t order 2]: u_tt = 2 a_t2, u_xx = 2 a_x2
+      const T c2 = p0 * p0;
+      if (dU) { dU[ct + 1] = T(2); dU[cx + 1] = -T(2) * c2; }
+      return T(2) * U[ct + 1] - c2 * T(2) * U[cx + 1];
+    }
+    case PDE_CONVECTION: {
+      if (dU) { dU[ct] = T(1); dU[cx] = p0; }
+      return u_t + p0 * U[cx];
     }
     case PDE_BURGERS: {
       const T ux = U[cx], uxx = T(2) * U[cx + 1];

@@ -18,7 +18,8 @@ _PATCHED = {}
 
 def patch_reference(compat: str = "reference"):
     mods = {"heat_equation": "HeatEquation", "burgers_equation": "BurgersEquation", "kdv_equation": "KdVEquation",
-            "allen_cahn": "AllenCahnEquation", "cahn_hilliard": "CahnHilliardEquation"}
+            "allen_cahn": "AllenCahnEquation", "cahn_hilliard": "CahnHilliardEquation",
+            "wave_equation": "WaveEquation", "convection_equation": "ConvectionEquation"}
     try:
         base = importlib.import_module("pinnrl.pdes.pde_base")
     except ImportError as e:   # pragma: no cover - pinnrl is not installed on the GPU box

@@ -24,10 +24,12 @@ from .engine import Segment, get_engine, get_program
 _PDE_NAMES = {
     "HeatEquation": "heat", "BurgersEquation": "burgers", "KdVEquation": "kdv",
     "AllenCahnEquation": "allen_cahn", "CahnHilliardEquation": "cahn_hilliard",
+    "WaveEquation": "wave", "ConvectionEquation": "convection",
 }
-_ORDER_1D = {"burgers": 2, "kdv": 3, "allen_cahn": 2, "cahn_hilliard": 4}
+_ORDER_1D = {"burgers": 2, "kdv": 3, "allen_cahn": 2, "cahn_hilliard": 4, "wave": 2, "convection": 1}
 _KIND_1D = {"heat": L.PDE_HEAT, "burgers": L.PDE_BURGERS, "kdv": L.PDE_KDV,
-            "allen_cahn": L.PDE_ALLEN_CAHN, "cahn_hilliard": L.PDE_CAHN_HILLIARD}
+            "allen_cahn": L.PDE_ALLEN_CAHN, "cahn_hilliard": L.PDE_CAHN_HILLIARD,
+            "wave": L.PDE_WAVE, "convection": L.PDE_CONVECTION}
 
 
 class UnsupportedPDE(NotImplementedError):
@@ -56,6 +58,18 @@ def _float_param(pde, name: str, default=None) -> float:
     return float(v)
 
 
+def _velocity_1d(pde) -> float:
+    """convection_equation.py:34-41: scalar or per-dimension list under ``velocity``."""
+    v = pde.get_parameter("velocity", default=1.0) if hasattr(pde, "get_parameter") else getattr(pde, "velocity", 1.0)
+    if isinstance(v, (list, tuple)):
+        v = v[0]
+    if isinstance(v, torch.Tensor):
+        if v.requires_grad:
+            raise UnsupportedPDE("trainable PDE parameters (inverse mode) are not supported by the fused path")
+        v = float(v.detach().reshape(-1)[0].cpu())
+    return float(v)
+
+
 def residual_spec(pde) -> Tuple[List, int, float, int]:
     """(directions, PINNK_PDE kind, p0, compat_math) for ``pde`` -- the jets its residual needs."""
     name = pde_name(pde)
@@ -65,9 +79,16 @@ def residual_spec(pde) -> Tuple[List, int, float, int]:
         raise ValueError("pde.compat must be 'reference' or 'math'")
     p0 = {"heat": lambda: _float_param(pde, "alpha"), "burgers": lambda: _float_param(pde, "nu", 0.01),
           "kdv": lambda: 0.0, "allen_cahn": lambda: _float_param(pde, "epsilon", 0.1),
-          "cahn_hilliard": lambda: _float_param(pde, "epsilon", 0.1)}[name]()
+          "cahn_hilliard": lambda: _float_param(pde, "epsilon", 0.1),
+          "wave": lambda: _float_param(pde, "c", 1.0), "convection": lambda: _velocity_1d(pde)}[name]()
     unit = lambda i: tuple(1.0 if k == i else 0.0 for k in range(d + 1))
     t_dir = (unit(d), 1)
+    if name in ("wave", "convection") and d != 1:
+        # wave_equation.py:78-107 degenerates to u_tt, convection_equation.py:67-76 raises in autograd.grad
+        # (no allow_unused): neither is on the hot path in more than one space dimension
+        raise UnsupportedPDE(f"{name}: only the 1-D operator is implemented on the B200 path")
+    if name == "wave":
+        return [(unit(0), 2), (unit(1), 2)], L.PDE_WAVE, p0, 0           # second-order time jets: u_tt = 2 a_t2
     if d == 1:
         if name == "heat":
             math = compat == "math"

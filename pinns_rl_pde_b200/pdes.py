@@ -444,8 +444,60 @@ class CahnHilliardEquation(_PhaseField):
     _allow_random_ic = True
 
 
+class _SineIC(PDEBase):
+    """Shared initial-condition table of the wave and convection equations (wave_equation.py:138-169,
+    convection_equation.py:97-119): ``A sin(k pi x)``, defaults A = 1, k = 2."""
+    _ic_types = ("sine",)
+
+    def _create_boundary_condition(self, bc_type, params):
+        if bc_type == "initial":
+            kind = params.get("type", "sine")
+            if kind in self._ic_types:
+                A, k = params.get("amplitude", 1.0), params.get("frequency", 2.0)
+                if self.dimension == 1:
+                    return lambda x, t: A * torch.sin(k * torch.pi * x)
+                return lambda x, t: A * torch.sin(k * torch.pi * torch.sum(x, dim=1, keepdim=True))
+            raise ValueError(f"Unsupported initial condition type: {kind}")
+        return super()._create_boundary_condition(bc_type, params)
+
+
+class WaveEquation(_SineIC):
+    """wave_equation.py: r = u_tt - c^2 u_xx (key ``c``, default 1.0); second-order jets in t as well as x."""
+
+    @property
+    def c(self):
+        return self.get_parameter("c", default=1.0)
+
+    def exact_solution(self, x, t):
+        if self.dimension == 1:
+            return torch.sin(2 * torch.pi * (x - self.c * t))
+        sol = torch.ones_like(x[:, 0:1])
+        for d in range(self.dimension):
+            sol = sol * torch.sin(2 * torch.pi * (x[:, d:d + 1] - self.c * t))
+        return sol
+
+
+class ConvectionEquation(_SineIC):
+    """convection_equation.py: r = u_t + v u_x (key ``velocity``: scalar or per-dimension list, default 1.0)."""
+    _ic_types = ("sine", "sin")
+
+    @property
+    def velocity(self):
+        v = self.get_parameter("velocity", default=1.0)
+        return [v] * self.dimension if isinstance(v, (int, float)) else v
+
+    def exact_solution(self, x, t):
+        if self.dimension == 1:
+            return torch.sin(2 * torch.pi * (x - self.velocity[0] * t))
+        sol = torch.ones_like(x[:, 0:1])
+        for d in range(self.dimension):
+            sol = sol * torch.sin(2 * torch.pi * (x[:, d:d + 1] - self.velocity[d] * t))
+        return sol
+
+
 _FACTORY = {"heat": HeatEquation, "burgers": BurgersEquation, "kdv": KdVEquation,
-            "allen_cahn": AllenCahnEquation, "cahn_hilliard": CahnHilliardEquation}
+            "allen_cahn": AllenCahnEquation, "cahn_hilliard": CahnHilliardEquation,
+            "wave": WaveEquation, "convection": ConvectionEquation}
 
 
 def create_pde(name: str, config: PDEConfig) -> PDEBase:

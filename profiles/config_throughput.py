@@ -28,6 +28,8 @@ run("C3 kdv/resnet 6x256 (loss)", "kdv", "resnet", 256, 6, 1, 1 << 19, "loss", {
 run("C4 ch2d/siren 5x256 as-written (mse)", "cahn_hilliard", "siren", 256, 5, 2, 1 << 20, "mse", {"omega_0": 30.0})
 run("C4 ch2d/siren 5x256 math 18 cols (mse)", "cahn_hilliard", "siren", 256, 5, 2, 1 << 17, "mse", {"omega_0": 30.0}, "math")
 run("C5 allen-cahn/ff 8x128 scoring", "allen_cahn", "feedforward", 128, 8, 1, 1 << 22, "score", {})
+run("next: wave/ff 8x128 (loss, 5 jet columns)", "wave", "feedforward", 128, 8, 1, 1 << 19, "loss", {})
+run("next: convection/ff 8x128 (loss, 3 jet columns)", "convection", "feedforward", 128, 8, 1, 1 << 20, "loss", {})
 
 from pinns_rl_pde_b200 import _lib
 def prof(name, pde_name, arch, hidden, layers, dim, n, extra, compat="reference"):

@@ -52,6 +52,8 @@ from pinnrl.pdes.burgers_equation import BurgersEquation  # noqa: E402
 from pinnrl.pdes.kdv_equation import KdVEquation  # noqa: E402
 from pinnrl.pdes.cahn_hilliard import CahnHilliardEquation  # noqa: E402
 from pinnrl.pdes.allen_cahn import AllenCahnEquation  # noqa: E402
+from pinnrl.pdes.wave_equation import WaveEquation  # noqa: E402
+from pinnrl.pdes.convection_equation import ConvectionEquation  # noqa: E402
 
 from oracle import ref_port, jets_oracle  # noqa: E402
 
@@ -85,6 +87,11 @@ PDES = {
     "allen_cahn": dict(cls=AllenCahnEquation, domain=[[-1.0, 1.0]], time=[0.0, 1.0],
                        params={"epsilon": 0.1}, bcs={"dirichlet": {"value": 0.0}},
                        ic={"type": "tanh", "epsilon": 0.1}, exact={}),
+    # the next PDE epilogues (second-order time jets; first-order transport)
+    "wave": dict(cls=WaveEquation, domain=[[0.0, 1.0]], time=[0.0, 1.0], params={"c": 1.5},
+                 bcs={"dirichlet": {"value": 0.0}}, ic={"type": "sine", "amplitude": 1.0, "frequency": 2.0}, exact={}),
+    "convection": dict(cls=ConvectionEquation, domain=[[0.0, 1.0]], time=[0.0, 1.0], params={"velocity": 0.7},
+                       bcs={"dirichlet": {"value": 0.0}}, ic={"type": "sine", "amplitude": 1.0, "frequency": 2.0}, exact={}),
 }
 
 
@@ -245,7 +252,7 @@ def run_case(tag, pde_name, arch, hidden, layers, n, dimension=1, mode="loss", s
 
     if save:
         out = {f"w::{k}": v.numpy() for k, v in state.items()}
-        out.update(x=x.numpy(), t=t.numpy(), residual32=r32.numpy(), residual64=r64.numpy(),
+        out.update(x=x.detach().numpy(), t=t.detach().numpy(), residual32=r32.numpy(), residual64=r64.numpy(),
                    grad32=g32.numpy(), grad64=g64.numpy())
         for k in ("residual", "boundary", "initial", "total"):
             if k in L32:
@@ -276,6 +283,19 @@ def _base_loss64(model, residual, s, fns):
     return {"residual": res_loss, "boundary": b, "initial": i, "total": res_loss + 10 * b + 10 * i}
 
 
+def main_next():
+    """`python tests/golden/make_golden.py next`: only the fixtures of the SURVEY 8(f).4 PDEs (existing files untouched)."""
+    reports = [run_case("x_wave_ff_small", "wave", "feedforward", 32, 3, 96),
+               run_case("x_wave_ff128", "wave", "feedforward", 128, 3, 64),
+               run_case("x_convection_ff128", "convection", "feedforward", 128, 4, 96),
+               run_case("x_convection_siren_small", "convection", "siren", 32, 3, 64, omega_0=30.0)]
+    path = os.path.join(HERE, "golden_report.json")
+    old = json.load(open(path)) if os.path.exists(path) else []
+    old = [r for r in old if r["case"] not in {r2["case"] for r2 in reports}]
+    with open(path, "w") as f:
+        json.dump(old + reports, f, indent=1)
+
+
 def main():
     reports = []
     # committed fixtures (small networks / few points)
@@ -298,4 +318,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main_next() if sys.argv[1:] == ["next"] else main()

@@ -21,6 +21,10 @@ PDES = {
                           bcs={"dirichlet": {"value": 0.0}}, ic={"type": "tanh", "epsilon": 0.1}, exact={}),
     "allen_cahn": dict(domain=[[-1.0, 1.0]], time=[0.0, 1.0], params={"epsilon": 0.1},
                        bcs={"dirichlet": {"value": 0.0}}, ic={"type": "tanh", "epsilon": 0.1}, exact={}),
+    "wave": dict(domain=[[0.0, 1.0]], time=[0.0, 1.0], params={"c": 1.5},
+                 bcs={"dirichlet": {"value": 0.0}}, ic={"type": "sine", "amplitude": 1.0, "frequency": 2.0}, exact={}),
+    "convection": dict(domain=[[0.0, 1.0]], time=[0.0, 1.0], params={"velocity": 0.7},
+                       bcs={"dirichlet": {"value": 0.0}}, ic={"type": "sine", "amplitude": 1.0, "frequency": 2.0}, exact={}),
 }
 
 

@@ -126,13 +126,14 @@ PDE_CASES = [  # (kind, compat, pde name, dims, compat string, orders)
     (3, 0, "allen_cahn", 1, "reference", [2, 1]), (4, 0, "cahn_hilliard", 1, "reference", [4, 1]),
     (5, 0, "cahn_hilliard", 2, "reference", [1]), (6, 0, "allen_cahn", 2, "reference", [1]),
     (7, 0, "cahn_hilliard", 2, "math", [4, 4, 4, 4, 1]),
+    (10, 0, "wave", 1, "reference", [2, 2]), (11, 0, "convection", 1, "reference", [1, 1]),
 ]
 
 
 @pytest.mark.parametrize("kind,compat,name,dim,cstr,orders", PDE_CASES)
 def test_pde_epilogue_and_partials(hm, kind, compat, name, dim, cstr, orders):
     rng = np.random.default_rng(kind)
-    params = {"alpha": 0.37, "nu": 0.37, "epsilon": 0.37}
+    params = {"alpha": 0.37, "nu": 0.37, "epsilon": 0.37, "c": 0.37, "velocity": 0.37}
     ncols = 1 + sum(orders)
     for trial in range(10):
         U = rng.standard_normal(ncols)
