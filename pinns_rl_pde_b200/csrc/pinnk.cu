@@ -402,7 +402,7 @@ static bool jet_orders(const JetSpec& js, int& k0, int& k1) {
 template <typename F>
 static bool dispatch_edge_jets(int k0, int k1, F&& f) {
 #define PK_EDGE_CASE(A, B) if (k0 == A && k1 == B) { f(std::integral_constant<int, A>(), std::integral_constant<int, B>()); return true; }
-  PK_EDGE_CASE(0, 0) PK_EDGE_CASE(1, 0) PK_EDGE_CASE(2, 0) PK_EDGE_CASE(3, 0) PK_EDGE_CASE(4, 0) PK_EDGE_CASE(1, 1) PK_EDGE_CASE(2, 1) PK_EDGE_CASE(3, 1) PK_EDGE_CASE(4, 1)
+  PK_EDGE_CASE(0, 0) PK_EDGE_CASE(1, 0) PK_EDGE_CASE(2, 0) PK_EDGE_CASE(3, 0) PK_EDGE_CASE(4, 0) PK_EDGE_CASE(1, 1) PK_EDGE_CASE(2, 1) PK_EDGE_CASE(3, 1) PK_EDGE_CASE(4, 1) PK_EDGE_CASE(2, 2)
 #undef PK_EDGE_CASE
   return false;
 }
@@ -942,7 +942,12 @@ extern "C" int pinnk_debug_stage_timers(int32_t which, uint64_t* out16, int32_t 
   if (!out16) return fail(PINNK_E_INVALID, "debug_stage_timers: null output");
   cudaDeviceSynchronize();
   if (which == 0) return tc_stage_timers_fwd((unsigned long long*)out16, reset);
-  if (which == 1) return tc_stage_timers_bwd((unsigned long long*)out16, reset);
+  if (which == 1) {          // plain / stashed-z reverse kernels + the output-jet variant (own translation unit)
+    unsigned long long a[16], b[16];
+    const int r1 = tc_stage_timers_bwd(a, reset), r2 = tc_stage_timers_bwd_y(b, reset);
+    for (int i = 0; i < 16; ++i) out16[i] = (i == 15) ? (a[i] > b[i] ? a[i] : b[i]) : a[i] + b[i];
+    return r1 ? r1 : r2;
+  }
   return tc_stage_timers_wgrad((unsigned long long*)out16, reset);
 }
 

@@ -28,7 +28,8 @@ int tc_linear_dgrad_actbwd(const float* dZ, const float* W, const float* Zprev, 
                            int out_dim, int k0, int k1, int act, float omega, int sm_count, cudaStream_t st, int from_y);
 // jet layouts (orders of the at most two directions) the fused epilogues are instantiated for
 inline bool tc_jets_supported(int k0, int k1) {
-  return (k0 == 0 && k1 == 0) || (k0 == 1 && k1 == 0) || (k0 == 2 && k1 == 1) || (k0 == 3 && k1 == 0);
+  return (k0 == 0 && k1 == 0) || (k0 == 1 && k1 == 0) || (k0 == 2 && k1 == 1) || (k0 == 3 && k1 == 0) ||       // 1, 2, 4, 4
+         (k0 == 1 && k1 == 1) || (k0 == 3 && k1 == 1) || (k0 == 2 && k1 == 2) || (k0 == 4 && k1 == 1);         // 3, 5, 5, 6 columns
 }
 // dgrad of the first hidden layer fused with the complete reverse of the network's input layer
 // (nn.Linear(net_in_dim <= 4, in_dim) + activation): accumulates dW0 / db0, writes nothing else.  vec0 / vec1: direction
@@ -37,6 +38,9 @@ int tc_linear_dgrad_firstbwd(const float* dZ, const float* W, int64_t M, int in_
                              float omega, const float* x, const float* t, int net_in_dim, const float* vec0,
                              const float* vec1, const float* W0, const float* b0, float* gW0, float* gb0, int sm_count,
                              cudaStream_t st);
+// internal: EPI_ACTBWD_Y dispatch (lives in its own translation unit)
+int tc_dgrad_actbwd_y(int k0, int k1, const float* dZ, const float* W, int in_dim, float* dZprev, int64_t M,
+                      const float* Yprev, int sm_count, cudaStream_t st, int out_dim, int accum);
 // dW[out,in] += dZ[M,out]^T X[M,in] ;  db[out] += sum over value-column rows of dZ
 int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
                     int jet_cols, int sm_count, cudaStream_t st);
@@ -44,4 +48,5 @@ int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64
 int tc_stage_timers_fwd(unsigned long long* out16, int reset);
 int tc_stage_timers_bwd(unsigned long long* out16, int reset);
 int tc_stage_timers_wgrad(unsigned long long* out16, int reset);
+int tc_stage_timers_bwd_y(unsigned long long* out16, int reset);
 }  // namespace pinnk

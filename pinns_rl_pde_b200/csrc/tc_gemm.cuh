@@ -525,6 +525,12 @@ static __device__ unsigned long long g_stage_timers[16];
 //               pre-activations: 512 B per row less traffic); z jets are recovered with tanh_dir_recover
 enum { EPI_PLAIN = 0, EPI_ACT = 1, EPI_ACTBWD = 2, EPI_ACTBWD_Y = 3, EPI_FIRSTBWD = 4 };
 
+// rows (tile columns) one epilogue warp owns for a jet column count JC: the largest multiple of JC that is <= 16 and a
+// quarter of a 48-, 60- or 64-row tile
+__host__ __device__ constexpr int jets_rows_per_warp(int jc) {
+  return (jc >= 1 && 16 % jc == 0) ? 16 : (jc == 3 || jc == 5) ? 15 : (jc == 6) ? 12 : 0;
+}
+
 // EPI_FIRSTBWD: dgrad of the first HIDDEN layer fused with the whole reverse of the network's input layer
 // (nn.Linear(in_dim <= 4, width) + activation): the epilogue holds dL/dY0 jets of feature f, recomputes the input layer's
 // pre-activation jets from (x, t) -- z0 = b0[f] + W0[f,:] . xt, first-order coefficient W0[f,:] . vec_d, higher orders 0 --
@@ -571,7 +577,12 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
   static_assert(ECOLS == 16 || ECOLS == 32, "epilogue warps own 16 or 32 tile rows");
   constexpr int JC = 1 + K0 + K1;                       // jet columns of the fused epilogues
   constexpr int MAXK = (K0 > K1 ? K0 : K1) > 0 ? (K0 > K1 ? K0 : K1) : 1;
-  static_assert(EPI == EPI_PLAIN || (ECOLS % JC) == 0, "fused epilogues need the jet column count to divide the rows per epilogue warp");
+  // Rows an epilogue warp really owns (ECE <= ECOLS) and rows per tile (TNE = 4 * ECE <= TN): jet column counts that do
+  // not divide 16 (3, 5, 6: Heat / convection, KdV / wave, 1-D Cahn-Hilliard) use 60- or 48-row tiles inside the same
+  // 64-row MMA (the spare operand rows are zero), so that every epilogue warp still owns whole points.
+  constexpr int ECE = (EPI == EPI_PLAIN) ? ECOLS : jets_rows_per_warp(JC);
+  constexpr int TNE = (TN / ECOLS) * ECE;
+  static_assert(ECE > 0 && ECE <= ECOLS && (EPI == EPI_PLAIN || (ECE % JC) == 0), "unsupported jet column count for the fused epilogues");
   constexpr int CHUNKS = K / 4;
   constexpr uint32_t X_BYTES = TN * K * 4;        // one of X_hi / X_lo per stage (32 KB)
   constexpr uint32_t RAW_BYTES = TN * K * 4;      // raw fp32 row tile (32 KB)
@@ -595,7 +606,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
 #endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * 128;
-  const int64_t ntiles = (M + TN - 1) / TN;
+  const int64_t ntiles = (M + TNE - 1) / TNE;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], NLW); mbar_init(&empty[s], 1); }
@@ -649,8 +660,8 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
         const int s = it % RS;
         const uint32_t ph = (uint32_t)(it / RS) & 1u;
         { PK_T0(); mbar_wait(&raw_empty[s], ph ^ 1u); PK_TACC(t_a); }
-        const int64_t r0 = tile * TN;
-        const uint32_t nrows = (M - r0 >= TN) ? TN : (uint32_t)(M - r0);
+        const int64_t r0 = tile * TNE;
+        const uint32_t nrows = (M - r0 >= TNE) ? TNE : (uint32_t)(M - r0);
         mbar_arrive_expect_tx(&raw_full[s], nrows * (uint32_t)(K * 4));
         const uint32_t dst = rb + (uint32_t)s * RAW_BYTES;
         if (ldx == K) tma_bulk_g2s(dst, X + r0 * K, nrows * (uint32_t)(K * 4), &raw_full[s]);
@@ -670,8 +681,8 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int rs = it % RS, s = it % STAGES;
       const uint32_t rph = (uint32_t)(it / RS) & 1u, ph = (uint32_t)(it / STAGES) & 1u;
-      const int64_t r0 = tile * TN;
-      const int nrows = (M - r0 >= TN) ? TN : (int)(M - r0);
+      const int64_t r0 = tile * TNE;
+      const int nrows = (M - r0 >= TNE) ? TNE : (int)(M - r0);
       { PK_T0(); mbar_wait(&raw_full[rs], rph); PK_TACC(t_a); }
       PK_T0();
       const uint32_t raw = rb + (uint32_t)rs * RAW_BYTES;
@@ -716,7 +727,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
     const int f = q * 32 + lane;
     const float bf = (!TRANS_W && bias) ? bias[n0 + f] : 0.f;
     const bool store_z = (EPI != EPI_ACT) || (Y != nullptr);     // forward-only callers (scoring) pass no stash buffer
-    const uint32_t lane_acc = tmem_base + ((uint32_t)(q * 32) << 16) + COL_ACC + (uint32_t)(h * ECOLS);
+    const uint32_t lane_acc = tmem_base + ((uint32_t)(q * 32) << 16) + COL_ACC + (uint32_t)(h * ECE);
     // EPI_FIRSTBWD: this thread's row of the input layer and its gradient accumulators
     float w0r[4] = {0.f, 0.f, 0.f, 0.f}, z1d[2] = {0.f, 0.f}, aw0[4] = {0.f, 0.f, 0.f, 0.f}, ab0 = 0.f, b0f = 0.f;
     if constexpr (EPI == EPI_FIRSTBWD) {
@@ -750,13 +761,13 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
       if constexpr (IS_BWD) {
         const float* const zs0 = Zs + r0 * ldy + n0 + f;
 #pragma unroll
-        for (int j = 0; j < ECOLS; ++j) zsr[j] = (FULL || j < nrows) ? __ldg(zs0 + j * ldy) : 0.f;
+        for (int j = 0; j < ECOLS; ++j) zsr[j] = (j < ECE && (FULL || j < nrows)) ? __ldg(zs0 + j * ldy) : 0.f;
       }
-      float xin[(EPI == EPI_FIRSTBWD) ? ECOLS / JC : 1][4];
+      float xin[(EPI == EPI_FIRSTBWD) ? ECE / JC : 1][4];
       if constexpr (EPI == EPI_FIRSTBWD) {
         const int64_t p0 = r0 / JC;                    // r0 is a multiple of JC (whole points per warp)
 #pragma unroll
-        for (int pp = 0; pp < ECOLS / JC; ++pp)
+        for (int pp = 0; pp < ECE / JC; ++pp)
 #pragma unroll
           for (int i = 0; i < 4; ++i)
             xin[pp][i] = (i < fl.in_dim && (FULL || pp * JC < nrows)) ? load_xt(fl.x, fl.t, p0 + pp, i, fl.in_dim) : 0.f;
@@ -765,7 +776,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
       float part[ACCUM ? ECOLS : 1];
       if constexpr (ACCUM) {
 #pragma unroll
-        for (int j = 0; j < ECOLS; ++j) part[j] = (FULL || j < nrows) ? yp[j * ldy] : 0.f;
+        for (int j = 0; j < ECOLS; ++j) part[j] = (j < ECE && (FULL || j < nrows)) ? yp[j * ldy] : 0.f;
       }
       { PK_T0(); mbar_wait_relaxed(&tfull[b], ph); PK_TACC(t_ea); }
       PK_T0();
@@ -796,7 +807,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
         float* const ya = (EPI == EPI_ACT && Yact != nullptr) ? Yact + r0 * ldy + n0 + f : nullptr;
         const float wo = (EPI == EPI_ACT && of.w_out != nullptr) ? of.w_out[n0 + f] : 0.f;
 #pragma unroll
-        for (int pp = 0; pp < ECOLS / JC; ++pp) {
+        for (int pp = 0; pp < ECE / JC; ++pp) {
           const int jb = pp * JC;
           if (FULL || jb < nrows) {
             float z[MAXK + 1], y[MAXK + 1], w[MAXK + 1];
@@ -940,6 +951,8 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
 #pragma unroll
               for (int j = 0; j < ECOLS; ++j) if (j >= nrows) acc[j] = 0.f;
             }
+#pragma unroll
+            for (int j = ECE; j < ECOLS; ++j) acc[j] = 0.f;          // columns of the next warp's rows
             constexpr int NLVL = (ECOLS == 16) ? 4 : 5;
 #pragma unroll
             for (int lvl = 0; lvl < NLVL; ++lvl) {
@@ -957,7 +970,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
 #pragma unroll
             for (int S = 32 / ECOLS / 2; S >= 1; S >>= 1) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], S);
             const int rj = lane / (32 / ECOLS);
-            if ((lane % (32 / ECOLS)) == 0 && (FULL || rj < nrows))
+            if ((lane % (32 / ECOLS)) == 0 && rj < ECE && (FULL || rj < nrows))
               of.u_part[(int64_t)(blockIdx.y * 4 + q) * M + r0 + rj] = acc[0];
           }
         }
@@ -968,8 +981,8 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int b = it % ACC;
       const uint32_t ph = (uint32_t)(it / ACC) & 1u;
-      const int64_t r0 = tile * TN + h * ECOLS;
-      if (M - r0 >= ECOLS) run_tile(std::true_type(), b, ph, r0, ECOLS);
+      const int64_t r0 = tile * TNE + h * ECE;
+      if (M - r0 >= ECE) run_tile(std::true_type(), b, ph, r0, ECE);
       else run_tile(std::false_type(), b, ph, r0, (int)(M - r0 > 0 ? M - r0 : 0));
     }
     if constexpr (EPI == EPI_FIRSTBWD) {
@@ -1059,7 +1072,8 @@ static int launch_linear_rows_ts_inst(const float* X, const float* W, int ldw, c
   constexpr size_t smem = 1024 + (size_t)2 * 2 * 64 * 128 * 4 + (size_t)3 * 64 * 128 * 4 + (2 * 2 + 2 * 2 + 2 * 3) * 8 + 16;
   static_assert(smem <= 232448, "shared memory budget (227 KB per CTA)");
   constexpr int NLW = 8, ECOLS = (EPI == EPI_PLAIN) ? 32 : 16;
-  const int64_t ntiles = (M + 63) / 64;
+  constexpr int TNE = (EPI == EPI_PLAIN) ? 64 : 4 * jets_rows_per_warp(1 + K0 + K1);      // rows per tile
+  const int64_t ntiles = (M + TNE - 1) / TNE;
   const int per_y = n_cols / 128;
   int gx = sm_count / per_y;
   if (gx < 1) gx = 1;
@@ -1416,7 +1430,7 @@ static int launch_wgrad(const float* G, const float* X, float* dW, float* db, in
 
 }  // namespace tc
 
-#if defined(PINNK_TC_TU_FWD) || defined(PINNK_TC_TU_BWD)
+#if defined(PINNK_TC_TU_FWD) || defined(PINNK_TC_TU_BWD) || defined(PINNK_TC_TU_BWD_Y) || defined(PINNK_TC_TU_BWD_FIRST)
 // jet layouts the fused epilogues are instantiated for: (K0, K1) = orders of the (at most two) directions
 template <bool TRANS_W, int EPI, int ACT>
 static inline int tc_dispatch_jets(int k0, int k1, const float* X, const float* W, int ldw, const float* bias, float* Y,
@@ -1428,6 +1442,7 @@ static inline int tc_dispatch_jets(int k0, int k1, const float* X, const float* 
     return tc::launch_linear_rows_ts<TRANS_W, EPI, ACT, A, B>(X, W, ldw, bias, Y, M, n_cols, 1 + A + B, Zs, Yact, omega, \
                                                               sm_count, st, ldx, accum, of, fl);
   PK_TC_CASE(0, 0) PK_TC_CASE(1, 0) PK_TC_CASE(2, 1) PK_TC_CASE(3, 0)
+  PK_TC_CASE(1, 1) PK_TC_CASE(3, 1) PK_TC_CASE(2, 2) PK_TC_CASE(4, 1)
 #undef PK_TC_CASE
   return TC_UNSUPPORTED;
 }
@@ -1512,6 +1527,45 @@ int tc_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t M, int i
   if (out_dim == 128) return tc::launch_linear_rows<128, 32, 3, 3, 8, 3, true>(dZ, W, in_dim, nullptr, dX, M, in_dim, 1, sm_count, st);
   return TC_UNSUPPORTED;
 }
+// dgrad + activation adjoint in one kernel: dZprev = act'(Zprev)^T (dZ W)
+int tc_linear_dgrad_actbwd(const float* dZ, const float* W, const float* Zprev, float* dZprev, int64_t M,
+                                         int in_dim, int out_dim, int k0, int k1, int act, float omega, int sm_count,
+                                         cudaStream_t st, int from_y) {
+  if (from_y && act != 1) return TC_UNSUPPORTED;
+  if (M < 1 || (out_dim != 128 && out_dim != 256) || (in_dim % 128) != 0 || !tc_jets_supported(k0, k1) || (act != 1 && act != 2))
+    return TC_UNSUPPORTED;
+  int accum = 0;
+  if (out_dim == 256) {
+    int rc = tc::launch_linear_rows_ts<true, tc::EPI_PLAIN, 1, 0, 0>(dZ, W, in_dim, nullptr, dZprev, M, in_dim, 1, nullptr, nullptr, 1.f, sm_count, st, out_dim, 0);
+    if (rc) return rc;
+    dZ += 128; W += (int64_t)128 * in_dim; accum = 1;
+  }
+  if (act == 1 && from_y) return tc_dgrad_actbwd_y(k0, k1, dZ, W, in_dim, dZprev, M, Zprev, sm_count, st, out_dim, accum);
+  if (act == 1) return tc_dispatch_jets<true, tc::EPI_ACTBWD, 1>(k0, k1, dZ, W, in_dim, nullptr, dZprev, M, in_dim, Zprev, nullptr, 1.f, sm_count, st, out_dim, accum);
+  return tc_dispatch_jets<true, tc::EPI_ACTBWD, 2>(k0, k1, dZ, W, in_dim, nullptr, dZprev, M, in_dim, Zprev, nullptr, omega, sm_count, st, out_dim, accum);
+}
+#endif
+
+#ifdef PINNK_TC_TU_BWD_Y
+int tc_stage_timers_bwd_y(unsigned long long* out16, int reset) {
+#ifdef PINNK_STAGE_TIMERS
+  if (cudaMemcpyFromSymbol(out16, tc::g_stage_timers, 16 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+  if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(tc::g_stage_timers, z, sizeof(z)); }
+  return 0;
+#else
+  for (int i = 0; i < 16; ++i) out16[i] = 0;
+  (void)reset;
+  return 1;
+#endif
+}
+// the output-jet variant of the fused dgrad + tanh adjoint (own translation unit: compile time)
+int tc_dgrad_actbwd_y(int k0, int k1, const float* dZ, const float* W, int in_dim, float* dZprev, int64_t M,
+                      const float* Yprev, int sm_count, cudaStream_t st, int out_dim, int accum) {
+  return tc_dispatch_jets<true, tc::EPI_ACTBWD_Y, 1>(k0, k1, dZ, W, in_dim, nullptr, dZprev, M, in_dim, Yprev, nullptr, 1.f, sm_count, st, out_dim, accum);
+}
+#endif
+
+#ifdef PINNK_TC_TU_BWD_FIRST
 // dgrad of the first hidden layer + the whole reverse of the input layer (EPI_FIRSTBWD)
 int tc_linear_dgrad_firstbwd(const float* dZ, const float* W, int64_t M, int in_dim, int out_dim, int k0, int k1, int act,
                              float omega, const float* x, const float* t, int net_in_dim, const float* vec0,
@@ -1526,23 +1580,6 @@ int tc_linear_dgrad_firstbwd(const float* dZ, const float* W, int64_t M, int in_
   if (out_dim == 256) return TC_UNSUPPORTED;      // (two K halves would need a partial-sum buffer: not wired up)
   if (act == 1) return tc_dispatch_jets<true, tc::EPI_FIRSTBWD, 1>(k0, k1, dZ, W, in_dim, nullptr, nullptr, M, in_dim, nullptr, nullptr, 1.f, sm_count, st, out_dim, 0, tc::OutFuse{}, fl);
   return tc_dispatch_jets<true, tc::EPI_FIRSTBWD, 2>(k0, k1, dZ, W, in_dim, nullptr, nullptr, M, in_dim, nullptr, nullptr, omega, sm_count, st, out_dim, 0, tc::OutFuse{}, fl);
-}
-// dgrad + activation adjoint in one kernel: dZprev = act'(Zprev)^T (dZ W)
-int tc_linear_dgrad_actbwd(const float* dZ, const float* W, const float* Zprev, float* dZprev, int64_t M,
-                                         int in_dim, int out_dim, int k0, int k1, int act, float omega, int sm_count,
-                                         cudaStream_t st, int from_y) {
-  if (from_y && act != 1) return TC_UNSUPPORTED;
-  if (M < 1 || (out_dim != 128 && out_dim != 256) || (in_dim % 128) != 0 || !tc_jets_supported(k0, k1) || (act != 1 && act != 2))
-    return TC_UNSUPPORTED;
-  int accum = 0;
-  if (out_dim == 256) {
-    int rc = tc::launch_linear_rows_ts<true, tc::EPI_PLAIN, 1, 0, 0>(dZ, W, in_dim, nullptr, dZprev, M, in_dim, 1, nullptr, nullptr, 1.f, sm_count, st, out_dim, 0);
-    if (rc) return rc;
-    dZ += 128; W += (int64_t)128 * in_dim; accum = 1;
-  }
-  if (act == 1 && from_y) return tc_dispatch_jets<true, tc::EPI_ACTBWD_Y, 1>(k0, k1, dZ, W, in_dim, nullptr, dZprev, M, in_dim, Zprev, nullptr, 1.f, sm_count, st, out_dim, accum);
-  if (act == 1) return tc_dispatch_jets<true, tc::EPI_ACTBWD, 1>(k0, k1, dZ, W, in_dim, nullptr, dZprev, M, in_dim, Zprev, nullptr, 1.f, sm_count, st, out_dim, accum);
-  return tc_dispatch_jets<true, tc::EPI_ACTBWD, 2>(k0, k1, dZ, W, in_dim, nullptr, dZprev, M, in_dim, Zprev, nullptr, omega, sm_count, st, out_dim, accum);
 }
 #endif
 
