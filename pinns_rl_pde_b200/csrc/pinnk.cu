@@ -285,6 +285,8 @@ struct ChunkCtx {
   int64_t n;          // points in this chunk
   const float* x;     // chunk-local input pointers
   const float* t;
+  const TcLossFuse* loss_fuse = nullptr;   // loss_step: fold residual + loss + output-layer reverse into the last hidden layer
+  mutable bool loss_done = false;          // set by forward_chunk when the fused kernel ran
   float* stash(int op) const { return ws + pl->off_stash + pl->ops[op].out_off * pl->chunk; }
   float* U() const { return ws + pl->off_U; }
   float* Ub() const { return ws + pl->off_Ub; }
@@ -526,6 +528,15 @@ static int forward_chunk(const ChunkCtx& c, bool keep_stash = true) {
                                   pl->ops[i + 2].in_op == i + 1 && !pl->ops[i + 2].op.w_transposed;
             const PinnkOp& lo = pl->ops[n_ops - 1].op;
             const float* w_out = fuse_out ? c.params[lo.w_index] : nullptr;
+            if (fuse_out && c.loss_fuse != nullptr && keep_stash && !want_z) {
+              // residual + loss + seeds + reverse of the output layer and of this tanh inside the epilogue: no activation
+              // store, no U, no loss kernel, no last-layer reverse kernel
+              ProfScope psl(PC_GEMM_FWD, c.st);
+              int rcl = tc_linear_act_fwd(in, W, b, nullptr, nullptr, c.n * js.ncols, o.in_dim, o.out_dim, k0, k1,
+                                          a.act == PINNK_ACT_TANH ? 1 : 2, a.scale, pl->sm_count, c.st, w_out, nullptr, c.loss_fuse);
+              if (rcl == 0) { g_launches.fetch_add(1); c.loss_done = true; i = n_ops - 1; break; }
+              if (rcl != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, std::string("tc_linear_act_fwd (loss fusion) launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+            }
             float* y_out = (fuse_out && !keep_stash) ? nullptr : c.stash(i + 1);
             int rc = tc_linear_act_fwd(in, W, b, want_z ? c.stash(i) : nullptr, y_out, c.n * js.ncols, o.in_dim, o.out_dim, k0, k1,
                                        a.act == PINNK_ACT_TANH ? 1 : 2, a.scale, pl->sm_count, c.st, w_out, fuse_out ? c.adj(0) : nullptr);
@@ -577,7 +588,8 @@ static int forward_chunk(const ChunkCtx& c, bool keep_stash = true) {
 
 // reverse pass of one chunk: Ub[n, C] -> flat_grad (accumulated)
 template <int MAXK>
-static int backward_chunk(const ChunkCtx& c, float* flat_grad) {
+// last_done: the loss-fused forward already produced dL/dZ of the last hidden layer in adj(0) and the output layer's gradient
+static int backward_chunk(const ChunkCtx& c, float* flat_grad, bool last_done = false) {
   const pinnk_plan_t pl = c.pl;
   const JetSpec& js = pl->js;
   const int n_ops = (int)pl->ops.size();
@@ -590,7 +602,7 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad) {
   int first_trainable = n_ops;
   for (int i = 0; i < n_ops; ++i)
     if (pl->ops[i].op.gw_offset >= 0 || pl->ops[i].op.gb_offset >= 0) { first_trainable = i; break; }
-  for (int i = n_ops - 1; i >= first_trainable; --i) {
+  for (int i = last_done ? n_ops - 3 : n_ops - 1; i >= first_trainable; --i) {
     const OpRt& r = pl->ops[i];
     const PinnkOp& o = r.op;
     const float* in = (r.in_op >= 0) ? c.stash(r.in_op) : nullptr;
@@ -765,6 +777,40 @@ static ChunkCtx make_ctx(pinnk_plan_t plan, const float* const* params, const fl
   return c;
 }
 
+static inline const float* params_host_ptr(const float* const* params, int idx) { return params[idx]; }
+
+// PINNK_DISABLE_LOSS_FUSE=1: residual / loss / output-layer reverse as separate kernels (A/B checks)
+static bool loss_fuse_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PINNK_DISABLE_LOSS_FUSE"); v = (e && e[0] == '1') ? 0 : 1; }
+  return v == 1 && tc_enabled() && out_fuse_enabled();
+}
+
+// Index of the segment whose loss can be folded into the last hidden layer's forward epilogue for the chunk
+// [p0, p0 + cn), or -1: exactly one segment touches the chunk, it covers it completely and is a plain error functional
+// (no target, no paired rows, no per-row error output / upstream gradient); the network ends in
+// Linear(128, 128) + tanh + Linear(128, 1) whose pre-activation stash is elided (so the reverse pass would work from
+// the output jets anyway).
+static int loss_fusable_segment(pinnk_plan_t pl, const PinnkSegment* segs, int n_segs, int64_t p0, int64_t cn) {
+  if (!loss_fuse_enabled()) return -1;
+  const int n_ops = (int)pl->ops.size();
+  if (n_ops < 4) return -1;
+  const PinnkOp& L = pl->ops[n_ops - 3].op;
+  if (!z_elided(pl, n_ops - 3) || L.in_dim != 128 || L.out_dim != 128) return -1;
+  if (pl->ops[n_ops - 1].op.w_transposed || first_trainable_op(pl) > n_ops - 3) return -1;
+  int found = -1;
+  for (int s = 0; s < n_segs; ++s) {
+    const PinnkSegment& g = segs[s];
+    const int64_t lo = std::max(g.row_start, p0), hi = std::min(g.row_start + g.row_count, p0 + cn);
+    if (lo >= hi) continue;
+    if (found >= 0) return -1;
+    if (g.row_start > p0 || g.row_start + g.row_count < p0 + cn) return -1;
+    if (g.target || g.error_out || g.error_grad || g.pair_offset != 0) return -1;
+    found = s;
+  }
+  return found;
+}
+
 extern "C" int pinnk_jets_forward(pinnk_plan_t plan, const float* const* params, const float* x, const float* t,
                                   int64_t n, float* out_jets, void* ws, int64_t ws_bytes, void* stream) {
   int rc = check_common(plan, params, x, n, ws, ws_bytes);
@@ -822,8 +868,31 @@ extern "C" int pinnk_loss_step(pinnk_plan_t plan, const float* const* params, co
     const int64_t cn = std::min(plan->chunk, n - p0);
     ChunkCtx c = make_ctx(plan, params, x, t, p0, cn, ws, stream);
     const bool keep = flat_grad != nullptr;
+    // loss fusion: one plain segment covers the whole chunk and the network ends in Linear(128,128) + tanh + Linear(.,1)
+    TcLossFuse lf;
+    const int fs = keep ? loss_fusable_segment(plan, segs, n_segs, p0, cn) : -1;
+    if (fs >= 0) {
+      const PinnkSegment& g = segs[fs];
+      const PinnkOp& lo = plan->ops.back().op;
+      memset(&lf, 0, sizeof(lf));
+      lf.pde.kind = g.pde.kind; lf.pde.compat_math = g.pde.compat_math; lf.pde.p0 = g.pde.p0; lf.pde.p1 = g.pde.p1;
+      lf.js = plan->js;
+      lf.loss_kind = g.loss_kind; lf.huber_delta = g.huber_delta; lf.weight = g.weight;
+      lf.grad_weight = g.weight * (grad_scale ? grad_scale[g.component] : 1.f);
+      lf.loss_slot = loss_sums ? loss_sums + g.component : nullptr;
+      lf.dz_out = c.adj(0);
+      lf.gw_out = lo.gw_offset >= 0 ? flat_grad + lo.gw_offset : nullptr;
+      lf.gb_out = lo.gb_offset >= 0 ? flat_grad + lo.gb_offset : nullptr;
+      lf.b_out = lo.b_index >= 0 ? params_host_ptr(params, lo.b_index) : nullptr;
+      c.loss_fuse = &lf;
+    }
     rc = dispatch_maxk(plan->maxk, [&](auto mk) { return forward_chunk<decltype(mk)::value>(c, keep); });
     if (rc) return rc;
+    if (c.loss_done) {
+      rc = dispatch_maxk(plan->maxk, [&](auto mk) { return backward_chunk<decltype(mk)::value>(c, flat_grad, true); });
+      if (rc) return rc;
+      continue;
+    }
     if (flat_grad) PK_CHECK_CUDA(cudaMemsetAsync(c.Ub(), 0, sizeof(float) * cn * C, c.st));
     for (int s = 0; s < n_segs; ++s) {
       const PinnkSegment& g = segs[s];

@@ -5,9 +5,28 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "jet_math.cuh"
 
 namespace pinnk {
 constexpr int TC_UNSUPPORTED = 1;
+
+// Loss fusion of the last hidden layer (tc_linear_act_fwd with w_out and this struct): the epilogue completes the output
+// jets U through shared memory, evaluates the PDE residual, the loss sum and its seeds dL/dU, runs the adjoint of the
+// output layer and of the tanh on the spot and writes dL/dZ of the last hidden layer: the activation output, U, the
+// loss epilogue kernel and the last-layer reverse kernel all disappear from the step.
+struct TcLossFuse {
+  PdeDesc pde;
+  JetSpec js;
+  int loss_kind;
+  float huber_delta;
+  float weight;        // multiplies rho(e) in the loss sum
+  float grad_weight;   // multiplies rho'(e) in the seeds
+  double* loss_slot;   // += sum rho * weight
+  float* dz_out;       // [M, N] dL/d(pre-activation jets of the last hidden layer)
+  float* gw_out;       // [N] += dL/dw_out, or null
+  float* gb_out;       // [1] += dL/db_out, or null
+  const float* b_out;  // [1] output-layer bias, or null
+};
 
 // Z[M,N] = X[M,K] W[N,K]^T (+ bias on value-column rows)
 int tc_linear_fwd(const float* X, const float* W, const float* bias, float* Z, int64_t M, int K, int N, int jet_cols,
@@ -18,7 +37,7 @@ int tc_linear_fwd(const float* X, const float* W, const float* bias, float* Z, i
 // output jets (sum them in order + bias: output_combine_kernel); Yact may then be null (forward-only callers).
 int tc_linear_act_fwd(const float* X, const float* W, const float* bias, float* Z, float* Yact, int64_t M, int K, int N,
                       int k0, int k1, int act, float omega, int sm_count, cudaStream_t st,
-                      const float* w_out = nullptr, float* u_part = nullptr);
+                      const float* w_out = nullptr, float* u_part = nullptr, const TcLossFuse* loss = nullptr);
 // dX[M,in] = dZ[M,out] W[out,in]   (W row-major [out,in])
 int tc_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t M, int in_dim, int out_dim, int sm_count,
                     cudaStream_t st);

@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 #include <type_traits>
 #include "jet_math.cuh"
 #include "tc_api.h"
@@ -561,11 +562,13 @@ struct OutFuse {
   float* u_part = nullptr;
 };
 
-template <bool TRANS_W, int EPI, int ACT, int K0, int K1, int NLW, int ECOLS, bool ACCUM, int LDYC>
+template <bool TRANS_W, int EPI, int ACT, int K0, int K1, int NLW, int ECOLS, bool ACCUM, int LDYC, bool LOSSF = false>
 __global__ void __launch_bounds__((NLW + 4 * (64 / ECOLS) + 2) * 32, 1)
 linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
                       float* __restrict__ Y, int64_t M, int ldy_rt, int jet_cols, const float* __restrict__ Zs,
-                      float* __restrict__ Yact, float omega, int ldx, OutFuse of, FirstLayer fl) {
+                      float* __restrict__ Yact, float omega, int ldx, OutFuse of, FirstLayer fl,
+                      TcLossFuse lfv) {
+  static_assert(!LOSSF || (EPI == EPI_ACT && ACT == 1 && ECOLS == 16 && !ACCUM), "loss fusion: tanh forward epilogue only");
   // LDYC: compile-time row stride of Y / Zs / Yact (0 = use the runtime value): with it every row address of the
   // epilogue is base + immediate instead of a 64-bit multiply-add per access
   const int ldy = LDYC ? LDYC : ldy_rt;
@@ -600,6 +603,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
   uint64_t* raw_full = bars + 2 * STAGES + 2 * ACC;
   uint64_t* raw_empty = raw_full + RS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + RS);
+  float* u_smem = reinterpret_cast<float*>(tmem_slot + 4);      // [4 row groups][4 lane quarters][16]  (LOSSF)
 
 #ifdef PINNK_STAGE_TIMERS
   unsigned long long g_entry; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_entry));
@@ -742,6 +746,10 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
         z1d[d] = (ACT == 2) ? a * omega : a;
       }
     }
+    // LOSSF: per-thread accumulators of the output layer's gradient and of the loss
+    float gw_acc = 0.f, gb_acc = 0.f;
+    double loss_acc = 0.0;
+    (void)gw_acc; (void)gb_acc; (void)loss_acc;
     // One tile of this warp.  FULL: all ECOLS rows exist, so no access is predicated and (with LDYC) every row address
     // is the tile base plus an immediate.
     long long t_ea = 0, t_eb = 0; (void)t_ea; (void)t_eb;
@@ -805,6 +813,8 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
       } else {
         // whole points: columns [pp*JC, pp*JC + JC) of this warp's ECOLS are the jet of point pp at feature f
         float* const ya = (EPI == EPI_ACT && Yact != nullptr) ? Yact + r0 * ldy + n0 + f : nullptr;
+        float yk[LOSSF ? ECOLS : 1];                              // output jets kept for the in-kernel adjoint
+        (void)yk;
         const float wo = (EPI == EPI_ACT && of.w_out != nullptr) ? of.w_out[n0 + f] : 0.f;
 #pragma unroll
         for (int pp = 0; pp < ECE / JC; ++pp) {
@@ -818,6 +828,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
               else { z[0] *= omega; sincosf(z[0], &y[0], &w[0]); }
               if (ya) ya[jb * ldy] = y[0];
               acc[jb] = y[0] * wo;                                   // (the accumulator value is consumed: reuse the slot)
+              if constexpr (LOSSF) yk[jb] = y[0];
 #pragma unroll
               for (int d = 0; d < 2; ++d) {
                 const int KD = d ? K1 : K0, cb = jb + (d ? K0 : 0);
@@ -836,6 +847,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
                     if (k <= KD) {
                       if (ya) ya[(cb + k) * ldy] = y[k];
                       acc[cb + k] = y[k] * wo;
+                      if constexpr (LOSSF) yk[cb + k] = y[k];
                     }
                 }
               }
@@ -970,8 +982,77 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
 #pragma unroll
             for (int S = 32 / ECOLS / 2; S >= 1; S >>= 1) acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], S);
             const int rj = lane / (32 / ECOLS);
-            if ((lane % (32 / ECOLS)) == 0 && rj < ECE && (FULL || rj < nrows))
-              of.u_part[(int64_t)(blockIdx.y * 4 + q) * M + r0 + rj] = acc[0];
+            if constexpr (!LOSSF) {
+              if ((lane % (32 / ECOLS)) == 0 && rj < ECE && (FULL || rj < nrows))
+                of.u_part[(int64_t)(blockIdx.y * 4 + q) * M + r0 + rj] = acc[0];
+            } else {
+              // ---- output jets of the tile through shared memory (fixed summation order over the four lane quarters)
+              const TcLossFuse& lf = lfv;
+              float* const ug = u_smem + h * 64;
+              if ((lane & 1) == 0 && rj < ECE) ug[q * 16 + rj] = (FULL || rj < nrows) ? acc[0] : 0.f;
+              named_bar_sync(1 + h, 128);
+              float Uv = 0.f;
+              if (lane < ECE) {
+                Uv = ((ug[lane] + ug[16 + lane]) + ug[32 + lane]) + ug[48 + lane];
+                if (lf.b_out != nullptr && (lane % JC) == 0) Uv += __ldg(lf.b_out);
+              }
+              named_bar_sync(1 + h, 128);                          // the group's slots may be rewritten (next tile)
+              // ---- residual, loss and seeds: lane l < ECE works on point l / JC (the JC lanes of a point redundantly),
+              // so ONE residual evaluation per tile and warp covers all its points; lane l then owns dL/dU of row l
+              float sd = 0.f;
+              {
+                const int pl_ = (lane < ECE) ? lane / JC : 0, cl_ = (lane < ECE) ? lane - pl_ * JC : 0;
+                float u[kMaxCols], du[kMaxCols];
+#pragma unroll
+                for (int c = 0; c < JC; ++c) u[c] = __shfl_sync(0xffffffffu, Uv, pl_ * JC + c);
+                const float e = pde_residual<float>(lf.pde, lf.js, u, du);
+                float drho;
+                const float rho = loss_rho<float>(lf.loss_kind, lf.huber_delta, e, &drho);
+                const bool live = lane < ECE && (FULL || lane < nrows);
+                float dsel = 0.f;
+#pragma unroll
+                for (int c = 0; c < JC; ++c) dsel = (c == cl_) ? du[c] : dsel;
+                sd = live ? drho * lf.grad_weight * dsel : 0.f;
+                if (q == 0 && live && cl_ == 0) { loss_acc += (double)rho * (double)lf.weight; gb_acc += sd; }
+              }
+              // ---- adjoint of output layer + tanh, per point (every lane: its own feature f):
+              // dL/dy[c] = dL/dU[c] * w_out[f];  dL/dw_out[f] += dL/dU[c] * y[c]
+#pragma unroll
+              for (int pp = 0; pp < ECE / JC; ++pp) {
+                const int jb = pp * JC;
+                float s_[JC];
+#pragma unroll
+                for (int c = 0; c < JC; ++c) s_[c] = __shfl_sync(0xffffffffu, sd, jb + c);
+                if (FULL || jb < nrows) {
+                  float y[MAXK + 1], w[MAXK + 1], z[MAXK + 1], yb[MAXK + 1], zb[MAXK + 1];
+                  y[0] = yk[jb];
+                  w[0] = 1.f - y[0] * y[0];
+                  const float inv_w0 = (w[0] > 1e-30f) ? __fdividef(1.f, w[0]) : 0.f;
+                  yb[0] = s_[0] * wo;
+                  gw_acc = fmaf(s_[0], y[0], gw_acc);
+                  float wb0 = 0.f;
+                  float* const gp = lf.dz_out + (r0 + jb) * ldy + n0 + f;
+#pragma unroll
+                  for (int d = 0; d < 2; ++d) {
+                    const int KD = d ? K1 : K0, cb = d ? K0 : 0;
+                    if (KD > 0) {
+#pragma unroll
+                      for (int k = 1; k <= MAXK; ++k) {
+                        y[k] = (k <= KD) ? yk[jb + cb + k] : 0.f;
+                        yb[k] = (k <= KD) ? s_[(k <= KD) ? cb + k : 0] * wo : 0.f;
+                        if (k <= KD) gw_acc = fmaf(s_[cb + k], y[k], gw_acc);
+                      }
+                      tanh_dir_recover<MAXK, float>(KD, y, w, z, inv_w0);
+                      tanh_dir_bwd<MAXK, float>(KD, z, y, w, yb, zb, wb0);
+#pragma unroll
+                      for (int k = 1; k <= MAXK; ++k)
+                        if (k <= KD) gp[(cb + k) * ldy] = zb[k];
+                    }
+                  }
+                  gp[0] = tanh_finish_bwd<float>(y[0], w[0], yb[0], wb0);
+                }
+              }
+            }
           }
         }
       }
@@ -984,6 +1065,20 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
       const int64_t r0 = tile * TNE + h * ECE;
       if (M - r0 >= ECE) run_tile(std::true_type(), b, ph, r0, ECE);
       else run_tile(std::false_type(), b, ph, r0, (int)(M - r0 > 0 ? M - r0 : 0));
+    }
+    if constexpr (LOSSF) {
+      if (lfv.gw_out) atomicAdd(lfv.gw_out + n0 + f, gw_acc);
+      if (q == 0) {                                    // the value-column lanes of this warp hold the partial sums
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          gb_acc += __shfl_xor_sync(0xffffffffu, gb_acc, o);
+          loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
+        }
+        if (lane == 0) {
+          if (lfv.gb_out) atomicAdd(lfv.gb_out, gb_acc);
+          if (lfv.loss_slot) atomicAdd(lfv.loss_slot, loss_acc);
+        }
+      }
     }
     if constexpr (EPI == EPI_FIRSTBWD) {
       if (fl.gW0) {
@@ -1065,11 +1160,11 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
   }
 }
 
-template <bool TRANS_W, int EPI, int ACT, int K0, int K1, bool ACCUM, int LDYC>
+template <bool TRANS_W, int EPI, int ACT, int K0, int K1, bool ACCUM, int LDYC, bool LOSSF = false>
 static int launch_linear_rows_ts_inst(const float* X, const float* W, int ldw, const float* bias, float* Y, int64_t M, int n_cols,
                                       int jet_cols, const float* Zs, float* Yact, float omega, int sm_count, cudaStream_t st,
-                                      int ldx, OutFuse of = OutFuse{}, FirstLayer fl = FirstLayer{}) {
-  constexpr size_t smem = 1024 + (size_t)2 * 2 * 64 * 128 * 4 + (size_t)3 * 64 * 128 * 4 + (2 * 2 + 2 * 2 + 2 * 3) * 8 + 16;
+                                      int ldx, OutFuse of = OutFuse{}, FirstLayer fl = FirstLayer{}, const TcLossFuse* loss = nullptr) {
+  constexpr size_t smem = 1024 + (size_t)2 * 2 * 64 * 128 * 4 + (size_t)3 * 64 * 128 * 4 + (2 * 2 + 2 * 2 + 2 * 3) * 8 + 16 + 1024;
   static_assert(smem <= 232448, "shared memory budget (227 KB per CTA)");
   constexpr int NLW = 8, ECOLS = (EPI == EPI_PLAIN) ? 32 : 16;
   constexpr int TNE = (EPI == EPI_PLAIN) ? 64 : 4 * jets_rows_per_warp(1 + K0 + K1);      // rows per tile
@@ -1080,13 +1175,16 @@ static int launch_linear_rows_ts_inst(const float* X, const float* W, int ldw, c
   if ((int64_t)gx > ntiles) gx = (int)ntiles;
   dim3 grid((unsigned)gx, (unsigned)per_y, 1);
   constexpr int threads = (NLW + 4 * (64 / ECOLS) + 2) * 32;
-  auto kern = linear_rows_ts_kernel<TRANS_W, EPI, ACT, K0, K1, NLW, ECOLS, ACCUM, LDYC>;
+  auto kern = linear_rows_ts_kernel<TRANS_W, EPI, ACT, K0, K1, NLW, ECOLS, ACCUM, LDYC, LOSSF>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     configured = true;
   }
-  kern<<<grid, threads, smem, st>>>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, ldx, of, fl);
+  TcLossFuse lf;
+  memset(&lf, 0, sizeof(lf));
+  if (loss) lf = *loss;
+  kern<<<grid, threads, smem, st>>>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, ldx, of, fl, lf);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -1095,7 +1193,16 @@ static int launch_linear_rows_ts_inst(const float* X, const float* W, int ldw, c
 template <bool TRANS_W, int EPI, int ACT, int K0, int K1>
 static int launch_linear_rows_ts(const float* X, const float* W, int ldw, const float* bias, float* Y, int64_t M, int n_cols,
                                  int jet_cols, const float* Zs, float* Yact, float omega, int sm_count, cudaStream_t st,
-                                 int ldx = 128, int accum = 0, OutFuse of = OutFuse{}, FirstLayer fl = FirstLayer{}) {
+                                 int ldx = 128, int accum = 0, OutFuse of = OutFuse{}, FirstLayer fl = FirstLayer{},
+                                 const TcLossFuse* loss = nullptr) {
+  if constexpr (EPI == EPI_ACT && ACT == 1) {
+    if (loss != nullptr) {         // loss-fused last hidden layer (tanh, one K pass, one 128-wide output block)
+      if (accum || n_cols != 128 || of.w_out == nullptr) return TC_UNSUPPORTED;
+      return launch_linear_rows_ts_inst<TRANS_W, EPI, ACT, K0, K1, false, 128, true>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, sm_count, st, ldx, of, fl, loss);
+    }
+  } else {
+    if (loss != nullptr) return TC_UNSUPPORTED;
+  }
   if (accum)
     return launch_linear_rows_ts_inst<TRANS_W, EPI, ACT, K0, K1, true, 0>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, sm_count, st, ldx, of, fl);
   if (n_cols == 128)
@@ -1436,11 +1543,11 @@ template <bool TRANS_W, int EPI, int ACT>
 static inline int tc_dispatch_jets(int k0, int k1, const float* X, const float* W, int ldw, const float* bias, float* Y,
                                    int64_t M, int n_cols, const float* Zs, float* Yact, float omega, int sm_count,
                                    cudaStream_t st, int ldx = 128, int accum = 0, tc::OutFuse of = tc::OutFuse{},
-                                   tc::FirstLayer fl = tc::FirstLayer{}) {
+                                   tc::FirstLayer fl = tc::FirstLayer{}, const TcLossFuse* loss = nullptr) {
 #define PK_TC_CASE(A, B)                                                                                         \
   if (k0 == A && k1 == B)                                                                                        \
     return tc::launch_linear_rows_ts<TRANS_W, EPI, ACT, A, B>(X, W, ldw, bias, Y, M, n_cols, 1 + A + B, Zs, Yact, omega, \
-                                                              sm_count, st, ldx, accum, of, fl);
+                                                              sm_count, st, ldx, accum, of, fl, loss);
   PK_TC_CASE(0, 0) PK_TC_CASE(1, 0) PK_TC_CASE(2, 1) PK_TC_CASE(3, 0)
   PK_TC_CASE(1, 1) PK_TC_CASE(3, 1) PK_TC_CASE(2, 2) PK_TC_CASE(4, 1)
 #undef PK_TC_CASE
@@ -1482,9 +1589,10 @@ int tc_linear_fwd(const float* X, const float* W, const float* bias, float* Z, i
 // Forward Linear + activation jets in one kernel: Z = X W^T + b (stash), Yact = act(Z).  act: 1 tanh, 2 sin(omega z).
 int tc_linear_act_fwd(const float* X, const float* W, const float* bias, float* Z, float* Yact, int64_t M, int K,
                                     int N, int k0, int k1, int act, float omega, int sm_count, cudaStream_t st,
-                                    const float* w_out, float* u_part) {
+                                    const float* w_out, float* u_part, const TcLossFuse* loss) {
   if (M < 1 || (K != 128 && K != 256) || (N % 128) != 0 || !tc_jets_supported(k0, k1) || (act != 1 && act != 2)) return TC_UNSUPPORTED;
   if (Yact == nullptr && w_out == nullptr) return TC_UNSUPPORTED;      // nothing would be produced
+  if (loss != nullptr && w_out == nullptr) return TC_UNSUPPORTED;
   tc::OutFuse of;
   of.w_out = w_out;
   of.u_part = u_part;
@@ -1495,7 +1603,8 @@ int tc_linear_act_fwd(const float* X, const float* W, const float* bias, float* 
     if (rc) return rc;
     X += 128; W += 128; accum = 1;
   }
-  if (act == 1) return tc_dispatch_jets<false, tc::EPI_ACT, 1>(k0, k1, X, W, K, bias, Z, M, N, nullptr, Yact, 1.f, sm_count, st, K, accum, of);
+  if (loss != nullptr && (act != 1 || K != 128)) return TC_UNSUPPORTED;
+  if (act == 1) return tc_dispatch_jets<false, tc::EPI_ACT, 1>(k0, k1, X, W, K, bias, Z, M, N, nullptr, Yact, 1.f, sm_count, st, K, accum, of, tc::FirstLayer{}, loss);
   return tc_dispatch_jets<false, tc::EPI_ACT, 2>(k0, k1, X, W, K, bias, Z, M, N, nullptr, Yact, omega, sm_count, st, K, accum, of);
 }
 #endif
