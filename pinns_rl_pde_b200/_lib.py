@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpinnk.so")
+LIB_PATH = os.environ.get("PINNK_LIB", os.path.join(HERE, "libpinnk.so"))     # PINNK_LIB: A/B builds of the same library
 
 OP_LINEAR, OP_ACT, OP_LAYERNORM, OP_SKIP_SAVE, OP_SKIP_ADD, OP_SINCOS = 1, 2, 3, 4, 5, 6
 ACT_TANH, ACT_SIN = 1, 2

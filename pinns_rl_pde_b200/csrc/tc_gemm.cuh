@@ -478,17 +478,11 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
 }
 // round-to-nearest (ties away) fp32 -> tf32 on the bit pattern: what cvt.rna.tf32.f32 computes for finite inputs
 __device__ __forceinline__ uint32_t rn_tf32_bits(uint32_t b) { return (b + 0x1000u) & 0xFFFFE000u; }
-// hi must be an exact tf32 value (it is subtracted from v).  lo only feeds the tensor core, which reads the upper 19 bits
-// of a 32-bit tf32 operand: adding half an ulp of tf32 and leaving the low 13 bits in place rounds to nearest once the
-// hardware drops them, and saves the mask (4 instead of 5 ALU operations per element; the convert warps are issue-bound).
-// PINNK_TF32_MASK_LO restores the explicit mask (A/B: tests/test_gpu_tc.py prints the error of both against fp64).
+// (leaving the low 13 bits of lo in place -- the tensor core drops them -- would save one AND per element; measured: same
+// GEMM error, no measurable speed-up, so the explicit mask stays)
 __device__ __forceinline__ void split_bits(float v, uint32_t& hi, uint32_t& lo) {
   hi = rn_tf32_bits(__float_as_uint(v));
-#ifdef PINNK_TF32_MASK_LO
   lo = rn_tf32_bits(__float_as_uint(v - __uint_as_float(hi)));
-#else
-  lo = __float_as_uint(v - __uint_as_float(hi)) + 0x1000u;
-#endif
 }
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
