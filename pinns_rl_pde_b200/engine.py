@@ -211,11 +211,12 @@ def get_program(model: nn.Module) -> NetProgram:
 
 
 def get_engine(model: nn.Module, directions: Sequence[Direction], n_points: int,
-               max_chunk: Optional[int] = None, whole: bool = False) -> JetEngine:
+               max_chunk: Optional[int] = None, whole: bool = False, program: Optional[NetProgram] = None) -> JetEngine:
     """Engine for (model, jet spec) able to process ``n_points`` rows per call; cached per model.
     ``whole``: the call must fit ONE chunk (paired periodic-BC rows reference each other), so only the
     workspace budget caps the chunk size."""
-    program = get_program(model)
+    if program is None:                # callers that already validated the model this call pass its program (the
+        program = get_program(model)   # parameter-signature walk is the dominant host cost of a small-batch step)
     cache = _CACHE[model]
     dirs = tuple((tuple(float(v) for v in vec), int(order)) for vec, order in directions)
     ncols = 1 + sum(o for _, o in dirs)

@@ -200,8 +200,9 @@ def compute_residual(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor) ->
     n = x.shape[0]
     eng = get_engine(model, dirs, n)
     proto = Segment(kind=kind, row_start=0, row_count=n, p0=p0, compat_math=cm)
-    model.train()   # pde_base.py:638 -- the reference flips the model into training mode here
-    return _ErrorFn.apply(eng, proto, x, t, *_trainable(model))
+    if not model.training:
+        model.train()   # pde_base.py:638 -- the reference flips the model into training mode here
+    return _ErrorFn.apply(eng, proto, x, t, *eng.program.grad_params)
 
 
 def score_residual(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, want_abs: bool = True,
@@ -271,9 +272,11 @@ def _build_calls(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_glob
     ng = n if n_global is None else int(n_global)
     lk, delta = _loss_kind(pde)
     mk = dict(loss_kind=lk, huber_delta=delta)
-    model.train()
+    if not model.training:
+        model.train()
+    program = get_program(model)
     calls = []
-    eng_r = get_engine(model, dirs, n)
+    eng_r = get_engine(model, dirs, n, program=program)
     calls.append((eng_r, x, t, [Segment(kind=kind, row_start=0, row_count=n, component=0, weight=1.0 / max(n, 1),
                                         p0=p0, compat_math=cm, **mk)]))
     dom, td = pde.domain, pde.time_domain
@@ -297,7 +300,7 @@ def _build_calls(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_glob
             x_min, x_max = pde.config.domain[0]
             pts = torch.cat([torch.cat([torch.full((nb, 1), x_min, device=dev), tb], dim=1),
                              torch.cat([torch.full((nb, 1), x_max, device=dev), tb], dim=1)], dim=0)
-            eng_b = get_engine(model, [((1.0, 0.0), 1)], 2 * nb, whole=True)
+            eng_b = get_engine(model, [((1.0, 0.0), 1)], 2 * nb, whole=True, program=program)
             calls.append((eng_b, pts, None, [
                 Segment(kind=L.PDE_VALUE, row_start=0, row_count=nb, component=1, weight=1.0 / nb, pair_offset=nb, **mk),
                 Segment(kind=L.PDE_DX, row_start=0, row_count=nb, component=1, weight=1.0 / nb, pair_offset=nb, **mk)]))
@@ -324,7 +327,7 @@ def _build_calls(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_glob
                 lo_pts.append(torch.cat([cmin, t_axis], dim=1))
                 hi_pts.append(torch.cat([cmax, t_axis], dim=1))
             pts = torch.cat(lo_pts + hi_pts, dim=0)
-            eng_b = get_engine(model, [], pts.shape[0], whole=True)
+            eng_b = get_engine(model, [], pts.shape[0], whole=True, program=program)
             calls.append((eng_b, pts, None, [
                 Segment(kind=L.PDE_VALUE, row_start=a * per_axis, row_count=per_axis, component=1,
                         weight=1.0 / per_axis, pair_offset=dim * per_axis, **mk) for a in range(dim)]))
@@ -341,7 +344,7 @@ def _build_calls(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_glob
                 for d in range(dim):
                     target = target * torch.sin(k * torch.pi * xi[:, d:d + 1])
         n_i = xi.shape[0]
-        eng_i = get_engine(model, [], n_i)
+        eng_i = get_engine(model, [], n_i, program=program)
         calls.append((eng_i, torch.cat([xi, ti], dim=1), None, [
             Segment(kind=L.PDE_VALUE, row_start=0, row_count=n_i, component=2, weight=1.0 / max(n_i, 1),
                     target=target.detach().to(torch.float32).reshape(-1).contiguous(), **mk)]))
@@ -373,11 +376,11 @@ def _build_calls(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_glob
             # when all components accumulate into one gradient buffer (the fused trainer step).
             segs.append(Segment(kind=L.PDE_VALUE, row_start=nbp, row_count=100, component=2, weight=0.01,
                                 target=ic_target, **mk))
-            calls.append((get_engine(model, [], nbp + 100), torch.cat([xb, xi], dim=0), torch.cat([tb, ti], dim=0), segs))
+            calls.append((get_engine(model, [], nbp + 100, program=program), torch.cat([xb, xi], dim=0), torch.cat([tb, ti], dim=0), segs))
         else:
             if segs:
-                calls.append((get_engine(model, [], nbp), xb, tb, segs))
-            calls.append((get_engine(model, [], 100), xi, ti, [
+                calls.append((get_engine(model, [], nbp, program=program), xb, tb, segs))
+            calls.append((get_engine(model, [], 100, program=program), xi, ti, [
                 Segment(kind=L.PDE_VALUE, row_start=0, row_count=100, component=2, weight=0.01, target=ic_target, **mk)]))
 
     return calls, _weights(pde, heat)
@@ -388,7 +391,7 @@ def loss_components(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_g
     weights the reference would combine them with.  ``n_global``: number of collocation rows of the whole
     (possibly sharded) batch -- the reference derives default BC/IC point counts from it."""
     calls, weights = _build_calls(pde, model, x, t, n_global)
-    program = get_program(model)
+    program = calls[0][0].program
     comp = _LossFn.apply(calls, 3, program, *program.grad_params)
     return comp, weights
 
@@ -408,7 +411,7 @@ def loss_step_flat(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_gl
         raise NotImplementedError("the fused step does not cover the smoothness regulariser; use compute_loss")
     if adaptive:
         w_res = w_bc = w_ic = 1.0
-    program = get_program(model)
+    program = calls[0][0].program
     dev = calls[0][1].device
     if flat is None:
         flat = torch.zeros(program.grad_floats, dtype=torch.float32, device=dev)
