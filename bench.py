@@ -284,12 +284,15 @@ def run_ours(args):
         from pinns_rl_pde_b200 import engine as _engine
         n_chunks = max(1, -(-n_local // _engine.MAX_CHUNK_POINTS))
         rows_per_launch = JET_COLS * n_local / n_chunks                      # stacked jet rows one launch processes
-        # algorithmic bytes per row of 128 floats: fwd+tanh reads X, writes Z and Y; dgrad+adjoint reads dZ and the
-        # stashed Z, writes dZ_prev; wgrad reads dZ and X (DESIGN.md "kernels")
-        bytes_per_row = {"gemm_fwd": 3 * 512, "gemm_dgrad": 3 * 512, "gemm_wgrad": 2 * 512}[dom]
+        # algorithmic bytes per row of 128 floats (DESIGN.md "kernels"): Linear+tanh reads X and writes Y (the pre-activation
+        # stash is elided; the loss-fused last layer reads X and writes dZ instead); dgrad+adjoint reads dZ and the stashed Y,
+        # writes dZ_prev; wgrad reads dZ and X
+        bytes_per_row = {"gemm_fwd": 2 * 512, "gemm_dgrad": 3 * 512, "gemm_wgrad": 2 * 512}[dom]
         flops_per_launch = 2 * rows_per_launch * HIDDEN * HIDDEN
-        # only the 7 hidden 128x128 launches per chunk count; value-only BC/IC launches are tiny
-        big = 2 * (LAYERS - 1) * n_chunks
+        # big launches per chunk in this class (value-only BC/IC launches are tiny): 7 hidden layers forward and wgrad; 6 fused
+        # dgrad+adjoint launches (the first hidden layer's dgrad is fused with the input layer's reverse: class first_linear_bwd)
+        per_chunk = {"gemm_fwd": LAYERS - 1, "gemm_dgrad": LAYERS - 2, "gemm_wgrad": LAYERS - 1}[dom]
+        big = 2 * per_chunk * n_chunks                                       # two profiled steps
         ms_launch = ms_dom / max(big, 1)
         peaks = {}
         try:
