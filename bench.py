@@ -289,9 +289,10 @@ def run_ours(args):
         # writes dZ_prev; wgrad reads dZ and X
         bytes_per_row = {"gemm_fwd": 2 * 512, "gemm_dgrad": 3 * 512, "gemm_wgrad": 2 * 512}[dom]
         flops_per_launch = 2 * rows_per_launch * HIDDEN * HIDDEN
-        # big launches per chunk in this class (value-only BC/IC launches are tiny): 7 hidden layers forward and wgrad; 6 fused
+        # big launches per chunk in this class (value-only BC/IC launches are tiny): 6 hidden layers forward, 7 wgrad; 6 fused
         # dgrad+adjoint launches (the first hidden layer's dgrad is fused with the input layer's reverse: class first_linear_bwd)
-        per_chunk = {"gemm_fwd": LAYERS - 1, "gemm_dgrad": LAYERS - 2, "gemm_wgrad": LAYERS - 1}[dom]
+        # (the last hidden layer's forward is the loss-fused launch: class fwd_loss_fused)
+        per_chunk = {"gemm_fwd": LAYERS - 2, "gemm_dgrad": LAYERS - 2, "gemm_wgrad": LAYERS - 1}[dom]
         big = 2 * per_chunk * n_chunks                                       # two profiled steps
         ms_launch = ms_dom / max(big, 1)
         peaks = {}

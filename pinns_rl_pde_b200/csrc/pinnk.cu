@@ -32,10 +32,10 @@ static std::atomic<int64_t> g_launches{0};
 
 // ---- optional per-kernel-class timing (bench.py roofline): CUDA event pairs on the launching stream
 enum ProfClass { PC_FIRST_FWD = 0, PC_GEMM_FWD, PC_ACT_FWD, PC_LN_FWD, PC_LAST_FWD, PC_EPILOGUE, PC_LAST_BWD,
-                 PC_ACT_BWD, PC_LN_BWD, PC_GEMM_DGRAD, PC_GEMM_WGRAD, PC_FIRST_BWD, PC_MISC, PC_COUNT };
+                 PC_ACT_BWD, PC_LN_BWD, PC_GEMM_DGRAD, PC_GEMM_WGRAD, PC_FIRST_BWD, PC_MISC, PC_FWD_LOSS, PC_COUNT };
 static const char* kProfNames[PC_COUNT] = {"first_linear_fwd", "gemm_fwd", "act_fwd", "layernorm_fwd", "last_linear_fwd",
                                            "epilogue", "last_linear_bwd", "act_bwd", "layernorm_bwd", "gemm_dgrad",
-                                           "gemm_wgrad", "first_linear_bwd", "misc"};
+                                           "gemm_wgrad", "first_linear_bwd", "misc", "fwd_loss_fused"};
 struct ProfRec { int cls; cudaEvent_t a, b; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
@@ -531,7 +531,7 @@ static int forward_chunk(const ChunkCtx& c, bool keep_stash = true) {
             if (fuse_out && c.loss_fuse != nullptr && keep_stash && !want_z) {
               // residual + loss + seeds + reverse of the output layer and of this tanh inside the epilogue: no activation
               // store, no U, no loss kernel, no last-layer reverse kernel
-              ProfScope psl(PC_GEMM_FWD, c.st);
+              ProfScope psl(PC_FWD_LOSS, c.st);
               int rcl = tc_linear_act_fwd(in, W, b, nullptr, nullptr, c.n * js.ncols, o.in_dim, o.out_dim, k0, k1,
                                           a.act == PINNK_ACT_TANH ? 1 : 2, a.scale, pl->sm_count, c.st, w_out, nullptr, c.loss_fuse);
               if (rcl == 0) { g_launches.fetch_add(1); c.loss_done = true; i = n_ops - 1; break; }
