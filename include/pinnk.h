@@ -67,14 +67,18 @@ typedef struct {
 /* per-row error functional e = f(U[row]) [- f(U[row+pair_offset])] [- target[i]] */
 enum { PINNK_PDE_HEAT = 0, PINNK_PDE_BURGERS = 1, PINNK_PDE_KDV = 2, PINNK_PDE_ALLEN_CAHN = 3,
        PINNK_PDE_CAHN_HILLIARD = 4, PINNK_PDE_UT_ONLY = 5, PINNK_PDE_UT_ALLEN_CAHN_ND = 6,
-       PINNK_PDE_CAHN_HILLIARD_2D = 7, PINNK_PDE_VALUE = 8, PINNK_PDE_DX = 9 };
+       PINNK_PDE_CAHN_HILLIARD_2D = 7, PINNK_PDE_VALUE = 8, PINNK_PDE_DX = 9,
+       PINNK_PDE_WAVE = 10,            /* u_tt - c^2 u_xx, jets [x:2, t:2]; p0 = c              (wave_equation.py:38-119)        */
+       PINNK_PDE_CONVECTION = 11,      /* u_t + v u_x, jets [x:1, t:1]; p0 = v                   (convection_equation.py:43-78)   */
+       PINNK_PDE_BLACK_SCHOLES = 12,   /* V_t + p0^2/2 S^2 V_SS + p1 S V_S - p1 V, jets [S:2, t:1] (black_scholes.py:44-94)        */
+       PINNK_PDE_PENDULUM = 13 };      /* u_tt + p0 sin u, jets [t:2]; p0 = g / L                (pendulum_equation.py:60-94)     */
 enum { PINNK_LOSS_MSE = 0, PINNK_LOSS_MAE = 1, PINNK_LOSS_HUBER = 2 };
 
 typedef struct {
   int32_t kind;          /* PINNK_PDE_*                                                        */
   int32_t compat_math;   /* HEAT: 0 = operator as written (u_t - a u_x), 1 = u_t - a u_xx */
-  float   p0;            /* alpha | nu | epsilon                                               */
-  float   p1;
+  float   p0;            /* alpha | nu | epsilon | c | v | sigma | g/L                         */
+  float   p1;            /* Black-Scholes: risk-free rate                                      */
 } PinnkPde;
 
 typedef struct {

@@ -167,9 +167,11 @@ def jet_spec(pde: str, dimension: int = 1, compat: str = "reference"):
     d = dimension
     e = lambda i: [1.0 if k == i else 0.0 for k in range(d + 1)]
     t_dir = (e(d), 1)
+    if pde == "pendulum":
+        return [(e(d), 2)]
     if d == 1:
         order = {"heat": 1 if compat == "reference" else 2, "burgers": 2, "kdv": 3,
-                 "allen_cahn": 2, "cahn_hilliard": 4, "wave": 2, "convection": 1}[pde]
+                 "allen_cahn": 2, "cahn_hilliard": 4, "wave": 2, "convection": 1, "black_scholes": 2}[pde]
         return [(e(0), order), (e(d), 2) if pde == "wave" else t_dir]
     if compat == "reference":
         # every multi-dim residual degenerates; only u and u_t enter.
@@ -181,10 +183,15 @@ def jet_spec(pde: str, dimension: int = 1, compat: str = "reference"):
 
 
 def residual_from_jet(pde: str, j: Jet, params: Dict[str, float], dimension: int = 1,
-                      compat: str = "reference") -> torch.Tensor:
+                      compat: str = "reference", x=None) -> torch.Tensor:
     u, dirs = j
     fact = [1.0, 1.0, 2.0, 6.0, 24.0]
     D = lambda d, k: fact[k] * dirs[d][k - 1]
+    if pde == "pendulum":
+        return D(0, 2) + (params.get("g", 9.81) / params.get("L", 1.0)) * torch.sin(u)
+    if pde == "black_scholes" and dimension == 1:
+        sg, rf = params.get("sigma", 0.2), params.get("r", 0.05)
+        return D(1, 1) + 0.5 * sg ** 2 * x ** 2 * D(0, 2) + rf * x * D(0, 1) - rf * u
     if dimension == 1:
         u_t = D(1, 1)
         if pde == "heat":
@@ -225,7 +232,7 @@ def residual_from_jet(pde: str, j: Jet, params: Dict[str, float], dimension: int
 def residual(model, pde: str, x, t, params=None, dimension=1, compat="reference"):
     xt = torch.cat([x, t], dim=1)
     j = network_jet(model, seed_jet(xt, jet_spec(pde, dimension, compat)))
-    return residual_from_jet(pde, j, params or {}, dimension, compat)
+    return residual_from_jet(pde, j, params or {}, dimension, compat, x=x)
 
 
 def flat_grad(model: nn.Module, loss: torch.Tensor) -> torch.Tensor:

@@ -370,10 +370,38 @@ def convection_residual(model, x, t, velocity=1.0, dimension=1):
     return u_t + v * u_x
 
 
+def black_scholes_residual(model, x, t, sigma=0.2, r=0.05, dimension=1):
+    """black_scholes.py:44-94 (1-D branch): V_t + sigma^2/2 S^2 V_SS + r S V_S - r V; flips every parameter to
+    requires_grad and the model to train mode (:61-66)."""
+    if dimension != 1:
+        raise NotImplementedError("black_scholes: 1-D only in the oracle")
+    x = x.detach().requires_grad_(True)
+    t = t.detach().requires_grad_(True)
+    for p in model.parameters():
+        p.requires_grad_(True)
+    model.train()
+    d = compute_derivatives(model, x, t, [1, 2], [1], dimension)
+    V = model(torch.cat([x, t], dim=1))
+    return d["dt"] + 0.5 * sigma ** 2 * x ** 2 * d["dx2"] + r * x * d["dx"] - r * V
+
+
+def pendulum_residual(model, x, t, g=9.81, L=1.0, dimension=1):
+    """pendulum_equation.py:60-94: u_tt + (g/L) sin u (no spatial derivative enters)."""
+    x = x.detach().requires_grad_(True)
+    t = t.detach().requires_grad_(True)
+    for p in model.parameters():
+        p.requires_grad_(True)
+    model.train()
+    d = compute_derivatives(model, x, t, [], [1, 2], dimension)
+    u = model(torch.cat([x, t], dim=1))
+    return d["dt2"] + (g / L) * torch.sin(u)
+
+
 RESIDUALS: Dict[str, Callable] = {
     "heat": heat_residual, "burgers": burgers_residual, "kdv": kdv_residual,
     "allen_cahn": allen_cahn_residual, "cahn_hilliard": cahn_hilliard_residual,
     "wave": wave_residual, "convection": convection_residual,
+    "black_scholes": black_scholes_residual, "pendulum": pendulum_residual,
 }
 
 
@@ -423,6 +451,24 @@ def initial_condition_fn(pde: str, ic: Dict, domain, params: Dict, dimension: in
             A, k = ic.get("amplitude", 1.0), ic.get("frequency", 2.0)
             return lambda x, t: A * torch.sin(k * torch.pi * x)
         raise ValueError(f"Unsupported initial condition type: {kind}")
+    if pde == "black_scholes":
+        kind = ic.get("type", "call_option")                       # black_scholes.py:128-151
+        if kind in ("call_option", "option"):
+            K = ic.get("strike_price", ic.get("strike", 1.0))
+            return lambda x, t: torch.maximum(x - K, torch.zeros_like(x))
+        raise ValueError(f"Unsupported initial condition type: {kind}")
+    if pde == "pendulum":
+        kind = ic.get("type", "small_angle")                       # pendulum_equation.py:125-156
+        if kind == "small_angle":
+            th0 = ic.get("initial_angle", 0.1)
+            return lambda x, t: torch.full_like(x, th0)
+        if kind == "sine":
+            a, f = ic.get("amplitude", 1.0), ic.get("frequency", 1.0)
+            return lambda x, t: a * torch.sin(f * x)
+        if kind == "gaussian":
+            a, c, sg = ic.get("amplitude", 1.0), ic.get("center", 0.0), ic.get("sigma", 0.1)
+            return lambda x, t: a * torch.exp(-((x - c) ** 2) / (2 * sg ** 2))
+        raise ValueError(f"Unknown initial condition type: {kind}")
     if pde in ("allen_cahn", "cahn_hilliard"):
         kind = ic.get("type", "tanh")
         if kind == "tanh":

@@ -9,13 +9,13 @@ from .functional import (compute_loss, compute_residual, jets, loss_and_flat_gra
                          score_residual)
 from .neural_networks import (Config, FeedForwardNetwork, FourierNetwork, ModelConfig, PINNModel, ResNet,
                               SIREN, make_model)
-from .pdes import (AllenCahnEquation, BurgersEquation, CahnHilliardEquation, ConvectionEquation, HeatEquation,
-                   KdVEquation, PDEBase, PDEConfig, WaveEquation, create_pde)
+from .pdes import (AllenCahnEquation, BlackScholesEquation, BurgersEquation, CahnHilliardEquation, ConvectionEquation,
+                   HeatEquation, KdVEquation, PDEBase, PDEConfig, PendulumEquation, WaveEquation, create_pde)
 from .training import PDETrainer, TrainingConfig
 from .dropin import patch_reference
 
 __all__ = ["compute_loss", "compute_residual", "jets", "loss_and_flat_grad", "model_forward", "score_residual",
            "Config", "ModelConfig", "PINNModel", "FeedForwardNetwork", "ResNet", "SIREN", "FourierNetwork",
            "make_model", "PDEConfig", "PDEBase", "HeatEquation", "BurgersEquation", "KdVEquation",
-           "AllenCahnEquation", "CahnHilliardEquation", "WaveEquation", "ConvectionEquation", "create_pde", "PDETrainer", "TrainingConfig",
+           "AllenCahnEquation", "CahnHilliardEquation", "WaveEquation", "ConvectionEquation", "BlackScholesEquation", "PendulumEquation", "create_pde", "PDETrainer", "TrainingConfig",
            "patch_reference"]

@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("PINNK_LIB", os.path.join(HERE, "libpinnk.so"))     # 
 OP_LINEAR, OP_ACT, OP_LAYERNORM, OP_SKIP_SAVE, OP_SKIP_ADD, OP_SINCOS = 1, 2, 3, 4, 5, 6
 ACT_TANH, ACT_SIN = 1, 2
 (PDE_HEAT, PDE_BURGERS, PDE_KDV, PDE_ALLEN_CAHN, PDE_CAHN_HILLIARD, PDE_UT_ONLY, PDE_UT_ALLEN_CAHN_ND,
- PDE_CAHN_HILLIARD_2D, PDE_VALUE, PDE_DX, PDE_WAVE, PDE_CONVECTION) = range(12)
+ PDE_CAHN_HILLIARD_2D, PDE_VALUE, PDE_DX, PDE_WAVE, PDE_CONVECTION, PDE_BLACK_SCHOLES, PDE_PENDULUM) = range(14)
 LOSS_MSE, LOSS_MAE, LOSS_HUBER = 0, 1, 2
 ABI_VERSION = 1
 

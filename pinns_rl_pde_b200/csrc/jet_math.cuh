@@ -209,6 +209,9 @@ enum PdeKind : int {
   PDE_DX = 9,              // r = u_x            (Heat periodic BC derivative match)
   PDE_WAVE = 10,           // r = u_tt - c^2 u_xx          (1-D; spec [x order 2, t order 2])   wave_equation.py:38-119
   PDE_CONVECTION = 11,     // r = u_t + v u_x              (1-D; spec [x order 1, t order 1])   convection_equation.py:43-78
+  PDE_BLACK_SCHOLES = 12,  // r = V_t + sigma^2/2 S^2 V_SS + r S V_S - r V   (1-D; spec [S order 2, t order 1]; needs the
+                           //     coordinate S = x of the point: `xs`)   black_scholes.py:44-94
+  PDE_PENDULUM = 13,       // r = u_tt + (g/L) sin u       (spec [t order 2], one direction)   pendulum_equation.py:60-94
 };
 
 struct PdeDesc {
@@ -222,7 +225,7 @@ struct PdeDesc {
 // For 1-D PDEs the spec is [x (order K), t (order 1)]: U = {u, a_x1..a_xK, a_t1}.
 // Returns r and, if dU != nullptr, dr/dU[col] for every column.
 template <typename T>
-PK_HD T pde_residual(const PdeDesc& pd, const JetSpec& js, const T* U, T* dU) {
+PK_HD T pde_residual(const PdeDesc& pd, const JetSpec& js, const T* U, T* dU, T xs = T(0)) {
   const int nc = js.ncols;
   if (dU) for (int c = 0; c < nc; ++c) dU[c] = T(0);
   const T u = U[0];
@@ -277,6 +280,15 @@ PK_HD T pde_residual(const PdeDesc& pd, const JetSpec& js, const T* U, T* dU) {
     case PDE_CONVECTION: {
       if (dU) { dU[ct] = T(1); dU[cx] = p0; }
       return u_t + p0 * U[cx];
+    }
+    case PDE_BLACK_SCHOLES: {   // p0 = sigma, p1 = risk-free rate; xs = S
+      const T rf = T(pd.p1), hs2 = T(0.5) * p0 * p0 * xs * xs;
+      if (dU) { dU[ct] = T(1); dU[cx + 1] = T(2) * hs2; dU[cx] = rf * xs; dU[0] = -rf; }
+      return u_t + hs2 * T(2) * U[cx + 1] + rf * xs * U[cx] - rf * u;
+    }
+    case PDE_PENDULUM: {        // one direction (t, order 2): ct = 1, u_tt = 2 a_t2; p0 = g / L
+      if (dU) { dU[ct + 1] = T(2); dU[0] = p0 * cos(u); }
+      return T(2) * U[ct + 1] + p0 * sin(u);
     }
     case PDE_BURGERS: {
       const T ux = U[cx], uxx = T(2) * U[cx + 1];

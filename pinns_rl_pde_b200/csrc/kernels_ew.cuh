@@ -709,20 +709,22 @@ struct SegmentDev {
 };
 
 // rows are relative to the chunk: U / Ub hold [chunk_rows, C]; `row_lo`.. is the part of the segment in this chunk.
+// xs / xs_stride: first spatial coordinate of the chunk's points (only the Black-Scholes residual reads it)
 __global__ void epilogue_kernel(const float* __restrict__ U, float* __restrict__ Ub, JetSpec js, SegmentDev sg,
-                                int64_t chunk_row0, int64_t lo, int64_t hi) {
+                                int64_t chunk_row0, int64_t lo, int64_t hi, const float* __restrict__ xs, int xs_stride) {
   const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // absolute row of the call
   double part = 0.0;
   if (i < hi) {
     const int64_t r = i - chunk_row0;
     float u[kMaxCols], du[kMaxCols];
     for (int c = 0; c < js.ncols; ++c) u[c] = U[r * js.ncols + c];
-    float e = pde_residual<float>(sg.pde, js, u, du);
+    const bool need_x = sg.pde.kind == PDE_BLACK_SCHOLES;
+    float e = pde_residual<float>(sg.pde, js, u, du, need_x ? xs[r * xs_stride] : 0.f);
     float du2[kMaxCols];
     if (sg.pair_offset != 0) {
       const int64_t r2 = r + sg.pair_offset;
       for (int c = 0; c < js.ncols; ++c) u[c] = U[r2 * js.ncols + c];
-      e -= pde_residual<float>(sg.pde, js, u, du2);
+      e -= pde_residual<float>(sg.pde, js, u, du2, need_x ? xs[r2 * xs_stride] : 0.f);
     }
     const int64_t k = i - sg.row_start;
     if (sg.target) e -= sg.target[k];
@@ -753,14 +755,15 @@ __global__ void epilogue_kernel(const float* __restrict__ U, float* __restrict__
 
 // |r| and (sum|r|, sum r^2, max|r|, count) for the adaptive samplers
 __global__ void score_kernel(const float* __restrict__ U, JetSpec js, PdeDesc pde, int64_t rows,
-                             float* __restrict__ abs_out, double* __restrict__ stats) {
+                             float* __restrict__ abs_out, double* __restrict__ stats, const float* __restrict__ xs,
+                             int xs_stride) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   double s1 = 0.0, s2 = 0.0;
   float mx = 0.f;
   if (r < rows) {
     float u[kMaxCols];
     for (int c = 0; c < js.ncols; ++c) u[c] = U[r * js.ncols + c];
-    const float a = fabsf(pde_residual<float>(pde, js, u, nullptr));
+    const float a = fabsf(pde_residual<float>(pde, js, u, nullptr, pde.kind == PDE_BLACK_SCHOLES ? xs[r * xs_stride] : 0.f));
     if (abs_out) abs_out[r] = a;
     s1 = a; s2 = (double)a * a; mx = a;
   }

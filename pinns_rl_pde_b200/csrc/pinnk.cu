@@ -806,6 +806,7 @@ static int loss_fusable_segment(pinnk_plan_t pl, const PinnkSegment* segs, int n
     if (found >= 0) return -1;
     if (g.row_start > p0 || g.row_start + g.row_count < p0 + cn) return -1;
     if (g.target || g.error_out || g.error_grad || g.pair_offset != 0) return -1;
+    if (g.pde.kind == PDE_BLACK_SCHOLES) return -1;            // needs the point coordinate, which the GEMM epilogue does not have
     found = s;
   }
   return found;
@@ -906,7 +907,8 @@ extern "C" int pinnk_loss_step(pinnk_plan_t plan, const float* const* params, co
       sd.target = g.target; sd.error_out = g.error_out; sd.error_grad = flat_grad ? g.error_grad : nullptr;
       sd.loss_slot = loss_sums ? loss_sums + g.component : nullptr;
       ProfScope ps(PC_EPILOGUE, c.st);
-      epilogue_kernel<<<blocks_for(hi - lo, threads), threads, 0, c.st>>>(c.U(), flat_grad ? c.Ub() : nullptr, plan->js, sd, p0, lo, hi);
+      epilogue_kernel<<<blocks_for(hi - lo, threads), threads, 0, c.st>>>(c.U(), flat_grad ? c.Ub() : nullptr, plan->js, sd, p0, lo, hi,
+                                                                            c.x, c.t ? plan->js.in_dim - 1 : plan->js.in_dim);
       PK_LAUNCH_OK();
     }
     if (flat_grad) {
@@ -930,7 +932,8 @@ extern "C" int pinnk_score(pinnk_plan_t plan, const float* const* params, const 
     ChunkCtx c = make_ctx(plan, params, x, t, p0, cn, ws, stream);
     rc = dispatch_maxk(plan->maxk, [&](auto mk) { return forward_chunk<decltype(mk)::value>(c, false); });
     if (rc) return rc;
-    score_kernel<<<blocks_for(cn, threads), threads, 0, c.st>>>(c.U(), plan->js, pd, cn, abs_out ? abs_out + p0 : nullptr, stats);
+    score_kernel<<<blocks_for(cn, threads), threads, 0, c.st>>>(c.U(), plan->js, pd, cn, abs_out ? abs_out + p0 : nullptr, stats,
+                                                                  c.x, c.t ? plan->js.in_dim - 1 : plan->js.in_dim);
     PK_LAUNCH_OK();
   }
   return 0;

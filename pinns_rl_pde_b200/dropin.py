@@ -19,7 +19,8 @@ _PATCHED = {}
 def patch_reference(compat: str = "reference"):
     mods = {"heat_equation": "HeatEquation", "burgers_equation": "BurgersEquation", "kdv_equation": "KdVEquation",
             "allen_cahn": "AllenCahnEquation", "cahn_hilliard": "CahnHilliardEquation",
-            "wave_equation": "WaveEquation", "convection_equation": "ConvectionEquation"}
+            "wave_equation": "WaveEquation", "convection_equation": "ConvectionEquation",
+            "black_scholes": "BlackScholesEquation", "pendulum_equation": "PendulumEquation"}
     try:
         base = importlib.import_module("pinnrl.pdes.pde_base")
     except ImportError as e:   # pragma: no cover - pinnrl is not installed on the GPU box

@@ -33,6 +33,7 @@ class Segment:
     component: int = 0
     weight: float = 1.0
     p0: float = 0.0
+    p1: float = 0.0
     compat_math: int = 0
     pair_offset: int = 0
     target: Optional[torch.Tensor] = None
@@ -145,7 +146,7 @@ class JetEngine:
         keep = []
         for i, s in enumerate(segments):
             c = segs[i]
-            c.pde.kind, c.pde.compat_math, c.pde.p0, c.pde.p1 = s.kind, s.compat_math, s.p0, 0.0
+            c.pde.kind, c.pde.compat_math, c.pde.p0, c.pde.p1 = s.kind, s.compat_math, s.p0, s.p1
             c.component, c.loss_kind, c.huber_delta, c.weight = s.component, s.loss_kind, s.huber_delta, s.weight
             c.row_start, c.row_count, c.pair_offset = s.row_start, s.row_count, s.pair_offset
             for name in ("target", "error_out", "error_grad"):
@@ -168,13 +169,13 @@ class JetEngine:
         return loss_sums, (flat_grad if want_grad else None)
 
     def score(self, x, t, kind: int, p0: float = 0.0, compat_math: int = 0, want_abs: bool = True,
-              stats: Optional[torch.Tensor] = None):
+              stats: Optional[torch.Tensor] = None, p1: float = 0.0):
         """Forward-only |r| and stats = [sum|r|, sum r^2, max|r|, count] (fp64, device)."""
         x, t, n = self._xt(x, t)
         abs_r = torch.empty(n, dtype=torch.float32, device=self.device) if want_abs else None
         if stats is None:
             stats = torch.zeros(4, dtype=torch.float64, device=self.device)
-        pde = L.PinnkPde(kind, compat_math, p0, 0.0)
+        pde = L.PinnkPde(kind, compat_math, p0, p1)
         if n:
             L.check(self.lib.pinnk_score(self.handle, self._params(), x.data_ptr(), self._ptr(t), n, C.byref(pde),
                                          self._ptr(abs_r), stats.data_ptr(), self.workspace.data_ptr(),

@@ -25,11 +25,12 @@ _PDE_NAMES = {
     "HeatEquation": "heat", "BurgersEquation": "burgers", "KdVEquation": "kdv",
     "AllenCahnEquation": "allen_cahn", "CahnHilliardEquation": "cahn_hilliard",
     "WaveEquation": "wave", "ConvectionEquation": "convection",
+    "BlackScholesEquation": "black_scholes", "PendulumEquation": "pendulum",
 }
-_ORDER_1D = {"burgers": 2, "kdv": 3, "allen_cahn": 2, "cahn_hilliard": 4, "wave": 2, "convection": 1}
+_ORDER_1D = {"burgers": 2, "kdv": 3, "allen_cahn": 2, "cahn_hilliard": 4, "wave": 2, "convection": 1, "black_scholes": 2}
 _KIND_1D = {"heat": L.PDE_HEAT, "burgers": L.PDE_BURGERS, "kdv": L.PDE_KDV,
             "allen_cahn": L.PDE_ALLEN_CAHN, "cahn_hilliard": L.PDE_CAHN_HILLIARD,
-            "wave": L.PDE_WAVE, "convection": L.PDE_CONVECTION}
+            "wave": L.PDE_WAVE, "convection": L.PDE_CONVECTION, "black_scholes": L.PDE_BLACK_SCHOLES}
 
 
 class UnsupportedPDE(NotImplementedError):
@@ -70,6 +71,11 @@ def _velocity_1d(pde) -> float:
     return float(v)
 
 
+def residual_p1(pde) -> float:
+    """Second scalar parameter of the residual (PinnkPde.p1): the Black-Scholes risk-free rate."""
+    return _float_param(pde, "r", 0.05) if pde_name(pde) == "black_scholes" else 0.0
+
+
 def residual_spec(pde) -> Tuple[List, int, float, int]:
     """(directions, PINNK_PDE kind, p0, compat_math) for ``pde`` -- the jets its residual needs."""
     name = pde_name(pde)
@@ -80,15 +86,19 @@ def residual_spec(pde) -> Tuple[List, int, float, int]:
     p0 = {"heat": lambda: _float_param(pde, "alpha"), "burgers": lambda: _float_param(pde, "nu", 0.01),
           "kdv": lambda: 0.0, "allen_cahn": lambda: _float_param(pde, "epsilon", 0.1),
           "cahn_hilliard": lambda: _float_param(pde, "epsilon", 0.1),
-          "wave": lambda: _float_param(pde, "c", 1.0), "convection": lambda: _velocity_1d(pde)}[name]()
+          "wave": lambda: _float_param(pde, "c", 1.0), "convection": lambda: _velocity_1d(pde),
+          "black_scholes": lambda: _float_param(pde, "sigma", 0.2),
+          "pendulum": lambda: _float_param(pde, "g", 9.81) / _float_param(pde, "L", 1.0)}[name]()
     unit = lambda i: tuple(1.0 if k == i else 0.0 for k in range(d + 1))
     t_dir = (unit(d), 1)
-    if name in ("wave", "convection") and d != 1:
+    if name in ("wave", "convection", "black_scholes", "pendulum") and d != 1:
         # wave_equation.py:78-107 degenerates to u_tt, convection_equation.py:67-76 raises in autograd.grad
         # (no allow_unused): neither is on the hot path in more than one space dimension
         raise UnsupportedPDE(f"{name}: only the 1-D operator is implemented on the B200 path")
     if name == "wave":
         return [(unit(0), 2), (unit(1), 2)], L.PDE_WAVE, p0, 0           # second-order time jets: u_tt = 2 a_t2
+    if name == "pendulum":
+        return [(unit(1), 2)], L.PDE_PENDULUM, p0, 0                      # an ODE in t: no spatial jets at all
     if d == 1:
         if name == "heat":
             math = compat == "math"
@@ -196,10 +206,13 @@ def model_forward(model: nn.Module, xt: torch.Tensor) -> torch.Tensor:
 
 def compute_residual(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor) -> torch.Tensor:
     dirs, kind, p0, cm = residual_spec(pde)
+    if pde_name(pde) in ("black_scholes", "pendulum"):
+        for p in model.parameters():            # black_scholes.py:61-63, pendulum_equation.py:79-81: side effect of the reference
+            p.requires_grad_(True)
     x, t = _prep(model, x, t)
     n = x.shape[0]
     eng = get_engine(model, dirs, n)
-    proto = Segment(kind=kind, row_start=0, row_count=n, p0=p0, compat_math=cm)
+    proto = Segment(kind=kind, row_start=0, row_count=n, p0=p0, p1=residual_p1(pde), compat_math=cm)
     if not model.training:
         model.train()   # pde_base.py:638 -- the reference flips the model into training mode here
     return _ErrorFn.apply(eng, proto, x, t, *eng.program.grad_params)
@@ -211,7 +224,7 @@ def score_residual(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, want
     dirs, kind, p0, cm = residual_spec(pde)
     x, t = _prep(model, x, t)
     eng = get_engine(model, dirs, x.shape[0])
-    return eng.score(x, t, kind, p0, cm, want_abs, stats)
+    return eng.score(x, t, kind, p0, cm, want_abs, stats, residual_p1(pde))
 
 
 def _weights(pde, heat: bool) -> Tuple[float, float, float, float, bool]:
@@ -278,7 +291,7 @@ def _build_calls(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_glob
     calls = []
     eng_r = get_engine(model, dirs, n, program=program)
     calls.append((eng_r, x, t, [Segment(kind=kind, row_start=0, row_count=n, component=0, weight=1.0 / max(n, 1),
-                                        p0=p0, compat_math=cm, **mk)]))
+                                        p0=p0, p1=residual_p1(pde), compat_math=cm, **mk)]))
     dom, td = pde.domain, pde.time_domain
     if heat:
         training = getattr(pde.config, "training", None)

@@ -495,9 +495,61 @@ class ConvectionEquation(_SineIC):
         return sol
 
 
+class BlackScholesEquation(PDEBase):
+    """black_scholes.py: r = V_t + sigma^2/2 S^2 V_SS + r S V_S - r V (keys ``sigma`` 0.2, ``r`` 0.05); the residual's
+    coefficients depend on the point's coordinate S."""
+
+    @property
+    def sigma(self):
+        return self.get_parameter("sigma", default=0.2)
+
+    @property
+    def r(self):
+        return self.get_parameter("r", default=0.05)
+
+    def _create_boundary_condition(self, bc_type, params):
+        if bc_type == "initial":
+            kind = params.get("type", "call_option")
+            if kind in ("call_option", "option"):
+                K = params.get("strike_price", params.get("strike", 1.0))
+                if self.dimension == 1:
+                    return lambda x, t: torch.maximum(x - K, torch.zeros_like(x))
+                return lambda x, t: torch.maximum(torch.sum(x, dim=1, keepdim=True) - K, torch.zeros_like(x[:, 0:1]))
+            raise ValueError(f"Unsupported initial condition type: {kind}")
+        return super()._create_boundary_condition(bc_type, params)
+
+
+class PendulumEquation(PDEBase):
+    """pendulum_equation.py: r = u_tt + (g/L) sin u (keys ``g`` 9.81, ``L`` 1.0): an ODE in t, second-order time jets only."""
+
+    @property
+    def g(self):
+        return self.get_parameter("g", default=9.81)
+
+    @property
+    def L(self):
+        return self.get_parameter("L", default=1.0)
+
+    def _create_boundary_condition(self, bc_type, params):
+        if bc_type == "initial":                                  # pendulum_equation.py:125-156
+            kind = params.get("type", "small_angle")
+            if kind == "small_angle":
+                th0 = params.get("initial_angle", 0.1)
+                return lambda x, t: torch.full_like(x, th0)
+            if kind == "sine":
+                a, f = params.get("amplitude", 1.0), params.get("frequency", 1.0)
+                return lambda x, t: a * torch.sin(f * x)
+            if kind == "gaussian":
+                a, c, sg = params.get("amplitude", 1.0), params.get("center", 0.0), params.get("sigma", 0.1)
+                return lambda x, t: a * torch.exp(-((x - c) ** 2) / (2 * sg ** 2))
+            raise ValueError(f"Unknown initial condition type: {kind}")
+        return super()._create_boundary_condition(bc_type, params)
+
+
 _FACTORY = {"heat": HeatEquation, "burgers": BurgersEquation, "kdv": KdVEquation,
             "allen_cahn": AllenCahnEquation, "cahn_hilliard": CahnHilliardEquation,
-            "wave": WaveEquation, "convection": ConvectionEquation}
+            "wave": WaveEquation, "convection": ConvectionEquation,
+            "black_scholes": BlackScholesEquation, "pendulum": PendulumEquation}
 
 
 def create_pde(name: str, config: PDEConfig) -> PDEBase:

@@ -54,6 +54,8 @@ from pinnrl.pdes.cahn_hilliard import CahnHilliardEquation  # noqa: E402
 from pinnrl.pdes.allen_cahn import AllenCahnEquation  # noqa: E402
 from pinnrl.pdes.wave_equation import WaveEquation  # noqa: E402
 from pinnrl.pdes.convection_equation import ConvectionEquation  # noqa: E402
+from pinnrl.pdes.black_scholes import BlackScholesEquation  # noqa: E402
+from pinnrl.pdes.pendulum_equation import PendulumEquation  # noqa: E402
 
 from oracle import ref_port, jets_oracle  # noqa: E402
 
@@ -92,6 +94,10 @@ PDES = {
                  bcs={"dirichlet": {"value": 0.0}}, ic={"type": "sine", "amplitude": 1.0, "frequency": 2.0}, exact={}),
     "convection": dict(cls=ConvectionEquation, domain=[[0.0, 1.0]], time=[0.0, 1.0], params={"velocity": 0.7},
                        bcs={"dirichlet": {"value": 0.0}}, ic={"type": "sine", "amplitude": 1.0, "frequency": 2.0}, exact={}),
+    "black_scholes": dict(cls=BlackScholesEquation, domain=[[0.5, 2.0]], time=[0.0, 1.0], params={"sigma": 0.3, "r": 0.04},
+                          bcs={"dirichlet": {"value": 0.0}}, ic={"type": "call_option", "strike_price": 1.0}, exact={}),
+    "pendulum": dict(cls=PendulumEquation, domain=[[0.0, 1.0]], time=[0.0, 2.0], params={"g": 9.81, "L": 2.0},
+                     bcs={"dirichlet": {"value": 0.0}}, ic={"type": "small_angle", "initial_angle": 0.2}, exact={}),
 }
 
 
@@ -288,7 +294,9 @@ def main_next():
     reports = [run_case("x_wave_ff_small", "wave", "feedforward", 32, 3, 96),
                run_case("x_wave_ff128", "wave", "feedforward", 128, 3, 64),
                run_case("x_convection_ff128", "convection", "feedforward", 128, 4, 96),
-               run_case("x_convection_siren_small", "convection", "siren", 32, 3, 64, omega_0=30.0)]
+               run_case("x_convection_siren_small", "convection", "siren", 32, 3, 64, omega_0=30.0),
+               run_case("x_black_scholes_ff128", "black_scholes", "feedforward", 128, 3, 96),
+               run_case("x_pendulum_ff128", "pendulum", "feedforward", 128, 3, 64)]
     path = os.path.join(HERE, "golden_report.json")
     old = json.load(open(path)) if os.path.exists(path) else []
     old = [r for r in old if r["case"] not in {r2["case"] for r2 in reports}]

@@ -25,6 +25,10 @@ PDES = {
                  bcs={"dirichlet": {"value": 0.0}}, ic={"type": "sine", "amplitude": 1.0, "frequency": 2.0}, exact={}),
     "convection": dict(domain=[[0.0, 1.0]], time=[0.0, 1.0], params={"velocity": 0.7},
                        bcs={"dirichlet": {"value": 0.0}}, ic={"type": "sine", "amplitude": 1.0, "frequency": 2.0}, exact={}),
+    "black_scholes": dict(domain=[[0.5, 2.0]], time=[0.0, 1.0], params={"sigma": 0.3, "r": 0.04},
+                          bcs={"dirichlet": {"value": 0.0}}, ic={"type": "call_option", "strike_price": 1.0}, exact={}),
+    "pendulum": dict(domain=[[0.0, 1.0]], time=[0.0, 2.0], params={"g": 9.81, "L": 2.0},
+                     bcs={"dirichlet": {"value": 0.0}}, ic={"type": "small_angle", "initial_angle": 0.2}, exact={}),
 }
 
 

@@ -64,5 +64,12 @@ double hm_pde(int kind, int compat_math, double p0, int ndirs, const int* orders
   PdeDesc pd{kind, compat_math, (float)p0, 0.f};
   return pde_residual<double>(pd, js, U, dU);
 }
+double hm_pde_x(int kind, double p0, double p1, int ndirs, const int* orders, int in_dim, const double* U, double* dU, double xs) {
+  JetSpec js{}; js.ndirs = ndirs; js.in_dim = in_dim; int col = 1;
+  for (int d = 0; d < ndirs; ++d) { js.order[d] = orders[d]; js.col0[d] = col; col += orders[d]; }
+  js.ncols = col;
+  PdeDesc pd{kind, 0, (float)p0, (float)p1};
+  return pde_residual<double>(pd, js, U, dU, xs);
+}
 double hm_rho(int kind, double delta, double e, double* drho) { return loss_rho<double>(kind, delta, e, drho); }
 }

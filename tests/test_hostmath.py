@@ -25,6 +25,7 @@ def hm(tmp_path_factory):
                            os.path.join(HERE, "hostmath", "hostmath.cpp")])
     lib = ctypes.CDLL(out)
     lib.hm_pde.restype = D
+    lib.hm_pde_x.restype = D
     lib.hm_rho.restype = D
     return lib
 
@@ -150,6 +151,30 @@ def test_pde_epilogue_and_partials(hm, kind, compat, name, dim, cstr, orders):
         rt = jo.residual_from_jet(name, (Ut[0:1], dirs), params, dim, cstr)
         (g,) = torch.autograd.grad(rt.sum(), Ut, allow_unused=True)
         assert abs(r - rt.item()) <= 1e-6 * max(1.0, abs(rt.item()))   # PdeDesc carries fp32 parameters
+        np.testing.assert_allclose(dU, g.numpy(), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("kind,name,orders", [(12, "black_scholes", [2, 1]), (13, "pendulum", [2])])
+def test_pde_epilogues_with_coordinate_or_single_direction(hm, kind, name, orders):
+    """Black-Scholes (coefficients depend on the point coordinate S) and the pendulum ODE (one jet direction, t, order 2)."""
+    rng = np.random.default_rng(kind)
+    params = {"sigma": 0.37, "r": 0.21, "g": 9.81, "L": 9.81 / 0.37}
+    ncols = 1 + sum(orders)
+    for trial in range(10):
+        U = rng.standard_normal(ncols)
+        xs = 0.5 + rng.random() * 2
+        dU = np.zeros(ncols)
+        iords = (ctypes.c_int * len(orders))(*orders)
+        r = hm.hm_pde_x(kind, D(0.37), D(0.21), len(orders), iords, 2, _p(U), _p(dU), D(xs))
+        Ut = torch.tensor(U, dtype=torch.float64, requires_grad=True)
+        dirs, col = [], 1
+        for o in orders:
+            dirs.append([Ut[col + k:col + k + 1] for k in range(o)])
+            col += o
+        rt = jo.residual_from_jet(name, (Ut[0:1], dirs), params, 1, "reference", x=torch.tensor([xs], dtype=torch.float64))
+        (g,) = torch.autograd.grad(rt.sum(), Ut, allow_unused=True)
+        g = torch.zeros_like(Ut) if g is None else g
+        assert abs(r - rt.item()) <= 1e-6 * max(1.0, abs(rt.item()))
         np.testing.assert_allclose(dU, g.numpy(), rtol=1e-6, atol=1e-7)
 
 
