@@ -281,19 +281,21 @@ def run_ours(args):
         gemm = {k: prof[k] for k in ("gemm_fwd", "gemm_dgrad", "gemm_wgrad")}
         dom = max(gemm, key=lambda k: gemm[k][0])
         ms_dom, n_dom = gemm[dom]
-        from pinns_rl_pde_b200 import engine as _engine
-        n_chunks = max(1, -(-n_local // _engine.MAX_CHUNK_POINTS))
+        from pinns_rl_pde_b200 import engine as _engine, functional as _F
+        chunk = _engine.get_engine(model, _F.residual_spec(pde)[0], n_local).chunk     # the cached engine the steps used
+        n_chunks = max(1, -(-n_local // chunk))
         rows_per_launch = JET_COLS * n_local / n_chunks                      # stacked jet rows one launch processes
         # algorithmic bytes per row of 128 floats (DESIGN.md "kernels"): Linear+tanh reads X and writes Y (the pre-activation
-        # stash is elided; the loss-fused last layer reads X and writes dZ instead); dgrad+adjoint reads dZ and the stashed Y,
-        # writes dZ_prev; wgrad reads dZ and X
-        bytes_per_row = {"gemm_fwd": 2 * 512, "gemm_dgrad": 3 * 512, "gemm_wgrad": 2 * 512}[dom]
+        # stash is elided); dgrad+adjoint reads dZ and the stashed Y, writes dZ_prev; wgrad reads dZ and X; the loss-fused last
+        # hidden layer (own class fwd_loss_fused) reads X and writes dZ
+        BYTES_PER_ROW = {"gemm_fwd": 2 * 512, "gemm_dgrad": 3 * 512, "gemm_wgrad": 2 * 512, "fwd_loss_fused": 2 * 512}
+        # big launches per chunk in each class (value-only BC/IC launches are tiny): 6 hidden layers forward (the 7th is the
+        # loss-fused launch), 7 wgrad, 6 fused dgrad+adjoint (the first hidden layer's dgrad is fused with the input layer's
+        # reverse: class first_linear_bwd)
+        PER_CHUNK = {"gemm_fwd": LAYERS - 2, "gemm_dgrad": LAYERS - 2, "gemm_wgrad": LAYERS - 1, "fwd_loss_fused": 1}
+        bytes_per_row = BYTES_PER_ROW[dom]
         flops_per_launch = 2 * rows_per_launch * HIDDEN * HIDDEN
-        # big launches per chunk in this class (value-only BC/IC launches are tiny): 6 hidden layers forward, 7 wgrad; 6 fused
-        # dgrad+adjoint launches (the first hidden layer's dgrad is fused with the input layer's reverse: class first_linear_bwd)
-        # (the last hidden layer's forward is the loss-fused launch: class fwd_loss_fused)
-        per_chunk = {"gemm_fwd": LAYERS - 2, "gemm_dgrad": LAYERS - 2, "gemm_wgrad": LAYERS - 1}[dom]
-        big = 2 * per_chunk * n_chunks                                       # two profiled steps
+        big = 2 * PER_CHUNK[dom] * n_chunks                                  # two profiled steps
         ms_launch = ms_dom / max(big, 1)
         peaks = {}
         try:
@@ -306,6 +308,12 @@ def run_ours(args):
             hbm, hbm_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md, of fallback)"
         bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
         tensor_peak = bf16 / 6.0                                              # /2 tf32, /3 three-pass split
+        per_kernel = {}
+        for k in BYTES_PER_ROW:
+            if k in prof and prof[k][1]:
+                ms_k = prof[k][0] / max(2 * PER_CHUNK[k] * n_chunks, 1)
+                gbs = BYTES_PER_ROW[k] * rows_per_launch / (ms_k * 1e-3) / 1e9
+                per_kernel[k] = {"launch_ms": ms_k, "achieved_gbs": gbs, "frac_hbm": gbs / hbm}
         achieved = bytes_per_row * rows_per_launch / (ms_launch * 1e-3) / 1e9
         traffic = None
         try:
@@ -316,7 +324,7 @@ def run_ours(args):
             pass
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                 "traffic": traffic, "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_per_row * rows_per_launch,
-                "launch_ms": ms_launch, "launches_per_step": n_dom // 2,
+                "launch_ms": ms_launch, "launches_per_step": n_dom // 2, "kernels": per_kernel,
                 "tensor": {"achieved_tflops": flops_per_launch / (ms_launch * 1e-3) / 1e12, "peak_tflops": tensor_peak,
                            "frac": flops_per_launch / (ms_launch * 1e-3) / 1e12 / tensor_peak,
                            "peak_source": "bf16_tflops_sustained / 2 (tf32) / 3 (3xTF32 split)"},

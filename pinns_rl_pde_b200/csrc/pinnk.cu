@@ -520,7 +520,6 @@ static int forward_chunk(const ChunkCtx& c, bool keep_stash = true) {
           if (tc_enabled() && i + 1 < n_ops - 1 && pl->ops[i + 1].op.kind == PINNK_OP_ACT && pl->ops[i + 1].skip_src < 0 &&
               jet_orders(js, k0, k1)) {
             const PinnkOp& a = pl->ops[i + 1].op;
-            ProfScope ps(PC_GEMM_FWD, c.st);
             const bool want_z = (keep_stash && !z_elided(pl, i)) || o.in_dim != 128;
             // last hidden layer: fold the output layer nn.Linear(width, 1) into the epilogue (partials in adj(0), which
             // is idle during the forward); forward-only callers then do not store the activation output either
@@ -537,6 +536,7 @@ static int forward_chunk(const ChunkCtx& c, bool keep_stash = true) {
               if (rcl == 0) { g_launches.fetch_add(1); c.loss_done = true; i = n_ops - 1; break; }
               if (rcl != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, std::string("tc_linear_act_fwd (loss fusion) launch failed: ") + cudaGetErrorString(cudaGetLastError()));
             }
+            ProfScope ps(PC_GEMM_FWD, c.st);          // (opened here: the loss-fused launch above is its own class)
             float* y_out = (fuse_out && !keep_stash) ? nullptr : c.stash(i + 1);
             int rc = tc_linear_act_fwd(in, W, b, want_z ? c.stash(i) : nullptr, y_out, c.n * js.ncols, o.in_dim, o.out_dim, k0, k1,
                                        a.act == PINNK_ACT_TANH ? 1 : 2, a.scale, pl->sm_count, c.st, w_out, fuse_out ? c.adj(0) : nullptr);
