@@ -23,6 +23,7 @@
 //     1 warp     MMA     : one elected thread issues tcgen05.mma / tcgen05.commit; owns TMEM alloc
 // Pipelines: smem full/empty mbarriers (loaders <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -504,6 +505,37 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
+// TMA tiled copy (cp.async.bulk.tensor.2d, SASS UTMALDG): one instruction moves a [box rows x 128 floats] tile of a row-major
+// matrix whose rows are wider than the tile (one K / N half of a 256-wide layer: 512-byte segments at a 1 KB stride) into
+// dense shared memory.  Rows past the end of the matrix are zero-filled and still counted in the transaction bytes.
+// (Before: one 512-byte cp.async.bulk per row from a single thread, ~50 cycles of issue each -- 3200 cycles per 64-row
+// tile, more than the tile's HBM time, bounded every 256-wide kernel.)
+__device__ __forceinline__ void tma_tile_2d(uint32_t dst_smem, const CUtensorMap* tm, int col0, int row0, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tm)), "r"(col0), "r"(row0), "r"(smem_u32(bar))
+               : "memory");
+}
+// Host: tensor map of a row-major fp32 matrix [rows, cols] with row stride ld floats, box = [box_rows x 128].
+// The driver entry point is looked up through the runtime (no link against libcuda).
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                        const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static inline bool make_tmap_rows(CUtensorMap* tm, const float* base, int64_t rows, int cols, int ld, int box_rows) {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || p == nullptr) return false;
+    fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {128u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // Optional stage timers (build with -DPINNK_STAGE_TIMERS): block 0 accumulates, per role, the cycles spent waiting on
 // each pipeline barrier; read back with pinnk_debug_stage_timers().  Slots: 0 tma:raw_empty  1 cvt:raw_full  2 cvt:empty
 // 3 cvt:work  4 mma:tempty  5 mma:full  6 mma:issue  7 epi:tfull  8 epi:work  9 tiles  10 total cycles of block 0
@@ -569,7 +601,7 @@ __global__ void __launch_bounds__((NLW + 4 * (64 / ECOLS) + 2) * 32, 1)
 linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
                       float* __restrict__ Y, int64_t M, int ldy_rt, int jet_cols, const float* __restrict__ Zs,
                       float* __restrict__ Yact, float omega, int ldx, OutFuse of, FirstLayer fl,
-                      TcLossFuse lfv) {
+                      TcLossFuse lfv, const __grid_constant__ CUtensorMap tmx) {
   static_assert(!LOSSF || (EPI == EPI_ACT && ACT == 1 && ECOLS == 16 && !ACCUM), "loss fusion: tanh forward epilogue only");
   // LDYC: compile-time row stride of Y / Zs / Yact (0 = use the runtime value): with it every row address of the
   // epilogue is base + immediate instead of a 64-bit multiply-add per access
@@ -668,10 +700,14 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
         { PK_T0(); mbar_wait(&raw_empty[s], ph ^ 1u); PK_TACC(t_a); }
         const int64_t r0 = tile * TNE;
         const uint32_t nrows = (M - r0 >= TNE) ? TNE : (uint32_t)(M - r0);
-        mbar_arrive_expect_tx(&raw_full[s], nrows * (uint32_t)(K * 4));
         const uint32_t dst = rb + (uint32_t)s * RAW_BYTES;
-        if (ldx == K) tma_bulk_g2s(dst, X + r0 * K, nrows * (uint32_t)(K * 4), &raw_full[s]);
-        else for (uint32_t r = 0; r < nrows; ++r) tma_bulk_g2s(dst + r * (K * 4), X + (r0 + r) * ldx, (uint32_t)(K * 4), &raw_full[s]);
+        if (ldx == K) {
+          mbar_arrive_expect_tx(&raw_full[s], nrows * (uint32_t)(K * 4));
+          tma_bulk_g2s(dst, X + r0 * K, nrows * (uint32_t)(K * 4), &raw_full[s]);
+        } else {          // one K half of a wider matrix: tiled copy, box = [TNE rows x 128] (rows past M arrive as zeros)
+          mbar_arrive_expect_tx(&raw_full[s], (uint32_t)TNE * (uint32_t)(K * 4));
+          tma_tile_2d(dst, &tmx, 0, (int)r0, &raw_full[s]);
+        }
       }
 #ifdef PINNK_STAGE_TIMERS
       if (blockIdx.x == 0 && blockIdx.y == 0) atomicAdd(&g_stage_timers[0], (unsigned long long)t_a);
@@ -1186,7 +1222,10 @@ static int launch_linear_rows_ts_inst(const float* X, const float* W, int ldw, c
   TcLossFuse lf;
   memset(&lf, 0, sizeof(lf));
   if (loss) lf = *loss;
-  kern<<<grid, threads, smem, st>>>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, ldx, of, fl, lf);
+  alignas(64) CUtensorMap tmx;
+  memset(&tmx, 0, sizeof(tmx));
+  if (ldx != 128 && !make_tmap_rows(&tmx, X, M, 128, ldx, TNE)) return -1;
+  kern<<<grid, threads, smem, st>>>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, ldx, of, fl, lf, tmx);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -1226,11 +1265,16 @@ static int launch_linear_rows_ts(const float* X, const float* W, int ldw, const 
 // "main" TMEM accumulators (hi*hi products), while four flush warps fold the finished segment into a running fp32 sum
 // (kept in TMEM, added in registers with round-to-nearest).  The tiny lo*hi + hi*lo corrections accumulate in their own
 // TMEM region for the whole kernel.   TMEM: [0,128) main0 | [128,256) main1 | [256,384) corr | [384,512) sum
-template <int TK, int RS, int OS, int NCW, int SEG>
+template <int TK, int RS, int OS, int NCW, int SEG, int CG>
 __global__ void __launch_bounds__((NCW + 8) * 32, 1)
 wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, int ldx, float* __restrict__ dW, int lddw,
-             float* __restrict__ db, int64_t M, int jet_cols, int in_blocks) {
+             float* __restrict__ db, int64_t M, int jet_cols, int in_blocks, const __grid_constant__ CUtensorMap tmg,
+             const __grid_constant__ CUtensorMap tmxm) {
   static_assert(TK == 32 && (NCW == 8 || NCW == 16), "tile shape");
+  // CG = convert groups.  1: all NCW convert warps work on the same tile.  2: even / odd warps form two groups that take
+  // alternate tiles (group g owns operand stage g), so two tiles are being converted at any time and one group's barrier
+  // round trips, LDS latency and proxy fence hide behind the other group's ALU work.
+  static_assert(CG == 1 || (CG == 2 && OS == 2 && NCW == 16), "convert groups");
   constexpr uint32_t OP_BYTES = TK * 512;          // one of G_hi / G_lo / X_hi / X_lo per operand stage (TK rows x 128 floats)
   constexpr uint32_t RAW_BYTES = TK * 512;         // raw G (or X) tile
   // warp roles: [0, NCW) convert | NCW..NCW+3 flush (TMEM lane quarters; NCW % 4 == 0) | NCW+4 MMA | NCW+5 TMA | 2 idle
@@ -1259,8 +1303,8 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
   const int64_t my_segs = (my_tiles + SEG - 1) / SEG;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < RS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], NCW); }
-    for (int s = 0; s < OS; ++s) { mbar_init(&full[s], NCW); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < RS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], NCW / CG); }
+    for (int s = 0; s < OS; ++s) { mbar_init(&full[s], NCW / CG); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
     fence_mbar_init();
   }
@@ -1283,11 +1327,13 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
         const int64_t r0 = tile * TK;
         const int nrows = (M - r0 >= TK) ? TK : (int)(M - r0);
         const uint32_t dg = rb + (uint32_t)s * 2 * RAW_BYTES, dx = dg + RAW_BYTES;
-        mbar_arrive_expect_tx(&raw_full[s], (uint32_t)nrows * 1024u);
+        // contiguous 128-wide tensors: one bulk copy; 128-column blocks of wider tensors: one tiled copy (box [TK x 128],
+        // rows past M arrive as zeros and count in the transaction bytes)
+        mbar_arrive_expect_tx(&raw_full[s], (uint32_t)(ldg == 128 ? nrows : TK) * 512u + (uint32_t)(ldx == 128 ? nrows : TK) * 512u);
         if (ldg == 128) tma_bulk_g2s(dg, G + r0 * 128, (uint32_t)nrows * 512u, &raw_full[s]);
-        else for (int r = 0; r < nrows; ++r) tma_bulk_g2s(dg + r * 512, G + (r0 + r) * ldg + o0, 512u, &raw_full[s]);
+        else tma_tile_2d(dg, &tmg, o0, (int)r0, &raw_full[s]);
         if (ldx == 128) tma_bulk_g2s(dx, X + r0 * 128, (uint32_t)nrows * 512u, &raw_full[s]);
-        else for (int r = 0; r < nrows; ++r) tma_bulk_g2s(dx + r * 512, X + (r0 + r) * ldx + i0, 512u, &raw_full[s]);
+        else tma_tile_2d(dx, &tmxm, i0, (int)r0, &raw_full[s]);
       }
 #ifdef PINNK_STAGE_TIMERS
       if (blockIdx.x == 0 && blockIdx.y == 0) atomicAdd(&g_stage_timers[0], (unsigned long long)t_a);
@@ -1301,6 +1347,88 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
     // l+96, so the four values of a feature for the quad are one 16-byte chunk and a quarter-warp's STS.128 hit eight
     // distinct 16-byte slots (conflict-free), while the raw reads are lane-contiguous LDS.32.
     static_assert(NCW == 16 && TK == 32, "convert mapping");
+    if constexpr (CG == 2) {
+      // group g = warp & 1 converts tiles it = g, g + 2, ...; inside a group warp u = warp >> 1 converts row quads
+      // 2 (u & 3), 2 (u & 3) + 1 of tensor u >> 2 (0 = G, 1 = X)
+      const int g = warp & 1, u = warp >> 1, sel = u >> 2, rq0 = 2 * (u & 3);
+      float bsum[4] = {0.f, 0.f, 0.f, 0.f};
+      const bool want_b = (db != nullptr) && (i0 == 0) && sel == 0;
+      const bool b_fixed = (jet_cols == 1 || jet_cols == 2 || jet_cols == 4);
+      const uint32_t b_mask = (jet_cols == 1) ? 0xFu : (jet_cols == 2) ? 0x5u : 0x1u;
+      const uint32_t ob = smem_u32(op_base), rb = smem_u32(raw_base);
+      const uint32_t lane_raw = (uint32_t)sel * RAW_BYTES + (uint32_t)(rq0 * 4) * 512u + (uint32_t)lane * 4u;
+      uint32_t off_e[2][4];
+#pragma unroll
+      for (int qd = 0; qd < 2; ++qd)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) off_e[qd][e] = (uint32_t)sel * 2 * OP_BYTES + sw128_offset(128, lane + 32 * e, rq0 + qd);
+      const uint32_t hi_base = ob + (uint32_t)g * 4 * OP_BYTES, lo_base = hi_base + OP_BYTES;
+      long long t_a = 0, t_b = 0, t_c = 0; (void)t_a; (void)t_b; (void)t_c;
+      int it = g;
+      for (int64_t tile = (int64_t)blockIdx.x + (int64_t)g * gridDim.x; tile < ntiles; tile += 2 * (int64_t)gridDim.x, it += 2) {
+        const int rs = it % RS;
+        const uint32_t rph = (uint32_t)(it / RS) & 1u, oph = (uint32_t)(it >> 1) & 1u;
+        const int64_t r0 = tile * TK;
+        const int nrows = (M - r0 >= TK) ? TK : (int)(M - r0);
+        { PK_T0(); mbar_wait(&raw_full[rs], rph); PK_TACC(t_a); }
+        PK_T0();
+        const uint32_t raw = rb + (uint32_t)rs * 2 * RAW_BYTES + lane_raw;
+        float v[8][4];                                       // [row of the two quads][feature e]
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = 0.f;
+            if (nrows == TK || rq0 * 4 + r < nrows) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(raw + (uint32_t)(r * 512 + e * 128)));
+            v[r][e] = x;
+          }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&raw_empty[rs]);                 // raw data is in registers: slot may be refilled
+        PK_TACC(t_c);
+        { PK_T0(); mbar_wait(&empty[g], oph ^ 1u); PK_TACC(t_b); }
+        const long long _t1 = clock64(); (void)_t1;
+        if (want_b) {
+          if (b_fixed) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r)
+              if ((b_mask >> (r & 3)) & 1u) { bsum[0] += v[r][0]; bsum[1] += v[r][1]; bsum[2] += v[r][2]; bsum[3] += v[r][3]; }
+          } else {
+            uint32_t cj = (uint32_t)((uint32_t)(r0 + rq0 * 4) % (uint32_t)jet_cols);
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+              if (cj == 0) { bsum[0] += v[r][0]; bsum[1] += v[r][1]; bsum[2] += v[r][2]; bsum[3] += v[r][3]; }
+              cj = (cj + 1 == (uint32_t)jet_cols) ? 0u : cj + 1;
+            }
+          }
+        }
+#pragma unroll
+        for (int qd = 0; qd < 2; ++qd)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+            split_bits(v[4 * qd][e], h0, l0); split_bits(v[4 * qd + 1][e], h1, l1);
+            split_bits(v[4 * qd + 2][e], h2, l2); split_bits(v[4 * qd + 3][e], h3, l3);
+            sts128(hi_base + off_e[qd][e], h0, h1, h2, h3);
+            sts128(lo_base + off_e[qd][e], l0, l1, l2, l3);
+          }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[g]);
+#ifdef PINNK_STAGE_TIMERS
+        t_c += clock64() - _t1;
+#endif
+      }
+#ifdef PINNK_STAGE_TIMERS
+      if (blockIdx.x == 0 && blockIdx.y == 0 && warp == 0 && lane == 0) {
+        atomicAdd(&g_stage_timers[1], (unsigned long long)t_a); atomicAdd(&g_stage_timers[2], (unsigned long long)t_b);
+        atomicAdd(&g_stage_timers[3], (unsigned long long)t_c);
+      }
+#endif
+      if (want_b) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) atomicAdd(db + o0 + lane + 32 * e, bsum[e]);
+      }
+    } else {
     const int rq = warp & 7, sel = warp >> 3;
     float bsum[4] = {0.f, 0.f, 0.f, 0.f};
     const bool want_b = (db != nullptr) && (i0 == 0) && sel == 0;
@@ -1384,6 +1512,7 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
     if (want_b) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) atomicAdd(db + o0 + lane + 32 * e, bsum[e]);
+    }
     }
   } else if (warp < MMAW) {
     // ===================== flush warps: fold finished segments into the fp32 running sum, write out at the end ======
@@ -1516,12 +1645,12 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
   }
 }
 
-template <int TK, int RS, int OS, int NCW, int SEG>
+template <int TK, int RS, int OS, int NCW, int SEG, int CG>
 static int launch_wgrad(const float* G, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
                         int jet_cols, int sm_count, cudaStream_t st) {
   constexpr size_t smem = 1024 + (size_t)OS * 4 * TK * 512 + (size_t)RS * 2 * TK * 512 + (2 * RS + 2 * OS + 4) * 8 + 16;
   static_assert(smem <= 232448 && (size_t)OS * 4 * TK * 512 >= 128 * 132 * 4, "shared memory budget / transpose buffer");
-  auto kern = wgrad_kernel<TK, RS, OS, NCW, SEG>;
+  auto kern = wgrad_kernel<TK, RS, OS, NCW, SEG, CG>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
@@ -1533,7 +1662,12 @@ static int launch_wgrad(const float* G, const float* X, float* dW, float* db, in
   if (gx < 1) gx = 1;
   if ((int64_t)gx > ntiles) gx = (int)ntiles;
   dim3 grid((unsigned)gx, (unsigned)blocks, 1);
-  kern<<<grid, (NCW + 8) * 32, smem, st>>>(G, out_dim, X, in_dim, dW, in_dim, db, M, jet_cols, in_blocks);
+  alignas(64) CUtensorMap tmg, tmx;
+  memset(&tmg, 0, sizeof(tmg));
+  memset(&tmx, 0, sizeof(tmx));
+  if (out_dim != 128 && !make_tmap_rows(&tmg, G, M, out_dim, out_dim, TK)) return -1;
+  if (in_dim != 128 && !make_tmap_rows(&tmx, X, M, in_dim, in_dim, TK)) return -1;
+  kern<<<grid, (NCW + 8) * 32, smem, st>>>(G, out_dim, X, in_dim, dW, in_dim, db, M, jet_cols, in_blocks, tmg, tmx);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -1710,7 +1844,10 @@ int tc_stage_timers_wgrad(unsigned long long* out16, int reset) {
 int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
                                   int jet_cols, int sm_count, cudaStream_t st) {
   if (M < 1 || (in_dim % 128) != 0 || (out_dim % 128) != 0 || dW == nullptr) return TC_UNSUPPORTED;
-  return tc::launch_wgrad<32, 3, 2, 16, 4>(dZ, X, dW, db, M, in_dim, out_dim, jet_cols, sm_count, st);
+  static int groups = -1;       // PINNK_WGRAD_CG=1: all convert warps on one tile (the earlier scheme, kept for A/B runs)
+  if (groups < 0) { const char* e = getenv("PINNK_WGRAD_CG"); groups = (e && e[0] == '1') ? 1 : 2; }
+  if (groups == 1) return tc::launch_wgrad<32, 3, 2, 16, 4, 1>(dZ, X, dW, db, M, in_dim, out_dim, jet_cols, sm_count, st);
+  return tc::launch_wgrad<32, 3, 2, 16, 4, 2>(dZ, X, dW, db, M, in_dim, out_dim, jet_cols, sm_count, st);
 }
 #endif
 }  // namespace pinnk
