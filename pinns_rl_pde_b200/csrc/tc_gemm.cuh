@@ -465,6 +465,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -1265,21 +1273,25 @@ static int launch_linear_rows_ts(const float* X, const float* W, int ldw, const 
 // "main" TMEM accumulators (hi*hi products), while four flush warps fold the finished segment into a running fp32 sum
 // (kept in TMEM, added in registers with round-to-nearest).  The tiny lo*hi + hi*lo corrections accumulate in their own
 // TMEM region for the whole kernel.   TMEM: [0,128) main0 | [128,256) main1 | [256,384) corr | [384,512) sum
-template <int TK, int RS, int OS, int NCW, int SEG, int CG>
+template <int TK, int RS, int OS, int NCW, int SEG, bool TSA>
 __global__ void __launch_bounds__((NCW + 8) * 32, 1)
 wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, int ldx, float* __restrict__ dW, int lddw,
              float* __restrict__ db, int64_t M, int jet_cols, int in_blocks, const __grid_constant__ CUtensorMap tmg,
              const __grid_constant__ CUtensorMap tmxm) {
   static_assert(TK == 32 && (NCW == 8 || NCW == 16), "tile shape");
-  // CG = convert groups.  1: all NCW convert warps work on the same tile.  2: even / odd warps form two groups that take
-  // alternate tiles (group g owns operand stage g), so two tiles are being converted at any time and one group's barrier
-  // round trips, LDS latency and proxy fence hide behind the other group's ALU work.
-  static_assert(CG == 1 || (CG == 2 && OS == 2 && NCW == 16), "convert groups");
+  // TSA: the G^T operand (A of the MMA: 128 out-features x 32 rows) lives in TENSOR MEMORY instead of shared memory.  An
+  // SS-mode 128x128x8 MMA reads 8 KB of operands from shared memory in its 64 cycles -- all of the SM's 128 B/cycle -- and
+  // the staging traffic (TMA 32 KB + LDS 32 KB + STS 64 KB per 32-row tile) has to share that port: 224 KB per tile =
+  // 1750 cycles, which is what the kernel measured (1600 cycles per tile at any clock; two convert groups changed nothing).
+  // With A in TMEM the G warps write tcgen05.st instead of STS and the MMA fetches only B: 144 KB per tile.
+  // TMEM (TSA): [0,256) main0|main1 | [256,384) sum | [384,512) 2 stages x {G_hi 32, G_lo 32}; the lo*hi + hi*lo corrections
+  // go to the segment's main accumulator (no room for their own; a segment is 48 accumulate steps instead of 16).
+  static_assert(!TSA || (OS == 2 && NCW == 16), "TS-mode wgrad: two operand stages, 8 G + 8 X convert warps");
   constexpr uint32_t OP_BYTES = TK * 512;          // one of G_hi / G_lo / X_hi / X_lo per operand stage (TK rows x 128 floats)
   constexpr uint32_t RAW_BYTES = TK * 512;         // raw G (or X) tile
   // warp roles: [0, NCW) convert | NCW..NCW+3 flush (TMEM lane quarters; NCW % 4 == 0) | NCW+4 MMA | NCW+5 TMA | 2 idle
   constexpr int EPI0 = NCW, MMAW = NCW + 4, TMAW = NCW + 5;
-  constexpr uint32_t COL_MAIN = 0, COL_CORR = 256, COL_SUM = 384;
+  constexpr uint32_t COL_MAIN = 0, COL_CORR = TSA ? 0 : 256, COL_SUM = TSA ? 256 : 384, COL_A = 384;   // (no COL_CORR with TSA)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* op_base = smem;                                  // [OS][G_hi|G_lo|X_hi|X_lo][OP_BYTES]
@@ -1303,8 +1315,8 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
   const int64_t my_segs = (my_tiles + SEG - 1) / SEG;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < RS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], NCW / CG); }
-    for (int s = 0; s < OS; ++s) { mbar_init(&full[s], NCW / CG); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < RS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], NCW); }
+    for (int s = 0; s < OS; ++s) { mbar_init(&full[s], NCW); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
     fence_mbar_init();
   }
@@ -1347,87 +1359,61 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
     // l+96, so the four values of a feature for the quad are one 16-byte chunk and a quarter-warp's STS.128 hit eight
     // distinct 16-byte slots (conflict-free), while the raw reads are lane-contiguous LDS.32.
     static_assert(NCW == 16 && TK == 32, "convert mapping");
-    if constexpr (CG == 2) {
-      // group g = warp & 1 converts tiles it = g, g + 2, ...; inside a group warp u = warp >> 1 converts row quads
-      // 2 (u & 3), 2 (u & 3) + 1 of tensor u >> 2 (0 = G, 1 = X)
-      const int g = warp & 1, u = warp >> 1, sel = u >> 2, rq0 = 2 * (u & 3);
-      float bsum[4] = {0.f, 0.f, 0.f, 0.f};
-      const bool want_b = (db != nullptr) && (i0 == 0) && sel == 0;
-      const bool b_fixed = (jet_cols == 1 || jet_cols == 2 || jet_cols == 4);
-      const uint32_t b_mask = (jet_cols == 1) ? 0xFu : (jet_cols == 2) ? 0x5u : 0x1u;
-      const uint32_t ob = smem_u32(op_base), rb = smem_u32(raw_base);
-      const uint32_t lane_raw = (uint32_t)sel * RAW_BYTES + (uint32_t)(rq0 * 4) * 512u + (uint32_t)lane * 4u;
-      uint32_t off_e[2][4];
-#pragma unroll
-      for (int qd = 0; qd < 2; ++qd)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) off_e[qd][e] = (uint32_t)sel * 2 * OP_BYTES + sw128_offset(128, lane + 32 * e, rq0 + qd);
-      const uint32_t hi_base = ob + (uint32_t)g * 4 * OP_BYTES, lo_base = hi_base + OP_BYTES;
-      long long t_a = 0, t_b = 0, t_c = 0; (void)t_a; (void)t_b; (void)t_c;
-      int it = g;
-      for (int64_t tile = (int64_t)blockIdx.x + (int64_t)g * gridDim.x; tile < ntiles; tile += 2 * (int64_t)gridDim.x, it += 2) {
-        const int rs = it % RS;
-        const uint32_t rph = (uint32_t)(it / RS) & 1u, oph = (uint32_t)(it >> 1) & 1u;
+    if (TSA && warp < 8) {
+      // ---- G warps, TS mode: warp (q = warp & 3, h = warp >> 2) owns TMEM lanes 32q.. (out-features f = 32q + lane) and
+      // rows 16h .. 16h + 15 of the tile: 16 lane-contiguous LDS.32, hi/lo split, two tcgen05.st of 16 columns
+      const int q = warp & 3, h = warp >> 2, f = q * 32 + lane;
+      float bsum1 = 0.f;
+      const bool want_b1 = (db != nullptr) && (i0 == 0);
+      const bool b_fixed1 = (jet_cols == 1 || jet_cols == 2 || jet_cols == 4);
+      const uint32_t b_mask1 = (jet_cols == 1) ? 0xFu : (jet_cols == 2) ? 0x5u : 0x1u;
+      const uint32_t lane_raw1 = smem_u32(raw_base) + (uint32_t)(h * 16) * 512u + (uint32_t)f * 4u;
+      const uint32_t a_lane = tmem_base + ((uint32_t)(q * 32) << 16) + COL_A + (uint32_t)(h * 16);
+      int rs = 0, os = 0;
+      uint32_t rph = 0, oph = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t r0 = tile * TK;
         const int nrows = (M - r0 >= TK) ? TK : (int)(M - r0);
-        { PK_T0(); mbar_wait(&raw_full[rs], rph); PK_TACC(t_a); }
-        PK_T0();
-        const uint32_t raw = rb + (uint32_t)rs * 2 * RAW_BYTES + lane_raw;
-        float v[8][4];                                       // [row of the two quads][feature e]
+        mbar_wait(&raw_full[rs], rph);
+        const uint32_t raw = lane_raw1 + (uint32_t)rs * 2 * RAW_BYTES;
+        float v[16];
 #pragma unroll
-        for (int r = 0; r < 8; ++r)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float x = 0.f;
-            if (nrows == TK || rq0 * 4 + r < nrows) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(raw + (uint32_t)(r * 512 + e * 128)));
-            v[r][e] = x;
-          }
+        for (int j = 0; j < 16; ++j) {
+          float x = 0.f;
+          if (nrows == TK || h * 16 + j < nrows) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(raw + (uint32_t)(j * 512)));
+          v[j] = x;
+        }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&raw_empty[rs]);                 // raw data is in registers: slot may be refilled
-        PK_TACC(t_c);
-        { PK_T0(); mbar_wait(&empty[g], oph ^ 1u); PK_TACC(t_b); }
-        const long long _t1 = clock64(); (void)_t1;
-        if (want_b) {
-          if (b_fixed) {
+        if (lane == 0) mbar_arrive(&raw_empty[rs]);
+        mbar_wait(&empty[os], oph ^ 1u);
+        tc_fence_after();
+        if (want_b1) {
+          if (b_fixed1) {
 #pragma unroll
-            for (int r = 0; r < 8; ++r)
-              if ((b_mask >> (r & 3)) & 1u) { bsum[0] += v[r][0]; bsum[1] += v[r][1]; bsum[2] += v[r][2]; bsum[3] += v[r][3]; }
+            for (int j = 0; j < 16; ++j)
+              if ((b_mask1 >> (j & 3)) & 1u) bsum1 += v[j];
           } else {
-            uint32_t cj = (uint32_t)((uint32_t)(r0 + rq0 * 4) % (uint32_t)jet_cols);
+            uint32_t cj = (uint32_t)((uint32_t)(r0 + h * 16) % (uint32_t)jet_cols);
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-              if (cj == 0) { bsum[0] += v[r][0]; bsum[1] += v[r][1]; bsum[2] += v[r][2]; bsum[3] += v[r][3]; }
+            for (int j = 0; j < 16; ++j) {
+              if (cj == 0) bsum1 += v[j];
               cj = (cj + 1 == (uint32_t)jet_cols) ? 0u : cj + 1;
             }
           }
         }
+        uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int qd = 0; qd < 2; ++qd)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-            split_bits(v[4 * qd][e], h0, l0); split_bits(v[4 * qd + 1][e], h1, l1);
-            split_bits(v[4 * qd + 2][e], h2, l2); split_bits(v[4 * qd + 3][e], h3, l3);
-            sts128(hi_base + off_e[qd][e], h0, h1, h2, h3);
-            sts128(lo_base + off_e[qd][e], l0, l1, l2, l3);
-          }
-        fence_proxy_async();
+        for (int j = 0; j < 16; ++j) split_bits(v[j], hi[j], lo[j]);
+        tmem_st16(a_lane + (uint32_t)os * 64u, hi);
+        tmem_st16(a_lane + (uint32_t)os * 64u + 32u, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&full[g]);
-#ifdef PINNK_STAGE_TIMERS
-        t_c += clock64() - _t1;
-#endif
+        if (lane == 0) mbar_arrive(&full[os]);
+        if (++rs == RS) { rs = 0; rph ^= 1u; }
+        if (++os == OS) { os = 0; oph ^= 1u; }
       }
-#ifdef PINNK_STAGE_TIMERS
-      if (blockIdx.x == 0 && blockIdx.y == 0 && warp == 0 && lane == 0) {
-        atomicAdd(&g_stage_timers[1], (unsigned long long)t_a); atomicAdd(&g_stage_timers[2], (unsigned long long)t_b);
-        atomicAdd(&g_stage_timers[3], (unsigned long long)t_c);
-      }
-#endif
-      if (want_b) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) atomicAdd(db + o0 + lane + 32 * e, bsum[e]);
-      }
+      if (want_b1) atomicAdd(db + o0 + f, bsum1);
     } else {
     const int rq = warp & 7, sel = warp >> 3;
     float bsum[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1513,7 +1499,7 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
 #pragma unroll
       for (int e = 0; e < 4; ++e) atomicAdd(db + o0 + lane + 32 * e, bsum[e]);
     }
-    }
+    }   // (X warps / SS-mode G warps)
   } else if (warp < MMAW) {
     // ===================== flush warps: fold finished segments into the fp32 running sum, write out at the end ======
     if (my_segs > 0) {
@@ -1547,10 +1533,10 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
       for (int c0 = 0; c0 < 128; c0 += 32) {
         uint32_t p[32], a[32];
         tmem_ld32_nowait(lane_base + COL_SUM + c0, p);
-        tmem_ld32_nowait(lane_base + COL_CORR + c0, a);
+        if constexpr (!TSA) tmem_ld32_nowait(lane_base + COL_CORR + c0, a);
         tmem_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) tr[f * 132 + c0 + j] = __uint_as_float(p[j]) + __uint_as_float(a[j]);
+        for (int j = 0; j < 32; ++j) tr[f * 132 + c0 + j] = TSA ? __uint_as_float(p[j]) : __uint_as_float(p[j]) + __uint_as_float(a[j]);
       }
       named_bar_sync(1, kEpiThreads);
       const int t = threadIdx.x - EPI0 * 32;
@@ -1600,9 +1586,16 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
           const uint32_t o = (uint32_t)ks * (32 >> 4);                 // 8 K values = 32 bytes inside the swizzle row
           const uint64_t a_hi = dconst | (uint64_t)(gh + o), a_lo = dconst | (uint64_t)(gl + o);
           const uint64_t b_hi = dconst | (uint64_t)(xh + o), b_lo = dconst | (uint64_t)(xl + o);
-          umma_tf32(d_corr, a_lo, b_hi, idesc, (it | ks) ? 1u : 0u);
-          umma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
-          umma_tf32(d_main, a_hi, b_hi, idesc, (in_seg | ks) ? 1u : 0u);
+          if constexpr (TSA) {
+            const uint32_t ta_hi = tmem_base + COL_A + (uint32_t)s * 64u + (uint32_t)ks * 8u, ta_lo = ta_hi + 32u;
+            umma_tf32_ts(d_main, ta_lo, b_hi, idesc, (in_seg | ks) ? 1u : 0u);
+            umma_tf32_ts(d_main, ta_hi, b_lo, idesc, 1u);
+            umma_tf32_ts(d_main, ta_hi, b_hi, idesc, 1u);
+          } else {
+            umma_tf32(d_corr, a_lo, b_hi, idesc, (it | ks) ? 1u : 0u);
+            umma_tf32(d_corr, a_hi, b_lo, idesc, 1u);
+            umma_tf32(d_main, a_hi, b_hi, idesc, (in_seg | ks) ? 1u : 0u);
+          }
         }
         umma_commit(&empty[s]);
         if (++in_seg == SEG || tile + gridDim.x >= ntiles) {
@@ -1645,12 +1638,12 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
   }
 }
 
-template <int TK, int RS, int OS, int NCW, int SEG, int CG>
+template <int TK, int RS, int OS, int NCW, int SEG, bool TSA>
 static int launch_wgrad(const float* G, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
                         int jet_cols, int sm_count, cudaStream_t st) {
   constexpr size_t smem = 1024 + (size_t)OS * 4 * TK * 512 + (size_t)RS * 2 * TK * 512 + (2 * RS + 2 * OS + 4) * 8 + 16;
   static_assert(smem <= 232448 && (size_t)OS * 4 * TK * 512 >= 128 * 132 * 4, "shared memory budget / transpose buffer");
-  auto kern = wgrad_kernel<TK, RS, OS, NCW, SEG, CG>;
+  auto kern = wgrad_kernel<TK, RS, OS, NCW, SEG, TSA>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
@@ -1844,10 +1837,10 @@ int tc_stage_timers_wgrad(unsigned long long* out16, int reset) {
 int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
                                   int jet_cols, int sm_count, cudaStream_t st) {
   if (M < 1 || (in_dim % 128) != 0 || (out_dim % 128) != 0 || dW == nullptr) return TC_UNSUPPORTED;
-  static int groups = -1;       // PINNK_WGRAD_CG=1: all convert warps on one tile (the earlier scheme, kept for A/B runs)
-  if (groups < 0) { const char* e = getenv("PINNK_WGRAD_CG"); groups = (e && e[0] == '1') ? 1 : 2; }
-  if (groups == 1) return tc::launch_wgrad<32, 3, 2, 16, 4, 1>(dZ, X, dW, db, M, in_dim, out_dim, jet_cols, sm_count, st);
-  return tc::launch_wgrad<32, 3, 2, 16, 4, 2>(dZ, X, dW, db, M, in_dim, out_dim, jet_cols, sm_count, st);
+  static int ss = -1;       // PINNK_WGRAD_SS=1: both operands in shared memory (the earlier kernel, kept for A/B runs)
+  if (ss < 0) { const char* e = getenv("PINNK_WGRAD_SS"); ss = (e && e[0] == '1') ? 1 : 0; }
+  if (ss) return tc::launch_wgrad<32, 3, 2, 16, 4, false>(dZ, X, dW, db, M, in_dim, out_dim, jet_cols, sm_count, st);
+  return tc::launch_wgrad<32, 3, 2, 16, 4, true>(dZ, X, dW, db, M, in_dim, out_dim, jet_cols, sm_count, st);
 }
 #endif
 }  // namespace pinnk
