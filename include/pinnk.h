@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PINNK_ABI_VERSION 1
+#define PINNK_ABI_VERSION 2
 
 #define PINNK_E_INVALID   (-1)   /* bad argument / unsupported program            */
 #define PINNK_E_CUDA      (-2)   /* CUDA runtime error (message has the string)   */
@@ -130,6 +130,19 @@ int pinnk_loss_step(pinnk_plan_t plan, const float* const* params, const float* 
                     int64_t n, const PinnkSegment* segments, int32_t n_segments,
                     const float* grad_scale, double* loss_sums, float* flat_grad,
                     void* workspace, int64_t workspace_bytes, void* stream);
+
+/* pinnk_loss_step with flags, for callers that split compute_residual and backward the way autograd does
+ * (r = pde.compute_residual(model, x, t); loss(r).backward() -- CONTRIBUTING.md:241, notebook 05):
+ *   PINNK_STEP_KEEP_STASH   a forward-only call (flat_grad == NULL) leaves the stash and the output jets in the workspace;
+ *   PINNK_STEP_REUSE_STASH  the reverse-pass call finds them there and does not recompute the forward.  The caller vouches
+ *                           that nothing else used the workspace and that rows and parameters are unchanged.
+ * Both need n <= chunk_points. */
+#define PINNK_STEP_KEEP_STASH 1
+#define PINNK_STEP_REUSE_STASH 2
+int pinnk_loss_step_flags(pinnk_plan_t plan, const float* const* params, const float* x, const float* t,
+                          int64_t n, const PinnkSegment* segments, int32_t n_segments,
+                          const float* grad_scale, double* loss_sums, float* flat_grad,
+                          void* workspace, int64_t workspace_bytes, void* stream, int32_t flags);
 
 /* Forward-only residual scoring for the adaptive samplers (pde_base.py:909-921,1364-1377):
  * abs_residual_out (device, nullable, [n]) receives |r|; stats (device, fp64 [4]) accumulates

@@ -13,7 +13,8 @@ ACT_TANH, ACT_SIN = 1, 2
 (PDE_HEAT, PDE_BURGERS, PDE_KDV, PDE_ALLEN_CAHN, PDE_CAHN_HILLIARD, PDE_UT_ONLY, PDE_UT_ALLEN_CAHN_ND,
  PDE_CAHN_HILLIARD_2D, PDE_VALUE, PDE_DX, PDE_WAVE, PDE_CONVECTION, PDE_BLACK_SCHOLES, PDE_PENDULUM) = range(14)
 LOSS_MSE, LOSS_MAE, LOSS_HUBER = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
+STEP_KEEP_STASH, STEP_REUSE_STASH = 1, 2      # pinnk_loss_step_flags (include/pinnk.h)
 
 
 class PinnkOp(C.Structure):
@@ -39,7 +40,7 @@ class PinnkSegment(C.Structure):
 
 
 EXPORTS = ["pinnk_plan_create", "pinnk_plan_destroy", "pinnk_plan_workspace_bytes", "pinnk_plan_ncols",
-           "pinnk_plan_grad_floats", "pinnk_jets_forward", "pinnk_jets_vjp", "pinnk_loss_step", "pinnk_score",
+           "pinnk_plan_grad_floats", "pinnk_jets_forward", "pinnk_jets_vjp", "pinnk_loss_step", "pinnk_loss_step_flags", "pinnk_score",
            "pinnk_last_error", "pinnk_abi_version", "pinnk_launch_count", "pinnk_prof_enable", "pinnk_prof_classes",
            "pinnk_prof_class_name", "pinnk_prof_collect", "pinnk_debug_linear_fwd",
            "pinnk_debug_linear_dgrad", "pinnk_debug_linear_wgrad", "pinnk_adam_step", "pinnk_debug_stage_timers"]
@@ -77,6 +78,8 @@ def load():
     lib.pinnk_jets_vjp.restype = C.c_int
     lib.pinnk_loss_step.argtypes = [vp, vp, vp, vp, i64, C.POINTER(PinnkSegment), i32, vp, vp, vp, vp, i64, vp]
     lib.pinnk_loss_step.restype = C.c_int
+    lib.pinnk_loss_step_flags.argtypes = [vp, vp, vp, vp, i64, C.POINTER(PinnkSegment), i32, vp, vp, vp, vp, i64, vp, i32]
+    lib.pinnk_loss_step_flags.restype = C.c_int
     lib.pinnk_score.argtypes = [vp, vp, vp, vp, i64, C.POINTER(PinnkPde), vp, vp, vp, i64, vp]
     lib.pinnk_score.restype = C.c_int
     lib.pinnk_last_error.argtypes = []

@@ -850,9 +850,25 @@ extern "C" int pinnk_jets_vjp(pinnk_plan_t plan, const float* const* params, con
 extern "C" int pinnk_loss_step(pinnk_plan_t plan, const float* const* params, const float* x, const float* t,
                                int64_t n, const PinnkSegment* segs, int32_t n_segs, const float* grad_scale,
                                double* loss_sums, float* flat_grad, void* ws, int64_t ws_bytes, void* stream) {
+  return pinnk_loss_step_flags(plan, params, x, t, n, segs, n_segs, grad_scale, loss_sums, flat_grad, ws, ws_bytes, stream, 0);
+}
+
+// flags: PINNK_STEP_KEEP_STASH  -- a forward-only call (flat_grad == NULL) leaves in the workspace everything a reverse
+//                                  pass needs (n <= chunk_points: one chunk);
+//        PINNK_STEP_REUSE_STASH -- the workspace still holds the stash and the output jets of a KEEP_STASH call on the
+//                                  same rows and parameters (the caller vouches for that): the forward is not recomputed.
+// Together they turn "r = compute_residual(...); loss(r).backward()" from two forward passes + one reverse into one + one.
+extern "C" int pinnk_loss_step_flags(pinnk_plan_t plan, const float* const* params, const float* x, const float* t,
+                                     int64_t n, const PinnkSegment* segs, int32_t n_segs, const float* grad_scale,
+                                     double* loss_sums, float* flat_grad, void* ws, int64_t ws_bytes, void* stream,
+                                     int32_t flags) {
   int rc = check_common(plan, params, x, n, ws, ws_bytes);
   if (rc) return rc;
   if (!segs || n_segs < 1) return fail(PINNK_E_INVALID, "loss_step: no segments");
+  const bool keep_stash = (flags & PINNK_STEP_KEEP_STASH) != 0, reuse_stash = (flags & PINNK_STEP_REUSE_STASH) != 0;
+  if ((keep_stash || reuse_stash) && n > plan->chunk)
+    return fail(PINNK_E_INVALID, "loss_step: KEEP_STASH / REUSE_STASH need n <= chunk_points (one chunk)");
+  if (reuse_stash && !flat_grad) return fail(PINNK_E_INVALID, "loss_step: REUSE_STASH without a gradient buffer");
   const int C = plan->js.ncols;
   for (int s = 0; s < n_segs; ++s) {
     const PinnkSegment& g = segs[s];
@@ -868,10 +884,10 @@ extern "C" int pinnk_loss_step(pinnk_plan_t plan, const float* const* params, co
   for (int64_t p0 = 0; p0 < n; p0 += plan->chunk) {
     const int64_t cn = std::min(plan->chunk, n - p0);
     ChunkCtx c = make_ctx(plan, params, x, t, p0, cn, ws, stream);
-    const bool keep = flat_grad != nullptr;
+    const bool keep = flat_grad != nullptr || keep_stash;
     // loss fusion: one plain segment covers the whole chunk and the network ends in Linear(128,128) + tanh + Linear(.,1)
     TcLossFuse lf;
-    const int fs = keep ? loss_fusable_segment(plan, segs, n_segs, p0, cn) : -1;
+    const int fs = (flat_grad != nullptr && !reuse_stash) ? loss_fusable_segment(plan, segs, n_segs, p0, cn) : -1;
     if (fs >= 0) {
       const PinnkSegment& g = segs[fs];
       const PinnkOp& lo = plan->ops.back().op;
@@ -887,8 +903,10 @@ extern "C" int pinnk_loss_step(pinnk_plan_t plan, const float* const* params, co
       lf.b_out = lo.b_index >= 0 ? params_host_ptr(params, lo.b_index) : nullptr;
       c.loss_fuse = &lf;
     }
-    rc = dispatch_maxk(plan->maxk, [&](auto mk) { return forward_chunk<decltype(mk)::value>(c, keep); });
-    if (rc) return rc;
+    if (!reuse_stash) {
+      rc = dispatch_maxk(plan->maxk, [&](auto mk) { return forward_chunk<decltype(mk)::value>(c, keep); });
+      if (rc) return rc;
+    }
     if (c.loss_done) {
       rc = dispatch_maxk(plan->maxk, [&](auto mk) { return backward_chunk<decltype(mk)::value>(c, flat_grad, true); });
       if (rc) return rc;

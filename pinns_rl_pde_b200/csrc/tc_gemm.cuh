@@ -1294,8 +1294,9 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
   constexpr uint32_t COL_MAIN = 0, COL_CORR = TSA ? 0 : 256, COL_SUM = TSA ? 256 : 384, COL_A = 384;   // (no COL_CORR with TSA)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* op_base = smem;                                  // [OS][G_hi|G_lo|X_hi|X_lo][OP_BYTES]
-  uint8_t* raw_base = smem + (size_t)OS * 4 * OP_BYTES;     // [RS][G|X][RAW_BYTES]
+  constexpr int OPS = TSA ? 2 : 4;                          // operand tiles per stage: TS mode keeps only X_hi | X_lo here
+  uint8_t* op_base = smem;                                  // [OS][G_hi|G_lo|X_hi|X_lo][OP_BYTES]   (TSA: [OS][X_hi|X_lo])
+  uint8_t* raw_base = smem + (size_t)OS * OPS * OP_BYTES;   // [RS][G|X][RAW_BYTES]
   uint64_t* bars = reinterpret_cast<uint64_t*>(raw_base + (size_t)RS * 2 * RAW_BYTES);
   uint64_t* raw_full = bars;
   uint64_t* raw_empty = bars + RS;
@@ -1426,7 +1427,7 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
     const uint32_t lane_raw = (uint32_t)sel * RAW_BYTES + (uint32_t)(rq * 4) * 512u + (uint32_t)lane * 4u;
     uint32_t off_e[4];                                        // K-major SW128: row = feature, 16-byte chunk = row quad
 #pragma unroll
-    for (int e = 0; e < 4; ++e) off_e[e] = (uint32_t)sel * 2 * OP_BYTES + sw128_offset(128, lane + 32 * e, rq);
+    for (int e = 0; e < 4; ++e) off_e[e] = (TSA ? 0u : (uint32_t)sel * 2 * OP_BYTES) + sw128_offset(128, lane + 32 * e, rq);
     long long t_a = 0, t_b = 0, t_c = 0; (void)t_a; (void)t_b; (void)t_c;
     int rs = 0, os = 0;
     uint32_t rph = 0, oph = 0;
@@ -1458,7 +1459,7 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
       PK_TACC(t_c);
       { PK_T0(); mbar_wait(&empty[os], oph ^ 1u); PK_TACC(t_b); }
       const long long _t1 = clock64(); (void)_t1;
-      const uint32_t hi_base = ob + (uint32_t)os * 4 * OP_BYTES, lo_base = hi_base + OP_BYTES;
+      const uint32_t hi_base = ob + (uint32_t)os * OPS * OP_BYTES, lo_base = hi_base + OP_BYTES;
       if (want_b) {
         if (b_fixed) {
 #pragma unroll
@@ -1528,7 +1529,7 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
         if (lane == 0) mbar_arrive(&tempty[b]);
       }
       // all MMAs (including the corrections) are complete: the last tfull commit covered them
-      float* tr = reinterpret_cast<float*>(op_base);             // operand stages are idle now: [128][132] transpose buffer
+      float* tr = reinterpret_cast<float*>(raw_base);            // the raw ring is idle now: [128][132] transpose buffer
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32) {
         uint32_t p[32], a[32];
@@ -1578,8 +1579,8 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
         { PK_T0(); mbar_wait(&full[s], ph); PK_TACC(t_b); }
         PK_T0();
         tc_fence_after();
-        const uint32_t gh = sbase + (uint32_t)s * (4 * OP_BYTES >> 4), gl = gh + (OP_BYTES >> 4), xh = gl + (OP_BYTES >> 4),
-                       xl = xh + (OP_BYTES >> 4);
+        const uint32_t gh = sbase + (uint32_t)s * (OPS * OP_BYTES >> 4), gl = gh + (OP_BYTES >> 4),
+                       xh = TSA ? gh : gl + (OP_BYTES >> 4), xl = xh + (OP_BYTES >> 4);
         const uint32_t d_main = tmem_base + COL_MAIN + (uint32_t)b * 128, d_corr = tmem_base + COL_CORR;
 #pragma unroll
         for (int ks = 0; ks < TK / 8; ++ks) {
@@ -1641,8 +1642,8 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
 template <int TK, int RS, int OS, int NCW, int SEG, bool TSA>
 static int launch_wgrad(const float* G, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
                         int jet_cols, int sm_count, cudaStream_t st) {
-  constexpr size_t smem = 1024 + (size_t)OS * 4 * TK * 512 + (size_t)RS * 2 * TK * 512 + (2 * RS + 2 * OS + 4) * 8 + 16;
-  static_assert(smem <= 232448 && (size_t)OS * 4 * TK * 512 >= 128 * 132 * 4, "shared memory budget / transpose buffer");
+  constexpr size_t smem = 1024 + (size_t)OS * (TSA ? 2 : 4) * TK * 512 + (size_t)RS * 2 * TK * 512 + (2 * RS + 2 * OS + 4) * 8 + 16;
+  static_assert(smem <= 232448 && (size_t)RS * 2 * TK * 512 >= 128 * 132 * 4, "shared memory budget / transpose buffer");
   auto kern = wgrad_kernel<TK, RS, OS, NCW, SEG, TSA>;
   static bool configured = false;
   if (!configured) {
@@ -1840,7 +1841,11 @@ int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64
   static int ss = -1;       // PINNK_WGRAD_SS=1: both operands in shared memory (the earlier kernel, kept for A/B runs)
   if (ss < 0) { const char* e = getenv("PINNK_WGRAD_SS"); ss = (e && e[0] == '1') ? 1 : 0; }
   if (ss) return tc::launch_wgrad<32, 3, 2, 16, 4, false>(dZ, X, dW, db, M, in_dim, out_dim, jet_cols, sm_count, st);
-  return tc::launch_wgrad<32, 3, 2, 16, 4, true>(dZ, X, dW, db, M, in_dim, out_dim, jet_cols, sm_count, st);
+  // TS mode frees the G operand tiles in shared memory: the raw ring is 5 deep (160 KB of loads in flight per SM)
+  static int rs3 = -1;
+  if (rs3 < 0) { const char* e = getenv("PINNK_WGRAD_RS3"); rs3 = (e && e[0] == '1') ? 1 : 0; }
+  if (rs3) return tc::launch_wgrad<32, 3, 2, 16, 4, true>(dZ, X, dW, db, M, in_dim, out_dim, jet_cols, sm_count, st);
+  return tc::launch_wgrad<32, 5, 2, 16, 4, true>(dZ, X, dW, db, M, in_dim, out_dim, jet_cols, sm_count, st);
 }
 #endif
 }  // namespace pinnk

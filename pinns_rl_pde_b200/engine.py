@@ -79,6 +79,10 @@ class JetEngine:
         assert int(self.lib.pinnk_plan_ncols(handle)) == self.ncols
         self.workspace = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
         self._ptrs = (C.c_void_p * max(1, len(program.tensors)))()
+        # token of the forward-only call whose stash the workspace still holds (loss_step(keep_stash=True)); any other
+        # call on this engine clears it
+        self._stash_token = None
+        self._token_count = 0
 
     # ------------------------------------------------------------------ helpers
     def _params(self):
@@ -113,6 +117,7 @@ class JetEngine:
 
     # ------------------------------------------------------------------ entry points
     def jets_forward(self, x, t=None) -> torch.Tensor:
+        self._stash_token = None
         x, t, n = self._xt(x, t)
         out = torch.empty(n, self.ncols, dtype=torch.float32, device=self.device)
         if n:
@@ -122,6 +127,7 @@ class JetEngine:
         return out
 
     def jets_vjp(self, x, t, adj: torch.Tensor, flat_grad: Optional[torch.Tensor] = None) -> torch.Tensor:
+        self._stash_token = None
         x, t, n = self._xt(x, t)
         _require_cuda_f32(adj, "adj_jets")
         adj = adj.contiguous()
@@ -135,11 +141,25 @@ class JetEngine:
                                             self.ws_bytes, self._stream()), "pinnk_jets_vjp")
         return flat_grad
 
+    def stash_signature(self):
+        """What has to be unchanged between a keep_stash forward and the reverse pass that reuses its stash."""
+        return tuple((tn.data_ptr(), tn._version) for tn in self.program.tensors)
+
     def loss_step(self, x, t, segments: Sequence[Segment], n_components: int, want_grad: bool,
                   grad_scale: Optional[Sequence[float]] = None, flat_grad: Optional[torch.Tensor] = None,
-                  loss_sums: Optional[torch.Tensor] = None):
-        """Returns (loss_sums fp64 [n_components], flat_grad or None)."""
+                  loss_sums: Optional[torch.Tensor] = None, keep_stash: bool = False, reuse_token=None):
+        """Returns (loss_sums fp64 [n_components], flat_grad or None).
+
+        ``keep_stash`` (forward-only call, n <= chunk): the workspace keeps what a reverse pass needs and
+        ``self._stash_token`` names this call; ``reuse_token``: run the reverse pass from that stash when the token is
+        still current (nothing else used the engine), else recompute the forward as usual."""
+        flags = 0
+        if reuse_token is not None and want_grad and reuse_token == self._stash_token:
+            flags = L.STEP_REUSE_STASH
+        self._stash_token = None
         x, t, n = self._xt(x, t)
+        if keep_stash and not want_grad and 0 < n <= self.chunk:
+            flags = L.STEP_KEEP_STASH
         if loss_sums is None:
             loss_sums = torch.zeros(n_components, dtype=torch.float64, device=self.device)
         if want_grad and flat_grad is None:
@@ -163,16 +183,20 @@ class JetEngine:
         if grad_scale is not None:
             gs = (C.c_float * n_components)(*[float(g) for g in grad_scale])
         if n:
-            L.check(self.lib.pinnk_loss_step(self.handle, self._params(), x.data_ptr(), self._ptr(t), n, segs,
-                                             len(segments), C.cast(gs, C.c_void_p) if gs is not None else None,
-                                             loss_sums.data_ptr(), self._ptr(flat_grad) if want_grad else None,
-                                             self.workspace.data_ptr(), self.ws_bytes, self._stream()),
+            L.check(self.lib.pinnk_loss_step_flags(self.handle, self._params(), x.data_ptr(), self._ptr(t), n, segs,
+                                                   len(segments), C.cast(gs, C.c_void_p) if gs is not None else None,
+                                                   loss_sums.data_ptr(), self._ptr(flat_grad) if want_grad else None,
+                                                   self.workspace.data_ptr(), self.ws_bytes, self._stream(), flags),
                     "pinnk_loss_step")
+            if flags == L.STEP_KEEP_STASH:
+                self._token_count += 1
+                self._stash_token = (self._token_count, x.data_ptr(), self._ptr(t), n, self.stash_signature())
         return loss_sums, (flat_grad if want_grad else None)
 
     def score(self, x, t, kind: int, p0: float = 0.0, compat_math: int = 0, want_abs: bool = True,
               stats: Optional[torch.Tensor] = None, p1: float = 0.0):
         """Forward-only |r| and stats = [sum|r|, sum r^2, max|r|, count] (fp64, device)."""
+        self._stash_token = None
         x, t, n = self._xt(x, t)
         abs_r = torch.empty(n, dtype=torch.float32, device=self.device) if want_abs else None
         if stats is None:

@@ -137,20 +137,25 @@ class _ErrorFn(torch.autograd.Function):
     """e[rows] of one segment prototype; backward = reverse pass seeded with dL/de."""
 
     @staticmethod
-    def forward(ctx, engine, proto: Segment, x, t, *params):
+    def forward(ctx, engine, proto: Segment, x, t, keep_stash, *params):
         e = torch.empty(proto.row_count, dtype=torch.float32, device=x.device)
         seg = Segment(**{**proto.__dict__, "error_out": e})
-        engine.loss_step(x, t, [seg], 1, want_grad=False)
-        ctx.engine, ctx.proto, ctx.x, ctx.t = engine, proto, x, t
+        # when a reverse pass will follow and the rows fit one chunk, the forward leaves its stash in the workspace and
+        # backward() starts from it instead of recomputing the forward (one forward + one reverse instead of two + one)
+        engine.loss_step(x, t, [seg], 1, want_grad=False, keep_stash=bool(keep_stash))
+        ctx.engine, ctx.proto, ctx.x, ctx.t, ctx.token = engine, proto, x, t, engine._stash_token
         return e.view(-1, 1)
 
     @staticmethod
     def backward(ctx, ge):
         ge = ge.reshape(-1).to(torch.float32).contiguous()
         seg = Segment(**{**ctx.proto.__dict__, "error_grad": ge})
-        _, flat = ctx.engine.loss_step(ctx.x, ctx.t, [seg], 1, want_grad=True)
+        eng, token = ctx.engine, ctx.token
+        if token is not None and (token[1:4] != (ctx.x.data_ptr(), eng._ptr(ctx.t), ctx.x.shape[0]) or token[4] != eng.stash_signature()):
+            token = None            # rows or parameters changed since the forward: recompute
+        _, flat = eng.loss_step(ctx.x, ctx.t, [seg], 1, want_grad=True, reuse_token=token)
         grads = ctx.engine.program.split_flat(flat)
-        return (None, None, None, None, *grads)
+        return (None, None, None, None, None, *grads)
 
 
 class _JetsFn(torch.autograd.Function):
@@ -215,7 +220,8 @@ def compute_residual(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor) ->
     proto = Segment(kind=kind, row_start=0, row_count=n, p0=p0, p1=residual_p1(pde), compat_math=cm)
     if not model.training:
         model.train()   # pde_base.py:638 -- the reference flips the model into training mode here
-    return _ErrorFn.apply(eng, proto, x, t, *eng.program.grad_params)
+    keep = torch.is_grad_enabled() and len(eng.program.grad_params) > 0     # (needs_input_grad ignores no_grad())
+    return _ErrorFn.apply(eng, proto, x, t, keep, *eng.program.grad_params)
 
 
 def score_residual(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, want_abs: bool = True,

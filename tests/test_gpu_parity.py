@@ -154,6 +154,46 @@ def test_chunking_is_invisible(dev):
     assert rel(flat_grad(model), g1) <= 2e-6
 
 
+@pytest.mark.parametrize("arch,extra,pde_name", [("feedforward", {}, "burgers"), ("resnet", {"num_blocks": 2}, "kdv"),
+                                                 ("siren", {"omega_0": 30.0}, "cahn_hilliard")])
+def test_residual_backward_reuses_the_forward_stash(dev, arch, extra, pde_name):
+    """r = compute_residual(...); loss(r).backward(): when the rows fit one chunk the reverse pass starts from the stash the
+    forward left in the workspace (pinnk_loss_step_flags KEEP_STASH / REUSE_STASH) and must give the gradient of the route
+    that recomputes the forward -- which is what runs when anything touched the engine, the rows or the parameters."""
+    import pinns_rl_pde_b200 as pk
+    from pinns_rl_pde_b200 import engine, functional as F
+    torch.manual_seed(3)
+    model = pk.make_model(arch, 2, 128, 3, dev, **extra)
+    pde = product_pde(pde_name, dev)
+    g = torch.Generator().manual_seed(5)
+    x, t = (torch.rand(3000, 1, generator=g) * 2 - 1).to(dev), torch.rand(3000, 1, generator=g).to(dev)
+    eng = engine.get_engine(model, F.residual_spec(pde)[0], 3000)
+
+    def grad(disturb):
+        model.zero_grad()
+        r = pde.compute_residual(model, x, t)
+        token = eng._stash_token
+        assert token is not None                       # the forward kept its stash
+        if disturb == "engine":                        # another call on the engine overwrites the workspace
+            pde.score_residual(model, x[:100], t[:100])
+            assert eng._stash_token is None
+        elif disturb == "params":                      # an in-place parameter update bumps the version counter
+            with torch.no_grad():
+                next(model.parameters()).add_(0.0)
+        (r ** 2).mean().backward()
+        return flat_grad(model).clone(), float((r.detach() ** 2).mean())
+
+    g_reuse, l_reuse = grad(None)
+    g_engine, l_engine = grad("engine")
+    g_params, _ = grad("params")
+    assert l_reuse == l_engine
+    assert torch.isfinite(g_reuse).all() and float(g_reuse.norm()) > 0
+    assert rel(g_reuse, g_engine) <= 2e-6 and rel(g_params, g_engine) <= 2e-6
+    with torch.no_grad():                              # forward-only callers keep nothing
+        pde.compute_residual(model, x, t)
+    assert eng._stash_token is None
+
+
 def test_model_forward_and_custom_loss_autograd(dev):
     """model(x) and jets() are differentiable w.r.t. parameters for callers that write their own loss."""
     import pinns_rl_pde_b200 as pk
