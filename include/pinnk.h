@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PINNK_ABI_VERSION 2
+#define PINNK_ABI_VERSION 3
 
 #define PINNK_E_INVALID   (-1)   /* bad argument / unsupported program            */
 #define PINNK_E_CUDA      (-2)   /* CUDA runtime error (message has the string)   */
@@ -157,6 +157,30 @@ int pinnk_score(pinnk_plan_t plan, const float* const* params, const float* x, c
 int pinnk_adam_step(float* const* params, const int64_t* numels, int32_t n_tensors, const float* flat_grad,
                     float* exp_avg, float* exp_avg_sq, double* scratch, int64_t step, float lr, float beta1,
                     float beta2, float eps, float weight_decay, float max_norm, void* stream);
+/* The same step with the step count and the learning rate in DEVICE memory (dyn[0] = step >= 1, dyn[1] = lr, doubles):
+ * nothing step-dependent is baked into the launch, so a captured CUDA graph of the trainer step can be replayed
+ * (the caller advances dyn[0] on the stream before this call). */
+int pinnk_adam_step_dev(float* const* params, const int64_t* numels, int32_t n_tensors, const float* flat_grad,
+                        float* exp_avg, float* exp_avg_sq, double* scratch, const double* dyn, float beta1,
+                        float beta2, float eps, float weight_decay, float max_norm, void* stream);
+
+/* Q-network of the RL sampler, value-only forward over a candidate grid in ONE launch.  Replaces
+ * DQNNetwork.forward (rl/rl_agent.py:15-88: [Linear -> LayerNorm -> ReLU -> Dropout] x n_hidden, Linear(hidden -> out_dim))
+ * as called by RLAgent.select_action (rl_agent.py:214-229) from PDEBase.generate_collocation_points("adaptive")
+ * (pdes/pde_base.py:961-1018).  All pointers are device pointers; bias / ln_weight / ln_bias / dropout_mask may be null.
+ * dropout_mask: [n, hidden] floats, 0 or 1/(1-p), drawn by the caller (the reference's policy net is left in train mode,
+ * so its dropout is live during scoring); null = eval mode.  states [n, in_dim of layer 0], q_out [n, out_dim]. */
+typedef struct PinnkDqnLayer {
+  const float* weight;       /* [out_dim, in_dim] row-major (nn.Linear.weight) */
+  const float* bias;         /* [out_dim] */
+  const float* ln_weight;    /* [out_dim] */
+  const float* ln_bias;      /* [out_dim] */
+  const float* dropout_mask; /* [n, out_dim] or null */
+  float eps;                 /* LayerNorm eps */
+  int32_t in_dim, out_dim;
+} PinnkDqnLayer;
+int pinnk_dqn_forward(const PinnkDqnLayer* layers, int32_t n_hidden, const float* w_out, const float* b_out,
+                      int32_t out_dim, const float* states, int64_t n, float* q_out, void* stream);
 
 const char* pinnk_last_error(void);
 int32_t pinnk_abi_version(void);

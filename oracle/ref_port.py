@@ -592,3 +592,20 @@ def heat_compute_loss(model, residual, domain, time_domain, ic_fn, num_boundary,
     total = weights[0] * res_loss + weights[1] * b_loss + weights[2] * i_loss
     return {"residual": res_loss, "boundary": b_loss, "initial": i_loss,
             "smoothness": zero, "data": zero.clone(), "total": total}
+
+
+# ------------------------------------------------------------------ RL sampler: Q-network forward
+def dqn_forward_port(state: Dict[str, torch.Tensor], x: torch.Tensor, dropout: float = 0.1,
+                     training: bool = False, eps: float = 1e-5) -> torch.Tensor:
+    """rl/rl_agent.py:15-88 ``DQNNetwork.forward`` restated on the network's state dict: groups
+    ``layers.{i}.0`` Linear -> ``layers.{i}.1`` LayerNorm -> ReLU -> Dropout, then ``layers.{n}`` Linear.
+    Pinned bit-identical (fp32, eval mode) to the unmodified reference by tests/golden/make_golden.py (case x_dqn)."""
+    import torch.nn.functional as Fn
+    h = x
+    i = 0
+    while f"layers.{i}.0.weight" in state:
+        h = Fn.linear(h, state[f"layers.{i}.0.weight"], state.get(f"layers.{i}.0.bias"))
+        h = Fn.layer_norm(h, (h.shape[-1],), state.get(f"layers.{i}.1.weight"), state.get(f"layers.{i}.1.bias"), eps)
+        h = Fn.dropout(torch.relu(h), dropout, training)
+        i += 1
+    return Fn.linear(h, state[f"layers.{i}.weight"], state.get(f"layers.{i}.bias"))

@@ -13,9 +13,11 @@ from .pdes import (AllenCahnEquation, BlackScholesEquation, BurgersEquation, Cah
                    HeatEquation, KdVEquation, PDEBase, PDEConfig, PendulumEquation, WaveEquation, create_pde)
 from .training import PDETrainer, TrainingConfig
 from .dropin import patch_reference
+from . import rl
+from .rl import DQNNetwork, dqn_forward
 
 __all__ = ["compute_loss", "compute_residual", "jets", "loss_and_flat_grad", "model_forward", "score_residual",
            "Config", "ModelConfig", "PINNModel", "FeedForwardNetwork", "ResNet", "SIREN", "FourierNetwork",
            "make_model", "PDEConfig", "PDEBase", "HeatEquation", "BurgersEquation", "KdVEquation",
            "AllenCahnEquation", "CahnHilliardEquation", "WaveEquation", "ConvectionEquation", "BlackScholesEquation", "PendulumEquation", "create_pde", "PDETrainer", "TrainingConfig",
-           "patch_reference"]
+           "patch_reference", "rl", "DQNNetwork", "dqn_forward"]

@@ -13,7 +13,7 @@ ACT_TANH, ACT_SIN = 1, 2
 (PDE_HEAT, PDE_BURGERS, PDE_KDV, PDE_ALLEN_CAHN, PDE_CAHN_HILLIARD, PDE_UT_ONLY, PDE_UT_ALLEN_CAHN_ND,
  PDE_CAHN_HILLIARD_2D, PDE_VALUE, PDE_DX, PDE_WAVE, PDE_CONVECTION, PDE_BLACK_SCHOLES, PDE_PENDULUM) = range(14)
 LOSS_MSE, LOSS_MAE, LOSS_HUBER = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 STEP_KEEP_STASH, STEP_REUSE_STASH = 1, 2      # pinnk_loss_step_flags (include/pinnk.h)
 
 
@@ -39,11 +39,17 @@ class PinnkSegment(C.Structure):
                 ("error_out", C.c_void_p), ("error_grad", C.c_void_p)]
 
 
+class PinnkDqnLayer(C.Structure):
+    _fields_ = [("weight", C.c_void_p), ("bias", C.c_void_p), ("ln_weight", C.c_void_p), ("ln_bias", C.c_void_p),
+                ("dropout_mask", C.c_void_p), ("eps", C.c_float), ("in_dim", C.c_int32), ("out_dim", C.c_int32)]
+
+
 EXPORTS = ["pinnk_plan_create", "pinnk_plan_destroy", "pinnk_plan_workspace_bytes", "pinnk_plan_ncols",
            "pinnk_plan_grad_floats", "pinnk_jets_forward", "pinnk_jets_vjp", "pinnk_loss_step", "pinnk_loss_step_flags", "pinnk_score",
            "pinnk_last_error", "pinnk_abi_version", "pinnk_launch_count", "pinnk_prof_enable", "pinnk_prof_classes",
            "pinnk_prof_class_name", "pinnk_prof_collect", "pinnk_debug_linear_fwd",
-           "pinnk_debug_linear_dgrad", "pinnk_debug_linear_wgrad", "pinnk_adam_step", "pinnk_debug_stage_timers"]
+           "pinnk_debug_linear_dgrad", "pinnk_debug_linear_wgrad", "pinnk_adam_step", "pinnk_adam_step_dev", "pinnk_dqn_forward",
+           "pinnk_debug_stage_timers"]
 
 _lib = None
 
@@ -101,6 +107,11 @@ def load():
     lib.pinnk_adam_step.argtypes = [vp, vp, i32, vp, vp, vp, vp, i64, C.c_float, C.c_float, C.c_float, C.c_float,
                                     C.c_float, C.c_float, vp]
     lib.pinnk_adam_step.restype = C.c_int
+    lib.pinnk_adam_step_dev.argtypes = [vp, vp, i32, vp, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, C.c_float,
+                                        C.c_float, vp]
+    lib.pinnk_adam_step_dev.restype = C.c_int
+    lib.pinnk_dqn_forward.argtypes = [C.POINTER(PinnkDqnLayer), i32, vp, vp, i32, vp, i64, vp, vp]
+    lib.pinnk_dqn_forward.restype = C.c_int
     lib.pinnk_debug_linear_dgrad.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp]
     lib.pinnk_debug_linear_dgrad.restype = C.c_int
     lib.pinnk_debug_linear_wgrad.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]

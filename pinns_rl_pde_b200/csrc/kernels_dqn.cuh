@@ -1,0 +1,124 @@
+// Value-only forward of the RL sampler's Q-network over a candidate grid:
+//   rl_agent.py:15-88   DQNNetwork = [Linear -> LayerNorm -> ReLU -> Dropout] x (num_layers - 1), Linear(hidden -> action_dim)
+//   rl_agent.py:214-229 RLAgent.select_action: policy_net(points).view(1, -1) on <= 100^(d+1) grid points
+// One kernel for the whole network: a block owns R candidate rows, thread f owns hidden unit f; the activations of the R
+// rows stay in shared memory from the state vector to the Q-values, weights are read through L1/L2 (<= 3 x 64 KB for the
+// reference's hidden_dim = 128).  The work is ~0.1 GFLOP per call: latency-bound, so the point of the kernel is one launch
+// instead of ~12 (and no [N, hidden] round trips), not tensor cores.
+#pragma once
+#include <cstdint>
+
+namespace pinnk {
+
+constexpr int DQN_MAX_LAYERS = 8;
+constexpr int DQN_ROWS = 8;
+
+struct DqnNet {
+  const float* W[DQN_MAX_LAYERS];       // [hidden, in] row-major (nn.Linear.weight)
+  const float* b[DQN_MAX_LAYERS];       // [hidden] or null
+  const float* gamma[DQN_MAX_LAYERS];   // LayerNorm weight / bias (null = no affine)
+  const float* beta[DQN_MAX_LAYERS];
+  const float* mask[DQN_MAX_LAYERS];    // [n, hidden] dropout mask already scaled by 1 / (1 - p), or null
+  float eps[DQN_MAX_LAYERS];
+  int n_hidden;                         // number of Linear-LayerNorm-ReLU groups
+  int state_dim, hidden, out_dim;
+  const float* W_out;                   // [out_dim, hidden]
+  const float* b_out;                   // [out_dim] or null
+};
+
+__device__ __forceinline__ float dqn_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// sum over the block's `hidden` threads of v[r], r < R; result broadcast to every thread.  red: [R][32] floats.
+template <int R>
+__device__ __forceinline__ void dqn_block_sum(float (&v)[R], float* red, int n_warps) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const float s = dqn_warp_sum(v[r]);
+    if (lane == 0) red[r * 32 + wid] = s;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    float s = (lane < n_warps) ? red[r * 32 + lane] : 0.f;
+    v[r] = dqn_warp_sum(s);
+  }
+  __syncthreads();
+}
+
+template <int R>
+__global__ void __launch_bounds__(1024) dqn_forward_kernel(DqnNet net, const float* __restrict__ states, int64_t n,
+                                                           float* __restrict__ q_out) {
+  extern __shared__ float sm[];
+  const int H = net.hidden;
+  float* h0 = sm;                        // [R][max(H, state_dim)]
+  const int ld = (H > net.state_dim) ? H : net.state_dim;
+  float* h1 = h0 + R * ld;
+  float* red = h1 + R * ld;              // [R][32]
+  const int f = threadIdx.x;
+  const bool live = f < H;
+  const int n_warps = (blockDim.x + 31) >> 5;
+  const float inv_h = 1.f / (float)H;
+  for (int64_t row0 = (int64_t)blockIdx.x * R; row0 < n; row0 += (int64_t)gridDim.x * R) {
+    const int rows = (int)((n - row0 < R) ? (n - row0) : R);
+    for (int i = f; i < R * net.state_dim; i += blockDim.x) {
+      const int r = i / net.state_dim, k = i - r * net.state_dim;
+      h0[r * ld + k] = (r < rows) ? states[(row0 + r) * net.state_dim + k] : 0.f;
+    }
+    __syncthreads();
+    float* hin = h0;
+    float* hout = h1;
+    int in_dim = net.state_dim;
+    for (int l = 0; l < net.n_hidden; ++l) {
+      float acc[R];
+      const float bias = (live && net.b[l]) ? net.b[l][f] : 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = bias;
+      if (live) {
+        const float* w = net.W[l] + (int64_t)f * in_dim;
+        for (int k = 0; k < in_dim; ++k) {
+          const float wk = w[k];
+#pragma unroll
+          for (int r = 0; r < R; ++r) acc[r] = fmaf(wk, hin[r * ld + k], acc[r]);
+        }
+      }
+      // LayerNorm over the hidden units of each row (biased variance, two passes like at::native_layer_norm)
+      float s[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) s[r] = live ? acc[r] : 0.f;
+      dqn_block_sum<R>(s, red, n_warps);
+      float c[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) { c[r] = acc[r] - s[r] * inv_h; s[r] = live ? c[r] * c[r] : 0.f; }
+      dqn_block_sum<R>(s, red, n_warps);
+      if (live) {
+        const float g = net.gamma[l] ? net.gamma[l][f] : 1.f;
+        const float be = net.beta[l] ? net.beta[l][f] : 0.f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          float y = fmaf(c[r] * rsqrtf(s[r] * inv_h + net.eps[l]), g, be);
+          y = fmaxf(y, 0.f);
+          if (net.mask[l] && r < rows) y *= net.mask[l][(row0 + r) * H + f];
+          hout[r * ld + f] = y;
+        }
+      }
+      __syncthreads();
+      float* tmp = hin; hin = hout; hout = tmp;
+      in_dim = H;
+    }
+    for (int i = f; i < rows * net.out_dim; i += blockDim.x) {
+      const int r = i / net.out_dim, a = i - r * net.out_dim;
+      const float* w = net.W_out + (int64_t)a * in_dim;
+      float q = net.b_out ? net.b_out[a] : 0.f;
+      for (int k = 0; k < in_dim; ++k) q = fmaf(w[k], hin[r * ld + k], q);
+      q_out[(row0 + r) * net.out_dim + a] = q;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace pinnk

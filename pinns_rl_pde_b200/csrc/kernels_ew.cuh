@@ -821,9 +821,15 @@ __global__ void sumsq_kernel(const float* __restrict__ g, int64_t count, double*
 
 __global__ void adam_kernel(ParamTable tab, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             const double* __restrict__ sumsq, float max_norm, float lr, float beta1, float beta2, float eps,
-                            float weight_decay, float bc1, float bc2_sqrt) {
+                            float weight_decay, float bc1, float bc2_sqrt, const double* __restrict__ dyn) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= tab.off[tab.n]) return;
+  if (dyn) {                                       // graph-replayable step: step count and lr live on the device
+    const float step = (float)dyn[0];
+    lr = (float)dyn[1];
+    bc1 = 1.f - powf(beta1, step);
+    bc2_sqrt = sqrtf(1.f - powf(beta2, step));
+  }
   int lo = 0, hi = tab.n - 1;                      // tensor holding flat index i
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;

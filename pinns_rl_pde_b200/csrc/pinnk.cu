@@ -22,6 +22,7 @@
 #include "jet_math.cuh"
 #include "kernels_ew.cuh"
 #include "kernels_edge.cuh"
+#include "kernels_dqn.cuh"
 #include "sgemm.cuh"
 #include "tc_api.h"
 
@@ -1042,10 +1043,11 @@ extern "C" int pinnk_debug_stage_timers(int32_t which, uint64_t* out16, int32_t 
 }
 
 // ---- fused optimizer tail: clip_grad_norm_ + Adam(L2) on the flat gradient (trainer.py:690-694,292-297)
-extern "C" int pinnk_adam_step(float* const* params, const int64_t* numels, int32_t n_tensors, const float* flat_grad,
-                               float* exp_avg, float* exp_avg_sq, double* scratch, int64_t step, float lr, float beta1,
-                               float beta2, float eps, float weight_decay, float max_norm, void* stream) {
-  if (!params || !numels || !flat_grad || !exp_avg || !exp_avg_sq || !scratch || n_tensors < 1 || n_tensors > 64 || step < 1)
+static int adam_step_impl(float* const* params, const int64_t* numels, int32_t n_tensors, const float* flat_grad,
+                          float* exp_avg, float* exp_avg_sq, double* scratch, int64_t step, float lr, const double* dyn,
+                          float beta1, float beta2, float eps, float weight_decay, float max_norm, void* stream) {
+  if (!params || !numels || !flat_grad || !exp_avg || !exp_avg_sq || !scratch || n_tensors < 1 || n_tensors > 64 ||
+      (!dyn && step < 1))
     return fail(PINNK_E_INVALID, "adam_step: bad argument (1..64 tensors, step >= 1)");
   ParamTable tab;
   tab.n = n_tensors;
@@ -1058,10 +1060,64 @@ extern "C" int pinnk_adam_step(float* const* params, const int64_t* numels, int3
     sumsq_kernel<<<(unsigned)std::min<int64_t>((off + 255) / 256, 592), 256, 0, st>>>(flat_grad, off, scratch);
     PK_LAUNCH_OK();
   }
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  const float bc1 = dyn ? 1.f : 1.f - powf(beta1, (float)step);
+  const float bc2_sqrt = dyn ? 1.f : sqrtf(1.f - powf(beta2, (float)step));
   adam_kernel<<<blocks_for(off, 256), 256, 0, st>>>(tab, flat_grad, exp_avg, exp_avg_sq, scratch, max_norm, lr, beta1, beta2, eps,
-                                                    weight_decay, bc1, bc2_sqrt);
+                                                    weight_decay, bc1, bc2_sqrt, dyn);
+  PK_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int pinnk_adam_step(float* const* params, const int64_t* numels, int32_t n_tensors, const float* flat_grad,
+                               float* exp_avg, float* exp_avg_sq, double* scratch, int64_t step, float lr, float beta1,
+                               float beta2, float eps, float weight_decay, float max_norm, void* stream) {
+  return adam_step_impl(params, numels, n_tensors, flat_grad, exp_avg, exp_avg_sq, scratch, step, lr, nullptr, beta1, beta2,
+                        eps, weight_decay, max_norm, stream);
+}
+
+// the same step with the step count and the learning rate read from device memory (dyn[0] = step >= 1, dyn[1] = lr), so
+// that a CUDA graph holding the launch stays valid from one optimizer step to the next
+extern "C" int pinnk_adam_step_dev(float* const* params, const int64_t* numels, int32_t n_tensors, const float* flat_grad,
+                                   float* exp_avg, float* exp_avg_sq, double* scratch, const double* dyn, float beta1,
+                                   float beta2, float eps, float weight_decay, float max_norm, void* stream) {
+  if (!dyn) return fail(PINNK_E_INVALID, "adam_step_dev: null dyn");
+  return adam_step_impl(params, numels, n_tensors, flat_grad, exp_avg, exp_avg_sq, scratch, 0, 0.f, dyn, beta1, beta2, eps,
+                        weight_decay, max_norm, stream);
+}
+
+// ---- RL sampler: Q-network forward over the candidate grid (rl_agent.py:15-88,214-229), one launch
+extern "C" int pinnk_dqn_forward(const PinnkDqnLayer* layers, int32_t n_hidden, const float* w_out, const float* b_out,
+                                 int32_t out_dim, const float* states, int64_t n, float* q_out, void* stream) {
+  if (!layers || n_hidden < 1 || n_hidden > DQN_MAX_LAYERS || !w_out || out_dim < 1 || !states || !q_out || n < 0)
+    return fail(PINNK_E_INVALID, "dqn_forward: bad argument (1..8 hidden layers, out_dim >= 1)");
+  if (n == 0) return 0;
+  DqnNet net;
+  memset(&net, 0, sizeof(net));
+  net.n_hidden = n_hidden;
+  net.state_dim = layers[0].in_dim;
+  net.hidden = layers[0].out_dim;
+  net.out_dim = out_dim;
+  net.W_out = w_out;
+  net.b_out = b_out;
+  if (net.state_dim < 1 || net.hidden < 1 || net.hidden > 1024) return fail(PINNK_E_INVALID, "dqn_forward: hidden width must be 1..1024");
+  for (int l = 0; l < n_hidden; ++l) {
+    const PinnkDqnLayer& L = layers[l];
+    if (!L.weight || L.out_dim != net.hidden || L.in_dim != (l == 0 ? net.state_dim : net.hidden) || !(L.eps >= 0.f))
+      return fail(PINNK_E_INVALID, "dqn_forward: layer shapes must chain state_dim -> hidden -> ... -> hidden");
+    net.W[l] = L.weight; net.b[l] = L.bias; net.gamma[l] = L.ln_weight; net.beta[l] = L.ln_bias; net.mask[l] = L.dropout_mask;
+    net.eps[l] = L.eps;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int threads = (net.hidden + 31) / 32 * 32;
+  const int ld = std::max(net.hidden, net.state_dim);
+  const size_t smem = sizeof(float) * (2 * (size_t)DQN_ROWS * ld + DQN_ROWS * 32);
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(dqn_forward_kernel<DQN_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    return fail(PINNK_E_CUDA, "dqn_forward: shared memory request refused");
+  const int64_t groups = (n + DQN_ROWS - 1) / DQN_ROWS;
+  const unsigned blocks = (unsigned)std::min<int64_t>(groups, 16 * (int64_t)sm_count_of(dev));
+  dqn_forward_kernel<DQN_ROWS><<<blocks, threads, smem, (cudaStream_t)stream>>>(net, states, n, q_out);
   PK_LAUNCH_OK();
   return 0;
 }

@@ -33,11 +33,33 @@ def patch_reference(compat: str = "reference"):
         cls.compat = compat
         cls.compute_residual = lambda self, model, x, t: F.compute_residual(self, model, x, t)
         cls.compute_loss = lambda self, model, x, t: F.compute_loss(self, model, x, t)
+    # RL sampler: RLAgent.select_action (rl/rl_agent.py:214-229) scores the candidate grid through pinnk_dqn_forward when
+    # the agent lives on a GPU; a CPU agent keeps the reference's own torch forward (the agent is not on the hot path then).
+    try:
+        agent_cls = importlib.import_module("pinnrl.rl.rl_agent").RLAgent
+    except Exception:          # the module imports matplotlib at the top; without it there is no agent to patch
+        agent_cls = None
+    if agent_cls is not None and agent_cls not in _PATCHED:
+        original = agent_cls.select_action
+        _PATCHED[agent_cls] = (original,)
+
+        def select_action(self, state, _orig=original):
+            import torch
+            from . import rl
+            if torch.device(self.device).type == "cuda":
+                return rl.select_action(self, state)
+            return _orig(self, state)
+        agent_cls.select_action = select_action
     return sorted(c.__name__ for c in _PATCHED)
 
 
 def unpatch_reference():
-    for cls, (res, loss) in list(_PATCHED.items()):
+    for cls, saved in list(_PATCHED.items()):
+        if len(saved) == 1:                      # RLAgent.select_action
+            cls.select_action = saved[0]
+            _PATCHED.pop(cls)
+            continue
+        res, loss = saved
         if res is not None:
             cls.compute_residual = res
         if loss is not None:

@@ -368,7 +368,10 @@ def _build_calls(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_glob
             Segment(kind=L.PDE_VALUE, row_start=0, row_count=n_i, component=2, weight=1.0 / max(n_i, 1),
                     target=target.detach().to(torch.float32).reshape(-1).contiguous(), **mk)]))
     else:
-        xb = torch.tensor([dom[0][0], dom[0][1]], dtype=torch.float32, device=dev).reshape(-1, 1)
+        # built on the device (no host copy: the call may be inside a CUDA-graph capture); same float32 values as
+        # torch.tensor([x_min, x_max])
+        xb = torch.cat([torch.full((1, 1), float(dom[0][0]), dtype=torch.float32, device=dev),
+                        torch.full((1, 1), float(dom[0][1]), dtype=torch.float32, device=dev)], dim=0)
         tb = torch.linspace(td[0], td[1], 100, device=dev).reshape(-1, 1)
         xb = xb.repeat_interleave(len(tb), dim=0)
         tb = tb.repeat(len(xb) // len(tb), 1)

@@ -16,6 +16,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as F
+from . import rl as _rl
 
 
 @dataclass
@@ -264,8 +265,7 @@ class PDEBase:
         axes.append(torch.linspace(self.time_domain[0], self.time_domain[1], gs, device=self.device))
         pts = torch.stack([g.flatten() for g in torch.meshgrid(*axes, indexing="ij")], dim=1)
         with torch.no_grad():
-            probs = torch.abs(self.rl_agent.select_action(pts))
-            probs = probs / torch.sum(probs)
+            probs = _rl.grid_scores(self.rl_agent, pts)      # DQNNetwork-shaped policy nets: one libpinnk launch
         sel = multinomial_large(probs.flatten(), min(num_points, len(pts)))
         chosen = pts[sel]
         if len(chosen) < num_points:

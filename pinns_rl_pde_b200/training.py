@@ -8,6 +8,7 @@ across ranks and the flat gradient + loss sums are all-reduced once per step (pa
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
@@ -53,7 +54,8 @@ class FusedAdam:
     """clip_grad_norm_ + Adam(L2 weight decay) on the flat gradient in two libpinnk launches
     (trainer.py:690-694,292-297); state and update rule identical to ``torch.optim.Adam``."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=0.0):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=0.0,
+                 capturable: bool = False):
         import ctypes as C
         from . import _lib
         self.params = [p for p in params if p.requires_grad]
@@ -70,6 +72,11 @@ class FusedAdam:
         self._ptrs = (C.c_void_p * len(self.params))()
         self._numels = (C.c_int64 * len(self.params))(*[p.numel() for p in self.params])
         self.param_groups = [{"lr": lr}]           # so torch LR schedulers can drive it
+        # capturable: step count and lr live in device memory ([step, lr] doubles) so a captured CUDA graph of the step
+        # stays valid from one call to the next (pinnk_adam_step_dev)
+        self.capturable = bool(capturable)
+        self._dyn = torch.tensor([0.0, lr], dtype=torch.float64, device=dev) if self.capturable else None
+        self._dyn_lr = float(lr)
 
     def step(self, flat_grad: torch.Tensor):
         C, L = self._C, self._lib
@@ -79,6 +86,19 @@ class FusedAdam:
                 raise L.PinnkError("FusedAdam needs contiguous float32 CUDA parameters")
             self._ptrs[i] = p.data_ptr()
         lr = float(self.param_groups[0]["lr"])
+        if self.capturable:
+            capturing = torch.cuda.is_current_stream_capturing()
+            if lr != self._dyn_lr:
+                if capturing:
+                    raise L.PinnkError("FusedAdam: set the learning rate outside the captured region (sync_lr())")
+                self.sync_lr()
+            self._dyn[0:1].add_(1.0)               # on the stream: replayed with the graph
+            L.check(L.load().pinnk_adam_step_dev(C.cast(self._ptrs, C.c_void_p), C.cast(self._numels, C.c_void_p),
+                                                 len(self.params), flat_grad.data_ptr(), self.exp_avg.data_ptr(),
+                                                 self.exp_avg_sq.data_ptr(), self._scratch.data_ptr(), self._dyn.data_ptr(),
+                                                 self.betas[0], self.betas[1], self.eps, self.weight_decay, self.max_norm,
+                                                 C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pinnk_adam_step_dev")
+            return
         L.check(L.load().pinnk_adam_step(C.cast(self._ptrs, C.c_void_p), C.cast(self._numels, C.c_void_p), len(self.params),
                                          flat_grad.data_ptr(), self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
                                          self._scratch.data_ptr(), self.step_count, lr, self.betas[0], self.betas[1],
@@ -86,9 +106,21 @@ class FusedAdam:
                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pinnk_adam_step")
 
 
+    def sync_lr(self):
+        """Push ``param_groups[0]['lr']`` to the device copy a captured step reads."""
+        lr = float(self.param_groups[0]["lr"])
+        if self.capturable and lr != self._dyn_lr:
+            self._dyn[1:2].fill_(lr)
+            self._dyn_lr = lr
+
+
 class PDETrainer:
     def __init__(self, model: nn.Module, pde, optimizer_config=None, config=None, device=None, rl_agent=None,
-                 fused: bool = False):
+                 fused: bool = False, graph: bool = False):
+        """``fused``: whole step inside libpinnk (loss + weighted gradient in one pass per row set, clip + Adam).
+        ``graph`` (needs ``fused``, single process): the fused step is captured into a CUDA graph per batch shape after
+        ``GRAPH_WARMUP`` eager steps and replayed afterwards -- small batches (the reference's 2 048-point default) are
+        bound by the ~100 launches of a step, not by the kernels."""
         self.model, self.pde, self.rl_agent = model, pde, rl_agent
         self.training: TrainingConfig = (getattr(config, "training", None) or config
                                          or getattr(pde.config, "training", None) or TrainingConfig())
@@ -97,10 +129,15 @@ class PDETrainer:
         self.device = device or next(model.parameters()).device
         oc = optimizer_config or {}
         self.fused = bool(fused)
+        self.graph = bool(graph)
+        if self.graph and not self.fused:
+            raise ValueError("PDETrainer(graph=True) captures the fused step: pass fused=True")
+        self._graphs: Dict[tuple, dict] = {}
         lr, wd = oc.get("learning_rate", self.training.learning_rate), oc.get("weight_decay", self.training.weight_decay)
         if self.fused:
             # whole step in libpinnk: loss + weighted gradient in one pass per row set, then clip + Adam in two launches
-            self.optimizer = FusedAdam(model.parameters(), lr=lr, weight_decay=wd, max_norm=self.training.gradient_clipping)
+            self.optimizer = FusedAdam(model.parameters(), lr=lr, weight_decay=wd, max_norm=self.training.gradient_clipping,
+                                       capturable=self.graph)
             self._flat = None
         else:
             self.optimizer = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)
@@ -121,6 +158,8 @@ class PDETrainer:
             lo, hi = parallel.shard_bounds(n_global)
             x, t = x[lo:hi], t[lo:hi]
         if self.fused:
+            if self.graph and parallel.world_size() == 1:
+                return self._graph_step(x, t)
             return self._fused_step(x, t, n_global)
         self.optimizer.zero_grad(set_to_none=True)
         if parallel.world_size() > 1:
@@ -148,6 +187,96 @@ class PDETrainer:
         zero = torch.zeros((), device=flat.device)
         return {"residual": sums[0], "boundary": sums[1], "initial": sums[2], "smoothness": zero, "data": zero.clone(),
                 "total": w_res * sums[0] + w_bc * sums[1] + w_ic * sums[2]}
+
+    GRAPH_WARMUP = 2
+
+    def _graph_step(self, x, t):
+        """The fused step through a CUDA graph: the first GRAPH_WARMUP calls for a batch shape run eagerly (they size the
+        workspaces and are real optimizer steps), the next one is captured, every later one copies the batch into the
+        graph's static rows and replays it.  Boundary / initial rows that the reference draws with torch's RNG stay
+        random under replay (torch registers the generator with the graph).  The returned tensors are overwritten by
+        the next step of the same shape."""
+        key = (tuple(x.shape), tuple(t.shape), x.dtype, t.dtype)
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._graphs[key] = {"calls": 0, "graph": None}
+        if g["graph"] is None:
+            g["calls"] += 1
+            if g["calls"] <= self.GRAPH_WARMUP:
+                return self._fused_step(x, t)
+            self.optimizer.sync_lr()
+            g["x"], g["t"] = x.detach().clone(), t.detach().clone()
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g["out"] = self._fused_step(g["x"], g["t"])
+            g["graph"] = graph
+        else:
+            g["x"].copy_(x)
+            g["t"].copy_(t)
+            self.optimizer.step_count += 1
+        self.optimizer.sync_lr()
+        g["graph"].replay()
+        return g["out"]
+
+    def _compute_validation_loss(self, num_points: int = 1000) -> Dict[str, float]:
+        """trainer.py:140-162: compute_loss on freshly generated points, returned as floats.  The reference builds the full
+        autograd graph for it (its derivatives ARE autograd); here the jets are forward-mode, so the call runs under
+        no_grad: forward kernels only, no stash, no gradient buffers.  Same RNG consumption as the reference
+        (one generate_collocation_points call); as there, eval() is undone by the derivative evaluation (pde_base.py:638)."""
+        self.model.eval()
+        x_val, t_val = self.pde.generate_collocation_points(num_points)
+        with torch.no_grad():
+            losses = self.pde.compute_loss(self.model, x_val.to(self.device), t_val.to(self.device))
+        return {"total_loss": losses["total"].item(), "residual_loss": losses["residual"].item(),
+                "boundary_loss": losses["boundary"].item(), "initial_loss": losses["initial"].item()}
+
+    def live_snapshot(self, epoch: int, grid_size: int = 60) -> Dict[str, object]:
+        """The arrays of trainer.py:171-279 (``live_snapshot.npz``): predicted u and the signed residual on a fixed
+        grid_size x grid_size grid -- (x, t) for 1-D problems, (x1, x2) at the middle of the time interval otherwise.
+        Both fields come from forward-only libpinnk passes (no autograd graph, no stash)."""
+        import numpy as np
+        pde, dev = self.pde, self.device
+        dim = int(getattr(pde, "dimension", 1))
+        t_lo, t_hi = float(pde.time_domain[0]), float(pde.time_domain[1])
+        if dim <= 1:
+            ax, ay = (np.linspace(float(pde.domain[0][0]), float(pde.domain[0][1]), grid_size, dtype=np.float32),
+                      np.linspace(t_lo, t_hi, grid_size, dtype=np.float32))
+            xx, tt = np.meshgrid(ax, ay, indexing="xy")
+            x_flat = torch.tensor(xx.reshape(-1, 1), device=dev)
+            t_flat = torch.tensor(tt.reshape(-1, 1), device=dev)
+            meta = dict(dimension=1, x_label="x", y_label="t", fixed_t=float("nan"))
+        else:
+            fixed_t = 0.5 * (t_lo + t_hi)
+            ax = np.linspace(float(pde.domain[0][0]), float(pde.domain[0][1]), grid_size, dtype=np.float32)
+            ay = np.linspace(float(pde.domain[1][0]), float(pde.domain[1][1]), grid_size, dtype=np.float32)
+            x1, x2 = np.meshgrid(ax, ay, indexing="xy")
+            x_flat = torch.tensor(np.stack([x1.reshape(-1), x2.reshape(-1)], axis=1), device=dev, dtype=torch.float32)
+            t_flat = torch.full((x_flat.shape[0], 1), fixed_t, dtype=torch.float32, device=dev)
+            meta = dict(dimension=2, x_label="x1", y_label="x2", fixed_t=float(fixed_t))
+        was_training = self.model.training
+        try:
+            with torch.no_grad():
+                u = F.model_forward(self.model, torch.cat([x_flat, t_flat], dim=1))
+                u_np = u.detach().cpu().numpy()
+                if u_np.ndim == 2 and u_np.shape[-1] > 1:
+                    u_np = u_np[..., 0]
+                u_np = u_np.reshape(grid_size, grid_size)
+                try:
+                    r = self.pde.compute_residual(self.model, x_flat, t_flat)
+                    r_np = r.detach().cpu().numpy().reshape(grid_size, grid_size)
+                except Exception:
+                    r_np = np.zeros_like(u_np)           # the reference swallows residual failures here too
+        finally:
+            self.model.train(was_training)
+        return dict(axis_x=ax, axis_y=ay, u_pred=u_np, residual=r_np, epoch=int(epoch), **meta)
+
+    def _save_live_snapshot(self, experiment_dir: str, epoch: int, grid_size: int = 60) -> None:
+        """trainer.py:171-279: write ``live_snapshot.npz`` for the dashboard's monitor tab (same keys)."""
+        import numpy as np
+        if not experiment_dir:
+            return
+        np.savez(os.path.join(experiment_dir, "live_snapshot.npz"), **self.live_snapshot(epoch, grid_size))
 
     def cosine_lr(self, epoch: int) -> float:
         t = self.training

@@ -289,6 +289,33 @@ def _base_loss64(model, residual, s, fns):
     return {"residual": res_loss, "boundary": b, "initial": i, "total": res_loss + 10 * b + 10 * i}
 
 
+def run_dqn_case(tag="x_dqn", state_dim=2, hidden=128, grid=24, seed=0):
+    """Q-network of the RL sampler (rl_agent.py:15-88) in eval mode over a grid x grid candidate mesh: the unmodified
+    reference vs oracle/ref_port.dqn_forward_port (bit-identical in fp32) -> weights, states, Q-values (fp32 / fp64)."""
+    from pinnrl.rl.rl_agent import DQNNetwork as RefDQN
+    torch.manual_seed(seed)
+    net = RefDQN(state_dim, 1, hidden).eval()
+    with torch.no_grad():                                   # non-trivial LayerNorm affine and biases (init is 1 / 0)
+        for name, p in net.named_parameters():
+            if name.endswith("bias") or ".1.weight" in name:
+                p.add_(0.1 * torch.randn_like(p))
+    axes = [torch.linspace(-1.0, 1.0, grid), torch.linspace(0.0, 1.0, grid)] + [torch.linspace(0.0, 1.0, grid)] * (state_dim - 2)
+    pts = torch.stack([g.flatten() for g in torch.meshgrid(*axes[:state_dim], indexing="ij")], dim=1)
+    with torch.no_grad():
+        q32 = net(pts)
+        port32 = ref_port.dqn_forward_port(net.state_dict(), pts)
+        net64 = copy.deepcopy(net).double()
+        q64 = net64(pts.double())
+        port64 = ref_port.dqn_forward_port(net64.state_dict(), pts.double())
+    assert torch.equal(q32, port32), "oracle port of DQNNetwork.forward is not bit-identical to the reference (fp32)"
+    assert torch.equal(q64, port64)
+    out = {"states": pts.numpy(), "q32": q32.numpy(), "q64": q64.numpy()}
+    for k, v in net.state_dict().items():
+        out["w::" + k] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, tag + ".npz"), **out)
+    return {"case": tag, "port_bit_identical_fp32": True, "ref32_vs_ref64": rel(q32.double(), q64), "states": int(pts.shape[0])}
+
+
 def main_next():
     """`python tests/golden/make_golden.py next`: only the fixtures of the SURVEY 8(f).4 PDEs (existing files untouched)."""
     reports = [run_case("x_wave_ff_small", "wave", "feedforward", 32, 3, 96),
@@ -326,4 +353,11 @@ def main():
 
 
 if __name__ == "__main__":
-    main_next() if sys.argv[1:] == ["next"] else main()
+    if sys.argv[1:] == ["dqn"]:
+        rep = run_dqn_case()
+        path = os.path.join(HERE, "golden_report.json")
+        old = [r for r in json.load(open(path)) if r["case"] != rep["case"]]
+        json.dump(old + [rep], open(path, "w"), indent=1)
+        print(rep)
+    else:
+        main_next() if sys.argv[1:] == ["next"] else main()

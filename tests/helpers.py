@@ -33,7 +33,8 @@ PDES = {
 
 
 def fixtures():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz"))
+    """PDE hot-path fixtures (x_dqn.npz, the RL sampler's Q-network, has its own tests in test_dqn.py)."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f != "x_dqn.npz")
 
 
 def load_fixture(tag):
