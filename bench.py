@@ -353,15 +353,19 @@ def run_ours(args):
                 gbs = BYTES_PER_ROW[k] * rows_per_launch / (ms_k * 1e-3) / 1e9
                 per_kernel[k] = {"launch_ms": ms_k, "achieved_gbs": gbs, "frac_hbm": gbs / hbm}
         achieved = bytes_per_row * rows_per_launch / (ms_launch * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_note = None, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            if dom in tj and tj[dom]["rows_per_launch"] == int(rows_per_launch):
-                traffic = tj[dom]["bytes_per_launch"]
+            if dom in tj:
+                # per launch like `achieved`: the capture's launch processed rows_per_launch(capture) stacked rows, the
+                # kernels stream every row once, so DRAM bytes scale with the rows of a launch
+                traffic = tj[dom]["bytes_per_launch"] * (rows_per_launch / tj[dom]["rows_per_launch"])
+                traffic_note = ("ncu --set full dram bytes of a %d-row launch (%s) x %.0f rows / launch here"
+                                % (tj[dom]["rows_per_launch"], tj[dom]["capture"], rows_per_launch))
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                "traffic": traffic, "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_per_row * rows_per_launch,
+                "traffic": traffic, "traffic_source": traffic_note, "peak_source": hbm_src, "algorithmic_bytes_per_launch": bytes_per_row * rows_per_launch,
                 "launch_ms": ms_launch, "launches_per_step": n_dom // 2, "kernels": per_kernel,
                 "tensor": {"achieved_tflops": flops_per_launch / (ms_launch * 1e-3) / 1e12, "peak_tflops": tensor_peak,
                            "frac": flops_per_launch / (ms_launch * 1e-3) / 1e12 / tensor_peak,
