@@ -370,8 +370,12 @@ def run_ours(args):
                 "tensor": {"achieved_tflops": flops_per_launch / (ms_launch * 1e-3) / 1e12, "peak_tflops": tensor_peak,
                            "frac": flops_per_launch / (ms_launch * 1e-3) / 1e12 / tensor_peak,
                            "peak_source": tensor_src},
-                "why_hbm": "32 algorithmic FLOP per byte x %.2f TB/s = %.0f TFLOP/s < %.0f TFLOP/s emulated-fp32 tensor peak"
-                           % (hbm / 1e3, 32 * hbm / 1e3, tensor_peak),
+                "why_hbm": "%s: %.1f algorithmic FLOP per byte (2*128*128 FLOP / %d B per row) x %.2f TB/s = %.0f TFLOP/s, "
+                           "below the %.0f TFLOP/s emulated-fp32 tensor peak; the 1024 B/row kernels (forward, wgrad) sit at "
+                           "%.0f TFLOP/s, i.e. at the crossover"
+                           % (dom, 2.0 * HIDDEN * HIDDEN / bytes_per_row, bytes_per_row, hbm / 1e3,
+                              2.0 * HIDDEN * HIDDEN / bytes_per_row * hbm / 1e3, tensor_peak,
+                              2.0 * HIDDEN * HIDDEN / 1024 * hbm / 1e3),
                 "share_of_step": {k: v[0] / 2 / step_ms for k, v in prof.items() if v[1]},
                 "step_flops_frac_of_tensor_peak": (FLOPS_PER_POINT_STEP * n_local / (ms_total / args.steps * 1e-3) / 1e12) / tensor_peak}
 

@@ -2,16 +2,17 @@
 //   rl_agent.py:15-88   DQNNetwork = [Linear -> LayerNorm -> ReLU -> Dropout] x (num_layers - 1), Linear(hidden -> action_dim)
 //   rl_agent.py:214-229 RLAgent.select_action: policy_net(points).view(1, -1) on <= 100^(d+1) grid points
 // One kernel for the whole network: a block owns R candidate rows, thread f owns hidden unit f; the activations of the R
-// rows stay in shared memory from the state vector to the Q-values, weights are read through L1/L2 (<= 3 x 64 KB for the
-// reference's hidden_dim = 128).  The work is ~0.1 GFLOP per call: latency-bound, so the point of the kernel is one launch
-// instead of ~12 (and no [N, hidden] round trips), not tensor cores.
+// rows stay in shared memory from the state vector to the Q-values; weight matrices are staged 32 K-columns at a time,
+// transposed, through shared memory (coalesced global reads, conflict-free per-unit reads) and each staged weight is used
+// for R rows.  The work is ~0.3 GFLOP per 100 x 100 grid: the point of the kernel is one FFMA-bound launch instead of ~12
+// launch-bound ones with [N, hidden] round trips, not tensor cores.
 #pragma once
 #include <cstdint>
 
 namespace pinnk {
 
 constexpr int DQN_MAX_LAYERS = 8;
-constexpr int DQN_ROWS = 8;
+constexpr int DQN_ROWS = 16;
 
 struct DqnNet {
   const float* W[DQN_MAX_LAYERS];       // [hidden, in] row-major (nn.Linear.weight)
@@ -50,26 +51,36 @@ __device__ __forceinline__ void dqn_block_sum(float (&v)[R], float* red, int n_w
   __syncthreads();
 }
 
+// shared memory: h0 | h1 [R][ld] activations (ld = widest layer rounded up to 4, zero padded), wt [KC][pitch] the current
+// K-chunk of a weight matrix TRANSPOSED (pitch odd: the transposing store and the per-unit read are both conflict-free),
+// red [R][32] block-reduction scratch.
+constexpr int DQN_KC = 32;
+__host__ __device__ inline int dqn_ld(int hidden, int state_dim) { const int m = hidden > state_dim ? hidden : state_dim; return (m + 3) & ~3; }
+__host__ __device__ inline int dqn_pitch(int hidden) { return hidden | 1; }
+__host__ __device__ inline size_t dqn_smem_bytes(int rows, int hidden, int state_dim) {
+  return sizeof(float) * ((size_t)2 * rows * dqn_ld(hidden, state_dim) + (size_t)DQN_KC * dqn_pitch(hidden) + (size_t)rows * 32);
+}
+
 template <int R>
 __global__ void __launch_bounds__(1024) dqn_forward_kernel(DqnNet net, const float* __restrict__ states, int64_t n,
                                                            float* __restrict__ q_out) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int H = net.hidden;
-  float* h0 = sm;                        // [R][max(H, state_dim)]
-  const int ld = (H > net.state_dim) ? H : net.state_dim;
+  const int ld = dqn_ld(H, net.state_dim), pitch = dqn_pitch(H);
+  float* h0 = sm;
   float* h1 = h0 + R * ld;
-  float* red = h1 + R * ld;              // [R][32]
+  float* wt = h1 + R * ld;
+  float* red = wt + DQN_KC * pitch;
   const int f = threadIdx.x;
   const bool live = f < H;
   const int n_warps = (blockDim.x + 31) >> 5;
   const float inv_h = 1.f / (float)H;
   for (int64_t row0 = (int64_t)blockIdx.x * R; row0 < n; row0 += (int64_t)gridDim.x * R) {
     const int rows = (int)((n - row0 < R) ? (n - row0) : R);
-    for (int i = f; i < R * net.state_dim; i += blockDim.x) {
-      const int r = i / net.state_dim, k = i - r * net.state_dim;
-      h0[r * ld + k] = (r < rows) ? states[(row0 + r) * net.state_dim + k] : 0.f;
+    for (int i = f; i < R * ld; i += blockDim.x) {          // state vectors, zero padded to ld
+      const int r = i / ld, k = i - r * ld;
+      h0[i] = (r < rows && k < net.state_dim) ? states[(row0 + r) * net.state_dim + k] : 0.f;
     }
-    __syncthreads();
     float* hin = h0;
     float* hout = h1;
     int in_dim = net.state_dim;
@@ -78,12 +89,25 @@ __global__ void __launch_bounds__(1024) dqn_forward_kernel(DqnNet net, const flo
       const float bias = (live && net.b[l]) ? net.b[l][f] : 0.f;
 #pragma unroll
       for (int r = 0; r < R; ++r) acc[r] = bias;
-      if (live) {
-        const float* w = net.W[l] + (int64_t)f * in_dim;
-        for (int k = 0; k < in_dim; ++k) {
-          const float wk = w[k];
+      const float* __restrict__ W = net.W[l];
+      for (int k0 = 0; k0 < in_dim; k0 += DQN_KC) {
+        __syncthreads();                                      // previous chunk consumed / hin complete
+        for (int i = f; i < H * DQN_KC; i += blockDim.x) {    // coalesced rows of W -> transposed chunk
+          const int u = i / DQN_KC, kk = i - u * DQN_KC;
+          wt[kk * pitch + u] = (k0 + kk < in_dim) ? W[(int64_t)u * in_dim + k0 + kk] : 0.f;
+        }
+        __syncthreads();
+        const int kc = (in_dim - k0 < DQN_KC) ? ((in_dim - k0 + 3) & ~3) : DQN_KC;   // h is zero padded to a multiple of 4
+        if (live) {
+          for (int kk = 0; kk < kc; kk += 4) {
+            const float w0 = wt[(kk + 0) * pitch + f], w1 = wt[(kk + 1) * pitch + f];
+            const float w2 = wt[(kk + 2) * pitch + f], w3 = wt[(kk + 3) * pitch + f];
 #pragma unroll
-          for (int r = 0; r < R; ++r) acc[r] = fmaf(wk, hin[r * ld + k], acc[r]);
+            for (int r = 0; r < R; ++r) {
+              const float4 hv = *reinterpret_cast<const float4*>(&hin[r * ld + k0 + kk]);   // broadcast read
+              acc[r] = fmaf(w0, hv.x, fmaf(w1, hv.y, fmaf(w2, hv.z, fmaf(w3, hv.w, acc[r]))));
+            }
+          }
         }
       }
       // LayerNorm over the hidden units of each row (biased variance, two passes like at::native_layer_norm)
@@ -95,21 +119,21 @@ __global__ void __launch_bounds__(1024) dqn_forward_kernel(DqnNet net, const flo
 #pragma unroll
       for (int r = 0; r < R; ++r) { c[r] = acc[r] - s[r] * inv_h; s[r] = live ? c[r] * c[r] : 0.f; }
       dqn_block_sum<R>(s, red, n_warps);
-      if (live) {
-        const float g = net.gamma[l] ? net.gamma[l][f] : 1.f;
-        const float be = net.beta[l] ? net.beta[l][f] : 0.f;
+      if (f < ld) {
+        const float g = (live && net.gamma[l]) ? net.gamma[l][f] : 1.f;
+        const float be = (live && net.beta[l]) ? net.beta[l][f] : 0.f;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           float y = fmaf(c[r] * rsqrtf(s[r] * inv_h + net.eps[l]), g, be);
           y = fmaxf(y, 0.f);
-          if (net.mask[l] && r < rows) y *= net.mask[l][(row0 + r) * H + f];
-          hout[r * ld + f] = y;
+          if (live && net.mask[l] && r < rows) y *= net.mask[l][(row0 + r) * H + f];
+          hout[r * ld + f] = live ? y : 0.f;                 // padding columns stay zero
         }
       }
-      __syncthreads();
       float* tmp = hin; hin = hout; hout = tmp;
       in_dim = H;
     }
+    __syncthreads();
     for (int i = f; i < rows * net.out_dim; i += blockDim.x) {
       const int r = i / net.out_dim, a = i - r * net.out_dim;
       const float* w = net.W_out + (int64_t)a * in_dim;

@@ -1110,8 +1110,8 @@ extern "C" int pinnk_dqn_forward(const PinnkDqnLayer* layers, int32_t n_hidden, 
   int dev = 0;
   cudaGetDevice(&dev);
   const int threads = (net.hidden + 31) / 32 * 32;
-  const int ld = std::max(net.hidden, net.state_dim);
-  const size_t smem = sizeof(float) * (2 * (size_t)DQN_ROWS * ld + DQN_ROWS * 32);
+  const size_t smem = dqn_smem_bytes(DQN_ROWS, net.hidden, net.state_dim);
+  if (smem > 227 * 1024) return fail(PINNK_E_INVALID, "dqn_forward: hidden width needs more than 227 KB of shared memory");
   if (smem > 48 * 1024 &&
       cudaFuncSetAttribute(dqn_forward_kernel<DQN_ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
     return fail(PINNK_E_CUDA, "dqn_forward: shared memory request refused");

@@ -67,7 +67,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Wait used by the (many) epilogue / flush warps: they have slack (double-buffered accumulators), so after a failed
 // probe they sleep instead of re-polling -- polling warps were stealing ~30 % of the issue slots from the convert warps
 // that share their scheduler.
+#ifndef PINNK_EPI_SLEEP
+#define PINNK_EPI_SLEEP 64      // ns between probes (A/B: PINNK_NVCC_EXTRA=-DPINNK_EPI_SLEEP=...; 0 = hinted try_wait instead)
+#endif
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+#if PINNK_EPI_SLEEP == 0
+  mbar_wait(bar, parity);
+  return;
+#endif
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
   for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
@@ -79,7 +86,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return;
-    __nanosleep(64);
+    __nanosleep(PINNK_EPI_SLEEP);
   }
   __trap();
 }

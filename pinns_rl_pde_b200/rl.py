@@ -52,6 +52,9 @@ class UnsupportedQNetwork(ValueError):
     pass
 
 
+MAX_HIDDEN = 128       # widest Q-network the one-launch kernel is used for (benchmarks/sampling.py:124 builds hidden_dim = 64)
+
+
 def _lower(net: nn.Module) -> Tuple[List[Tuple[nn.Linear, nn.LayerNorm, float]], nn.Linear]:
     """By structure, so the reference's own ``DQNNetwork`` instances are accepted."""
     seq = getattr(net, "layers", None)
@@ -72,6 +75,11 @@ def _lower(net: nn.Module) -> Tuple[List[Tuple[nn.Linear, nn.LayerNorm, float]],
         raise UnsupportedQNetwork("the Q-network must end in a Linear layer")
     if not 1 <= len(groups) <= 8:
         raise UnsupportedQNetwork("1..8 hidden groups")
+    if groups[0][0].out_features > MAX_HIDDEN:
+        # the one-launch kernel is FFMA-bound: measured x1.8 (eval) / x1.15 (live dropout) over the torch modules at
+        # hidden 128 on a 100 x 100 grid, but x0.6 at hidden 256 where cuBLAS takes over -- wider nets are declined
+        # (callers keep the agent's own forward) rather than made slower
+        raise UnsupportedQNetwork(f"hidden width {groups[0][0].out_features} > {MAX_HIDDEN}: not covered by pinnk_dqn_forward")
     return groups, out
 
 

@@ -37,6 +37,8 @@ def test_mirror_loads_reference_state_dict_and_refuses_cpu():
         rl.dqn_forward(net, pts)                     # CPU tensors: no fallback
     with pytest.raises(rl.UnsupportedQNetwork):
         rl._lower(torch.nn.Sequential(torch.nn.Linear(2, 1)))
+    with pytest.raises(rl.UnsupportedQNetwork):       # wider than the one-launch kernel is used for: declined, loudly
+        rl._lower(rl.DQNNetwork(2, 1, 512))
 
 
 def _torch_twin(net):
@@ -62,9 +64,10 @@ def test_gpu_matches_reference_fixture():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("state_dim,hidden,layers,actions,n", [(2, 128, 3, 1, 10000), (3, 64, 4, 1, 1003), (2, 256, 2, 4, 77),
-                                                              (4, 100, 3, 2, 1), (2, 1024, 3, 1, 513)])
-def test_gpu_shapes_against_oracle(state_dim, hidden, layers, actions, n):
+                                                              (4, 100, 3, 2, 1), (2, 512, 3, 1, 513), (5, 50, 3, 3, 40)])
+def test_gpu_shapes_against_oracle(state_dim, hidden, layers, actions, n, monkeypatch):
     from pinns_rl_pde_b200 import rl
+    monkeypatch.setattr(rl, "MAX_HIDDEN", 1024)          # the kernel itself covers what fits in shared memory
     dev = torch.device("cuda:0")
     torch.manual_seed(state_dim * 1000 + hidden)
     net = rl.DQNNetwork(state_dim, actions, hidden, num_layers=layers).to(dev).eval()

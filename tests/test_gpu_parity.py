@@ -377,7 +377,9 @@ def test_full_size_1m_points_properties(dev):
     (g2,) = torch.autograd.grad(c2[0], [p for p in model.parameters()][4:5])
     assert abs(comp[0].item() - 0.5 * (c1[0].item() + c2[0].item())) <= 2e-6 * abs(comp[0].item())
     assert abs(comp[0].item() - float((r.double() ** 2).mean())) <= 2e-6 * abs(comp[0].item())
-    assert rel(0.5 * (g1 + g2), gw) <= 5e-6
+    # two independent fp32 evaluations of the same gradient: the wgrad partial sums are combined with atomic reductions, so
+    # even identical calls differ by 2e-6 .. 4e-6 from run to run (profiles/flaky_probe.py); the gate is the path's 1e-5
+    assert rel(0.5 * (g1 + g2), gw) <= 1e-5
     assert abs(comp[1].item() - c1[1].item()) <= 1e-7 * abs(comp[1].item()) + 1e-12       # BC/IC terms do not depend on the shard
 
 
