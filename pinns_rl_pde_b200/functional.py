@@ -273,8 +273,11 @@ def _data_loss(pde, model) -> torch.Tensor:
     return pde._apply_loss_fn(u - obs["u"].to(dev))
 
 
+MERGE_ALL_MAX_POINTS = 32768    # fused step: up to this many collocation rows, ALL row sets go through one pass
+
+
 def _build_calls(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_global: Optional[int] = None,
-                 merge_value_rows: bool = False):
+                 merge_value_rows: bool = False, merge_all_rows: bool = False):
     """The libpinnk calls (engine, rows, segments) that make up compute_loss: residual rows (component 0), boundary
     rows (1), initial rows (2), exactly the point sets and targets the reference builds."""
     name = pde_name(pde)
@@ -405,6 +408,21 @@ def _build_calls(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_glob
             calls.append((get_engine(model, [], 100, program=program), xi, ti, [
                 Segment(kind=L.PDE_VALUE, row_start=0, row_count=100, component=2, weight=0.01, target=ic_target, **mk)]))
 
+    if merge_all_rows and len(calls) > 1:
+        # Small batches are bound by the number of launches, not by the kernels: put boundary / initial rows BEHIND the
+        # collocation rows of the same call (they ride through the jet kernels with unused derivative columns -- a few
+        # hundred rows) so that a step is one forward and one reverse sweep (~27 launches) instead of two or three.  The
+        # value / d/dx error functionals read the same columns in the residual's jet layout (direction 0 is x).  Like
+        # merge_value_rows this is only valid when every component accumulates into one gradient buffer.
+        import dataclasses
+        rows, segs, off = [], [], 0
+        for _, xx, tt, ss in calls:
+            pts = xx if tt is None else torch.cat([xx, tt], dim=1)
+            rows.append(pts)
+            segs.extend(dataclasses.replace(sg, row_start=sg.row_start + off) for sg in ss)
+            off += pts.shape[0]
+        eng = get_engine(model, dirs, off, whole=True, program=program)
+        calls = [(eng, torch.cat(rows, dim=0), None, segs)]
     return calls, _weights(pde, heat)
 
 
@@ -427,7 +445,8 @@ def loss_step_flat(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_gl
     Returns (components fp32 [3] = residual, boundary, initial means; weights; flat gradient of
     ``res_scale * w_res * residual + rest_scale * (w_bc * boundary + w_ic * initial)`` in ``model.parameters()`` order).
     ``res_scale`` / ``rest_scale`` are the shard weights of the data-parallel step (parallel.py)."""
-    calls, weights = _build_calls(pde, model, x, t, n_global, merge_value_rows=True)
+    calls, weights = _build_calls(pde, model, x, t, n_global, merge_value_rows=True,
+                                  merge_all_rows=x.shape[0] <= MERGE_ALL_MAX_POINTS)
     w_res, w_bc, w_ic, w_smooth, adaptive = weights
     if w_smooth:
         raise NotImplementedError("the fused step does not cover the smoothness regulariser; use compute_loss")

@@ -211,6 +211,10 @@ class PDETrainer:
             with torch.cuda.graph(graph):
                 g["out"] = self._fused_step(g["x"], g["t"])
             g["graph"] = graph
+            # the graph holds raw pointers into the engines' workspaces: keep those engines alive even if a later, larger
+            # batch makes the cache replace them
+            from . import engine as _engine
+            g["keep"] = list(_engine._CACHE.get(self.model, {}).values())
         else:
             g["x"].copy_(x)
             g["t"].copy_(t)

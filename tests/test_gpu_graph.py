@@ -30,7 +30,8 @@ def test_graph_replay_matches_eager_steps(pde_name, arch, layers, extra):
     dev = torch.device("cuda:0")
     m_a, m_b, t_a, t_b = _trainers(pde_name, arch, layers, extra, dev)
     g = torch.Generator().manual_seed(3)
-    shapes = [2025] * 7 + [777] * 4 + [2025] * 2          # a second shape captures its own graph; the first is kept
+    shapes = [2025] * 7 + [777] * 4 + [2025] * 2 + [5000] * 4 + [2025] * 2   # other shapes capture their own graphs (5000 regrows
+    # the engines: the first graph must keep its workspaces alive)
     for i, n in enumerate(shapes):
         x = torch.rand(n, 1, generator=g).to(dev)
         t = torch.rand(n, 1, generator=g).to(dev)
@@ -42,7 +43,7 @@ def test_graph_replay_matches_eager_steps(pde_name, arch, layers, extra):
         for k in ("residual", "boundary", "initial", "total"):
             a, b = float(l_a[k]), float(l_b[k])
             assert abs(a - b) <= 2e-5 * max(abs(a), 1e-12), (i, k, a, b)
-    assert sum(1 for v in t_b._graphs.values() if v["graph"] is not None) == 2
+    assert sum(1 for v in t_b._graphs.values() if v["graph"] is not None) == 3
     assert t_a.optimizer.step_count == t_b.optimizer.step_count == len(shapes)
     assert float(t_b.optimizer._dyn[0]) == len(shapes)
     # norm-wise: Adam turns the round-off of an (analytically) zero gradient element into +-lr steps, and the wgrad
