@@ -273,6 +273,29 @@ def _data_loss(pde, model) -> torch.Tensor:
     return pde._apply_loss_fn(u - obs["u"].to(dev))
 
 
+def _cached_rows(pde, key, build):
+    """Boundary / initial rows and targets that are pure functions of the PDE object (linspace grids, no RNG): built once
+    per (device, domain, boundary functions, initial condition, sizes) instead of ~20 tiny torch launches per step -- at the
+    reference's batch sizes those launches were a quarter of a step.  Nothing is stored while a CUDA graph is being captured
+    (the tensors would live in the graph's private pool)."""
+    cache = pde.__dict__.setdefault("_pinnk_rows_cache", {})
+    hit = cache.get(key)
+    if hit is not None:
+        return hit
+    val = build()
+    if not torch.cuda.is_current_stream_capturing():
+        if len(cache) >= 8:
+            cache.clear()
+        cache[key] = val
+    return val
+
+
+def _rows_key(pde, dev, *extra):
+    ic = getattr(pde.config, "initial_condition", None)
+    return (str(dev), repr(pde.domain), repr(pde.time_domain), tuple((k, id(f)) for k, f in pde.boundary_conditions.items()),
+            repr(ic), getattr(pde, "compat", "reference")) + tuple(extra)
+
+
 MERGE_ALL_MAX_POINTS = 32768    # fused step: up to this many collocation rows, ALL row sets go through one pass
 
 
@@ -316,25 +339,35 @@ def _build_calls(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_glob
         t_max = pde.config.time_domain[1]
         t_early = t_max * 0.01
         n_early = max(nb // 4, 1)
-        tb = torch.cat([torch.linspace(0, t_early, n_early, device=dev),
-                        torch.linspace(t_early, t_max, nb - n_early, device=dev)]).reshape(-1, 1)
+
+        def heat_time_rows():
+            return torch.cat([torch.linspace(0, t_early, n_early, device=dev),
+                              torch.linspace(t_early, t_max, nb - n_early, device=dev)]).reshape(-1, 1)
+
         if dim == 1:
             x_min, x_max = pde.config.domain[0]
-            pts = torch.cat([torch.cat([torch.full((nb, 1), x_min, device=dev), tb], dim=1),
-                             torch.cat([torch.full((nb, 1), x_max, device=dev), tb], dim=1)], dim=0)
+
+            def build_heat_rows():
+                tb = heat_time_rows()
+                pts = torch.cat([torch.cat([torch.full((nb, 1), x_min, device=dev), tb], dim=1),
+                                 torch.cat([torch.full((nb, 1), x_max, device=dev), tb], dim=1)], dim=0)
+                xb10 = (x_max - x_min) * 0.1
+                xi = torch.cat([torch.linspace(x_min, x_min + xb10, ni // 4, device=dev),
+                                torch.linspace(x_min + xb10, x_max - xb10, ni // 2, device=dev),
+                                torch.linspace(x_max - xb10, x_max, ni // 4, device=dev)]).reshape(-1, 1)
+                ti = torch.zeros_like(xi)
+                if "initial" in pde.boundary_conditions:
+                    target = pde.boundary_conditions["initial"](xi, ti)
+                else:
+                    target = torch.sin(pde.config.initial_condition.get("frequency", 2.0) * torch.pi * xi)
+                return pts, xi, ti, target.detach()
+
+            pts, xi, ti, target = _cached_rows(pde, _rows_key(pde, dev, "heat1d", nb, ni, repr(pde.config.domain),
+                                                              repr(pde.config.time_domain)), build_heat_rows)
             eng_b = get_engine(model, [((1.0, 0.0), 1)], 2 * nb, whole=True, program=program)
             calls.append((eng_b, pts, None, [
                 Segment(kind=L.PDE_VALUE, row_start=0, row_count=nb, component=1, weight=1.0 / nb, pair_offset=nb, **mk),
                 Segment(kind=L.PDE_DX, row_start=0, row_count=nb, component=1, weight=1.0 / nb, pair_offset=nb, **mk)]))
-            xb10 = (x_max - x_min) * 0.1
-            xi = torch.cat([torch.linspace(x_min, x_min + xb10, ni // 4, device=dev),
-                            torch.linspace(x_min + xb10, x_max - xb10, ni // 2, device=dev),
-                            torch.linspace(x_max - xb10, x_max, ni // 4, device=dev)]).reshape(-1, 1)
-            ti = torch.zeros_like(xi)
-            if "initial" in pde.boundary_conditions:
-                target = pde.boundary_conditions["initial"](xi, ti)
-            else:
-                target = torch.sin(pde.config.initial_condition.get("frequency", 2.0) * torch.pi * xi)
         else:
             per_axis = max(nb // (2 * dim), 1)
             lo_pts, hi_pts = [], []
@@ -371,37 +404,40 @@ def _build_calls(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_glob
             Segment(kind=L.PDE_VALUE, row_start=0, row_count=n_i, component=2, weight=1.0 / max(n_i, 1),
                     target=target.detach().to(torch.float32).reshape(-1).contiguous(), **mk)]))
     else:
-        # built on the device (no host copy: the call may be inside a CUDA-graph capture); same float32 values as
-        # torch.tensor([x_min, x_max])
-        xb = torch.cat([torch.full((1, 1), float(dom[0][0]), dtype=torch.float32, device=dev),
-                        torch.full((1, 1), float(dom[0][1]), dtype=torch.float32, device=dev)], dim=0)
-        tb = torch.linspace(td[0], td[1], 100, device=dev).reshape(-1, 1)
-        xb = xb.repeat_interleave(len(tb), dim=0)
-        tb = tb.repeat(len(xb) // len(tb), 1)
-        nbp = xb.shape[0]
-        segs = []
-        for fn in pde.boundary_conditions.values():
-            tgt = fn(xb, tb).detach().to(torch.float32).reshape(-1).contiguous()
-            segs.append(Segment(kind=L.PDE_VALUE, row_start=0, row_count=nbp, component=1, weight=1.0 / nbp,
-                                target=tgt, **mk))
-        xi = torch.linspace(dom[0][0], dom[0][1], 100, device=dev).reshape(-1, 1)
-        ti = torch.zeros_like(xi)
-        if "initial" in pde.boundary_conditions:
-            target = pde.boundary_conditions["initial"](xi, ti)
-        else:
-            ic = pde.config.initial_condition
-            if ic.get("type", "sine") == "sine" and "amplitude" in ic and "frequency" in ic:
-                target = ic["amplitude"] * torch.sin(ic["frequency"] * torch.pi * xi)
+        def build_rows():
+            # built on the device (no host copy: the call may be inside a CUDA-graph capture); same float32 values as
+            # torch.tensor([x_min, x_max])
+            xb = torch.cat([torch.full((1, 1), float(dom[0][0]), dtype=torch.float32, device=dev),
+                            torch.full((1, 1), float(dom[0][1]), dtype=torch.float32, device=dev)], dim=0)
+            tb = torch.linspace(td[0], td[1], 100, device=dev).reshape(-1, 1)
+            xb = xb.repeat_interleave(len(tb), dim=0)
+            tb = tb.repeat(len(xb) // len(tb), 1)
+            bc_targets = [fn(xb, tb).detach().to(torch.float32).reshape(-1).contiguous()
+                          for fn in pde.boundary_conditions.values()]
+            xi = torch.linspace(dom[0][0], dom[0][1], 100, device=dev).reshape(-1, 1)
+            ti = torch.zeros_like(xi)
+            if "initial" in pde.boundary_conditions:
+                target = pde.boundary_conditions["initial"](xi, ti)
             else:
-                target = pde._create_boundary_condition("initial", ic)(xi, ti)
-        ic_target = target.detach().to(torch.float32).reshape(-1).contiguous()
+                ic = pde.config.initial_condition
+                if ic.get("type", "sine") == "sine" and "amplitude" in ic and "frequency" in ic:
+                    target = ic["amplitude"] * torch.sin(ic["frequency"] * torch.pi * xi)
+                else:
+                    target = pde._create_boundary_condition("initial", ic)(xi, ti)
+            ic_target = target.detach().to(torch.float32).reshape(-1).contiguous()
+            return xb, tb, bc_targets, xi, ti, ic_target, torch.cat([xb, xi], dim=0), torch.cat([tb, ti], dim=0)
+
+        xb, tb, bc_targets, xi, ti, ic_target, x_all, t_all = _cached_rows(pde, _rows_key(pde, dev, "1d"), build_rows)
+        nbp = xb.shape[0]
+        segs = [Segment(kind=L.PDE_VALUE, row_start=0, row_count=nbp, component=1, weight=1.0 / nbp, target=tgt, **mk)
+                for tgt in bc_targets]
         if merge_value_rows and segs:
             # boundary and initial rows are both value-only rows (one jet column): ONE pass over [boundary rows; initial
             # rows] with one segment per error functional instead of two passes of ~30 tiny launches each.  Only valid
             # when all components accumulate into one gradient buffer (the fused trainer step).
             segs.append(Segment(kind=L.PDE_VALUE, row_start=nbp, row_count=100, component=2, weight=0.01,
                                 target=ic_target, **mk))
-            calls.append((get_engine(model, [], nbp + 100, program=program), torch.cat([xb, xi], dim=0), torch.cat([tb, ti], dim=0), segs))
+            calls.append((get_engine(model, [], nbp + 100, program=program), x_all, t_all, segs))
         else:
             if segs:
                 calls.append((get_engine(model, [], nbp, program=program), xb, tb, segs))
