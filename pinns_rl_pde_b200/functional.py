@@ -195,6 +195,40 @@ class _LossFn(torch.autograd.Function):
         return (None, None, None, *ctx.program.split_flat(flat))
 
 
+class _LazyLossFn(torch.autograd.Function):
+    """Component losses [n_components] of ONE merged call (all row sets behind each other, small batches): the forward
+    is a forward-only sweep that leaves its stash in the workspace; backward(g) is ONE reverse sweep whose seeds carry
+    g[component], so whatever weights autograd applies to the components (fixed, adaptive, one component at a time with
+    retain_graph) the gradient is exact.  A second backward, or one after something else used the engine, recomputes the
+    forward first.  ~27 launches per loss + backward instead of ~70 for three eager per-component passes."""
+
+    @staticmethod
+    def forward(ctx, call, n_components, program, *params):
+        engine, x, t, segments = call
+        want_grad = any(ctx.needs_input_grad[3:])
+        sums = torch.zeros(n_components, dtype=torch.float64, device=x.device)
+        engine.loss_step(x, t, segments, n_components, False, None, None, sums, keep_stash=want_grad)
+        ctx.call, ctx.n, ctx.program = call, n_components, program
+        ctx.token = engine._stash_token if want_grad else None
+        ctx.versions = [p._version for p in params]
+        ctx.params = params
+        return sums.to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        engine, x, t, segments = ctx.call
+        if [p._version for p in ctx.params] != ctx.versions:
+            raise RuntimeError("a model parameter was modified in place between compute_loss and backward")
+        scale = [float(v) for v in g.detach().to(torch.float32).reshape(-1).tolist()]
+        token = ctx.token
+        if token is not None and (token[1:4] != (x.data_ptr(), engine._ptr(t), x.shape[0])
+                                  or token[4] != engine.stash_signature()):
+            token = None
+        ctx.token = None                    # the reverse sweep consumes the stash
+        _, flat = engine.loss_step(x, t, segments, ctx.n, True, scale, None, None, reuse_token=token)
+        return (None, None, None, *ctx.program.split_flat(flat))
+
+
 # ------------------------------------------------------------------ public functions
 def jets(model: nn.Module, xt: torch.Tensor, directions: Sequence) -> torch.Tensor:
     """Differentiable (w.r.t. parameters) output jets of the network: column 0 = u, then the
@@ -458,17 +492,31 @@ def _build_calls(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_glob
             segs.extend(dataclasses.replace(sg, row_start=sg.row_start + off) for sg in ss)
             off += pts.shape[0]
         eng = get_engine(model, dirs, off, whole=True, program=program)
-        calls = [(eng, torch.cat(rows, dim=0), None, segs)]
+        if eng.chunk >= off:                       # paired rows (periodic BC) must share a chunk with their partners
+            calls = [(eng, torch.cat(rows, dim=0), None, segs)]
     return calls, _weights(pde, heat)
+
+
+def _eager_loss_grad() -> bool:
+    """PINNK_EAGER_LOSS_GRAD=1: per-component gradients computed inside compute_loss at every batch size (A/B)."""
+    import os
+    return os.environ.get("PINNK_EAGER_LOSS_GRAD", "0") == "1"
 
 
 def loss_components(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_global: Optional[int] = None):
     """The three physics components [residual, boundary, initial] as one differentiable tensor, plus the
     weights the reference would combine them with.  ``n_global``: number of collocation rows of the whole
     (possibly sharded) batch -- the reference derives default BC/IC point counts from it."""
-    calls, weights = _build_calls(pde, model, x, t, n_global)
+    lazy = x.shape[0] <= MERGE_ALL_MAX_POINTS and not _eager_loss_grad()
+    calls, weights = _build_calls(pde, model, x, t, n_global, merge_value_rows=lazy, merge_all_rows=lazy)
     program = calls[0][0].program
-    comp = _LossFn.apply(calls, 3, program, *program.grad_params)
+    if lazy and len(calls) == 1:
+        comp = _LazyLossFn.apply(calls[0], 3, program, *program.grad_params)
+    elif lazy:                                    # could not merge (one chunk does not hold all rows): separate row sets
+        calls, weights = _build_calls(pde, model, x, t, n_global)
+        comp = _LossFn.apply(calls, 3, program, *program.grad_params)
+    else:
+        comp = _LossFn.apply(calls, 3, program, *program.grad_params)
     return comp, weights
 
 
