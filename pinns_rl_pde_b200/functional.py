@@ -317,7 +317,7 @@ def _cached_rows(pde, key, build):
     if hit is not None:
         return hit
     val = build()
-    if not torch.cuda.is_current_stream_capturing():
+    if not (torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()):
         if len(cache) >= 8:
             cache.clear()
         cache[key] = val

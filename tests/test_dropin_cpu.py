@@ -48,3 +48,42 @@ def test_patch_and_unpatch_reference():
         assert r.shape == (4, 1)
     finally:
         sys.path.remove(REF)
+
+
+def test_cached_rows_are_keyed_on_what_they_depend_on():
+    """functional._cached_rows / _rows_key (host logic of the small-batch path): boundary rows are rebuilt when the boundary
+    functions, the initial condition, the domain or the requested sizes change, and reused otherwise."""
+    import types
+    from pinns_rl_pde_b200 import functional as F
+    calls = []
+
+    def build():
+        calls.append(1)
+        return torch.zeros(3)
+
+    bc = {"dirichlet": lambda x, t: x * 0}
+    pde = types.SimpleNamespace(domain=[[-1.0, 1.0]], time_domain=[0.0, 1.0], boundary_conditions=bc, compat="reference",
+                                config=types.SimpleNamespace(initial_condition={"type": "sine", "amplitude": 1.0, "frequency": 1.0}))
+    dev = torch.device("cpu")
+    a = F._cached_rows(pde, F._rows_key(pde, dev, "1d"), build)
+    b = F._cached_rows(pde, F._rows_key(pde, dev, "1d"), build)
+    assert a is b and len(calls) == 1
+    pde.config.initial_condition["amplitude"] = 2.0                       # mutated in place: new key
+    F._cached_rows(pde, F._rows_key(pde, dev, "1d"), build)
+    assert len(calls) == 2
+    pde.boundary_conditions["dirichlet"] = lambda x, t: x * 0 + 1         # replaced function: new key
+    F._cached_rows(pde, F._rows_key(pde, dev, "1d"), build)
+    assert len(calls) == 3
+    F._cached_rows(pde, F._rows_key(pde, dev, "heat1d", 50, 100), build)  # sizes are part of the key
+    F._cached_rows(pde, F._rows_key(pde, dev, "heat1d", 60, 100), build)
+    assert len(calls) == 5
+    for i in range(12):                                                   # bounded
+        F._cached_rows(pde, F._rows_key(pde, dev, "n", i), build)
+    assert len(pde._pinnk_rows_cache) <= 8
+
+
+def test_graph_trainer_needs_the_fused_step():
+    import pinns_rl_pde_b200 as pk
+    model = torch.nn.Linear(2, 1)
+    with pytest.raises(ValueError):
+        pk.PDETrainer(model, object.__new__(pk.BurgersEquation), config=pk.TrainingConfig(), device=torch.device("cpu"), graph=True)
