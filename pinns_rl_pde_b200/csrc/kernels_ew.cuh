@@ -175,6 +175,142 @@ __global__ void act_bwd_kernel(const float* __restrict__ Z, const float* __restr
   else G[base] = (yb[0] * w[0] - wb0 * y[0]) * omega;
 }
 
+// The same two kernels with PPT points per thread (same feature, consecutive points): every load of a phase is issued for
+// all PPT points before the recurrences run.  A/B variant (PINNK_ACT_PPT=2), parity-green but slower than one point per
+// thread on a B200 (64 - 70 registers against 40 - 48: the occupancy lost outweighs the batched loads), so not the default.
+// A ragged last group clamps its loads to the group's first point and skips the stores.
+template <int ACT, int MAXK, int PPT>
+__global__ void act_fwd_multi_kernel(const float* __restrict__ Z, const float* __restrict__ S, float* __restrict__ Y,
+                                     int64_t n, int width, JetSpec js, float omega) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t groups = (n + PPT - 1) / PPT;
+  if (idx >= groups * width) return;
+  const int64_t q = idx / width;
+  const int f = (int)(idx - q * width);
+  int64_t base[PPT];
+  bool ok[PPT];
+#pragma unroll
+  for (int u = 0; u < PPT; ++u) {
+    const int64_t p = q * PPT + u;
+    ok[u] = p < n;
+    base[u] = (ok[u] ? p : q * PPT) * js.ncols * width + f;
+  }
+  float z[PPT][MAXK + 1], y[PPT][MAXK + 1], w[PPT][MAXK + 1];
+#pragma unroll
+  for (int u = 0; u < PPT; ++u) z[u][0] = Z[base[u]] + (S ? S[base[u]] : 0.f);
+#pragma unroll
+  for (int u = 0; u < PPT; ++u) {
+    if (ACT == 1) {
+      y[u][0] = tanhf(z[u][0]);
+      w[u][0] = 1.f - y[u][0] * y[u][0];
+    } else {
+      z[u][0] *= omega;
+      sincosf(z[u][0], &y[u][0], &w[u][0]);
+    }
+    if (ok[u]) Y[base[u]] = y[u][0];
+  }
+  for (int d = 0; d < js.ndirs; ++d) {
+    const int K = js.order[d];
+    const int64_t c0 = (int64_t)js.col0[d] * width;
+#pragma unroll
+    for (int u = 0; u < PPT; ++u)
+#pragma unroll
+      for (int k = 1; k <= MAXK; ++k)
+        if (k <= K) {
+          const int64_t o = base[u] + c0 + (int64_t)(k - 1) * width;
+          z[u][k] = Z[o] + (S ? S[o] : 0.f);
+          if (ACT == 2) z[u][k] *= omega;
+        }
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) {
+      if (ACT == 1) tanh_dir_fwd<MAXK, float>(K, z[u], y[u], w[u]);
+      else sincos_dir_fwd<MAXK, float>(K, z[u], y[u], w[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < PPT; ++u)
+#pragma unroll
+      for (int k = 1; k <= MAXK; ++k)
+        if (k <= K && ok[u]) Y[base[u] + c0 + (int64_t)(k - 1) * width] = y[u][k];
+  }
+}
+
+template <int ACT, int MAXK, int PPT>
+__global__ void act_bwd_multi_kernel(const float* __restrict__ Z, const float* __restrict__ S, float* __restrict__ G,
+                                     int64_t n, int width, JetSpec js, float omega) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t groups = (n + PPT - 1) / PPT;
+  if (idx >= groups * width) return;
+  const int64_t q = idx / width;
+  const int f = (int)(idx - q * width);
+  int64_t base[PPT];
+  bool ok[PPT];
+#pragma unroll
+  for (int u = 0; u < PPT; ++u) {
+    const int64_t p = q * PPT + u;
+    ok[u] = p < n;
+    base[u] = (ok[u] ? p : q * PPT) * js.ncols * width + f;
+  }
+  float z[PPT][MAXK + 1], y[PPT][MAXK + 1], w[PPT][MAXK + 1], yb[PPT][MAXK + 1], zb[PPT][MAXK + 1], wb[MAXK + 1];
+  float wb0[PPT];
+#pragma unroll
+  for (int u = 0; u < PPT; ++u) {
+    z[u][0] = Z[base[u]] + (S ? S[base[u]] : 0.f);
+    yb[u][0] = G[base[u]];
+    wb0[u] = 0.f;
+  }
+#pragma unroll
+  for (int u = 0; u < PPT; ++u) {
+    if (ACT == 1) {
+      y[u][0] = tanhf(z[u][0]);
+      w[u][0] = 1.f - y[u][0] * y[u][0];
+    } else {
+      z[u][0] *= omega;
+      sincosf(z[u][0], &y[u][0], &w[u][0]);
+    }
+  }
+  for (int d = 0; d < js.ndirs; ++d) {
+    const int K = js.order[d];
+    const int64_t c0 = (int64_t)js.col0[d] * width;
+#pragma unroll
+    for (int u = 0; u < PPT; ++u)
+#pragma unroll
+      for (int k = 1; k <= MAXK; ++k)
+        if (k <= K) {
+          const int64_t o = base[u] + c0 + (int64_t)(k - 1) * width;
+          z[u][k] = Z[o] + (S ? S[o] : 0.f);
+          if (ACT == 2) z[u][k] *= omega;
+          yb[u][k] = G[o];
+        } else {
+          yb[u][k] = 0.f;
+        }
+#pragma unroll
+    for (int u = 0; u < PPT; ++u) {
+      if (ACT == 1) {
+        tanh_dir_fwd<MAXK, float>(K, z[u], y[u], w[u]);
+        tanh_dir_bwd<MAXK, float>(K, z[u], y[u], w[u], yb[u], zb[u], wb0[u]);
+      } else {
+#pragma unroll
+        for (int k = 0; k <= MAXK; ++k) wb[k] = 0.f;
+        wb[0] = wb0[u];
+        sincos_dir_fwd<MAXK, float>(K, z[u], y[u], w[u]);
+        sincos_dir_bwd<MAXK, float>(K, z[u], y[u], w[u], yb[u], wb, zb[u]);
+        wb0[u] = wb[0];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PPT; ++u)
+#pragma unroll
+      for (int k = 1; k <= MAXK; ++k)
+        if (k <= K && ok[u]) G[base[u] + c0 + (int64_t)(k - 1) * width] = (ACT == 2) ? zb[u][k] * omega : zb[u][k];
+  }
+#pragma unroll
+  for (int u = 0; u < PPT; ++u) {
+    if (!ok[u]) continue;
+    if (ACT == 1) G[base[u]] = tanh_finish_bwd<float>(y[u][0], w[u][0], yb[u][0], wb0[u]);
+    else G[base[u]] = (yb[u][0] * w[u][0] - wb0[u] * y[u][0]) * omega;
+  }
+}
+
 // Fourier features: Y[..., 0:m] = sin(Z), Y[..., m:2m] = cos(Z)   (fourier.py:12-16); no adjoint (B is a buffer).
 template <int MAXK>
 __global__ void sincos_fwd_kernel(const float* __restrict__ Z, float* __restrict__ Y, int64_t n, int m, JetSpec js) {

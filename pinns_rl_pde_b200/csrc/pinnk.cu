@@ -409,6 +409,15 @@ static bool dispatch_edge_jets(int k0, int k1, F&& f) {
 #undef PK_EDGE_CASE
   return false;
 }
+// PINNK_ACT_PPT=2: stand-alone activation kernels with two points per thread.  Measured and NOT the default: the extra
+// registers cost more occupancy than the batched loads gain (C3 act_fwd 18.4 -> 20.9 ms, C4-math act_bwd 5.6 -> 7.5 ms;
+// profiles/r01m_act_ppt_ab.log) -- these kernels are not latency-bound per thread.
+static bool act_ppt2_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("PINNK_ACT_PPT"); v = (e && e[0] == '2') ? 1 : 0; }
+  return v == 1;
+}
+
 static bool edge_fast_enabled() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("PINNK_DISABLE_EDGE_FAST"); v = (e && e[0] == '1') ? 0 : 1; }
@@ -563,7 +572,13 @@ static int forward_chunk(const ChunkCtx& c, bool keep_stash = true) {
         ProfScope ps(PC_ACT_FWD, c.st);
         const float* S = (r.skip_src >= 0) ? c.stash(r.skip_src) : nullptr;
         const unsigned blocks = blocks_for(c.n * o.in_dim, threads);
-        if (o.act == PINNK_ACT_TANH)
+        if (act_ppt2_enabled()) {
+          const unsigned b2 = blocks_for(((c.n + 1) / 2) * o.in_dim, threads);
+          if (o.act == PINNK_ACT_TANH)
+            act_fwd_multi_kernel<1, MAXK, 2><<<b2, threads, 0, c.st>>>(in, S, c.stash(i), c.n, o.in_dim, js, 1.f);
+          else
+            act_fwd_multi_kernel<2, MAXK, 2><<<b2, threads, 0, c.st>>>(in, S, c.stash(i), c.n, o.in_dim, js, o.scale);
+        } else if (o.act == PINNK_ACT_TANH)
           act_fwd_kernel<1, MAXK><<<blocks, threads, 0, c.st>>>(in, S, c.stash(i), c.n, o.in_dim, js, 1.f);
         else
           act_fwd_kernel<2, MAXK><<<blocks, threads, 0, c.st>>>(in, S, c.stash(i), c.n, o.in_dim, js, o.scale);
@@ -724,7 +739,13 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad, bool last_done = 
         const unsigned blocks = blocks_for(c.n * o.in_dim, threads);
         if (z_elided(pl, r.in_op)) return fail(PINNK_E_INVALID, "backward: generic activation adjoint reached for an elided pre-activation stash");
         ProfScope ps(PC_ACT_BWD, c.st);
-        if (o.act == PINNK_ACT_TANH)
+        if (act_ppt2_enabled()) {
+          const unsigned b2 = blocks_for(((c.n + 1) / 2) * o.in_dim, threads);
+          if (o.act == PINNK_ACT_TANH)
+            act_bwd_multi_kernel<1, MAXK, 2><<<b2, threads, 0, c.st>>>(in, S, c.adj(cur), c.n, o.in_dim, js, 1.f);
+          else
+            act_bwd_multi_kernel<2, MAXK, 2><<<b2, threads, 0, c.st>>>(in, S, c.adj(cur), c.n, o.in_dim, js, o.scale);
+        } else if (o.act == PINNK_ACT_TANH)
           act_bwd_kernel<1, MAXK><<<blocks, threads, 0, c.st>>>(in, S, c.adj(cur), c.n, o.in_dim, js, 1.f);
         else
           act_bwd_kernel<2, MAXK><<<blocks, threads, 0, c.st>>>(in, S, c.adj(cur), c.n, o.in_dim, js, o.scale);
