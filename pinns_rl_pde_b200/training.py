@@ -20,6 +20,16 @@ from . import parallel
 
 
 @dataclass
+class LBFGSConfig:
+    """config/__init__.py:47-63: settings handed to torch.optim.LBFGS."""
+    history_size: int = 50
+    max_iter: int = 20
+    line_search_fn: Optional[str] = "strong_wolfe"
+    tolerance_grad: float = 1e-7
+    tolerance_change: float = 1e-9
+
+
+@dataclass
 class TrainingConfig:
     """The fields of pinnrl.config.TrainingConfig the step reads (config/__init__.py:90-169)."""
     num_epochs: int = 100
@@ -37,8 +47,14 @@ class TrainingConfig:
     mode: str = "forward"
     loss_function: str = "mse"
     huber_delta: float = 1.0
+    optimizer: str = "adam"            # "adam" | "lbfgs" (config/__init__.py:123; the adam_lbfgs hand-over: switch_to_lbfgs())
+    lbfgs: Optional[LBFGSConfig] = None
 
     def __post_init__(self):
+        if self.lbfgs is None:
+            self.lbfgs = LBFGSConfig()
+        if self.optimizer not in ("adam", "lbfgs"):
+            raise ValueError(f"unknown optimizer {self.optimizer!r}: choose 'adam' or 'lbfgs'")
         if self.loss_weights is None:
             self.loss_weights = {"residual": 1.0, "boundary": 1.0, "initial": 1.0}
         self.loss_weights.setdefault("data", 1.0)
@@ -134,7 +150,12 @@ class PDETrainer:
             raise ValueError("PDETrainer(graph=True) captures the fused step: pass fused=True")
         self._graphs: Dict[tuple, dict] = {}
         lr, wd = oc.get("learning_rate", self.training.learning_rate), oc.get("weight_decay", self.training.weight_decay)
-        if self.fused:
+        self._is_lbfgs = self.training.optimizer == "lbfgs"
+        if self._is_lbfgs and self.fused:
+            raise ValueError("fused=True is the Adam step; L-BFGS drives compute_loss + backward through its closure")
+        if self._is_lbfgs:
+            self.optimizer = self._build_lbfgs(lr)
+        elif self.fused:
             # whole step in libpinnk: loss + weighted gradient in one pass per row set, then clip + Adam in two launches
             self.optimizer = FusedAdam(model.parameters(), lr=lr, weight_decay=wd, max_norm=self.training.gradient_clipping,
                                        capturable=self.graph)
@@ -143,7 +164,7 @@ class PDETrainer:
             self.optimizer = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)
         self.scheduler = None
         self._epoch = 0
-        if self.training.scheduler == "cosine" and not self.fused:
+        if self.training.scheduler == "cosine" and not self.fused and not self._is_lbfgs:
             self.scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(
                 self.optimizer, T_max=self.training.num_epochs, eta_min=self.training.min_lr)
         self.history: Dict[str, List[float]] = {"train_loss": [], "residual_loss": [], "boundary_loss": [],
@@ -157,6 +178,8 @@ class PDETrainer:
             n_global = x.shape[0]
             lo, hi = parallel.shard_bounds(n_global)
             x, t = x[lo:hi], t[lo:hi]
+        if self._is_lbfgs:
+            return self._lbfgs_step(x, t)
         if self.fused:
             if self.graph and parallel.world_size() == 1:
                 return self._graph_step(x, t)
@@ -187,6 +210,37 @@ class PDETrainer:
         zero = torch.zeros((), device=flat.device)
         return {"residual": sums[0], "boundary": sums[1], "initial": sums[2], "smoothness": zero, "data": zero.clone(),
                 "total": w_res * sums[0] + w_bc * sums[1] + w_ic * sums[2]}
+
+    def _build_lbfgs(self, lr):
+        """trainer.py:299-309."""
+        cfg = self.training.lbfgs
+        return torch.optim.LBFGS(self.model.parameters(), lr=lr, history_size=cfg.history_size, max_iter=cfg.max_iter,
+                                 line_search_fn=cfg.line_search_fn, tolerance_grad=cfg.tolerance_grad,
+                                 tolerance_change=cfg.tolerance_change)
+
+    def switch_to_lbfgs(self):
+        """trainer.py:366-371: second phase of ``adam_lbfgs`` (the fused / graph Adam step hands over to the closure route)."""
+        self.optimizer = self._build_lbfgs(self.training.learning_rate)
+        self._is_lbfgs, self.fused, self.graph, self.scheduler = True, False, False, None
+
+    def _lbfgs_step(self, x, t):
+        """trainer.py:373-389: one L-BFGS step; the closure re-evaluates compute_loss + backward on libpinnk as often as the
+        line search asks (up to ``max_iter`` times, ~1.25 evaluations per iteration with strong Wolfe)."""
+        if parallel.world_size() > 1:
+            raise NotImplementedError("L-BFGS is a full-batch single-process optimiser in the reference (trainer.py:456-462)")
+        captured: Dict[str, Dict[str, torch.Tensor]] = {}
+
+        def closure():
+            self.optimizer.zero_grad()
+            losses = self.pde.compute_loss(self.model, x, t)
+            losses["total"].backward()
+            captured["losses"] = losses
+            return losses["total"]
+
+        self.optimizer.step(closure)
+        if "losses" not in captured:               # no closure call happened (tolerance already met)
+            captured["losses"] = self.pde.compute_loss(self.model, x, t)
+        return captured["losses"]
 
     GRAPH_WARMUP = 2
 
@@ -288,6 +342,8 @@ class PDETrainer:
 
     def train(self, num_epochs: int, batch_size: int, num_points: int, experiment_dir: str = None):
         self.model.train()
+        if self._is_lbfgs:
+            batch_size = num_points                # trainer.py:456-462: L-BFGS needs the deterministic full-batch loss
         for _ in range(num_epochs):
             epoch = []
             for _ in range(num_points // batch_size):

@@ -76,3 +76,54 @@ def test_backward_after_other_use_of_the_engine_and_inplace_guard():
         next(model.parameters()).mul_(1.0)
     with pytest.raises(RuntimeError):
         losses["total"].backward()
+
+
+def test_lbfgs_closure_step_follows_the_reference_algorithm():
+    """trainer.py:373-389 (_lbfgs_step): torch.optim.LBFGS re-enters compute_loss + backward through its closure.  Same
+    start, same rows, same settings as the oracle (reference algorithm, fp64, CPU): the loss goes down and the two
+    trajectories stay together over two steps of five strong-Wolfe iterations."""
+    import math
+    import pinns_rl_pde_b200 as pk
+    from oracle import ref_port
+    from helpers import PDES
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    model = pk.make_model("feedforward", 2, 128, 3, dev)
+    pde = product_pde("burgers", dev)
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand(600, 1, generator=g) * 2 - 1
+    t = torch.rand(600, 1, generator=g)
+    cfg = pk.TrainingConfig(optimizer="lbfgs", learning_rate=1.0, lbfgs=pk.LBFGSConfig(history_size=10, max_iter=5))
+    trainer = pk.PDETrainer(model, pde, config=cfg, device=dev)
+    # oracle
+    om = ref_port.PINNModel("feedforward", 2, 128, 3)
+    om.load_state_dict({k: v.detach().cpu() for k, v in model.state_dict().items()})
+    om = om.double()
+    s = PDES["burgers"]
+    fns = ref_port.boundary_condition_fns("burgers", s["bcs"], s["ic"], [tuple(d) for d in s["domain"]], s["params"])
+    opt = torch.optim.LBFGS(om.parameters(), lr=1.0, history_size=10, max_iter=5, line_search_fn="strong_wolfe",
+                            tolerance_grad=1e-7, tolerance_change=1e-9)
+    xd, td = x.double(), t.double()
+
+    def oracle_total():
+        r = ref_port.burgers_residual(om, xd, td, nu=s["params"]["nu"])
+        return ref_port.base_compute_loss(om, r, [tuple(d) for d in s["domain"]], tuple(s["time"]), fns)["total"]
+
+    def closure():
+        opt.zero_grad()
+        total = oracle_total()
+        total.backward()
+        return total
+
+    start = float(pde.compute_loss(model, x.to(dev), t.to(dev))["total"])
+    assert abs(start - float(oracle_total())) <= 1e-5 * abs(start)
+    got, want = [], []
+    for _ in range(2):
+        trainer.train_step(x.to(dev), t.to(dev))
+        with torch.no_grad():
+            got.append(float(pde.compute_loss(model, x.to(dev), t.to(dev))["total"]))
+        opt.step(closure)
+        want.append(float(oracle_total()))
+    assert got[0] < start and got[1] < got[0], (start, got)
+    for a, b in zip(got, want):
+        assert abs(a - b) <= 5e-3 * abs(b), (start, got, want)
