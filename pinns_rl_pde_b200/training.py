@@ -1,8 +1,9 @@
 """Host-side mirror of the inner training step of ``pinnrl.training.trainer.PDETrainer``
-(trainer.py:292-332 optimiser/scheduler set-up, :539-698 the step).  Plots, dashboards, metadata
-files, adaptive loss re-weighting and L-BFGS are outside the hot path and not mirrored; for those,
-patch the reference (``patch_reference``) and use its own trainer.
+(trainer.py:292-332 optimiser/scheduler set-up, :539-698 the step, :373-389 the L-BFGS closure step, :140-162 validation
+loss, :171-279 live snapshot).  Plots, dashboards, metadata files and adaptive loss re-weighting are outside the hot path
+and not mirrored; for those, patch the reference (``patch_reference``) and use its own trainer.
 
+``fused=True`` runs the whole Adam step inside libpinnk; ``graph=True`` replays it as a CUDA graph per batch shape.
 With ``world_size > 1`` (one process per GPU, torch.distributed/NCCL) collocation rows are sharded
 across ranks and the flat gradient + loss sums are all-reduced once per step (parallel.py).
 """
