@@ -609,3 +609,39 @@ def dqn_forward_port(state: Dict[str, torch.Tensor], x: torch.Tensor, dropout: f
         h = Fn.dropout(torch.relu(h), dropout, training)
         i += 1
     return Fn.linear(h, state[f"layers.{i}.weight"], state.get(f"layers.{i}.bias"))
+
+
+# ------------------------------------------------------------------ adaptive loss re-weighting (trainer.py:580-634)
+class AdaptiveLossWeightsPort:
+    """components/adaptive_weights.py:6-134 restated: LRW (weights inversely proportional to the running gradient norms)
+    and RBW (weights proportional to the running losses, smoothed once more with the previous weights).  The first call
+    of either strategy returns the initial weights and only seeds the running average.  Pinned bit-identical to the
+    unmodified reference on random sequences by tests/golden/make_golden.py (case x_adaptive_weights)."""
+
+    def __init__(self, strategy="rbw", alpha=0.9, eps=1e-5, initial_weights=None):
+        self.strategy, self.alpha, self.eps = strategy.lower(), alpha, float(eps)
+        self.initial = None if initial_weights is None else torch.tensor(initial_weights)
+        self.weights = self.running = self.prev = None
+
+    def update(self, losses=None, gradients=None):
+        if self.strategy == "lrw" and gradients is not None:
+            v = gradients
+        elif self.strategy == "rbw" and losses is not None:
+            v = losses
+        else:
+            raise ValueError(f"Invalid combination of strategy ({self.strategy}) and inputs")
+        if self.running is None:
+            self.running = v
+            self.weights = self.initial.to(v.device) if self.initial is not None else torch.ones_like(v)
+            return self.weights
+        self.running = self.alpha * self.running + (1 - self.alpha) * v
+        eps = torch.tensor(self.eps, device=v.device)
+        if self.strategy == "lrw":
+            inv = 1.0 / (self.running + eps)
+            self.weights = inv / torch.sum(inv)
+            return self.weights
+        self.weights = self.running / (self.running.sum() + eps)
+        if self.prev is not None:
+            self.weights = self.alpha * self.prev + (1 - self.alpha) * self.weights
+        self.prev = self.weights.clone()
+        return self.weights

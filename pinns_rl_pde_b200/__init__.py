@@ -11,7 +11,7 @@ from .neural_networks import (Config, FeedForwardNetwork, FourierNetwork, ModelC
                               SIREN, make_model)
 from .pdes import (AllenCahnEquation, BlackScholesEquation, BurgersEquation, CahnHilliardEquation, ConvectionEquation,
                    HeatEquation, KdVEquation, PDEBase, PDEConfig, PendulumEquation, WaveEquation, create_pde)
-from .training import LBFGSConfig, PDETrainer, TrainingConfig
+from .training import AdaptiveLossWeights, AdaptiveWeightsConfig, LBFGSConfig, PDETrainer, TrainingConfig
 from .dropin import patch_reference
 from . import rl
 from .rl import DQNNetwork, dqn_forward
@@ -19,5 +19,5 @@ from .rl import DQNNetwork, dqn_forward
 __all__ = ["compute_loss", "compute_residual", "jets", "loss_and_flat_grad", "model_forward", "score_residual",
            "Config", "ModelConfig", "PINNModel", "FeedForwardNetwork", "ResNet", "SIREN", "FourierNetwork",
            "make_model", "PDEConfig", "PDEBase", "HeatEquation", "BurgersEquation", "KdVEquation",
-           "AllenCahnEquation", "CahnHilliardEquation", "WaveEquation", "ConvectionEquation", "BlackScholesEquation", "PendulumEquation", "create_pde", "PDETrainer", "TrainingConfig", "LBFGSConfig",
+           "AllenCahnEquation", "CahnHilliardEquation", "WaveEquation", "ConvectionEquation", "BlackScholesEquation", "PendulumEquation", "create_pde", "PDETrainer", "TrainingConfig", "LBFGSConfig", "AdaptiveWeightsConfig", "AdaptiveLossWeights",
            "patch_reference", "rl", "DQNNetwork", "dqn_forward"]

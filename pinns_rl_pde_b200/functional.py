@@ -497,6 +497,24 @@ def _build_calls(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_glob
     return calls, _weights(pde, heat)
 
 
+def loss_components_and_grads(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_global: Optional[int] = None):
+    """Component losses [3] (residual, boundary, initial) AND the gradient of each one as a row of ``G [3, P]``
+    (``model.parameters()`` order), no autograd graph: what adaptive re-weighting needs (trainer.py:580-634).  The reference
+    gets the per-component gradient norms of its LRW strategy from three extra ``backward(retain_graph=True)`` passes and then
+    differentiates the weighted total a fourth time; here one reverse pass per row set fills ``G`` and any weighting is
+    ``w @ G``."""
+    calls, weights = _build_calls(pde, model, x, t, n_global)
+    program = calls[0][0].program
+    dev = calls[0][1].device
+    sums = torch.zeros(3, dtype=torch.float64, device=dev)
+    G = torch.zeros(3, program.grad_floats, dtype=torch.float32, device=dev)
+    for engine, xx, tt, segments in calls:
+        comp = segments[0].component
+        assert all(sg.component == comp for sg in segments)
+        engine.loss_step(xx, tt, segments, 3, True, None, G[comp], sums)
+    return sums.to(torch.float32), G, weights
+
+
 def _eager_loss_grad() -> bool:
     """PINNK_EAGER_LOSS_GRAD=1: per-component gradients computed inside compute_loss at every batch size (A/B)."""
     import os

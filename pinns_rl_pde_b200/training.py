@@ -1,7 +1,7 @@
 """Host-side mirror of the inner training step of ``pinnrl.training.trainer.PDETrainer``
 (trainer.py:292-332 optimiser/scheduler set-up, :539-698 the step, :373-389 the L-BFGS closure step, :140-162 validation
-loss, :171-279 live snapshot).  Plots, dashboards, metadata files and adaptive loss re-weighting are outside the hot path
-and not mirrored; for those, patch the reference (``patch_reference``) and use its own trainer.
+loss, :171-279 live snapshot, :580-634 adaptive re-weighting).  Plots, dashboards and metadata files are outside the hot
+path and not mirrored; for those, patch the reference (``patch_reference``) and use its own trainer.
 
 ``fused=True`` runs the whole Adam step inside libpinnk; ``graph=True`` replays it as a CUDA graph per batch shape.
 With ``world_size > 1`` (one process per GPU, torch.distributed/NCCL) collocation rows are sharded
@@ -31,6 +31,58 @@ class LBFGSConfig:
 
 
 @dataclass
+class AdaptiveWeightsConfig:
+    """config/__init__.py:67-87."""
+    enabled: bool = False
+    strategy: str = "rbw"              # "lrw" | "rbw"
+    alpha: float = 0.9
+    eps: float = 1e-5
+    initial_weights: Optional[List[float]] = None
+
+    def __post_init__(self):
+        if self.initial_weights is None:
+            self.initial_weights = [0.5, 0.3, 0.2]
+
+
+class AdaptiveLossWeights:
+    """components/adaptive_weights.py:6-134 on device 3-vectors.  ``update(losses=...)`` (RBW: weights follow the running
+    losses, smoothed with the previous weights) or ``update(gradients=...)`` (LRW: weights inversely proportional to the
+    running per-component gradient norms); the first call returns the initial weights and seeds the running average."""
+
+    def __init__(self, strategy="rbw", alpha=0.9, eps=1e-5, initial_weights=None):
+        self.strategy, self.alpha, self.eps = str(strategy).lower(), float(alpha), float(eps)
+        if self.strategy not in ("lrw", "rbw"):
+            raise ValueError(f"unknown adaptive-weights strategy {strategy!r}")
+        self.initial_weights = None if initial_weights is None else torch.tensor(initial_weights)
+        self.weights = self.running = self.prev_weights = None
+
+    def update(self, losses: Optional[torch.Tensor] = None, gradients: Optional[torch.Tensor] = None) -> torch.Tensor:
+        v = gradients if self.strategy == "lrw" else losses
+        if v is None:
+            raise ValueError(f"Invalid combination of strategy ({self.strategy}) and inputs")
+        if self.running is None:
+            self.running = v
+            self.weights = (self.initial_weights.to(v.device) if self.initial_weights is not None else torch.ones_like(v))
+            return self.weights
+        self.running = self.alpha * self.running + (1 - self.alpha) * v
+        eps = torch.tensor(self.eps, device=v.device)
+        if self.strategy == "lrw":
+            inv = 1.0 / (self.running + eps)
+            self.weights = inv / torch.sum(inv)
+            return self.weights
+        self.weights = self.running / (self.running.sum() + eps)
+        if self.prev_weights is not None:
+            self.weights = self.alpha * self.prev_weights + (1 - self.alpha) * self.weights
+        self.prev_weights = self.weights.clone()
+        return self.weights
+
+    def get_weights(self) -> torch.Tensor:
+        if self.weights is not None:
+            return self.weights
+        return self.initial_weights if self.initial_weights is not None else torch.ones(3) / 3.0
+
+
+@dataclass
 class TrainingConfig:
     """The fields of pinnrl.config.TrainingConfig the step reads (config/__init__.py:90-169)."""
     num_epochs: int = 100
@@ -50,10 +102,13 @@ class TrainingConfig:
     huber_delta: float = 1.0
     optimizer: str = "adam"            # "adam" | "lbfgs" (config/__init__.py:123; the adam_lbfgs hand-over: switch_to_lbfgs())
     lbfgs: Optional[LBFGSConfig] = None
+    adaptive_weights: Optional[AdaptiveWeightsConfig] = None
 
     def __post_init__(self):
         if self.lbfgs is None:
             self.lbfgs = LBFGSConfig()
+        if self.adaptive_weights is None:
+            self.adaptive_weights = AdaptiveWeightsConfig()
         if self.optimizer not in ("adam", "lbfgs"):
             raise ValueError(f"unknown optimizer {self.optimizer!r}: choose 'adam' or 'lbfgs'")
         if self.loss_weights is None:
@@ -151,6 +206,12 @@ class PDETrainer:
             raise ValueError("PDETrainer(graph=True) captures the fused step: pass fused=True")
         self._graphs: Dict[tuple, dict] = {}
         lr, wd = oc.get("learning_rate", self.training.learning_rate), oc.get("weight_decay", self.training.weight_decay)
+        aw = self.training.adaptive_weights
+        self.use_adaptive_weights = bool(aw.enabled)
+        self.adaptive_weights = (AdaptiveLossWeights(aw.strategy, aw.alpha, aw.eps, aw.initial_weights)
+                                 if self.use_adaptive_weights else None)
+        if self.use_adaptive_weights and self.graph:
+            raise ValueError("adaptive re-weighting changes the weights every step on the host: not with graph=True")
         self._is_lbfgs = self.training.optimizer == "lbfgs"
         if self._is_lbfgs and self.fused:
             raise ValueError("fused=True is the Adam step; L-BFGS drives compute_loss + backward through its closure")
@@ -180,7 +241,9 @@ class PDETrainer:
             lo, hi = parallel.shard_bounds(n_global)
             x, t = x[lo:hi], t[lo:hi]
         if self._is_lbfgs:
-            return self._lbfgs_step(x, t)
+            return self._lbfgs_step(x, t)              # (adaptive weights are disabled under L-BFGS, trainer.py:464-468)
+        if self.use_adaptive_weights and self.training.mode != "data_only":
+            return self._adaptive_step(x, t)
         if self.fused:
             if self.graph and parallel.world_size() == 1:
                 return self._graph_step(x, t)
@@ -211,6 +274,40 @@ class PDETrainer:
         zero = torch.zeros((), device=flat.device)
         return {"residual": sums[0], "boundary": sums[1], "initial": sums[2], "smoothness": zero, "data": zero.clone(),
                 "total": w_res * sums[0] + w_bc * sums[1] + w_ic * sums[2]}
+
+    def _adaptive_step(self, x, t):
+        """trainer.py:580-694 with adaptive re-weighting: per-component losses and gradients in one reverse pass per row set
+        (``G [3, P]``), LRW weights from the rows' norms / RBW weights from the losses, weighted gradient ``w @ G``, clip, Adam.
+        ``pde.compat == "reference"`` keeps a quirk of the reference's LRW branch: its last per-component ``backward`` is not
+        followed by a ``zero_grad`` (trainer.py:611-622,689), so the gradient it steps with is ``w @ G`` PLUS the gradient
+        of the initial-condition component; ``compat == "math"`` steps with ``w @ G``."""
+        if parallel.world_size() > 1:
+            raise NotImplementedError("adaptive re-weighting is single-process in this mirror")
+        comp, G, _ = F.loss_components_and_grads(self.pde, self.model, x, t)
+        lrw = self.adaptive_weights.strategy == "lrw"
+        if lrw:
+            w = self.adaptive_weights.update(gradients=torch.linalg.vector_norm(G, dim=1))
+        else:
+            w = self.adaptive_weights.update(losses=comp.detach().clone())
+        w = w.to(torch.float32)
+        flat = w @ G
+        if lrw and getattr(self.pde, "compat", "reference") == "reference":
+            flat = flat + G[2]
+        total = torch.dot(w, comp)
+        self.history.setdefault("loss_weights", []).append(w.detach())
+        if self.fused:
+            self.optimizer.step(flat.contiguous())
+        else:
+            self.optimizer.zero_grad(set_to_none=True)
+            program = F.get_program(self.model)
+            for p, g in zip(program.grad_params, program.split_flat(flat)):
+                p.grad = g.clone()
+            if self.training.gradient_clipping > 0:
+                nn.utils.clip_grad_norm_(self.model.parameters(), self.training.gradient_clipping)
+            self.optimizer.step()
+        zero = torch.zeros((), device=flat.device)
+        return {"residual": comp[0], "boundary": comp[1], "initial": comp[2], "smoothness": zero, "data": zero.clone(),
+                "total": total}
 
     def _build_lbfgs(self, lr):
         """trainer.py:299-309."""

@@ -316,6 +316,28 @@ def run_dqn_case(tag="x_dqn", state_dim=2, hidden=128, grid=24, seed=0):
     return {"case": tag, "port_bit_identical_fp32": True, "ref32_vs_ref64": rel(q32.double(), q64), "states": int(pts.shape[0])}
 
 
+def run_adaptive_case(tag="x_adaptive_weights", steps=12, seed=0):
+    """components/adaptive_weights.py (the re-weighting of trainer.py:580-634): unmodified reference vs the oracle port on a
+    random sequence of component losses / gradient norms, both strategies -> inputs and the weights after every update."""
+    from pinnrl.components.adaptive_weights import AdaptiveLossWeights as RefALW
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for strategy in ("rbw", "lrw"):
+        seq = torch.rand(steps, 3, generator=g) * torch.tensor([5.0, 0.5, 0.05])
+        ref = RefALW(strategy=strategy, alpha=0.9, eps=1e-5, initial_weights=[0.5, 0.3, 0.2])
+        port = ref_port.AdaptiveLossWeightsPort(strategy=strategy, alpha=0.9, eps=1e-5, initial_weights=[0.5, 0.3, 0.2])
+        ws = []
+        for v in seq:
+            kw = {"losses": v} if strategy == "rbw" else {"gradients": v}
+            a, b = ref.update(**kw), port.update(**kw)
+            assert torch.equal(a, b), "oracle port of AdaptiveLossWeights differs from the reference"
+            ws.append(a.clone())
+        out[strategy + "_in"] = seq.numpy()
+        out[strategy + "_w"] = torch.stack(ws).numpy()
+    np.savez_compressed(os.path.join(HERE, tag + ".npz"), **out)
+    return {"case": tag, "port_bit_identical_fp32": True, "steps": steps}
+
+
 def main_next():
     """`python tests/golden/make_golden.py next`: only the fixtures of the SURVEY 8(f).4 PDEs (existing files untouched)."""
     reports = [run_case("x_wave_ff_small", "wave", "feedforward", 32, 3, 96),
@@ -353,8 +375,8 @@ def main():
 
 
 if __name__ == "__main__":
-    if sys.argv[1:] == ["dqn"]:
-        rep = run_dqn_case()
+    if sys.argv[1:] in (["dqn"], ["adaptive"]):
+        rep = run_dqn_case() if sys.argv[1] == "dqn" else run_adaptive_case()
         path = os.path.join(HERE, "golden_report.json")
         old = [r for r in json.load(open(path)) if r["case"] != rep["case"]]
         json.dump(old + [rep], open(path, "w"), indent=1)

@@ -33,8 +33,8 @@ PDES = {
 
 
 def fixtures():
-    """PDE hot-path fixtures (x_dqn.npz, the RL sampler's Q-network, has its own tests in test_dqn.py)."""
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f != "x_dqn.npz")
+    """PDE hot-path fixtures (x_dqn.npz, the RL sampler's Q-network, and x_adaptive_weights.npz have their own tests)."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f not in ("x_dqn.npz", "x_adaptive_weights.npz"))
 
 
 def load_fixture(tag):
