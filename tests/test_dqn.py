@@ -139,3 +139,30 @@ def test_adaptive_sampling_goes_through_libpinnk():
         p_ref = p_ref / p_ref.sum()
     assert torch.allclose(p_lib, p_ref, rtol=1e-4, atol=1e-9)
     assert pts.shape == (400, 2)
+
+
+def test_adaptive_sampler_keeps_foreign_agents_on_their_own_forward():
+    """An agent without a DQNNetwork-shaped ``policy_net`` (or a wider one than the kernel is used for) is not replaced:
+    grid_scores falls through to ``agent.select_action`` (pde_base.py:1003-1008 unchanged).  Runs on the CPU."""
+    import types
+    from helpers import product_pde
+    from pinns_rl_pde_b200 import rl
+    calls = []
+
+    def select_action(points):
+        calls.append(points.shape)
+        return torch.linspace(1.0, 2.0, points.shape[0]).view(1, -1)
+
+    agent = types.SimpleNamespace(select_action=select_action, epsilon=0.0, device=torch.device("cpu"))
+    pts = torch.rand(50, 2)
+    p = rl.grid_scores(agent, pts)
+    assert calls == [pts.shape] and abs(float(p.sum()) - 1.0) < 1e-6 and p.shape == (1, 50)
+    agent.policy_net = rl.DQNNetwork(2, 1, 512)                       # wider than rl.MAX_HIDDEN: declined, agent's own forward
+    rl.grid_scores(agent, pts)
+    assert len(calls) == 2
+    pde = product_pde("burgers", torch.device("cpu"))
+    pde.rl_agent = agent
+    torch.manual_seed(0)
+    x, t = pde.generate_collocation_points(300, strategy="adaptive")
+    assert x.shape == (300, 1) and t.shape == (300, 1) and len(calls) == 3
+    assert float(x.min()) >= -1.0 and float(x.max()) <= 1.0 and float(t.min()) >= 0.0 and float(t.max()) <= 1.0
