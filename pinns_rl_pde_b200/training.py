@@ -283,7 +283,9 @@ class PDETrainer:
         of the initial-condition component; ``compat == "math"`` steps with ``w @ G``."""
         if parallel.world_size() > 1:
             raise NotImplementedError("adaptive re-weighting is single-process in this mirror")
-        comp, G, _ = F.loss_components_and_grads(self.pde, self.model, x, t)
+        comp, G, weights = F.loss_components_and_grads(self.pde, self.model, x, t)
+        if weights[3]:
+            raise NotImplementedError("adaptive re-weighting with a smoothness term (a fourth component) is not mirrored")
         lrw = self.adaptive_weights.strategy == "lrw"
         if lrw:
             w = self.adaptive_weights.update(gradients=torch.linalg.vector_norm(G, dim=1))
