@@ -338,6 +338,28 @@ def run_adaptive_case(tag="x_adaptive_weights", steps=12, seed=0):
     return {"case": tag, "port_bit_identical_fp32": True, "steps": steps}
 
 
+def run_snapshot_case(tag="x_live_snapshot", grid=12, seed=0):
+    """trainer.py:171-279 ``_save_live_snapshot`` of the UNMODIFIED reference (Burgers, feed-forward 3x32, CPU): the npz it writes
+    plus the weights, so that the mirror's grid construction / ordering / keys can be checked against the real file."""
+    import tempfile
+    from pinnrl.training.trainer import PDETrainer as RefTrainer
+    torch.manual_seed(seed)
+    model = ref_model("feedforward", 2, 32, 3)
+    pde = ref_pde("burgers")
+    tr = RefTrainer.__new__(RefTrainer)                      # only the attributes the method reads
+    tr.model, tr.pde, tr.device = model, pde, CPU
+    import logging
+    tr.logger = logging.getLogger("golden")
+    d = tempfile.mkdtemp()
+    tr._save_live_snapshot(d, epoch=3, grid_size=grid)
+    z = np.load(os.path.join(d, "live_snapshot.npz"))
+    out = {"snap::" + k: z[k] for k in z.files}
+    for k, v in model.state_dict().items():
+        out["w::" + k] = v.numpy()
+    np.savez_compressed(os.path.join(HERE, tag + ".npz"), **out)
+    return {"case": tag, "keys": sorted(z.files), "grid": grid}
+
+
 def main_next():
     """`python tests/golden/make_golden.py next`: only the fixtures of the SURVEY 8(f).4 PDEs (existing files untouched)."""
     reports = [run_case("x_wave_ff_small", "wave", "feedforward", 32, 3, 96),
@@ -375,8 +397,8 @@ def main():
 
 
 if __name__ == "__main__":
-    if sys.argv[1:] in (["dqn"], ["adaptive"]):
-        rep = run_dqn_case() if sys.argv[1] == "dqn" else run_adaptive_case()
+    if sys.argv[1:] in (["dqn"], ["adaptive"], ["snapshot"]):
+        rep = {"dqn": run_dqn_case, "adaptive": run_adaptive_case, "snapshot": run_snapshot_case}[sys.argv[1]]()
         path = os.path.join(HERE, "golden_report.json")
         old = [r for r in json.load(open(path)) if r["case"] != rep["case"]]
         json.dump(old + [rep], open(path, "w"), indent=1)

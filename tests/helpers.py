@@ -34,7 +34,7 @@ PDES = {
 
 def fixtures():
     """PDE hot-path fixtures (x_dqn.npz, the RL sampler's Q-network, and x_adaptive_weights.npz have their own tests)."""
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f not in ("x_dqn.npz", "x_adaptive_weights.npz"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f not in ("x_dqn.npz", "x_adaptive_weights.npz", "x_live_snapshot.npz"))
 
 
 def load_fixture(tag):

@@ -87,3 +87,40 @@ def test_graph_trainer_needs_the_fused_step():
     model = torch.nn.Linear(2, 1)
     with pytest.raises(ValueError):
         pk.PDETrainer(model, object.__new__(pk.BurgersEquation), config=pk.TrainingConfig(), device=torch.device("cpu"), graph=True)
+
+
+def test_live_snapshot_layout_matches_the_reference_file(monkeypatch):
+    """trainer.py:171-279: the mirror's PDETrainer.live_snapshot (grid construction, ordering, keys) executed on the CPU with
+    the network / residual evaluations routed to the oracle, against the npz the UNMODIFIED reference wrote
+    (tests/golden/x_live_snapshot.npz, made by make_golden.py snapshot).  The libpinnk evaluations themselves are covered by
+    tests/test_gpu_graph.py::test_validation_loss_and_live_snapshot."""
+    import types
+    import numpy as np
+    import pinns_rl_pde_b200 as pk
+    from pinns_rl_pde_b200 import training
+    from oracle import ref_port
+    from helpers import GOLDEN, PDES
+    z = np.load(os.path.join(GOLDEN, "x_live_snapshot.npz"))
+    state = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w::")}
+    want = {k[6:]: z[k] for k in z.files if k.startswith("snap::")}
+    model = ref_port.PINNModel("feedforward", 2, 32, 3)
+    model.load_state_dict(state)
+    s = PDES["burgers"]
+    pde = types.SimpleNamespace(dimension=1, domain=s["domain"], time_domain=s["time"],
+                                compute_residual=lambda m, x, t: ref_port.burgers_residual(m, x, t, nu=s["params"]["nu"]).detach())
+    monkeypatch.setattr(training.F, "model_forward", lambda m, xt: m(xt))
+    tr = object.__new__(pk.PDETrainer)
+    tr.model, tr.pde, tr.device = model, pde, torch.device("cpu")
+    snap = tr.live_snapshot(epoch=3, grid_size=12)
+    assert set(snap) == set(want)
+    for k in ("axis_x", "axis_y"):
+        assert np.array_equal(snap[k], want[k])
+    assert int(snap["epoch"]) == int(want["epoch"]) and int(snap["dimension"]) == int(want["dimension"])
+    assert str(snap["x_label"]) == str(want["x_label"]) and str(snap["y_label"]) == str(want["y_label"])
+    assert np.isnan(snap["fixed_t"]) and np.isnan(want["fixed_t"])
+    assert np.allclose(snap["u_pred"], want["u_pred"], rtol=0, atol=1e-6)
+    # the oracle residual needs grad-enabled inputs: live_snapshot runs it under no_grad in the product (forward-mode jets), so
+    # here the comparison is made with the oracle called directly on the snapshot's grid, in the snapshot's ordering
+    xx, tt = np.meshgrid(snap["axis_x"], snap["axis_y"], indexing="xy")
+    r = ref_port.burgers_residual(model, torch.tensor(xx.reshape(-1, 1)), torch.tensor(tt.reshape(-1, 1)), nu=s["params"]["nu"])
+    assert np.allclose(r.detach().numpy().reshape(12, 12), want["residual"], rtol=1e-5, atol=1e-6)
