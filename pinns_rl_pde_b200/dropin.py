@@ -23,7 +23,7 @@ def patch_reference(compat: str = "reference"):
             "black_scholes": "BlackScholesEquation", "pendulum_equation": "PendulumEquation"}
     try:
         base = importlib.import_module("pinnrl.pdes.pde_base")
-    except ImportError as e:   # pragma: no cover - pinnrl is not installed on the GPU box
+    except ImportError as e:
         raise ImportError("patch_reference() needs the reference package `pinnrl` importable") from e
     for mod, cls_name in mods.items():
         cls = getattr(importlib.import_module(f"pinnrl.pdes.{mod}"), cls_name)
@@ -47,6 +47,12 @@ def patch_reference(compat: str = "reference"):
             import torch
             from . import rl
             if torch.device(self.device).type == "cuda":
+                try:
+                    rl._lower(getattr(self, "policy_net", None))
+                except rl.UnsupportedQNetwork:
+                    # not a DQNNetwork-shaped policy net (or a width pinnk_dqn_forward does not cover): the agent's own
+                    # torch forward, exactly as before the patch
+                    return _orig(self, state)
                 return rl.select_action(self, state)
             return _orig(self, state)
         agent_cls.select_action = select_action

@@ -1,24 +1,19 @@
-"""CPU: patch_reference() swaps the hot path into the reference's own classes (only runs where /root/reference
-exists, i.e. in the build container); with no GPU the patched methods must raise -- never fall back."""
+"""CPU: patch_reference() swaps the hot path into the reference's own classes (the unmodified reference installed to
+baseline/_ref by oracle/install_reference.py); with no GPU the patched methods must raise -- never fall back."""
 import os
 import sys
-from unittest.mock import MagicMock
 
 import pytest
 import torch
 
-REF = "/root/reference"
-pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "pinnrl")), reason="reference not mounted")
+from oracle import ref_env
+
+needs_ref = pytest.mark.skipif(not ref_env.available(), reason="baseline/_ref not installed")
 
 
+@needs_ref
 def test_patch_and_unpatch_reference():
-    sys.path.insert(0, REF)
-    for m in ("matplotlib", "matplotlib.pyplot", "matplotlib.colors", "plotly", "plotly.graph_objects",
-              "plotly.subplots", "plotly.express"):
-        if m not in sys.modules:
-            mm = MagicMock()
-            mm.__path__ = []
-            sys.modules[m] = mm
+    ref_env.activate()
     try:
         import pinnrl.pdes.burgers_equation as be
         from pinnrl.config import Config, ModelConfig
@@ -47,7 +42,38 @@ def test_patch_and_unpatch_reference():
         r = pde.compute_residual(model, torch.zeros(4, 1), torch.zeros(4, 1))      # the reference path again
         assert r.shape == (4, 1)
     finally:
-        sys.path.remove(REF)
+        pass
+
+
+@needs_ref
+def test_patched_select_action_keeps_the_agents_forward_for_unsupported_q_networks():
+    """dropin: RLAgent.select_action after patch_reference() must not raise for policy networks pinnk_dqn_forward does
+    not cover -- it falls back to the reference's own method, here on a CPU agent and, via the
+    UnsupportedQNetwork probe, for any non-DQNNetwork-shaped policy net."""
+    ref_env.activate()
+    import pinns_rl_pde_b200 as pk
+    from pinns_rl_pde_b200 import dropin, rl
+    from pinnrl.rl.rl_agent import RLAgent
+    agent = RLAgent(state_dim=2, action_dim=1, hidden_dim=512, epsilon_start=0.0, epsilon_end=0.0, device=torch.device("cpu"))
+    pk.patch_reference()
+    try:
+        out = agent.select_action(torch.rand(50, 2))
+        assert out.shape == (1, 50)
+        with pytest.raises(rl.UnsupportedQNetwork):
+            rl._lower(torch.nn.Linear(2, 1))
+    finally:
+        dropin.unpatch_reference()
+
+
+@needs_ref
+def test_reference_trainer_harness_runs_the_unmodified_trainer_on_cpu():
+    """tests/ref_trainer_harness.py (the stock arm of the GPU trajectory test): 2 epochs of pinnrl's own PDETrainer.train
+    in fp32 and fp64 from the same seed agree to fp32 round-off, i.e. both arms see the same points and weights."""
+    import ref_trainer_harness as H
+    a = H.run("c1_heat_fourier", "cpu", 2, batch_size=128, num_points=300)
+    b = H.run("c1_heat_fourier", "cpu", 2, batch_size=128, num_points=300, dtype=torch.float64)
+    assert len(a["train_loss"]) == 2 and len(a["val_loss"]) == 1
+    assert max(H.deviation(a["train_loss"], b["train_loss"]).values()) < 1e-5
 
 
 def test_cached_rows_are_keyed_on_what_they_depend_on():

