@@ -229,7 +229,9 @@ class PINNModel(nn.Module):
 def _grad(y, x):
     g = torch.autograd.grad(y, x, grad_outputs=torch.ones_like(y), create_graph=True,
                             allow_unused=True, retain_graph=True)[0]
-    return torch.zeros_like(y) if g is None else g
+    # pde_base.py:668-671,711-714: the zeros that stand in for an unused input are made to require grad, so that the next
+    # order can be "differentiated" again (-> None -> zeros) instead of raising
+    return torch.zeros_like(y).requires_grad_(True) if g is None else g
 
 
 def compute_derivatives(model, x, t, spatial: Sequence[int], temporal: Sequence[int],

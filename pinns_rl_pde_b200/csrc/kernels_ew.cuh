@@ -961,10 +961,12 @@ __global__ void adam_kernel(ParamTable tab, const float* __restrict__ g, float* 
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= tab.off[tab.n]) return;
   if (dyn) {                                       // graph-replayable step: step count and lr live on the device
-    const float step = (float)dyn[0];
+    // bias corrections in double, as torch.optim.Adam computes them (1 - beta ** step in Python floats): in fp32,
+    // 1 - 0.999^step is off by ~1e-5 relative for the first steps
+    const double step = dyn[0];
     lr = (float)dyn[1];
-    bc1 = 1.f - powf(beta1, step);
-    bc2_sqrt = sqrtf(1.f - powf(beta2, step));
+    bc1 = (float)(1.0 - pow((double)beta1, step));
+    bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, step));
   }
   int lo = 0, hi = tab.n - 1;                      // tensor holding flat index i
   while (lo < hi) {

@@ -335,12 +335,24 @@ static int gemm_dgrad(const ChunkCtx& c, const float* Zb, const float* W, float*
   return 0;
 }
 
-static int gemm_wgrad(const ChunkCtx& c, const float* Zb, const float* X, float* gW, float* gb, int in_dim, int out_dim) {
+// PINNK_DETERMINISTIC=1: the hidden layers' weight gradients are reduced in a fixed order (per-CTA partial slabs in an
+// idle adjoint buffer + wgrad_det_reduce_kernel) instead of with atomics in CTA arrival order: bit-identical dW / db of
+// every 128-multiple hidden Linear from run to run (the arrival-order reduction moved them by 2e-6 .. 4e-6 relative).
+// The few hundred per-thread atomics of the edge layers (input / output layer gradients) keep their arrival order.
+static bool deterministic_enabled() {
+  const char* e = getenv("PINNK_DETERMINISTIC");         // read per call: tests switch it on and off
+  return e && e[0] == '1';
+}
+
+static int gemm_wgrad(const ChunkCtx& c, const float* Zb, const float* X, float* gW, float* gb, int in_dim, int out_dim,
+                      float* scratch = nullptr) {
   ProfScope ps(PC_GEMM_WGRAD, c.st);
   const int64_t M = c.n * c.pl->js.ncols;   // contraction length
   if (tc_enabled() && gW) {
-    int rc = tc_linear_wgrad(Zb, X, gW, gb, M, in_dim, out_dim, c.pl->js.ncols, c.pl->sm_count, c.st);
-    if (rc == 0) { g_launches.fetch_add(1); return 0; }
+    const bool det = scratch != nullptr && deterministic_enabled();
+    int rc = tc_linear_wgrad(Zb, X, gW, gb, M, in_dim, out_dim, c.pl->js.ncols, c.pl->sm_count, c.st, det ? scratch : nullptr,
+                             det ? (int64_t)c.pl->js.ncols * c.pl->chunk * c.pl->max_width : 0);
+    if (rc == 0) { g_launches.fetch_add(det ? 2 : 1); return 0; }
     if (rc != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, std::string("tc_linear_wgrad launch failed: ") + cudaGetErrorString(cudaGetLastError()));
   }
   if (gW) {
@@ -665,7 +677,8 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad, bool last_done = 
           first_linear_bwd_kernel<<<grid, 128, 0, c.st>>>(c.x, c.t, c.n, o.out_dim, js, c.adj(cur), G(o.gw_offset), G(o.gb_offset));
           PK_LAUNCH_OK();
         } else {
-          int rc = gemm_wgrad(c, c.adj(cur), in, G(o.gw_offset), G(o.gb_offset), o.in_dim, o.out_dim);
+          // (the adjoint buffer the dgrad below will write is idle during the wgrad: scratch of the deterministic reduction)
+          int rc = gemm_wgrad(c, c.adj(cur), in, G(o.gw_offset), G(o.gb_offset), o.in_dim, o.out_dim, c.adj(other(cur, held)));
           if (rc) return rc;
           if (i > first_trainable) {
             const int nxt = other(cur, held);
@@ -1081,8 +1094,9 @@ static int adam_step_impl(float* const* params, const int64_t* numels, int32_t n
     sumsq_kernel<<<(unsigned)std::min<int64_t>((off + 255) / 256, 592), 256, 0, st>>>(flat_grad, off, scratch);
     PK_LAUNCH_OK();
   }
-  const float bc1 = dyn ? 1.f : 1.f - powf(beta1, (float)step);
-  const float bc2_sqrt = dyn ? 1.f : sqrtf(1.f - powf(beta2, (float)step));
+  // (double, like torch.optim.Adam's Python-float bias corrections; the device-side variant does the same in the kernel)
+  const float bc1 = dyn ? 1.f : (float)(1.0 - pow((double)beta1, (double)step));
+  const float bc2_sqrt = dyn ? 1.f : (float)sqrt(1.0 - pow((double)beta2, (double)step));
   adam_kernel<<<blocks_for(off, 256), 256, 0, st>>>(tab, flat_grad, exp_avg, exp_avg_sq, scratch, max_norm, lr, beta1, beta2, eps,
                                                     weight_decay, bc1, bc2_sqrt, dyn);
   PK_LAUNCH_OK();

@@ -61,8 +61,10 @@ int tc_linear_dgrad_firstbwd(const float* dZ, const float* W, int64_t M, int in_
 int tc_dgrad_actbwd_y(int k0, int k1, const float* dZ, const float* W, int in_dim, float* dZprev, int64_t M,
                       const float* Yprev, int sm_count, cudaStream_t st, int out_dim, int accum);
 // dW[out,in] += dZ[M,out]^T X[M,in] ;  db[out] += sum over value-column rows of dZ
+// det_scratch != null: deterministic reduction -- per-CTA partial slabs in det_scratch (det_floats floats available,
+// >= 16640 per 128 x 128 block), added in CTA order by a second kernel instead of atomics in arrival order
 int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
-                    int jet_cols, int sm_count, cudaStream_t st);
+                    int jet_cols, int sm_count, cudaStream_t st, float* det_scratch = nullptr, int64_t det_floats = 0);
 // stage timers of the rows kernels (zeros unless built with -DPINNK_STAGE_TIMERS); 0 ok, 1 not compiled in
 int tc_stage_timers_fwd(unsigned long long* out16, int reset);
 int tc_stage_timers_bwd(unsigned long long* out16, int reset);

@@ -1284,7 +1284,11 @@ template <int TK, int RS, int OS, int NCW, int SEG, bool TSA>
 __global__ void __launch_bounds__((NCW + 8) * 32, 1)
 wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, int ldx, float* __restrict__ dW, int lddw,
              float* __restrict__ db, int64_t M, int jet_cols, int in_blocks, const __grid_constant__ CUtensorMap tmg,
-             const __grid_constant__ CUtensorMap tmxm) {
+             const __grid_constant__ CUtensorMap tmxm, float* __restrict__ det_part, float* __restrict__ det_bpart) {
+  // det_part != null (PINNK_DETERMINISTIC=1): every CTA stores its 128 x 128 partial sum to its own slab
+  // det_part[(blockIdx.y * gridDim.x + blockIdx.x) * 16384] (and its bias partials to det_bpart[cta][2][128]) instead of
+  // reducing into dW / db with atomics in arrival order; wgrad_det_reduce_kernel then adds the slabs in CTA order, so the
+  // gradient is bit-identical from run to run.
   static_assert(TK == 32 && (NCW == 8 || NCW == 16), "tile shape");
   // TSA: the G^T operand (A of the MMA: 128 out-features x 32 rows) lives in TENSOR MEMORY instead of shared memory.  An
   // SS-mode 128x128x8 MMA reads 8 KB of operands from shared memory in its 64 cycles -- all of the SM's 128 B/cycle -- and
@@ -1421,7 +1425,10 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
         if (++rs == RS) { rs = 0; rph ^= 1u; }
         if (++os == OS) { os = 0; oph ^= 1u; }
       }
-      if (want_b1) atomicAdd(db + o0 + f, bsum1);
+      if (want_b1) {
+        if (det_bpart) det_bpart[((int64_t)(blockIdx.y * gridDim.x + blockIdx.x) * 2 + h) * 128 + f] = bsum1;
+        else atomicAdd(db + o0 + f, bsum1);
+      }
     } else {
     const int rq = warp & 7, sel = warp >> 3;
     float bsum[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1549,7 +1556,11 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
       named_bar_sync(1, kEpiThreads);
       const int t = threadIdx.x - EPI0 * 32;
       float* const dw0 = dW + (int64_t)o0 * lddw + i0;
-      if (((reinterpret_cast<uintptr_t>(dw0) & 15) == 0) && (lddw & 3) == 0) {
+      if (det_part != nullptr) {
+        float4* const slab = reinterpret_cast<float4*>(det_part + (int64_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16384);
+        for (int idx = t; idx < 128 * 32; idx += kEpiThreads)
+          slab[idx] = *reinterpret_cast<const float4*>(tr + (idx >> 5) * 132 + (idx & 31) * 4);
+      } else if (((reinterpret_cast<uintptr_t>(dw0) & 15) == 0) && (lddw & 3) == 0) {
         // 16-byte vector reductions: a quarter of the atomic operations (all CTAs add into the same 128 x 128 block)
         for (int idx = t; idx < 128 * 32; idx += kEpiThreads) {
           const int row = idx >> 5, c4 = (idx & 31) * 4;
@@ -1646,9 +1657,35 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
   }
 }
 
+// fixed-order reduction of the per-CTA partial slabs of a deterministic wgrad launch: dW[block] += sum_x part[block][x]
+// (x = 0 .. gx-1 in order), db[o] += sum_x (bpart[x][0][o] + bpart[x][1][o]).  grid (16, blocks), 256 threads.
+static __global__ void wgrad_det_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bpart, int gx,
+                                               int in_blocks, float* __restrict__ dW, int lddw, float* __restrict__ db) {
+  const int blk = blockIdx.y, o0 = (blk / in_blocks) * 128, i0 = (blk % in_blocks) * 128;
+  const int idx = blockIdx.x * 256 + threadIdx.x;                    // float4 index inside the 128 x 128 block
+  const int row = idx >> 5, c4 = (idx & 31) * 4;
+  const float4* p = reinterpret_cast<const float4*>(part + (int64_t)blk * gx * 16384) + idx;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int x = 0; x < gx; ++x) {
+    const float4 v = p[(int64_t)x * 4096];
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  float* d = dW + (int64_t)(o0 + row) * lddw + i0 + c4;
+  d[0] += a.x; d[1] += a.y; d[2] += a.z; d[3] += a.w;
+  if (db != nullptr && i0 == 0 && idx < 128) {
+    float b = 0.f;
+    for (int x = 0; x < gx; ++x) {
+      const float* q = bpart + ((int64_t)(blk * gx + x) * 2) * 128 + idx;
+      b += q[0];
+      b += q[128];
+    }
+    db[o0 + idx] += b;
+  }
+}
+
 template <int TK, int RS, int OS, int NCW, int SEG, bool TSA>
 static int launch_wgrad(const float* G, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
-                        int jet_cols, int sm_count, cudaStream_t st) {
+                        int jet_cols, int sm_count, cudaStream_t st, float* det_scratch = nullptr, int64_t det_floats = 0) {
   constexpr size_t smem = 1024 + (size_t)OS * (TSA ? 2 : 4) * TK * 512 + (size_t)RS * 2 * TK * 512 + (2 * RS + 2 * OS + 4) * 8 + 16;
   static_assert(smem <= 232448 && (size_t)RS * 2 * TK * 512 >= 128 * 132 * 4, "shared memory budget / transpose buffer");
   auto kern = wgrad_kernel<TK, RS, OS, NCW, SEG, TSA>;
@@ -1662,13 +1699,29 @@ static int launch_wgrad(const float* G, const float* X, float* dW, float* db, in
   int gx = sm_count / blocks;
   if (gx < 1) gx = 1;
   if ((int64_t)gx > ntiles) gx = (int)ntiles;
+  float* det_part = nullptr;
+  float* det_bpart = nullptr;
+  if (det_scratch != nullptr) {
+    if (!TSA) return TC_UNSUPPORTED;
+    // per CTA: a 128 x 128 slab + 2 x 128 bias partials; fewer CTAs when the scratch buffer is small (small chunks)
+    const int64_t per_cta = 16384 + 256;
+    const int64_t cap = det_floats / (per_cta * blocks);
+    if (cap < 1) return TC_UNSUPPORTED;
+    if ((int64_t)gx > cap) gx = (int)cap;
+    det_part = det_scratch;
+    det_bpart = det_scratch + (int64_t)gx * blocks * 16384;
+  }
   dim3 grid((unsigned)gx, (unsigned)blocks, 1);
   alignas(64) CUtensorMap tmg, tmx;
   memset(&tmg, 0, sizeof(tmg));
   memset(&tmx, 0, sizeof(tmx));
   if (out_dim != 128 && !make_tmap_rows(&tmg, G, M, out_dim, out_dim, TK)) return -1;
   if (in_dim != 128 && !make_tmap_rows(&tmx, X, M, in_dim, in_dim, TK)) return -1;
-  kern<<<grid, (NCW + 8) * 32, smem, st>>>(G, out_dim, X, in_dim, dW, in_dim, db, M, jet_cols, in_blocks, tmg, tmx);
+  kern<<<grid, (NCW + 8) * 32, smem, st>>>(G, out_dim, X, in_dim, dW, in_dim, db, M, jet_cols, in_blocks, tmg, tmx, det_part,
+                                           det_bpart);
+  if (cudaGetLastError() != cudaSuccess) return -1;
+  if (det_part != nullptr)
+    wgrad_det_reduce_kernel<<<dim3(16, (unsigned)blocks, 1), 256, 0, st>>>(det_part, det_bpart, gx, in_blocks, dW, in_dim, db);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -1843,8 +1896,10 @@ int tc_stage_timers_wgrad(unsigned long long* out16, int reset) {
 }
 // dW[out,in] += dZ[M,out]^T X[M,in] ;  db[out] += sum over value-column rows of dZ
 int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
-                                  int jet_cols, int sm_count, cudaStream_t st) {
+                                  int jet_cols, int sm_count, cudaStream_t st, float* det_scratch, int64_t det_floats) {
   if (M < 1 || (in_dim % 128) != 0 || (out_dim % 128) != 0 || dW == nullptr) return TC_UNSUPPORTED;
+  if (det_scratch != nullptr)
+    return tc::launch_wgrad<32, 5, 2, 16, 4, true>(dZ, X, dW, db, M, in_dim, out_dim, jet_cols, sm_count, st, det_scratch, det_floats);
   static int ss = -1;       // PINNK_WGRAD_SS=1: both operands in shared memory (the earlier kernel, kept for A/B runs)
   if (ss < 0) { const char* e = getenv("PINNK_WGRAD_SS"); ss = (e && e[0] == '1') ? 1 : 0; }
   if (ss) return tc::launch_wgrad<32, 3, 2, 16, 4, false>(dZ, X, dW, db, M, in_dim, out_dim, jet_cols, sm_count, st);

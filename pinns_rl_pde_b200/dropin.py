@@ -33,6 +33,14 @@ def patch_reference(compat: str = "reference"):
         cls.compat = compat
         cls.compute_residual = lambda self, model, x, t: F.compute_residual(self, model, x, t)
         cls.compute_loss = lambda self, model, x, t: F.compute_loss(self, model, x, t)
+    # plugin PDEs (CONTRIBUTING.md:152-244) write compute_residual on top of PDEBase.compute_derivatives: one jet pass
+    # (same keys, same F1 / F2 bookkeeping under compat="reference") instead of nested autograd.grad chains
+    if base.PDEBase not in _PATCHED:
+        _PATCHED[base.PDEBase] = ("compute_derivatives", base.PDEBase.__dict__.get("compute_derivatives"))
+        if not hasattr(base.PDEBase, "compat"):
+            base.PDEBase.compat = compat
+        base.PDEBase.compute_derivatives = (lambda self, model, x, t, temporal_derivatives=None, spatial_derivatives=None:
+                                            F.compute_derivatives(self, model, x, t, temporal_derivatives, spatial_derivatives))
     # RL sampler: RLAgent.select_action (rl/rl_agent.py:214-229) scores the candidate grid through pinnk_dqn_forward when
     # the agent lives on a GPU; a CPU agent keeps the reference's own torch forward (the agent is not on the hot path then).
     try:
@@ -61,6 +69,11 @@ def patch_reference(compat: str = "reference"):
 
 def unpatch_reference():
     for cls, saved in list(_PATCHED.items()):
+        if len(saved) == 2 and saved[0] == "compute_derivatives":
+            if saved[1] is not None:
+                cls.compute_derivatives = saved[1]
+            _PATCHED.pop(cls)
+            continue
         if len(saved) == 1:                      # RLAgent.select_action
             cls.select_action = saved[0]
             _PATCHED.pop(cls)

@@ -258,6 +258,87 @@ def compute_residual(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor) ->
     return _ErrorFn.apply(eng, proto, x, t, keep, *eng.program.grad_params)
 
 
+def compute_derivatives(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, temporal_derivatives=None,
+                        spatial_derivatives=None) -> Dict[str, torch.Tensor]:
+    """``PDEBase.compute_derivatives`` (pde_base.py:590-794), the documented building block of plugin PDEs
+    (CONTRIBUTING.md:152-244), from ONE forward jet pass (``pinnk_jets_forward``); every returned ``[N, 1]`` tensor is
+    differentiable w.r.t. the model parameters through ``pinnk_jets_vjp`` (not w.r.t. ``x`` / ``t``: derivatives of
+    derivatives are requested as higher orders here, not by differentiating the results again).
+
+    Same keys as the reference: ``dt`` / ``dt2``; 1-D ``dx`` / ``dx{i}`` and ``laplacian``; multi-dim ``dx1``, ``dx1x1``,
+    ... per axis and ``laplacian``.  ``pde.compat == "reference"`` (default) reproduces the reference's bookkeeping:
+      * 1-D: ONE more differentiation per LISTED order, starting from ``u`` (pde_base.py:694-732), so the k-th listed
+        non-zero order holds the k-th derivative whatever its key says -- ``spatial_derivatives=[2]`` puts u_x under
+        ``"dx2"`` and ``"laplacian"`` (SURVEY F1); the same for the temporal list (:655-692);
+      * dimension >= 2: every spatial entry is zero (differentiation w.r.t. a fresh slice of x).
+    ``compat == "math"`` returns what the keys say (true i-th derivatives along each axis, true Laplacian)."""
+    temporal = sorted(set(int(i) for i in (temporal_derivatives or [])))
+    spatial = sorted(set(int(i) for i in (spatial_derivatives or [])))
+    if temporal and max(temporal) > 2:
+        raise ValueError(f"Temporal derivative order {max(temporal)} is not supported. Maximum order is 2.")
+    if spatial and max(spatial) > 4:
+        raise ValueError(f"Spatial derivative order {max(spatial)} is not supported. Maximum order is 4.")
+    compat = getattr(pde, "compat", "reference")
+    if compat not in ("reference", "math"):
+        raise ValueError("pde.compat must be 'reference' or 'math'")
+    as_written = compat == "reference"
+    d = int(pde.dimension)
+    for p in model.parameters():                 # pde_base.py:634-638: side effects of the reference
+        p.requires_grad_(True)
+    if not model.training:
+        model.train()
+    t_listed = [i for i in temporal if i > 0]
+    s_listed = [i for i in spatial if i > 0]
+    # derivative order actually stored under each listed key
+    t_real = {i: (k + 1 if as_written else i) for k, i in enumerate(t_listed)}
+    s_real = {i: (k + 1 if as_written else i) for k, i in enumerate(s_listed)}
+    if as_written and t_listed and t_listed[0] != 1:
+        pass                                      # (order 2 listed alone: one differentiation of u, like the spatial quirk)
+    unit = lambda i: tuple(1.0 if k == i else 0.0 for k in range(d + 1))
+    dirs, col = [], {}
+    c = 1
+    kt = max(t_real.values()) if t_real else 0
+    if kt:
+        dirs.append((unit(d), kt))
+        col["t"] = c
+        c += kt
+    spatial_live = bool(s_listed) and (d == 1 or not as_written)
+    ks = max(s_real.values()) if s_real else 0
+    if spatial_live:
+        for a in range(d):
+            dirs.append((unit(a), ks))
+            col[a] = c
+            c += ks
+    x, t = _prep(model, x, t)
+    U = jets(model, torch.cat([x, t], dim=1), dirs)
+    fact = (1.0, 1.0, 2.0, 6.0, 24.0)
+    out: Dict[str, torch.Tensor] = {}
+    for i in t_listed:
+        k = t_real[i]
+        out["dt" if i == 1 else f"dt{i}"] = U[:, col["t"] + k - 1:col["t"] + k] * fact[k]
+    if s_listed:
+        if d == 1:
+            for i in s_listed:
+                k = s_real[i]
+                out["dx" if i == 1 else f"dx{i}"] = U[:, col[0] + k - 1:col[0] + k] * fact[k]
+            if 2 in spatial:
+                out["laplacian"] = out["dx2"]
+        else:
+            zero = torch.zeros(x.shape[0], 1, dtype=torch.float32, device=x.device)
+            for a in range(d):
+                name = f"x{a + 1}"
+                for order in s_listed:
+                    for i in range(1, order + 1):          # pde_base.py:741-778: keys d<name>, d<name><name>, ...
+                        key = "d" + name * i
+                        out[key] = (U[:, col[a] + i - 1:col[a] + i] * fact[i]) if spatial_live else zero
+            if 2 in spatial:
+                lap = out["dx1x1"]
+                for a in range(1, d):
+                    lap = lap + out["d" + f"x{a + 1}" * 2]
+                out["laplacian"] = lap
+    return out
+
+
 def score_residual(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, want_abs: bool = True,
                    stats: Optional[torch.Tensor] = None):
     """Forward-only |r| [n] and stats [sum|r|, sum r^2, max|r|, count] (fp64 on device)."""
@@ -312,6 +393,12 @@ def _cached_rows(pde, key, build):
     per (device, domain, boundary functions, initial condition, sizes) instead of ~20 tiny torch launches per step -- at the
     reference's batch sizes those launches were a quarter of a step.  Nothing is stored while a CUDA graph is being captured
     (the tensors would live in the graph's private pool)."""
+    ic = getattr(getattr(pde, "config", None), "initial_condition", None)
+    if isinstance(ic, dict) and ic.get("type") == "random" and key and key[0] != "loss_weights":
+        # the `random` initial condition is amp * (2 * rand_like - 1) (pde_base.py:533-538): the reference redraws it on
+        # every compute_loss call (once per boundary_conditions entry, once for the initial term), so neither the targets
+        # nor the torch RNG stream may be frozen by a cache
+        return build()
     cache = pde.__dict__.setdefault("_pinnk_rows_cache", {})
     hit = cache.get(key)
     if hit is not None:
@@ -328,6 +415,21 @@ def _rows_key(pde, dev, *extra):
     ic = getattr(pde.config, "initial_condition", None)
     return (str(dev), repr(pde.domain), repr(pde.time_domain), tuple((k, id(f)) for k, f in pde.boundary_conditions.items()),
             repr(ic), getattr(pde, "compat", "reference")) + tuple(extra)
+
+
+def data_term_active(pde) -> bool:
+    """True when compute_loss has a data term or a non-forward training mode (pde_base.py:1150-1233): observation data
+    attached, or mode in {inverse, data_only, data_augmented}.  The fused / sharded / adaptive steps build the objective
+    from the three physics components only, so they must not be used then."""
+    mode = pde._training_mode() if hasattr(pde, "_training_mode") else "forward"
+    return bool(getattr(pde, "observation_data", None)) or mode != "forward"
+
+
+def _require_physics_only(pde, what: str):
+    if data_term_active(pde):
+        raise NotImplementedError(
+            f"{what} covers the residual / boundary / initial objective only; this PDE has observation data or a "
+            "non-forward training mode (data term, data_only gating): use compute_loss(...)['total'].backward()")
 
 
 MERGE_ALL_MAX_POINTS = 32768    # fused step: up to this many collocation rows, ALL row sets go through one pass
@@ -503,6 +605,7 @@ def loss_components_and_grads(pde, model: nn.Module, x: torch.Tensor, t: torch.T
     gets the per-component gradient norms of its LRW strategy from three extra ``backward(retain_graph=True)`` passes and then
     differentiates the weighted total a fourth time; here one reverse pass per row set fills ``G`` and any weighting is
     ``w @ G``."""
+    _require_physics_only(pde, "loss_components_and_grads (adaptive re-weighting step)")
     calls, weights = _build_calls(pde, model, x, t, n_global)
     program = calls[0][0].program
     dev = calls[0][1].device
@@ -547,6 +650,7 @@ def loss_step_flat(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_gl
     Returns (components fp32 [3] = residual, boundary, initial means; weights; flat gradient of
     ``res_scale * w_res * residual + rest_scale * (w_bc * boundary + w_ic * initial)`` in ``model.parameters()`` order).
     ``res_scale`` / ``rest_scale`` are the shard weights of the data-parallel step (parallel.py)."""
+    _require_physics_only(pde, "loss_step_flat (fused trainer step)")
     calls, weights = _build_calls(pde, model, x, t, n_global, merge_value_rows=True,
                                   merge_all_rows=x.shape[0] <= MERGE_ALL_MAX_POINTS)
     w_res, w_bc, w_ic, w_smooth, adaptive = weights

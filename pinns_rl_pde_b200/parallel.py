@@ -30,12 +30,36 @@ def shard_bounds(n: int, r: Optional[int] = None, w: Optional[int] = None) -> Tu
     return lo, lo + base + (1 if r < rem else 0)
 
 
+# Optional timing of the step's collective (bench.py: `collective_ms`): when TIMING is a list, every all-reduce of the
+# gradient buffer appends a (start, end) pair of CUDA events recorded on the current stream around it.
+TIMING: Optional[list] = None
+
+
+def _timed_all_reduce(buf: torch.Tensor, group=None):
+    if TIMING is not None and buf.is_cuda:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+        b.record()
+        TIMING.append((a, b))
+    else:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+
+
+def reduce_inplace(buf: torch.Tensor, group=None) -> torch.Tensor:
+    """All-reduce(sum) IN PLACE of a step buffer laid out [flat_grad || loss sums] (the fused step writes its three loss
+    sums into the buffer's tail, so there is no concatenation and no copy around the collective)."""
+    if world_size() > 1:
+        _timed_all_reduce(buf, group)
+    return buf
+
+
 def reduce_flat(local_flat: torch.Tensor, local_sums: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """All-reduce(sum) of [flat_grad || loss sums] in one call; returns the two views."""
     if world_size() == 1:
         return local_flat, local_sums
     buf = torch.cat([local_flat.reshape(-1), local_sums.reshape(-1).to(local_flat.dtype)])
-    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    _timed_all_reduce(buf, group)
     n = local_flat.numel()
     return buf[:n].view_as(local_flat), buf[n:].view_as(local_sums)
 
@@ -56,6 +80,8 @@ def sharded_loss_backward(pde, model: nn.Module, x: torch.Tensor, t: torch.Tenso
     functional.loss_components."""
     from . import functional as F
     comp_fn = components or F.loss_components
+    if components is None:
+        F._require_physics_only(pde, "sharded_loss_backward (data-parallel step)")
     w, r = world_size(), rank()
     if n_global is None:
         n = x.shape[0]

@@ -186,6 +186,10 @@ class PDEBase:
     def compute_loss(self, model: nn.Module, x: torch.Tensor, t: torch.Tensor) -> Dict[str, torch.Tensor]:
         return F.compute_loss(self, model, x, t)
 
+    def compute_derivatives(self, model, x, t, temporal_derivatives=None, spatial_derivatives=None):
+        """pde_base.py:590-794 -- the plugin-PDE building block (CONTRIBUTING.md:152-244): same keys, one jet pass."""
+        return F.compute_derivatives(self, model, x, t, temporal_derivatives, spatial_derivatives)
+
     def score_residual(self, model, x, t, want_abs=True):
         return F.score_residual(self, model, x, t, want_abs)
 

@@ -124,7 +124,8 @@ class TrainingConfig:
 
 class FusedAdam:
     """clip_grad_norm_ + Adam(L2 weight decay) on the flat gradient in two libpinnk launches
-    (trainer.py:690-694,292-297); state and update rule identical to ``torch.optim.Adam``."""
+    (trainer.py:690-694,292-297); state and update rule of ``torch.optim.Adam`` (bias corrections in double like
+    torch's Python-float ones; the moments and the update in fp32)."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_norm=0.0,
                  capturable: bool = False):
@@ -152,6 +153,12 @@ class FusedAdam:
 
     def step(self, flat_grad: torch.Tensor):
         C, L = self._C, self._lib
+        n = self.exp_avg.numel()
+        if not (flat_grad.is_cuda and flat_grad.dtype == torch.float32 and flat_grad.is_contiguous()
+                and flat_grad.numel() == n and flat_grad.device == self.exp_avg.device):
+            # (requires_grad flags changed after construction would otherwise make the kernel read out of bounds)
+            raise L.PinnkError(f"FusedAdam.step: flat gradient must be a contiguous float32 CUDA tensor of {n} elements "
+                               f"on {self.exp_avg.device} (got {tuple(flat_grad.shape)}, {flat_grad.dtype}, {flat_grad.device})")
         self.step_count += 1
         for i, p in enumerate(self.params):
             if not (p.is_cuda and p.is_contiguous() and p.dtype == torch.float32):
@@ -206,6 +213,7 @@ class PDETrainer:
             raise ValueError("PDETrainer(graph=True) captures the fused step: pass fused=True")
         self._graphs: Dict[tuple, dict] = {}
         lr, wd = oc.get("learning_rate", self.training.learning_rate), oc.get("weight_decay", self.training.weight_decay)
+        self._base_lr = float(lr)          # what the optimiser was really built with (optimizer_config wins, trainer.py:292-297)
         aw = self.training.adaptive_weights
         self.use_adaptive_weights = bool(aw.enabled)
         self.adaptive_weights = (AdaptiveLossWeights(aw.strategy, aw.alpha, aw.eps, aw.initial_weights)
@@ -226,7 +234,9 @@ class PDETrainer:
             self.optimizer = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=wd)
         self.scheduler = None
         self._epoch = 0
-        if self.training.scheduler == "cosine" and not self.fused and not self._is_lbfgs:
+        if self._is_lbfgs:
+            self.scheduler = self._plateau_scheduler()
+        elif self.training.scheduler == "cosine" and not self.fused:
             self.scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(
                 self.optimizer, T_max=self.training.num_epochs, eta_min=self.training.min_lr)
         self.history: Dict[str, List[float]] = {"train_loss": [], "residual_loss": [], "boundary_loss": [],
@@ -244,6 +254,14 @@ class PDETrainer:
             return self._lbfgs_step(x, t)              # (adaptive weights are disabled under L-BFGS, trainer.py:464-468)
         if self.use_adaptive_weights and self.training.mode != "data_only":
             return self._adaptive_step(x, t)
+        if self.fused and F.data_term_active(self.pde):
+            # data term / data_only gating (pde_base.py:1150-1233): the fused objective is physics-only, so these modes take
+            # compute_loss + the autograd bridge for the gradient and keep the fused clip + Adam
+            if self.graph or parallel.world_size() > 1:
+                raise NotImplementedError("observation data / non-forward training modes: use fused=True without graph, single process")
+            losses, flat = F.loss_and_flat_grad(self.pde, self.model, x, t)
+            self.optimizer.step(flat.contiguous())
+            return losses
         if self.fused:
             if self.graph and parallel.world_size() == 1:
                 return self._graph_step(x, t)
@@ -264,12 +282,20 @@ class PDETrainer:
         n_loc = x.shape[0]
         n_all = n_loc if n_global is None else int(n_global)
         frac = n_loc / max(n_all, 1) if w > 1 else 1.0
+        # one step buffer [flat gradient || residual, boundary, initial sums || pad]: the reverse pass accumulates into
+        # its head, the loss sums land in its tail, and the data-parallel step all-reduces it in place (no concatenation)
+        P = F.get_program(self.model).grad_floats
+        if self._flat is None or self._flat.numel() != P + 4:
+            self._flat = torch.zeros(P + 4, dtype=torch.float32, device=x.device if x.is_cuda else self.device)
+        buf = self._flat
         comp, (w_res, w_bc, w_ic), flat = F.loss_step_flat(self.pde, self.model, x, t, n_global=n_all, res_scale=frac,
-                                                           rest_scale=1.0 / w, flat=self._flat)
-        self._flat = flat
-        sums = torch.stack([frac * comp[0], comp[1] / w, comp[2] / w])
+                                                           rest_scale=1.0 / w, flat=buf[:P])
         if w > 1:
-            flat, sums = parallel.reduce_flat(flat, sums)
+            buf[P:P + 3].copy_(comp * comp.new_tensor([frac, 1.0 / w, 1.0 / w]))
+            parallel.reduce_inplace(buf)
+            sums = buf[P:P + 3]
+        else:
+            sums = comp
         self.optimizer.step(flat)
         zero = torch.zeros((), device=flat.device)
         return {"residual": sums[0], "boundary": sums[1], "initial": sums[2], "smoothness": zero, "data": zero.clone(),
@@ -320,8 +346,16 @@ class PDETrainer:
 
     def switch_to_lbfgs(self):
         """trainer.py:366-371: second phase of ``adam_lbfgs`` (the fused / graph Adam step hands over to the closure route)."""
-        self.optimizer = self._build_lbfgs(self.training.learning_rate)
-        self._is_lbfgs, self.fused, self.graph, self.scheduler = True, False, False, None
+        self.optimizer = self._build_lbfgs(self._base_lr)
+        self._is_lbfgs, self.fused, self.graph = True, False, False
+        self.scheduler = self._plateau_scheduler()
+
+    def _plateau_scheduler(self):
+        """trainer.py:311-325: L-BFGS has its own line search, so the reference overrides whatever scheduler is configured
+        with ReduceLROnPlateau (factor / patience / min_lr of the scheduler config), stepped on the epoch's mean loss."""
+        t = self.training
+        return torch.optim.lr_scheduler.ReduceLROnPlateau(self.optimizer, mode="min", factor=getattr(t, "lr_factor", 0.5),
+                                                          patience=getattr(t, "lr_patience", 10), min_lr=t.min_lr)
 
     def _lbfgs_step(self, x, t):
         """trainer.py:373-389: one L-BFGS step; the closure re-evaluates compute_loss + backward on libpinnk as often as the
@@ -438,7 +472,7 @@ class PDETrainer:
 
     def cosine_lr(self, epoch: int) -> float:
         t = self.training
-        return t.min_lr + 0.5 * (t.learning_rate - t.min_lr) * (1 + __import__("math").cos(__import__("math").pi * epoch / max(t.num_epochs, 1)))
+        return t.min_lr + 0.5 * (self._base_lr - t.min_lr) * (1 + __import__("math").cos(__import__("math").pi * epoch / max(t.num_epochs, 1)))
 
     def train(self, num_epochs: int, batch_size: int, num_points: int, experiment_dir: str = None):
         self.model.train()
@@ -452,7 +486,10 @@ class PDETrainer:
                 x, t = self.pde.generate_collocation_points(batch_size, strategy=strategy, **kw)
                 losses = self.train_step(x.to(self.device), t.to(self.device))
                 epoch.append({k: float(v.item()) for k, v in losses.items() if k in ("total", "residual", "boundary", "initial")})
-            if self.scheduler is not None:
+            if isinstance(self.scheduler, torch.optim.lr_scheduler.ReduceLROnPlateau):
+                if epoch:
+                    self.scheduler.step(sum(e["total"] for e in epoch) / len(epoch))      # trainer.py:164-169
+            elif self.scheduler is not None:
                 self.scheduler.step()
             elif self.fused and self.training.scheduler == "cosine":
                 self._epoch += 1
