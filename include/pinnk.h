@@ -205,6 +205,15 @@ int pinnk_debug_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t
                              int32_t mode, void* stream);
 int pinnk_debug_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int32_t K, int32_t N,
                              int32_t jet_cols, int32_t mode, void* stream);
+/* Reverse pass of ONE hidden Linear(128, 128) fed by a tanh layer, on raw tensors (the per-layer step of
+ * loss["total"].backward(), trainer.py:689): dZprev[M,128] = tanh'(.)^T (dZ[M,128] W[128,128]) with the tanh adjoint taken
+ * from the previous layer's OUTPUT jets Yprev[M,128]; dW[128,128] += dZ^T Yprev; db[128] += value-column rows of dZ.
+ * (k0, k1): jet orders of the (at most two) directions, 1 + k0 + k1 in {1, 2, 4}.  _pair: one launch of CTA pairs sharing the
+ * tile stream (bwd_pair_kernel); _split: the dgrad + adjoint kernel and the wgrad kernel as two launches. */
+int pinnk_debug_bwd_pair(const float* dZ, const float* W, const float* Yprev, float* dZprev, float* dW, float* db,
+                         int64_t M, int32_t k0, int32_t k1, void* stream);
+int pinnk_debug_bwd_split(const float* dZ, const float* W, const float* Yprev, float* dZprev, float* dW, float* db,
+                          int64_t M, int32_t k0, int32_t k1, void* stream);
 
 /* Builder tool: cycles block 0 of the tcgen05 rows kernels spent waiting on each pipeline barrier, accumulated since the
  * last reset (which: 0 = forward rows kernels, 1 = reverse rows kernels, 2 = wgrad; out16: 16 counters, see csrc/tc_gemm.cuh).

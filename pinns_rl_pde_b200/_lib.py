@@ -49,7 +49,7 @@ EXPORTS = ["pinnk_plan_create", "pinnk_plan_destroy", "pinnk_plan_workspace_byte
            "pinnk_last_error", "pinnk_abi_version", "pinnk_launch_count", "pinnk_prof_enable", "pinnk_prof_classes",
            "pinnk_prof_class_name", "pinnk_prof_collect", "pinnk_debug_linear_fwd",
            "pinnk_debug_linear_dgrad", "pinnk_debug_linear_wgrad", "pinnk_adam_step", "pinnk_adam_step_dev", "pinnk_dqn_forward",
-           "pinnk_debug_stage_timers"]
+           "pinnk_debug_stage_timers", "pinnk_debug_bwd_pair", "pinnk_debug_bwd_split"]
 
 _lib = None
 
@@ -116,6 +116,9 @@ def load():
     lib.pinnk_debug_linear_dgrad.restype = C.c_int
     lib.pinnk_debug_linear_wgrad.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]
     lib.pinnk_debug_linear_wgrad.restype = C.c_int
+    for fn in (lib.pinnk_debug_bwd_pair, lib.pinnk_debug_bwd_split):
+        fn.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]
+        fn.restype = C.c_int
     lib.pinnk_debug_stage_timers.argtypes = [i32, C.POINTER(C.c_uint64), i32]
     lib.pinnk_debug_stage_timers.restype = C.c_int
     if lib.pinnk_abi_version() != ABI_VERSION:
@@ -182,6 +185,20 @@ def debug_linear_wgrad(dZ, X, jet_cols: int, mode: int):
     check(lib.pinnk_debug_linear_wgrad(dZ.data_ptr(), X.data_ptr(), dW.data_ptr(), db.data_ptr(), M, K, N, jet_cols, mode,
                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pinnk_debug_linear_wgrad")
     return dW, db
+
+
+def debug_bwd_layer(dZ, W, Yprev, k0: int, k1: int, pair: bool):
+    """(dZprev, dW, db) of one hidden Linear(128, 128) + tanh reverse step: the paired kernel or the two-launch route."""
+    import torch
+    lib = load()
+    M = dZ.shape[0]
+    dZp = torch.empty(M, 128, dtype=torch.float32, device=dZ.device)
+    dW = torch.zeros(128, 128, dtype=torch.float32, device=dZ.device)
+    db = torch.zeros(128, dtype=torch.float32, device=dZ.device)
+    fn = lib.pinnk_debug_bwd_pair if pair else lib.pinnk_debug_bwd_split
+    check(fn(dZ.data_ptr(), W.data_ptr(), Yprev.data_ptr(), dZp.data_ptr(), dW.data_ptr(), db.data_ptr(), M, k0, k1,
+             C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pinnk_debug_bwd_pair" if pair else "pinnk_debug_bwd_split")
+    return dZp, dW, db
 
 
 def stage_timers(which: int, reset: bool = True):

@@ -33,10 +33,10 @@ static std::atomic<int64_t> g_launches{0};
 
 // ---- optional per-kernel-class timing (bench.py roofline): CUDA event pairs on the launching stream
 enum ProfClass { PC_FIRST_FWD = 0, PC_GEMM_FWD, PC_ACT_FWD, PC_LN_FWD, PC_LAST_FWD, PC_EPILOGUE, PC_LAST_BWD,
-                 PC_ACT_BWD, PC_LN_BWD, PC_GEMM_DGRAD, PC_GEMM_WGRAD, PC_FIRST_BWD, PC_MISC, PC_FWD_LOSS, PC_COUNT };
+                 PC_ACT_BWD, PC_LN_BWD, PC_GEMM_DGRAD, PC_GEMM_WGRAD, PC_FIRST_BWD, PC_MISC, PC_FWD_LOSS, PC_BWD_PAIR, PC_COUNT };
 static const char* kProfNames[PC_COUNT] = {"first_linear_fwd", "gemm_fwd", "act_fwd", "layernorm_fwd", "last_linear_fwd",
                                            "epilogue", "last_linear_bwd", "act_bwd", "layernorm_bwd", "gemm_dgrad",
-                                           "gemm_wgrad", "first_linear_bwd", "misc", "fwd_loss_fused"};
+                                           "gemm_wgrad", "first_linear_bwd", "misc", "fwd_loss_fused", "bwd_pair"};
 struct ProfRec { int cls; cudaEvent_t a, b; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
@@ -450,6 +450,12 @@ static bool first_fuse_enabled() {
   return v == 1 && tc_enabled();
 }
 
+// PINNK_DISABLE_PAIR=1: dgrad + adjoint and wgrad of a hidden layer as two launches (A/B checks of the paired kernel)
+static bool pair_enabled() {
+  const char* e = getenv("PINNK_DISABLE_PAIR");           // read per call: tests switch it
+  return !(e && e[0] == '1') && tc_enabled();
+}
+
 static int first_trainable_op(const pinnk_plan_t pl) {
   const int n_ops = (int)pl->ops.size();
   for (int i = 0; i < n_ops; ++i)
@@ -677,6 +683,22 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad, bool last_done = 
           first_linear_bwd_kernel<<<grid, 128, 0, c.st>>>(c.x, c.t, c.n, o.out_dim, js, c.adj(cur), G(o.gw_offset), G(o.gb_offset));
           PK_LAUNCH_OK();
         } else {
+          // Linear(128, 128) fed by a plain tanh whose output jets are stashed: dgrad + tanh adjoint and the weight gradient in
+          // ONE launch of CTA pairs sharing the tile stream (bwd_pair_kernel): dZ and Y come out of HBM once, not twice
+          if (i > first_trainable && pair_enabled() && !deterministic_enabled() && o.in_dim == 128 && o.out_dim == 128 &&
+              o.gw_offset >= 0 && r.in_op == i - 1 && pl->ops[i - 1].op.kind == PINNK_OP_ACT && pl->ops[i - 1].skip_src < 0 &&
+              pl->ops[i - 1].in_op >= 0 && !(pl->fuse_first && i - 1 == 1 && first_trainable == 0) &&
+              z_elided(pl, pl->ops[i - 1].in_op)) {
+            int pk0 = 0, pk1 = 0;
+            if (jet_orders(js, pk0, pk1)) {
+              ProfScope ps(PC_BWD_PAIR, c.st);
+              const int nxt = other(cur, held);
+              int prc = tc_bwd_pair(c.adj(cur), W, c.stash(i - 1), c.adj(nxt), G(o.gw_offset), G(o.gb_offset), c.n * js.ncols,
+                                    o.in_dim, o.out_dim, pk0, pk1, pl->sm_count, c.st);
+              if (prc == 0) { g_launches.fetch_add(1); cur = nxt; --i; break; }
+              if (prc != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, std::string("tc_bwd_pair launch failed: ") + cudaGetErrorString(cudaGetLastError()));
+            }
+          }
           // (the adjoint buffer the dgrad below will write is idle during the wgrad: scratch of the deterministic reduction)
           int rc = gemm_wgrad(c, c.adj(cur), in, G(o.gw_offset), G(o.gb_offset), o.in_dim, o.out_dim, c.adj(other(cur, held)));
           if (rc) return rc;
@@ -1059,6 +1081,35 @@ extern "C" int pinnk_debug_linear_wgrad(const float* dZ, const float* X, float* 
     bias_grad_kernel<<<g2, 128, 0, st>>>(dZ, M / jet_cols, N, jet_cols, db);
     PK_LAUNCH_OK();
   }
+  return 0;
+}
+
+// ---- debug / micro-benchmark entry: the paired reverse kernel of one Linear(128, 128) + tanh on raw tensors:
+// dZprev = tanh'(from Yprev)^T (dZ W), dW += dZ^T Yprev, db += value rows of dZ  (k0, k1 = jet orders; 1 + k0 + k1 in {1, 2, 4})
+extern "C" int pinnk_debug_bwd_pair(const float* dZ, const float* W, const float* Yprev, float* dZprev, float* dW, float* db,
+                                    int64_t M, int32_t k0, int32_t k1, void* stream) {
+  if (!dZ || !W || !Yprev || !dZprev || !dW || M < 1) return fail(PINNK_E_INVALID, "debug_bwd_pair: bad argument");
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int rc = tc_bwd_pair(dZ, W, Yprev, dZprev, dW, db, M, 128, 128, k0, k1, sm_count_of(dev), (cudaStream_t)stream);
+  if (rc == TC_UNSUPPORTED) return fail(PINNK_E_INVALID, "debug_bwd_pair: shape / jet layout not covered by the paired kernel");
+  if (rc != 0) return fail(PINNK_E_CUDA, std::string("tc_bwd_pair: ") + cudaGetErrorString(cudaGetLastError()));
+  g_launches.fetch_add(1);
+  return 0;
+}
+
+// the two-launch route on the same raw tensors (reference for the paired kernel): tc_linear_dgrad_actbwd(from_y) + tc_linear_wgrad
+extern "C" int pinnk_debug_bwd_split(const float* dZ, const float* W, const float* Yprev, float* dZprev, float* dW, float* db,
+                                     int64_t M, int32_t k0, int32_t k1, void* stream) {
+  if (!dZ || !W || !Yprev || !dZprev || !dW || M < 1) return fail(PINNK_E_INVALID, "debug_bwd_split: bad argument");
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int smc = sm_count_of(dev);
+  int rc = tc_linear_wgrad(dZ, Yprev, dW, db, M, 128, 128, 1 + k0 + k1, smc, (cudaStream_t)stream);
+  if (rc == 0) rc = tc_linear_dgrad_actbwd(dZ, W, Yprev, dZprev, M, 128, 128, k0, k1, 1, 1.f, smc, (cudaStream_t)stream, 1);
+  if (rc == TC_UNSUPPORTED) return fail(PINNK_E_INVALID, "debug_bwd_split: shape / jet layout not covered");
+  if (rc != 0) return fail(PINNK_E_CUDA, std::string("debug_bwd_split: ") + cudaGetErrorString(cudaGetLastError()));
+  g_launches.fetch_add(2);
   return 0;
 }
 

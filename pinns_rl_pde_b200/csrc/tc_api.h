@@ -65,6 +65,10 @@ int tc_dgrad_actbwd_y(int k0, int k1, const float* dZ, const float* W, int in_di
 // >= 16640 per 128 x 128 block), added in CTA order by a second kernel instead of atomics in arrival order
 int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
                     int jet_cols, int sm_count, cudaStream_t st, float* det_scratch = nullptr, int64_t det_floats = 0);
+// dgrad + tanh adjoint (from the previous layer's OUTPUT jets) and wgrad of one Linear(128, 128) in ONE launch of CTA pairs
+// sharing a tile stream (bwd_pair_kernel): 1536 B of HBM traffic per row instead of 2560
+int tc_bwd_pair(const float* dZ, const float* W, const float* Yprev, float* dZprev, float* dW, float* db, int64_t M, int in_dim,
+                int out_dim, int k0, int k1, int sm_count, cudaStream_t st);
 // stage timers of the rows kernels (zeros unless built with -DPINNK_STAGE_TIMERS); 0 ok, 1 not compiled in
 int tc_stage_timers_fwd(unsigned long long* out16, int reset);
 int tc_stage_timers_bwd(unsigned long long* out16, int reset);

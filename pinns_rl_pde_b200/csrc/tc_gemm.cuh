@@ -551,6 +551,44 @@ static inline bool make_tmap_rows(CUtensorMap* tm, const float* base, int64_t ro
             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// ---- thread-block cluster helpers (the paired reverse kernel: one CTA pair per tile stream)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_smem_addr` in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+// Lock-step throttle between the two CTAs of a pair that walk the SAME tile stream (one does dgrad + adjoint, the other
+// wgrad): each publishes the number of macro tiles whose loads it has issued into the partner's shared memory (DSMEM
+// store) and never runs more than kPairLead macro tiles ahead of the partner, so that the second reader of a tile finds
+// it in L2 -- the tile pair (dZ, Y) comes out of HBM once instead of twice.
+constexpr uint32_t kPairLead = 4;
+struct PairSync {
+  uint32_t my_word = 0;        // local shared address of the word the PARTNER writes (its issued macro tiles)
+  uint32_t peer_word = 0;      // shared::cluster address of the partner's word (where this CTA publishes)
+  __device__ __forceinline__ void wait_turn(uint32_t n) const {      // before issuing the loads of macro tile n
+    if (n < kPairLead) return;
+    for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
+      uint32_t v;
+      asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(my_word) : "memory");
+      if (v + kPairLead > n) return;
+      __nanosleep(40);
+    }
+    __trap();
+  }
+  __device__ __forceinline__ void publish(uint32_t issued) const {
+    asm volatile("st.relaxed.cluster.shared::cluster.u32 [%0], %1;" ::"r"(peer_word), "r"(issued) : "memory");
+  }
+};
+
 // Optional stage timers (build with -DPINNK_STAGE_TIMERS): block 0 accumulates, per role, the cycles spent waiting on
 // each pipeline barrier; read back with pinnk_debug_stage_timers().  Slots: 0 tma:raw_empty  1 cvt:raw_full  2 cvt:empty
 // 3 cvt:work  4 mma:tempty  5 mma:full  6 mma:issue  7 epi:tfull  8 epi:work  9 tiles  10 total cycles of block 0
@@ -611,12 +649,16 @@ struct OutFuse {
   float* u_part = nullptr;
 };
 
-template <bool TRANS_W, int EPI, int ACT, int K0, int K1, int NLW, int ECOLS, bool ACCUM, int LDYC, bool LOSSF = false>
-__global__ void __launch_bounds__((NLW + 4 * (64 / ECOLS) + 2) * 32, 1)
-linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
-                      float* __restrict__ Y, int64_t M, int ldy_rt, int jet_cols, const float* __restrict__ Zs,
-                      float* __restrict__ Yact, float omega, int ldx, OutFuse of, FirstLayer fl,
-                      TcLossFuse lfv, const __grid_constant__ CUtensorMap tmx) {
+// (body of linear_rows_ts_kernel; cta_x / ncta_x / cta_y are the block index / grid size the kernel passes in, so that the
+// paired reverse kernel can run it on one CTA of each cluster with the pair index; PAIR adds the lock-step throttle to the
+// TMA warp)
+template <bool TRANS_W, int EPI, int ACT, int K0, int K1, int NLW, int ECOLS, bool ACCUM, int LDYC, bool LOSSF = false, bool PAIR = false>
+__device__ __forceinline__ void
+linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
+                    float* __restrict__ Y, int64_t M, int ldy_rt, int jet_cols, const float* __restrict__ Zs,
+                    float* __restrict__ Yact, float omega, int ldx, const OutFuse& of, const FirstLayer& fl,
+                    const TcLossFuse& lfv, const CUtensorMap* tmxp, const int cta_x, const int ncta_x, const int cta_y,
+                    const PairSync ps) {
   static_assert(!LOSSF || (EPI == EPI_ACT && ACT == 1 && ECOLS == 16 && !ACCUM), "loss fusion: tanh forward epilogue only");
   // LDYC: compile-time row stride of Y / Zs / Yact (0 = use the runtime value): with it every row address of the
   // epilogue is base + immediate instead of a 64-bit multiply-add per access
@@ -658,7 +700,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
   unsigned long long g_entry; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_entry));
 #endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.y * 128;
+  const int n0 = cta_y * 128;
   const int64_t ntiles = (M + TNE - 1) / TNE;
 
   if (threadIdx.x == 0) {
@@ -709,10 +751,11 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
       const uint32_t rb = smem_u32(raw_st);
       long long t_a = 0; (void)t_a;
       int it = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      for (int64_t tile = cta_x; tile < ntiles; tile += ncta_x, ++it) {
         const int s = it % RS;
         const uint32_t ph = (uint32_t)(it / RS) & 1u;
         { PK_T0(); mbar_wait(&raw_empty[s], ph ^ 1u); PK_TACC(t_a); }
+        if constexpr (PAIR) ps.wait_turn((uint32_t)it);
         const int64_t r0 = tile * TNE;
         const uint32_t nrows = (M - r0 >= TNE) ? TNE : (uint32_t)(M - r0);
         const uint32_t dst = rb + (uint32_t)s * RAW_BYTES;
@@ -721,11 +764,13 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
           tma_bulk_g2s(dst, X + r0 * K, nrows * (uint32_t)(K * 4), &raw_full[s]);
         } else {          // one K half of a wider matrix: tiled copy, box = [TNE rows x 128] (rows past M arrive as zeros)
           mbar_arrive_expect_tx(&raw_full[s], (uint32_t)TNE * (uint32_t)(K * 4));
-          tma_tile_2d(dst, &tmx, 0, (int)r0, &raw_full[s]);
+          tma_tile_2d(dst, tmxp, 0, (int)r0, &raw_full[s]);
         }
+        if constexpr (PAIR) ps.publish((uint32_t)it + 1u);
       }
+      if constexpr (PAIR) ps.publish(0x7fffffffu);        // done: never hold the partner back
 #ifdef PINNK_STAGE_TIMERS
-      if (blockIdx.x == 0 && blockIdx.y == 0) atomicAdd(&g_stage_timers[0], (unsigned long long)t_a);
+      if (cta_x == 0 && cta_y == 0) atomicAdd(&g_stage_timers[0], (unsigned long long)t_a);
 #endif
     }
     __syncwarp();
@@ -735,7 +780,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
     const uint32_t x_base = smem_u32(x_st), rb = smem_u32(raw_st);
     long long t_a = 0, t_b = 0, t_c = 0; (void)t_a; (void)t_b; (void)t_c;
     int it = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    for (int64_t tile = cta_x; tile < ntiles; tile += ncta_x, ++it) {
       const int rs = it % RS, s = it % STAGES;
       const uint32_t rph = (uint32_t)(it / RS) & 1u, ph = (uint32_t)(it / STAGES) & 1u;
       const int64_t r0 = tile * TNE;
@@ -772,7 +817,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
 #endif
     }
 #ifdef PINNK_STAGE_TIMERS
-    if (blockIdx.x == 0 && blockIdx.y == 0 && warp == 0 && lane == 0) {
+    if (cta_x == 0 && cta_y == 0 && warp == 0 && lane == 0) {
       atomicAdd(&g_stage_timers[1], (unsigned long long)t_a); atomicAdd(&g_stage_timers[2], (unsigned long long)t_b);
       atomicAdd(&g_stage_timers[3], (unsigned long long)t_c);
     }
@@ -1037,7 +1082,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
             const int rj = lane / (32 / ECOLS);
             if constexpr (!LOSSF) {
               if ((lane % (32 / ECOLS)) == 0 && rj < ECE && (FULL || rj < nrows))
-                of.u_part[(int64_t)(blockIdx.y * 4 + q) * M + r0 + rj] = acc[0];
+                of.u_part[(int64_t)(cta_y * 4 + q) * M + r0 + rj] = acc[0];
             } else {
               // ---- output jets of the tile through shared memory (fixed summation order over the four lane quarters)
               const TcLossFuse& lf = lfv;
@@ -1112,7 +1157,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
       PK_TACC(t_eb);
     };
     int it = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    for (int64_t tile = cta_x; tile < ntiles; tile += ncta_x, ++it) {
       const int b = it % ACC;
       const uint32_t ph = (uint32_t)(it / ACC) & 1u;
       const int64_t r0 = tile * TNE + h * ECE;
@@ -1142,7 +1187,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
       if (fl.gb0) atomicAdd(fl.gb0 + n0 + f, ab0);
     }
 #ifdef PINNK_STAGE_TIMERS
-    if (blockIdx.x == 0 && blockIdx.y == 0 && e == 0 && lane == 0) {
+    if (cta_x == 0 && cta_y == 0 && e == 0 && lane == 0) {
       atomicAdd(&g_stage_timers[7], (unsigned long long)t_ea); atomicAdd(&g_stage_timers[8], (unsigned long long)t_eb);
     }
 #endif
@@ -1158,7 +1203,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
       unsigned long long g_start; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_start));
 #endif
       int it = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      for (int64_t tile = cta_x; tile < ntiles; tile += ncta_x, ++it) {
         const int s = it % STAGES, b = it % ACC;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u, bph = (uint32_t)(it / ACC) & 1u;
         { PK_T0(); mbar_wait(&tempty[b], bph ^ 1u); PK_TACC(t_a); }
@@ -1186,7 +1231,7 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
         unsigned long long g_e2; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_e2));
         atomicMax(&g_stage_timers[15], g_e2 - g_start);
       }
-      if (blockIdx.x == 0 && blockIdx.y == 0) {
+      if (cta_x == 0 && cta_y == 0) {
         atomicAdd(&g_stage_timers[4], (unsigned long long)t_a); atomicAdd(&g_stage_timers[5], (unsigned long long)t_b);
         atomicAdd(&g_stage_timers[6], (unsigned long long)t_c); atomicAdd(&g_stage_timers[9], (unsigned long long)n_t);
         atomicAdd(&g_stage_timers[10], (unsigned long long)(clock64() - t_start));
@@ -1204,13 +1249,24 @@ linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, 
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
 #ifdef PINNK_STAGE_TIMERS
-    if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) {
+    if (cta_x == 0 && cta_y == 0 && lane == 0) {
       unsigned long long g_exit; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_exit));
       atomicAdd(&g_stage_timers[13], g_exit - g_entry);         // whole kernel, block 0
       atomicAdd(&g_stage_timers[14], 1ull);
     }
 #endif
   }
+}
+
+template <bool TRANS_W, int EPI, int ACT, int K0, int K1, int NLW, int ECOLS, bool ACCUM, int LDYC, bool LOSSF = false>
+__global__ void __launch_bounds__((NLW + 4 * (64 / ECOLS) + 2) * 32, 1)
+linear_rows_ts_kernel(const float* __restrict__ X, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
+                      float* __restrict__ Y, int64_t M, int ldy_rt, int jet_cols, const float* __restrict__ Zs,
+                      float* __restrict__ Yact, float omega, int ldx, OutFuse of, FirstLayer fl,
+                      TcLossFuse lfv, const __grid_constant__ CUtensorMap tmx) {
+  linear_rows_ts_body<TRANS_W, EPI, ACT, K0, K1, NLW, ECOLS, ACCUM, LDYC, LOSSF, false>(
+      X, W, ldw, bias, Y, M, ldy_rt, jet_cols, Zs, Yact, omega, ldx, of, fl, lfv, &tmx, (int)blockIdx.x, (int)gridDim.x,
+      (int)blockIdx.y, PairSync{});
 }
 
 template <bool TRANS_W, int EPI, int ACT, int K0, int K1, bool ACCUM, int LDYC, bool LOSSF = false>
@@ -1280,11 +1336,15 @@ static int launch_linear_rows_ts(const float* X, const float* W, int ldw, const 
 // "main" TMEM accumulators (hi*hi products), while four flush warps fold the finished segment into a running fp32 sum
 // (kept in TMEM, added in registers with round-to-nearest).  The tiny lo*hi + hi*lo corrections accumulate in their own
 // TMEM region for the whole kernel.   TMEM: [0,128) main0 | [128,256) main1 | [256,384) corr | [384,512) sum
-template <int TK, int RS, int OS, int NCW, int SEG, bool TSA>
-__global__ void __launch_bounds__((NCW + 8) * 32, 1)
-wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, int ldx, float* __restrict__ dW, int lddw,
-             float* __restrict__ db, int64_t M, int jet_cols, int in_blocks, const __grid_constant__ CUtensorMap tmg,
-             const __grid_constant__ CUtensorMap tmxm, float* __restrict__ det_part, float* __restrict__ det_bpart) {
+// (body of wgrad_kernel; cta_x / ncta_x / cta_y as in linear_rows_ts_body.  PAIR: the CTA is the wgrad half of a reverse-pass
+// pair and walks the 64-row macro tiles of its partner -- 32-row tiles 2T, 2T+1 for T = cta_x, cta_x + ncta_x, ... -- with the
+// lock-step throttle in its TMA warp)
+template <int TK, int RS, int OS, int NCW, int SEG, bool TSA, bool PAIR = false>
+__device__ __forceinline__ void
+wgrad_body(const float* __restrict__ G, int ldg, const float* __restrict__ X, int ldx, float* __restrict__ dW, int lddw,
+           float* __restrict__ db, int64_t M, int jet_cols, int in_blocks, const CUtensorMap* tmgp, const CUtensorMap* tmxmp,
+           float* __restrict__ det_part, float* __restrict__ det_bpart, const int cta_x, const int ncta_x, const int cta_y,
+           const PairSync ps) {
   // det_part != null (PINNK_DETERMINISTIC=1): every CTA stores its 128 x 128 partial sum to its own slab
   // det_part[(blockIdx.y * gridDim.x + blockIdx.x) * 16384] (and its bias partials to det_bpart[cta][2][128]) instead of
   // reducing into dW / db with atomics in arrival order; wgrad_det_reduce_kernel then adds the slabs in CTA order, so the
@@ -1321,9 +1381,22 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
   unsigned long long g_entry; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_entry));
 #endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int o0 = (blockIdx.y / in_blocks) * 128, i0 = (blockIdx.y % in_blocks) * 128;
+  const int o0 = (cta_y / in_blocks) * 128, i0 = (cta_y % in_blocks) * 128;
   const int64_t ntiles = (M + TK - 1) / TK;
-  const int64_t my_tiles = (ntiles > (int64_t)blockIdx.x) ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  // tile handled in iteration `it` of this CTA, and how many it handles
+  auto tile_at = [&](int64_t it) -> int64_t {
+    if constexpr (PAIR) return 2 * ((int64_t)cta_x + (it >> 1) * ncta_x) + (it & 1);
+    else return (int64_t)cta_x + it * ncta_x;
+  };
+  int64_t my_tiles;
+  if constexpr (PAIR) {
+    const int64_t nmac = (ntiles + 1) / 2;
+    const int64_t my_mac = (nmac > (int64_t)cta_x) ? (nmac - cta_x + ncta_x - 1) / ncta_x : 0;
+    my_tiles = 2 * my_mac;
+    if (my_mac > 0 && 2 * ((int64_t)cta_x + (my_mac - 1) * ncta_x) + 1 >= ntiles) --my_tiles;     // odd tail
+  } else {
+    my_tiles = (ntiles > (int64_t)cta_x) ? (ntiles - cta_x + ncta_x - 1) / ncta_x : 0;
+  }
   const int64_t my_segs = (my_tiles + SEG - 1) / SEG;
 
   if (threadIdx.x == 0) {
@@ -1343,11 +1416,12 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
     if (elect_one()) {
       const uint32_t rb = smem_u32(raw_base);
       long long t_a = 0; (void)t_a;
-      int it = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int s = it % RS;
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const int64_t tile = tile_at(it);
+        const int s = (int)(it % RS);
         const uint32_t ph = (uint32_t)(it / RS) & 1u;
         { PK_T0(); mbar_wait(&raw_empty[s], ph ^ 1u); PK_TACC(t_a); }
+        if constexpr (PAIR) { if ((it & 1) == 0) ps.wait_turn((uint32_t)(it >> 1)); }
         const int64_t r0 = tile * TK;
         const int nrows = (M - r0 >= TK) ? TK : (int)(M - r0);
         const uint32_t dg = rb + (uint32_t)s * 2 * RAW_BYTES, dx = dg + RAW_BYTES;
@@ -1355,12 +1429,14 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
         // rows past M arrive as zeros and count in the transaction bytes)
         mbar_arrive_expect_tx(&raw_full[s], (uint32_t)(ldg == 128 ? nrows : TK) * 512u + (uint32_t)(ldx == 128 ? nrows : TK) * 512u);
         if (ldg == 128) tma_bulk_g2s(dg, G + r0 * 128, (uint32_t)nrows * 512u, &raw_full[s]);
-        else tma_tile_2d(dg, &tmg, o0, (int)r0, &raw_full[s]);
+        else tma_tile_2d(dg, tmgp, o0, (int)r0, &raw_full[s]);
         if (ldx == 128) tma_bulk_g2s(dx, X + r0 * 128, (uint32_t)nrows * 512u, &raw_full[s]);
-        else tma_tile_2d(dx, &tmxm, i0, (int)r0, &raw_full[s]);
+        else tma_tile_2d(dx, tmxmp, i0, (int)r0, &raw_full[s]);
+        if constexpr (PAIR) { if (it & 1) ps.publish((uint32_t)(it >> 1) + 1u); }
       }
+      if constexpr (PAIR) ps.publish(0x7fffffffu);        // done: never hold the partner back
 #ifdef PINNK_STAGE_TIMERS
-      if (blockIdx.x == 0 && blockIdx.y == 0) atomicAdd(&g_stage_timers[0], (unsigned long long)t_a);
+      if (cta_x == 0 && cta_y == 0) atomicAdd(&g_stage_timers[0], (unsigned long long)t_a);
 #endif
     }
     __syncwarp();
@@ -1383,7 +1459,8 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
       const uint32_t a_lane = tmem_base + ((uint32_t)(q * 32) << 16) + COL_A + (uint32_t)(h * 16);
       int rs = 0, os = 0;
       uint32_t rph = 0, oph = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const int64_t tile = tile_at(it);
         const int64_t r0 = tile * TK;
         const int nrows = (M - r0 >= TK) ? TK : (int)(M - r0);
         mbar_wait(&raw_full[rs], rph);
@@ -1426,7 +1503,7 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
         if (++os == OS) { os = 0; oph ^= 1u; }
       }
       if (want_b1) {
-        if (det_bpart) det_bpart[((int64_t)(blockIdx.y * gridDim.x + blockIdx.x) * 2 + h) * 128 + f] = bsum1;
+        if (det_bpart) det_bpart[((int64_t)(cta_y * ncta_x + cta_x) * 2 + h) * 128 + f] = bsum1;
         else atomicAdd(db + o0 + f, bsum1);
       }
     } else {
@@ -1445,7 +1522,8 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
     long long t_a = 0, t_b = 0, t_c = 0; (void)t_a; (void)t_b; (void)t_c;
     int rs = 0, os = 0;
     uint32_t rph = 0, oph = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t it = 0; it < my_tiles; ++it) {
+      const int64_t tile = tile_at(it);
       const int64_t r0 = tile * TK;
       const int nrows = (M - r0 >= TK) ? TK : (int)(M - r0);
       { PK_T0(); mbar_wait(&raw_full[rs], rph); PK_TACC(t_a); }
@@ -1505,7 +1583,7 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
       if (++os == OS) { os = 0; oph ^= 1u; }
     }
 #ifdef PINNK_STAGE_TIMERS
-    if (blockIdx.x == 0 && blockIdx.y == 0 && warp == 0 && lane == 0) {
+    if (cta_x == 0 && cta_y == 0 && warp == 0 && lane == 0) {
       atomicAdd(&g_stage_timers[1], (unsigned long long)t_a); atomicAdd(&g_stage_timers[2], (unsigned long long)t_b);
       atomicAdd(&g_stage_timers[3], (unsigned long long)t_c);
     }
@@ -1557,7 +1635,7 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
       const int t = threadIdx.x - EPI0 * 32;
       float* const dw0 = dW + (int64_t)o0 * lddw + i0;
       if (det_part != nullptr) {
-        float4* const slab = reinterpret_cast<float4*>(det_part + (int64_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16384);
+        float4* const slab = reinterpret_cast<float4*>(det_part + (int64_t)(cta_y * ncta_x + cta_x) * 16384);
         for (int idx = t; idx < 128 * 32; idx += kEpiThreads)
           slab[idx] = *reinterpret_cast<const float4*>(tr + (idx >> 5) * 132 + (idx & 31) * 4);
       } else if (((reinterpret_cast<uintptr_t>(dw0) & 15) == 0) && (lddw & 3) == 0) {
@@ -1586,11 +1664,10 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
 #ifdef PINNK_STAGE_TIMERS
       unsigned long long g_start; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_start));
 #endif
-      int it = 0;
       int64_t seg = 0;
       int in_seg = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int s = it % OS;
+      for (int64_t it = 0; it < my_tiles; ++it) {
+        const int s = (int)(it % OS);
         const uint32_t ph = (uint32_t)(it / OS) & 1u;
         const int b = (int)(seg & 1);
         if (in_seg == 0) { PK_T0(); mbar_wait(&tempty[b], ((uint32_t)(seg >> 1) & 1u) ^ 1u); PK_TACC(t_a); }    // previous use of this buffer flushed
@@ -1617,7 +1694,7 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
           }
         }
         umma_commit(&empty[s]);
-        if (++in_seg == SEG || tile + gridDim.x >= ntiles) {
+        if (++in_seg == SEG || it + 1 == my_tiles) {
           umma_commit(&tfull[b]);
           in_seg = 0;
           ++seg;
@@ -1630,7 +1707,7 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
         unsigned long long g_e2; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_e2));
         atomicMax(&g_stage_timers[15], g_e2 - g_start);
       }
-      if (blockIdx.x == 0 && blockIdx.y == 0) {
+      if (cta_x == 0 && cta_y == 0) {
         atomicAdd(&g_stage_timers[4], (unsigned long long)t_a); atomicAdd(&g_stage_timers[5], (unsigned long long)t_b);
         atomicAdd(&g_stage_timers[6], (unsigned long long)t_c); atomicAdd(&g_stage_timers[9], (unsigned long long)n_t);
         atomicAdd(&g_stage_timers[10], (unsigned long long)(clock64() - t_start));
@@ -1648,13 +1725,22 @@ wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, 
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
 #ifdef PINNK_STAGE_TIMERS
-    if (blockIdx.x == 0 && blockIdx.y == 0 && lane == 0) {
+    if (cta_x == 0 && cta_y == 0 && lane == 0) {
       unsigned long long g_exit; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_exit));
       atomicAdd(&g_stage_timers[13], g_exit - g_entry);         // whole kernel, block 0
       atomicAdd(&g_stage_timers[14], 1ull);
     }
 #endif
   }
+}
+
+template <int TK, int RS, int OS, int NCW, int SEG, bool TSA>
+__global__ void __launch_bounds__((NCW + 8) * 32, 1)
+wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, int ldx, float* __restrict__ dW, int lddw,
+             float* __restrict__ db, int64_t M, int jet_cols, int in_blocks, const __grid_constant__ CUtensorMap tmg,
+             const __grid_constant__ CUtensorMap tmxm, float* __restrict__ det_part, float* __restrict__ det_bpart) {
+  wgrad_body<TK, RS, OS, NCW, SEG, TSA, false>(G, ldg, X, ldx, dW, lddw, db, M, jet_cols, in_blocks, &tmg, &tmxm, det_part, det_bpart,
+                                               (int)blockIdx.x, (int)gridDim.x, (int)blockIdx.y, PairSync{});
 }
 
 // fixed-order reduction of the per-CTA partial slabs of a deterministic wgrad launch: dW[block] += sum_x part[block][x]
@@ -1722,6 +1808,65 @@ static int launch_wgrad(const float* G, const float* X, float* dW, float* db, in
   if (cudaGetLastError() != cudaSuccess) return -1;
   if (det_part != nullptr)
     wgrad_det_reduce_kernel<<<dim3(16, (unsigned)blocks, 1), 256, 0, st>>>(det_part, det_bpart, gx, in_blocks, dW, in_dim, db);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Paired reverse kernel of one hidden Linear(128, 128) + tanh: dgrad + tanh adjoint AND the weight gradient in ONE launch.
+// Both products read the same two tensors (dZ of this layer, the output jets Y of the previous one).  As separate kernels
+// they pull them out of HBM twice (2560 B per row with the dZ_prev store).  Here the grid is 74 clusters of two CTAs: rank 0
+// runs the rows kernel (EPI_ACTBWD_Y: dZ_prev = tanh'(.)^T (dZ W)), rank 1 the TS-mode wgrad kernel, both over the SAME
+// 64-row macro tiles T = pair, pair + 74, ..., held in lock step by the DSMEM throttle (PairSync): the second reader of
+// a tile hits L2, so a row costs 1536 B of HBM traffic.  Each role keeps its whole SM (512 TMEM columns, 225 KB of shared
+// memory, its warp roles) -- nothing of the two pipelines had to shrink, which a single-CTA fusion would have required.
+template <int K0, int K1>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(832, 1)
+bwd_pair_kernel(const float* __restrict__ dZ, const float* __restrict__ W, const float* __restrict__ Yprev,
+                float* __restrict__ dZprev, float* __restrict__ dW, float* __restrict__ db, int64_t M, int jet_cols,
+                const __grid_constant__ CUtensorMap tm_unused, uint32_t dyn_bytes) {
+  // the throttle word lives in the last 16 bytes of the dynamic allocation: the same offset in both CTAs, past either role's
+  // layout (no static shared memory: it would push the 1024-byte aligned dynamic region over the 227 KB budget)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t rank = cluster_ctarank();
+  PairSync ps;
+  ps.my_word = smem_u32(smem_raw) + dyn_bytes - 16u;
+  if (threadIdx.x == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(ps.my_word), "r"(0u) : "memory");
+  __syncthreads();
+  cluster_sync_all();                         // both words are zero before either CTA can publish into its partner
+  ps.peer_word = mapa_u32(ps.my_word, rank ^ 1u);
+  const int pair = (int)(blockIdx.x >> 1), npairs = (int)(gridDim.x >> 1);
+  if (rank == 0) {
+    linear_rows_ts_body<true, EPI_ACTBWD_Y, 1, K0, K1, 8, 16, false, 128, false, true>(
+        dZ, W, 128, nullptr, dZprev, M, 128, jet_cols, Yprev, nullptr, 1.f, 128, OutFuse{}, FirstLayer{}, TcLossFuse{},
+        &tm_unused, pair, npairs, 0, ps);
+  } else {
+    wgrad_body<32, 5, 2, 16, 4, true, true>(dZ, 128, Yprev, 128, dW, 128, db, M, jet_cols, 1, &tm_unused, &tm_unused, nullptr,
+                                            nullptr, pair, npairs, 0, ps);
+  }
+  cluster_sync_all();                         // no CTA may exit while its partner can still store into its shared memory
+}
+
+template <int K0, int K1>
+static int launch_bwd_pair(const float* dZ, const float* W, const float* Yprev, float* dZprev, float* dW, float* db, int64_t M,
+                           int sm_count, cudaStream_t st) {
+  constexpr size_t smem_rows = 1024 + (size_t)2 * 2 * 64 * 128 * 4 + (size_t)3 * 64 * 128 * 4 + (2 * 2 + 2 * 2 + 2 * 3) * 8 + 16 + 1024;
+  constexpr size_t smem_wg = 1024 + (size_t)2 * 2 * 32 * 512 + (size_t)5 * 2 * 32 * 512 + (2 * 5 + 2 * 2 + 4) * 8 + 16;
+  constexpr size_t smem = (smem_rows > smem_wg ? smem_rows : smem_wg) + 16;      // + the throttle word
+  static_assert(smem <= 232448, "shared memory budget (227 KB per CTA)");
+  static_assert(jets_rows_per_warp(1 + K0 + K1) == 16, "paired kernel: 64-row tiles only (1, 2 or 4 jet columns)");
+  auto kern = bwd_pair_kernel<K0, K1>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    configured = true;
+  }
+  const int64_t nmac = (M + 63) / 64;
+  int pairs = sm_count / 2;
+  if (pairs < 1) pairs = 1;
+  if ((int64_t)pairs > nmac) pairs = (int)nmac;
+  alignas(64) CUtensorMap tmu;
+  memset(&tmu, 0, sizeof(tmu));
+  kern<<<dim3((unsigned)(2 * pairs), 1, 1), 832, smem, st>>>(dZ, W, Yprev, dZprev, dW, db, M, 1 + K0 + K1, tmu, (uint32_t)smem);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
@@ -1908,6 +2053,18 @@ int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64
   if (rs3 < 0) { const char* e = getenv("PINNK_WGRAD_RS3"); rs3 = (e && e[0] == '1') ? 1 : 0; }
   if (rs3) return tc::launch_wgrad<32, 3, 2, 16, 4, true>(dZ, X, dW, db, M, in_dim, out_dim, jet_cols, sm_count, st);
   return tc::launch_wgrad<32, 5, 2, 16, 4, true>(dZ, X, dW, db, M, in_dim, out_dim, jet_cols, sm_count, st);
+}
+#endif
+#ifdef PINNK_TC_TU_PAIR
+// dZprev[M,128] = tanh'(from the output jets Yprev)^T (dZ[M,128] W[128,128]);  dW += dZ^T Yprev;  db += value rows of dZ
+int tc_bwd_pair(const float* dZ, const float* W, const float* Yprev, float* dZprev, float* dW, float* db, int64_t M, int in_dim,
+                int out_dim, int k0, int k1, int sm_count, cudaStream_t st) {
+  if (M < 64 || in_dim != 128 || out_dim != 128 || dW == nullptr || sm_count < 2) return TC_UNSUPPORTED;
+  if (k0 == 0 && k1 == 0) return tc::launch_bwd_pair<0, 0>(dZ, W, Yprev, dZprev, dW, db, M, sm_count, st);
+  if (k0 == 1 && k1 == 0) return tc::launch_bwd_pair<1, 0>(dZ, W, Yprev, dZprev, dW, db, M, sm_count, st);
+  if (k0 == 2 && k1 == 1) return tc::launch_bwd_pair<2, 1>(dZ, W, Yprev, dZprev, dW, db, M, sm_count, st);
+  if (k0 == 3 && k1 == 0) return tc::launch_bwd_pair<3, 0>(dZ, W, Yprev, dZprev, dW, db, M, sm_count, st);
+  return TC_UNSUPPORTED;
 }
 #endif
 }  // namespace pinnk
