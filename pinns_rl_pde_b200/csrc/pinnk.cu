@@ -450,10 +450,13 @@ static bool first_fuse_enabled() {
   return v == 1 && tc_enabled();
 }
 
-// PINNK_DISABLE_PAIR=1: dgrad + adjoint and wgrad of a hidden layer as two launches (A/B checks of the paired kernel)
+// PINNK_ENABLE_PAIR=1: dgrad + tanh adjoint and wgrad of a hidden Linear(128, 128) in ONE launch of CTA pairs sharing the tile
+// stream (bwd_pair_kernel).  Measured and NOT the default: each role then runs on 74 SMs, and a single SM cannot pull its
+// tiles fast enough to make up for the halved parallelism (one 4 Mi-row layer: 2.41 ms paired vs 1.90 ms as two launches;
+// the roles alone on 74 SMs take 1.28 / 1.49 ms -- profiles/r02c_pair_probe.log).  Kept for A/B runs.
 static bool pair_enabled() {
-  const char* e = getenv("PINNK_DISABLE_PAIR");           // read per call: tests switch it
-  return !(e && e[0] == '1') && tc_enabled();
+  const char* e = getenv("PINNK_ENABLE_PAIR");            // read per call: tests switch it
+  return (e && e[0] == '1') && tc_enabled();
 }
 
 static int first_trainable_op(const pinnk_plan_t pl) {
@@ -1105,7 +1108,8 @@ extern "C" int pinnk_debug_bwd_split(const float* dZ, const float* W, const floa
   int dev = 0;
   cudaGetDevice(&dev);
   const int smc = sm_count_of(dev);
-  int rc = tc_linear_wgrad(dZ, Yprev, dW, db, M, 128, 128, 1 + k0 + k1, smc, (cudaStream_t)stream);
+  const char* skip = getenv("PINNK_DEBUG_SKIP_WGRAD");          // probes: the dgrad + adjoint kernel alone
+  int rc = (skip && skip[0] == '1') ? 0 : tc_linear_wgrad(dZ, Yprev, dW, db, M, 128, 128, 1 + k0 + k1, smc, (cudaStream_t)stream);
   if (rc == 0) rc = tc_linear_dgrad_actbwd(dZ, W, Yprev, dZprev, M, 128, 128, k0, k1, 1, 1.f, smc, (cudaStream_t)stream, 1);
   if (rc == TC_UNSUPPORTED) return fail(PINNK_E_INVALID, "debug_bwd_split: shape / jet layout not covered");
   if (rc != 0) return fail(PINNK_E_CUDA, std::string("debug_bwd_split: ") + cudaGetErrorString(cudaGetLastError()));

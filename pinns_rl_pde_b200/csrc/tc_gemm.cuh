@@ -570,11 +570,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
 // wgrad): each publishes the number of macro tiles whose loads it has issued into the partner's shared memory (DSMEM
 // store) and never runs more than kPairLead macro tiles ahead of the partner, so that the second reader of a tile finds
 // it in L2 -- the tile pair (dZ, Y) comes out of HBM once instead of twice.
-constexpr uint32_t kPairLead = 4;
 struct PairSync {
   uint32_t my_word = 0;        // local shared address of the word the PARTNER writes (its issued macro tiles)
   uint32_t peer_word = 0;      // shared::cluster address of the partner's word (where this CTA publishes)
+  uint32_t lead = 4;           // macro tiles a CTA may run ahead of its partner (PINNK_PAIR_LEAD)
   __device__ __forceinline__ void wait_turn(uint32_t n) const {      // before issuing the loads of macro tile n
+    const uint32_t kPairLead = lead;
     if (n < kPairLead) return;
     for (uint32_t spin = 0; spin < (1u << 26); ++spin) {
       uint32_t v;
@@ -786,6 +787,11 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
       const int64_t r0 = tile * TNE;
       const int nrows = (M - r0 >= TNE) ? TNE : (int)(M - r0);
       { PK_T0(); mbar_wait(&raw_full[rs], rph); PK_TACC(t_a); }
+      // The raw tile was written by the async proxy (cp.async.bulk) and is read below with generic-proxy loads: without a
+      // proxy fence after the mbarrier wait ~0.03 % of the rows (always in the tail of the 32 KB tile, which lands last)
+      // were read BEFORE the copy's bytes were visible -- stale rows of the slot's previous tile -- whenever the kernel
+      // ran HBM-bound with the convert warps waiting on the copy (profiles/r02_stale_tile_rows.md).
+      fence_proxy_async();
       PK_T0();
       const uint32_t raw = rb + (uint32_t)rs * RAW_BYTES;
       float4 v[RPW];
@@ -1464,6 +1470,7 @@ wgrad_body(const float* __restrict__ G, int ldg, const float* __restrict__ X, in
         const int64_t r0 = tile * TK;
         const int nrows = (M - r0 >= TK) ? TK : (int)(M - r0);
         mbar_wait(&raw_full[rs], rph);
+        fence_proxy_async();          // async-proxy (TMA) writes -> generic-proxy reads, as in the rows kernels
         const uint32_t raw = lane_raw1 + (uint32_t)rs * 2 * RAW_BYTES;
         float v[16];
 #pragma unroll
@@ -1527,6 +1534,7 @@ wgrad_body(const float* __restrict__ G, int ldg, const float* __restrict__ X, in
       const int64_t r0 = tile * TK;
       const int nrows = (M - r0 >= TK) ? TK : (int)(M - r0);
       { PK_T0(); mbar_wait(&raw_full[rs], rph); PK_TACC(t_a); }
+      fence_proxy_async();            // async-proxy (TMA) writes -> generic-proxy reads, as in the rows kernels
       PK_T0();
       const uint32_t raw = rb + (uint32_t)rs * 2 * RAW_BYTES + lane_raw;
       float v[4][4];                                       // [row of the quad][feature e]
@@ -1823,12 +1831,13 @@ template <int K0, int K1>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(832, 1)
 bwd_pair_kernel(const float* __restrict__ dZ, const float* __restrict__ W, const float* __restrict__ Yprev,
                 float* __restrict__ dZprev, float* __restrict__ dW, float* __restrict__ db, int64_t M, int jet_cols,
-                const __grid_constant__ CUtensorMap tm_unused, uint32_t dyn_bytes) {
+                const __grid_constant__ CUtensorMap tm_unused, uint32_t dyn_bytes, uint32_t lead) {
   // the throttle word lives in the last 16 bytes of the dynamic allocation: the same offset in both CTAs, past either role's
   // layout (no static shared memory: it would push the 1024-byte aligned dynamic region over the 227 KB budget)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t rank = cluster_ctarank();
   PairSync ps;
+  ps.lead = lead;
   ps.my_word = smem_u32(smem_raw) + dyn_bytes - 16u;
   if (threadIdx.x == 0) asm volatile("st.shared.u32 [%0], %1;" ::"r"(ps.my_word), "r"(0u) : "memory");
   __syncthreads();
@@ -1866,7 +1875,9 @@ static int launch_bwd_pair(const float* dZ, const float* W, const float* Yprev, 
   if ((int64_t)pairs > nmac) pairs = (int)nmac;
   alignas(64) CUtensorMap tmu;
   memset(&tmu, 0, sizeof(tmu));
-  kern<<<dim3((unsigned)(2 * pairs), 1, 1), 832, smem, st>>>(dZ, W, Yprev, dZprev, dW, db, M, 1 + K0 + K1, tmu, (uint32_t)smem);
+  uint32_t lead = 4;
+  if (const char* e = getenv("PINNK_PAIR_LEAD")) { const int v = atoi(e); if (v > 0) lead = (uint32_t)v; }
+  kern<<<dim3((unsigned)(2 * pairs), 1, 1), 832, smem, st>>>(dZ, W, Yprev, dZprev, dW, db, M, 1 + K0 + K1, tmu, (uint32_t)smem, lead);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 

@@ -9,8 +9,8 @@
   PINNK_DISABLE_FIRST_FUSE=1   reverse of the input layer as its own kernel instead of inside the first hidden layer's dgrad
   PINNK_DISABLE_LOSS_FUSE=1    PDE residual, loss sums, seeds and the output layer's reverse as separate kernels instead of
                                inside the last hidden layer's forward epilogue
-  PINNK_DISABLE_PAIR=1         dgrad + tanh adjoint and wgrad of a hidden layer as two launches instead of one launch of CTA
-                               pairs sharing the tile stream (bwd_pair_kernel)
+  PINNK_ENABLE_PAIR=1          dgrad + tanh adjoint and wgrad of a hidden layer in one launch of CTA pairs sharing the tile
+                               stream (bwd_pair_kernel; measured slower than the two launches, so not the default)
   PINNK_DISABLE_TC=1           every GEMM on the exact-fp32 CUDA-core kernel, unfused activations
 
 All eight must give the same residuals, loss components and parameter gradients to fp32 round-off; the model has one
@@ -50,7 +50,7 @@ def test_optimised_routes_agree_with_plain_routes(tmp_path):
                      ("separate_output_layer", {"PINNK_DISABLE_OUT_FUSE": "1"}),
                      ("separate_input_layer_reverse", {"PINNK_DISABLE_FIRST_FUSE": "1"}),
                      ("separate_loss_kernels", {"PINNK_DISABLE_LOSS_FUSE": "1"}),
-                     ("separate_dgrad_wgrad", {"PINNK_DISABLE_PAIR": "1"})):
+                     ("paired_dgrad_wgrad", {"PINNK_ENABLE_PAIR": "1"})):
         v = _run(tmp_path, tag, env)
         for k in base.files:
             assert np.all(np.isfinite(v[k])) and np.all(np.isfinite(base[k])), (tag, k)
