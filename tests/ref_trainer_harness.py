@@ -119,6 +119,21 @@ def run(name: str, device, epochs: int, batch_size: int = 2048, num_points: int 
             "params": flat}
 
 
+def pointwise(a, b):
+    """|a - b| / |b| per epoch."""
+    return [abs(x - y) / max(abs(y), 1e-300) for x, y in zip(a, b)]
+
+
+def window_medians(dev, width=100):
+    """{(lo, hi): median of the pointwise deviations in epochs [lo, hi)} -- robust to the loss spikes of the chaotic phase."""
+    out = {}
+    for lo in range(0, len(dev), width):
+        w = sorted(dev[lo:lo + width])
+        if w:
+            out[(lo, min(lo + width, len(dev)))] = w[len(w) // 2]
+    return out
+
+
 def deviation(a, b):
     """max over epochs of |a - b| / |b| for the windows [0, E): {E: dev}."""
     out = {}
