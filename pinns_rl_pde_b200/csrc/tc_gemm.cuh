@@ -1759,21 +1759,23 @@ static __global__ void wgrad_det_reduce_kernel(const float* __restrict__ part, c
   const int idx = blockIdx.x * 256 + threadIdx.x;                    // float4 index inside the 128 x 128 block
   const int row = idx >> 5, c4 = (idx & 31) * 4;
   const float4* p = reinterpret_cast<const float4*>(part + (int64_t)blk * gx * 16384) + idx;
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  // the partial sums are combined in double (exactly, for all practical purposes) and rounded once: fixed order AND closer to
+  // the true sum than any fp32 ordering of the 148 partials
+  double ax = 0.0, ay = 0.0, az = 0.0, aw = 0.0;
   for (int x = 0; x < gx; ++x) {
     const float4 v = p[(int64_t)x * 4096];
-    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    ax += (double)v.x; ay += (double)v.y; az += (double)v.z; aw += (double)v.w;
   }
   float* d = dW + (int64_t)(o0 + row) * lddw + i0 + c4;
-  d[0] += a.x; d[1] += a.y; d[2] += a.z; d[3] += a.w;
+  d[0] += (float)ax; d[1] += (float)ay; d[2] += (float)az; d[3] += (float)aw;
   if (db != nullptr && i0 == 0 && idx < 128) {
-    float b = 0.f;
+    double b = 0.0;
     for (int x = 0; x < gx; ++x) {
       const float* q = bpart + ((int64_t)(blk * gx + x) * 2) * 128 + idx;
-      b += q[0];
-      b += q[128];
+      b += (double)q[0];
+      b += (double)q[128];
     }
-    db[o0 + idx] += b;
+    db[o0 + idx] += (float)b;
   }
 }
 

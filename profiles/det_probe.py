@@ -7,10 +7,18 @@ from helpers import product_pde
 os.environ["PINNK_DETERMINISTIC"] = "1"
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
-model = pk.make_model("feedforward", 2, 128, 8, dev)
-pde = product_pde("burgers", dev)
+ARCH = sys.argv[1] if len(sys.argv) > 1 else "feedforward"
+if ARCH == "siren":
+    model = pk.make_model("siren", 2, 256, 4, dev, omega_0=30.0)
+    pde = product_pde("allen_cahn", dev)
+elif ARCH == "resnet":
+    model = pk.make_model("resnet", 2, 256, 2, dev, num_blocks=2)
+    pde = product_pde("kdv", dev)
+else:
+    model = pk.make_model("feedforward", 2, 128, 8, dev)
+    pde = product_pde("burgers", dev)
 g = torch.Generator().manual_seed(1)
-n = 200000
+n = 60000 if ARCH != 'feedforward' else 200000
 x, t = (torch.rand(n, 1, generator=g) * 2 - 1).to(dev), torch.rand(n, 1, generator=g).to(dev)
 def run():
     model.zero_grad()
