@@ -125,24 +125,6 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// 32 consecutive TMEM columns of this thread's lane
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 // 16 consecutive TMEM columns of this thread's lane, no wait (caller issues tmem_wait_ld once for a batch of loads)
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -154,6 +136,24 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[1
       : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// tcgen05.wait::ld that NAMES the registers the pending loads write.  The destination registers of a tcgen05.ld are not valid
+// until the wait, but to the compiler they are ordinary asm outputs, ready as soon as the load statement has been issued: under
+// register pressure it spilled them to local memory between the load and the wait (the sin epilogue of the 256-wide layers)
+// and read back whatever the registers held before the data arrived -- a handful of wrong elements per launch, different
+// from run to run (profiles/r02_stale_tile_rows.md).  As "+r" operands of the wait they cannot be touched before it.
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&a)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]) :: "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&a)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]), "+r"(a[16]), "+r"(a[17]), "+r"(a[18]), "+r"(a[19]), "+r"(a[20]), "+r"(a[21]), "+r"(a[22]), "+r"(a[23]), "+r"(a[24]), "+r"(a[25]), "+r"(a[26]), "+r"(a[27]), "+r"(a[28]), "+r"(a[29]), "+r"(a[30]), "+r"(a[31]) :: "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&a)[16], uint32_t (&b)[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" : "+r"(a[0]), "+r"(a[1]), "+r"(a[2]), "+r"(a[3]), "+r"(a[4]), "+r"(a[5]), "+r"(a[6]), "+r"(a[7]), "+r"(a[8]), "+r"(a[9]), "+r"(a[10]), "+r"(a[11]), "+r"(a[12]), "+r"(a[13]), "+r"(a[14]), "+r"(a[15]), "+r"(b[0]), "+r"(b[1]), "+r"(b[2]), "+r"(b[3]), "+r"(b[4]), "+r"(b[5]), "+r"(b[6]), "+r"(b[7]), "+r"(b[8]), "+r"(b[9]), "+r"(b[10]), "+r"(b[11]), "+r"(b[12]), "+r"(b[13]), "+r"(b[14]), "+r"(b[15]) :: "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&a)[32], uint32_t (&b)[32]) {
+  tmem_wait_ld(a);
+  tmem_wait_ld(b);
+}
 
 // UMMA shared-memory matrix descriptor, K-major, SWIZZLE_128B: SBO = 1024 B (one 8-row group), LBO unused (1)
 __device__ __forceinline__ uint64_t make_desc_k_sw128(uint32_t smem_addr) {
@@ -369,7 +369,8 @@ linear_rows_kernel(const float* __restrict__ X, const float* __restrict__ W, int
       uint32_t part[KB + 1][16];
 #pragma unroll
       for (int kb = 0; kb <= KB; ++kb) tmem_ld16_nowait(tb + kb * TN, part[kb]);
-      tmem_wait_ld();
+#pragma unroll
+      for (int kb = 0; kb <= KB; ++kb) tmem_wait_ld(part[kb]);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[b]);
@@ -897,7 +898,7 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
       uint32_t pm[ECOLS], pc[ECOLS];
       if constexpr (ECOLS == 32) { tmem_ld32_nowait(tb, pm); tmem_ld32_nowait(tb + TN, pc); }
       else { tmem_ld16_nowait(tb, pm); tmem_ld16_nowait(tb + TN, pc); }
-      tmem_wait_ld();
+      tmem_wait_ld(pm, pc);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[b]);
@@ -1616,7 +1617,8 @@ wgrad_body(const float* __restrict__ G, int ldg, const float* __restrict__ X, in
           uint32_t p[32], a[32];
           tmem_ld32_nowait(lane_base + COL_MAIN + b * 128 + c0, p);
           if (seg > 0) tmem_ld32_nowait(lane_base + COL_SUM + c0, a);
-          tmem_wait_ld();
+          tmem_wait_ld(p);
+          if (seg > 0) tmem_wait_ld(a);
           if (seg > 0) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) p[j] = __float_as_uint(__uint_as_float(p[j]) + __uint_as_float(a[j]));
@@ -1635,7 +1637,8 @@ wgrad_body(const float* __restrict__ G, int ldg, const float* __restrict__ X, in
         uint32_t p[32], a[32];
         tmem_ld32_nowait(lane_base + COL_SUM + c0, p);
         if constexpr (!TSA) tmem_ld32_nowait(lane_base + COL_CORR + c0, a);
-        tmem_wait_ld();
+        tmem_wait_ld(p);
+        if constexpr (!TSA) tmem_wait_ld(a);
 #pragma unroll
         for (int j = 0; j < 32; ++j) tr[f * 132 + c0 + j] = TSA ? __uint_as_float(p[j]) : __uint_as_float(p[j]) + __uint_as_float(a[j]);
       }
