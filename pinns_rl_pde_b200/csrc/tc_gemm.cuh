@@ -46,6 +46,15 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Arrive on a "slot may be refilled" barrier AFTER the shared-memory loads that read the slot have completed.  `dep` must be
+// computed from one destination register of EVERY such load; storing it to a scratch word makes the store -- and the arrive
+// behind it -- wait for the loads' data (an unused asm operand does not: ptxas drops it).  A plain arrive only follows the
+// loads' ISSUE: they can still sit in the load/store queue when the TMA warp sees the slot free and refills it, and the late
+// ones then read the NEXT tile's rows (profiles/r02_stale_tile_rows.md).
+__device__ __forceinline__ void mbar_arrive_after_loads(uint64_t* bar, uint32_t dep, uint32_t* scratch) {
+  asm volatile("st.shared.u32 [%1], %2;\n\tmbarrier.arrive.shared::cta.b64 _, [%0];"
+               ::"r"(smem_u32(bar)), "r"(smem_u32(scratch)), "r"(dep) : "memory");
+}
 // Bounded wait: a protocol bug must trap (error returned to the host), never hang the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -788,11 +797,6 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
       const int64_t r0 = tile * TNE;
       const int nrows = (M - r0 >= TNE) ? TNE : (int)(M - r0);
       { PK_T0(); mbar_wait(&raw_full[rs], rph); PK_TACC(t_a); }
-      // The raw tile was written by the async proxy (cp.async.bulk) and is read below with generic-proxy loads: without a
-      // proxy fence after the mbarrier wait ~0.03 % of the rows (always in the tail of the 32 KB tile, which lands last)
-      // were read BEFORE the copy's bytes were visible -- stale rows of the slot's previous tile -- whenever the kernel
-      // ran HBM-bound with the convert warps waiting on the copy (profiles/r02_stale_tile_rows.md).
-      fence_proxy_async();
       PK_T0();
       const uint32_t raw = rb + (uint32_t)rs * RAW_BYTES;
       float4 v[RPW];
@@ -801,8 +805,11 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
         const int r = warp + NLW * i;
         v[i] = (r < nrows) ? lds128(raw + r * (K * 4) + lane * 16) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      uint32_t dep = 0;                                           // one register of every load above
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) dep |= __float_as_uint(v[i].w);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&raw_empty[rs]);                 // raw data is in registers: slot may be refilled
+      if (lane == 0) mbar_arrive_after_loads(&raw_empty[rs], dep, tmem_slot + 1);    // raw data IS in registers: slot may be refilled
       PK_TACC(t_c);
       { PK_T0(); mbar_wait(&empty[s], ph ^ 1u); PK_TACC(t_b); }
       const long long _t1 = clock64(); (void)_t1;
@@ -1471,7 +1478,6 @@ wgrad_body(const float* __restrict__ G, int ldg, const float* __restrict__ X, in
         const int64_t r0 = tile * TK;
         const int nrows = (M - r0 >= TK) ? TK : (int)(M - r0);
         mbar_wait(&raw_full[rs], rph);
-        fence_proxy_async();          // async-proxy (TMA) writes -> generic-proxy reads, as in the rows kernels
         const uint32_t raw = lane_raw1 + (uint32_t)rs * 2 * RAW_BYTES;
         float v[16];
 #pragma unroll
@@ -1480,8 +1486,11 @@ wgrad_body(const float* __restrict__ G, int ldg, const float* __restrict__ X, in
           if (nrows == TK || h * 16 + j < nrows) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(raw + (uint32_t)(j * 512)));
           v[j] = x;
         }
+        uint32_t dep = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dep |= __float_as_uint(v[j]);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&raw_empty[rs]);
+        if (lane == 0) mbar_arrive_after_loads(&raw_empty[rs], dep, tmem_slot + 1);
         mbar_wait(&empty[os], oph ^ 1u);
         tc_fence_after();
         if (want_b1) {
@@ -1535,7 +1544,6 @@ wgrad_body(const float* __restrict__ G, int ldg, const float* __restrict__ X, in
       const int64_t r0 = tile * TK;
       const int nrows = (M - r0 >= TK) ? TK : (int)(M - r0);
       { PK_T0(); mbar_wait(&raw_full[rs], rph); PK_TACC(t_a); }
-      fence_proxy_async();            // async-proxy (TMA) writes -> generic-proxy reads, as in the rows kernels
       PK_T0();
       const uint32_t raw = rb + (uint32_t)rs * 2 * RAW_BYTES + lane_raw;
       float v[4][4];                                       // [row of the quad][feature e]
@@ -1555,8 +1563,13 @@ wgrad_body(const float* __restrict__ G, int ldg, const float* __restrict__ X, in
             v[r][e] = x;
           }
       }
+      uint32_t dep = 0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dep |= __float_as_uint(v[r][e]);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&raw_empty[rs]);                 // raw data is in registers: slot may be refilled
+      if (lane == 0) mbar_arrive_after_loads(&raw_empty[rs], dep, tmem_slot + 1);    // raw data IS in registers: slot may be refilled
       PK_TACC(t_c);
       { PK_T0(); mbar_wait(&empty[os], oph ^ 1u); PK_TACC(t_b); }
       const long long _t1 = clock64(); (void)_t1;
