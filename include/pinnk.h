@@ -215,6 +215,22 @@ int pinnk_debug_bwd_pair(const float* dZ, const float* W, const float* Yprev, fl
 int pinnk_debug_bwd_split(const float* dZ, const float* W, const float* Yprev, float* dZprev, float* dW, float* db,
                           int64_t M, int32_t k0, int32_t k1, void* stream);
 
+/* On-device samplers of the adaptive collocation strategies.
+ * pinnk_sample_weighted: m draws WITH replacement from {0..n-1} with probability proportional to weights[i] + eps -- the RAR
+ * draw `torch.multinomial(|r| + 1e-8, m, replacement=True)` of pde_base.py:924-931, fed directly by pinnk_score's abs_out, for
+ * any n (torch.multinomial stops at 2^24 categories).  u: device [m] fp64 uniforms in [0, 1) (drawn by the caller: torch owns
+ * the RNG); idx_out: device [m] int64; ws: device scratch of pinnk_sample_workspace_doubles(n) doubles.  Three launches, no
+ * host synchronisation.
+ * pinnk_jittered_grid: the jittered n_side x n_side collocation grid of _sample_uniform (pde_base.py:806-829) in one launch:
+ * x[i*n_side+j] = clamp(xs[i] + noise_x * x_noise), t = clamp(ts[j] + noise_t * t_noise); xs / ts = the linspace vectors,
+ * noise_* = the randn draws (made by the caller with the reference's RNG calls; the result is bit-identical to the torch ops). */
+int64_t pinnk_sample_workspace_doubles(int64_t n);
+int pinnk_sample_weighted(const float* weights, int64_t n, float eps, const double* u, int64_t m, int64_t* idx_out,
+                          double* ws, int64_t ws_doubles, void* stream);
+int pinnk_jittered_grid(const float* xs, const float* ts, int32_t n_side, const float* noise_x, const float* noise_t,
+                        float x_noise, float t_noise, float x_lo, float x_hi, float t_lo, float t_hi, float* x_out,
+                        float* t_out, void* stream);
+
 /* Builder tool: cycles block 0 of the tcgen05 rows kernels spent waiting on each pipeline barrier, accumulated since the
  * last reset (which: 0 = forward rows kernels, 1 = reverse rows kernels, 2 = wgrad; out16: 16 counters, see csrc/tc_gemm.cuh).
  * Returns 1 and zeros unless the library was built with -DPINNK_STAGE_TIMERS. */

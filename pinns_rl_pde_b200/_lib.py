@@ -49,7 +49,8 @@ EXPORTS = ["pinnk_plan_create", "pinnk_plan_destroy", "pinnk_plan_workspace_byte
            "pinnk_last_error", "pinnk_abi_version", "pinnk_launch_count", "pinnk_prof_enable", "pinnk_prof_classes",
            "pinnk_prof_class_name", "pinnk_prof_collect", "pinnk_debug_linear_fwd",
            "pinnk_debug_linear_dgrad", "pinnk_debug_linear_wgrad", "pinnk_adam_step", "pinnk_adam_step_dev", "pinnk_dqn_forward",
-           "pinnk_debug_stage_timers", "pinnk_debug_bwd_pair", "pinnk_debug_bwd_split"]
+           "pinnk_debug_stage_timers", "pinnk_debug_bwd_pair", "pinnk_debug_bwd_split",
+           "pinnk_sample_workspace_doubles", "pinnk_sample_weighted", "pinnk_jittered_grid"]
 
 _lib = None
 
@@ -119,6 +120,12 @@ def load():
     for fn in (lib.pinnk_debug_bwd_pair, lib.pinnk_debug_bwd_split):
         fn.argtypes = [vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]
         fn.restype = C.c_int
+    lib.pinnk_sample_workspace_doubles.argtypes = [i64]
+    lib.pinnk_sample_workspace_doubles.restype = i64
+    lib.pinnk_sample_weighted.argtypes = [vp, i64, C.c_float, vp, i64, vp, vp, i64, vp]
+    lib.pinnk_sample_weighted.restype = C.c_int
+    lib.pinnk_jittered_grid.argtypes = [vp, vp, i32, vp, vp] + [C.c_float] * 6 + [vp, vp, vp]
+    lib.pinnk_jittered_grid.restype = C.c_int
     lib.pinnk_debug_stage_timers.argtypes = [i32, C.POINTER(C.c_uint64), i32]
     lib.pinnk_debug_stage_timers.restype = C.c_int
     if lib.pinnk_abi_version() != ABI_VERSION:

@@ -23,6 +23,7 @@
 #include "kernels_ew.cuh"
 #include "kernels_edge.cuh"
 #include "kernels_dqn.cuh"
+#include "kernels_sample.cuh"
 #include "sgemm.cuh"
 #include "tc_api.h"
 
@@ -1173,6 +1174,43 @@ extern "C" int pinnk_adam_step_dev(float* const* params, const int64_t* numels, 
   if (!dyn) return fail(PINNK_E_INVALID, "adam_step_dev: null dyn");
   return adam_step_impl(params, numels, n_tensors, flat_grad, exp_avg, exp_avg_sq, scratch, 0, 0.f, dyn, beta1, beta2, eps,
                         weight_decay, max_norm, stream);
+}
+
+// ---- on-device samplers (pde_base.py:806-935): weighted draw with replacement, jittered grid
+extern "C" int64_t pinnk_sample_workspace_doubles(int64_t n) { return n > 0 ? (n + SAMPLE_BLOCK - 1) / SAMPLE_BLOCK + 1 : 1; }
+
+extern "C" int pinnk_sample_weighted(const float* weights, int64_t n, float eps, const double* u, int64_t m, int64_t* idx_out,
+                                     double* ws, int64_t ws_doubles, void* stream) {
+  if (!weights || !u || !idx_out || !ws || n < 1 || m < 0) return fail(PINNK_E_INVALID, "sample_weighted: bad argument");
+  const int64_t nb = (n + SAMPLE_BLOCK - 1) / SAMPLE_BLOCK;
+  if (ws_doubles < nb + 1) return fail(PINNK_E_WORKSPACE, "sample_weighted: workspace smaller than pinnk_sample_workspace_doubles()");
+  if (m == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  sample_block_sums_kernel<<<(unsigned)nb, 256, 0, st>>>(weights, n, eps, ws);
+  PK_LAUNCH_OK();
+  sample_scan_kernel<<<1, 1024, 0, st>>>(ws, nb);
+  PK_LAUNCH_OK();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int64_t warps_needed = m;
+  const unsigned blocks = (unsigned)std::min<int64_t>((warps_needed + 7) / 8, 16 * (int64_t)sm_count_of(dev));
+  sample_draw_kernel<<<blocks, 256, 0, st>>>(weights, n, eps, ws, nb, u, m, idx_out);
+  PK_LAUNCH_OK();
+  return 0;
+}
+
+extern "C" int pinnk_jittered_grid(const float* xs, const float* ts, int32_t n_side, const float* noise_x, const float* noise_t,
+                                   float x_noise, float t_noise, float x_lo, float x_hi, float t_lo, float t_hi, float* x_out,
+                                   float* t_out, void* stream) {
+  if (!xs || !ts || !noise_x || !noise_t || !x_out || !t_out || n_side < 1) return fail(PINNK_E_INVALID, "jittered_grid: bad argument");
+  const int64_t n = (int64_t)n_side * n_side;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, 32 * (int64_t)sm_count_of(dev));
+  jittered_grid_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(xs, ts, n_side, noise_x, noise_t, x_noise, t_noise, x_lo, x_hi,
+                                                                  t_lo, t_hi, x_out, t_out);
+  PK_LAUNCH_OK();
+  return 0;
 }
 
 // ---- RL sampler: Q-network forward over the candidate grid (rl_agent.py:15-88,214-229), one launch

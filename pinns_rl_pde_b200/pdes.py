@@ -202,6 +202,10 @@ class PDEBase:
             n_side = int(np.sqrt(num_points))
             x = torch.linspace(self.domain[0][0], self.domain[0][1], n_side, device=self.device).reshape(-1, 1)
             t = torch.linspace(self.time_domain[0], self.time_domain[1], n_side, device=self.device).reshape(-1, 1)
+            if x.is_cuda and n_side >= 1:
+                # meshgrid + jitter + clamp in ONE libpinnk launch (pinnk_jittered_grid): same linspace vectors, same two
+                # randn draws in the same order as the reference, bit-identical points, 1 launch instead of ~10
+                return jittered_grid_device(x.reshape(-1), t.reshape(-1), self.domain[0], self.time_domain)
             X, T = torch.meshgrid(x.squeeze(), t.squeeze(), indexing="ij")
             x, t = X.reshape(-1, 1), T.reshape(-1, 1)
             x = x + torch.randn_like(x) * (self.domain[0][1] - self.domain[0][0]) * 0.01
@@ -244,7 +248,9 @@ class PDEBase:
         x_pool, t_pool = self._sample_uniform(num_points * 4)
         x_pool, t_pool = x_pool.to(self.device), t_pool.to(self.device)
         mag, _ = F.score_residual(self, model, x_pool, t_pool, want_abs=True)
-        sel = multinomial_large(mag + 1e-8, num_points)
+        # probs = |r| + 1e-8, multinomial with replacement (pde_base.py:924-931): inverse-CDF draw on the device straight from
+        # the scoring kernel's |r| (no normalised copy, no 2^24 limit, no host round trip)
+        sel = weighted_sample_device(mag, 1e-8, num_points)
         return x_pool[sel].detach(), t_pool[sel].detach()
 
     def generate_collocation_points(self, num_points: int, strategy: str = "uniform", **kwargs):
@@ -298,11 +304,58 @@ class PDEBase:
                 "mean_error": torch.mean(err).item()}
 
 
+def weighted_sample_device(weights: torch.Tensor, eps: float, num_samples: int) -> torch.Tensor:
+    """``torch.multinomial((w + eps) / sum, num_samples, replacement=True)`` on the device for ANY number of categories
+    (pinnk_sample_weighted: fp64 block sums, one scan, one warp per sample; torch.multinomial stops at 2^24).
+    The uniforms come from torch's CUDA generator (one ``torch.rand`` call of ``num_samples`` doubles).  int64 indices."""
+    import ctypes as C
+    from . import _lib as L
+    w = weights.detach().reshape(-1)
+    if not (w.is_cuda and w.dtype == torch.float32):
+        raise L.PinnkError("weighted_sample_device needs float32 CUDA weights (there is no CPU path)")
+    w = w.contiguous()
+    n, m = w.numel(), int(num_samples)
+    idx = torch.empty(m, dtype=torch.int64, device=w.device)
+    if n == 0 or m == 0:
+        if m:
+            raise ValueError("cannot sample from an empty candidate set")
+        return idx
+    lib = L.load()
+    ws_n = int(lib.pinnk_sample_workspace_doubles(n))
+    ws = torch.empty(ws_n, dtype=torch.float64, device=w.device)
+    u = torch.rand(m, dtype=torch.float64, device=w.device)
+    L.check(lib.pinnk_sample_weighted(w.data_ptr(), n, float(eps), u.data_ptr(), m, idx.data_ptr(), ws.data_ptr(), ws_n,
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pinnk_sample_weighted")
+    return idx
+
+
+def jittered_grid_device(xs: torch.Tensor, ts: torch.Tensor, x_dom, t_dom):
+    """The jittered ``len(xs) x len(ts)`` grid of ``_sample_uniform`` (pde_base.py:806-829) in one launch; draws the jitter
+    with the reference's two ``randn`` calls ([n, 1] for x, then [n, 1] for t)."""
+    import ctypes as C
+    from . import _lib as L
+    n_side = xs.numel()
+    n = n_side * n_side
+    nx = torch.randn(n, 1, dtype=torch.float32, device=xs.device)
+    nt = torch.randn(n, 1, dtype=torch.float32, device=xs.device)
+    x = torch.empty(n, 1, dtype=torch.float32, device=xs.device)
+    t = torch.empty(n, 1, dtype=torch.float32, device=xs.device)
+    if n:
+        L.check(L.load().pinnk_jittered_grid(xs.contiguous().data_ptr(), ts.contiguous().data_ptr(), n_side, nx.data_ptr(),
+                                             nt.data_ptr(), (x_dom[1] - x_dom[0]) * 0.01, (t_dom[1] - t_dom[0]) * 0.01,
+                                             float(x_dom[0]), float(x_dom[1]), float(t_dom[0]), float(t_dom[1]),
+                                             x.data_ptr(), t.data_ptr(),
+                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pinnk_jittered_grid")
+    return x, t
+
+
 def multinomial_large(weights: torch.Tensor, num_samples: int, block: int = 1 << 20) -> torch.Tensor:
     """``torch.multinomial(w / w.sum(), num_samples, replacement=True)`` without the 2^24 category limit
     (SURVEY F7): draw a block proportionally to block mass, then a point inside the block."""
     w = weights.reshape(-1).to(torch.float32)
     n = w.numel()
+    if w.is_cuda:
+        return weighted_sample_device(w, 0.0, num_samples)
     if n <= (1 << 24):
         return torch.multinomial(w / w.sum(), num_samples, replacement=True)
     nb = -(-n // block)
