@@ -181,6 +181,12 @@ typedef struct PinnkDqnLayer {
 } PinnkDqnLayer;
 int pinnk_dqn_forward(const PinnkDqnLayer* layers, int32_t n_hidden, const float* w_out, const float* b_out,
                       int32_t out_dim, const float* states, int64_t n, float* q_out, void* stream);
+/* The same forward for hidden widths that are multiples of 128, up to 1024 (config.yaml:363 ships hidden_dim 512;
+ * train.py:348-351): the hidden Linear layers run on the tcgen05 3xTF32 rows kernel, LayerNorm / ReLU / dropout mask / the
+ * first and the output layer in one row kernel around them.  ws: device scratch of 2 * n * hidden floats. */
+int pinnk_dqn_forward_wide(const PinnkDqnLayer* layers, int32_t n_hidden, const float* w_out, const float* b_out,
+                           int32_t out_dim, const float* states, int64_t n, float* q_out, float* ws, int64_t ws_floats,
+                           void* stream);
 
 const char* pinnk_last_error(void);
 int32_t pinnk_abi_version(void);

@@ -50,7 +50,7 @@ EXPORTS = ["pinnk_plan_create", "pinnk_plan_destroy", "pinnk_plan_workspace_byte
            "pinnk_prof_class_name", "pinnk_prof_collect", "pinnk_debug_linear_fwd",
            "pinnk_debug_linear_dgrad", "pinnk_debug_linear_wgrad", "pinnk_adam_step", "pinnk_adam_step_dev", "pinnk_dqn_forward",
            "pinnk_debug_stage_timers", "pinnk_debug_bwd_pair", "pinnk_debug_bwd_split",
-           "pinnk_sample_workspace_doubles", "pinnk_sample_weighted", "pinnk_jittered_grid"]
+           "pinnk_dqn_forward_wide", "pinnk_sample_workspace_doubles", "pinnk_sample_weighted", "pinnk_jittered_grid"]
 
 _lib = None
 
@@ -113,6 +113,8 @@ def load():
     lib.pinnk_adam_step_dev.restype = C.c_int
     lib.pinnk_dqn_forward.argtypes = [C.POINTER(PinnkDqnLayer), i32, vp, vp, i32, vp, i64, vp, vp]
     lib.pinnk_dqn_forward.restype = C.c_int
+    lib.pinnk_dqn_forward_wide.argtypes = [C.POINTER(PinnkDqnLayer), i32, vp, vp, i32, vp, i64, vp, vp, i64, vp]
+    lib.pinnk_dqn_forward_wide.restype = C.c_int
     lib.pinnk_debug_linear_dgrad.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp]
     lib.pinnk_debug_linear_dgrad.restype = C.c_int
     lib.pinnk_debug_linear_wgrad.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]

@@ -145,4 +145,69 @@ __global__ void __launch_bounds__(1024) dqn_forward_kernel(DqnNet net, const flo
   }
 }
 
+// ---- wide Q-networks (hidden a multiple of 128 up to 1024; config.yaml:363 ships hidden_dim 512): the Linear layers between
+// hidden groups run on the tcgen05 3xTF32 rows kernel (tc_linear_fwd), and this kernel does everything around them, one
+// warp per candidate row with the row's hidden units in registers:
+//   FIRST  z = W_0 s + b_0 from the state vector (state_dim <= 8), else z is read from Z (the GEMM's output);
+//   LayerNorm (two passes, biased variance) -> ReLU -> dropout mask;
+//   LAST   the output layer Linear(hidden, out_dim) as a warp reduction, else the activations go to Y for the next GEMM.
+template <int NPER, bool FIRST, bool LAST>
+__global__ void dqn_ln_relu_rows_kernel(const float* __restrict__ Z, const float* __restrict__ states, int state_dim,
+                                        const float* __restrict__ W0, const float* __restrict__ b0,
+                                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                        const float* __restrict__ mask, int64_t n, float* __restrict__ Y,
+                                        const float* __restrict__ W_out, const float* __restrict__ b_out, int out_dim,
+                                        float* __restrict__ q_out) {
+  constexpr int H = NPER * 32;
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float inv_h = 1.f / (float)H;
+  for (int64_t row = (((int64_t)blockIdx.x * blockDim.x) + threadIdx.x) >> 5; row < n; row += warps) {
+    float z[NPER];
+    if constexpr (FIRST) {
+      float s[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s[k] = (k < state_dim) ? states[row * state_dim + k] : 0.f;
+#pragma unroll
+      for (int i = 0; i < NPER; ++i) {
+        const int f = lane + 32 * i;
+        float a = b0 ? b0[f] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < state_dim) a = fmaf(W0[(int64_t)f * state_dim + k], s[k], a);
+        z[i] = a;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NPER; ++i) z[i] = Z[row * H + lane + 32 * i];
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) sum += z[i];
+    const float mean = dqn_warp_sum(sum) * inv_h;
+    float vs = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) { z[i] -= mean; vs += z[i] * z[i]; }
+    const float rstd = rsqrtf(dqn_warp_sum(vs) * inv_h + eps);
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) {
+      const int f = lane + 32 * i;
+      float y = fmaf(z[i] * rstd, gamma ? gamma[f] : 1.f, beta ? beta[f] : 0.f);
+      y = fmaxf(y, 0.f);
+      if (mask) y *= mask[row * H + f];
+      z[i] = y;
+      if constexpr (!LAST) Y[row * H + f] = y;
+    }
+    if constexpr (LAST) {
+      for (int a = 0; a < out_dim; ++a) {
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < NPER; ++i) q = fmaf(W_out[(int64_t)a * H + lane + 32 * i], z[i], q);
+        q = dqn_warp_sum(q);
+        if (lane == 0) q_out[row * out_dim + a] = q + (b_out ? b_out[a] : 0.f);
+      }
+    }
+  }
+}
+
 }  // namespace pinnk

@@ -1214,8 +1214,27 @@ extern "C" int pinnk_jittered_grid(const float* xs, const float* ts, int32_t n_s
 }
 
 // ---- RL sampler: Q-network forward over the candidate grid (rl_agent.py:15-88,214-229), one launch
+static int dqn_forward_impl(const PinnkDqnLayer* layers, int32_t n_hidden, const float* w_out, const float* b_out,
+                            int32_t out_dim, const float* states, int64_t n, float* q_out, float* ws, int64_t ws_floats,
+                            void* stream);
+
 extern "C" int pinnk_dqn_forward(const PinnkDqnLayer* layers, int32_t n_hidden, const float* w_out, const float* b_out,
                                  int32_t out_dim, const float* states, int64_t n, float* q_out, void* stream) {
+  return dqn_forward_impl(layers, n_hidden, w_out, b_out, out_dim, states, n, q_out, nullptr, 0, stream);
+}
+
+// the same network for hidden widths that are multiples of 128 (up to 1024): the hidden Linear layers run on the tcgen05
+// 3xTF32 rows kernel; ws = 2 * n * hidden floats of device scratch
+extern "C" int pinnk_dqn_forward_wide(const PinnkDqnLayer* layers, int32_t n_hidden, const float* w_out, const float* b_out,
+                                      int32_t out_dim, const float* states, int64_t n, float* q_out, float* ws,
+                                      int64_t ws_floats, void* stream) {
+  if (!ws) return fail(PINNK_E_WORKSPACE, "dqn_forward_wide: null workspace");
+  return dqn_forward_impl(layers, n_hidden, w_out, b_out, out_dim, states, n, q_out, ws, ws_floats, stream);
+}
+
+static int dqn_forward_impl(const PinnkDqnLayer* layers, int32_t n_hidden, const float* w_out, const float* b_out,
+                            int32_t out_dim, const float* states, int64_t n, float* q_out, float* ws, int64_t ws_floats,
+                            void* stream) {
   if (!layers || n_hidden < 1 || n_hidden > DQN_MAX_LAYERS || !w_out || out_dim < 1 || !states || !q_out || n < 0)
     return fail(PINNK_E_INVALID, "dqn_forward: bad argument (1..8 hidden layers, out_dim >= 1)");
   if (n == 0) return 0;
@@ -1237,6 +1256,41 @@ extern "C" int pinnk_dqn_forward(const PinnkDqnLayer* layers, int32_t n_hidden, 
   }
   int dev = 0;
   cudaGetDevice(&dev);
+  if (ws != nullptr) {
+    // wide route: hidden Linear layers on the tcgen05 rows kernel, everything else in dqn_ln_relu_rows_kernel
+    const int H = net.hidden;
+    if ((H % 128) != 0 || H > 1024 || net.state_dim > 8) return fail(PINNK_E_INVALID, "dqn_forward_wide: hidden must be a multiple of 128 up to 1024, state_dim <= 8");
+    if (ws_floats < 2 * n * H) return fail(PINNK_E_WORKSPACE, "dqn_forward_wide: workspace smaller than 2 * n * hidden floats");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int smc = sm_count_of(dev);
+    float* A = ws;                       // activations of the previous group
+    float* Zb = ws + n * H;              // GEMM output
+    const unsigned blocks = (unsigned)std::min<int64_t>((n + 7) / 8, 16 * (int64_t)smc);
+#define PK_DQN_ROWS(NP, FIRSTv, LASTv, Zin, l)                                                                          \
+    dqn_ln_relu_rows_kernel<NP, FIRSTv, LASTv><<<blocks, 256, 0, st>>>(Zin, states, net.state_dim, net.W[0], net.b[0],  \
+        net.gamma[l], net.beta[l], net.eps[l], net.mask[l], n, A, net.W_out, net.b_out, net.out_dim, q_out)
+#define PK_DQN_DISPATCH(FIRSTv, LASTv, Zin, l)                                                                          \
+    do { switch (H / 32) { case 4: PK_DQN_ROWS(4, FIRSTv, LASTv, Zin, l); break; case 8: PK_DQN_ROWS(8, FIRSTv, LASTv, Zin, l); break;  \
+                           case 12: PK_DQN_ROWS(12, FIRSTv, LASTv, Zin, l); break; case 16: PK_DQN_ROWS(16, FIRSTv, LASTv, Zin, l); break; \
+                           case 20: PK_DQN_ROWS(20, FIRSTv, LASTv, Zin, l); break; case 24: PK_DQN_ROWS(24, FIRSTv, LASTv, Zin, l); break; \
+                           case 28: PK_DQN_ROWS(28, FIRSTv, LASTv, Zin, l); break; default: PK_DQN_ROWS(32, FIRSTv, LASTv, Zin, l); break; } } while (0)
+    for (int l = 0; l < n_hidden; ++l) {
+      const bool last = l == n_hidden - 1;
+      if (l == 0) {
+        if (last) PK_DQN_DISPATCH(true, true, nullptr, 0); else PK_DQN_DISPATCH(true, false, nullptr, 0);
+      } else {
+        int rc = tc_linear_fwd(A, net.W[l], net.b[l], Zb, n, H, H, 1, smc, st);
+        if (rc == TC_UNSUPPORTED) return fail(PINNK_E_INVALID, "dqn_forward_wide: hidden width not covered by the tcgen05 rows kernel");
+        if (rc != 0) return fail(PINNK_E_CUDA, std::string("dqn_forward_wide: tc_linear_fwd: ") + cudaGetErrorString(cudaGetLastError()));
+        g_launches.fetch_add(H / 128);
+        if (last) PK_DQN_DISPATCH(false, true, Zb, l); else PK_DQN_DISPATCH(false, false, Zb, l);
+      }
+      PK_LAUNCH_OK();
+    }
+#undef PK_DQN_DISPATCH
+#undef PK_DQN_ROWS
+    return 0;
+  }
   const int threads = (net.hidden + 31) / 32 * 32;
   const size_t smem = dqn_smem_bytes(DQN_ROWS, net.hidden, net.state_dim);
   if (smem > 227 * 1024) return fail(PINNK_E_INVALID, "dqn_forward: hidden width needs more than 227 KB of shared memory");

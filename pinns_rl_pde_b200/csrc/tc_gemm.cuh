@@ -1948,6 +1948,17 @@ int tc_linear_fwd(const float* X, const float* W, const float* bias, float* Z, i
   }
   if (K == 128) return tc::launch_linear_rows<128, 32, 3, 3, 8, 3, false>(X, W, K, bias, Z, M, N, jet_cols, sm_count, st);
   if (K == 64) return tc::launch_linear_rows<64, 64, 4, 2, 8, 2, false>(X, W, K, bias, Z, M, N, jet_cols, sm_count, st);
+  if (K > 256 && (K % 128) == 0 && K <= 1024 && !use_ss) {
+    // wider contractions (the RL sampler's 512-wide Q-network): K / 128 passes of the K = 128 kernel, each adding its partial
+    // product to Z; the last one adds the bias
+    for (int k0 = 0; k0 < K; k0 += 128) {
+      const bool last = k0 + 128 == K;
+      int rc = tc::launch_linear_rows_ts<false, tc::EPI_PLAIN, 1, 0, 0>(X + k0, W + k0, K, last ? bias : nullptr, Z, M, N, jet_cols, nullptr,
+                                                                       nullptr, 1.f, sm_count, st, K, k0 ? 1 : 0);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   return TC_UNSUPPORTED;
 }
 // Forward Linear + activation jets in one kernel: Z = X W^T + b (stash), Yact = act(Z).  act: 1 tanh, 2 sin(omega z).

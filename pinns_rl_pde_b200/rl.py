@@ -53,6 +53,8 @@ class UnsupportedQNetwork(ValueError):
 
 
 MAX_HIDDEN = 128       # widest Q-network the one-launch kernel is used for (benchmarks/sampling.py:124 builds hidden_dim = 64)
+MAX_HIDDEN_WIDE = 1024  # multiples of 128 above that run their hidden Linear layers on the tcgen05 rows kernel
+                        # (pinnk_dqn_forward_wide; config.yaml:363 / train.py:348-351 build hidden_dim = 512)
 
 
 def _lower(net: nn.Module) -> Tuple[List[Tuple[nn.Linear, nn.LayerNorm, float]], nn.Linear]:
@@ -75,11 +77,14 @@ def _lower(net: nn.Module) -> Tuple[List[Tuple[nn.Linear, nn.LayerNorm, float]],
         raise UnsupportedQNetwork("the Q-network must end in a Linear layer")
     if not 1 <= len(groups) <= 8:
         raise UnsupportedQNetwork("1..8 hidden groups")
-    if groups[0][0].out_features > MAX_HIDDEN:
-        # the one-launch kernel is FFMA-bound: measured x1.8 (eval) / x1.15 (live dropout) over the torch modules at
-        # hidden 128 on a 100 x 100 grid, but x0.6 at hidden 256 where cuBLAS takes over -- wider nets are declined
-        # (callers keep the agent's own forward) rather than made slower
-        raise UnsupportedQNetwork(f"hidden width {groups[0][0].out_features} > {MAX_HIDDEN}: not covered by pinnk_dqn_forward")
+    h = groups[0][0].out_features
+    if h > MAX_HIDDEN and not (h % 128 == 0 and h <= MAX_HIDDEN_WIDE and groups[0][0].in_features <= 8):
+        # the one-launch kernel is FFMA-bound (x1.8 over the torch modules at hidden 128 on a 100 x 100 grid, x0.6 at 256); wider
+        # nets take the tcgen05 route when their width is a multiple of 128, anything else keeps the agent's own forward
+        raise UnsupportedQNetwork(f"hidden width {h}: not covered by pinnk_dqn_forward (<= {MAX_HIDDEN}) nor by "
+                                  f"pinnk_dqn_forward_wide (multiples of 128 up to {MAX_HIDDEN_WIDE})")
+    if any(lin.out_features != h for lin, _, _ in groups):
+        raise UnsupportedQNetwork("hidden groups of different widths")
     return groups, out
 
 
@@ -117,10 +122,18 @@ def dqn_forward(net: nn.Module, states: torch.Tensor) -> torch.Tensor:
     q = torch.empty(n, out.out_features, dtype=torch.float32, device=x.device)
     if n == 0:
         return q.reshape(*states.shape[:-1], out.out_features)
-    L.check(L.load().pinnk_dqn_forward(layers, len(groups), _ptr(out.weight.detach()),
-                                       _ptr(None if out.bias is None else out.bias.detach()), out.out_features,
-                                       x.data_ptr(), n, q.data_ptr(),
-                                       C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pinnk_dqn_forward")
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    h = groups[0][0].out_features
+    if h > MAX_HIDDEN:
+        ws = torch.empty(2 * n * h, dtype=torch.float32, device=x.device)
+        L.check(L.load().pinnk_dqn_forward_wide(layers, len(groups), _ptr(out.weight.detach()),
+                                                _ptr(None if out.bias is None else out.bias.detach()), out.out_features,
+                                                x.data_ptr(), n, q.data_ptr(), ws.data_ptr(), ws.numel(), stream),
+                "pinnk_dqn_forward_wide")
+    else:
+        L.check(L.load().pinnk_dqn_forward(layers, len(groups), _ptr(out.weight.detach()),
+                                           _ptr(None if out.bias is None else out.bias.detach()), out.out_features,
+                                           x.data_ptr(), n, q.data_ptr(), stream), "pinnk_dqn_forward")
     return q.reshape(*states.shape[:-1], out.out_features)
 
 

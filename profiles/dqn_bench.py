@@ -13,7 +13,7 @@ def timed(fn, reps=200):
     for _ in range(reps): fn()
     e.record(); torch.cuda.synchronize()
     return a.elapsed_time(e) / reps * 1e3
-for hidden, n in ((128, 10000), (128, 1000000), (256, 10000)):
+for hidden, n in ((128, 10000), (128, 1000000), (256, 10000), (512, 10000), (512, 1000000)):
     net = rl.DQNNetwork(2, 1, hidden).to(dev)
     twin = torch.nn.Sequential(*[torch.nn.Sequential(*list(g)) if isinstance(g, torch.nn.Sequential) else g for g in net.layers])
     x = torch.rand(n, 2, device=dev)

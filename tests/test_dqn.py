@@ -37,8 +37,9 @@ def test_mirror_loads_reference_state_dict_and_refuses_cpu():
         rl.dqn_forward(net, pts)                     # CPU tensors: no fallback
     with pytest.raises(rl.UnsupportedQNetwork):
         rl._lower(torch.nn.Sequential(torch.nn.Linear(2, 1)))
-    with pytest.raises(rl.UnsupportedQNetwork):       # wider than the one-launch kernel is used for: declined, loudly
-        rl._lower(rl.DQNNetwork(2, 1, 512))
+    rl._lower(rl.DQNNetwork(2, 1, 512))               # the shipped width (config.yaml:363): the tcgen05 route takes it
+    with pytest.raises(rl.UnsupportedQNetwork):       # neither <= 128 nor a multiple of 128: declined, loudly
+        rl._lower(rl.DQNNetwork(2, 1, 200))
 
 
 def _torch_twin(net):
@@ -83,6 +84,50 @@ def test_gpu_shapes_against_oracle(state_dim, hidden, layers, actions, n, monkey
     err = float((q.double().cpu() - ref).norm() / ref.norm())
     assert err <= 1e-5, err
     assert rl.dqn_forward(net, x[:0]).shape == (0, actions)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("state_dim,hidden,layers,actions,n,train", [
+    (2, 512, 3, 1, 10000, False),      # the shipped agent (config.yaml:363, train.py:348-351) on the 100 x 100 grid
+    (2, 512, 3, 1, 10000, True),       # with live dropout, as the reference scores (policy_net stays in train mode)
+    (2, 256, 3, 1, 4097, False), (3, 384, 4, 2, 1000, True), (2, 1024, 2, 1, 333, False), (8, 640, 3, 1, 64, False),
+    (2, 512, 3, 1, 1, False), (2, 512, 3, 1, 1000000, False)])
+def test_gpu_wide_q_networks_on_the_tensor_core_route(state_dim, hidden, layers, actions, n, train):
+    """pinnk_dqn_forward_wide: hidden Linear layers on the tcgen05 3xTF32 rows kernel, LayerNorm / ReLU / mask / first and
+    output layer in one row kernel -- against the same torch modules in fp64 (eval) or on the same generator state (train)."""
+    import parity_log
+    from pinns_rl_pde_b200 import rl, _lib
+    dev = torch.device("cuda:0")
+    torch.manual_seed(hidden + n)
+    net = rl.DQNNetwork(state_dim, actions, hidden, num_layers=layers).to(dev)
+    with torch.no_grad():
+        for name, p in net.named_parameters():
+            if name.endswith("bias") or ".1.weight" in name:
+                p.add_(0.1 * torch.randn_like(p))
+    net.train(train)
+    twin = _torch_twin(net).train(train)
+    x = torch.rand(n, state_dim, device=dev) * 2 - 1
+    torch.manual_seed(5)
+    before = _lib.launch_count()
+    q = rl.dqn_forward(net, x)
+    launches = _lib.launch_count() - before
+    after = torch.rand(4, device=dev)
+    assert q.shape == (n, actions) and launches == (layers - 1) + (layers - 2) * (hidden // 128)
+    torch.manual_seed(5)
+    with torch.no_grad():
+        ref32 = twin(x)
+        after_ref = torch.rand(4, device=dev)
+        if train:
+            ref = ref32.double()                                 # same masks only through the same generator calls
+        else:
+            import copy
+            ref = copy.deepcopy(twin).double()(x.double())
+    assert torch.equal(after, after_ref)                         # the generator advanced exactly as under the torch modules
+    err = float((q.double() - ref).norm() / ref.norm())
+    floor = float((ref32.double() - ref).norm() / ref.norm())
+    parity_log.log(f"[dqn wide] hidden {hidden} x {layers - 1} groups, {n} states, {'train' if train else 'eval'}: rel err vs "
+                   f"{'torch fp32 (same masks)' if train else 'fp64'} {err:.2e} (torch fp32 vs fp64 {floor:.2e}), {launches} launches")
+    assert err <= max(1e-5, 2 * floor), (err, floor)
 
 
 @pytest.mark.gpu
