@@ -202,7 +202,7 @@ def test_adaptive_sampler_keeps_foreign_agents_on_their_own_forward():
     pts = torch.rand(50, 2)
     p = rl.grid_scores(agent, pts)
     assert calls == [pts.shape] and abs(float(p.sum()) - 1.0) < 1e-6 and p.shape == (1, 50)
-    agent.policy_net = rl.DQNNetwork(2, 1, 512)                       # wider than rl.MAX_HIDDEN: declined, agent's own forward
+    agent.policy_net = rl.DQNNetwork(2, 1, 200)                       # wider than rl.MAX_HIDDEN and not a multiple of 128: declined, agent's own forward
     rl.grid_scores(agent, pts)
     assert len(calls) == 2
     pde = product_pde("burgers", torch.device("cpu"))
