@@ -8,6 +8,7 @@ seeded runs see the same points and targets.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Any, Callable, Dict, List, Optional, Tuple, Union
 
@@ -248,9 +249,16 @@ class PDEBase:
         x_pool, t_pool = self._sample_uniform(num_points * 4)
         x_pool, t_pool = x_pool.to(self.device), t_pool.to(self.device)
         mag, _ = F.score_residual(self, model, x_pool, t_pool, want_abs=True)
-        # probs = |r| + 1e-8, multinomial with replacement (pde_base.py:924-931): inverse-CDF draw on the device straight from
-        # the scoring kernel's |r| (no normalised copy, no 2^24 limit, no host round trip)
-        sel = weighted_sample_device(mag, 1e-8, num_points)
+        # probs = |r| + 1e-8, multinomial with replacement (pde_base.py:924-931).  Up to torch.multinomial's 2^24 categories
+        # the draw IS torch.multinomial on the reference's normalised probabilities: the same generator calls, hence the same
+        # random stream as the reference for the rest of the run (trajectory parity).  Beyond that, where the reference fails
+        # (SURVEY F7), or with PINNK_DEVICE_SAMPLER=1: inverse-CDF draw on the device straight from the scoring kernel's |r|
+        # (no normalised copy, no host round trip).
+        if use_device_sampler(mag.numel()):
+            sel = weighted_sample_device(mag, 1e-8, num_points)
+        else:
+            probs = mag.reshape(-1) + 1e-8
+            sel = torch.multinomial(probs / probs.sum(), num_points, replacement=True)
         return x_pool[sel].detach(), t_pool[sel].detach()
 
     def generate_collocation_points(self, num_points: int, strategy: str = "uniform", **kwargs):
@@ -304,6 +312,12 @@ class PDEBase:
                 "mean_error": torch.mean(err).item()}
 
 
+def use_device_sampler(n: int) -> bool:
+    """torch.multinomial serves up to 2^24 categories with the reference's own generator calls; pinnk_sample_weighted takes
+    over beyond that, or everywhere with PINNK_DEVICE_SAMPLER=1 (a different, equally distributed draw)."""
+    return n > (1 << 24) or os.environ.get("PINNK_DEVICE_SAMPLER", "0") == "1"
+
+
 def weighted_sample_device(weights: torch.Tensor, eps: float, num_samples: int) -> torch.Tensor:
     """``torch.multinomial((w + eps) / sum, num_samples, replacement=True)`` on the device for ANY number of categories
     (pinnk_sample_weighted: fp64 block sums, one scan, one warp per sample; torch.multinomial stops at 2^24).
@@ -354,7 +368,7 @@ def multinomial_large(weights: torch.Tensor, num_samples: int, block: int = 1 <<
     (SURVEY F7): draw a block proportionally to block mass, then a point inside the block."""
     w = weights.reshape(-1).to(torch.float32)
     n = w.numel()
-    if w.is_cuda:
+    if w.is_cuda and use_device_sampler(n):
         return weighted_sample_device(w, 0.0, num_samples)
     if n <= (1 << 24):
         return torch.multinomial(w / w.sum(), num_samples, replacement=True)

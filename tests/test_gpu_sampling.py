@@ -82,13 +82,25 @@ def test_jittered_grid_is_bit_identical_to_the_torch_ops():
     assert torch.equal(s1, torch.cuda.get_rng_state(0))
 
 
-def test_rar_sampler_prefers_high_residual_regions_and_stays_on_device():
+def test_rar_sampler_prefers_high_residual_regions_and_stays_on_device(monkeypatch):
     import pinns_rl_pde_b200 as pk
     dev = torch.device(DEV)
     torch.manual_seed(0)
     model = pk.make_model("feedforward", 2, 64, 3, dev)
     pde = product_pde("burgers", dev)
+    # same generator state -> the draw is the reference's torch.multinomial on (|r| + 1e-8) / sum  (pde_base.py:924-931)
+    torch.manual_seed(5)
     x, t = pde.generate_collocation_points(4000, strategy="residual_based", model=model)
+    assert x.shape == (4000, 1) and t.shape == (4000, 1)
+    torch.manual_seed(5)
+    xq, tq = pde._sample_uniform(16000)
+    mag = pde.score_residual(model, xq, tq)[0].reshape(-1) + 1e-8
+    sel = torch.multinomial(mag / mag.sum(), 4000, replacement=True)
+    assert torch.equal(x, xq[sel]) and torch.equal(t, tq[sel])
+    # the device sampler (the route beyond 2^24 candidates) on the same pool: another draw of the same distribution
+    monkeypatch.setenv("PINNK_DEVICE_SAMPLER", "1")
+    x, t = pde.generate_collocation_points(4000, strategy="residual_based", model=model)
+    monkeypatch.delenv("PINNK_DEVICE_SAMPLER")
     assert x.shape == (4000, 1) and t.shape == (4000, 1)
     # the selected points carry larger residuals on average than the pool they were drawn from
     xp, tp = pde._sample_uniform(16000)
