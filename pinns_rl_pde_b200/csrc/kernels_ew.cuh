@@ -126,7 +126,7 @@ __global__ void act_fwd_kernel(const float* __restrict__ Z, const float* __restr
 // G (in: dL/dY, out: dL/dZ) in place; Z (+S) is the stashed pre-activation.
 template <int ACT, int MAXK>
 __global__ void act_bwd_kernel(const float* __restrict__ Z, const float* __restrict__ S, float* __restrict__ G,
-                               int64_t n, int width, JetSpec js, float omega) {
+                               int64_t n, int width, JetSpec js, float omega, const float* __restrict__ G2 = nullptr) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * width) return;
   const int64_t p = idx / width;
@@ -141,7 +141,7 @@ __global__ void act_bwd_kernel(const float* __restrict__ Z, const float* __restr
     z[0] *= omega;
     sincosf(z[0], &y[0], &w[0]);
   }
-  yb[0] = G[base];
+  yb[0] = G[base] + (G2 ? G2[base] : 0.f);      // G2: a second adjoint of the same output (arriving over a skip connection)
   float wb0 = 0.f;   // tanh: adjoint of w0 ; sin: adjoint of c0
   for (int d = 0; d < js.ndirs; ++d) {
     const int K = js.order[d];
@@ -152,7 +152,7 @@ __global__ void act_bwd_kernel(const float* __restrict__ Z, const float* __restr
         const int64_t o = b1 + (int64_t)(k - 1) * width;
         z[k] = Z[o] + (S ? S[o] : 0.f);
         if (ACT == 2) z[k] *= omega;
-        yb[k] = G[o];
+        yb[k] = G[o] + (G2 ? G2[o] : 0.f);
       } else {
         yb[k] = 0.f;
       }
@@ -767,6 +767,373 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ Z, const float* _
     }
   }
   // block-level accumulation of dgamma / dbeta
+#pragma unroll
+  for (int i = 0; i < NPER; ++i) {
+    const int f = lane + 32 * i;
+    if (f < width) {
+      atomicAdd(&red[f], dg[i]);
+      atomicAdd(&red[width + f], db[i]);
+    }
+  }
+  __syncthreads();
+  for (int f = threadIdx.x; f < width; f += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + f, red[f]);
+    if (dbeta) atomicAdd(dbeta + f, red[width + f]);
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm + activation in one sweep
+// Y = act(LayerNorm(Z) (+ S)): resnet.py:45-65 runs Linear -> LayerNorm -> tanh and Linear -> LayerNorm -> (+ x) -> tanh; as
+// separate kernels the LayerNorm output makes a round trip through HBM in the forward pass and is read twice more in the
+// reverse pass.  One warp per point as above; the normalised jets stay in registers and go straight into the activation
+// recurrences of each of the lane's NPER features.
+template <int ACT, int MAXK, int NPER>
+__global__ void lnact_fwd_kernel(const float* __restrict__ Z, const float* __restrict__ S, float* __restrict__ Y, int64_t n,
+                                 int width, JetSpec js, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                 float eps, float omega) {
+  const int lane = threadIdx.x & 31;
+  const int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (p >= n) return;
+  const float inv_w = 1.f / (float)width;
+  const int64_t base = p * js.ncols * width;
+  float c0[NPER], g[NPER], y0[NPER], w0[NPER];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NPER; ++i) {
+    const int f = lane + 32 * i;
+    c0[i] = (f < width) ? Z[base + f] : 0.f;
+    g[i] = (f < width) ? gamma[f] : 0.f;
+    sum += c0[i];
+  }
+  const float mean0 = warp_sum(sum) * inv_w;
+  float vs = 0.f;
+#pragma unroll
+  for (int i = 0; i < NPER; ++i) {
+    const int f = lane + 32 * i;
+    c0[i] = (f < width) ? (c0[i] - mean0) : 0.f;
+    vs += c0[i] * c0[i];
+  }
+  float v[MAXK + 1], s[MAXK + 1];
+  v[0] = warp_sum(vs) * inv_w + eps;
+  s[0] = 1.f / sqrtf(v[0]);
+#pragma unroll
+  for (int i = 0; i < NPER; ++i) {
+    const int f = lane + 32 * i;
+    if (f < width) {
+      float z0 = g[i] * c0[i] * s[0] + beta[f];
+      if (S) z0 += S[base + f];
+      if (ACT == 1) { y0[i] = tanhf(z0); w0[i] = 1.f - y0[i] * y0[i]; }
+      else { z0 *= omega; sincosf(z0, &y0[i], &w0[i]); }
+      Y[base + f] = y0[i];
+    } else {
+      y0[i] = 0.f; w0[i] = 0.f;
+    }
+  }
+  for (int d = 0; d < js.ndirs; ++d) {
+    const int K = js.order[d];
+    const int64_t b1 = base + (int64_t)js.col0[d] * width;
+    float c[MAXK + 1][NPER], sj[MAXK + 1][NPER];
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) c[0][i] = c0[i];
+    // every load of the direction is issued before the first reduction needs one
+#pragma unroll
+    for (int k = 1; k <= MAXK; ++k)
+#pragma unroll
+      for (int i = 0; i < NPER; ++i) {
+        const int f = lane + 32 * i;
+        const bool in = k <= K && f < width;
+        c[k][i] = in ? Z[b1 + (int64_t)(k - 1) * width + f] : 0.f;
+        sj[k][i] = (in && S) ? S[b1 + (int64_t)(k - 1) * width + f] : 0.f;
+      }
+#pragma unroll
+    for (int k = 1; k <= MAXK; ++k) {
+      if (k <= K) {
+        float sm = 0.f;
+#pragma unroll
+        for (int i = 0; i < NPER; ++i) sm += c[k][i];
+        const float mk = warp_sum(sm) * inv_w;
+        float vk = 0.f;
+#pragma unroll
+        for (int i = 0; i < NPER; ++i) {
+          const int f = lane + 32 * i;
+          c[k][i] = (f < width) ? (c[k][i] - mk) : 0.f;
+#pragma unroll
+          for (int j = 0; j <= k; ++j) vk += c[j][i] * c[k - j][i];
+        }
+        v[k] = warp_sum(vk) * inv_w;
+      }
+    }
+    rsqrt_dir_fwd<MAXK, float>(K, v, s);
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) {
+      const int f = lane + 32 * i;
+      if (f < width) {
+        float z[MAXK + 1], y[MAXK + 1], w[MAXK + 1];
+        z[0] = 0.f; y[0] = y0[i]; w[0] = w0[i];
+#pragma unroll
+        for (int k = 1; k <= MAXK; ++k) {
+          if (k <= K) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j <= k; ++j) a += c[j][i] * s[k - j];
+            z[k] = g[i] * a + sj[k][i];
+            if (ACT == 2) z[k] *= omega;
+          } else {
+            z[k] = 0.f;
+          }
+        }
+        if (ACT == 1) tanh_dir_fwd<MAXK, float>(K, z, y, w);
+        else sincos_dir_fwd<MAXK, float>(K, z, y, w);
+#pragma unroll
+        for (int k = 1; k <= MAXK; ++k)
+          if (k <= K) Y[b1 + (int64_t)(k - 1) * width + f] = y[k];
+      }
+    }
+  }
+}
+
+// Reverse of lnact_fwd_kernel in one sweep: Gin (+ Gin2, the adjoint arriving over a skip connection, nullable) = dL/dY;
+// Gout = dL/dZ (a buffer distinct from Gin); Gz (nullable, may alias Gin) receives dL/d(pre-activation), which is the adjoint
+// of the skip source S.  LayerNorm and activation jets are recomputed from Z (+ S); per direction the activation adjoint
+// produces the adjoint of the normalised jets in registers and the LayerNorm reverse consumes it on the spot.  The order-0
+// terms, which need the activation's order-0 adjoint of ALL directions, are linear accumulations and run after the loop.
+template <int ACT, int MAXK, int NPER>
+__global__ void __launch_bounds__(128)
+lnact_bwd_kernel(const float* __restrict__ Z, const float* __restrict__ S, const float* Gin, const float* __restrict__ Gin2,
+                 float* Gz, float* __restrict__ Gout, int64_t n, int width, JetSpec js, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, float omega, float* __restrict__ dgamma,
+                 float* __restrict__ dbeta) {
+  extern __shared__ float red[];   // [2][width]
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const float inv_w = 1.f / (float)width;
+  for (int i = threadIdx.x; i < 2 * width; i += blockDim.x) red[i] = 0.f;
+  __syncthreads();
+  float g[NPER], dg[NPER], db[NPER];
+#pragma unroll
+  for (int i = 0; i < NPER; ++i) {
+    const int f = lane + 32 * i;
+    g[i] = (f < width) ? gamma[f] : 0.f;
+    dg[i] = 0.f;
+    db[i] = 0.f;
+  }
+  for (int64_t p = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); p < n;
+       p += (int64_t)gridDim.x * warps_per_block) {
+    const int64_t base = p * js.ncols * width;
+    // ---- order 0 of the forward: centred input, 1/sigma, activation value
+    float c0[NPER], y0[NPER], w0[NPER], yb0[NPER], wb0[NPER], cb0[NPER];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) {
+      const int f = lane + 32 * i;
+      c0[i] = (f < width) ? Z[base + f] : 0.f;
+      sum += c0[i];
+    }
+    const float mean0 = warp_sum(sum) * inv_w;
+    float vs = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) {
+      const int f = lane + 32 * i;
+      c0[i] = (f < width) ? (c0[i] - mean0) : 0.f;
+      vs += c0[i] * c0[i];
+    }
+    float v[MAXK + 1], s[MAXK + 1];
+    v[0] = warp_sum(vs) * inv_w + eps;
+    s[0] = 1.f / sqrtf(v[0]);
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) {
+      const int f = lane + 32 * i;
+      if (f < width) {
+        float z0 = g[i] * c0[i] * s[0] + beta[f];
+        if (S) z0 += S[base + f];
+        if (ACT == 1) { y0[i] = tanhf(z0); w0[i] = 1.f - y0[i] * y0[i]; }
+        else { z0 *= omega; sincosf(z0, &y0[i], &w0[i]); }
+        yb0[i] = Gin[base + f] + (Gin2 ? Gin2[base + f] : 0.f);
+      } else {
+        y0[i] = 0.f; w0[i] = 0.f; yb0[i] = 0.f;
+      }
+      wb0[i] = 0.f;
+      cb0[i] = 0.f;
+    }
+    float sb0 = 0.f, vb0 = 0.f;
+    for (int d = 0; d < js.ndirs; ++d) {
+      const int K = js.order[d];
+      const int64_t b1 = base + (int64_t)js.col0[d] * width;
+      float c[MAXK + 1][NPER], yb[MAXK + 1][NPER], sj[MAXK + 1][NPER];
+#pragma unroll
+      for (int i = 0; i < NPER; ++i) { c[0][i] = c0[i]; yb[0][i] = 0.f; }
+      // every load of the direction (input jets, skip jets, output adjoints) is issued before the first reduction needs one
+      // and before any store of this direction (Gz may alias Gin)
+#pragma unroll
+      for (int k = 1; k <= MAXK; ++k)
+#pragma unroll
+        for (int i = 0; i < NPER; ++i) {
+          const int f = lane + 32 * i;
+          const bool in = k <= K && f < width;
+          const int64_t o = b1 + (int64_t)(k - 1) * width + f;
+          c[k][i] = in ? Z[o] : 0.f;
+          sj[k][i] = (in && S) ? S[o] : 0.f;
+          yb[k][i] = in ? Gin[o] + (Gin2 ? Gin2[o] : 0.f) : 0.f;
+        }
+#pragma unroll
+      for (int k = 1; k <= MAXK; ++k) {
+        if (k <= K) {
+          float sm = 0.f;
+#pragma unroll
+          for (int i = 0; i < NPER; ++i) sm += c[k][i];
+          const float mk = warp_sum(sm) * inv_w;
+          float vk = 0.f;
+#pragma unroll
+          for (int i = 0; i < NPER; ++i) {
+            const int f = lane + 32 * i;
+            c[k][i] = (f < width) ? (c[k][i] - mk) : 0.f;
+#pragma unroll
+            for (int j = 0; j <= k; ++j) vk += c[j][i] * c[k - j][i];
+          }
+          v[k] = warp_sum(vk) * inv_w;
+        } else {
+          v[k] = 0.f;
+        }
+      }
+      rsqrt_dir_fwd<MAXK, float>(K, v, s);
+      // ---- activation: forward jets from the normalised jets, then its adjoint -> yb[k][i] = dL/d(LayerNorm output jets)
+#pragma unroll
+      for (int i = 0; i < NPER; ++i) {
+        const int f = lane + 32 * i;
+        if (f < width) {
+          float z[MAXK + 1], y[MAXK + 1], w[MAXK + 1], ab[MAXK + 1], zb[MAXK + 1];
+          z[0] = 0.f; y[0] = y0[i]; w[0] = w0[i]; ab[0] = yb0[i];
+#pragma unroll
+          for (int k = 1; k <= MAXK; ++k) {
+            if (k <= K) {
+              float a = 0.f;
+#pragma unroll
+              for (int j = 0; j <= k; ++j) a += c[j][i] * s[k - j];
+              z[k] = g[i] * a + sj[k][i];
+              if (ACT == 2) z[k] *= omega;
+              ab[k] = yb[k][i];
+            } else {
+              z[k] = 0.f; ab[k] = 0.f;
+            }
+          }
+          if (ACT == 1) {
+            tanh_dir_fwd<MAXK, float>(K, z, y, w);
+            tanh_dir_bwd<MAXK, float>(K, z, y, w, ab, zb, wb0[i]);
+          } else {
+            float wb[MAXK + 1];
+#pragma unroll
+            for (int k = 0; k <= MAXK; ++k) wb[k] = 0.f;
+            wb[0] = wb0[i];
+            sincos_dir_fwd<MAXK, float>(K, z, y, w);
+            sincos_dir_bwd<MAXK, float>(K, z, y, w, ab, wb, zb);
+            wb0[i] = wb[0];
+          }
+          yb0[i] = ab[0];
+#pragma unroll
+          for (int k = 1; k <= MAXK; ++k)
+            yb[k][i] = (k <= K) ? ((ACT == 2) ? zb[k] * omega : zb[k]) : 0.f;
+        }
+      }
+      if (Gz) {
+#pragma unroll
+        for (int k = 1; k <= MAXK; ++k)
+          if (k <= K) {
+#pragma unroll
+            for (int i = 0; i < NPER; ++i) {
+              const int f = lane + 32 * i;
+              if (f < width) Gz[b1 + (int64_t)(k - 1) * width + f] = yb[k][i];
+            }
+          }
+      }
+      // ---- LayerNorm reverse for this direction (as layernorm_bwd_kernel)
+      float sb[MAXK + 1], cb[MAXK + 1][NPER];
+#pragma unroll
+      for (int m = 0; m <= MAXK; ++m) {
+        float part = 0.f;
+#pragma unroll
+        for (int i = 0; i < NPER; ++i) {
+          float a = 0.f;
+#pragma unroll
+          for (int k = (m > 1 ? m : 1); k <= MAXK; ++k)
+            if (k <= K) {
+              a += yb[k][i] * s[k - m];
+              part += g[i] * yb[k][i] * c[k - m][i];
+            }
+          cb[m][i] = g[i] * a;
+        }
+        sb[m] = warp_sum(part);
+      }
+#pragma unroll
+      for (int k = 1; k <= MAXK; ++k)
+        if (k <= K) {
+#pragma unroll
+          for (int i = 0; i < NPER; ++i) {
+            float a = 0.f;
+#pragma unroll
+            for (int j = 0; j <= k; ++j) a += c[j][i] * s[k - j];
+            dg[i] += yb[k][i] * a;
+          }
+        }
+      float vb[MAXK + 1];
+      rsqrt_dir_bwd<MAXK, float>(K, v, s, sb, vb, vb0);
+      sb0 += sb[0];
+#pragma unroll
+      for (int m = 0; m <= MAXK; ++m) {
+#pragma unroll
+        for (int i = 0; i < NPER; ++i) {
+          float a = 0.f;
+#pragma unroll
+          for (int k = (m > 1 ? m : 1); k <= MAXK; ++k)
+            if (k <= K) a += vb[k] * c[k - m][i];
+          cb[m][i] += 2.f * inv_w * a;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NPER; ++i) cb0[i] += cb[0][i];
+#pragma unroll
+      for (int k = 1; k <= MAXK; ++k)
+        if (k <= K) {
+          float sm = 0.f;
+#pragma unroll
+          for (int i = 0; i < NPER; ++i) sm += cb[k][i];
+          const float mk = warp_sum(sm) * inv_w;
+#pragma unroll
+          for (int i = 0; i < NPER; ++i) {
+            const int f = lane + 32 * i;
+            if (f < width) Gout[b1 + (int64_t)(k - 1) * width + f] = cb[k][i] - mk;
+          }
+        }
+    }
+    // ---- order 0: close the activation adjoint, then the LayerNorm's direct terms and its closure
+    {
+      float part = 0.f;
+#pragma unroll
+      for (int i = 0; i < NPER; ++i) {
+        const int f = lane + 32 * i;
+        const float a0 = (ACT == 1) ? tanh_finish_bwd<float>(y0[i], w0[i], yb0[i], wb0[i])
+                                    : (yb0[i] * w0[i] - wb0[i] * y0[i]) * omega;
+        if (Gz && f < width) Gz[base + f] = a0;
+        dg[i] += a0 * c0[i] * s[0];
+        db[i] += a0;
+        cb0[i] += g[i] * a0 * s[0];
+        part += g[i] * a0 * c0[i];
+      }
+      sb0 += warp_sum(part);
+    }
+    vb0 += sb0 * (-0.5f) * s[0] / v[0];
+    float sm = 0.f;
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) {
+      cb0[i] += 2.f * inv_w * vb0 * c0[i];
+      sm += cb0[i];
+    }
+    const float m0 = warp_sum(sm) * inv_w;
+#pragma unroll
+    for (int i = 0; i < NPER; ++i) {
+      const int f = lane + 32 * i;
+      if (f < width) Gout[base + f] = cb0[i] - m0;
+    }
+  }
 #pragma unroll
   for (int i = 0; i < NPER; ++i) {
     const int f = lane + 32 * i;

@@ -406,6 +406,66 @@ static int ln_bwd(const ChunkCtx& c, const float* Z, const float* Gin, float* Go
   return 0;
 }
 
+// LayerNorm + activation as ONE kernel each way (lnact_fwd_kernel / lnact_bwd_kernel): index of the ACT op that consumes
+// LAYERNORM op `ln` directly (possibly across a SKIP_ADD marker), or -1.  Forward and reverse pass both ask this function:
+// for a fused pair the LayerNorm output is never written, and the reverse pass recomputes it from the LayerNorm input.
+// PINNK_ENABLE_LNACT=1 switches it on (read per call so that tests can switch it).  Measured and NOT the default: with one warp
+// per point and 8 features per lane the activation recurrences of a point run serially at 8 - 16 warps per SM, and the pair
+// costs more than the two bandwidth-bound kernels it replaces (C3, 262 144 points: forward 22.2 ms vs 6.8 + 9.5, reverse
+// 75.9 ms vs 16.8 + 10.7; profiles/r02r_c3_lnact.log).  The separate kernels already run at 4.3 - 5.7 TB/s.
+static int lnact_partner(const pinnk_plan_t pl, int ln) {
+  const char* e = getenv("PINNK_ENABLE_LNACT");
+  if (!(e && e[0] == '1')) return -1;
+  const int n_ops = (int)pl->ops.size();
+  if (ln < 1 || ln >= n_ops - 1 || pl->ops[ln].op.kind != PINNK_OP_LAYERNORM) return -1;
+  int j = ln + 1;
+  if (j < n_ops - 1 && pl->ops[j].op.kind == PINNK_OP_SKIP_ADD) ++j;
+  if (j >= n_ops - 1 || pl->ops[j].op.kind != PINNK_OP_ACT || pl->ops[j].in_op != ln) return -1;
+  return j;
+}
+static int lnact_of_act(const pinnk_plan_t pl, int act) {
+  if (act < 1 || pl->ops[act].op.kind != PINNK_OP_ACT) return -1;
+  const int ln = pl->ops[act].in_op;
+  return (ln >= 1 && lnact_partner(pl, ln) == act) ? ln : -1;
+}
+
+template <int MAXK>
+static int lnact_fwd(const ChunkCtx& c, const float* Z, const float* S, float* Y, int width, const float* g, const float* b,
+                     float eps, int act, float omega) {
+  ProfScope ps(PC_LN_FWD, c.st);
+  const int threads = 256;
+  const unsigned blocks = blocks_for(c.n * 32, threads);
+  const int nper = (width + 31) / 32;
+#define LNA_F(A, NP) lnact_fwd_kernel<A, MAXK, NP><<<blocks, threads, 0, c.st>>>(Z, S, Y, c.n, width, c.pl->js, g, b, eps, omega)
+#define LNA_FA(NP) do { if (act == PINNK_ACT_TANH) LNA_F(1, NP); else LNA_F(2, NP); } while (0)
+  if (nper <= 1) LNA_FA(1); else if (nper <= 2) LNA_FA(2); else if (nper <= 4) LNA_FA(4); else LNA_FA(8);
+#undef LNA_FA
+#undef LNA_F
+  PK_LAUNCH_OK();
+  return 0;
+}
+
+template <int MAXK>
+static int lnact_bwd(const ChunkCtx& c, const float* Z, const float* S, const float* Gin, const float* Gin2, float* Gz,
+                     float* Gout, int width, const float* g, const float* b, float eps, int act, float omega, float* dg,
+                     float* db) {
+  ProfScope ps(PC_LN_BWD, c.st);
+  const int threads = 128;
+  const int wpb = threads / 32;
+  int64_t blocks = (c.n + wpb - 1) / wpb;
+  const int64_t cap = (int64_t)c.pl->sm_count * 16;
+  if (blocks > cap) blocks = cap;
+  const size_t sh = 2 * (size_t)width * sizeof(float);
+  const int nper = (width + 31) / 32;
+#define LNA_B(A, NP) lnact_bwd_kernel<A, MAXK, NP><<<(unsigned)blocks, threads, sh, c.st>>>(Z, S, Gin, Gin2, Gz, Gout, c.n, width, c.pl->js, g, b, eps, omega, dg, db)
+#define LNA_BA(NP) do { if (act == PINNK_ACT_TANH) LNA_B(1, NP); else LNA_B(2, NP); } while (0)
+  if (nper <= 1) LNA_BA(1); else if (nper <= 2) LNA_BA(2); else if (nper <= 4) LNA_BA(4); else LNA_BA(8);
+#undef LNA_BA
+#undef LNA_B
+  PK_LAUNCH_OK();
+  return 0;
+}
+
 // (K0, K1) of the fused tcgen05 epilogues, or false when the jet spec has more than two directions
 static bool jet_orders(const JetSpec& js, int& k0, int& k1) {
   if (js.ndirs > 2) return false;
@@ -608,6 +668,15 @@ static int forward_chunk(const ChunkCtx& c, bool keep_stash = true) {
         break;
       }
       case PINNK_OP_LAYERNORM: {
+        const int ja = lnact_partner(pl, i);
+        if (ja >= 0) {      // LayerNorm + the activation behind it in one sweep; the LayerNorm output is never written
+          const OpRt& ar = pl->ops[ja];
+          int rc = lnact_fwd<MAXK>(c, in, ar.skip_src >= 0 ? c.stash(ar.skip_src) : nullptr, c.stash(ja), o.in_dim,
+                                   c.params[o.w_index], c.params[o.b_index], o.eps, ar.op.act, ar.op.scale);
+          if (rc) return rc;
+          i = ja;
+          break;
+        }
         int rc = ln_fwd<MAXK>(c, in, c.stash(i), o.in_dim, c.params[o.w_index], c.params[o.b_index], o.eps);
         if (rc) return rc;
         break;
@@ -634,6 +703,7 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad, bool last_done = 
   const int threads = 256;
   int cur = 0;            // adjoint buffer holding dL/d(output of the op being processed)
   int held = -1;          // buffer holding the skip-branch adjoint
+  int pend = -1;          // buffer whose adjoint the next fused LayerNorm + activation reverse kernel adds to its input
   auto other = [&](int a, int b) { for (int k = 0; k < 3; ++k) if (k != a && k != b) return k; return -1; };
   auto G = [&](int64_t off) -> float* { return off >= 0 ? flat_grad + off : nullptr; };
   // earliest op that still needs an input adjoint: stop propagating below the last trainable op
@@ -713,8 +783,9 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad, bool last_done = 
             const OpRt& pa = pl->ops[i - 1];
             // (the first activation's adjoint is fused with the first Linear instead, and has no stash to read)
             const bool first_pair = pl->fuse_first && i - 1 == 1 && first_trainable == 0;
+            // (an activation fused with the LayerNorm in front of it has no stashed input: its adjoint runs in lnact_bwd)
             if (tc_enabled() && r.in_op == i - 1 && pa.op.kind == PINNK_OP_ACT && pa.skip_src < 0 && pa.in_op >= 0 &&
-                !first_pair && jet_orders(js, k0, k1)) {
+                !first_pair && lnact_of_act(pl, i - 1) < 0 && jet_orders(js, k0, k1)) {
               ProfScope ps(PC_GEMM_DGRAD, c.st);
               const bool from_y = z_elided(pl, pa.in_op);      // the forward did not stash this pre-activation
               rc = tc_linear_dgrad_actbwd(c.adj(cur), W, from_y ? c.stash(i - 1) : c.stash(pa.in_op), c.adj(nxt), c.n * js.ncols,
@@ -776,27 +847,42 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad, bool last_done = 
         }
         const float* S = (r.skip_src >= 0) ? c.stash(r.skip_src) : nullptr;
         const unsigned blocks = blocks_for(c.n * o.in_dim, threads);
+        const int ln = lnact_of_act(pl, i);
+        if (ln >= 0) {
+          // activation adjoint + LayerNorm reverse in one sweep: dL/dY in adj(cur) (+ adj(pend), the skip adjoint deferred at
+          // SKIP_SAVE) -> dL/d(LayerNorm input) in a free buffer; with a skip the pre-activation adjoint is written in place
+          // and becomes the held skip adjoint (no copy)
+          const OpRt& lr = pl->ops[ln];
+          const int nxt = other(cur, held >= 0 ? held : pend);
+          int rc = lnact_bwd<MAXK>(c, c.stash(lr.in_op), S, c.adj(cur), pend >= 0 ? c.adj(pend) : nullptr,
+                                   r.skip_src >= 0 ? c.adj(cur) : nullptr, c.adj(nxt), o.in_dim, c.params[lr.op.w_index],
+                                   c.params[lr.op.b_index], lr.op.eps, o.act, o.scale, G(lr.op.gw_offset), G(lr.op.gb_offset));
+          if (rc) return rc;
+          pend = -1;
+          if (r.skip_src >= 0) held = cur;
+          cur = nxt;
+          i = ln;          // the LayerNorm (and a SKIP_ADD marker in between) are done
+          break;
+        }
         if (z_elided(pl, r.in_op)) return fail(PINNK_E_INVALID, "backward: generic activation adjoint reached for an elided pre-activation stash");
         ProfScope ps(PC_ACT_BWD, c.st);
-        if (act_ppt2_enabled()) {
+        // G2: the skip adjoint deferred at SKIP_SAVE is added while the output adjoint is read (no separate add kernel)
+        const float* G2 = pend >= 0 ? c.adj(pend) : nullptr;
+        if (act_ppt2_enabled() && G2 == nullptr) {
           const unsigned b2 = blocks_for(((c.n + 1) / 2) * o.in_dim, threads);
           if (o.act == PINNK_ACT_TANH)
             act_bwd_multi_kernel<1, MAXK, 2><<<b2, threads, 0, c.st>>>(in, S, c.adj(cur), c.n, o.in_dim, js, 1.f);
           else
             act_bwd_multi_kernel<2, MAXK, 2><<<b2, threads, 0, c.st>>>(in, S, c.adj(cur), c.n, o.in_dim, js, o.scale);
         } else if (o.act == PINNK_ACT_TANH)
-          act_bwd_kernel<1, MAXK><<<blocks, threads, 0, c.st>>>(in, S, c.adj(cur), c.n, o.in_dim, js, 1.f);
+          act_bwd_kernel<1, MAXK><<<blocks, threads, 0, c.st>>>(in, S, c.adj(cur), c.n, o.in_dim, js, 1.f, G2);
         else
-          act_bwd_kernel<2, MAXK><<<blocks, threads, 0, c.st>>>(in, S, c.adj(cur), c.n, o.in_dim, js, o.scale);
+          act_bwd_kernel<2, MAXK><<<blocks, threads, 0, c.st>>>(in, S, c.adj(cur), c.n, o.in_dim, js, o.scale, G2);
         PK_LAUNCH_OK();
-        if (r.skip_src >= 0) {
-          // dL/dz feeds both the LayerNorm branch and the skip: keep this buffer, continue in a copy
-          const int nxt = other(cur, -1);
-          PK_CHECK_CUDA(cudaMemcpyAsync(c.adj(nxt), c.adj(cur), sizeof(float) * c.n * js.ncols * o.in_dim,
-                                        cudaMemcpyDeviceToDevice, c.st));
-          held = cur;
-          cur = nxt;
-        }
+        pend = -1;
+        // dL/dz feeds both the LayerNorm branch and the skip: this buffer stays as the held skip adjoint (the LayerNorm
+        // reverse below reads it and writes another buffer, so no copy is needed)
+        if (r.skip_src >= 0) held = cur;
         break;
       }
       case PINNK_OP_LAYERNORM: {
@@ -808,6 +894,14 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad, bool last_done = 
       }
       case PINNK_OP_SKIP_SAVE: {
         if (held < 0) return fail(PINNK_E_INVALID, "backward: SKIP_SAVE without a held adjoint");
+        if (i - 1 >= first_trainable && pl->ops[i - 1].op.kind == PINNK_OP_ACT && !(i - 1 == 1 && pl->fuse_first && tc_enabled()) &&
+            !z_elided(pl, pl->ops[i - 1].in_op)) {
+          // the op below is an activation whose reverse kernel (act_bwd_kernel / lnact_bwd_kernel) adds the two adjoints
+          // while it reads them: no separate add pass
+          pend = held;
+          held = -1;
+          break;
+        }
         const int64_t cnt = c.n * js.ncols * pl->ops[r.in_op].op.out_dim;
         add_inplace_kernel<<<blocks_for(cnt, threads), threads, 0, c.st>>>(c.adj(cur), c.adj(held), cnt);
         PK_LAUNCH_OK();

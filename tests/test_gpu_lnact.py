@@ -1,0 +1,63 @@
+"""GPU: LayerNorm + activation as one kernel each way (lnact_fwd_kernel / lnact_bwd_kernel, resnet.py:45-65; opt-in with
+PINNK_ENABLE_LNACT=1 because it measured slower) against the separate LayerNorm and activation kernels of the same library
+on identical seeded inputs.  The switch is read per call, so both routes run in one process.  The default route of residual
+networks (skip adjoint kept in place, deferred add inside the activation adjoint) is covered against the oracle by
+test_gpu_parity.py's ResNet cases."""
+import numpy as np
+import pytest
+import torch
+
+import parity_log
+from helpers import flat_grad, product_pde
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.double().reshape(-1), b.double().reshape(-1)
+    return float((a - b).norm() / b.norm().clamp_min(1e-300))
+
+
+def _step(pde, model, x, t):
+    for p in model.parameters():
+        p.grad = None
+    losses = pde.compute_loss(model, x, t)
+    losses["total"].backward()
+    torch.cuda.synchronize()
+    return ({k: float(losses[k]) for k in ("residual", "boundary", "initial", "total")}, flat_grad(model).clone(),
+            pde.compute_residual(model, x, t).detach().clone(), pde.score_residual(model, x, t)[0].clone())
+
+
+@pytest.mark.parametrize("pde_name,width,blocks,n", [("kdv", 256, 2, 3000), ("burgers", 128, 3, 2500), ("cahn_hilliard", 256, 1, 1100)])
+def test_fused_layernorm_activation_matches_separate_kernels(monkeypatch, pde_name, width, blocks, n):
+    import pinns_rl_pde_b200 as pk
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    model = pk.make_model("resnet", 2, width, blocks, dev)
+    with torch.no_grad():          # LayerNorm affine parameters away from their (1, 0) initial values
+        for m in model.modules():
+            if isinstance(m, torch.nn.LayerNorm):
+                m.weight.add_(0.3 * torch.randn_like(m.weight))
+                m.bias.add_(0.2 * torch.randn_like(m.bias))
+    pde = product_pde(pde_name, dev)
+    g = torch.Generator().manual_seed(5)
+    lo, hi = pde.domain[0]
+    x = (lo + (hi - lo) * torch.rand(n, 1, generator=g)).to(dev)
+    t = (pde.time_domain[0] + (pde.time_domain[1] - pde.time_domain[0]) * torch.rand(n, 1, generator=g)).to(dev)
+    from pinns_rl_pde_b200 import _lib
+    monkeypatch.setenv("PINNK_ENABLE_LNACT", "1")
+    before = _lib.launch_count()
+    fused = _step(pde, model, x, t)
+    n_fused = _lib.launch_count() - before
+    monkeypatch.delenv("PINNK_ENABLE_LNACT")
+    before = _lib.launch_count()
+    plain = _step(pde, model, x, t)
+    n_plain = _lib.launch_count() - before
+    assert n_fused < n_plain, (n_fused, n_plain)              # the fused route really ran (fewer launches)
+    for k in fused[0]:
+        assert abs(fused[0][k] - plain[0][k]) <= 2e-6 * abs(plain[0][k]) + 1e-12, (k, fused[0][k], plain[0][k])
+    eg, er, es = _rel(fused[1], plain[1]), _rel(fused[2], plain[2]), _rel(fused[3], plain[3])
+    parity_log.log(f"[lnact {pde_name} resnet {blocks}x{width}] fused vs separate kernels: grad {eg:.2e}, residual {er:.2e}, "
+                   f"|r| scores {es:.2e}; launches {n_fused} vs {n_plain}")
+    assert eg <= 3e-6 and er <= 3e-6 and es <= 3e-6, (eg, er, es)
+    assert np.isfinite(fused[1].cpu().numpy()).all()
