@@ -596,6 +596,22 @@ def heat_compute_loss(model, residual, domain, time_domain, ic_fn, num_boundary,
             "smoothness": zero, "data": zero.clone(), "total": total}
 
 
+def heat_smoothness_loss(model, x, t, domain, eps=1e-4):
+    """heat_equation.py:625-650 ``_compute_smoothness_loss``: sum over the spatial axes of mean|forward difference| +
+    mean|backward difference| of the model VALUES at x +- eps (clamped to the domain), divided by eps.  Pinned bit-identical
+    (fp32) to the unmodified reference by tests/golden/make_golden.py (fixture x_heat_smoothness.npz)."""
+    u_c = model(torch.cat([x, t], dim=1))
+    out = torch.tensor(0.0, device=x.device)
+    for d in range(x.shape[1]):
+        xp, xm = x.clone(), x.clone()
+        xp[:, d:d + 1] = torch.clamp(x[:, d:d + 1] + eps, domain[d][0], domain[d][1])
+        xm[:, d:d + 1] = torch.clamp(x[:, d:d + 1] - eps, domain[d][0], domain[d][1])
+        u_p = model(torch.cat([xp, t], dim=1))
+        u_m = model(torch.cat([xm, t], dim=1))
+        out = out + torch.mean(torch.abs((u_p - u_c) / eps)) + torch.mean(torch.abs((u_c - u_m) / eps))
+    return out
+
+
 # ------------------------------------------------------------------ RL sampler: Q-network forward (SURVEY 8(f).3)
 def dqn_forward_port(state: Dict[str, torch.Tensor], x: torch.Tensor, dropout: float = 0.1,
                      training: bool = False, eps: float = 1e-5) -> torch.Tensor:

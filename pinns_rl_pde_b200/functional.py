@@ -641,34 +641,68 @@ def loss_components(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_g
     return comp, weights
 
 
+def _smoothness_calls(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, program):
+    """The finite-difference smoothness regulariser of HeatEquation.compute_loss (heat_equation.py:625-650) as libpinnk
+    calls: for every spatial axis the value-only rows [x + eps e_d ; x ; x - eps e_d] (clamped to the domain as the
+    reference clamps them) go through one forward sweep, and two paired mean-|e| segments -- e = u(x + eps) - u(x) and
+    e = u(x) - u(x - eps), weight 1 / (N eps) -- give mean|du_forward| + mean|du_backward| in component 3 and seed the
+    reverse pass with sign(e) / (N eps).  Groups of at most chunk / 3 points keep partners inside one chunk."""
+    eps = 1e-4
+    x, t = _prep(model, x, t)
+    n = x.shape[0]
+    calls = []
+    if n == 0:
+        return calls
+    eng = get_engine(model, [], 3 * n, whole=True, program=program)
+    group = max(1, min(n, eng.chunk // 3))
+    for d in range(int(pde.dimension)):
+        lo, hi = float(pde.domain[d][0]), float(pde.domain[d][1])
+        for g0 in range(0, n, group):
+            xs, ts = x[g0:g0 + group], t[g0:g0 + group]
+            b = xs.shape[0]
+            xp, xm = xs.clone(), xs.clone()
+            xp[:, d:d + 1] = torch.clamp(xs[:, d:d + 1] + eps, lo, hi)
+            xm[:, d:d + 1] = torch.clamp(xs[:, d:d + 1] - eps, lo, hi)
+            w = 1.0 / (n * eps)
+            segs = [Segment(kind=L.PDE_VALUE, row_start=0, row_count=b, component=3, weight=w, pair_offset=b,
+                            loss_kind=L.LOSS_MAE),
+                    Segment(kind=L.PDE_VALUE, row_start=b, row_count=b, component=3, weight=w, pair_offset=b,
+                            loss_kind=L.LOSS_MAE)]
+            calls.append((eng, torch.cat([xp, xs, xm], dim=0), torch.cat([ts, ts, ts], dim=0), segs))
+    return calls
+
+
 def loss_step_flat(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor, n_global: Optional[int] = None,
                    res_scale: float = 1.0, rest_scale: float = 1.0, flat: Optional[torch.Tensor] = None):
     """compute_loss and the gradient of its weighted total in ONE pass per row set, with the final weights folded into
     the seeds of the reverse pass -- the trainer's inner step when the weights are known up front
     (trainer.py:578,689 with fixed ``loss_weights``).  No per-component gradient buffers, no autograd graph.
 
-    Returns (components fp32 [3] = residual, boundary, initial means; weights; flat gradient of
-    ``res_scale * w_res * residual + rest_scale * (w_bc * boundary + w_ic * initial)`` in ``model.parameters()`` order).
-    ``res_scale`` / ``rest_scale`` are the shard weights of the data-parallel step (parallel.py)."""
+    Returns (components fp32 [4] = residual, boundary, initial means and the Heat smoothness term (0 when its weight is 0);
+    weights (w_res, w_bc, w_ic, w_smooth); flat gradient of ``res_scale * (w_res * residual + w_smooth * smoothness) +
+    rest_scale * (w_bc * boundary + w_ic * initial)`` in ``model.parameters()`` order).  ``res_scale`` / ``rest_scale`` are
+    the shard weights of the data-parallel step (parallel.py): residual and smoothness are means over this rank's
+    collocation rows, boundary / initial rows are replicated."""
     _require_physics_only(pde, "loss_step_flat (fused trainer step)")
     calls, weights = _build_calls(pde, model, x, t, n_global, merge_value_rows=True,
                                   merge_all_rows=x.shape[0] <= MERGE_ALL_MAX_POINTS)
     w_res, w_bc, w_ic, w_smooth, adaptive = weights
-    if w_smooth:
-        raise NotImplementedError("the fused step does not cover the smoothness regulariser; use compute_loss")
     if adaptive:
         w_res = w_bc = w_ic = 1.0
     program = calls[0][0].program
     dev = calls[0][1].device
+    smooth_on = bool(w_smooth) and pde_name(pde) == "heat"          # only HeatEquation.compute_loss has the term
+    if smooth_on:
+        calls = calls + _smoothness_calls(pde, model, x, t, program)
     if flat is None:
         flat = torch.zeros(program.grad_floats, dtype=torch.float32, device=dev)
     else:
         flat.zero_()
-    sums = torch.zeros(3, dtype=torch.float64, device=dev)
-    scale = [res_scale * w_res, rest_scale * w_bc, rest_scale * w_ic]
+    sums = torch.zeros(4, dtype=torch.float64, device=dev)
+    scale = [res_scale * w_res, rest_scale * w_bc, rest_scale * w_ic, res_scale * float(w_smooth)]
     for engine, xx, tt, segments in calls:
-        engine.loss_step(xx, tt, segments, 3, True, scale, flat, sums)
-    return sums.to(torch.float32), (w_res, w_bc, w_ic), flat
+        engine.loss_step(xx, tt, segments, 4, True, scale, flat, sums)
+    return sums.to(torch.float32), (w_res, w_bc, w_ic, float(w_smooth) if smooth_on else 0.0), flat
 
 
 def compute_loss(pde, model: nn.Module, x: torch.Tensor, t: torch.Tensor) -> Dict[str, torch.Tensor]:

@@ -91,24 +91,33 @@ def sharded_loss_backward(pde, model: nn.Module, x: torch.Tensor, t: torch.Tenso
         n = int(n_global)
         lo, hi = 0, x.shape[0]
     comp, (w_res, w_bc, w_ic, w_smooth, adaptive) = comp_fn(pde, model, x, t, n_global=n)
-    if w_smooth:
-        raise NotImplementedError("smoothness regulariser is not supported with data parallelism")
     if adaptive:
         w_res = w_bc = w_ic = 1.0
     frac = (hi - lo) / max(n, 1)
     local = frac * w_res * comp[0] + (w_bc * comp[1] + w_ic * comp[2]) / w
+    # Heat's finite-difference smoothness term (heat_equation.py:625-650) is a mean over the collocation rows, so it shards
+    # like the residual: each rank evaluates it on its rows and contributes frac_r * smooth_r
+    smooth = None
+    if w_smooth and F.pde_name(pde) == "heat" and components is None:
+        xs, ts = F._prep(model, x, t)
+        smooth = F._heat_smoothness(pde, model, xs, ts)
+        local = local + frac * w_smooth * smooth
     params = [p for p in model.parameters() if p.requires_grad]
     grads = torch.autograd.grad(local, params, allow_unused=True)
     flat = torch.cat([(torch.zeros_like(p) if g is None else g).reshape(-1) for p, g in zip(params, grads)])
-    sums = torch.stack([frac * comp[0].detach(), comp[1].detach() / w, comp[2].detach() / w]).to(flat.dtype)
+    sm = frac * smooth.detach() if smooth is not None else torch.zeros((), device=flat.device, dtype=comp.dtype)
+    sums = torch.stack([frac * comp[0].detach(), comp[1].detach() / w, comp[2].detach() / w, sm.to(comp.dtype)]).to(flat.dtype)
     flat, sums = reduce_flat(flat, sums, group)
     off = 0
     for p in params:
         p.grad = flat[off:off + p.numel()].view_as(p)
         off += p.numel()
     zero = torch.zeros((), device=flat.device)
-    return {"residual": sums[0], "boundary": sums[1], "initial": sums[2], "smoothness": zero, "data": zero.clone(),
-            "total": w_res * sums[0] + w_bc * sums[1] + w_ic * sums[2]}
+    total = w_res * sums[0] + w_bc * sums[1] + w_ic * sums[2]
+    if smooth is not None:
+        total = total + w_smooth * sums[3]
+    return {"residual": sums[0], "boundary": sums[1], "initial": sums[2], "smoothness": sums[3], "data": zero,
+            "total": total}
 
 
 # ---------------------------------------------------------------------------------- sharded residual scoring

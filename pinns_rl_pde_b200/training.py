@@ -288,18 +288,21 @@ class PDETrainer:
         if self._flat is None or self._flat.numel() != P + 4:
             self._flat = torch.zeros(P + 4, dtype=torch.float32, device=x.device if x.is_cuda else self.device)
         buf = self._flat
-        comp, (w_res, w_bc, w_ic), flat = F.loss_step_flat(self.pde, self.model, x, t, n_global=n_all, res_scale=frac,
-                                                           rest_scale=1.0 / w, flat=buf[:P])
+        comp, (w_res, w_bc, w_ic, w_sm), flat = F.loss_step_flat(self.pde, self.model, x, t, n_global=n_all, res_scale=frac,
+                                                                 rest_scale=1.0 / w, flat=buf[:P])
         if w > 1:
-            buf[P:P + 3].copy_(comp * comp.new_tensor([frac, 1.0 / w, 1.0 / w]))
+            buf[P:P + 4].copy_(comp * comp.new_tensor([frac, 1.0 / w, 1.0 / w, frac]))
             parallel.reduce_inplace(buf)
-            sums = buf[P:P + 3]
+            sums = buf[P:P + 4]
         else:
             sums = comp
         self.optimizer.step(flat)
         zero = torch.zeros((), device=flat.device)
-        return {"residual": sums[0], "boundary": sums[1], "initial": sums[2], "smoothness": zero, "data": zero.clone(),
-                "total": w_res * sums[0] + w_bc * sums[1] + w_ic * sums[2]}
+        total = w_res * sums[0] + w_bc * sums[1] + w_ic * sums[2]
+        if w_sm:
+            total = total + w_sm * sums[3]
+        return {"residual": sums[0], "boundary": sums[1], "initial": sums[2], "smoothness": sums[3], "data": zero,
+                "total": total}
 
     def _adaptive_step(self, x, t):
         """trainer.py:580-694 with adaptive re-weighting: per-component losses and gradients in one reverse pass per row set

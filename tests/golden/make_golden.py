@@ -360,6 +360,53 @@ def run_snapshot_case(tag="x_live_snapshot", grid=12, seed=0):
     return {"case": tag, "keys": sorted(z.files), "grid": grid}
 
 
+def run_smoothness_case(tag="x_heat_smoothness", n=300, seed=0):
+    """HeatEquation._compute_smoothness_loss (heat_equation.py:625-650) and the full HeatEquation.compute_loss with the
+    shipped smoothness weight 0.1 (config.yaml:338-343): unmodified reference (fp32 / fp64) vs oracle/ref_port (bit-identical
+    in fp32) -> weights, points, smoothness value, its parameter gradient, and the loss dict with the term switched on."""
+    torch.manual_seed(seed)
+    model = ref_model("fourier", 2, 128, 3, mapping_size=32, scale=10.0)
+    pde = ref_pde("heat")
+    x, t = points("heat", n, 1, seed + 1)
+    x[:3] = torch.tensor([[0.0], [1.0], [0.99995]])                       # rows the clamp acts on
+    out = {"x": x.numpy(), "t": t.numpy()}
+    for k, v in model.state_dict().items():
+        out["w::" + k] = v.numpy()
+    port = port_model("fourier", 2, 128, 3, model.state_dict(), mapping_size=32, scale=10.0)
+    s_ref = pde._compute_smoothness_loss(model, x, t)
+    s_port = ref_port.heat_smoothness_loss(port, x, t, PDES["heat"]["domain"])
+    assert torch.equal(s_ref, s_port), "oracle port of the smoothness regulariser is not bit-identical to the reference (fp32)"
+    g_ref, g_port = grads_of(model, s_ref), grads_of(port, s_port)
+    assert torch.equal(g_ref, g_port)
+    m64 = copy.deepcopy(model).double()
+    s64 = pde._compute_smoothness_loss(m64, x.double(), t.double())
+    g64 = grads_of(m64, s64)
+    # (fp64 gradients are stored rounded to fp32 -- 6e-8, far below every gate -- and the reference's own fp32 results as
+    # their distance to fp64: the fixture stays ~0.3 MB)
+    out.update(smooth32=s_ref.detach().numpy(), smooth64=s64.detach().numpy(), gsmooth64=g64.float().numpy(),
+               gsmooth32_err=np.array(rel(g_ref.double(), g64)))
+    # the whole compute_loss with the term on (fixed weights incl. smoothness 0.1), as the trainer calls it
+    pde.config.training = {"num_collocation_points": n, "num_boundary_points": 40, "num_initial_points": 40,
+                           "loss_weights": {"residual": 1.0, "boundary": 10.0, "initial": 10.0, "smoothness": 0.1}}
+    for dt, m, xx, tt in ((torch.float32, model, x, t), (torch.float64, m64, x.double(), t.double())):
+        torch.set_default_dtype(dt)              # the reference builds its boundary / initial rows with the default dtype
+        try:
+            L = pde.compute_loss(m, xx, tt)
+            sfx = "32" if dt == torch.float32 else "64"
+            out["loss" + sfx] = np.array([float(L[k]) for k in ("residual", "boundary", "initial", "smoothness", "total")])
+            gt = grads_of(m, L["total"])
+            if dt == torch.float64:
+                out["gtotal64"] = gt.float().numpy()
+                out["gtotal32_err"] = np.array(rel(g32_total.double(), gt))
+            else:
+                g32_total = gt
+        finally:
+            torch.set_default_dtype(torch.float32)
+    np.savez_compressed(os.path.join(HERE, tag + ".npz"), **out)
+    return {"case": tag, "port_bit_identical_fp32": True, "ref32_vs_ref64_value": abs(float(s_ref) - float(s64)) / abs(float(s64)),
+            "ref32_vs_ref64_grad": rel(g_ref.double(), g64)}
+
+
 def main_next():
     """`python tests/golden/make_golden.py next`: only the fixtures of the SURVEY 8(f).4 PDEs (existing files untouched)."""
     reports = [run_case("x_wave_ff_small", "wave", "feedforward", 32, 3, 96),
@@ -397,8 +444,9 @@ def main():
 
 
 if __name__ == "__main__":
-    if sys.argv[1:] in (["dqn"], ["adaptive"], ["snapshot"]):
-        rep = {"dqn": run_dqn_case, "adaptive": run_adaptive_case, "snapshot": run_snapshot_case}[sys.argv[1]]()
+    if sys.argv[1:] in (["dqn"], ["adaptive"], ["snapshot"], ["smoothness"]):
+        rep = {"dqn": run_dqn_case, "adaptive": run_adaptive_case, "snapshot": run_snapshot_case,
+               "smoothness": run_smoothness_case}[sys.argv[1]]()
         path = os.path.join(HERE, "golden_report.json")
         old = [r for r in json.load(open(path)) if r["case"] != rep["case"]]
         json.dump(old + [rep], open(path, "w"), indent=1)

@@ -33,8 +33,9 @@ PDES = {
 
 
 def fixtures():
-    """PDE hot-path fixtures (x_dqn.npz, the RL sampler's Q-network, and x_adaptive_weights.npz have their own tests)."""
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f not in ("x_dqn.npz", "x_adaptive_weights.npz", "x_live_snapshot.npz"))
+    """PDE hot-path fixtures (x_dqn.npz, the RL sampler's Q-network, x_adaptive_weights.npz, x_live_snapshot.npz and
+    x_heat_smoothness.npz have their own tests)."""
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f not in ("x_dqn.npz", "x_adaptive_weights.npz", "x_live_snapshot.npz", "x_heat_smoothness.npz"))
 
 
 def load_fixture(tag):

@@ -60,3 +60,25 @@ def test_layernorm_reference_inexactness_is_recorded():
     """the unmodified reference differs from exact math through nn.LayerNorm at 3rd order."""
     z, meta, _ = load_fixture("c3_kdv_resnet_small")
     assert rel(z["residual64"], z["residual64_corrected"]) > 1e-3
+
+
+def test_heat_smoothness_port_matches_reference_fixture():
+    """oracle/ref_port.heat_smoothness_loss (heat_equation.py:625-650) against the values the UNMODIFIED reference produced
+    (tests/golden/x_heat_smoothness.npz, written by make_golden.py after asserting bit-equality in fp32)."""
+    import os
+    import numpy as np
+    from helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "x_heat_smoothness.npz"))
+    state = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w::")}
+    x, t = torch.from_numpy(z["x"]), torch.from_numpy(z["t"])
+    dom = PDES["heat"]["domain"]
+    for dtype, key, tol in ((torch.float32, "smooth32", 2e-6), (torch.float64, "smooth64", 1e-12)):
+        m = ref_port.PINNModel("fourier", 2, 128, 3, 1, "tanh", mapping_size=32, scale=10.0)
+        m.load_state_dict(state)
+        m = m.to(dtype)
+        s = ref_port.heat_smoothness_loss(m, x.to(dtype), t.to(dtype), dom)
+        assert abs(float(s) - float(z[key])) <= tol * abs(float(z[key])), (key, float(s), float(z[key]))
+        if dtype == torch.float64:
+            g = torch.autograd.grad(s, list(m.parameters()), allow_unused=True)
+            g = torch.cat([(torch.zeros_like(p) if gi is None else gi).reshape(-1) for p, gi in zip(m.parameters(), g)])
+            assert rel(g, z["gsmooth64"]) <= 1e-6          # (the fixture stores the fp64 gradient rounded to fp32)
