@@ -211,6 +211,10 @@ int pinnk_debug_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t
                              int32_t mode, void* stream);
 int pinnk_debug_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int32_t K, int32_t N,
                              int32_t jet_cols, int32_t mode, void* stream);
+/* The tcgen05 forward (trans = 0: Z[M,N] = X[M,K] W[N,K]^T + bias) or dgrad (trans = 1: Z[M,N] = X[M,K] W[K,N]) GEMM with a
+ * scratch buffer for the K-split launch of K = 256 contractions (ring: device, ring_floats floats; null = two K-half passes). */
+int pinnk_debug_linear_ks(const float* X, const float* W, const float* bias, float* Z, int64_t M, int32_t K, int32_t N,
+                          int32_t jet_cols, int32_t trans, float* ring, int64_t ring_floats, void* stream);
 /* Reverse pass of ONE hidden Linear(128, 128) fed by a tanh layer, on raw tensors (the per-layer step of
  * loss["total"].backward(), trainer.py:689): dZprev[M,128] = tanh'(.)^T (dZ[M,128] W[128,128]) with the tanh adjoint taken
  * from the previous layer's OUTPUT jets Yprev[M,128]; dW[128,128] += dZ^T Yprev; db[128] += value-column rows of dZ.

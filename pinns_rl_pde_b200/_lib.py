@@ -50,7 +50,8 @@ EXPORTS = ["pinnk_plan_create", "pinnk_plan_destroy", "pinnk_plan_workspace_byte
            "pinnk_prof_class_name", "pinnk_prof_collect", "pinnk_debug_linear_fwd",
            "pinnk_debug_linear_dgrad", "pinnk_debug_linear_wgrad", "pinnk_adam_step", "pinnk_adam_step_dev", "pinnk_dqn_forward",
            "pinnk_debug_stage_timers", "pinnk_debug_bwd_pair", "pinnk_debug_bwd_split",
-           "pinnk_dqn_forward_wide", "pinnk_sample_workspace_doubles", "pinnk_sample_weighted", "pinnk_jittered_grid"]
+           "pinnk_dqn_forward_wide", "pinnk_sample_workspace_doubles", "pinnk_sample_weighted", "pinnk_jittered_grid",
+           "pinnk_debug_linear_ks"]
 
 _lib = None
 
@@ -115,6 +116,8 @@ def load():
     lib.pinnk_dqn_forward.restype = C.c_int
     lib.pinnk_dqn_forward_wide.argtypes = [C.POINTER(PinnkDqnLayer), i32, vp, vp, i32, vp, i64, vp, vp, i64, vp]
     lib.pinnk_dqn_forward_wide.restype = C.c_int
+    lib.pinnk_debug_linear_ks.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp, i64, vp]
+    lib.pinnk_debug_linear_ks.restype = C.c_int
     lib.pinnk_debug_linear_dgrad.argtypes = [vp, vp, vp, i64, i32, i32, i32, vp]
     lib.pinnk_debug_linear_dgrad.restype = C.c_int
     lib.pinnk_debug_linear_wgrad.argtypes = [vp, vp, vp, vp, i64, i32, i32, i32, i32, vp]
@@ -170,6 +173,21 @@ def debug_linear_fwd(X, W, bias, jet_cols: int, mode: int):
     check(lib.pinnk_debug_linear_fwd(X.data_ptr(), W.data_ptr(), bias.data_ptr() if bias is not None else None,
                                      Z.data_ptr(), M, K, N, jet_cols, mode,
                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pinnk_debug_linear_fwd")
+    return Z
+
+
+def debug_linear_ks(X, W, bias, jet_cols: int, trans: bool, ring=None, out=None):
+    """tcgen05 forward (Z = X W^T + bias) or dgrad (Z = X W) GEMM with the K-split scratch (``ring``: fp32 device tensor or
+    None for the two K-half passes)."""
+    import torch
+    lib = load()
+    M, K = X.shape
+    N = W.shape[1] if trans else W.shape[0]
+    Z = out if out is not None else torch.empty(M, N, dtype=torch.float32, device=X.device)
+    check(lib.pinnk_debug_linear_ks(X.data_ptr(), W.data_ptr(), bias.data_ptr() if bias is not None else None, Z.data_ptr(),
+                                    M, K, N, jet_cols, 1 if trans else 0, ring.data_ptr() if ring is not None else None,
+                                    ring.numel() if ring is not None else 0,
+                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)), "pinnk_debug_linear_ks")
     return Z
 
 

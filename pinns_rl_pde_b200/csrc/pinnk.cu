@@ -303,9 +303,9 @@ static bool tc_enabled() {
 }
 
 static int linear_fwd_any(const float* X, const float* W, const float* b, float* Z, int64_t M, int in_dim, int out_dim,
-                          int ncols, int sm_count, cudaStream_t st, bool allow_tc) {
+                          int ncols, int sm_count, cudaStream_t st, bool allow_tc, float* ring = nullptr, int64_t ring_floats = 0) {
   if (allow_tc) {
-    int rc = tc_linear_fwd(X, W, b, Z, M, in_dim, out_dim, ncols, sm_count, st);
+    int rc = tc_linear_fwd(X, W, b, Z, M, in_dim, out_dim, ncols, sm_count, st, ring, ring_floats);
     if (rc == 0) { g_launches.fetch_add(1); return 0; }
     if (rc != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, std::string("tc_linear_fwd launch failed: ") + cudaGetErrorString(cudaGetLastError()));
   }
@@ -316,16 +316,24 @@ static int linear_fwd_any(const float* X, const float* W, const float* b, float*
   return 0;
 }
 
+// Scratch of the K-split launches of 256-wide layers (ring of partial products, tc_api.h).  Forward: an adjoint buffer (idle
+// until the reverse pass; adj(0) may hold the output layer's partials, so adj(1)).  Reverse: the stash slot of the Linear being
+// differentiated -- its output (the pre-activations) was consumed by the adjoint kernels that ran just before.
+static inline int64_t adj_floats(const ChunkCtx& c) { return (int64_t)c.pl->js.ncols * c.pl->chunk * c.pl->max_width; }
+static inline int64_t stash_floats(const ChunkCtx& c, int op) { return (int64_t)c.pl->js.ncols * c.pl->chunk * c.pl->ops[op].op.out_dim; }
+
 static int gemm_fwd(const ChunkCtx& c, const float* X, const float* W, const float* b, float* Z, int in_dim, int out_dim) {
   ProfScope ps(PC_GEMM_FWD, c.st);
-  return linear_fwd_any(X, W, b, Z, c.n * c.pl->js.ncols, in_dim, out_dim, c.pl->js.ncols, c.pl->sm_count, c.st, tc_enabled());
+  return linear_fwd_any(X, W, b, Z, c.n * c.pl->js.ncols, in_dim, out_dim, c.pl->js.ncols, c.pl->sm_count, c.st, tc_enabled(),
+                        c.adj(1), adj_floats(c));
 }
 
-static int gemm_dgrad(const ChunkCtx& c, const float* Zb, const float* W, float* Xb, int in_dim, int out_dim) {
+static int gemm_dgrad(const ChunkCtx& c, const float* Zb, const float* W, float* Xb, int in_dim, int out_dim,
+                      float* ring = nullptr, int64_t ring_floats = 0) {
   ProfScope ps(PC_GEMM_DGRAD, c.st);
   const int64_t M = c.n * c.pl->js.ncols;
   if (tc_enabled()) {
-    int rc = tc_linear_dgrad(Zb, W, Xb, M, in_dim, out_dim, c.pl->sm_count, c.st);
+    int rc = tc_linear_dgrad(Zb, W, Xb, M, in_dim, out_dim, c.pl->sm_count, c.st, ring, ring_floats);
     if (rc == 0) { g_launches.fetch_add(1); return 0; }
     if (rc != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, std::string("tc_linear_dgrad launch failed: ") + cudaGetErrorString(cudaGetLastError()));
   }
@@ -631,7 +639,8 @@ static int forward_chunk(const ChunkCtx& c, bool keep_stash = true) {
             ProfScope ps(PC_GEMM_FWD, c.st);          // (opened here: the loss-fused launch above is its own class)
             float* y_out = (fuse_out && !keep_stash) ? nullptr : c.stash(i + 1);
             int rc = tc_linear_act_fwd(in, W, b, want_z ? c.stash(i) : nullptr, y_out, c.n * js.ncols, o.in_dim, o.out_dim, k0, k1,
-                                       a.act == PINNK_ACT_TANH ? 1 : 2, a.scale, pl->sm_count, c.st, w_out, fuse_out ? c.adj(0) : nullptr);
+                                       a.act == PINNK_ACT_TANH ? 1 : 2, a.scale, pl->sm_count, c.st, w_out, fuse_out ? c.adj(0) : nullptr,
+                                       nullptr, c.adj(1), adj_floats(c));
             if (rc == 0 && fuse_out) {
               g_launches.fetch_add(1);
               ProfScope ps2(PC_LAST_FWD, c.st);
@@ -790,7 +799,8 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad, bool last_done = 
               const bool from_y = z_elided(pl, pa.in_op);      // the forward did not stash this pre-activation
               rc = tc_linear_dgrad_actbwd(c.adj(cur), W, from_y ? c.stash(i - 1) : c.stash(pa.in_op), c.adj(nxt), c.n * js.ncols,
                                           o.in_dim, o.out_dim, k0, k1, pa.op.act == PINNK_ACT_TANH ? 1 : 2, pa.op.scale,
-                                          pl->sm_count, c.st, from_y ? 1 : 0);
+                                          pl->sm_count, c.st, from_y ? 1 : 0, r.out_off >= 0 ? c.stash(i) : nullptr,
+                                          r.out_off >= 0 ? stash_floats(c, i) : 0);
               if (rc == 0) { g_launches.fetch_add(1); cur = nxt; --i; break; }
               if (rc != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, std::string("tc_linear_dgrad_actbwd launch failed: ") + cudaGetErrorString(cudaGetLastError()));
               if (from_y) return fail(PINNK_E_INVALID, "backward: pre-activation stash elided but the fused adjoint kernel refused the shape");
@@ -808,7 +818,8 @@ static int backward_chunk(const ChunkCtx& c, float* flat_grad, bool last_done = 
               if (rc == 0) { g_launches.fetch_add(1); i = 0; break; }      // ops 1 (activation) and 0 (input layer) are done
               if (rc != TC_UNSUPPORTED) return fail(PINNK_E_CUDA, std::string("tc_linear_dgrad_firstbwd launch failed: ") + cudaGetErrorString(cudaGetLastError()));
             }
-            rc = gemm_dgrad(c, c.adj(cur), W, c.adj(nxt), o.in_dim, o.out_dim);
+            rc = gemm_dgrad(c, c.adj(cur), W, c.adj(nxt), o.in_dim, o.out_dim, r.out_off >= 0 ? c.stash(i) : nullptr,
+                            r.out_off >= 0 ? stash_floats(c, i) : 0);
             if (rc) return rc;
             cur = nxt;
           }
@@ -1128,6 +1139,20 @@ extern "C" int pinnk_debug_linear_fwd(const float* X, const float* W, const floa
     return 0;
   }
   return linear_fwd_any(X, W, bias, Z, M, K, N, jet_cols, smc, (cudaStream_t)stream, false);
+}
+
+extern "C" int pinnk_debug_linear_ks(const float* X, const float* W, const float* bias, float* Z, int64_t M, int32_t K, int32_t N,
+                                     int32_t jet_cols, int32_t trans, float* ring, int64_t ring_floats, void* stream) {
+  if (!X || !W || !Z || M < 1 || (K % 4) || (N % 4) || jet_cols < 1) return fail(PINNK_E_INVALID, "debug_linear_ks: bad argument");
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int smc = sm_count_of(dev);
+  const int rc = trans ? tc_linear_dgrad(X, W, Z, M, N, K, smc, (cudaStream_t)stream, ring, ring_floats)
+                       : tc_linear_fwd(X, W, bias, Z, M, K, N, jet_cols, smc, (cudaStream_t)stream, ring, ring_floats);
+  if (rc == TC_UNSUPPORTED) return fail(PINNK_E_INVALID, "debug_linear_ks: shape not covered by the tcgen05 path");
+  if (rc != 0) return fail(PINNK_E_CUDA, std::string("debug_linear_ks: ") + cudaGetErrorString(cudaGetLastError()));
+  g_launches.fetch_add(1);
+  return 0;
 }
 
 // dX[M,K_in] = dZ[M,N] W[N,K_in]  (mode as above)

@@ -29,22 +29,37 @@ struct TcLossFuse {
 };
 
 // Z[M,N] = X[M,K] W[N,K]^T (+ bias on value-column rows)
+// ring / ring_floats (here and below): device scratch for the K-split launch of 256-wide contractions (one launch of CTA
+// pairs instead of two K-half passes; needs (sm_count / 2) * 32768 floats); null -> two passes
 int tc_linear_fwd(const float* X, const float* W, const float* bias, float* Z, int64_t M, int K, int N, int jet_cols,
-                  int sm_count, cudaStream_t st);
+                  int sm_count, cudaStream_t st, float* ring = nullptr, int64_t ring_floats = 0);
 // Forward Linear + activation jets in one kernel: Z = X W^T + b (stash, may be null for K = 128), Yact = act(Z).
 // act: 1 tanh, 2 sin(omega z); (k0, k1) = jet orders of the (at most two) directions.
 // w_out != null folds the network's output layer nn.Linear(N, 1) in: u_part[(N/128) * 4][M] receives per-warp partial
 // output jets (sum them in order + bias: output_combine_kernel); Yact may then be null (forward-only callers).
 int tc_linear_act_fwd(const float* X, const float* W, const float* bias, float* Z, float* Yact, int64_t M, int K, int N,
                       int k0, int k1, int act, float omega, int sm_count, cudaStream_t st,
-                      const float* w_out = nullptr, float* u_part = nullptr, const TcLossFuse* loss = nullptr);
+                      const float* w_out = nullptr, float* u_part = nullptr, const TcLossFuse* loss = nullptr,
+                      float* ring = nullptr, int64_t ring_floats = 0);
 // dX[M,in] = dZ[M,out] W[out,in]   (W row-major [out,in])
 int tc_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t M, int in_dim, int out_dim, int sm_count,
-                    cudaStream_t st);
+                    cudaStream_t st, float* ring = nullptr, int64_t ring_floats = 0);
 // dgrad + activation adjoint in one kernel: dZprev = act'(Zprev)^T (dZ W).  from_y = 1 (tanh only): Zprev holds the
 // activation OUTPUT jets instead of the pre-activation jets (the forward pass then does not stash the latter)
 int tc_linear_dgrad_actbwd(const float* dZ, const float* W, const float* Zprev, float* dZprev, int64_t M, int in_dim,
-                           int out_dim, int k0, int k1, int act, float omega, int sm_count, cudaStream_t st, int from_y);
+                           int out_dim, int k0, int k1, int act, float omega, int sm_count, cudaStream_t st, int from_y,
+                           float* ring = nullptr, int64_t ring_floats = 0);
+// internal: the K-split launches (own translation units tc_ksplit_fwd.cu / tc_ksplit_bwd.cu); TC_UNSUPPORTED when the
+// shape, the row count or the scratch size rules the launch out
+int tc_ks_linear_fwd(const float* X, const float* W, const float* bias, float* Z, int64_t M, int N, int jet_cols, int sm_count,
+                     cudaStream_t st, float* ring, int64_t ring_floats);
+int tc_ks_linear_act_fwd(const float* X, const float* W, const float* bias, float* Z, float* Yact, int64_t M, int N, int k0,
+                         int k1, int act, float omega, int sm_count, cudaStream_t st, const float* w_out, float* u_part,
+                         float* ring, int64_t ring_floats);
+int tc_ks_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t M, int in_dim, int sm_count, cudaStream_t st,
+                       float* ring, int64_t ring_floats);
+int tc_ks_linear_dgrad_actbwd(const float* dZ, const float* W, const float* Zprev, float* dZprev, int64_t M, int in_dim, int k0,
+                              int k1, int act, float omega, int sm_count, cudaStream_t st, float* ring, int64_t ring_floats);
 // jet layouts (orders of the at most two directions) the fused epilogues are instantiated for
 inline bool tc_jets_supported(int k0, int k1) {
   return (k0 == 0 && k1 == 0) || (k0 == 1 && k1 == 0) || (k0 == 2 && k1 == 1) || (k0 == 3 && k1 == 0) ||       // 1, 2, 4, 4

@@ -576,6 +576,36 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
 }
+// mbarrier traffic between the two CTAs of a cluster (the K-split rows kernel): arrive on a barrier in the PARTNER's shared
+// memory with release semantics at cluster scope (everything this thread -- and, through bar.warp.sync, its warp -- wrote
+// before is visible to a thread that then observes the phase with an acquire at cluster scope), and the matching wait.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t remote_bar_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
+}
+// "slot consumed" signal: orders nothing but itself (the caller has made sure its loads of the slot have delivered); a
+// release here would put a memory barrier -- behind the warp's own output stores -- on every epilogue warp's path per tile
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t remote_bar_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+#ifdef PINNK_KS_NOSYNC
+  return;
+#endif
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    __nanosleep(64);
+  }
+  __trap();
+}
 // Lock-step throttle between the two CTAs of a pair that walk the SAME tile stream (one does dgrad + adjoint, the other
 // wgrad): each publishes the number of macro tiles whose loads it has issued into the partner's shared memory (DSMEM
 // store) and never runs more than kPairLead macro tiles ahead of the partner, so that the second reader of a tile finds
@@ -622,7 +652,9 @@ static __device__ unsigned long long g_stage_timers[16];
 // direction 1, with C = 1 + K0 + K1 dividing 32 so that every epilogue warp owns whole points.
 //   EPI_ACTBWD_Y  as EPI_ACTBWD for tanh, but Zs holds the activation OUTPUT jets (the forward pass then never writes the
 //               pre-activations: 512 B per row less traffic); z jets are recovered with tanh_dir_recover
-enum { EPI_PLAIN = 0, EPI_ACT = 1, EPI_ACTBWD = 2, EPI_ACTBWD_Y = 3, EPI_FIRSTBWD = 4 };
+//   EPI_PARTIAL producer half of the K-split kernel (below): the epilogue only moves its partial product to the pair's ring
+enum { EPI_PLAIN = 0, EPI_ACT = 1, EPI_ACTBWD = 2, EPI_ACTBWD_Y = 3, EPI_FIRSTBWD = 4, EPI_PARTIAL = 5 };
+constexpr int kKsRing = 8;                 // ring slots ([64 rows x 128 features] fp32 partial products) per CTA pair
 
 // rows (tile columns) one epilogue warp owns for a jet column count JC: the largest multiple of JC that is <= 16 and a
 // quarter of a 48-, 60- or 64-row tile
@@ -663,14 +695,20 @@ struct OutFuse {
 // (body of linear_rows_ts_kernel; cta_x / ncta_x / cta_y are the block index / grid size the kernel passes in, so that the
 // paired reverse kernel can run it on one CTA of each cluster with the pair index; PAIR adds the lock-step throttle to the
 // TMA warp)
-template <bool TRANS_W, int EPI, int ACT, int K0, int K1, int NLW, int ECOLS, bool ACCUM, int LDYC, bool LOSSF = false, bool PAIR = false>
+// KS: K-split of a 256-wide contraction over the two CTAs of a cluster.  KS = 1 (EPI_PARTIAL): this CTA contracts its K half
+// and hands the partial product of every tile to its partner through `ring` (kKsRing slots in global memory -- they stay in
+// L2 -- guarded by mbarriers in the two CTAs' shared memory); KS = 2 (ACCUM): this CTA contracts the other K half, adds the
+// partner's partial product and runs the epilogue.  Both walk the same tiles in the same order.
+template <bool TRANS_W, int EPI, int ACT, int K0, int K1, int NLW, int ECOLS, bool ACCUM, int LDYC, bool LOSSF = false, bool PAIR = false,
+          int KS = 0>
 __device__ __forceinline__ void
 linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, int ldw, const float* __restrict__ bias,
                     float* __restrict__ Y, int64_t M, int ldy_rt, int jet_cols, const float* __restrict__ Zs,
                     float* __restrict__ Yact, float omega, int ldx, const OutFuse& of, const FirstLayer& fl,
                     const TcLossFuse& lfv, const CUtensorMap* tmxp, const int cta_x, const int ncta_x, const int cta_y,
-                    const PairSync ps) {
+                    const PairSync ps, float* __restrict__ ring = nullptr) {
   static_assert(!LOSSF || (EPI == EPI_ACT && ACT == 1 && ECOLS == 16 && !ACCUM), "loss fusion: tanh forward epilogue only");
+  static_assert((KS == 1) == (EPI == EPI_PARTIAL) && (KS != 2 || ACCUM) && (KS == 0 || (!LOSSF && !PAIR)), "K-split roles");
   // LDYC: compile-time row stride of Y / Zs / Yact (0 = use the runtime value): with it every row address of the
   // epilogue is base + immediate instead of a 64-bit multiply-add per access
   const int ldy = LDYC ? LDYC : ldy_rt;
@@ -685,9 +723,10 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
   // Rows an epilogue warp really owns (ECE <= ECOLS) and rows per tile (TNE = 4 * ECE <= TN): jet column counts that do
   // not divide 16 (3, 5, 6: Heat / convection, KdV / wave, 1-D Cahn-Hilliard) use 60- or 48-row tiles inside the same
   // 64-row MMA (the spare operand rows are zero), so that every epilogue warp still owns whole points.
-  constexpr int ECE = (EPI == EPI_PLAIN) ? ECOLS : jets_rows_per_warp(JC);
+  // (EPI_PARTIAL takes the tile geometry of its partner: 32-row warps when that runs the plain epilogue, else the jet layout)
+  constexpr int ECE = (EPI == EPI_PLAIN || (EPI == EPI_PARTIAL && ECOLS == 32)) ? ECOLS : jets_rows_per_warp(JC);
   constexpr int TNE = (TN / ECOLS) * ECE;
-  static_assert(ECE > 0 && ECE <= ECOLS && (EPI == EPI_PLAIN || (ECE % JC) == 0), "unsupported jet column count for the fused epilogues");
+  static_assert(ECE > 0 && ECE <= ECOLS && (EPI == EPI_PLAIN || EPI == EPI_PARTIAL || (ECE % JC) == 0), "unsupported jet column count for the fused epilogues");
   constexpr int CHUNKS = K / 4;
   constexpr uint32_t X_BYTES = TN * K * 4;        // one of X_hi / X_lo per stage (32 KB)
   constexpr uint32_t RAW_BYTES = TN * K * 4;      // raw fp32 row tile (32 KB)
@@ -706,6 +745,9 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
   uint64_t* raw_empty = raw_full + RS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + RS);
   float* u_smem = reinterpret_cast<float*>(tmem_slot + 4);      // [4 row groups][4 lane quarters][16]  (LOSSF)
+  uint64_t* pfull = reinterpret_cast<uint64_t*>(u_smem);        // KS (never LOSSF): [kKsRing] partial product landed in slot
+  uint64_t* pempty = pfull + kKsRing;                           //                   [kKsRing] slot read by the consumer
+  uint32_t* ks_cnt = reinterpret_cast<uint32_t*>(pempty + kKsRing);   //             [kKsRing] producer warps done with the slot
 
 #ifdef PINNK_STAGE_TIMERS
   unsigned long long g_entry; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_entry));
@@ -718,6 +760,10 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], NLW); mbar_init(&empty[s], 1); }
     for (int b = 0; b < ACC; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], NEW); }
     for (int s = 0; s < RS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], NLW); }
+    if constexpr (KS != 0) {
+      // pfull: ONE arrive per tile (the producer warp that finishes last publishes for all); pempty: one per consumer warp
+      for (int s = 0; s < kKsRing; ++s) { mbar_init(&pfull[s], 1); mbar_init(&pempty[s], NEW); ks_cnt[s] = 0u; }
+    }
     fence_mbar_init();
   }
   if (warp == MMAW) tmem_alloc(tmem_slot, 512);
@@ -725,6 +771,19 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // K-split: the partner's barriers (same offsets in its shared memory); both CTAs' barriers exist before either can arrive
+  uint32_t peer_pfull = 0, peer_pempty = 0;
+#ifndef PINNK_KS_NOCLUSTER
+  if constexpr (KS != 0) {
+    const uint32_t peer = cluster_ctarank() ^ 1u;
+    peer_pfull = mapa_u32(smem_u32(pfull), peer);
+    peer_pempty = mapa_u32(smem_u32(pempty), peer);
+    cluster_sync_all();
+  }
+#else
+  if constexpr (KS != 0) { peer_pfull = smem_u32(pfull); peer_pempty = smem_u32(pempty); }
+#endif
+  (void)peer_pfull; (void)peer_pempty;
 
   // resident weights -> TMEM: an epilogue warp (q, h) owns TMEM lanes 32q.. (rows f of the A operand) and stages the
   // 32-column blocks h, h + NEW/4, ...: all epilogue warps load at once, so the prologue is one round of global latency
@@ -865,8 +924,32 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
     // One tile of this warp.  FULL: all ECOLS rows exist, so no access is predicated and (with LDYC) every row address
     // is the tile base plus an immediate.
     long long t_ea = 0, t_eb = 0; (void)t_ea; (void)t_eb;
-    auto run_tile = [&](auto full_tag, const int b, const uint32_t ph, const int64_t r0, const int nrows) {
+    // K-split consumer: the partner's partial product of a tile is fetched one tile AHEAD (while the previous tile's
+    // epilogue runs): an epilogue warp walks every tile of the CTA in turn, and an L2 round trip per tile on that serial
+    // path (~1 us against 0.8 us of tensor time per tile) halved the throughput.  The MMA warp stays two tiles behind the
+    // partner, so the slot is always complete when it is asked for here.  Rows h * ECE .. of ring slot it % kKsRing (every
+    // row of a slot is written; L2 only -- the slot is rewritten every kKsRing tiles and L1 is not coherent).
+    float part_nx[(KS == 2) ? ECOLS : 1], part_n2[(KS == 2) ? ECOLS : 1];     // tiles it + 1 and it + 2
+    auto ks_prefetch = [&](const int it_, float (&dst)[(KS == 2) ? ECOLS : 1]) {
+      if constexpr (KS == 2) {
+        const int s_ = it_ % kKsRing;
+        // (CTA-scope wait: an acquire at cluster scope invalidates the SM's whole L1 -- CCTL.IVALL -- and 17 of those per tile
+        // were the longest item of the consumer's tile time.  The phase flips only after the partner's release has made its
+        // stores visible in L2, the loads below are issued after the flip is seen and bypass L1 (ld.global.cg).)
+#ifndef PINNK_KS_NOSYNC
+        mbar_wait(&pfull[s_], (uint32_t)(it_ / kKsRing) & 1u);
+#endif
+        const float* const rp = ring + (size_t)s_ * (64 * 128) + (size_t)(h * ECE) * 128 + f;
+#pragma unroll
+        for (int j = 0; j < ECOLS; ++j) dst[j] = (j < ECE) ? __ldcg(rp + j * 128) : 0.f;
+      }
+    };
+    auto run_tile = [&](auto full_tag, const int b, const uint32_t ph, const int64_t r0, const int nrows, const int it_,
+                        const bool has_next2) {
       constexpr bool FULL = decltype(full_tag)::value;
+      const int ks_s = it_ % kKsRing;                               // K-split: ring slot and barrier phase of this tile
+      const uint32_t ks_ph = (uint32_t)(it_ / kKsRing) & 1u;
+      (void)ks_s; (void)ks_ph; (void)has_next2;
       uint32_t vmask = 0;
       if constexpr (EPI == EPI_PLAIN) {
         if (!TRANS_W && bias) {
@@ -894,7 +977,11 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
       }
       // second K half of a 256-wide layer: the first half's partial result is in Y
       float part[ACCUM ? ECOLS : 1];
-      if constexpr (ACCUM) {
+      uint32_t pdep = 0;
+      (void)pdep;
+      if constexpr (ACCUM && KS == 2) {
+        // (fetched two tiles ago -- ks_prefetch; read below, after the accumulator has arrived)
+      } else if constexpr (ACCUM) {
 #pragma unroll
         for (int j = 0; j < ECOLS; ++j) part[j] = (j < ECE && (FULL || j < nrows)) ? yp[j * ldy] : 0.f;
       }
@@ -913,7 +1000,20 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
 #pragma unroll
       for (int j = 0; j < ECOLS; ++j) {
         acc[j] = __uint_as_float(pc[j]) + __uint_as_float(pm[j]);
-        if constexpr (ACCUM) acc[j] += part[j];
+        if constexpr (ACCUM && KS == 2) { acc[j] += part_nx[j]; pdep |= __float_as_uint(part_nx[j]); }
+        else if constexpr (ACCUM) acc[j] += part[j];
+      }
+      if constexpr (KS == 2) {
+        // this tile's slot has been read (its values are in acc): the partner may refill it; the next tile's partial product
+        // is already on its way (or here), the one after that is requested now
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(smem_u32(tmem_slot + 2)), "r"(pdep) : "memory");
+          mbar_arrive_remote_relaxed(peer_pempty + (uint32_t)ks_s * 8u);
+        }
+#pragma unroll
+        for (int j = 0; j < ECOLS; ++j) part_nx[j] = part_n2[j];
+        if (has_next2) ks_prefetch(it_ + 2, part_n2);
       }
       if constexpr (EPI == EPI_PLAIN) {
 #pragma unroll
@@ -921,6 +1021,28 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
           float val = acc[j];
           if ((vmask >> j) & 1u) val += bf;
           if (FULL || j < nrows) yp[j * ldy] = val;
+        }
+      } else if constexpr (EPI == EPI_PARTIAL) {
+        // hand the partial product to the partner: wait until it has read this slot's previous tile, store, publish
+#ifndef PINNK_KS_NOSYNC
+        mbar_wait(&pempty[ks_s], ks_ph ^ 1u);          // (write-after-read only: nothing of the partner's is read here)
+#endif
+        float* const rp = ring + (size_t)ks_s * (64 * 128) + (size_t)(h * ECE) * 128 + f;
+#pragma unroll
+        for (int j = 0; j < ECOLS; ++j)
+          if (j < ECE) __stcg(rp + j * 128, acc[j]);
+        // Publish once per tile: every warp counts itself done (acq_rel at CTA scope, after a warp barrier that orders all its
+        // lanes' stores before the count), and the warp that arrives last releases the slot to the partner at cluster scope.
+        // A release is cumulative over what happens-before it, so one memory barrier per tile covers all 16 warps' stores
+        // (a barrier per warp and tile -- let alone per lane -- was the longest item on these warps' serial path).
+        __syncwarp();
+        if (lane == 0) {
+          uint32_t old;
+          asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(&ks_cnt[ks_s])) : "memory");
+          if (old == (uint32_t)(NEW - 1)) {
+            asm volatile("st.relaxed.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(&ks_cnt[ks_s])), "r"(0u) : "memory");
+            mbar_arrive_remote(peer_pfull + (uint32_t)ks_s * 8u);
+          }
         }
       } else {
         // whole points: columns [pp*JC, pp*JC + JC) of this warp's ECOLS are the jet of point pp at feature f
@@ -1171,12 +1293,17 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
       PK_TACC(t_eb);
     };
     int it = 0;
+    if constexpr (KS == 2) {
+      if ((int64_t)cta_x < ntiles) ks_prefetch(0, part_nx);
+      if ((int64_t)cta_x + ncta_x < ntiles) ks_prefetch(1, part_n2);
+    }
     for (int64_t tile = cta_x; tile < ntiles; tile += ncta_x, ++it) {
       const int b = it % ACC;
       const uint32_t ph = (uint32_t)(it / ACC) & 1u;
       const int64_t r0 = tile * TNE + h * ECE;
-      if (M - r0 >= ECE) run_tile(std::true_type(), b, ph, r0, ECE);
-      else run_tile(std::false_type(), b, ph, r0, (int)(M - r0 > 0 ? M - r0 : 0));
+      const bool has_next2 = tile + 2 * (int64_t)ncta_x < ntiles;
+      if (M - r0 >= ECE) run_tile(std::true_type(), b, ph, r0, ECE, it, has_next2);
+      else run_tile(std::false_type(), b, ph, r0, (int)(M - r0 > 0 ? M - r0 : 0), it, has_next2);
     }
     if constexpr (LOSSF) {
       if (lfv.gw_out) atomicAdd(lfv.gw_out + n0 + f, gw_acc);
@@ -1222,6 +1349,18 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u, bph = (uint32_t)(it / ACC) & 1u;
         { PK_T0(); mbar_wait(&tempty[b], bph ^ 1u); PK_TACC(t_a); }
         { PK_T0(); mbar_wait(&full[s], ph); PK_TACC(t_b); }
+        if constexpr (KS == 2) {
+          // stay kKsLag tiles behind the partner: when this tile's accumulator completes, its partial product has been in
+          // the ring long enough for the epilogue warps' loads (issued before they wait for the accumulator) to have landed;
+          // in lock step every tile would expose an L2 round trip in the epilogue
+          constexpr int kKsLag = 3;
+          if (tile + (int64_t)kKsLag * ncta_x < ntiles) {
+            const int it2 = it + kKsLag;
+#ifndef PINNK_KS_NOSYNC
+            mbar_wait(&pfull[it2 % kKsRing], (uint32_t)(it2 / kKsRing) & 1u);
+#endif
+          }
+        }
         PK_T0();
         tc_fence_after();
         const uint32_t xh = x_base + (uint32_t)s * (2 * X_BYTES >> 4), xl = xh + (X_BYTES >> 4);
@@ -1259,6 +1398,10 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
   }
   tc_fence_before();
   __syncthreads();
+  // K-split: no CTA may exit while its partner can still arrive on its barriers
+#ifndef PINNK_KS_NOCLUSTER
+  if constexpr (KS != 0) cluster_sync_all();
+#endif
   if (warp == MMAW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -1334,6 +1477,97 @@ static int launch_linear_rows_ts(const float* X, const float* W, int ldw, const 
   if (n_cols == 128)
     return launch_linear_rows_ts_inst<TRANS_W, EPI, ACT, K0, K1, false, 128>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, sm_count, st, ldx, of, fl);
   return launch_linear_rows_ts_inst<TRANS_W, EPI, ACT, K0, K1, false, 0>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, sm_count, st, ldx, of, fl);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K-split rows kernel for 256-wide contractions (ResNet 6x256, SIREN 5x256): ONE launch of CTA pairs (clusters of two along
+// grid z) instead of two K-half launches with the partial product written to and re-read from HBM.  A 128 x 256 weight block
+// in hi/lo form is 256 KB -- all of one SM's tensor memory -- so the contraction has to be split over two SMs either way;
+// here both halves run at the same time on the same tiles: rank 0 (EPI_PARTIAL) contracts K half 0 and hands each 64 x 128
+// partial product to rank 1 through a 4-slot ring in global memory (128 KB per pair, 9.5 MB in all: it lives in L2), rank 1
+// contracts K half 1, adds the partial product and runs the epilogue (bias / activation jets / activation adjoint).  HBM
+// traffic per row drops from 4.5 - 5.5 KB (two passes) to what the layer needs (read X, (stash,) write Y), and both halves are
+// tensor-bound like the first pass alone was (82 % tensor pipe active, profiles/r02s_c3_rows.md).
+template <bool TRANS_W, int EPI, int ACT, int K0, int K1, int ECOLS, int LDYC>
+__global__ void
+#ifndef PINNK_KS_NOCLUSTER
+__cluster_dims__(1, 1, 2)
+#endif
+__launch_bounds__((8 + 4 * (64 / ECOLS) + 2) * 32, 1)
+linear_rows_ts_ksplit_kernel(const float* __restrict__ X, const float* __restrict__ W, int ldw, int w_half_stride,
+                             const float* __restrict__ bias, float* __restrict__ Y, int64_t M, int ldy_rt, int jet_cols,
+                             const float* __restrict__ Zs, float* __restrict__ Yact, float omega, int ldx, OutFuse of,
+                             float* __restrict__ ring_base, const __grid_constant__ CUtensorMap tm0,
+                             const __grid_constant__ CUtensorMap tm1) {
+  float* const ring = ring_base + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * (kKsRing * 64 * 128);
+#ifdef PINNK_KS_NOCLUSTER
+  if (blockIdx.z == 0) {
+#else
+  if (cluster_ctarank() == 0) {
+#endif
+    linear_rows_ts_body<TRANS_W, EPI_PARTIAL, 1, K0, K1, 8, ECOLS, false, 128, false, false, 1>(
+        X, W, ldw, nullptr, nullptr, M, ldy_rt, jet_cols, nullptr, nullptr, 1.f, ldx, OutFuse{}, FirstLayer{}, TcLossFuse{}, &tm0,
+        (int)blockIdx.x, (int)gridDim.x, (int)blockIdx.y, PairSync{}, ring);
+  } else {
+    linear_rows_ts_body<TRANS_W, EPI, ACT, K0, K1, 8, ECOLS, true, LDYC, false, false, 2>(
+        X + 128, W + w_half_stride, ldw, bias, Y, M, ldy_rt, jet_cols, Zs, Yact, omega, ldx, of, FirstLayer{}, TcLossFuse{}, &tm1,
+        (int)blockIdx.x, (int)gridDim.x, (int)blockIdx.y, PairSync{}, ring);
+  }
+}
+
+// rows below which the two-pass route is used (a K-split launch keeps every SM busy only with >= 2 tiles per CTA pair)
+constexpr int64_t kKsMinRows = 16384;
+
+template <bool TRANS_W, int EPI, int ACT, int K0, int K1>
+static int launch_linear_rows_ts_ksplit(const float* X, const float* W, int ldw, const float* bias, float* Y, int64_t M, int n_cols,
+                                        int jet_cols, const float* Zs, float* Yact, float omega, int sm_count, cudaStream_t st,
+                                        OutFuse of, float* ring, int64_t ring_floats) {
+  constexpr size_t smem = 1024 + (size_t)2 * 2 * 64 * 128 * 4 + (size_t)3 * 64 * 128 * 4 + (2 * 2 + 2 * 2 + 2 * 3) * 8 + 16 + 1024;
+  static_assert(smem <= 232448, "shared memory budget (227 KB per CTA)");
+  constexpr int ECOLS = 16;        // 16 epilogue warps in every variant (the plain epilogue too: twice the loads in flight)
+  constexpr int TNE = (EPI == EPI_PLAIN) ? 64 : 4 * jets_rows_per_warp(1 + K0 + K1);
+  constexpr int ldx = 256;
+  const int64_t ntiles = (M + TNE - 1) / TNE;
+  const int per_y = n_cols / 128;
+  int gx = sm_count / (2 * per_y);
+  if (gx < 1 || ring == nullptr || M < kKsMinRows) return TC_UNSUPPORTED;
+  if ((int64_t)gx > ntiles) gx = (int)ntiles;
+  if ((int64_t)gx * per_y * kKsRing * 64 * 128 > ring_floats) return TC_UNSUPPORTED;
+  constexpr int threads = (8 + 4 * (64 / ECOLS) + 2) * 32;
+  if (n_cols != 256) return TC_UNSUPPORTED;                    // (compile-time output stride: every 256-wide net of the path)
+  auto kern = linear_rows_ts_ksplit_kernel<TRANS_W, EPI, ACT, K0, K1, ECOLS, 256>;
+  static bool configured = false;
+  static int max_clusters = 0;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    // How many CTA pairs can be resident at once?  Not necessarily sm_count / 2: a pair needs both SMs of one TPC, and parts
+    // ship with TPCs that have a single SM enabled.  A persistent grid with even one pair too many runs that pair as a
+    // second wave -- twice the kernel time (measured: 74 pairs on a 148-SM B200 took 2x the time of the pairs that fit).
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * (unsigned)(sm_count / 2), 1, 1);
+    cfg.blockDim = dim3(threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = sm_count / 2; }
+    max_clusters = n;
+    configured = true;
+  }
+  if (const char* e = getenv("PINNK_KS_PAIRS")) { const int v = atoi(e); if (v > 0) max_clusters = v; }     // (experiments)
+  if (gx * per_y > max_clusters) gx = max_clusters / per_y;
+  if (gx < 1) return TC_UNSUPPORTED;
+  dim3 grid((unsigned)gx, (unsigned)per_y, 2);
+  alignas(64) CUtensorMap tm0, tm1;
+  if (!make_tmap_rows(&tm0, X, M, 128, ldx, TNE) || !make_tmap_rows(&tm1, X + 128, M, 128, ldx, TNE)) return -1;
+  // K half 1 of the weights: columns 128.. of W[n_out, 256] (forward) or rows 128.. of W[256, n_in] (dgrad)
+  const int w_half_stride = TRANS_W ? 128 * ldw : 128;
+  kern<<<grid, threads, smem, st>>>(X, W, ldw, w_half_stride, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, ldx, of, ring, tm0, tm1);
+  return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1921,6 +2155,59 @@ static inline int tc_dispatch_jets(int k0, int k1, const float* X, const float* 
 // epilogue, no bias), the second adds it in its epilogue (bias, activation ... as requested).
 #endif
 
+#if defined(PINNK_TC_TU_KS_FWD) || defined(PINNK_TC_TU_KS_BWD)
+// K-split launches of the jet layouts the fused epilogues are instantiated for
+template <bool TRANS_W, int EPI, int ACT>
+static inline int tc_ks_dispatch_jets(int k0, int k1, const float* X, const float* W, int ldw, const float* bias, float* Y,
+                                      int64_t M, int n_cols, const float* Zs, float* Yact, float omega, int sm_count,
+                                      cudaStream_t st, tc::OutFuse of, float* ring, int64_t ring_floats) {
+#define PK_KS_CASE(A, B)                                                                                          \
+  if (k0 == A && k1 == B)                                                                                         \
+    return tc::launch_linear_rows_ts_ksplit<TRANS_W, EPI, ACT, A, B>(X, W, ldw, bias, Y, M, n_cols, 1 + A + B, Zs, Yact, omega, \
+                                                                     sm_count, st, of, ring, ring_floats);
+  PK_KS_CASE(0, 0) PK_KS_CASE(1, 0) PK_KS_CASE(2, 1) PK_KS_CASE(3, 0)
+  PK_KS_CASE(1, 1) PK_KS_CASE(3, 1) PK_KS_CASE(2, 2) PK_KS_CASE(4, 1)
+#undef PK_KS_CASE
+  return TC_UNSUPPORTED;
+}
+#endif
+
+#ifdef PINNK_TC_TU_KS_FWD
+// K = 256 forward Linear in one K-split launch (see linear_rows_ts_ksplit_kernel); TC_UNSUPPORTED -> caller runs two passes
+int tc_ks_linear_fwd(const float* X, const float* W, const float* bias, float* Z, int64_t M, int N, int jet_cols, int sm_count,
+                     cudaStream_t st, float* ring, int64_t ring_floats) {
+  if (M < 1 || (N % 128) != 0) return TC_UNSUPPORTED;
+  return tc::launch_linear_rows_ts_ksplit<false, tc::EPI_PLAIN, 1, 0, 0>(X, W, 256, bias, Z, M, N, jet_cols, nullptr, nullptr, 1.f,
+                                                                         sm_count, st, tc::OutFuse{}, ring, ring_floats);
+}
+int tc_ks_linear_act_fwd(const float* X, const float* W, const float* bias, float* Z, float* Yact, int64_t M, int N, int k0,
+                         int k1, int act, float omega, int sm_count, cudaStream_t st, const float* w_out, float* u_part,
+                         float* ring, int64_t ring_floats) {
+  if (M < 1 || (N % 128) != 0 || !tc_jets_supported(k0, k1) || (act != 1 && act != 2)) return TC_UNSUPPORTED;
+  tc::OutFuse of;
+  of.w_out = w_out;
+  of.u_part = u_part;
+  if (act == 1) return tc_ks_dispatch_jets<false, tc::EPI_ACT, 1>(k0, k1, X, W, 256, bias, Z, M, N, nullptr, Yact, 1.f, sm_count, st, of, ring, ring_floats);
+  return tc_ks_dispatch_jets<false, tc::EPI_ACT, 2>(k0, k1, X, W, 256, bias, Z, M, N, nullptr, Yact, omega, sm_count, st, of, ring, ring_floats);
+}
+#endif
+
+#ifdef PINNK_TC_TU_KS_BWD
+// out_dim = 256 dgrad (+ activation adjoint from the stashed pre-activations) in one K-split launch
+int tc_ks_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t M, int in_dim, int sm_count, cudaStream_t st,
+                       float* ring, int64_t ring_floats) {
+  if (M < 1 || (in_dim % 128) != 0) return TC_UNSUPPORTED;
+  return tc::launch_linear_rows_ts_ksplit<true, tc::EPI_PLAIN, 1, 0, 0>(dZ, W, in_dim, nullptr, dX, M, in_dim, 1, nullptr, nullptr, 1.f,
+                                                                        sm_count, st, tc::OutFuse{}, ring, ring_floats);
+}
+int tc_ks_linear_dgrad_actbwd(const float* dZ, const float* W, const float* Zprev, float* dZprev, int64_t M, int in_dim, int k0,
+                              int k1, int act, float omega, int sm_count, cudaStream_t st, float* ring, int64_t ring_floats) {
+  if (M < 1 || (in_dim % 128) != 0 || !tc_jets_supported(k0, k1) || (act != 1 && act != 2)) return TC_UNSUPPORTED;
+  if (act == 1) return tc_ks_dispatch_jets<true, tc::EPI_ACTBWD, 1>(k0, k1, dZ, W, in_dim, nullptr, dZprev, M, in_dim, Zprev, nullptr, 1.f, sm_count, st, tc::OutFuse{}, ring, ring_floats);
+  return tc_ks_dispatch_jets<true, tc::EPI_ACTBWD, 2>(k0, k1, dZ, W, in_dim, nullptr, dZprev, M, in_dim, Zprev, nullptr, omega, sm_count, st, tc::OutFuse{}, ring, ring_floats);
+}
+#endif
+
 #ifdef PINNK_TC_TU_FWD
 int tc_stage_timers_fwd(unsigned long long* out16, int reset) {
 #ifdef PINNK_STAGE_TIMERS
@@ -1935,12 +2222,25 @@ int tc_stage_timers_fwd(unsigned long long* out16, int reset) {
 }
 // Z[M,N] = X[M,K] W[N,K]^T (+ bias on value-column rows).  Returns 0 when launched,
 // TC_UNSUPPORTED when the shape is not covered (caller uses the exact-fp32 CUDA-core GEMM), <0 on error.
+// PINNK_ENABLE_KSPLIT=1: 256-wide contractions as ONE launch of CTA pairs (linear_rows_ts_ksplit_kernel) instead of two K-half
+// launches with the partial product through HBM.  Read per call so that tests can switch it.  Bit-identical to the two passes
+// and NOT the default: measured slower (one 256 x 256 layer over 1.31 M rows: forward 1.65 ms vs 1.29, dgrad 1.30 vs 1.14;
+// profiles/r02y_ksplit.md has the experiments that ruled out the hand-off, the cluster launch and the ring depth).
+static inline bool ksplit_enabled(const float* ring) {
+  if (ring == nullptr) return false;
+  const char* e = getenv("PINNK_ENABLE_KSPLIT");
+  return e && e[0] == '1';
+}
 int tc_linear_fwd(const float* X, const float* W, const float* bias, float* Z, int64_t M, int K, int N,
-                                int jet_cols, int sm_count, cudaStream_t st) {
+                                int jet_cols, int sm_count, cudaStream_t st, float* ring, int64_t ring_floats) {
   if (M < 1 || (N % 128) != 0) return TC_UNSUPPORTED;
   static int use_ss = -1;
   if (use_ss < 0) { const char* e = getenv("PINNK_TC_SS"); use_ss = (e && e[0] == '1') ? 1 : 0; }
   if (K == 128 && !use_ss) return tc::launch_linear_rows_ts<false, tc::EPI_PLAIN, 1, 0, 0>(X, W, K, bias, Z, M, N, jet_cols, nullptr, nullptr, 1.f, sm_count, st);
+  if (K == 256 && ksplit_enabled(ring)) {
+    const int rc = tc_ks_linear_fwd(X, W, bias, Z, M, N, jet_cols, sm_count, st, ring, ring_floats);
+    if (rc != TC_UNSUPPORTED) return rc;
+  }
   if (K == 256) {      // two K halves, the second accumulates onto the first and adds the bias
     int rc = tc::launch_linear_rows_ts<false, tc::EPI_PLAIN, 1, 0, 0>(X, W, K, nullptr, Z, M, N, jet_cols, nullptr, nullptr, 1.f, sm_count, st, K, 0);
     if (rc) return rc;
@@ -1964,10 +2264,14 @@ int tc_linear_fwd(const float* X, const float* W, const float* bias, float* Z, i
 // Forward Linear + activation jets in one kernel: Z = X W^T + b (stash), Yact = act(Z).  act: 1 tanh, 2 sin(omega z).
 int tc_linear_act_fwd(const float* X, const float* W, const float* bias, float* Z, float* Yact, int64_t M, int K,
                                     int N, int k0, int k1, int act, float omega, int sm_count, cudaStream_t st,
-                                    const float* w_out, float* u_part, const TcLossFuse* loss) {
+                                    const float* w_out, float* u_part, const TcLossFuse* loss, float* ring, int64_t ring_floats) {
   if (M < 1 || (K != 128 && K != 256) || (N % 128) != 0 || !tc_jets_supported(k0, k1) || (act != 1 && act != 2)) return TC_UNSUPPORTED;
   if (Yact == nullptr && w_out == nullptr) return TC_UNSUPPORTED;      // nothing would be produced
   if (loss != nullptr && w_out == nullptr) return TC_UNSUPPORTED;
+  if (K == 256 && loss == nullptr && ksplit_enabled(ring)) {
+    const int rc = tc_ks_linear_act_fwd(X, W, bias, Z, Yact, M, N, k0, k1, act, omega, sm_count, st, w_out, u_part, ring, ring_floats);
+    if (rc != TC_UNSUPPORTED) return rc;
+  }
   tc::OutFuse of;
   of.w_out = w_out;
   of.u_part = u_part;
@@ -1997,12 +2301,21 @@ int tc_stage_timers_bwd(unsigned long long* out16, int reset) {
 #endif
 }
 // dX[M,in] = dZ[M,out] W[out,in]   (W row-major [out,in])
+static inline bool ksplit_enabled_bwd(const float* ring) {          // (see ksplit_enabled in the forward unit)
+  if (ring == nullptr) return false;
+  const char* e = getenv("PINNK_ENABLE_KSPLIT");
+  return e && e[0] == '1';
+}
 int tc_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t M, int in_dim, int out_dim,
-                                  int sm_count, cudaStream_t st) {
+                                  int sm_count, cudaStream_t st, float* ring, int64_t ring_floats) {
   if (M < 1 || (in_dim % 128) != 0) return TC_UNSUPPORTED;
   static int use_ss = -1;
   if (use_ss < 0) { const char* e = getenv("PINNK_TC_SS"); use_ss = (e && e[0] == '1') ? 1 : 0; }
   if (out_dim == 128 && !use_ss) return tc::launch_linear_rows_ts<true, tc::EPI_PLAIN, 1, 0, 0>(dZ, W, in_dim, nullptr, dX, M, in_dim, 1, nullptr, nullptr, 1.f, sm_count, st);
+  if (out_dim == 256 && ksplit_enabled_bwd(ring)) {
+    const int rc = tc_ks_linear_dgrad(dZ, W, dX, M, in_dim, sm_count, st, ring, ring_floats);
+    if (rc != TC_UNSUPPORTED) return rc;
+  }
   if (out_dim == 256) {
     int rc = tc::launch_linear_rows_ts<true, tc::EPI_PLAIN, 1, 0, 0>(dZ, W, in_dim, nullptr, dX, M, in_dim, 1, nullptr, nullptr, 1.f, sm_count, st, out_dim, 0);
     if (rc) return rc;
@@ -2014,10 +2327,14 @@ int tc_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t M, int i
 // dgrad + activation adjoint in one kernel: dZprev = act'(Zprev)^T (dZ W)
 int tc_linear_dgrad_actbwd(const float* dZ, const float* W, const float* Zprev, float* dZprev, int64_t M,
                                          int in_dim, int out_dim, int k0, int k1, int act, float omega, int sm_count,
-                                         cudaStream_t st, int from_y) {
+                                         cudaStream_t st, int from_y, float* ring, int64_t ring_floats) {
   if (from_y && act != 1) return TC_UNSUPPORTED;
   if (M < 1 || (out_dim != 128 && out_dim != 256) || (in_dim % 128) != 0 || !tc_jets_supported(k0, k1) || (act != 1 && act != 2))
     return TC_UNSUPPORTED;
+  if (out_dim == 256 && !from_y && ksplit_enabled_bwd(ring)) {
+    const int rc = tc_ks_linear_dgrad_actbwd(dZ, W, Zprev, dZprev, M, in_dim, k0, k1, act, omega, sm_count, st, ring, ring_floats);
+    if (rc != TC_UNSUPPORTED) return rc;
+  }
   int accum = 0;
   if (out_dim == 256) {
     int rc = tc::launch_linear_rows_ts<true, tc::EPI_PLAIN, 1, 0, 0>(dZ, W, in_dim, nullptr, dZprev, M, in_dim, 1, nullptr, nullptr, 1.f, sm_count, st, out_dim, 0);
