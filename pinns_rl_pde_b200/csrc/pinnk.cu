@@ -193,7 +193,7 @@ extern "C" int pinnk_plan_create(const PinnkOp* ops, int32_t n_ops, int32_t in_d
       case PINNK_OP_LAYERNORM:
         if (o.in_dim != cur_width || o.out_dim != cur_width) return bad("LAYERNORM width mismatch");
         if (o.w_index < 0 || o.b_index < 0) return bad("LAYERNORM needs gamma and beta");
-        if (cur_width > 256) return bad("LAYERNORM width > 256 not supported");
+        if (cur_width > 512) return bad("LAYERNORM width > 512 not supported");
         if (prev < 0) return bad("LAYERNORM cannot be the first op");
         if (pending_skip != -2) return bad("SKIP_ADD must be followed by ACT");
         break;
@@ -390,7 +390,8 @@ static int ln_fwd(const ChunkCtx& c, const float* Z, float* Y, int width, const 
   const unsigned blocks = blocks_for(c.n * 32, threads);
   const int nper = (width + 31) / 32;
 #define LN_F(NP) layernorm_fwd_kernel<MAXK, NP><<<blocks, threads, 0, c.st>>>(Z, Y, c.n, width, c.pl->js, g, b, eps)
-  if (nper <= 1) LN_F(1); else if (nper <= 2) LN_F(2); else if (nper <= 4) LN_F(4); else LN_F(8);
+  // (NPER = 16: the 512-wide residual network the reference's YAML ships, config.yaml:15-19)
+  if (nper <= 1) LN_F(1); else if (nper <= 2) LN_F(2); else if (nper <= 4) LN_F(4); else if (nper <= 8) LN_F(8); else LN_F(16);
 #undef LN_F
   PK_LAUNCH_OK();
   return 0;
@@ -408,7 +409,7 @@ static int ln_bwd(const ChunkCtx& c, const float* Z, const float* Gin, float* Go
   const size_t sh = 2 * (size_t)width * sizeof(float);
   const int nper = (width + 31) / 32;
 #define LN_B(NP) layernorm_bwd_kernel<MAXK, NP><<<(unsigned)blocks, threads, sh, c.st>>>(Z, Gin, Gout, c.n, width, c.pl->js, g, eps, dg, db)
-  if (nper <= 1) LN_B(1); else if (nper <= 2) LN_B(2); else if (nper <= 4) LN_B(4); else LN_B(8);
+  if (nper <= 1) LN_B(1); else if (nper <= 2) LN_B(2); else if (nper <= 4) LN_B(4); else if (nper <= 8) LN_B(8); else LN_B(16);
 #undef LN_B
   PK_LAUNCH_OK();
   return 0;
@@ -425,7 +426,7 @@ static int lnact_partner(const pinnk_plan_t pl, int ln) {
   const char* e = getenv("PINNK_ENABLE_LNACT");
   if (!(e && e[0] == '1')) return -1;
   const int n_ops = (int)pl->ops.size();
-  if (ln < 1 || ln >= n_ops - 1 || pl->ops[ln].op.kind != PINNK_OP_LAYERNORM) return -1;
+  if (ln < 1 || ln >= n_ops - 1 || pl->ops[ln].op.kind != PINNK_OP_LAYERNORM || pl->ops[ln].op.in_dim > 256) return -1;
   int j = ln + 1;
   if (j < n_ops - 1 && pl->ops[j].op.kind == PINNK_OP_SKIP_ADD) ++j;
   if (j >= n_ops - 1 || pl->ops[j].op.kind != PINNK_OP_ACT || pl->ops[j].in_op != ln) return -1;

@@ -2322,6 +2322,15 @@ int tc_linear_dgrad(const float* dZ, const float* W, float* dX, int64_t M, int i
     return tc::launch_linear_rows_ts<true, tc::EPI_PLAIN, 1, 0, 0>(dZ + 128, W + (int64_t)128 * in_dim, in_dim, nullptr, dX, M, in_dim, 1, nullptr, nullptr, 1.f, sm_count, st, out_dim, 1);
   }
   if (out_dim == 128) return tc::launch_linear_rows<128, 32, 3, 3, 8, 3, true>(dZ, W, in_dim, nullptr, dX, M, in_dim, 1, sm_count, st);
+  if (out_dim > 256 && (out_dim % 128) == 0 && out_dim <= 1024 && !use_ss) {
+    // wider layers (the 512-wide residual network of the reference's YAML): out_dim / 128 passes, each adding its partial product
+    for (int k0 = 0; k0 < out_dim; k0 += 128) {
+      int rc = tc::launch_linear_rows_ts<true, tc::EPI_PLAIN, 1, 0, 0>(dZ + k0, W + (int64_t)k0 * in_dim, in_dim, nullptr, dX, M, in_dim, 1,
+                                                                      nullptr, nullptr, 1.f, sm_count, st, out_dim, k0 ? 1 : 0);
+      if (rc) return rc;
+    }
+    return 0;
+  }
   return TC_UNSUPPORTED;
 }
 // dgrad + activation adjoint in one kernel: dZprev = act'(Zprev)^T (dZ W)

@@ -119,6 +119,8 @@ FULL = [  # (pde, arch, hidden, layers, dimension, n, extra)  -- BASELINE config
     ("cahn_hilliard", "siren", 256, 5, 2, 1500, {"omega_0": 30.0}),
     ("cahn_hilliard", "siren", 256, 5, 1, 700, {"omega_0": 30.0}),
     ("allen_cahn", "feedforward", 128, 8, 1, 3000, {}),
+    # the residual network the reference's YAML ships (config.yaml:15-19: hidden_dim 512; fewer blocks to keep the CPU oracle short)
+    ("burgers", "resnet", 512, 2, 1, 600, {"num_blocks": 2}),
 ]
 
 
