@@ -62,6 +62,11 @@ CONFIGS = [
          n1=1 << 20, n8=1 << 24, C=18, W=263168),
     dict(key="c5_allen_cahn_scoring", cfg="configs[4]", pde="allen_cahn", arch="feedforward", hidden=128, layers=8, dim=1,
          extra={}, compat="reference", mode="score", n1=1 << 23, n8=1 << 26, C=4, W=115072),
+    # residual-adaptive refinement over BASELINE configs[4]'s 64 M-candidate pool (pde_base.py:895-935: score, then draw pool / 4
+    # points with probability |r| + 1e-8): forward-only scoring + the on-device inverse-CDF sampler (the pool is past
+    # torch.multinomial's 2^24 limit).  The global pool is 64 M at every GPU count (strong scaling).
+    dict(key="c5_rar_draw_64m", cfg="configs[4] pool, scored and sampled (RAR)", pde="allen_cahn", arch="feedforward", hidden=128,
+         layers=8, dim=1, extra={}, compat="reference", mode="rar", n1=1 << 26, n8=1 << 26, C=4, W=115072, fixed_global=True),
 ]
 PDE_SPECS = {
     "heat": dict(domain=[[0.0, 1.0]], time=[0.0, 1.0], params={"alpha": 0.01}, bcs={"dirichlet": {"type": "dirichlet"}},
@@ -291,8 +296,8 @@ def run_config_entry(pk, c, dev, world, rank, tensor_tf32, tensor_bf16, flush):
     """One secondary entry: 2 warm-up + 3 timed steps (CUDA events per step, L2 flushed in between, max over ranks)."""
     import torch.distributed as dist
     from pinns_rl_pde_b200 import engine, parallel, functional as F
-    strong = world == 8 and c["n8"] is not None
-    n_global = c["n8"] if strong else c["n1"] * world
+    strong = (world == 8 and c["n8"] is not None) or (c.get("fixed_global", False) and world > 1)
+    n_global = c["n1"] if c.get("fixed_global", False) else (c["n8"] if strong else c["n1"] * world)
     lo, hi = parallel.shard_bounds(n_global, rank, world)
     n_local = hi - lo
     torch.manual_seed(0)
@@ -326,6 +331,10 @@ def run_config_entry(pk, c, dev, world, rank, tensor_tf32, tensor_bf16, flush):
             buf[P:P + 1].copy_(sums)
             parallel.reduce_inplace(buf)
             return buf[P]
+    elif c["mode"] == "rar":
+        def step():
+            xs, ts = parallel.sharded_residual_sample(pde, model, x, t, n_global // 4)
+            return xs.shape[0]
     else:
         def step():
             return parallel.sharded_score(pde, model, x, t, want_abs=True)[1]
@@ -351,14 +360,15 @@ def run_config_entry(pk, c, dev, world, rank, tensor_tf32, tensor_bf16, flush):
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     ms = float(tt.item())
-    flops_pt = (2 if c["mode"] == "score" else 6) * c["C"] * c["W"]
+    flops_pt = (2 if c["mode"] in ("score", "rar") else 6) * c["C"] * c["W"]
     pps = n_global / (ms * 1e-3)
     tfl = pps * flops_pt / 1e12 / world                     # per GPU
     del model, pde
     engine._CACHE.clear() if hasattr(engine._CACHE, "clear") else None
     torch.cuda.empty_cache()
     return {"key": c["key"], "baseline_config": c["cfg"], "step": {"loss": "compute_loss + backward + clip + Adam (fused trainer step)",
-                                                                    "mse": "mean(compute_residual^2) + backward", "score": "forward-only |r| + statistics"}[c["mode"]],
+                                                                    "mse": "mean(compute_residual^2) + backward", "score": "forward-only |r| + statistics",
+                                                                    "rar": "forward-only |r| of the pool + device draw of pool / 4 points (two-level inverse CDF)"}[c["mode"]],
             "global_points": n_global, "points_per_gpu": n_local, "scaling": "strong" if strong else "weak", "n_gpus": world,
             "ms_per_step": ms, "value": pps, "unit": "points/s", "jet_columns": c["C"], "flop_per_point": flops_pt,
             "achieved_tflops_per_gpu": tfl,
