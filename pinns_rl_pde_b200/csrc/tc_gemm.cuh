@@ -79,6 +79,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #ifndef PINNK_EPI_SLEEP
 #define PINNK_EPI_SLEEP 64      // ns between probes (A/B: PINNK_NVCC_EXTRA=-DPINNK_EPI_SLEEP=...; 0 = hinted try_wait instead)
 #endif
+// Wait of the wgrad flush warps: a segment (SEG tiles, ~3 us) separates two flushes and the accumulators are double-buffered, so
+// waking up to half a microsecond late costs nothing, while probing every ~100 ns made these four mostly idle warps issue a
+// fifth of the kernel's instructions (152 probes per tile and SM; profiles/r02_final.md) on schedulers the convert warps need.
+__device__ __forceinline__ void mbar_wait_lazy(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+    __nanosleep(512);
+  }
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
 #if PINNK_EPI_SLEEP == 0
   mbar_wait(bar, parity);
@@ -1857,7 +1876,7 @@ wgrad_body(const float* __restrict__ G, int ldg, const float* __restrict__ X, in
       const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
       for (int64_t seg = 0; seg < my_segs; ++seg) {
         const int b = (int)(seg & 1);
-        mbar_wait_relaxed(&tfull[b], (uint32_t)(seg >> 1) & 1u);
+        mbar_wait_lazy(&tfull[b], (uint32_t)(seg >> 1) & 1u);
         tc_fence_after();
 #pragma unroll 1
         for (int c0 = 0; c0 < 128; c0 += 32) {
