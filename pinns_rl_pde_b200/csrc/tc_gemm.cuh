@@ -1606,7 +1606,11 @@ static int launch_linear_rows_ts_ksplit(const float* X, const float* W, int ldw,
 // (body of wgrad_kernel; cta_x / ncta_x / cta_y as in linear_rows_ts_body.  PAIR: the CTA is the wgrad half of a reverse-pass
 // pair and walks the 64-row macro tiles of its partner -- 32-row tiles 2T, 2T+1 for T = cta_x, cta_x + ncta_x, ... -- with the
 // lock-step throttle in its TMA warp)
-template <int TK, int RS, int OS, int NCW, int SEG, bool TSA, bool PAIR = false>
+// GLD (TS mode): the G warps read their rows of dZ straight from global memory into registers, two tiles ahead, instead of
+// through the TMA ring -- G goes to tensor memory anyway, so its trip through shared memory (a TMA write and a shared-memory
+// read of 16 KB per tile, 256 of the ~1 150 wavefronts the shared-memory port carries per tile) bought nothing.  These warps
+// execute no generic->async proxy fence (their operand path is tcgen05.st), so loads in flight do not stall on one.
+template <int TK, int RS, int OS, int NCW, int SEG, bool TSA, bool PAIR = false, bool GLD = false>
 __device__ __forceinline__ void
 wgrad_body(const float* __restrict__ G, int ldg, const float* __restrict__ X, int ldx, float* __restrict__ dW, int lddw,
            float* __restrict__ db, int64_t M, int jet_cols, int in_blocks, const CUtensorMap* tmgp, const CUtensorMap* tmxmp,
@@ -1625,6 +1629,7 @@ wgrad_body(const float* __restrict__ G, int ldg, const float* __restrict__ X, in
   // TMEM (TSA): [0,256) main0|main1 | [256,384) sum | [384,512) 2 stages x {G_hi 32, G_lo 32}; the lo*hi + hi*lo corrections
   // go to the segment's main accumulator (no room for their own; a segment is 48 accumulate steps instead of 16).
   static_assert(!TSA || (OS == 2 && NCW == 16), "TS-mode wgrad: two operand stages, 8 G + 8 X convert warps");
+  static_assert(!GLD || TSA, "direct G loads need the tensor-memory operand path");
   constexpr uint32_t OP_BYTES = TK * 512;          // one of G_hi / G_lo / X_hi / X_lo per operand stage (TK rows x 128 floats)
   constexpr uint32_t RAW_BYTES = TK * 512;         // raw G (or X) tile
   // warp roles: [0, NCW) convert | NCW..NCW+3 flush (TMEM lane quarters; NCW % 4 == 0) | NCW+4 MMA | NCW+5 TMA | 2 idle
@@ -1667,7 +1672,7 @@ wgrad_body(const float* __restrict__ G, int ldg, const float* __restrict__ X, in
   const int64_t my_segs = (my_tiles + SEG - 1) / SEG;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < RS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], NCW); }
+    for (int s = 0; s < RS; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], GLD ? NCW / 2 : NCW); }   // (GLD: X warps only)
     for (int s = 0; s < OS; ++s) { mbar_init(&full[s], NCW); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
     fence_mbar_init();
@@ -1694,9 +1699,11 @@ wgrad_body(const float* __restrict__ G, int ldg, const float* __restrict__ X, in
         const uint32_t dg = rb + (uint32_t)s * 2 * RAW_BYTES, dx = dg + RAW_BYTES;
         // contiguous 128-wide tensors: one bulk copy; 128-column blocks of wider tensors: one tiled copy (box [TK x 128],
         // rows past M arrive as zeros and count in the transaction bytes)
-        mbar_arrive_expect_tx(&raw_full[s], (uint32_t)(ldg == 128 ? nrows : TK) * 512u + (uint32_t)(ldx == 128 ? nrows : TK) * 512u);
-        if (ldg == 128) tma_bulk_g2s(dg, G + r0 * 128, (uint32_t)nrows * 512u, &raw_full[s]);
-        else tma_tile_2d(dg, tmgp, o0, (int)r0, &raw_full[s]);
+        mbar_arrive_expect_tx(&raw_full[s], (GLD ? 0u : (uint32_t)(ldg == 128 ? nrows : TK) * 512u) + (uint32_t)(ldx == 128 ? nrows : TK) * 512u);
+        if constexpr (!GLD) {
+          if (ldg == 128) tma_bulk_g2s(dg, G + r0 * 128, (uint32_t)nrows * 512u, &raw_full[s]);
+          else tma_tile_2d(dg, tmgp, o0, (int)r0, &raw_full[s]);
+        }
         if (ldx == 128) tma_bulk_g2s(dx, X + r0 * 128, (uint32_t)nrows * 512u, &raw_full[s]);
         else tma_tile_2d(dx, tmxmp, i0, (int)r0, &raw_full[s]);
         if constexpr (PAIR) { if (it & 1) ps.publish((uint32_t)(it >> 1) + 1u); }
@@ -1714,7 +1721,76 @@ wgrad_body(const float* __restrict__ G, int ldg, const float* __restrict__ X, in
     // l+96, so the four values of a feature for the quad are one 16-byte chunk and a quarter-warp's STS.128 hit eight
     // distinct 16-byte slots (conflict-free), while the raw reads are lane-contiguous LDS.32.
     static_assert(NCW == 16 && TK == 32, "convert mapping");
-    if (TSA && warp < 8) {
+    if (TSA && GLD && warp < 8) {
+      // ---- G warps, TS mode, direct loads: warp (q, h) owns out-features f = 32q + lane and rows 16h .. 16h + 15 of a tile; its
+      // 16 values per lane come from global memory (each warp instruction reads 128 contiguous bytes of one row) into one of
+      // two register tiles, requested two tiles before they are converted
+      const int q = warp & 3, h = warp >> 2, f = q * 32 + lane;
+      float bsum1 = 0.f;
+      const bool want_b1 = (db != nullptr) && (i0 == 0);
+      const bool b_fixed1 = (jet_cols == 1 || jet_cols == 2 || jet_cols == 4);
+      const uint32_t b_mask1 = (jet_cols == 1) ? 0xFu : (jet_cols == 2) ? 0x5u : 0x1u;
+      const uint32_t a_lane = tmem_base + ((uint32_t)(q * 32) << 16) + COL_A + (uint32_t)(h * 16);
+      const float* const gcol = G + o0 + f;
+      auto gload = [&](const int64_t it, float (&dst)[16]) {
+        if (it < my_tiles) {
+          const int64_t r0 = tile_at(it) * TK + h * 16;
+          const float* gp = gcol + r0 * ldg;
+          if (M - r0 >= 16) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dst[j] = __ldg(gp + (int64_t)j * ldg);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dst[j] = (r0 + j < M) ? __ldg(gp + (int64_t)j * ldg) : 0.f;
+          }
+        }
+      };
+      int os = 0;
+      uint32_t oph = 0;
+      auto gconvert = [&](const int64_t it, const float (&v)[16]) {
+        mbar_wait(&empty[os], oph ^ 1u);
+        tc_fence_after();
+        if (want_b1) {
+          if (b_fixed1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if ((b_mask1 >> (j & 3)) & 1u) bsum1 += v[j];
+          } else {
+            uint32_t cj = (uint32_t)((uint32_t)(tile_at(it) * TK + h * 16) % (uint32_t)jet_cols);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (cj == 0) bsum1 += v[j];
+              cj = (cj + 1 == (uint32_t)jet_cols) ? 0u : cj + 1;
+            }
+          }
+        }
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) split_bits(v[j], hi[j], lo[j]);
+        tmem_st16(a_lane + (uint32_t)os * 64u, hi);
+        tmem_st16(a_lane + (uint32_t)os * 64u + 32u, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[os]);
+        if (++os == OS) { os = 0; oph ^= 1u; }
+      };
+      float va[16], vb[16];
+      gload(0, va);
+      gload(1, vb);
+      for (int64_t it = 0; it < my_tiles; it += 2) {
+        gconvert(it, va);
+        gload(it + 2, va);
+        if (it + 1 < my_tiles) {
+          gconvert(it + 1, vb);
+          gload(it + 3, vb);
+        }
+      }
+      if (want_b1) {
+        if (det_bpart) det_bpart[((int64_t)(cta_y * ncta_x + cta_x) * 2 + h) * 128 + f] = bsum1;
+        else atomicAdd(db + o0 + f, bsum1);
+      }
+    } else if (TSA && warp < 8) {
       // ---- G warps, TS mode: warp (q = warp & 3, h = warp >> 2) owns TMEM lanes 32q.. (out-features f = 32q + lane) and
       // rows 16h .. 16h + 15 of the tile: 16 lane-contiguous LDS.32, hi/lo split, two tcgen05.st of 16 columns
       const int q = warp & 3, h = warp >> 2, f = q * 32 + lane;
@@ -2011,13 +2087,13 @@ wgrad_body(const float* __restrict__ G, int ldg, const float* __restrict__ X, in
   }
 }
 
-template <int TK, int RS, int OS, int NCW, int SEG, bool TSA>
+template <int TK, int RS, int OS, int NCW, int SEG, bool TSA, bool GLD = false>
 __global__ void __launch_bounds__((NCW + 8) * 32, 1)
 wgrad_kernel(const float* __restrict__ G, int ldg, const float* __restrict__ X, int ldx, float* __restrict__ dW, int lddw,
              float* __restrict__ db, int64_t M, int jet_cols, int in_blocks, const __grid_constant__ CUtensorMap tmg,
              const __grid_constant__ CUtensorMap tmxm, float* __restrict__ det_part, float* __restrict__ det_bpart) {
-  wgrad_body<TK, RS, OS, NCW, SEG, TSA, false>(G, ldg, X, ldx, dW, lddw, db, M, jet_cols, in_blocks, &tmg, &tmxm, det_part, det_bpart,
-                                               (int)blockIdx.x, (int)gridDim.x, (int)blockIdx.y, PairSync{});
+  wgrad_body<TK, RS, OS, NCW, SEG, TSA, false, GLD>(G, ldg, X, ldx, dW, lddw, db, M, jet_cols, in_blocks, &tmg, &tmxm, det_part, det_bpart,
+                                                    (int)blockIdx.x, (int)gridDim.x, (int)blockIdx.y, PairSync{});
 }
 
 // fixed-order reduction of the per-CTA partial slabs of a deterministic wgrad launch: dW[block] += sum_x part[block][x]
@@ -2048,12 +2124,12 @@ static __global__ void wgrad_det_reduce_kernel(const float* __restrict__ part, c
   }
 }
 
-template <int TK, int RS, int OS, int NCW, int SEG, bool TSA>
+template <int TK, int RS, int OS, int NCW, int SEG, bool TSA, bool GLD = false>
 static int launch_wgrad(const float* G, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
                         int jet_cols, int sm_count, cudaStream_t st, float* det_scratch = nullptr, int64_t det_floats = 0) {
   constexpr size_t smem = 1024 + (size_t)OS * (TSA ? 2 : 4) * TK * 512 + (size_t)RS * 2 * TK * 512 + (2 * RS + 2 * OS + 4) * 8 + 16;
   static_assert(smem <= 232448 && (size_t)RS * 2 * TK * 512 >= 128 * 132 * 4, "shared memory budget / transpose buffer");
-  auto kern = wgrad_kernel<TK, RS, OS, NCW, SEG, TSA>;
+  auto kern = wgrad_kernel<TK, RS, OS, NCW, SEG, TSA, GLD>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
@@ -2428,6 +2504,10 @@ int tc_stage_timers_wgrad(unsigned long long* out16, int reset) {
 int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
                                   int jet_cols, int sm_count, cudaStream_t st, float* det_scratch, int64_t det_floats) {
   if (M < 1 || (in_dim % 128) != 0 || (out_dim % 128) != 0 || dW == nullptr) return TC_UNSUPPORTED;
+  // PINNK_WGRAD_GLD=1: the G operand straight from global memory into registers instead of through the TMA ring (A/B; read per call)
+  { const char* e = getenv("PINNK_WGRAD_GLD");
+    if (e && e[0] == '1')
+      return tc::launch_wgrad<32, 5, 2, 16, 4, true, true>(dZ, X, dW, db, M, in_dim, out_dim, jet_cols, sm_count, st, det_scratch, det_floats); }
   if (det_scratch != nullptr)
     return tc::launch_wgrad<32, 5, 2, 16, 4, true>(dZ, X, dW, db, M, in_dim, out_dim, jet_cols, sm_count, st, det_scratch, det_floats);
   static int ss = -1;       // PINNK_WGRAD_SS=1: both operands in shared memory (the earlier kernel, kept for A/B runs)
