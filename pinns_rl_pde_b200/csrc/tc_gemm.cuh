@@ -607,9 +607,6 @@ __device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t remote_bar_a
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-#ifdef PINNK_KS_NOSYNC
-  return;
-#endif
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
   for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
@@ -792,16 +789,12 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
   const uint32_t tmem_base = *tmem_slot;
   // K-split: the partner's barriers (same offsets in its shared memory); both CTAs' barriers exist before either can arrive
   uint32_t peer_pfull = 0, peer_pempty = 0;
-#ifndef PINNK_KS_NOCLUSTER
   if constexpr (KS != 0) {
     const uint32_t peer = cluster_ctarank() ^ 1u;
     peer_pfull = mapa_u32(smem_u32(pfull), peer);
     peer_pempty = mapa_u32(smem_u32(pempty), peer);
     cluster_sync_all();
   }
-#else
-  if constexpr (KS != 0) { peer_pfull = smem_u32(pfull); peer_pempty = smem_u32(pempty); }
-#endif
   (void)peer_pfull; (void)peer_pempty;
 
   // resident weights -> TMEM: an epilogue warp (q, h) owns TMEM lanes 32q.. (rows f of the A operand) and stages the
@@ -955,9 +948,7 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
         // (CTA-scope wait: an acquire at cluster scope invalidates the SM's whole L1 -- CCTL.IVALL -- and 17 of those per tile
         // were the longest item of the consumer's tile time.  The phase flips only after the partner's release has made its
         // stores visible in L2, the loads below are issued after the flip is seen and bypass L1 (ld.global.cg).)
-#ifndef PINNK_KS_NOSYNC
         mbar_wait(&pfull[s_], (uint32_t)(it_ / kKsRing) & 1u);
-#endif
         const float* const rp = ring + (size_t)s_ * (64 * 128) + (size_t)(h * ECE) * 128 + f;
 #pragma unroll
         for (int j = 0; j < ECOLS; ++j) dst[j] = (j < ECE) ? __ldcg(rp + j * 128) : 0.f;
@@ -1043,9 +1034,7 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
         }
       } else if constexpr (EPI == EPI_PARTIAL) {
         // hand the partial product to the partner: wait until it has read this slot's previous tile, store, publish
-#ifndef PINNK_KS_NOSYNC
         mbar_wait(&pempty[ks_s], ks_ph ^ 1u);          // (write-after-read only: nothing of the partner's is read here)
-#endif
         float* const rp = ring + (size_t)ks_s * (64 * 128) + (size_t)(h * ECE) * 128 + f;
 #pragma unroll
         for (int j = 0; j < ECOLS; ++j)
@@ -1375,9 +1364,7 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
           constexpr int kKsLag = 3;
           if (tile + (int64_t)kKsLag * ncta_x < ntiles) {
             const int it2 = it + kKsLag;
-#ifndef PINNK_KS_NOSYNC
             mbar_wait(&pfull[it2 % kKsRing], (uint32_t)(it2 / kKsRing) & 1u);
-#endif
           }
         }
         PK_T0();
@@ -1418,9 +1405,7 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
   tc_fence_before();
   __syncthreads();
   // K-split: no CTA may exit while its partner can still arrive on its barriers
-#ifndef PINNK_KS_NOCLUSTER
   if constexpr (KS != 0) cluster_sync_all();
-#endif
   if (warp == MMAW) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -1508,22 +1493,14 @@ static int launch_linear_rows_ts(const float* X, const float* W, int ldw, const 
 // traffic per row drops from 4.5 - 5.5 KB (two passes) to what the layer needs (read X, (stash,) write Y), and both halves are
 // tensor-bound like the first pass alone was (82 % tensor pipe active, profiles/r02s_c3_rows.md).
 template <bool TRANS_W, int EPI, int ACT, int K0, int K1, int ECOLS, int LDYC>
-__global__ void
-#ifndef PINNK_KS_NOCLUSTER
-__cluster_dims__(1, 1, 2)
-#endif
-__launch_bounds__((8 + 4 * (64 / ECOLS) + 2) * 32, 1)
+__global__ void __cluster_dims__(1, 1, 2) __launch_bounds__((8 + 4 * (64 / ECOLS) + 2) * 32, 1)
 linear_rows_ts_ksplit_kernel(const float* __restrict__ X, const float* __restrict__ W, int ldw, int w_half_stride,
                              const float* __restrict__ bias, float* __restrict__ Y, int64_t M, int ldy_rt, int jet_cols,
                              const float* __restrict__ Zs, float* __restrict__ Yact, float omega, int ldx, OutFuse of,
                              float* __restrict__ ring_base, const __grid_constant__ CUtensorMap tm0,
                              const __grid_constant__ CUtensorMap tm1) {
   float* const ring = ring_base + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * (kKsRing * 64 * 128);
-#ifdef PINNK_KS_NOCLUSTER
-  if (blockIdx.z == 0) {
-#else
   if (cluster_ctarank() == 0) {
-#endif
     linear_rows_ts_body<TRANS_W, EPI_PARTIAL, 1, K0, K1, 8, ECOLS, false, 128, false, false, 1>(
         X, W, ldw, nullptr, nullptr, M, ldy_rt, jet_cols, nullptr, nullptr, 1.f, ldx, OutFuse{}, FirstLayer{}, TcLossFuse{}, &tm0,
         (int)blockIdx.x, (int)gridDim.x, (int)blockIdx.y, PairSync{}, ring);
