@@ -86,6 +86,8 @@ class JetEngine:
 
     # ------------------------------------------------------------------ helpers
     def _params(self):
+        if self.program.padded:
+            self.program.refresh_shadows()
         for i, tn in enumerate(self.program.tensors):
             _require_cuda_f32(tn, "model parameter")
             if not tn.is_contiguous():
@@ -136,14 +138,33 @@ class JetEngine:
         if flat_grad is None:
             flat_grad = torch.zeros(self.program.grad_floats, dtype=torch.float32, device=self.device)
         if n:
+            target = self._pad_target(flat_grad)
             L.check(self.lib.pinnk_jets_vjp(self.handle, self._params(), x.data_ptr(), self._ptr(t), n,
-                                            adj.data_ptr(), flat_grad.data_ptr(), self.workspace.data_ptr(),
+                                            adj.data_ptr(), target.data_ptr(), self.workspace.data_ptr(),
                                             self.ws_bytes, self._stream()), "pinnk_jets_vjp")
+            self._pad_finish(target, flat_grad)
         return flat_grad
+
+    # width-padded programs (program.pad_entries): the library accumulates into a zeroed flat gradient laid out over the
+    # shadow tensors; the real entries are then added into the caller's buffer (model.parameters() layout)
+    def _pad_target(self, flat_grad: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+        if flat_grad is None or not self.program.padded:
+            return flat_grad
+        if getattr(self, "_flat_pad", None) is None:
+            self._flat_pad = torch.zeros(self.program.pad_floats, dtype=torch.float32, device=self.device)
+        else:
+            self._flat_pad.zero_()
+        return self._flat_pad
+
+    def _pad_finish(self, target: Optional[torch.Tensor], flat_grad: Optional[torch.Tensor]):
+        if flat_grad is not None and target is not flat_grad:
+            self.program.unpad_add(target, flat_grad)
 
     def stash_signature(self):
         """What has to be unchanged between a keep_stash forward and the reverse pass that reuses its stash."""
-        return tuple((tn.data_ptr(), tn._version) for tn in self.program.tensors)
+        # (width-padded programs: the REAL parameters -- the shadows are rewritten from them at every call)
+        tens = [real for real, _, _, _ in self.program.pad_entries] if self.program.padded else self.program.tensors
+        return tuple((tn.data_ptr(), tn._version) for tn in tens)
 
     def loss_step(self, x, t, segments: Sequence[Segment], n_components: int, want_grad: bool,
                   grad_scale: Optional[Sequence[float]] = None, flat_grad: Optional[torch.Tensor] = None,
@@ -183,11 +204,13 @@ class JetEngine:
         if grad_scale is not None:
             gs = (C.c_float * n_components)(*[float(g) for g in grad_scale])
         if n:
+            target = self._pad_target(flat_grad if want_grad else None)
             L.check(self.lib.pinnk_loss_step_flags(self.handle, self._params(), x.data_ptr(), self._ptr(t), n, segs,
                                                    len(segments), C.cast(gs, C.c_void_p) if gs is not None else None,
-                                                   loss_sums.data_ptr(), self._ptr(flat_grad) if want_grad else None,
+                                                   loss_sums.data_ptr(), self._ptr(target) if want_grad else None,
                                                    self.workspace.data_ptr(), self.ws_bytes, self._stream(), flags),
                     "pinnk_loss_step")
+            self._pad_finish(target, flat_grad if want_grad else None)
             if flags == L.STEP_KEEP_STASH:
                 self._token_count += 1
                 self._stash_token = (self._token_count, x.data_ptr(), self._ptr(t), n, self.stash_signature())
