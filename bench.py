@@ -309,7 +309,9 @@ def run_config_entry(pk, c, dev, world, rank, tensor_tf32, tensor_bf16, flush):
     t = torch.rand(n_local, 1, generator=g, device=dev) * (s["time"][1] - s["time"][0]) + s["time"][0]
     if c["mode"] == "loss":
         cfg = pk.TrainingConfig(learning_rate=1e-3, weight_decay=0.0, gradient_clipping=1.0, scheduler="none")
-        trainer = pk.PDETrainer(model, pde, config=cfg, device=dev, fused=True)
+        # batches of the reference's own size (BASELINE configs[0]: 4 900 points) are launch-bound: replay the step as a CUDA graph
+        use_graph = world == 1 and n_local <= 32768
+        trainer = pk.PDETrainer(model, pde, config=cfg, device=dev, fused=True, graph=use_graph)
 
         def step():
             return trainer.train_step(x, t, n_global=n_global)["total"]
@@ -343,7 +345,7 @@ def run_config_entry(pk, c, dev, world, rank, tensor_tf32, tensor_bf16, flush):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-    for _ in range(2):
+    for _ in range(6 if (c["mode"] == "loss" and world == 1 and n_local <= 32768) else 2):     # (graph: eager warm-up calls + capture)
         step()
     evs = []
     sync()
@@ -368,7 +370,8 @@ def run_config_entry(pk, c, dev, world, rank, tensor_tf32, tensor_bf16, flush):
     torch.cuda.empty_cache()
     return {"key": c["key"], "baseline_config": c["cfg"], "step": {"loss": "compute_loss + backward + clip + Adam (fused trainer step)",
                                                                     "mse": "mean(compute_residual^2) + backward", "score": "forward-only |r| + statistics",
-                                                                    "rar": "forward-only |r| of the pool + device draw of pool / 4 points (two-level inverse CDF)"}[c["mode"]],
+                                                                    "loss_graph": "compute_loss + backward + clip + Adam (fused trainer step replayed as a CUDA graph)",
+                                                                    "rar": "forward-only |r| of the pool + device draw of pool / 4 points (two-level inverse CDF)"}["loss_graph" if (c["mode"] == "loss" and world == 1 and n_local <= 32768) else c["mode"]],
             "global_points": n_global, "points_per_gpu": n_local, "scaling": "strong" if strong else "weak", "n_gpus": world,
             "ms_per_step": ms, "value": pps, "unit": "points/s", "jet_columns": c["C"], "flop_per_point": flops_pt,
             "achieved_tflops_per_gpu": tfl,
