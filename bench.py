@@ -49,9 +49,11 @@ CPU_SAMPLE_POINTS = 65536                         # N_cpu
 # n1: points per GPU in the default (weak) runs; n8: BASELINE's GLOBAL size, used with --gpus 8 (strong-scaling entry).
 CONFIGS = [
     dict(key="c1_heat_fourier_4900", cfg="configs[0]", pde="heat", arch="fourier", hidden=128, layers=4, dim=1,
-         extra={"mapping_size": 32, "scale": 10.0}, compat="reference", mode="loss", n1=4900, n8=None, C=3, W=41152),
+         extra={"mapping_size": 32, "scale": 10.0}, compat="reference", mode="loss", n1=4900, n8=None, C=3, W=41152,
+         training={"num_collocation_points": 5000, "num_boundary_points": 500, "num_initial_points": 500}),      # README.md:99-141
     dict(key="c1_heat_fourier_1m", cfg="configs[0] network at 1 M points", pde="heat", arch="fourier", hidden=128, layers=4, dim=1,
-         extra={"mapping_size": 32, "scale": 10.0}, compat="reference", mode="loss", n1=1 << 20, n8=None, C=3, W=41152),
+         extra={"mapping_size": 32, "scale": 10.0}, compat="reference", mode="loss", n1=1 << 20, n8=None, C=3, W=41152,
+         training={"num_collocation_points": 5000, "num_boundary_points": 500, "num_initial_points": 500}),      # (same README row counts)
     dict(key="c3_kdv_resnet_6x256", cfg="configs[2]", pde="kdv", arch="resnet", hidden=256, layers=6, dim=1,
          extra={"num_blocks": 6}, compat="reference", mode="loss", n1=1 << 19, n8=1 << 22, C=5, W=787200),
     dict(key="c4_cahn_hilliard_2d_siren_5x256_as_written", cfg="configs[3], operator as the reference evaluates it (u_t, SURVEY F2)",
@@ -286,7 +288,8 @@ def make_pde(pk, c, dev):
     s = PDE_SPECS[c["pde"]]
     cfg = pk.PDEConfig(name=c["pde"], domain=[list(d) for d in s["domain"] * c["dim"]], time_domain=list(s["time"]),
                        parameters=dict(s["params"]), boundary_conditions={k: dict(v) for k, v in s["bcs"].items()},
-                       initial_condition=dict(s["ic"]), exact_solution=dict(s["exact"]), dimension=c["dim"], device=dev)
+                       initial_condition=dict(s["ic"]), exact_solution=dict(s["exact"]), dimension=c["dim"], device=dev,
+                       training=c.get("training"))
     pde = pk.create_pde(c["pde"], cfg)
     pde.compat = c["compat"]
     return pde
