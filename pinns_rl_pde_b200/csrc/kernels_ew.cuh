@@ -557,16 +557,21 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ Z, float* __restr
     float c[MAXK + 1][NPER];
 #pragma unroll
     for (int i = 0; i < NPER; ++i) c[0][i] = c0[i];
+    // every load of the direction is issued before the first reduction needs one (a warp walks its point alone: a load
+    // issued behind a shuffle chain is a round trip on its serial path)
+#pragma unroll
+    for (int k = 1; k <= MAXK; ++k)
+#pragma unroll
+      for (int i = 0; i < NPER; ++i) {
+        const int f = lane + 32 * i;
+        c[k][i] = (k <= K && f < width) ? Z[b1 + (int64_t)(k - 1) * width + f] : 0.f;
+      }
 #pragma unroll
     for (int k = 1; k <= MAXK; ++k) {
       if (k <= K) {
         float sm = 0.f;
 #pragma unroll
-        for (int i = 0; i < NPER; ++i) {
-          const int f = lane + 32 * i;
-          c[k][i] = (f < width) ? Z[b1 + (int64_t)(k - 1) * width + f] : 0.f;
-          sm += c[k][i];
-        }
+        for (int i = 0; i < NPER; ++i) sm += c[k][i];
         const float mk = warp_sum(sm) * inv_w;
         float vk = 0.f;
 #pragma unroll
@@ -597,8 +602,13 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ Z, float* __restr
 }
 
 // Reverse of the above.  G_in = dL/dY, G_out = dL/dZ (distinct buffers); dgamma/dbeta accumulated per block.
+// Four resident blocks per SM (128 registers, a few hundred bytes of spills at 8 features per lane) beat the three that the
+// kernel's natural 168 registers allow: C3's LayerNorm reverse 16.7 -> 15.1 ms; five blocks (96 registers) lose again (19.5 ms).
+#ifndef PINNK_LNB_MINBLOCKS
+#define PINNK_LNB_MINBLOCKS 4
+#endif
 template <int MAXK, int NPER>
-__global__ void layernorm_bwd_kernel(const float* __restrict__ Z, const float* __restrict__ Gin,
+__global__ void __launch_bounds__(128, (NPER <= 8) ? PINNK_LNB_MINBLOCKS : 1) layernorm_bwd_kernel(const float* __restrict__ Z, const float* __restrict__ Gin,
                                      float* __restrict__ Gout, int64_t n, int width, JetSpec js,
                                      const float* __restrict__ gamma, float eps,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta) {
@@ -659,17 +669,22 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ Z, const float* _
       float c[MAXK + 1][NPER], yb[MAXK + 1][NPER];
 #pragma unroll
       for (int i = 0; i < NPER; ++i) { c[0][i] = c0[i]; yb[0][i] = 0.f; }   // yb[0] direct term handled above
+      // (all loads of the direction first: see layernorm_fwd_kernel)
+#pragma unroll
+      for (int k = 1; k <= MAXK; ++k)
+#pragma unroll
+        for (int i = 0; i < NPER; ++i) {
+          const int f = lane + 32 * i;
+          const bool in = k <= K && f < width;
+          c[k][i] = in ? Z[b1 + (int64_t)(k - 1) * width + f] : 0.f;
+          yb[k][i] = in ? Gin[b1 + (int64_t)(k - 1) * width + f] : 0.f;
+        }
 #pragma unroll
       for (int k = 1; k <= MAXK; ++k) {
         if (k <= K) {
           float sm = 0.f;
 #pragma unroll
-          for (int i = 0; i < NPER; ++i) {
-            const int f = lane + 32 * i;
-            c[k][i] = (f < width) ? Z[b1 + (int64_t)(k - 1) * width + f] : 0.f;
-            yb[k][i] = (f < width) ? Gin[b1 + (int64_t)(k - 1) * width + f] : 0.f;
-            sm += c[k][i];
-          }
+          for (int i = 0; i < NPER; ++i) sm += c[k][i];
           const float mk = warp_sum(sm) * inv_w;
           float vk = 0.f;
 #pragma unroll
@@ -681,8 +696,6 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ Z, const float* _
           }
           v[k] = warp_sum(vk) * inv_w;
         } else {
-#pragma unroll
-          for (int i = 0; i < NPER; ++i) { c[k][i] = 0.f; yb[k][i] = 0.f; }
           v[k] = 0.f;
         }
       }
