@@ -47,6 +47,36 @@ def main():
     ok2 = ds < 1e-6 and xs.shape == (4096, 1) and ts.shape == (4096, 1)
     print(f"rank {dist.get_rank()}: sharded score stats rel {ds:.2e}, RAR selection {tuple(xs.shape)} -> {'OK' if ok2 else 'FAIL'}")
     ok = ok and ok2
+    # Heat with the smoothness regulariser (heat_equation.py:625-650, weight 0.1 as the reference's YAML ships it): the fused
+    # data-parallel trainer step (rows sharded, one in-place all-reduce of [gradient || 4 loss sums]) follows the single-process one
+    import copy
+    training = {"num_collocation_points": 5000, "num_boundary_points": 200, "num_initial_points": 200,
+                "loss_weights": {"residual": 1.0, "boundary": 10.0, "initial": 10.0, "smoothness": 0.1}}
+    cfgh = pk.PDEConfig(name="heat", domain=[[0.0, 1.0]], time_domain=[0.0, 1.0], parameters={"alpha": 0.01},
+                        boundary_conditions={"dirichlet": {"type": "dirichlet"}},
+                        initial_condition={"type": "sine", "amplitude": 1.0, "frequency": 2.0},
+                        exact_solution={"type": "sin_exp_decay", "amplitude": 1.0, "frequency": 2.0}, dimension=1, device=dev,
+                        training=training)
+    heat = pk.HeatEquation(cfgh)
+    torch.manual_seed(2)
+    mh = pk.make_model("fourier", 2, 128, 3, dev, mapping_size=32, scale=10.0)
+    m1 = copy.deepcopy(mh)
+    tcfg = pk.TrainingConfig(learning_rate=1e-3, weight_decay=0.0, gradient_clipping=1.0, scheduler="none",
+                             loss_weights=dict(training["loss_weights"]))
+    tr_sh = pk.PDETrainer(mh, heat, config=tcfg, device=dev, fused=True)
+    nh = 20000
+    xh, th = torch.rand(nh, 1, generator=g).to(dev), torch.rand(nh, 1, generator=g).to(dev)
+    lo, hi = parallel.shard_bounds(nh)
+    l_sh = tr_sh.train_step(xh[lo:hi], th[lo:hi], n_global=nh)
+    # single-process reference of the same step: loss_step_flat on all rows (no collective), then the same optimizer step
+    from pinns_rl_pde_b200 import functional as F
+    comp, wts, flat = F.loss_step_flat(heat, m1, xh, th)
+    tot1 = float(wts[0] * comp[0] + wts[1] * comp[1] + wts[2] * comp[2] + wts[3] * comp[3])
+    dl2 = abs(float(l_sh["total"]) - tot1) / abs(tot1)
+    ds2 = abs(float(l_sh["smoothness"]) - float(comp[3])) / abs(float(comp[3]))
+    ok3 = dl2 < 2e-5 and ds2 < 2e-5 and float(comp[3]) > 0
+    print(f"rank {dist.get_rank()}: sharded Heat + smoothness step: total rel {dl2:.2e}, smoothness rel {ds2:.2e} -> {'OK' if ok3 else 'FAIL'}")
+    ok = ok and ok3
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
