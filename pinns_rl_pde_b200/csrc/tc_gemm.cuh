@@ -1964,6 +1964,9 @@ wgrad_body(const float* __restrict__ G, int ldg, const float* __restrict__ X, in
       named_bar_sync(1, kEpiThreads);
       const int t = threadIdx.x - EPI0 * 32;
       float* const dw0 = dW + (int64_t)o0 * lddw + i0;
+      // columns of this block that exist (lddw = in_dim): a layer narrower than 128 inputs (the 64 Fourier features of fourier.py)
+      // runs as one block whose missing input columns arrive as zeros from the tiled copy and are not written back
+      const int ncol = (lddw - i0 < 128) ? lddw - i0 : 128;
       if (det_part != nullptr) {
         float4* const slab = reinterpret_cast<float4*>(det_part + (int64_t)(cta_y * ncta_x + cta_x) * 16384);
         for (int idx = t; idx < 128 * 32; idx += kEpiThreads)
@@ -1972,6 +1975,7 @@ wgrad_body(const float* __restrict__ G, int ldg, const float* __restrict__ X, in
         // 16-byte vector reductions: a quarter of the atomic operations (all CTAs add into the same 128 x 128 block)
         for (int idx = t; idx < 128 * 32; idx += kEpiThreads) {
           const int row = idx >> 5, c4 = (idx & 31) * 4;
+          if (c4 >= ncol) continue;
           const float4 v = *reinterpret_cast<const float4*>(tr + row * 132 + c4);
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dw0 + (int64_t)row * lddw + c4), "f"(v.x), "f"(v.y),
                        "f"(v.z), "f"(v.w) : "memory");
@@ -1979,7 +1983,7 @@ wgrad_body(const float* __restrict__ G, int ldg, const float* __restrict__ X, in
       } else {
         for (int idx = t; idx < 128 * 128; idx += kEpiThreads) {
           const int row = idx >> 7, col = idx & 127;
-          atomicAdd(dw0 + (int64_t)row * lddw + col, tr[row * 132 + col]);
+          if (col < ncol) atomicAdd(dw0 + (int64_t)row * lddw + col, tr[row * 132 + col]);
         }
       }
     }
@@ -2088,8 +2092,10 @@ static __global__ void wgrad_det_reduce_kernel(const float* __restrict__ part, c
     const float4 v = p[(int64_t)x * 4096];
     ax += (double)v.x; ay += (double)v.y; az += (double)v.z; aw += (double)v.w;
   }
-  float* d = dW + (int64_t)(o0 + row) * lddw + i0 + c4;
-  d[0] += (float)ax; d[1] += (float)ay; d[2] += (float)az; d[3] += (float)aw;
+  if (i0 + c4 < lddw) {                                              // (in_dim is a multiple of 4: whole float4 groups exist or not)
+    float* d = dW + (int64_t)(o0 + row) * lddw + i0 + c4;
+    d[0] += (float)ax; d[1] += (float)ay; d[2] += (float)az; d[3] += (float)aw;
+  }
   if (db != nullptr && i0 == 0 && idx < 128) {
     double b = 0.0;
     for (int x = 0; x < gx; ++x) {
@@ -2113,7 +2119,7 @@ static int launch_wgrad(const float* G, const float* X, float* dW, float* db, in
     configured = true;
   }
   const int64_t ntiles = (M + TK - 1) / TK;
-  const int in_blocks = in_dim / 128, blocks = in_blocks * (out_dim / 128);
+  const int in_blocks = (in_dim + 127) / 128, blocks = in_blocks * (out_dim / 128);
   int gx = sm_count / blocks;
   if (gx < 1) gx = 1;
   if ((int64_t)gx > ntiles) gx = (int)ntiles;
@@ -2480,7 +2486,9 @@ int tc_stage_timers_wgrad(unsigned long long* out16, int reset) {
 // dW[out,in] += dZ[M,out]^T X[M,in] ;  db[out] += sum over value-column rows of dZ
 int tc_linear_wgrad(const float* dZ, const float* X, float* dW, float* db, int64_t M, int in_dim, int out_dim,
                                   int jet_cols, int sm_count, cudaStream_t st, float* det_scratch, int64_t det_floats) {
-  if (M < 1 || (in_dim % 128) != 0 || (out_dim % 128) != 0 || dW == nullptr) return TC_UNSUPPORTED;
+  // in_dim: multiples of 128, or one narrower block (multiple of 4, e.g. the 64 Fourier features feeding the first hidden layer)
+  if (M < 1 || !((in_dim % 128) == 0 || (in_dim < 128 && (in_dim % 4) == 0 && in_dim >= 16)) || (out_dim % 128) != 0 || dW == nullptr)
+    return TC_UNSUPPORTED;
   // PINNK_WGRAD_GLD=1: the G operand straight from global memory into registers instead of through the TMA ring (A/B; read per call)
   { const char* e = getenv("PINNK_WGRAD_GLD");
     if (e && e[0] == '1')

@@ -53,7 +53,8 @@ def test_tc_linear_dgrad_matches_fp64(dev, M, K, N):
 
 
 @pytest.mark.parametrize("M,K,N,C", [(4 * 3001, 128, 128, 4), (5 * 777, 128, 128, 5), (8, 128, 128, 1),
-                                     (4 * 20000, 128, 128, 4), (4 * 1024, 256, 128, 4), (4 * 1024, 128, 256, 4)])
+                                     (4 * 20000, 128, 128, 4), (4 * 1024, 256, 128, 4), (4 * 1024, 128, 256, 4),
+                                     (3 * 5001, 64, 128, 3), (4 * 999, 32, 256, 4)])     # input widths below 128 (Fourier features)
 def test_tc_linear_wgrad_matches_fp64(dev, M, K, N, C):
     from pinns_rl_pde_b200 import _lib
     g = torch.Generator(device="cpu").manual_seed(M + K + 2)
