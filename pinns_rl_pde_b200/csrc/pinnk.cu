@@ -554,7 +554,8 @@ static bool z_elided(const pinnk_plan_t pl, int lin) {
   if (A.in_op != lin || N.op.kind != PINNK_OP_LINEAR || N.in_op != lin + 1) return false;
   int k0 = 0, k1 = 0;
   if (!jet_orders(pl->js, k0, k1) || !tc_jets_supported(k0, k1)) return false;
-  if (L.in_dim != 128 || (L.out_dim % 128) != 0) return false;                    // producer: tc_linear_act_fwd, K = 128
+  // producer: tc_linear_act_fwd in one pass (K = 128, or a narrower first hidden layer such as the Fourier network's K = 64)
+  if (L.in_dim > 128 || L.in_dim < 16 || (L.in_dim % 4) != 0 || (L.out_dim % 128) != 0) return false;
   if (lin + 2 == n_ops - 1)                                                         // consumer: last_act_bwd_fast_kernel
     return pl->fuse_last && (N.op.in_dim % 128) == 0 && first_trainable_op(pl) <= n_ops - 2;
   return (N.op.out_dim == 128 || N.op.out_dim == 256) && (N.op.in_dim % 128) == 0; // consumer: tc_linear_dgrad_actbwd
@@ -621,7 +622,7 @@ static int forward_chunk(const ChunkCtx& c, bool keep_stash = true) {
           if (tc_enabled() && i + 1 < n_ops - 1 && pl->ops[i + 1].op.kind == PINNK_OP_ACT && pl->ops[i + 1].skip_src < 0 &&
               jet_orders(js, k0, k1)) {
             const PinnkOp& a = pl->ops[i + 1].op;
-            const bool want_z = (keep_stash && !z_elided(pl, i)) || o.in_dim != 128;
+            const bool want_z = (keep_stash && !z_elided(pl, i)) || o.in_dim > 128;      // (K = 256: the partial-sum buffer)
             // last hidden layer: fold the output layer nn.Linear(width, 1) into the epilogue (partials in adj(0), which
             // is idle during the forward); forward-only callers then do not store the activation output either
             const bool fuse_out = out_fuse_enabled() && i + 2 == n_ops - 1 && pl->ops[i + 2].op.kind == PINNK_OP_LINEAR &&

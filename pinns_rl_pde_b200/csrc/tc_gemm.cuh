@@ -809,11 +809,14 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
 #pragma unroll
         for (int j = 0; j < 32; ++j) split_bits(W[(int64_t)(c0 + j) * ldw + n0 + f], hi[j], lo[j]);   // lanes contiguous
       } else {
-        // a thread's 32 values are one 128-byte line of its weight row: 8 x LDG.128 (ldw % 4 == 0)
+        // a thread's 32 values are one 128-byte line of its weight row: 8 x LDG.128 (ldw % 4 == 0).  kv: contraction columns
+        // that exist -- a layer with fewer than 128 inputs (the 64 Fourier features of fourier.py) runs with the missing
+        // columns zero here and zero-filled by the tiled copy of its input rows
+        const int kv = (ldx < K) ? ldx : K;
         const float4* wr = reinterpret_cast<const float4*>(W + (int64_t)(n0 + f) * ldw + c0);
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 v = __ldg(wr + j4);
+          const float4 v = (c0 + 4 * j4 < kv) ? __ldg(wr + j4) : make_float4(0.f, 0.f, 0.f, 0.f);
           split_bits(v.x, hi[4 * j4], lo[4 * j4]); split_bits(v.y, hi[4 * j4 + 1], lo[4 * j4 + 1]);
           split_bits(v.z, hi[4 * j4 + 2], lo[4 * j4 + 2]); split_bits(v.w, hi[4 * j4 + 3], lo[4 * j4 + 3]);
         }
@@ -1456,7 +1459,7 @@ static int launch_linear_rows_ts_inst(const float* X, const float* W, int ldw, c
   if (loss) lf = *loss;
   alignas(64) CUtensorMap tmx;
   memset(&tmx, 0, sizeof(tmx));
-  if (ldx != 128 && !make_tmap_rows(&tmx, X, M, 128, ldx, TNE)) return -1;
+  if (ldx != 128 && !make_tmap_rows(&tmx, X, M, ldx < 128 ? ldx : 128, ldx, TNE)) return -1;
   kern<<<grid, threads, smem, st>>>(X, W, ldw, bias, Y, M, n_cols, jet_cols, Zs, Yact, omega, ldx, of, fl, lf, tmx);
   return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
@@ -2343,9 +2346,12 @@ int tc_linear_fwd(const float* X, const float* W, const float* bias, float* Z, i
 int tc_linear_act_fwd(const float* X, const float* W, const float* bias, float* Z, float* Yact, int64_t M, int K,
                                     int N, int k0, int k1, int act, float omega, int sm_count, cudaStream_t st,
                                     const float* w_out, float* u_part, const TcLossFuse* loss, float* ring, int64_t ring_floats) {
-  if (M < 1 || (K != 128 && K != 256) || (N % 128) != 0 || !tc_jets_supported(k0, k1) || (act != 1 && act != 2)) return TC_UNSUPPORTED;
+  // K: 128, 256 (two K halves / K-split), or one narrower block (multiple of 4: the Fourier network's first hidden layer, K = 64)
+  const bool narrow = K < 128 && K >= 16 && (K % 4) == 0;
+  if (M < 1 || (K != 128 && K != 256 && !narrow) || (N % 128) != 0 || !tc_jets_supported(k0, k1) || (act != 1 && act != 2)) return TC_UNSUPPORTED;
   if (Yact == nullptr && w_out == nullptr) return TC_UNSUPPORTED;      // nothing would be produced
   if (loss != nullptr && w_out == nullptr) return TC_UNSUPPORTED;
+  if (narrow && (loss != nullptr)) return TC_UNSUPPORTED;
   if (K == 256 && loss == nullptr && ksplit_enabled(ring)) {
     const int rc = tc_ks_linear_act_fwd(X, W, bias, Z, Yact, M, N, k0, k1, act, omega, sm_count, st, w_out, u_part, ring, ring_floats);
     if (rc != TC_UNSUPPORTED) return rc;
