@@ -121,6 +121,8 @@ FULL = [  # (pde, arch, hidden, layers, dimension, n, extra)  -- BASELINE config
     ("allen_cahn", "feedforward", 128, 8, 1, 3000, {}),
     # the residual network the reference's YAML ships (config.yaml:15-19: hidden_dim 512; fewer blocks to keep the CPU oracle short)
     ("burgers", "resnet", 512, 2, 1, 600, {"num_blocks": 2}),
+    # the Fourier network of the YAML (config.yaml:25-31: mapping_size 512 -> 1024 features, hidden 512, scale 4; fewer layers)
+    ("heat", "fourier", 512, 3, 1, 500, {"mapping_size": 512, "scale": 4.0}),
 ]
 
 
