@@ -41,5 +41,6 @@ def run(name, pde_name, arch, hidden, layers, dim, n, mode, extra, compat="refer
 
 if "c3" in which: run("C3 kdv/resnet 6x256 (loss)", "kdv", "resnet", 256, 6, 1, 1 << 18, "loss", {"num_blocks": 6})
 if "c4" in which: run("C4 ch2d/siren 5x256 math (mse)", "cahn_hilliard", "siren", 256, 5, 2, 1 << 17, "mse", {"omega_0": 30.0}, "math")
+if "c4w" in which: run("C4 ch2d/siren 5x256 as written (mse)", "cahn_hilliard", "siren", 256, 5, 2, 1 << 20, "mse", {"omega_0": 30.0})
 if "c1" in which: run("C1 heat/fourier 4x128 (loss, 1M)", "heat", "fourier", 128, 4, 1, 1 << 20, "loss", {"mapping_size": 32, "scale": 10.0})
 if "c2" in which: run("C2 burgers/ff 8x128 (loss)", "burgers", "feedforward", 128, 8, 1, 1 << 20, "loss", {})
