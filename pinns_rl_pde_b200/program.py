@@ -60,6 +60,8 @@ class NetProgram:
         updates parameters through raw pointers, so version counters cannot be trusted)."""
         for real, shadow, _, _ in self.pad_entries:
             src = real.detach()
+            if shadow.device != src.device or shadow.dtype != src.dtype:      # the model was moved after the program was compiled
+                shadow.data = torch.zeros(shadow.shape, dtype=src.dtype, device=src.device)
             if src.dim() == 2:
                 shadow[:src.shape[0], :src.shape[1]].copy_(src)
             else:

@@ -51,3 +51,16 @@ def test_widths_that_stay_unpadded(monkeypatch):
     assert program.compile_network(pk.make_model("feedforward", 2, 248, 3, dev)).padded
     monkeypatch.setenv("PINNK_DISABLE_PAD", "1")
     assert not program.compile_network(pk.make_model("feedforward", 2, 248, 3, dev)).padded
+
+
+def test_shadows_follow_the_model_to_another_device_or_dtype():
+    import pinns_rl_pde_b200 as pk
+    from pinns_rl_pde_b200 import program
+    m = pk.make_model("siren", 2, 124, 3, torch.device("cpu"), omega_0=30.0)
+    pr = program.compile_network(m)
+    m.double()                                  # same Parameter objects, new storage (what model.to(device) does as well)
+    pr.refresh_shadows()
+    for real, sh, _, _ in pr.pad_entries:
+        assert sh.dtype == real.dtype and sh.device == real.device
+        blk = sh[:real.shape[0], :real.shape[1]] if real.dim() == 2 else sh[:real.shape[0]]
+        assert torch.equal(blk, real.detach())
