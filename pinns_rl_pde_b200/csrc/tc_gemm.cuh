@@ -1250,7 +1250,18 @@ linear_rows_ts_body(const float* __restrict__ X, const float* __restrict__ W, in
                 float u[kMaxCols], du[kMaxCols];
 #pragma unroll
                 for (int c = 0; c < JC; ++c) u[c] = __shfl_sync(0xffffffffu, Uv, pl_ * JC + c);
-                const float e = pde_residual<float>(lf.pde, lf.js, u, du);
+                // column layout of this instantiation, [u | K0 columns of direction 0 | K1 columns of direction 1], as compile-time
+                // constants (the launcher checks lf.js against it): with the run-time JetSpec the residual's U[js.col0[..]] /
+                // dU[..] accesses were dynamically indexed, which put u[] and du[] in LOCAL memory -- 15 local loads / stores per
+                // warp and tile, 2.7 GB of L2 traffic per 4 Mi-row launch next to the kernel's 4.3 GB (ncu, r02_full_lossf_raw.csv)
+                JetSpec jsl;
+                jsl.ncols = JC;
+                jsl.ndirs = (K1 > 0) ? 2 : 1;
+                jsl.col0[0] = 1;
+                jsl.col0[1] = 1 + K0;
+#pragma unroll
+                for (int d = 2; d < kMaxDirs; ++d) jsl.col0[d] = 1;     // (five-direction operators never come here: the launcher declines)
+                const float e = pde_residual<float>(lf.pde, jsl, u, du);
                 float drho;
                 const float rho = loss_rho<float>(lf.loss_kind, lf.huber_delta, e, &drho);
                 const bool live = lane < ECE && (FULL || lane < nrows);
@@ -1456,7 +1467,13 @@ static int launch_linear_rows_ts_inst(const float* X, const float* W, int ldw, c
   }
   TcLossFuse lf;
   memset(&lf, 0, sizeof(lf));
-  if (loss) lf = *loss;
+  if (loss) {
+    lf = *loss;
+    // the kernel's residual uses the compile-time column layout [u | K0 | K1]
+    const bool two = K1 > 0;
+    if (lf.js.ncols != 1 + K0 + K1 || lf.js.ndirs != (two ? 2 : 1) || lf.js.col0[0] != 1 || (two && lf.js.col0[1] != 1 + K0))
+      return TC_UNSUPPORTED;
+  }
   alignas(64) CUtensorMap tmx;
   memset(&tmx, 0, sizeof(tmx));
   if (ldx != 128 && !make_tmap_rows(&tmx, X, M, ldx < 128 ? ldx : 128, ldx, TNE)) return -1;
