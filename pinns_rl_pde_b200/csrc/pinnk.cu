@@ -26,6 +26,7 @@
 #include "kernels_sample.cuh"
 #include "sgemm.cuh"
 #include "tc_api.h"
+#include "lnact_api.h"
 
 using namespace pinnk;
 
@@ -422,15 +423,34 @@ static int ln_bwd(const ChunkCtx& c, const float* Z, const float* Gin, float* Go
 // per point and 8 features per lane the activation recurrences of a point run serially at 8 - 16 warps per SM, and the pair
 // costs more than the two bandwidth-bound kernels it replaces (C3, 262 144 points: forward 22.2 ms vs 6.8 + 9.5, reverse
 // 75.9 ms vs 16.8 + 10.7; profiles/r02r_c3_lnact.log).  The separate kernels already run at 4.3 - 5.7 TB/s.
-static int lnact_partner(const pinnk_plan_t pl, int ln) {
+//
+// Round 2, last: the feature-per-thread kernels of lnact_feat.cu (a block per point, two features per thread, all
+// cross-feature sums of a phase in one block reduction) ARE the default where they apply -- tanh, width 128 / 256 / 512, the
+// two-direction jet layouts of the 1-D PDEs.  PINNK_ENABLE_LNACT=0: always the separate kernels; =1: the warp-per-point pair
+// above for every LayerNorm -> activation pair (comparison runs); unset: lnact_feat.cu where it applies, separate kernels else.
+static int lnact_mode() {
   const char* e = getenv("PINNK_ENABLE_LNACT");
-  if (!(e && e[0] == '1')) return -1;
+  if (!e || !e[0]) return 2;
+  return e[0] == '1' ? 1 : (e[0] == '0' ? 0 : 2);
+}
+static bool jet_orders(const JetSpec& js, int& k0, int& k1);
+static bool lnact_feat_ok(const pinnk_plan_t pl, int width, int act) {
+  int k0 = 0, k1 = 0;
+  if (act != PINNK_ACT_TANH || !jet_orders(pl->js, k0, k1)) return false;
+  const JetSpec& js = pl->js;
+  if (js.ndirs < 1 || js.ncols != 1 + k0 + k1 || js.col0[0] != 1 || (js.ndirs > 1 && js.col0[1] != 1 + k0)) return false;
+  return lnact_feat_supported(width, k0, k1);
+}
+static int lnact_partner(const pinnk_plan_t pl, int ln) {
+  const int mode = lnact_mode();
+  if (mode == 0) return -1;
   const int n_ops = (int)pl->ops.size();
-  if (ln < 1 || ln >= n_ops - 1 || pl->ops[ln].op.kind != PINNK_OP_LAYERNORM || pl->ops[ln].op.in_dim > 256) return -1;
+  if (ln < 1 || ln >= n_ops - 1 || pl->ops[ln].op.kind != PINNK_OP_LAYERNORM) return -1;
   int j = ln + 1;
   if (j < n_ops - 1 && pl->ops[j].op.kind == PINNK_OP_SKIP_ADD) ++j;
   if (j >= n_ops - 1 || pl->ops[j].op.kind != PINNK_OP_ACT || pl->ops[j].in_op != ln) return -1;
-  return j;
+  if (mode == 1) return pl->ops[ln].op.in_dim <= 256 ? j : -1;
+  return lnact_feat_ok(pl, pl->ops[ln].op.in_dim, pl->ops[j].op.act) ? j : -1;
 }
 static int lnact_of_act(const pinnk_plan_t pl, int act) {
   if (act < 1 || pl->ops[act].op.kind != PINNK_OP_ACT) return -1;
@@ -442,6 +462,13 @@ template <int MAXK>
 static int lnact_fwd(const ChunkCtx& c, const float* Z, const float* S, float* Y, int width, const float* g, const float* b,
                      float eps, int act, float omega) {
   ProfScope ps(PC_LN_FWD, c.st);
+  if (lnact_mode() == 2 && lnact_feat_ok(c.pl, width, act)) {
+    int k0 = 0, k1 = 0;
+    jet_orders(c.pl->js, k0, k1);
+    const int rc = lnact_feat_fwd(Z, S, Y, c.n, width, k0, k1, g, b, eps, c.pl->sm_count, c.st);
+    if (rc == 0) return 0;
+    return fail(PINNK_E_CUDA, "lnact_feat_fwd launch failed");
+  }
   const int threads = 256;
   const unsigned blocks = blocks_for(c.n * 32, threads);
   const int nper = (width + 31) / 32;
@@ -459,6 +486,13 @@ static int lnact_bwd(const ChunkCtx& c, const float* Z, const float* S, const fl
                      float* Gout, int width, const float* g, const float* b, float eps, int act, float omega, float* dg,
                      float* db) {
   ProfScope ps(PC_LN_BWD, c.st);
+  if (lnact_mode() == 2 && lnact_feat_ok(c.pl, width, act)) {
+    int k0 = 0, k1 = 0;
+    jet_orders(c.pl->js, k0, k1);
+    const int rc = lnact_feat_bwd(Z, S, Gin, Gin2, Gz, Gout, c.n, width, k0, k1, g, b, eps, dg, db, c.pl->sm_count, c.st);
+    if (rc == 0) return 0;
+    return fail(PINNK_E_CUDA, "lnact_feat_bwd launch failed");
+  }
   const int threads = 128;
   const int wpb = threads / 32;
   int64_t blocks = (c.n + wpb - 1) / wpb;

@@ -1,8 +1,9 @@
-"""GPU: LayerNorm + activation as one kernel each way (lnact_fwd_kernel / lnact_bwd_kernel, resnet.py:45-65; opt-in with
-PINNK_ENABLE_LNACT=1 because it measured slower) against the separate LayerNorm and activation kernels of the same library
-on identical seeded inputs.  The switch is read per call, so both routes run in one process.  The default route of residual
-networks (skip adjoint kept in place, deferred add inside the activation adjoint) is covered against the oracle by
-test_gpu_parity.py's ResNet cases."""
+"""GPU: LayerNorm + activation as one kernel each way (resnet.py:45-65) against the separate LayerNorm and activation kernels of the
+same library on identical seeded inputs.  Two fused routes: the feature-per-thread kernels of lnact_feat.cu (the default where they
+apply: tanh, width 128 / 256 / 512, two-direction jets) and the warp-per-point pair lnact_fwd_kernel / lnact_bwd_kernel
+(PINNK_ENABLE_LNACT=1, measured slower, kept for comparison); PINNK_ENABLE_LNACT=0 selects the separate kernels.  The switch is
+read per call, so all routes run in one process.  Both routes are also covered against the oracle by test_gpu_parity.py's ResNet
+cases (default route) ."""
 import numpy as np
 import pytest
 import torch
@@ -28,8 +29,11 @@ def _step(pde, model, x, t):
             pde.compute_residual(model, x, t).detach().clone(), pde.score_residual(model, x, t)[0].clone())
 
 
-@pytest.mark.parametrize("pde_name,width,blocks,n", [("kdv", 256, 2, 3000), ("burgers", 128, 3, 2500), ("cahn_hilliard", 256, 1, 1100)])
-def test_fused_layernorm_activation_matches_separate_kernels(monkeypatch, pde_name, width, blocks, n):
+@pytest.mark.parametrize("route", ["feat", "warp"])
+@pytest.mark.parametrize("pde_name,width,blocks,n", [("kdv", 256, 2, 3000), ("burgers", 128, 3, 2500), ("cahn_hilliard", 256, 1, 1100),
+                                                     ("heat", 512, 1, 700), ("wave", 256, 1, 900), ("convection", 128, 2, 1300),
+                                                     ("pendulum", 128, 1, 600)])
+def test_fused_layernorm_activation_matches_separate_kernels(monkeypatch, pde_name, width, blocks, n, route):
     import pinns_rl_pde_b200 as pk
     dev = torch.device("cuda:0")
     torch.manual_seed(3)
@@ -45,11 +49,16 @@ def test_fused_layernorm_activation_matches_separate_kernels(monkeypatch, pde_na
     x = (lo + (hi - lo) * torch.rand(n, 1, generator=g)).to(dev)
     t = (pde.time_domain[0] + (pde.time_domain[1] - pde.time_domain[0]) * torch.rand(n, 1, generator=g)).to(dev)
     from pinns_rl_pde_b200 import _lib
-    monkeypatch.setenv("PINNK_ENABLE_LNACT", "1")
+    if route == "warp":
+        if width > 256:
+            pytest.skip("the warp-per-point pair covers widths up to 256")
+        monkeypatch.setenv("PINNK_ENABLE_LNACT", "1")
+    else:
+        monkeypatch.delenv("PINNK_ENABLE_LNACT", raising=False)
     before = _lib.launch_count()
     fused = _step(pde, model, x, t)
     n_fused = _lib.launch_count() - before
-    monkeypatch.delenv("PINNK_ENABLE_LNACT")
+    monkeypatch.setenv("PINNK_ENABLE_LNACT", "0")
     before = _lib.launch_count()
     plain = _step(pde, model, x, t)
     n_plain = _lib.launch_count() - before
@@ -57,7 +66,7 @@ def test_fused_layernorm_activation_matches_separate_kernels(monkeypatch, pde_na
     for k in fused[0]:
         assert abs(fused[0][k] - plain[0][k]) <= 2e-6 * abs(plain[0][k]) + 1e-12, (k, fused[0][k], plain[0][k])
     eg, er, es = _rel(fused[1], plain[1]), _rel(fused[2], plain[2]), _rel(fused[3], plain[3])
-    parity_log.log(f"[lnact {pde_name} resnet {blocks}x{width}] fused vs separate kernels: grad {eg:.2e}, residual {er:.2e}, "
+    parity_log.log(f"[lnact {route} {pde_name} resnet {blocks}x{width}] fused vs separate kernels: grad {eg:.2e}, residual {er:.2e}, "
                    f"|r| scores {es:.2e}; launches {n_fused} vs {n_plain}")
     assert eg <= 3e-6 and er <= 3e-6 and es <= 3e-6, (eg, er, es)
     assert np.isfinite(fused[1].cpu().numpy()).all()
