@@ -200,8 +200,11 @@ lnact_feat_fwd_kernel(const float* __restrict__ Z, const float* __restrict__ S, 
   }
 }
 
+#ifndef PINNK_LNF_BWD_THREADS_PER_SM
+#define PINNK_LNF_BWD_THREADS_PER_SM 1024
+#endif
 template <int K0, int K1, int NW>
-__global__ void __launch_bounds__(NW * 32)
+__global__ void __launch_bounds__(NW * 32, PINNK_LNF_BWD_THREADS_PER_SM / (NW * 32))
 lnact_feat_bwd_kernel(const float* __restrict__ Z, const float* __restrict__ S, const float* Gin, const float* __restrict__ Gin2,
                       float* Gz, float* __restrict__ Gout, int64_t n, const float* __restrict__ gamma,
                       const float* __restrict__ beta, float eps, float* __restrict__ dgamma, float* __restrict__ dbeta) {
