@@ -130,8 +130,9 @@ lnact_feat_fwd_kernel(const float* __restrict__ Z, const float* __restrict__ S, 
   constexpr int C = 1 + K0 + K1, W2 = NW * 32, MAXK = Jets<K0, K1>::MAXK;
   __shared__ float part[2][8 * NW];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float2 g = __ldg(reinterpret_cast<const float2*>(gamma) + tid);
-  const float2 bt = __ldg(reinterpret_cast<const float2*>(beta) + tid);
+  // (scalar loads: a parameter tensor may be a view at any 4-byte offset of a caller's flat buffer)
+  const float2 g = make_float2(__ldg(gamma + 2 * tid), __ldg(gamma + 2 * tid + 1));
+  const float2 bt = make_float2(__ldg(beta + 2 * tid), __ldg(beta + 2 * tid + 1));
   const float inv_w = 1.f / (float)(2 * W2);
   for (int64_t p = blockIdx.x; p < n; p += gridDim.x) {
     const int64_t o = p * (int64_t)(C * W2) + tid;
@@ -214,8 +215,9 @@ lnact_feat_bwd_kernel(const float* __restrict__ Z, const float* __restrict__ S, 
   static_assert(NV3 <= 16, "sums of the third round");
   __shared__ float part[2][16 * NW];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float2 g = __ldg(reinterpret_cast<const float2*>(gamma) + tid);
-  const float2 bt = __ldg(reinterpret_cast<const float2*>(beta) + tid);
+  // (scalar loads: a parameter tensor may be a view at any 4-byte offset of a caller's flat buffer)
+  const float2 g = make_float2(__ldg(gamma + 2 * tid), __ldg(gamma + 2 * tid + 1));
+  const float2 bt = make_float2(__ldg(beta + 2 * tid), __ldg(beta + 2 * tid + 1));
   const float inv_w = 1.f / (float)(2 * W2);
   float2 dg = make_float2(0.f, 0.f), db = make_float2(0.f, 0.f);
   int tog = 0;                   // three rounds per point: the two buffers keep alternating across points
@@ -483,6 +485,7 @@ bool lnact_feat_supported(int width, int k0, int k1) {
 int lnact_feat_fwd(const float* Z, const float* S, float* Y, int64_t n, int width, int k0, int k1, const float* gamma,
                    const float* beta, float eps, int sm_count, cudaStream_t st) {
   if (n < 1 || !lnact_feat_supported(width, k0, k1)) return 1;
+  if (((reinterpret_cast<uintptr_t>(Z) | reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(Y)) & 7) != 0) return -1;   // float2 rows
   int rc = -1;
   dispatch_jets(k0, k1, [&](auto a, auto b) {
     constexpr int A = decltype(a)::value, B = decltype(b)::value;
@@ -497,6 +500,8 @@ int lnact_feat_bwd(const float* Z, const float* S, const float* Gin, const float
                    int width, int k0, int k1, const float* gamma, const float* beta, float eps, float* dgamma, float* dbeta,
                    int sm_count, cudaStream_t st) {
   if (n < 1 || !lnact_feat_supported(width, k0, k1)) return 1;
+  if (((reinterpret_cast<uintptr_t>(Z) | reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(Gin) | reinterpret_cast<uintptr_t>(Gin2) |
+        reinterpret_cast<uintptr_t>(Gz) | reinterpret_cast<uintptr_t>(Gout)) & 7) != 0) return -1;                                    // float2 rows
   int rc = -1;
   dispatch_jets(k0, k1, [&](auto a, auto b) {
     constexpr int A = decltype(a)::value, B = decltype(b)::value;
