@@ -105,21 +105,38 @@ __global__ void act_fwd_kernel(const float* __restrict__ Z, const float* __restr
     sincosf(z[0], &y[0], &w[0]);
   }
   Y[base] = y[0];
-  for (int d = 0; d < js.ndirs; ++d) {
-    const int K = js.order[d];
-    const int64_t b1 = base + (int64_t)js.col0[d] * width;
+  // Every jet column of the element is requested before the first one is used: with the loads of a direction issued only when
+  // the previous direction had been stored, a thread had at most MAXK requests in flight and the kernel ran latency-bound
+  // (C4, 18 columns: 3.6 TB/s at 95 % occupancy with long-scoreboard stalls on top, profiles/r02_final.md).  The direction loop is
+  // unrolled over kMaxDirs so that zin[][] stays in registers.
+  float zin[kMaxDirs][MAXK];
 #pragma unroll
-    for (int k = 1; k <= MAXK; ++k)
-      if (k <= K) {
-        const int64_t o = b1 + (int64_t)(k - 1) * width;
-        z[k] = Z[o] + (S ? S[o] : 0.f);
-        if (ACT == 2) z[k] *= omega;
-      }
-    if (ACT == 1) tanh_dir_fwd<MAXK, float>(K, z, y, w);
-    else sincos_dir_fwd<MAXK, float>(K, z, y, w);
+  for (int d = 0; d < kMaxDirs; ++d) {
+    if (d < js.ndirs) {
+      const int K = js.order[d];
+      const int64_t b1 = base + (int64_t)js.col0[d] * width;
 #pragma unroll
-    for (int k = 1; k <= MAXK; ++k)
-      if (k <= K) Y[b1 + (int64_t)(k - 1) * width] = y[k];
+      for (int k = 1; k <= MAXK; ++k)
+        if (k <= K) {
+          const int64_t o = b1 + (int64_t)(k - 1) * width;
+          zin[d][k - 1] = Z[o] + (S ? S[o] : 0.f);
+        }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < kMaxDirs; ++d) {
+    if (d < js.ndirs) {
+      const int K = js.order[d];
+      const int64_t b1 = base + (int64_t)js.col0[d] * width;
+#pragma unroll
+      for (int k = 1; k <= MAXK; ++k)
+        if (k <= K) z[k] = (ACT == 2) ? zin[d][k - 1] * omega : zin[d][k - 1];
+      if (ACT == 1) tanh_dir_fwd<MAXK, float>(K, z, y, w);
+      else sincos_dir_fwd<MAXK, float>(K, z, y, w);
+#pragma unroll
+      for (int k = 1; k <= MAXK; ++k)
+        if (k <= K) Y[b1 + (int64_t)(k - 1) * width] = y[k];
+    }
   }
 }
 
