@@ -70,3 +70,33 @@ def test_fused_layernorm_activation_matches_separate_kernels(monkeypatch, pde_na
                    f"|r| scores {es:.2e}; launches {n_fused} vs {n_plain}")
     assert eg <= 3e-6 and er <= 3e-6 and es <= 3e-6, (eg, er, es)
     assert np.isfinite(fused[1].cpu().numpy()).all()
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_fused_trainer_on_a_residual_network_follows_the_autograd_route(graph):
+    """The fused trainer step (pinnk_loss_step_flags with its KEEP / REUSE stash flows, optionally replayed as a CUDA graph) on a
+    residual network -- LayerNorm + tanh through lnact_feat.cu -- against compute_loss + backward + clip + Adam on a copy."""
+    import copy
+    import pinns_rl_pde_b200 as pk
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    m1 = pk.make_model("resnet", 2, 256, 2, dev)
+    m2 = copy.deepcopy(m1)
+    pde = product_pde("kdv", dev)
+    cfg = pk.TrainingConfig(learning_rate=1e-3, weight_decay=1e-4, gradient_clipping=1.0, scheduler="none")
+    pde.config.training = cfg
+    t1 = pk.PDETrainer(m1, pde, config=cfg, device=dev, fused=True, graph=graph)
+    t2 = pk.PDETrainer(m2, pde, config=cfg, device=dev, fused=False)
+    g = torch.Generator().manual_seed(3)
+    lo, hi = pde.domain[0]
+    t_lo, t_hi = pde.time_domain
+    for it in range(10):
+        x = (lo + (hi - lo) * torch.rand(1536, 1, generator=g)).to(dev)
+        t = (t_lo + (t_hi - t_lo) * torch.rand(1536, 1, generator=g)).to(dev)
+        l1, l2 = t1.train_step(x, t), t2.train_step(x, t)
+        assert abs(float(l1["total"]) - float(l2["total"])) <= 5e-5 * abs(float(l2["total"])), (it, float(l1["total"]), float(l2["total"]))
+    p1 = torch.cat([p.detach().reshape(-1) for p in m1.parameters()])
+    p2 = torch.cat([p.detach().reshape(-1) for p in m2.parameters()])
+    e = _rel(p1, p2)
+    parity_log.log(f"[lnact trainer kdv resnet 2x256, graph={graph}] 10 fused steps vs autograd route: parameters {e:.3e}")
+    assert e <= 1e-4
