@@ -10,7 +10,8 @@ boundary + 100 initial rows) -> backward -> [all-reduce of the flat gradient whe
 
 `value`   device-timed steps with the collocation rows resident in HBM;
 `e2e`     the same step through the public API from pinned HOST buffers (H2D of the rows and D2H of the
-          loss inside the timed region);
+          loss inside the timed region, every step; pipelined like a loader: the next step's rows are copied on a side
+          stream while this step computes, and this step's loss is read on the host during the next step);
 `roofline`     dominant kernel class timed with CUDA event pairs inside libpinnk (profiling pass); the whole step against
                BOTH tensor denominators (TF32 measured in this run / 3, and MEASURED_PEAKS bf16_sustained / 6);
 `cpu_baseline` the UNMODIFIED reference (pinnrl, installed to baseline/_ref; kind "reference") on the host cores -- the
@@ -489,15 +490,46 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # end to end: pinned host rows -> device -> step -> loss back on the host, every step
-    xd, td = torch.empty_like(x), torch.empty_like(t)
+    # end to end: pinned host rows -> device -> step -> loss back on the host, every step.  Pipelined the way a training loop's
+    # loader is: the rows of step i + 1 are copied on a side stream while step i computes (two device buffers), and the loss of
+    # step i goes to pinned host memory behind the step and is read by the host during step i + 1 -- so every step still has its
+    # own H2D copy of its rows and its own D2H read inside the timed region, but neither drains the launch queue.
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [(torch.empty_like(x), torch.empty_like(t)) for _ in range(2)]
+    loss_probe = step(x, t).detach().reshape(1)
+    loss_h = [torch.empty(1, dtype=loss_probe.dtype).pin_memory() for _ in range(2)]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    ev_loss = [torch.cuda.Event() for _ in range(2)]
+    e2e_state = {"i": 0, "loss": None}
+
+    def e2e_prefetch(j):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_free[j])          # the step that last read this pair of buffers has finished
+            bufs[j][0].copy_(xh, non_blocking=True)
+            bufs[j][1].copy_(th, non_blocking=True)
+            ev_in[j].record(copy_stream)
 
     def e2e_step():
-        xd.copy_(xh, non_blocking=True)
-        td.copy_(th, non_blocking=True)
-        return float(step(xd, td).item())
+        i = e2e_state["i"]
+        j = i & 1
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev_in[j])
+        loss = step(bufs[j][0], bufs[j][1])
+        ev_free[j].record(cur)
+        loss_h[j].copy_(loss.detach().reshape(1), non_blocking=True)
+        ev_loss[j].record(cur)
+        e2e_prefetch(j ^ 1)
+        if i > 0:
+            ev_loss[j ^ 1].synchronize()
+            e2e_state["loss"] = float(loss_h[j ^ 1][0])
+        e2e_state["i"] = i + 1
+    e2e_prefetch(0)
+    e2e_step()
     e2e_step()
     ms_e2e, _ = timed(e2e_step, args.steps)
+    if not math.isfinite(e2e_state["loss"]):
+        raise SystemExit("end-to-end arm: the loss read back on the host is not finite")
 
     # roofline: profiling pass (event pairs around every libpinnk kernel class)
     roof = None
@@ -594,7 +626,7 @@ def run_ours(args):
     configs = None
     if not args.no_configs:
         from pinns_rl_pde_b200 import engine as _engine
-        del trainer, model, pde, x, t, xd, td
+        del trainer, model, pde, x, t, bufs
         _engine._CACHE.clear() if hasattr(_engine._CACHE, "clear") else None
         torch.cuda.empty_cache()
         configs = []
@@ -612,7 +644,10 @@ def run_ours(args):
                 "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": workload_config(args, world), "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": int(loss_h[0].element_size()),
+                        "pipelining": "rows of step i+1 copied on a side stream during step i; loss of step i read on the host "
+                                      "during step i+1"},
                 "gpu_launches": int(launches), "roofline": roof}
         if per_rank is not None:
             line["per_rank_step_ms"], line["collective_ms"] = per_rank
