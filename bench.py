@@ -524,10 +524,20 @@ def run_ours(args):
             ev_loss[j ^ 1].synchronize()
             e2e_state["loss"] = float(loss_h[j ^ 1][0])
         e2e_state["i"] = i + 1
-    e2e_prefetch(0)
-    e2e_step()
-    e2e_step()
-    ms_e2e, _ = timed(e2e_step, args.steps)
+    e2e_serial = os.environ.get("PINNK_BENCH_E2E_SERIAL", "0") == "1"      # A/B: copy, step and loss.item() back to back
+
+    def e2e_step_serial():
+        bufs[0][0].copy_(xh, non_blocking=True)
+        bufs[0][1].copy_(th, non_blocking=True)
+        e2e_state["loss"] = float(step(bufs[0][0], bufs[0][1]).item())
+    if e2e_serial:
+        e2e_step_serial()
+        ms_e2e, _ = timed(e2e_step_serial, args.steps)
+    else:
+        e2e_prefetch(0)
+        e2e_step()
+        e2e_step()
+        ms_e2e, _ = timed(e2e_step, args.steps)
     if not math.isfinite(e2e_state["loss"]):
         raise SystemExit("end-to-end arm: the loss read back on the host is not finite")
 
@@ -646,7 +656,8 @@ def run_ours(args):
                 "config": workload_config(args, world), "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "points/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": int(loss_h[0].element_size()),
-                        "pipelining": "rows of step i+1 copied on a side stream during step i; loss of step i read on the host "
+                        "pipelining": "none (PINNK_BENCH_E2E_SERIAL=1)" if e2e_serial else
+                                      "rows of step i+1 copied on a side stream during step i; loss of step i read on the host "
                                       "during step i+1"},
                 "gpu_launches": int(launches), "roofline": roof}
         if per_rank is not None:
